@@ -1,0 +1,227 @@
+/*
+ * ncf_b200.h - C ABI of libncf_b200.so: the B200 (sm_100a) implementation of the AdvancedNCF
+ * training + scoring hot path of ethanshenley/Neural-Collaborative-Filtering-Demo.
+ *
+ * The reference has no FFI: the path sits behind a PyTorch nn.Module (reference
+ * src/model/architecture.py:121 `AdvancedNCF`).  This header is the boundary a maintainer binds
+ * with ctypes from that module; every entry point cites the reference
+ * code it replaces (paths relative to the reference repository root).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is DEVICE memory unless named host_*;
+ *   - the library never allocates or frees device memory: scratch is a caller-provided
+ *     workspace sized by the *_workspace_bytes queries;
+ *   - every launch goes on the `stream` argument (a cudaStream_t passed as void*); no hidden
+ *     synchronisation, so calls are CUDA-graph capturable;
+ *   - return value: 0 on success, negative ncf_status on error (message: ncf_last_error());
+ *     no C++ exception crosses the boundary;
+ *   - model geometry is the reference's configuration (config/config.yaml:53-69):
+ *     embedding dim 64 (both towers), MLP 96->256->128->64, 4 heads x 16, temporal dim 32.
+ *   - ids are int64 (the KeyedJaggedTensor `values` dtype, data_prep.py:286-298); a sample row
+ *     n uses user_ids[n] and item_ids[n]; rows b*S .. b*S+S-1 form one interaction group.
+ */
+#ifndef NCF_B200_H
+#define NCF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NCF_ABI_VERSION 1
+#if defined(__GNUC__)
+#define NCF_API __attribute__((visibility("default")))
+#else
+#define NCF_API
+#endif
+#define NCF_D 64          /* embedding dim of all four tables */
+#define NCF_H1 256
+#define NCF_H2 128
+#define NCF_H3 64
+#define NCF_HEADS 4
+#define NCF_TDIM 32       /* temporal_dim */
+#define NCF_MAX_S 8       /* 1 + negative_samples supported by the attention kernels */
+
+typedef enum ncf_status {
+  NCF_OK = 0,
+  NCF_ERR_ARG = -1,        /* bad argument (null pointer, size, alignment, unsupported S) */
+  NCF_ERR_WORKSPACE = -2,  /* workspace too small */
+  NCF_ERR_CUDA = -3,       /* a CUDA runtime call or launch failed */
+  NCF_ERR_UNSUPPORTED = -4
+} ncf_status;
+
+/* Table order used everywhere: the four EmbeddingBagCollection tables of
+ * architecture.py:153-190 (SUM-pooled bags of length 1 == row gather). */
+enum { NCF_T_USER_MF = 0, NCF_T_ITEM_MF = 1, NCF_T_USER_MLP = 2, NCF_T_ITEM_MLP = 3 };
+
+typedef struct ncf_tables {
+  float* w[4];            /* fp32 [rows, 64] row-major, 16-byte aligned */
+  float* m[4];            /* Adam first moment  (may be NULL when no table update is requested) */
+  float* v[4];            /* Adam second moment */
+  float* g[4];            /* dense gradient [rows,64], only for NCF_EMB_MATERIALIZE (caller zeroes) */
+  uint8_t* touched[2];    /* [rows_user], [rows_item] scratch flags, zero between steps */
+  int64_t rows_user;
+  int64_t rows_item;
+} ncf_tables;
+
+/* Offsets (in floats) of the 30 dense tensors `forward` uses inside ONE flat fp32 buffer
+ * (83,909 values padded to 16-byte boundaries).  Names are the reference state_dict keys
+ * (SURVEY Appendix C).  ncf_dense_offset(id) returns the offset, ncf_dense_numel() the length. */
+typedef enum ncf_dense_id {
+  NCF_P_MF_NORM_W = 0, NCF_P_MF_NORM_B, NCF_P_MLP_NORM_W, NCF_P_MLP_NORM_B,
+  NCF_P_Q_W, NCF_P_K_W, NCF_P_V_W, NCF_P_O_W,   /* k_proj and v_proj adjacent: one [128,64] GEMM */
+  NCF_P_Q_B, NCF_P_K_B, NCF_P_V_B, NCF_P_O_B,
+  NCF_P_MLP0_W, NCF_P_MLP0_B, NCF_P_LN0_W, NCF_P_LN0_B,
+  NCF_P_MLP1_W, NCF_P_MLP1_B, NCF_P_LN1_W, NCF_P_LN1_B,
+  NCF_P_MLP2_W, NCF_P_MLP2_B, NCF_P_LN2_W, NCF_P_LN2_B,
+  NCF_P_MF_OUT_W, NCF_P_MF_OUT_B, NCF_P_MLP_OUT_W, NCF_P_MLP_OUT_B,
+  NCF_P_FINAL_W, NCF_P_FINAL_B,
+  NCF_P_COUNT
+} ncf_dense_id;
+
+typedef enum ncf_precision {
+  NCF_FP32 = 0,      /* CUDA-core fp32 towers: <=1e-5 relative vs the reference (BASELINE config 1) */
+  NCF_BF16_TC = 1    /* tcgen05 bf16 towers, fp32 accumulate (BASELINE config 2) */
+} ncf_precision;
+
+typedef struct ncf_run_cfg {
+  int32_t S;              /* rows per interaction group: 1+negative_samples in train, 1 in eval
+                             (architecture.py:275) */
+  int32_t training;       /* nn.Module.training */
+  int32_t precision;      /* ncf_precision */
+  float dropout_p;        /* architecture.py:51, 238 (train only) */
+  uint64_t seed;          /* Philox key of the in-kernel dropout */
+  uint64_t step;          /* Philox stream offset: one value per forward call */
+} ncf_run_cfg;
+
+typedef enum ncf_emb_mode {
+  NCF_EMB_NONE = 0,         /* no table gradient (tables frozen) */
+  NCF_EMB_MATERIALIZE = 1,  /* write the dense table gradient into tables->g (reference layout:
+                               aten::_embedding_bag_dense_backward, trainer.py:276) */
+  NCF_EMB_ADAM_SPARSE = 2,  /* fused scatter+Adam on touched rows only */
+  NCF_EMB_ADAM_DENSE_EQUIV = 3 /* touched rows as above, then every untouched row gets the
+                               reference's g = wd*w Adam step (trainer.py:71-75, 285) */
+} ncf_emb_mode;
+
+typedef struct ncf_adam_cfg {
+  float lr, beta1, beta2, eps, weight_decay;
+  int32_t step;             /* 1-based optimizer step (bias correction) */
+  int32_t emb_mode;         /* ncf_emb_mode */
+} ncf_adam_cfg;
+
+/* ---- library ------------------------------------------------------------------------- */
+NCF_API int ncf_version(void);
+NCF_API const char* ncf_last_error(void);
+NCF_API int64_t ncf_dense_numel(void);
+NCF_API int64_t ncf_dense_offset(int32_t dense_id);
+NCF_API int64_t ncf_dense_size(int32_t dense_id);
+
+/* ---- forward ---------------------------------------------------------------------------
+ * AdvancedNCF.forward (architecture.py:258-381) and forward_simple (:409-485).
+ * hour == NULL: the temporal columns are zeros (:329-340).  hour != NULL: forward_simple's
+ * hour path; tmod [24,64] and tail1 [24,256] come from ncf_temporal_tables.
+ * out: probabilities [N].  The workspace keeps the activations ncf_backward needs. */
+NCF_API int64_t ncf_workspace_bytes(int64_t N, const ncf_run_cfg* cfg);
+NCF_API int ncf_forward(const ncf_run_cfg* cfg, const ncf_tables* tables, const float* dense,
+                const int64_t* user_ids, const int64_t* item_ids, int64_t N,
+                const int64_t* hour, const float* tmod, const float* tail1,
+                float* out, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* loss.backward() of trainer.py:276 for `out` produced by ncf_forward with the same workspace:
+ * grad_out = dL/d out [N].  Accumulates (+=) into dense_grad (flat layout above) and handles the
+ * four tables according to adam->emb_mode (the fused sorted-id scatter + Adam, or the dense
+ * gradient the reference materialises). */
+NCF_API int ncf_backward(const ncf_run_cfg* cfg, const ncf_adam_cfg* adam, const ncf_tables* tables,
+                 const float* dense, float* dense_grad,
+                 const int64_t* user_ids, const int64_t* item_ids, int64_t N,
+                 const float* grad_out, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* nn.BCELoss() mean reduction with torch's log clamp at -100 (trainer.py:78, 271) and its
+ * gradient: loss_out[0] = mean loss, grad_out[n] = dL/d out[n]. */
+NCF_API int ncf_bce_loss(const float* out, const float* targets, int64_t N, float* loss_out,
+                 float* grad_out, void* stream);
+
+/* torch.optim.Adam (L2-coupled weight decay) on a flat buffer (trainer.py:71-75, 285). */
+NCF_API int ncf_dense_adam(float* w, const float* g, float* m, float* v, int64_t n,
+                   const ncf_adam_cfg* adam, void* stream);
+
+/* One iteration of ModelTrainer.train_epoch's loop body (trainer.py:253-289): forward, BCELoss,
+ * zero_grad, backward, Adam on the dense flat buffer and on the tables.  loss_out: device float. */
+NCF_API int ncf_train_step(const ncf_run_cfg* cfg, const ncf_adam_cfg* adam, const ncf_tables* tables,
+                   float* dense, float* dense_grad, float* dense_m, float* dense_v,
+                   const int64_t* user_ids, const int64_t* item_ids, const float* targets,
+                   int64_t N, float* out, float* loss_out,
+                   void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---- individual kernels (also used by the unit tests) ---------------------------------- */
+/* K1: fused dual-tower gather + LayerNorm + GMF product (architecture.py:286-287, 305-312).
+ * mf_pred[N] = mf_output(LN(U_mf[u]) * LN(P_mf[p])); xu/xp [N,64] = mlp_norm of the MLP rows.
+ * y_item_mf (optional, [N,64]) receives mf_norm(P_mf[p]) for the backward. */
+NCF_API int ncf_gather_ln_gmf_fwd(const ncf_tables* tables, const float* dense,
+                          const int64_t* user_ids, const int64_t* item_ids, int64_t N,
+                          const int64_t* hour, const float* tmod,
+                          float* mf_pred, float* xu, float* xp, float* y_item_mf, void* stream);
+
+/* get_user_embeddings / get_product_embeddings rows (architecture.py:383-407): LN'd rows of one
+ * side. side 0 = user, 1 = item. */
+NCF_API int ncf_gather_ln(const ncf_tables* tables, const float* dense, int32_t side,
+                  const int64_t* ids, int64_t n, float* mf_out, float* mlp_out, void* stream);
+
+/* K6: sorted-id fused embedding backward + Adam for one side (0 user, 1 item).  d_mf_pred [N],
+ * d_x [N,64] = gradient wrt the LN'd MLP row of this side.  The GMF product needs the OTHER side's
+ * LN'd MF row of every sample: other_y_mf [N,64] if the forward saved it, else NULL = gather it from
+ * the other side's table, which must then still hold the forward's values (so with the Adam modes
+ * run the item side first with NULL, then the user side with the saved item rows).  Sort workspace
+ * from ncf_emb_bwd_workspace_bytes. */
+NCF_API int64_t ncf_emb_bwd_workspace_bytes(int64_t N);
+NCF_API int ncf_emb_bwd_adam(const ncf_adam_cfg* adam, const ncf_tables* tables, const float* dense,
+                     float* dense_grad, int32_t side,
+                     const int64_t* user_ids, const int64_t* item_ids, int64_t N,
+                     const float* d_mf_pred, const float* d_x, const float* other_y_mf,
+                     void* workspace, int64_t workspace_bytes, void* stream);
+
+/* the "every untouched row" half of NCF_EMB_ADAM_DENSE_EQUIV; clears tables->touched. */
+NCF_API int ncf_emb_adam_sweep(const ncf_adam_cfg* adam, const ncf_tables* tables, void* stream);
+
+/* TemporalEncoding.forward (architecture.py:86-94): out [n,32]. */
+NCF_API int ncf_temporal_fwd(const float* hour_embed, const float* day_embed, const float* month_embed,
+                     const float* pe, const int64_t* hour, const int64_t* day, const int64_t* month,
+                     const int64_t* days_since, int64_t n, float* out, void* stream);
+
+/* forward_simple hour path tables (architecture.py:433-444, 454-456, 466-468):
+ * tmod[h] = 1 + 0.3*(proj_w . hour_embed[h] + proj_b)  [24,64]
+ * tail1[h] = mlp.0.weight[:,64:96] . hour_embed[h]      [24,256] */
+NCF_API int ncf_temporal_tables(const float* hour_embed, const float* proj_w, const float* proj_b,
+                        const float* dense, float* tmod, float* tail1, void* stream);
+
+/* keep-mask of dropout site (0 attention probs [B,H,S,S]; 1,2,3 MLP layers [N,256|128|64]) exactly
+ * as the forward kernels draw it; used by the parity tests to feed the oracle. */
+NCF_API int ncf_dropout_mask(const ncf_run_cfg* cfg, int32_t site, int64_t numel, uint8_t* keep, void* stream);
+
+/* ---- full-catalogue scoring (app.py:43-77) ---------------------------------------------- */
+/* eval-mode factorisation: P_hat [I,64], g [I] with logit(u,i) = LN_mf(U_mf[u]).P_hat[i] + g[i]. */
+NCF_API int64_t ncf_item_fold_workspace_bytes(int64_t I);
+NCF_API int ncf_item_fold(const ncf_tables* tables, const float* dense, float* p_hat, float* g,
+                  void* workspace, int64_t workspace_bytes, void* stream);
+/* scores + top-k per user: order = score descending, ties -> lowest item index (nlargest keep='first').
+ * topk_idx int64 [n_users,k], topk_score fp32 [n_users,k]. */
+NCF_API int64_t ncf_score_topk_workspace_bytes(int64_t n_users, int64_t I, int32_t k);
+NCF_API int ncf_score_topk(const ncf_tables* tables, const float* dense, const float* p_hat, const float* g,
+                   const int64_t* user_ids, int64_t n_users, int64_t I, int32_t k,
+                   int64_t* topk_idx, float* topk_score,
+                   void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---- row-wise sharding (torchrec ROW_WISE convention) ------------------------- */
+/* block = ceil(rows/world); owner = id / block; local = id % block.  Buckets ids by owner:
+ * counts[world], perm[n] (stable: position of each id in owner-major order), local_ids[n]
+ * written in owner-major order. */
+NCF_API int64_t ncf_shard_bucketize_workspace_bytes(int64_t n, int32_t world);
+NCF_API int ncf_shard_bucketize(const int64_t* ids, int64_t n, int64_t rows, int32_t world,
+                        int64_t* counts, int64_t* perm, int64_t* local_ids,
+                        void* workspace, int64_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NCF_B200_H */

@@ -1,0 +1,128 @@
+"""ctypes binding of libncf_b200.so (include/ncf_b200.h).
+
+The library is the product: if it is missing or a call fails this module raises - there is no
+CPU or PyTorch fallback for the hot path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libncf_b200.so")
+
+NCF_FP32, NCF_BF16_TC = 0, 1
+EMB_NONE, EMB_MATERIALIZE, EMB_ADAM_SPARSE, EMB_ADAM_DENSE_EQUIV = 0, 1, 2, 3
+MAX_S = 8
+
+# dense flat layout ids, in ncf_dense_id order, with the reference state_dict key of each
+DENSE_KEYS = (
+    "mf_norm.weight", "mf_norm.bias", "mlp_norm.weight", "mlp_norm.bias",
+    "user_product_attention.q_proj.weight", "user_product_attention.k_proj.weight",
+    "user_product_attention.v_proj.weight", "user_product_attention.out_proj.weight",
+    "user_product_attention.q_proj.bias", "user_product_attention.k_proj.bias",
+    "user_product_attention.v_proj.bias", "user_product_attention.out_proj.bias",
+    "mlp.0.weight", "mlp.0.bias", "mlp.2.weight", "mlp.2.bias",
+    "mlp.4.weight", "mlp.4.bias", "mlp.6.weight", "mlp.6.bias",
+    "mlp.8.weight", "mlp.8.bias", "mlp.10.weight", "mlp.10.bias",
+    "mf_output.weight", "mf_output.bias", "mlp_output.weight", "mlp_output.bias",
+    "final.0.weight", "final.0.bias",
+)
+
+
+class NcfError(RuntimeError):
+    pass
+
+
+class Tables(C.Structure):
+    _fields_ = [("w", C.c_void_p * 4), ("m", C.c_void_p * 4), ("v", C.c_void_p * 4), ("g", C.c_void_p * 4),
+                ("touched", C.c_void_p * 2), ("rows_user", C.c_int64), ("rows_item", C.c_int64)]
+
+
+class RunCfg(C.Structure):
+    _fields_ = [("S", C.c_int32), ("training", C.c_int32), ("precision", C.c_int32), ("dropout_p", C.c_float),
+                ("seed", C.c_uint64), ("step", C.c_uint64)]
+
+
+class AdamCfg(C.Structure):
+    _fields_ = [("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
+                ("weight_decay", C.c_float), ("step", C.c_int32), ("emb_mode", C.c_int32)]
+
+
+_P = C.c_void_p
+_I64 = C.c_int64
+_I32 = C.c_int32
+_SIGS = {
+    "ncf_version": (C.c_int, []),
+    "ncf_last_error": (C.c_char_p, []),
+    "ncf_dense_numel": (_I64, []),
+    "ncf_dense_offset": (_I64, [_I32]),
+    "ncf_dense_size": (_I64, [_I32]),
+    "ncf_workspace_bytes": (_I64, [_I64, C.POINTER(RunCfg)]),
+    "ncf_forward": (C.c_int, [C.POINTER(RunCfg), C.POINTER(Tables), _P, _P, _P, _I64, _P, _P, _P, _P, _P, _I64, _P]),
+    "ncf_backward": (C.c_int, [C.POINTER(RunCfg), C.POINTER(AdamCfg), C.POINTER(Tables), _P, _P, _P, _P, _I64, _P, _P,
+                               _I64, _P]),
+    "ncf_bce_loss": (C.c_int, [_P, _P, _I64, _P, _P, _P]),
+    "ncf_dense_adam": (C.c_int, [_P, _P, _P, _P, _I64, C.POINTER(AdamCfg), _P]),
+    "ncf_train_step": (C.c_int, [C.POINTER(RunCfg), C.POINTER(AdamCfg), C.POINTER(Tables), _P, _P, _P, _P, _P, _P, _P,
+                                 _I64, _P, _P, _P, _I64, _P]),
+    "ncf_gather_ln_gmf_fwd": (C.c_int, [C.POINTER(Tables), _P, _P, _P, _I64, _P, _P, _P, _P, _P, _P, _P]),
+    "ncf_gather_ln": (C.c_int, [C.POINTER(Tables), _P, _I32, _P, _I64, _P, _P, _P]),
+    "ncf_emb_bwd_workspace_bytes": (_I64, [_I64]),
+    "ncf_emb_bwd_adam": (C.c_int, [C.POINTER(AdamCfg), C.POINTER(Tables), _P, _P, _I32, _P, _P, _I64, _P, _P, _P, _P,
+                                   _I64, _P]),
+    "ncf_emb_adam_sweep": (C.c_int, [C.POINTER(AdamCfg), C.POINTER(Tables), _P]),
+    "ncf_temporal_fwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _P, _P]),
+    "ncf_temporal_tables": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
+    "ncf_dropout_mask": (C.c_int, [C.POINTER(RunCfg), _I32, _I64, _P, _P]),
+    "ncf_item_fold_workspace_bytes": (_I64, [_I64]),
+    "ncf_item_fold": (C.c_int, [C.POINTER(Tables), _P, _P, _P, _P, _I64, _P]),
+    "ncf_score_topk_workspace_bytes": (_I64, [_I64, _I64, _I32]),
+    "ncf_score_topk": (C.c_int, [C.POINTER(Tables), _P, _P, _P, _P, _I64, _I64, _I32, _P, _P, _P, _I64, _P]),
+    "ncf_shard_bucketize_workspace_bytes": (_I64, [_I64, _I32]),
+    "ncf_shard_bucketize": (C.c_int, [_P, _I64, _I64, _I32, _P, _P, _P, _P, _I64, _P]),
+}
+EXPORTS = tuple(_SIGS)
+
+_lock = threading.Lock()
+_lib = None
+
+
+def load():
+    """dlopen libncf_b200.so (built in-tree by build.py); raises NcfError when it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise NcfError(f"{LIB_PATH} is missing: run `python __graft_entry__.py build` (nvcc, sm_100a). "
+                               "There is no CPU fallback for the AdvancedNCF hot path.")
+            lib = C.CDLL(LIB_PATH)
+            for name, (res, args) in _SIGS.items():
+                fn = getattr(lib, name)      # AttributeError here = header/library mismatch
+                fn.restype = res
+                fn.argtypes = args
+            if lib.ncf_version() != 1:
+                raise NcfError("libncf_b200.so ABI version mismatch")
+            _lib = lib
+    return _lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load().ncf_last_error().decode("utf-8", "replace")
+        raise NcfError(f"{what or 'libncf_b200'} failed ({rc}): {msg}")
+
+
+def dense_layout():
+    """[(state_dict key, offset, size)] of the flat dense buffer, and its padded length."""
+    lib = load()
+    return [(k, int(lib.ncf_dense_offset(i)), int(lib.ncf_dense_size(i))) for i, k in enumerate(DENSE_KEYS)], \
+        int(lib.ncf_dense_numel())
+
+
+def ptr(t):
+    """device pointer of a torch tensor (or None)"""
+    return None if t is None else C.c_void_p(t.data_ptr())

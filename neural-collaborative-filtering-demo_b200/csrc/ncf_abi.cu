@@ -1,0 +1,115 @@
+// extern "C" boundary of libncf_b200.so: argument checking, workspace carving, kernel sequencing.
+#include <stdarg.h>
+#include <string.h>
+
+#include "ncf_tower.cuh"
+
+namespace ncf {
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+  set_error("CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);
+  return NCF_ERR_CUDA;
+}
+}  // namespace ncf
+
+using namespace ncf;
+
+extern "C" int ncf_version(void) { return NCF_ABI_VERSION; }
+extern "C" const char* ncf_last_error(void) { return g_err; }
+extern "C" int64_t ncf_dense_numel(void) { return kLayout.total; }
+extern "C" int64_t ncf_dense_offset(int32_t id) { return id >= 0 && id < NCF_P_COUNT ? kLayout.off[id] : -1; }
+extern "C" int64_t ncf_dense_size(int32_t id) { return id >= 0 && id < NCF_P_COUNT ? kLayout.size[id] : -1; }
+
+static int check_cfg(const ncf_run_cfg* cfg, int64_t N) {
+  NCF_REQUIRE(cfg, "null run cfg");
+  NCF_REQUIRE(cfg->S >= 1 && cfg->S <= NCF_MAX_S, "S=%d outside [1,%d]", cfg->S, NCF_MAX_S);
+  NCF_REQUIRE(N >= 0 && N % cfg->S == 0, "N=%lld is not a multiple of S=%d (architecture.py:276)", (long long)N, cfg->S);
+  NCF_REQUIRE(N < ((int64_t)1 << 31), "N too large");
+  NCF_REQUIRE(cfg->dropout_p >= 0.f && cfg->dropout_p < 1.f, "dropout_p outside [0,1)");
+  if (cfg->precision != NCF_FP32) {
+    set_error("precision %d not available in this build", cfg->precision);
+    return NCF_ERR_UNSUPPORTED;
+  }
+  return NCF_OK;
+}
+
+extern "C" int64_t ncf_workspace_bytes(int64_t N, const ncf_run_cfg* cfg) {
+  if (!cfg || N < 0) return -1;
+  return carve_tower_ws(nullptr, std::max<int64_t>(N, 1), *cfg).total;
+}
+
+extern "C" int ncf_forward(const ncf_run_cfg* cfg, const ncf_tables* T, const float* dense, const int64_t* user_ids,
+                           const int64_t* item_ids, int64_t N, const int64_t* hour, const float* tmod,
+                           const float* tail1, float* out, void* workspace, int64_t workspace_bytes, void* stream) {
+  NCF_TRY(check_cfg(cfg, N));
+  NCF_REQUIRE(T && dense && user_ids && item_ids && out && workspace, "forward: null argument");
+  NCF_REQUIRE(!hour || (tmod && tail1), "forward: the hour path needs tmod and tail1");
+  if (N == 0) return NCF_OK;
+  TowerWs w = carve_tower_ws(workspace, N, *cfg);
+  if (workspace_bytes < w.total) {
+    set_error("forward: workspace %lld < %lld bytes", (long long)workspace_bytes, (long long)w.total);
+    return NCF_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  NCF_TRY(ncf_gather_ln_gmf_fwd(T, dense, user_ids, item_ids, N, hour, tmod, w.mf_pred, w.xu, w.xp,
+                                cfg->training ? w.y_pmf : nullptr, stream));
+  return tower_f32_forward(*cfg, dense, N, hour, tail1, out, w, st);
+}
+
+extern "C" int ncf_backward(const ncf_run_cfg* cfg, const ncf_adam_cfg* adam, const ncf_tables* T, const float* dense,
+                            float* dense_grad, const int64_t* user_ids, const int64_t* item_ids, int64_t N,
+                            const float* grad_out, void* workspace, int64_t workspace_bytes, void* stream) {
+  NCF_TRY(check_cfg(cfg, N));
+  NCF_REQUIRE(adam && T && dense && dense_grad && user_ids && item_ids && grad_out && workspace, "backward: null argument");
+  NCF_REQUIRE(cfg->training, "backward: needs the workspace of a training-mode forward");
+  if (N == 0) return NCF_OK;
+  TowerWs w = carve_tower_ws(workspace, N, *cfg);
+  if (workspace_bytes < w.total) {
+    set_error("backward: workspace %lld < %lld bytes", (long long)workspace_bytes, (long long)w.total);
+    return NCF_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  NCF_TRY(tower_f32_backward(*cfg, dense, dense_grad, N, grad_out, w, st));
+  if (adam->emb_mode != NCF_EMB_NONE) {
+    // item side first: it gathers the user MF rows, which the user-side pass then overwrites (Adam);
+    // the user side reads the item rows the forward saved.
+    NCF_TRY(ncf_emb_bwd_adam(adam, T, dense, dense_grad, 1, user_ids, item_ids, N, w.d_mf, w.dxp, nullptr, w.emb, w.emb_bytes, stream));
+    NCF_TRY(ncf_emb_bwd_adam(adam, T, dense, dense_grad, 0, user_ids, item_ids, N, w.d_mf, w.dxu, w.y_pmf, w.emb, w.emb_bytes, stream));
+    if (adam->emb_mode == NCF_EMB_ADAM_DENSE_EQUIV) NCF_TRY(ncf_emb_adam_sweep(adam, T, stream));
+  }
+  return NCF_OK;
+}
+
+extern "C" int ncf_bce_loss(const float* out, const float* targets, int64_t N, float* loss_out, float* grad_out,
+                            void* stream) {
+  NCF_REQUIRE(out && targets && loss_out && N >= 0, "bce_loss: bad argument");
+  return launch_bce(out, targets, N, loss_out, grad_out, (cudaStream_t)stream);
+}
+
+extern "C" int ncf_train_step(const ncf_run_cfg* cfg, const ncf_adam_cfg* adam, const ncf_tables* T, float* dense,
+                              float* dense_grad, float* dense_m, float* dense_v, const int64_t* user_ids,
+                              const int64_t* item_ids, const float* targets, int64_t N, float* out, float* loss_out,
+                              void* workspace, int64_t workspace_bytes, void* stream) {
+  NCF_TRY(check_cfg(cfg, N));
+  NCF_REQUIRE(adam && T && dense && dense_grad && dense_m && dense_v && targets && out && loss_out, "train_step: null argument");
+  NCF_REQUIRE(cfg->training, "train_step: cfg->training must be set");
+  NCF_REQUIRE(N > 0, "train_step: empty batch");
+  cudaStream_t st = (cudaStream_t)stream;
+  TowerWs w = carve_tower_ws(workspace, N, *cfg);
+  if (workspace_bytes < w.total) {
+    set_error("train_step: workspace %lld < %lld bytes", (long long)workspace_bytes, (long long)w.total);
+    return NCF_ERR_WORKSPACE;
+  }
+  NCF_CUDA(cudaMemsetAsync(dense_grad, 0, sizeof(float) * kLayout.total, st));                       // optimizer.zero_grad()
+  NCF_TRY(ncf_forward(cfg, T, dense, user_ids, item_ids, N, nullptr, nullptr, nullptr, out, workspace, workspace_bytes, stream));
+  // BCELoss gradient goes into the (not yet used) backward scratch g128b
+  NCF_TRY(launch_bce(out, targets, N, loss_out, w.g128b, st));
+  NCF_TRY(ncf_backward(cfg, adam, T, dense, dense_grad, user_ids, item_ids, N, w.g128b, workspace, workspace_bytes, stream));
+  return ncf_dense_adam(dense, dense_grad, dense_m, dense_v, kLayout.total, adam, stream);
+}

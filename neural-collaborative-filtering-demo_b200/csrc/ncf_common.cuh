@@ -1,0 +1,166 @@
+// Shared device/host helpers for libncf_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "ncf_b200.h"
+
+namespace ncf {
+
+constexpr int D = NCF_D;
+constexpr int H1 = NCF_H1, H2 = NCF_H2, H3 = NCF_H3;
+constexpr int HEADS = NCF_HEADS, HD = NCF_D / NCF_HEADS;
+constexpr int TDIM = NCF_TDIM;
+constexpr int K0 = NCF_D + NCF_TDIM;  // mlp.0 in_features = 96
+constexpr float LN_EPS = 1e-5f;
+
+// ---- error plumbing ---------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+#define NCF_CUDA(call)                                                          \
+  do {                                                                          \
+    cudaError_t e__ = (call);                                                   \
+    if (e__ != cudaSuccess) return ::ncf::cuda_fail(e__, #call, __FILE__, __LINE__); \
+  } while (0)
+#define NCF_LAUNCH_CHECK() NCF_CUDA(cudaGetLastError())
+#define NCF_REQUIRE(cond, ...)                 \
+  do {                                         \
+    if (!(cond)) {                             \
+      ::ncf::set_error(__VA_ARGS__);           \
+      return NCF_ERR_ARG;                      \
+    }                                          \
+  } while (0)
+#define NCF_TRY(expr)            \
+  do {                           \
+    int rc__ = (expr);           \
+    if (rc__ != NCF_OK) return rc__; \
+  } while (0)
+
+// ---- dense flat layout --------------------------------------------------------------------
+struct DenseLayout {
+  int64_t off[NCF_P_COUNT];
+  int64_t size[NCF_P_COUNT];
+  int64_t total;
+};
+constexpr DenseLayout make_layout() {
+  DenseLayout L{};
+  const int64_t sizes[NCF_P_COUNT] = {
+      D, D, D, D,
+      D * D, D * D, D * D, D * D, D, D, D, D,
+      (int64_t)H1 * K0, H1, H1, H1,
+      (int64_t)H2 * H1, H2, H2, H2,
+      (int64_t)H3 * H2, H3, H3, H3,
+      D, 1, H3, 1, 2, 1};
+  int64_t o = 0;
+  for (int i = 0; i < NCF_P_COUNT; ++i) {
+    L.off[i] = o;
+    L.size[i] = sizes[i];
+    o += (sizes[i] + 3) / 4 * 4;  // keep every tensor 16-byte aligned
+  }
+  L.total = o;
+  return L;
+}
+constexpr DenseLayout kLayout = make_layout();   // host-side table
+// compile-time offsets usable in device code
+template <int ID>
+struct DenseOff {
+  static constexpr int64_t value = make_layout().off[ID];
+};
+#define NCF_OFF(id) (::ncf::DenseOff<id>::value)
+
+inline int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
+inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+
+// bump allocator over the caller-provided workspace
+struct Carver {
+  char* base;
+  int64_t used = 0;
+  explicit Carver(void* p) : base(static_cast<char*>(p)) {}
+  template <typename T>
+  T* take(int64_t count) {
+    used = align_up(used, 256);
+    T* p = base ? reinterpret_cast<T*>(base + used) : nullptr;
+    used += count * (int64_t)sizeof(T);
+    return p;
+  }
+};
+
+// ---- device helpers -------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// sum over the 16 lanes of a half warp (lanes keep their half)
+__device__ __forceinline__ float half_warp_sum(float v) {
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ float4 f4_fma(float a, float4 x, float4 y) {
+  return make_float4(fmaf(a, x.x, y.x), fmaf(a, x.y, y.y), fmaf(a, x.z, y.z), fmaf(a, x.w, y.w));
+}
+__device__ __forceinline__ float4 f4_add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ float4 f4_mul(float4 a, float4 b) { return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
+__device__ __forceinline__ float f4_dot(float4 a, float4 b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
+__device__ __forceinline__ float f4_hsum(float4 a) { return (a.x + a.y) + (a.z + a.w); }
+
+// Philox4x32-10 (Salmon et al. 2011): counter-based, so every dropout element is a pure function
+// of (seed, step, site, element index) - the backward and the test-side mask dump regenerate it.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+  constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+    const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += W0;
+    key.y += W1;
+  }
+  return ctr;
+}
+// random 32-bit word of dropout element `idx` at `site`
+struct DropoutRng {
+  uint2 key;
+  uint32_t step_lo, step_hi_site;
+  uint32_t thresh;  // keep iff word >= thresh
+  float scale;      // 1/(1-p)
+  __device__ __forceinline__ uint4 draw4(uint64_t group) const {
+    return philox4x32_10(make_uint4((uint32_t)group, (uint32_t)(group >> 32), step_lo, step_hi_site), key);
+  }
+  __device__ __forceinline__ bool keep(uint64_t idx) const {
+    const uint4 r = draw4(idx >> 2);
+    const uint32_t c = (uint32_t)idx & 3u;
+    const uint32_t w = c == 0 ? r.x : c == 1 ? r.y : c == 2 ? r.z : r.w;
+    return w >= thresh;
+  }
+};
+__host__ __device__ inline DropoutRng make_rng(const ncf_run_cfg& cfg, int site) {
+  DropoutRng r;
+  r.key = make_uint2((uint32_t)cfg.seed, (uint32_t)(cfg.seed >> 32));
+  r.step_lo = (uint32_t)cfg.step;
+  r.step_hi_site = ((uint32_t)(cfg.step >> 32) & 0x00ffffffu) | ((uint32_t)site << 24);
+  const double p = (cfg.training && cfg.dropout_p > 0.f) ? (double)cfg.dropout_p : 0.0;
+  double t = p * 4294967296.0;
+  r.thresh = t >= 4294967295.0 ? 0xffffffffu : (uint32_t)t;
+  r.scale = (float)(1.0 / (1.0 - p));
+  return r;
+}
+#endif  // __CUDACC__
+
+}  // namespace ncf

@@ -1,0 +1,718 @@
+// Embedding path of AdvancedNCF on sm_100a: fused dual-tower gather + LayerNorm + GMF (K1), the
+// sorted-id fused embedding backward + Adam (K6), the dense-equivalent Adam sweep, the temporal
+// encoding kernels and the dropout-mask dump.  All HBM-bound: rows are 256 B (64 fp32), moved as
+// 128-bit vectors by half warps (16 lanes x 16 B = one row), id blocks staged into shared memory
+// by cp.async.bulk (TMA bulk copy) with an mbarrier, reductions by warp shuffles.
+#include <cub/device/device_radix_sort.cuh>
+
+#include "ncf_common.cuh"
+
+namespace ncf {
+
+// ---- mbarrier / bulk-copy PTX ---------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  const uint32_t a = smem_u32(bar);
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(a), "r"(parity)
+        : "memory");
+  }
+}
+
+// LayerNorm of a 64-float row held as one float4 per lane of a half warp.  Returns the
+// normalised values (x - mean) * rstd; rstd through the reference.
+__device__ __forceinline__ float4 ln_normalise(float4 x, float& rstd) {
+  const float mean = half_warp_sum(f4_hsum(x)) * (1.0f / 64.0f);
+  const float4 d = make_float4(x.x - mean, x.y - mean, x.z - mean, x.w - mean);
+  const float var = half_warp_sum(f4_dot(d, d)) * (1.0f / 64.0f);
+  rstd = rsqrtf(var + LN_EPS);
+  return make_float4(d.x * rstd, d.y * rstd, d.z * rstd, d.w * rstd);
+}
+__device__ __forceinline__ float4 affine(float4 xh, float4 g, float4 b) {
+  return make_float4(fmaf(xh.x, g.x, b.x), fmaf(xh.y, g.y, b.y), fmaf(xh.z, g.z, b.z), fmaf(xh.w, g.w, b.w));
+}
+
+// =============================================================================================
+// K1  fused dual-tower gather + LayerNorm + GMF product   (architecture.py:286-287, 305-312)
+// =============================================================================================
+constexpr int K1_THREADS = 256;
+constexpr int K1_TILE = 128;  // sample rows per CTA iteration (id block = 2 x 1 KiB)
+
+template <bool HOUR>
+__global__ void __launch_bounds__(K1_THREADS) gather_ln_gmf_fwd_kernel(
+    const float* __restrict__ t_umf, const float* __restrict__ t_pmf, const float* __restrict__ t_umlp,
+    const float* __restrict__ t_pmlp, const float* __restrict__ dense, const int64_t* __restrict__ user_ids,
+    const int64_t* __restrict__ item_ids, int64_t N, const int64_t* __restrict__ hour,
+    const float* __restrict__ tmod, float* __restrict__ mf_pred, float* __restrict__ xu, float* __restrict__ xp,
+    float* __restrict__ y_item_mf) {
+  __shared__ __align__(16) int64_t s_ids[2][2][K1_TILE];
+  __shared__ __align__(8) uint64_t s_bar[2];
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int half = lane >> 4, l16 = lane & 15;
+  const int64_t num_tiles = (N + K1_TILE - 1) / K1_TILE;
+  const bool bulk_ok = ((reinterpret_cast<uintptr_t>(user_ids) | reinterpret_cast<uintptr_t>(item_ids)) & 15) == 0;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&s_bar[0], 1);
+    mbar_init(&s_bar[1], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  // per-lane constants: this half's tables and LayerNorm affine slices
+  const float* tab_mf = half ? t_pmf : t_umf;
+  const float* tab_mlp = half ? t_pmlp : t_umlp;
+  const float4 g_mf = ldg4(dense + NCF_OFF(NCF_P_MF_NORM_W) + 4 * l16);
+  const float4 b_mf = ldg4(dense + NCF_OFF(NCF_P_MF_NORM_B) + 4 * l16);
+  const float4 g_ml = ldg4(dense + NCF_OFF(NCF_P_MLP_NORM_W) + 4 * l16);
+  const float4 b_ml = ldg4(dense + NCF_OFF(NCF_P_MLP_NORM_B) + 4 * l16);
+  const float4 w_out = ldg4(dense + NCF_OFF(NCF_P_MF_OUT_W) + 4 * l16);
+  const float b_out = __ldg(dense + NCF_OFF(NCF_P_MF_OUT_B));
+
+  auto stage = [&](int64_t tile, int buf) {  // whole CTA calls; thread 0 issues the bulk copies
+    const int64_t n0 = tile * K1_TILE;
+    const int rows = (int)min((int64_t)K1_TILE, N - n0);
+    if (bulk_ok && (rows & 1) == 0) {
+      if (threadIdx.x == 0) {
+        mbar_arrive_expect_tx(&s_bar[buf], 2u * rows * 8u);
+        bulk_g2s(&s_ids[buf][0][0], user_ids + n0, rows * 8u, &s_bar[buf]);
+        bulk_g2s(&s_ids[buf][1][0], item_ids + n0, rows * 8u, &s_bar[buf]);
+      }
+    } else {  // unaligned / odd tail: plain loads, then complete the same barrier phase
+      for (int i = threadIdx.x; i < 2 * rows; i += K1_THREADS) {
+        const int side = i >= rows, r = side ? i - rows : i;
+        s_ids[buf][side][r] = side ? item_ids[n0 + r] : user_ids[n0 + r];
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) mbar_arrive_expect_tx(&s_bar[buf], 0);
+    }
+  };
+
+  uint32_t phase[2] = {0, 0};
+  int buf = 0;
+  int64_t tile = blockIdx.x;
+  if (tile < num_tiles) stage(tile, 0);
+  for (; tile < num_tiles; tile += gridDim.x, buf ^= 1) {
+    const int64_t next = tile + gridDim.x;
+    if (next < num_tiles) stage(next, buf ^ 1);  // prefetch the next id block while this one is consumed
+    mbar_wait(&s_bar[buf], phase[buf]);
+    phase[buf] ^= 1;
+
+    const int64_t n0 = tile * K1_TILE;
+    const int rows = (int)min((int64_t)K1_TILE, N - n0);
+    // each warp owns rows warp*16 .. warp*16+15 of the tile, four at a time (8 x 128-bit loads in flight)
+#pragma unroll 1
+    for (int r0 = warp * (K1_TILE / 8); r0 < (warp + 1) * (K1_TILE / 8); r0 += 4) {
+      float4 a[4], b[4];
+      int64_t id[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int r = min(r0 + j, rows - 1);
+        id[j] = s_ids[buf][half][r];
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        a[j] = ldg4(tab_mf + id[j] * D + 4 * l16);
+        b[j] = ldg4(tab_mlp + id[j] * D + 4 * l16);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int r = r0 + j;
+        float rs;
+        float4 y_mf = affine(ln_normalise(a[j], rs), g_mf, b_mf);
+        float4 y_ml = affine(ln_normalise(b[j], rs), g_ml, b_ml);
+        if (HOUR) {  // forward_simple hour path: item rows scaled by 1 + 0.3 * proj(hour_embed[h])
+          const int64_t h = hour[n0 + min(r, rows - 1)];
+          const float4 t = ldg4(tmod + h * D + 4 * l16);
+          if (half) {
+            y_mf = f4_mul(y_mf, t);
+            y_ml = f4_mul(y_ml, t);
+          }
+        }
+        const float4 other = make_float4(__shfl_xor_sync(0xffffffffu, y_mf.x, 16), __shfl_xor_sync(0xffffffffu, y_mf.y, 16),
+                                         __shfl_xor_sync(0xffffffffu, y_mf.z, 16), __shfl_xor_sync(0xffffffffu, y_mf.w, 16));
+        const float dot = half_warp_sum(f4_dot(f4_mul(y_mf, other), w_out));
+        if (r < rows) {
+          const int64_t n = n0 + r;
+          if (lane == 0) mf_pred[n] = dot + b_out;
+          st4((half ? xp : xu) + n * D + 4 * l16, y_ml);
+          if (y_item_mf && half) st4(y_item_mf + n * D + 4 * l16, y_mf);   // kept for the backward
+        }
+      }
+    }
+    __syncthreads();  // everyone is done with s_ids[buf] before it is refilled two tiles later
+  }
+}
+
+// LN'd rows of one side (get_user_embeddings / get_product_embeddings, architecture.py:383-407)
+__global__ void __launch_bounds__(256) gather_ln_kernel(const float* __restrict__ t_mf, const float* __restrict__ t_mlp,
+                                                         const float* __restrict__ dense,
+                                                         const int64_t* __restrict__ ids, int64_t n,
+                                                         float* __restrict__ mf_out, float* __restrict__ mlp_out) {
+  const int lane = threadIdx.x & 31, half = lane >> 4, l16 = lane & 15;
+  const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const float* tab = half ? t_mlp : t_mf;
+  float* out = half ? mlp_out : mf_out;
+  const float4 g = ldg4(dense + (half ? NCF_OFF(NCF_P_MLP_NORM_W) : NCF_OFF(NCF_P_MF_NORM_W)) + 4 * l16);
+  const float4 b = ldg4(dense + (half ? NCF_OFF(NCF_P_MLP_NORM_B) : NCF_OFF(NCF_P_MF_NORM_B)) + 4 * l16);
+  for (int64_t r = warp; r < n; r += nwarps) {
+    const int64_t id = ids[r];
+    float rs;
+    const float4 y = affine(ln_normalise(ldg4(tab + id * D + 4 * l16), rs), g, b);
+    if (out) st4(out + r * D + 4 * l16, y);
+  }
+}
+
+// =============================================================================================
+// K6  sorted-id fused embedding backward + Adam
+//
+// For one side (user or item) the sample rows are sorted by id, so all rows that hit the same table
+// row are adjacent.  LayerNorm backward is linear in its upstream gradient for a fixed input row, so
+// the upstream gradients of a run are summed FIRST and LayerNorm-backward + Adam run once per unique
+// id: the per-sample row gradients are never written to memory.
+//   upstream(MF row)  = sum_n d_mf_pred[n] * w_mf * LN(other side's MF row of sample n)
+//   upstream(MLP row) = sum_n d_x[n]
+// A warp owns a chunk of EB_CHUNK sorted positions; half 0 works on the MF tower, half 1 on the MLP
+// tower.  Runs that cross chunk borders leave per-chunk partial sums that phase 2 adds in a fixed
+// order (deterministic, no float atomics on table rows).
+// =============================================================================================
+constexpr int EB_CHUNK = 32;
+constexpr int EB_THREADS = 256;
+
+struct AdamScalars {
+  float lr_bc1;       // lr / (1 - beta1^t)
+  float inv_sqrt_bc2; // 1 / sqrt(1 - beta2^t)
+  float beta1, beta2, eps, wd;
+};
+inline AdamScalars adam_scalars(const ncf_adam_cfg& a) {
+  AdamScalars s;
+  const double bc1 = 1.0 - pow((double)a.beta1, (double)a.step);
+  const double bc2 = 1.0 - pow((double)a.beta2, (double)a.step);
+  s.lr_bc1 = (float)((double)a.lr / bc1);
+  s.inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
+  s.beta1 = a.beta1;
+  s.beta2 = a.beta2;
+  s.eps = a.eps;
+  s.wd = a.weight_decay;
+  return s;
+}
+// torch.optim.Adam single-tensor update order
+__device__ __forceinline__ void adam_update(float& w, float& m, float& v, float g, const AdamScalars& s) {
+  g = fmaf(s.wd, w, g);
+  m = m + (g - m) * (1.0f - s.beta1);
+  v = fmaf(s.beta2, v, (1.0f - s.beta2) * g * g);
+  const float denom = fmaf(sqrtf(v), s.inv_sqrt_bc2, s.eps);
+  w = w - s.lr_bc1 * (m / denom);
+}
+__device__ __forceinline__ void adam_update4(float4& w, float4& m, float4& v, float4 g, const AdamScalars& s) {
+  adam_update(w.x, m.x, v.x, g.x, s);
+  adam_update(w.y, m.y, v.y, g.y, s);
+  adam_update(w.z, m.z, v.z, g.z, s);
+  adam_update(w.w, m.w, v.w, g.w, s);
+}
+
+struct EmbBwdArgs {
+  // this side's two tables (mf, mlp) and their optimizer state / dense-grad targets
+  float* w[2];
+  float* m[2];
+  float* v[2];
+  float* g[2];
+  uint8_t* touched;
+  const float* other_mf;          // other side's MF table (for the GMF product), used when other_y == null
+  const float* other_y;           // [N,64] LN'd MF row of the other side saved by the forward (or null)
+  const int64_t* other_ids;       // other side's ids, original sample order
+  const uint32_t* sorted_ids;     // this side's ids, sorted
+  const int32_t* perm;            // sample row of each sorted position
+  const float* d_mf_pred;         // [N]
+  const float* d_x;               // [N,64] gradient wrt this side's LN'd MLP row
+  const float* dense;
+  float* dense_grad;
+  float* partial;                 // [nchunks][2][128]
+  int64_t N;
+  int32_t mode;                   // ncf_emb_mode
+  int32_t accumulate_wmf;         // only one side adds d mf_output.weight
+  AdamScalars adam;
+};
+
+// Finish one unique id: LayerNorm backward of the summed upstream gradient, then Adam / store.
+// `acc` = summed upstream gradient of this lane's 4 columns (half 0: MF tower, half 1: MLP tower).
+__device__ __forceinline__ void emb_finalize(const EmbBwdArgs& A, int64_t id, float4 acc, float4 xhat, float rstd,
+                                             float4 wrow, float4 gamma, float4& dgamma, float4& dbeta, int half,
+                                             int l16) {
+  dgamma = f4_add(dgamma, f4_mul(acc, xhat));
+  dbeta = f4_add(dbeta, acc);
+  const float4 dyg = f4_mul(acc, gamma);
+  const float m1 = half_warp_sum(f4_hsum(dyg)) * (1.0f / 64.0f);
+  const float m2 = half_warp_sum(f4_dot(dyg, xhat)) * (1.0f / 64.0f);
+  float4 graw = make_float4(rstd * (dyg.x - m1 - xhat.x * m2), rstd * (dyg.y - m1 - xhat.y * m2),
+                            rstd * (dyg.z - m1 - xhat.z * m2), rstd * (dyg.w - m1 - xhat.w * m2));
+  const int64_t o = id * D + 4 * l16;
+  if (A.mode == NCF_EMB_MATERIALIZE) {
+    st4(A.g[half] + o, graw);
+  } else {
+    float4 mm = ld4(A.m[half] + o), vv = ld4(A.v[half] + o);
+    adam_update4(wrow, mm, vv, graw, A.adam);
+    st4(A.w[half] + o, wrow);
+    st4(A.m[half] + o, mm);
+    st4(A.v[half] + o, vv);
+    if (A.touched && l16 == 0 && half == 0) A.touched[id] = 1;
+  }
+}
+
+__device__ __forceinline__ void block_flush(float* s_red, float4 val, float* dst, int lane, int warp, int nwarps,
+                                            bool active_half, int l16) {
+  // reduce one float4-per-lane accumulator (16 lanes x 4 = 64 columns, per half) over the block's warps
+  __syncthreads();
+  float* mine = s_red + (warp * 32 + lane) * 4;
+  mine[0] = val.x; mine[1] = val.y; mine[2] = val.z; mine[3] = val.w;
+  __syncthreads();
+  if (warp == 0) {
+    float4 t = make_float4(0, 0, 0, 0);
+    for (int w = 0; w < nwarps; ++w) {
+      const float* p = s_red + (w * 32 + lane) * 4;
+      t = f4_add(t, make_float4(p[0], p[1], p[2], p[3]));
+    }
+    if (active_half && dst) {
+      atomicAdd(dst + 4 * l16 + 0, t.x);
+      atomicAdd(dst + 4 * l16 + 1, t.y);
+      atomicAdd(dst + 4 * l16 + 2, t.z);
+      atomicAdd(dst + 4 * l16 + 3, t.w);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(EB_THREADS) emb_bwd_phase1_kernel(EmbBwdArgs A) {
+  __shared__ float s_red[(EB_THREADS / 32) * 32 * 4];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = EB_THREADS / 32;
+  const int half = lane >> 4, l16 = lane & 15;
+  const int64_t nchunks = (A.N + EB_CHUNK - 1) / EB_CHUNK;
+  const int64_t gw = (int64_t)blockIdx.x * nwarps + warp, gstride = (int64_t)gridDim.x * nwarps;
+
+  const float4 gamma = ldg4(A.dense + (half ? NCF_OFF(NCF_P_MLP_NORM_W) : NCF_OFF(NCF_P_MF_NORM_W)) + 4 * l16);
+  const float4 beta = ldg4(A.dense + (half ? NCF_OFF(NCF_P_MLP_NORM_B) : NCF_OFF(NCF_P_MF_NORM_B)) + 4 * l16);
+  const float4 g_mf = ldg4(A.dense + NCF_OFF(NCF_P_MF_NORM_W) + 4 * l16);   // for the other side's MF row
+  const float4 b_mf = ldg4(A.dense + NCF_OFF(NCF_P_MF_NORM_B) + 4 * l16);
+  const float4 w_out = ldg4(A.dense + NCF_OFF(NCF_P_MF_OUT_W) + 4 * l16);
+  float4 dgamma = make_float4(0, 0, 0, 0), dbeta = dgamma, dwout = dgamma;
+
+  for (int64_t c = gw; c < nchunks; c += gstride) {
+    const int64_t p0 = c * EB_CHUNK;
+    const int cnt = (int)min((int64_t)EB_CHUNK, A.N - p0);
+    // lane i holds sorted position p0+i
+    const uint32_t my_id = lane < cnt ? A.sorted_ids[p0 + lane] : 0xffffffffu;
+    const int32_t my_row = lane < cnt ? A.perm[p0 + lane] : 0;
+    const int64_t my_other = lane < cnt ? A.other_ids[my_row] : 0;
+    const float my_dmf = lane < cnt ? A.d_mf_pred[my_row] : 0.f;
+    const uint32_t prev_id = p0 > 0 ? A.sorted_ids[p0 - 1] : 0xffffffffu;             // uniform
+    const uint32_t next_id = p0 + cnt < A.N ? A.sorted_ids[p0 + cnt] : 0xffffffffu;   // uniform
+    const bool has_prev = p0 > 0, has_next = p0 + cnt < A.N;
+
+    int i = 0;
+    while (i < cnt) {
+      const uint32_t id = __shfl_sync(0xffffffffu, my_id, i);
+      // run [i, j) of equal ids inside this chunk
+      const uint32_t same = __ballot_sync(0xffffffffu, my_id == id && lane >= i && lane < cnt);
+      int e;
+      {  // ids are sorted, so the run is the contiguous set of lanes with my_id == id starting at i
+        const uint32_t m = same >> i;                                  // bit k <-> lane i+k
+        e = i + (m == 0xffffffffu ? 32 : __ffs(~m) - 1);               // trailing ones = run length
+        if (e > cnt) e = cnt;
+      }
+      const bool starts_here = !(i == 0 && has_prev && prev_id == id);
+      const bool ends_here = !(e == cnt && has_next && next_id == id);
+
+      // this side's own rows: needed for d mf_output.weight (user pass) and to finalise
+      float rstd;
+      const float4 wrow = ld4(A.w[half] + (int64_t)id * D + 4 * l16);
+      const float4 xhat = ln_normalise(wrow, rstd);
+      const float4 y_self_mf_lane = affine(xhat, gamma, beta);  // meaningful on half 0 (MF tower)
+
+      float4 acc = make_float4(0, 0, 0, 0);
+      for (int k = i; k < e; k += 2) {
+        // two sample rows per iteration (independent 128-bit loads in flight)
+        float4 x[2];
+        float dmf[2];
+        bool ok[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int kk = min(k + u, e - 1);
+          ok[u] = k + u < e;
+          const int32_t row = __shfl_sync(0xffffffffu, my_row, kk);
+          const int64_t oid = __shfl_sync(0xffffffffu, my_other, kk);
+          dmf[u] = __shfl_sync(0xffffffffu, my_dmf, kk);
+          const float* src = half ? A.d_x + (int64_t)row * D
+                                  : (A.other_y ? A.other_y + (int64_t)row * D : A.other_mf + oid * D);
+          x[u] = ldg4(src + 4 * l16);
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          float rs;
+          float4 yo = affine(ln_normalise(x[u], rs), g_mf, b_mf);   // LN of the other side's MF row
+          if (A.other_y) yo = x[u];                                  // already normalised by the forward
+          if (ok[u]) {
+            if (half) {
+              acc = f4_add(acc, x[u]);
+            } else {
+              const float4 t = make_float4(dmf[u] * yo.x, dmf[u] * yo.y, dmf[u] * yo.z, dmf[u] * yo.w);
+              acc = f4_add(acc, f4_mul(t, w_out));
+              dwout = f4_add(dwout, f4_mul(t, y_self_mf_lane));
+            }
+          }
+        }
+      }
+
+      if (starts_here && ends_here) {
+        if (A.mode != NCF_EMB_NONE) emb_finalize(A, id, acc, xhat, rstd, wrow, gamma, dgamma, dbeta, half, l16);
+      } else {
+        // piece of a run that crosses a chunk border: slot 1 if it continues into the next chunk,
+        // else slot 0 (it came from the previous chunk and ends here)
+        const int slot = ends_here ? 0 : 1;
+        st4(A.partial + ((c * 2 + slot) * 2 + half) * D + 4 * l16, acc);
+      }
+      i = e;
+    }
+  }
+  // LayerNorm affine gradients (half 0 -> mf_norm, half 1 -> mlp_norm) and d mf_output.weight
+  float* dg = A.dense_grad;
+  block_flush(s_red, dgamma, dg ? dg + NCF_OFF(NCF_P_MF_NORM_W) : nullptr, lane, warp, nwarps, half == 0, l16);
+  block_flush(s_red, dgamma, dg ? dg + NCF_OFF(NCF_P_MLP_NORM_W) : nullptr, lane, warp, nwarps, half == 1, l16);
+  block_flush(s_red, dbeta, dg ? dg + NCF_OFF(NCF_P_MF_NORM_B) : nullptr, lane, warp, nwarps, half == 0, l16);
+  block_flush(s_red, dbeta, dg ? dg + NCF_OFF(NCF_P_MLP_NORM_B) : nullptr, lane, warp, nwarps, half == 1, l16);
+  if (A.accumulate_wmf)
+    block_flush(s_red, dwout, dg ? dg + NCF_OFF(NCF_P_MF_OUT_W) : nullptr, lane, warp, nwarps, half == 0, l16);
+}
+
+// Phase 2: a warp per chunk in which a border-crossing run ENDS; adds the run's partials in a fixed
+// order (its own slot 0, then slot 1 of the preceding chunks walking backwards) and finalises.
+__global__ void __launch_bounds__(EB_THREADS) emb_bwd_phase2_kernel(EmbBwdArgs A) {
+  __shared__ float s_red[(EB_THREADS / 32) * 32 * 4];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = EB_THREADS / 32;
+  const int half = lane >> 4, l16 = lane & 15;
+  const int64_t nchunks = (A.N + EB_CHUNK - 1) / EB_CHUNK;
+  const int64_t gw = (int64_t)blockIdx.x * nwarps + warp, gstride = (int64_t)gridDim.x * nwarps;
+  const float4 gamma = ldg4(A.dense + (half ? NCF_OFF(NCF_P_MLP_NORM_W) : NCF_OFF(NCF_P_MF_NORM_W)) + 4 * l16);
+  float4 dgamma = make_float4(0, 0, 0, 0), dbeta = dgamma;
+
+  for (int64_t c = gw; c < nchunks; c += gstride) {
+    if (c == 0) continue;
+    const int64_t p0 = c * EB_CHUNK;
+    const int cnt = (int)min((int64_t)EB_CHUNK, A.N - p0);
+    const uint32_t id = A.sorted_ids[p0];
+    if (A.sorted_ids[p0 - 1] != id) continue;                      // nothing crosses into this chunk
+    const uint32_t last = A.sorted_ids[p0 + cnt - 1];
+    const bool continues = last == id && p0 + cnt < A.N && A.sorted_ids[p0 + cnt] == id;
+    if (continues) continue;                                        // the run ends in a later chunk
+    float4 acc = ld4(A.partial + ((c * 2 + 0) * 2 + half) * D + 4 * l16);
+    for (int64_t cc = c - 1; cc >= 0; --cc) {
+      acc = f4_add(acc, ld4(A.partial + ((cc * 2 + 1) * 2 + half) * D + 4 * l16));
+      const int64_t q0 = cc * EB_CHUNK;
+      if (!(A.sorted_ids[q0] == id && q0 > 0 && A.sorted_ids[q0 - 1] == id)) break;
+    }
+    if (A.mode != NCF_EMB_NONE) {
+      float rstd;
+      const float4 wrow = ld4(A.w[half] + (int64_t)id * D + 4 * l16);
+      const float4 xhat = ln_normalise(wrow, rstd);
+      emb_finalize(A, id, acc, xhat, rstd, wrow, gamma, dgamma, dbeta, half, l16);
+    }
+  }
+  float* dg = A.dense_grad;
+  block_flush(s_red, dgamma, dg ? dg + NCF_OFF(NCF_P_MF_NORM_W) : nullptr, lane, warp, nwarps, half == 0, l16);
+  block_flush(s_red, dgamma, dg ? dg + NCF_OFF(NCF_P_MLP_NORM_W) : nullptr, lane, warp, nwarps, half == 1, l16);
+  block_flush(s_red, dbeta, dg ? dg + NCF_OFF(NCF_P_MF_NORM_B) : nullptr, lane, warp, nwarps, half == 0, l16);
+  block_flush(s_red, dbeta, dg ? dg + NCF_OFF(NCF_P_MLP_NORM_B) : nullptr, lane, warp, nwarps, half == 1, l16);
+}
+
+__global__ void ids_to_keys_kernel(const int64_t* __restrict__ ids, int64_t n, uint32_t* __restrict__ keys,
+                                   int32_t* __restrict__ vals) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    keys[i] = (uint32_t)ids[i];
+    vals[i] = (int32_t)i;
+  }
+}
+
+// every row the step did not touch: g = wd * w (what the reference's dense Adam does, trainer.py:285)
+__global__ void __launch_bounds__(256) emb_adam_sweep_kernel(float* __restrict__ w0, float* __restrict__ m0,
+                                                              float* __restrict__ v0, float* __restrict__ w1,
+                                                              float* __restrict__ m1, float* __restrict__ v1,
+                                                              uint8_t* __restrict__ touched, int64_t rows,
+                                                              AdamScalars s) {
+  const int lane = threadIdx.x & 31, half = lane >> 4, l16 = lane & 15;
+  const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  float* w = half ? w1 : w0;
+  float* m = half ? m1 : m0;
+  float* v = half ? v1 : v0;
+  for (int64_t r = warp; r < rows; r += nwarps) {
+    const uint8_t t = touched ? touched[r] : 0;
+    if (t) {
+      __syncwarp();
+      if (lane == 0) touched[r] = 0;
+      continue;
+    }
+    const int64_t o = r * D + 4 * l16;
+    float4 ww = ld4(w + o), mm = ld4(m + o), vv = ld4(v + o);
+    adam_update4(ww, mm, vv, make_float4(0, 0, 0, 0), s);
+    st4(w + o, ww);
+    st4(m + o, mm);
+    st4(v + o, vv);
+  }
+}
+
+__global__ void dense_adam_kernel(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ m,
+                                  float* __restrict__ v, int64_t n, AdamScalars s) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    float ww = w[i], mm = m[i], vv = v[i];
+    adam_update(ww, mm, vv, g[i], s);
+    w[i] = ww;
+    m[i] = mm;
+    v[i] = vv;
+  }
+}
+
+// TemporalEncoding.forward (architecture.py:86-94)
+__global__ void temporal_fwd_kernel(const float* __restrict__ he, const float* __restrict__ de,
+                                    const float* __restrict__ me, const float* __restrict__ pe,
+                                    const int64_t* __restrict__ hour, const int64_t* __restrict__ day,
+                                    const int64_t* __restrict__ month, const int64_t* __restrict__ days_since,
+                                    int64_t n, float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // one float4 (4 of 32 columns) per thread
+  const int64_t r = i >> 3;
+  const int c = (int)(i & 7) * 4;
+  if (r >= n) return;
+  int64_t ds = days_since[r] % 365;
+  if (ds < 0) ds += 365;  // python modulo
+  float4 a = ldg4(he + hour[r] * TDIM + c);
+  a = f4_add(a, ldg4(de + day[r] * TDIM + c));
+  a = f4_add(a, ldg4(me + month[r] * TDIM + c));
+  a = f4_add(a, ldg4(pe + ds * TDIM + c));
+  st4(out + r * TDIM + c, a);
+}
+
+// forward_simple hour tables: one block per hour (24), 256 threads
+__global__ void temporal_tables_kernel(const float* __restrict__ he, const float* __restrict__ proj_w,
+                                       const float* __restrict__ proj_b, const float* __restrict__ dense,
+                                       float* __restrict__ tmod, float* __restrict__ tail1) {
+  __shared__ float e[TDIM];
+  const int h = blockIdx.x, t = threadIdx.x;
+  if (t < TDIM) e[t] = he[h * TDIM + t];
+  __syncthreads();
+  if (t < D) {
+    float s = proj_b[t];
+    for (int k = 0; k < TDIM; ++k) s = fmaf(e[k], proj_w[t * TDIM + k], s);   // F.linear order: sum_k x_k W[t,k] + b
+    tmod[h * D + t] = 1.0f + 0.3f * s;
+  }
+  if (t < H1) {
+    const float* w0 = dense + NCF_OFF(NCF_P_MLP0_W) + (int64_t)t * K0 + D;
+    float s = 0.f;
+    for (int k = 0; k < TDIM; ++k) s = fmaf(e[k], w0[k], s);
+    tail1[h * H1 + t] = s;
+  }
+}
+
+__global__ void dropout_mask_kernel(DropoutRng rng, int64_t numel, uint8_t* __restrict__ keep) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < numel) keep[i] = rng.keep((uint64_t)i) ? 1 : 0;
+}
+
+}  // namespace ncf
+
+using namespace ncf;
+
+// ---- host entry points ------------------------------------------------------------------------
+extern "C" int ncf_gather_ln_gmf_fwd(const ncf_tables* T, const float* dense, const int64_t* user_ids,
+                                     const int64_t* item_ids, int64_t N, const int64_t* hour, const float* tmod,
+                                     float* mf_pred, float* xu, float* xp, float* y_item_mf, void* stream) {
+  NCF_REQUIRE(T && dense && user_ids && item_ids && mf_pred && xu && xp, "gather_ln_gmf_fwd: null argument");
+  NCF_REQUIRE(N >= 0, "gather_ln_gmf_fwd: N < 0");
+  NCF_REQUIRE(!hour || tmod, "gather_ln_gmf_fwd: hour needs tmod");
+  if (N == 0) return NCF_OK;
+  const int64_t tiles = (N + K1_TILE - 1) / K1_TILE;
+  const int grid = (int)std::min<int64_t>(tiles, (int64_t)num_sms() * 6);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (hour)
+    gather_ln_gmf_fwd_kernel<true><<<grid, K1_THREADS, 0, st>>>(T->w[0], T->w[1], T->w[2], T->w[3], dense, user_ids,
+                                                                item_ids, N, hour, tmod, mf_pred, xu, xp, y_item_mf);
+  else
+    gather_ln_gmf_fwd_kernel<false><<<grid, K1_THREADS, 0, st>>>(T->w[0], T->w[1], T->w[2], T->w[3], dense, user_ids,
+                                                                 item_ids, N, nullptr, nullptr, mf_pred, xu, xp, y_item_mf);
+  NCF_LAUNCH_CHECK();
+  return NCF_OK;
+}
+
+extern "C" int ncf_gather_ln(const ncf_tables* T, const float* dense, int32_t side, const int64_t* ids, int64_t n,
+                             float* mf_out, float* mlp_out, void* stream) {
+  NCF_REQUIRE(T && dense && ids && (side == 0 || side == 1), "gather_ln: bad argument");
+  if (n == 0) return NCF_OK;
+  const int grid = (int)std::min<int64_t>((n + 7) / 8, (int64_t)num_sms() * 8);
+  gather_ln_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(T->w[side], T->w[2 + side], dense, ids, n, mf_out, mlp_out);
+  NCF_LAUNCH_CHECK();
+  return NCF_OK;
+}
+
+static int bits_for(int64_t rows) {
+  int b = 1;
+  while (b < 32 && ((int64_t)1 << b) < rows) ++b;
+  return b;
+}
+
+struct EmbWs {
+  uint32_t *keys_in, *keys_out;
+  int32_t *vals_in, *vals_out;
+  float* partial;
+  void* cub_tmp;
+  size_t cub_bytes;
+  int64_t total;
+};
+static EmbWs carve_emb_ws(void* ws, int64_t N) {
+  EmbWs w;
+  Carver c(ws);
+  w.keys_in = c.take<uint32_t>(N);
+  w.keys_out = c.take<uint32_t>(N);
+  w.vals_in = c.take<int32_t>(N);
+  w.vals_out = c.take<int32_t>(N);
+  const int64_t nchunks = (N + EB_CHUNK - 1) / EB_CHUNK;
+  w.partial = c.take<float>(nchunks * 2 * 2 * D);
+  w.cub_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, w.cub_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr,
+                                  (const int32_t*)nullptr, (int32_t*)nullptr, (int)std::max<int64_t>(N, 1), 0, 32);
+  w.cub_tmp = c.take<char>((int64_t)w.cub_bytes);
+  w.total = align_up(c.used, 256);
+  return w;
+}
+
+extern "C" int64_t ncf_emb_bwd_workspace_bytes(int64_t N) { return carve_emb_ws(nullptr, std::max<int64_t>(N, 1)).total; }
+
+extern "C" int ncf_emb_bwd_adam(const ncf_adam_cfg* adam, const ncf_tables* T, const float* dense, float* dense_grad,
+                                int32_t side, const int64_t* user_ids, const int64_t* item_ids, int64_t N,
+                                const float* d_mf_pred, const float* d_x, const float* other_y_mf, void* workspace,
+                                int64_t workspace_bytes, void* stream) {
+  NCF_REQUIRE(adam && T && dense && user_ids && item_ids && d_mf_pred && d_x, "emb_bwd_adam: null argument");
+  NCF_REQUIRE(side == 0 || side == 1, "emb_bwd_adam: side must be 0 or 1");
+  NCF_REQUIRE(N < ((int64_t)1 << 31), "emb_bwd_adam: N too large");
+  if (N == 0 || adam->emb_mode == NCF_EMB_NONE) return NCF_OK;
+  EmbWs w = carve_emb_ws(workspace, N);
+  if (workspace_bytes < w.total) {
+    set_error("emb_bwd_adam: workspace %lld < %lld", (long long)workspace_bytes, (long long)w.total);
+    return NCF_ERR_WORKSPACE;
+  }
+  const int64_t rows = side ? T->rows_item : T->rows_user;
+  NCF_REQUIRE(rows > 0 && rows < ((int64_t)1 << 32), "emb_bwd_adam: table rows out of range");
+  if (adam->emb_mode == NCF_EMB_MATERIALIZE)
+    NCF_REQUIRE(T->g[side] && T->g[2 + side], "emb_bwd_adam: materialize mode needs tables->g");
+  else
+    NCF_REQUIRE(T->m[side] && T->v[side] && T->m[2 + side] && T->v[2 + side], "emb_bwd_adam: Adam mode needs m and v");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t* ids = side ? item_ids : user_ids;
+  ids_to_keys_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(ids, N, w.keys_in, w.vals_in);
+  NCF_LAUNCH_CHECK();
+  size_t tmp = w.cub_bytes;
+  NCF_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tmp, w.keys_in, w.keys_out, w.vals_in, w.vals_out, (int)N, 0,
+                                           bits_for(rows), st));
+  EmbBwdArgs A;
+  A.w[0] = T->w[side];
+  A.w[1] = T->w[2 + side];
+  A.m[0] = T->m[side];
+  A.m[1] = T->m[2 + side];
+  A.v[0] = T->v[side];
+  A.v[1] = T->v[2 + side];
+  A.g[0] = T->g[side];
+  A.g[1] = T->g[2 + side];
+  A.touched = adam->emb_mode == NCF_EMB_ADAM_DENSE_EQUIV ? T->touched[side] : nullptr;
+  A.other_mf = T->w[side ? 0 : 1];
+  A.other_y = other_y_mf;
+  A.other_ids = side ? user_ids : item_ids;
+  A.sorted_ids = w.keys_out;
+  A.perm = w.vals_out;
+  A.d_mf_pred = d_mf_pred;
+  A.d_x = d_x;
+  A.dense = dense;
+  A.dense_grad = dense_grad;
+  A.partial = w.partial;
+  A.N = N;
+  A.mode = adam->emb_mode;
+  A.accumulate_wmf = side == 0;
+  A.adam = adam_scalars(*adam);
+  if (adam->emb_mode == NCF_EMB_ADAM_DENSE_EQUIV) NCF_REQUIRE(A.touched, "dense-equivalent mode needs tables->touched");
+  const int64_t nchunks = (N + EB_CHUNK - 1) / EB_CHUNK;
+  const int wpb = EB_THREADS / 32;
+  const int grid = (int)std::min<int64_t>((nchunks + wpb - 1) / wpb, (int64_t)num_sms() * 8);
+  emb_bwd_phase1_kernel<<<grid, EB_THREADS, 0, st>>>(A);
+  NCF_LAUNCH_CHECK();
+  emb_bwd_phase2_kernel<<<grid, EB_THREADS, 0, st>>>(A);
+  NCF_LAUNCH_CHECK();
+  return NCF_OK;
+}
+
+extern "C" int ncf_emb_adam_sweep(const ncf_adam_cfg* adam, const ncf_tables* T, void* stream) {
+  NCF_REQUIRE(adam && T, "emb_adam_sweep: null argument");
+  const AdamScalars s = adam_scalars(*adam);
+  for (int side = 0; side < 2; ++side) {
+    const int64_t rows = side ? T->rows_item : T->rows_user;
+    if (rows == 0) continue;
+    NCF_REQUIRE(T->m[side] && T->v[side] && T->m[2 + side] && T->v[2 + side], "emb_adam_sweep: needs m and v");
+    const int grid = (int)std::min<int64_t>((rows + 7) / 8, (int64_t)num_sms() * 8);
+    emb_adam_sweep_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(T->w[side], T->m[side], T->v[side], T->w[2 + side],
+                                                                  T->m[2 + side], T->v[2 + side], T->touched[side],
+                                                                  rows, s);
+    NCF_LAUNCH_CHECK();
+  }
+  return NCF_OK;
+}
+
+extern "C" int ncf_dense_adam(float* w, const float* g, float* m, float* v, int64_t n, const ncf_adam_cfg* adam,
+                              void* stream) {
+  NCF_REQUIRE(w && g && m && v && adam && n >= 0, "dense_adam: bad argument");
+  if (n == 0) return NCF_OK;
+  dense_adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(w, g, m, v, n, adam_scalars(*adam));
+  NCF_LAUNCH_CHECK();
+  return NCF_OK;
+}
+
+extern "C" int ncf_temporal_fwd(const float* he, const float* de, const float* me, const float* pe,
+                                const int64_t* hour, const int64_t* day, const int64_t* month,
+                                const int64_t* days_since, int64_t n, float* out, void* stream) {
+  NCF_REQUIRE(he && de && me && pe && hour && day && month && days_since && out, "temporal_fwd: null argument");
+  if (n == 0) return NCF_OK;
+  const int64_t threads = n * 8;
+  temporal_fwd_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(he, de, me, pe, hour, day,
+                                                                                          month, days_since, n, out);
+  NCF_LAUNCH_CHECK();
+  return NCF_OK;
+}
+
+extern "C" int ncf_temporal_tables(const float* he, const float* proj_w, const float* proj_b, const float* dense,
+                                   float* tmod, float* tail1, void* stream) {
+  NCF_REQUIRE(he && proj_w && proj_b && dense && tmod && tail1, "temporal_tables: null argument");
+  temporal_tables_kernel<<<24, 256, 0, (cudaStream_t)stream>>>(he, proj_w, proj_b, dense, tmod, tail1);
+  NCF_LAUNCH_CHECK();
+  return NCF_OK;
+}
+
+extern "C" int ncf_dropout_mask(const ncf_run_cfg* cfg, int32_t site, int64_t numel, uint8_t* keep, void* stream) {
+  NCF_REQUIRE(cfg && keep && site >= 0 && site < 4 && numel >= 0, "dropout_mask: bad argument");
+  if (numel == 0) return NCF_OK;
+  dropout_mask_kernel<<<(unsigned)((numel + 255) / 256), 256, 0, (cudaStream_t)stream>>>(make_rng(*cfg, site), numel, keep);
+  NCF_LAUNCH_CHECK();
+  return NCF_OK;
+}

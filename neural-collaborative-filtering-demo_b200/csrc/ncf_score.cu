@@ -1,0 +1,356 @@
+// Full-catalogue scoring + deterministic top-k (app.py:43-77), the eval-mode item fold behind it,
+// and the row-wise shard bucketizer.
+//
+// Eval mode attends over ONE key, so softmax == 1 and the MLP tower depends on the item only
+// (architecture.py:275-276, 315-323):  logit(u,i) = LN_mf(U_mf[u]) . P_hat[i] + g[i].
+// ncf_item_fold computes P_hat/g once per catalogue with the regular tower kernels; ncf_score_topk
+// streams P_hat against tiles of users and keeps, per user, the k best (score desc, index asc)
+// in shared memory: candidates that beat the current k-th best are appended to a buffer that is
+// bitonic-merged into the running list when it fills up.
+#include <cub/device/device_radix_sort.cuh>
+
+#include "ncf_tower.cuh"
+
+namespace ncf {
+
+__global__ void iota_kernel(int64_t* p, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = i;
+}
+
+__global__ void item_fold_kernel(const float* __restrict__ ymf, const float* __restrict__ mlp_pred,
+                                 const float* __restrict__ dense, float* __restrict__ p_hat, float* __restrict__ g,
+                                 int64_t I) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // one float4 per thread
+  const int64_t i = t >> 4;
+  const int c = (int)(t & 15) * 4;
+  if (i >= I) return;
+  const float a = __ldg(dense + NCF_OFF(NCF_P_FINAL_W));
+  const float4 w = ldg4(dense + NCF_OFF(NCF_P_MF_OUT_W) + c);
+  const float4 y = ld4(ymf + i * D + c);
+  st4(p_hat + i * D + c, make_float4(a * y.x * w.x, a * y.y * w.y, a * y.z * w.z, a * y.w * w.w));
+  if (c == 0) {
+    const float cc = __ldg(dense + NCF_OFF(NCF_P_FINAL_W) + 1);
+    g[i] = fmaf(a, __ldg(dense + NCF_OFF(NCF_P_MF_OUT_B)), fmaf(cc, mlp_pred[i], __ldg(dense + NCF_OFF(NCF_P_FINAL_B))));
+  }
+}
+
+// ---- top-k -------------------------------------------------------------------------------------
+constexpr int TK_THREADS = 256;
+constexpr int TK_UT = 4;        // users per CTA (share every P_hat row load)
+constexpr int TK_KMAX = 128;    // running list length (k <= 128)
+constexpr int TK_BUF = 512;     // list + candidate buffer, power of two for the bitonic network
+
+// larger key == better: fp32 score bits (scores are positive) then lower item index
+__device__ __forceinline__ unsigned long long tk_key(float score, uint32_t idx) {
+  return ((unsigned long long)__float_as_uint(score) << 32) | (unsigned long long)(0xffffffffu - idx);
+}
+
+// descending bitonic sort of n (power of two) keys in shared memory by the whole CTA
+__device__ void bitonic_sort_desc(unsigned long long* a, int n) {
+  for (int k = 2; k <= n; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      __syncthreads();
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int l = i ^ j;
+        if (l > i) {
+          const unsigned long long x = a[i], y = a[l];
+          const bool desc = (i & k) == 0;
+          if (desc ? x < y : x > y) {
+            a[i] = y;
+            a[l] = x;
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(TK_THREADS) score_topk_kernel(const float* __restrict__ t_umf,
+                                                                const float* __restrict__ dense,
+                                                                const float* __restrict__ p_hat, const float* __restrict__ g,
+                                                                const int64_t* __restrict__ user_ids, int64_t n_users,
+                                                                int64_t I, int nsplit,
+                                                                unsigned long long* __restrict__ part /*[n_users][nsplit][KMAX]*/) {
+  __shared__ __align__(16) float s_u[TK_UT][D];
+  __shared__ unsigned long long s_buf[TK_UT][TK_BUF];
+  __shared__ int s_cnt[TK_UT];
+  __shared__ unsigned long long s_thr[TK_UT];
+  const int64_t u0 = (int64_t)blockIdx.x * TK_UT;
+  const int split = blockIdx.y;
+  const int nu = (int)min((int64_t)TK_UT, n_users - u0);
+
+  // LN_mf of the tile's user rows (64 threads per user; two-pass variance like nn.LayerNorm)
+  {
+    const int uu = threadIdx.x >> 6, c = threadIdx.x & 63;
+    __shared__ float s_tmp[TK_UT][D];
+    float x = 0.f;
+    if (uu < nu) x = t_umf[user_ids[u0 + uu] * D + c];
+    s_tmp[uu][c] = x;
+    __syncthreads();
+    float mean = 0.f;
+    for (int k = 0; k < D; ++k) mean += s_tmp[uu][k];
+    mean *= (1.0f / D);
+    float var = 0.f;
+    for (int k = 0; k < D; ++k) var = fmaf(s_tmp[uu][k] - mean, s_tmp[uu][k] - mean, var);
+    const float rstd = rsqrtf(var * (1.0f / D) + LN_EPS);
+    s_u[uu][c] = fmaf((x - mean) * rstd, __ldg(dense + NCF_OFF(NCF_P_MF_NORM_W) + c), __ldg(dense + NCF_OFF(NCF_P_MF_NORM_B) + c));
+  }
+  for (int i = threadIdx.x; i < TK_UT * TK_BUF; i += TK_THREADS) (&s_buf[0][0])[i] = 0ull;
+  if (threadIdx.x < TK_UT) {
+    s_cnt[threadIdx.x] = TK_KMAX;   // slots [0,KMAX) hold the running list (zeros = empty)
+    s_thr[threadIdx.x] = 0ull;
+  }
+  __syncthreads();
+
+  const int64_t per = (I + nsplit - 1) / nsplit;
+  const int64_t i_begin = split * per, i_end = min(I, i_begin + per);
+  for (int64_t base = i_begin; base < i_end; base += TK_THREADS) {
+    const int64_t i = base + threadIdx.x;
+    if (i < i_end) {
+      float acc[TK_UT];
+#pragma unroll
+      for (int uu = 0; uu < TK_UT; ++uu) acc[uu] = 0.f;
+      const float* row = p_hat + i * D;
+#pragma unroll
+      for (int q = 0; q < D / 4; ++q) {
+        const float4 p = ldg4(row + 4 * q);
+#pragma unroll
+        for (int uu = 0; uu < TK_UT; ++uu) {
+          const float4 uv = *reinterpret_cast<const float4*>(&s_u[uu][4 * q]);
+          acc[uu] = fmaf(uv.x, p.x, acc[uu]);
+          acc[uu] = fmaf(uv.y, p.y, acc[uu]);
+          acc[uu] = fmaf(uv.z, p.z, acc[uu]);
+          acc[uu] = fmaf(uv.w, p.w, acc[uu]);
+        }
+      }
+      const float gi = __ldg(g + i);
+#pragma unroll
+      for (int uu = 0; uu < TK_UT; ++uu) {
+        if (uu < nu) {
+          const float s = 1.0f / (1.0f + expf(-(acc[uu] + gi)));
+          const unsigned long long key = tk_key(s, (uint32_t)i);
+          if (key > s_thr[uu]) {
+            const int pos = atomicAdd(&s_cnt[uu], 1);
+            s_buf[uu][pos] = key;
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // merge any list whose buffer might overflow during the next step
+    for (int uu = 0; uu < nu; ++uu) {
+      if (s_cnt[uu] > TK_BUF - TK_THREADS) {   // uniform: s_cnt read after the barrier
+        bitonic_sort_desc(s_buf[uu], TK_BUF);
+        for (int k = TK_KMAX + threadIdx.x; k < TK_BUF; k += TK_THREADS) s_buf[uu][k] = 0ull;
+        if (threadIdx.x == 0) {
+          s_cnt[uu] = TK_KMAX;
+          s_thr[uu] = s_buf[uu][TK_KMAX - 1];
+        }
+        __syncthreads();
+      }
+    }
+  }
+  for (int uu = 0; uu < nu; ++uu) {
+    bitonic_sort_desc(s_buf[uu], TK_BUF);
+    unsigned long long* dst = part + ((u0 + uu) * nsplit + split) * TK_KMAX;
+    for (int k = threadIdx.x; k < TK_KMAX; k += TK_THREADS) dst[k] = s_buf[uu][k];
+  }
+}
+
+// merge the per-split lists of one user and emit (index, score)
+constexpr int TM_MAX = 4096;
+__global__ void __launch_bounds__(256) topk_merge_kernel(const unsigned long long* __restrict__ part, int nsplit, int k,
+                                                         int64_t* __restrict__ idx_out, float* __restrict__ score_out) {
+  __shared__ unsigned long long s[TM_MAX];
+  const int64_t u = blockIdx.x;
+  const int n = nsplit * TK_KMAX;
+  int n2 = 1;
+  while (n2 < n) n2 <<= 1;
+  for (int i = threadIdx.x; i < n2; i += blockDim.x) s[i] = i < n ? part[u * n + i] : 0ull;
+  bitonic_sort_desc(s, n2);
+  for (int i = threadIdx.x; i < k; i += blockDim.x) {
+    const unsigned long long key = s[i];
+    idx_out[u * k + i] = key == 0ull ? -1 : (int64_t)(0xffffffffu - (uint32_t)(key & 0xffffffffull));
+    score_out[u * k + i] = __uint_as_float((uint32_t)(key >> 32));
+  }
+}
+
+// ---- shard bucketize ---------------------------------------------------------------------------
+__global__ void owner_keys_kernel(const int64_t* __restrict__ ids, int64_t n, int64_t block, uint32_t* __restrict__ keys,
+                                  int32_t* __restrict__ vals) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    keys[i] = (uint32_t)(ids[i] / block);
+    vals[i] = (int32_t)i;
+  }
+}
+__global__ void bucket_finish_kernel(const int64_t* __restrict__ ids, const uint32_t* __restrict__ skeys,
+                                     const int32_t* __restrict__ svals, int64_t n, int64_t block, int world,
+                                     int64_t* __restrict__ counts, int64_t* __restrict__ order,
+                                     int64_t* __restrict__ local_ids) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const int64_t src = svals[i];
+    order[i] = src;
+    local_ids[i] = ids[src] % block;
+  }
+  if (i < world) {   // counts[w] = upper_bound(w) - lower_bound(w) in the sorted owner keys
+    int64_t lo = 0, hi = n;
+    while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (skeys[mid] < (uint32_t)i) lo = mid + 1; else hi = mid; }
+    const int64_t lb = lo;
+    hi = n;
+    while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (skeys[mid] <= (uint32_t)i) lo = mid + 1; else hi = mid; }
+    counts[i] = lo - lb;
+  }
+}
+
+}  // namespace ncf
+
+using namespace ncf;
+
+static ncf_run_cfg eval_cfg() {
+  ncf_run_cfg c{};
+  c.S = 1;
+  c.training = 0;
+  c.precision = NCF_FP32;
+  return c;
+}
+
+struct FoldWs {
+  int64_t* ids;
+  float* ymf;
+  float* out;
+  void* tower;
+  int64_t tower_bytes, total;
+};
+static FoldWs carve_fold(void* ws, int64_t I) {
+  FoldWs f;
+  Carver c(ws);
+  f.ids = c.take<int64_t>(I);
+  f.ymf = c.take<float>(I * D);
+  f.out = c.take<float>(I);
+  f.tower_bytes = carve_tower_ws(nullptr, I, eval_cfg()).total;
+  f.tower = c.take<char>(f.tower_bytes);
+  f.total = align_up(c.used, 256);
+  return f;
+}
+
+extern "C" int64_t ncf_item_fold_workspace_bytes(int64_t I) { return carve_fold(nullptr, std::max<int64_t>(I, 1)).total; }
+
+extern "C" int ncf_item_fold(const ncf_tables* T, const float* dense, float* p_hat, float* g, void* workspace,
+                             int64_t workspace_bytes, void* stream) {
+  NCF_REQUIRE(T && dense && p_hat && g && workspace, "item_fold: null argument");
+  const int64_t I = T->rows_item;
+  NCF_REQUIRE(I > 0 && I < ((int64_t)1 << 31), "item_fold: bad item count");
+  FoldWs f = carve_fold(workspace, I);
+  if (workspace_bytes < f.total) {
+    set_error("item_fold: workspace %lld < %lld", (long long)workspace_bytes, (long long)f.total);
+    return NCF_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const ncf_run_cfg cfg = eval_cfg();
+  TowerWs w = carve_tower_ws(f.tower, I, cfg);
+  iota_kernel<<<(unsigned)((I + 255) / 256), 256, 0, st>>>(f.ids, I);
+  NCF_LAUNCH_CHECK();
+  NCF_TRY(ncf_gather_ln(T, dense, 1, f.ids, I, f.ymf, w.xp, stream));
+  NCF_CUDA(cudaMemsetAsync(w.mf_pred, 0, sizeof(float) * I, st));
+  NCF_TRY(tower_f32_forward(cfg, dense, I, nullptr, nullptr, f.out, w, st));
+  item_fold_kernel<<<(unsigned)((I * 16 + 255) / 256), 256, 0, st>>>(f.ymf, w.mlp_pred, dense, p_hat, g, I);
+  NCF_LAUNCH_CHECK();
+  return NCF_OK;
+}
+
+static int topk_splits(int64_t n_users, int64_t I) {
+  const int64_t tiles = (n_users + TK_UT - 1) / TK_UT;
+  int64_t want = std::max<int64_t>(1, (2 * (int64_t)num_sms() + tiles - 1) / tiles);
+  const int64_t max_by_items = std::max<int64_t>(1, I / (4 * TK_THREADS));
+  want = std::min<int64_t>(std::min<int64_t>(want, max_by_items), TM_MAX / TK_KMAX);
+  return (int)want;
+}
+
+extern "C" int64_t ncf_score_topk_workspace_bytes(int64_t n_users, int64_t I, int32_t k) {
+  (void)k;
+  return align_up(std::max<int64_t>(n_users, 1) * topk_splits(n_users, I) * TK_KMAX * 8, 256);
+}
+
+extern "C" int ncf_score_topk(const ncf_tables* T, const float* dense, const float* p_hat, const float* g,
+                              const int64_t* user_ids, int64_t n_users, int64_t I, int32_t k, int64_t* topk_idx,
+                              float* topk_score, void* workspace, int64_t workspace_bytes, void* stream) {
+  NCF_REQUIRE(T && dense && p_hat && g && user_ids && topk_idx && topk_score && workspace, "score_topk: null argument");
+  NCF_REQUIRE(k >= 1 && k <= TK_KMAX, "score_topk: k=%d outside [1,%d]", k, TK_KMAX);
+  NCF_REQUIRE(I >= 1 && I < ((int64_t)1 << 32) - 1, "score_topk: bad catalogue size");
+  if (n_users == 0) return NCF_OK;
+  const int nsplit = topk_splits(n_users, I);
+  const int64_t need = ncf_score_topk_workspace_bytes(n_users, I, k);
+  if (workspace_bytes < need) {
+    set_error("score_topk: workspace %lld < %lld", (long long)workspace_bytes, (long long)need);
+    return NCF_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned long long* part = static_cast<unsigned long long*>(workspace);
+  const int64_t tiles = (n_users + TK_UT - 1) / TK_UT;
+  NCF_REQUIRE(tiles < ((int64_t)1 << 31), "score_topk: too many users in one call");
+  dim3 grid((unsigned)tiles, nsplit);
+  score_topk_kernel<<<grid, TK_THREADS, 0, st>>>(T->w[0], dense, p_hat, g, user_ids, n_users, I, nsplit, part);
+  NCF_LAUNCH_CHECK();
+  topk_merge_kernel<<<(unsigned)n_users, 256, 0, st>>>(part, nsplit, k, topk_idx, topk_score);
+  NCF_LAUNCH_CHECK();
+  return NCF_OK;
+}
+
+struct BucketWs {
+  uint32_t *keys_in, *keys_out;
+  int32_t *vals_in, *vals_out;
+  void* cub_tmp;
+  size_t cub_bytes;
+  int64_t total;
+};
+static BucketWs carve_bucket(void* ws, int64_t n) {
+  BucketWs b;
+  Carver c(ws);
+  b.keys_in = c.take<uint32_t>(n);
+  b.keys_out = c.take<uint32_t>(n);
+  b.vals_in = c.take<int32_t>(n);
+  b.vals_out = c.take<int32_t>(n);
+  b.cub_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, b.cub_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr,
+                                  (const int32_t*)nullptr, (int32_t*)nullptr, (int)std::max<int64_t>(n, 1), 0, 32);
+  b.cub_tmp = c.take<char>((int64_t)b.cub_bytes);
+  b.total = align_up(c.used, 256);
+  return b;
+}
+
+extern "C" int64_t ncf_shard_bucketize_workspace_bytes(int64_t n, int32_t world) {
+  (void)world;
+  return carve_bucket(nullptr, std::max<int64_t>(n, 1)).total;
+}
+
+extern "C" int ncf_shard_bucketize(const int64_t* ids, int64_t n, int64_t rows, int32_t world, int64_t* counts,
+                                   int64_t* order, int64_t* local_ids, void* workspace, int64_t workspace_bytes,
+                                   void* stream) {
+  NCF_REQUIRE(ids && counts && order && local_ids && workspace, "shard_bucketize: null argument");
+  NCF_REQUIRE(world >= 1 && world <= 1024 && rows >= 1, "shard_bucketize: bad world/rows");
+  NCF_REQUIRE(n >= 0 && n < ((int64_t)1 << 31), "shard_bucketize: bad n");
+  cudaStream_t st = (cudaStream_t)stream;
+  NCF_CUDA(cudaMemsetAsync(counts, 0, sizeof(int64_t) * world, st));
+  if (n == 0) return NCF_OK;
+  BucketWs b = carve_bucket(workspace, n);
+  if (workspace_bytes < b.total) {
+    set_error("shard_bucketize: workspace %lld < %lld", (long long)workspace_bytes, (long long)b.total);
+    return NCF_ERR_WORKSPACE;
+  }
+  const int64_t block = (rows + world - 1) / world;
+  owner_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ids, n, block, b.keys_in, b.vals_in);
+  NCF_LAUNCH_CHECK();
+  int bits = 1;
+  while ((1 << bits) < world) ++bits;
+  size_t tmp = b.cub_bytes;
+  NCF_CUDA(cub::DeviceRadixSort::SortPairs(b.cub_tmp, tmp, b.keys_in, b.keys_out, b.vals_in, b.vals_out, (int)n, 0, bits, st));
+  const int64_t threads = std::max<int64_t>(n, world);
+  bucket_finish_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(ids, b.keys_out, b.vals_out, n, block, world,
+                                                                           counts, order, local_ids);
+  NCF_LAUNCH_CHECK();
+  return NCF_OK;
+}

@@ -1,0 +1,32 @@
+// Internal interface between the C-ABI glue (ncf_abi.cu) and the tower implementations.
+#pragma once
+#include <algorithm>
+
+#include "ncf_common.cuh"
+
+namespace ncf {
+
+// activations kept between forward and backward, carved out of the caller's workspace
+struct TowerWs {
+  float *mf_pred, *mlp_pred, *p_saved;     // [N]
+  float *xu, *xp;                          // [N,64]  mlp_norm(user row), mlp_norm(item row)
+  float *y_pmf;                            // [N,64]  mf_norm(item row), training only
+  float *q, *kv, *ctx, *a;                 // [N,64] [N,128] [N,64] [N,64]
+  float *r1, *y1, *r2, *y2, *r3, *y3;      // relu outputs / layer outputs of the 3 MLP layers
+  // backward scratch (training only)
+  float *d_mf;                             // [N]
+  float *g64a, *g64b, *g128, *g128b, *g256, *g256b;
+  float *dxu, *dxp;                        // aliases set by the backward
+  char* emb;                               // workspace of the fused embedding backward
+  int64_t emb_bytes;
+  int64_t total;
+};
+
+TowerWs carve_tower_ws(void* ws, int64_t N, const ncf_run_cfg& cfg);
+int tower_f32_forward(const ncf_run_cfg& cfg, const float* dense, int64_t N, const int64_t* hour, const float* tail1,
+                      float* out, TowerWs& w, cudaStream_t st);
+int tower_f32_backward(const ncf_run_cfg& cfg, const float* dense, float* dense_grad, int64_t N, const float* grad_out,
+                       TowerWs& w, cudaStream_t st);
+int launch_bce(const float* out, const float* targets, int64_t N, float* loss_out, float* grad_out, cudaStream_t st);
+
+}  // namespace ncf

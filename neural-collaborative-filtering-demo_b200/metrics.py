@@ -1,0 +1,79 @@
+"""Ranking metrics of the reference (`src/utils/metrics.py`), vectorised so they run on the device
+that holds the scores: HR@K, NDCG@K, MRR@K, MAP@K over [batch, 1+neg] groups
+(:110-242), AUC (:244-265, rank-sum form of sklearn.roc_auc_score) and accuracy (:267-275).
+Same keys and argument meaning as `calculate_metrics` (:9-108)."""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+
+
+def calculate_auc(preds: torch.Tensor, targets: torch.Tensor) -> float:
+    preds = preds.reshape(-1).double()
+    pos = targets.reshape(-1) > 0.5
+    n_pos = int(pos.sum())
+    n_neg = preds.numel() - n_pos
+    if n_pos == 0 or n_neg == 0:
+        return float("nan")          # sklearn: undefined with a single class (reference validate() hits this)
+    order = torch.argsort(preds, stable=True)
+    sp = preds[order]
+    _, inv, cnt = torch.unique_consecutive(sp, return_inverse=True, return_counts=True)
+    end = torch.cumsum(cnt, 0).double()
+    avg_rank = ((end - cnt.double() + 1.0 + end) / 2.0)[inv]
+    ranks = torch.empty_like(avg_rank)
+    ranks[order] = avg_rank
+    return float((ranks[pos].sum() - n_pos * (n_pos + 1) / 2.0) / (n_pos * n_neg))
+
+
+def calculate_accuracy(preds: torch.Tensor, targets: torch.Tensor, threshold: float = 0.5) -> float:
+    return float(((preds >= threshold) == (targets > 0.5)).float().mean())
+
+
+def calculate_metrics(predictions: torch.Tensor, targets: torch.Tensor, k_values: List[int] = [1, 5, 10],
+                      batch_size: Optional[int] = None, negative_samples: Optional[int] = None) -> Dict[str, float]:
+    predictions = predictions.detach()
+    targets = targets.detach()
+    if predictions.dim() == 2 and predictions.size(1) == 1:
+        predictions = predictions.squeeze(1)
+    if targets.dim() == 2 and targets.size(1) == 1:
+        targets = targets.squeeze(1)
+    if batch_size is None or negative_samples is None:
+        raise ValueError("Please provide both batch_size and negative_samples "
+                         "to reshape predictions into [batch_size, 1+negative_samples].")
+    M = 1 + negative_samples
+    if predictions.numel() != batch_size * M:
+        raise ValueError(f"Size mismatch: got {predictions.numel()} total preds, "
+                         f"but expected batch_size*M = {batch_size * M}.")
+    P = predictions.reshape(batch_size, M).float()
+    T = targets.reshape(batch_size, M).float()
+    dev = P.device
+    out: Dict[str, float] = {}
+    order = torch.sort(P, dim=1, descending=True).indices
+    rel_sorted = torch.gather(T, 1, order)
+    ideal = torch.sort(T, dim=1, descending=True).values
+    for k in k_values:
+        kk = min(k, M)
+        rel = rel_sorted[:, :kk]
+        pos = torch.arange(1, kk + 1, device=dev, dtype=torch.float32)
+        disc = 1.0 / torch.log2(pos + 1.0)
+        out[f"hit_rate@{k}"] = float((rel.sum(1) > 0).float().mean())
+        dcg = (rel * disc).sum(1)
+        idcg = (ideal[:, :kk] * disc).sum(1)
+        out[f"ndcg@{k}"] = float(torch.where(idcg > 0, dcg / idcg.clamp_min(1e-30), torch.zeros_like(dcg)).mean())
+        is_pos = rel == 1
+        first = torch.where(is_pos, 1.0 / pos, torch.zeros((), device=dev)).max(dim=1).values
+        out[f"mrr@{k}"] = float(first.mean())
+        cum = torch.cumsum(is_pos.float(), dim=1)
+        prec = torch.where(is_pos, cum / pos, torch.zeros((), device=dev)).sum(1)
+        nrel = is_pos.float().sum(1)
+        out[f"map@{k}"] = float(torch.where(nrel > 0, prec / nrel.clamp_min(1.0), torch.zeros_like(prec)).mean())
+    flat_p, flat_t = P.reshape(-1), T.reshape(-1)
+    out["auc"] = calculate_auc(flat_p, flat_t)
+    out["accuracy"] = calculate_accuracy(flat_p, flat_t)
+    pm, nm = flat_t == 1, flat_t == 0
+    if bool(pm.any()):
+        out["pos_accuracy"] = calculate_accuracy(flat_p[pm], flat_t[pm])
+    if bool(nm.any()):
+        out["neg_accuracy"] = calculate_accuracy(flat_p[nm], flat_t[nm])
+    return out

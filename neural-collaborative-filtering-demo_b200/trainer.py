@@ -1,0 +1,255 @@
+"""Training runtime for AdvancedNCF on B200.
+
+`NCFTrainEngine` is the fast path: one call = one iteration of the reference's
+`ModelTrainer.train_epoch` loop body (trainer.py:253-289: forward, BCELoss, zero_grad, backward,
+Adam) executed entirely by libncf_b200.so (`ncf_train_step`), with the dense Adam state in one
+flat buffer and the table update fused into the backward.
+
+`ModelTrainer` mirrors the reference class (same constructor arguments, `train_epoch`, `validate`,
+`train`) for callers that drive the model through `model(features)` / `loss.backward()` /
+`optimizer.step()`; BigQuery loading (trainer.py:164-205) is out of scope - loaders are passed in.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import logging
+import os
+from typing import Any, Dict, List, Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .architecture import AdvancedNCF, _stream
+from .metrics import calculate_metrics
+
+
+class NCFTrainEngine:
+    def __init__(self, model: AdvancedNCF, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
+                 weight_decay: float = 1e-5, table_mode: str = "fused_dense_equiv", max_rows: int = 0):
+        if table_mode not in ("fused_dense_equiv", "fused_sparse"):
+            raise ValueError("the engine updates the tables itself: table_mode must be fused_dense_equiv or fused_sparse")
+        self.model = model
+        self.lib = _lib.load()
+        model._ensure_flat()
+        model.configure_table_optimizer(table_mode, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
+        dev = model._flat.device
+        self.device = dev
+        n = model._flat.numel()
+        self.dense_grad = torch.zeros(n, device=dev)
+        self.dense_m = torch.zeros(n, device=dev)
+        self.dense_v = torch.zeros(n, device=dev)
+        self.loss = torch.zeros(1, device=dev)
+        self.hp = dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay)
+        self.table_mode = table_mode
+        self.step = 0
+        self._ws = None
+        self._out = None
+        self._dev_in = None
+        self.S = 1 + model.negative_samples
+        if max_rows:
+            self._reserve(max_rows)
+
+    def _reserve(self, N):
+        cfg = self._cfg()
+        need = int(self.lib.ncf_workspace_bytes(N, C.byref(cfg)))
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        if self._out is None or self._out.numel() < N:
+            self._out = torch.empty(N, device=self.device)
+
+    def _cfg(self):
+        m = self.model
+        cfg = _lib.RunCfg()
+        cfg.S, cfg.training = self.S, 1
+        cfg.precision = _lib.NCF_BF16_TC if m.compute_precision == "bf16" else _lib.NCF_FP32
+        cfg.dropout_p = float(m.dropout)
+        cfg.seed = m._dropout_seed
+        cfg.step = self.step
+        return cfg
+
+    def train_step(self, user_ids: torch.Tensor, item_ids: torch.Tensor, targets: torch.Tensor) -> torch.Tensor:
+        """ids int64 [N] and targets fp32 [N] on the device; returns the loss as a device scalar
+        (no host sync).  Probabilities of this step stay in `self.outputs`."""
+        N = user_ids.numel()
+        if N % self.S:
+            raise ValueError(f"{N} rows are not groups of {self.S}")
+        self.model._ensure_flat()
+        self.step += 1
+        self._reserve(N)
+        cfg = self._cfg()
+        adam = _lib.AdamCfg()
+        adam.lr, (adam.beta1, adam.beta2) = self.hp["lr"], self.hp["betas"]
+        adam.eps, adam.weight_decay, adam.step = self.hp["eps"], self.hp["weight_decay"], self.step
+        adam.emb_mode = _lib.EMB_ADAM_DENSE_EQUIV if self.table_mode == "fused_dense_equiv" else _lib.EMB_ADAM_SPARSE
+        tables = self.model._tables_struct()
+        _lib.check(self.lib.ncf_train_step(C.byref(cfg), C.byref(adam), C.byref(tables), _lib.ptr(self.model._flat),
+                                           _lib.ptr(self.dense_grad), _lib.ptr(self.dense_m), _lib.ptr(self.dense_v),
+                                           _lib.ptr(user_ids), _lib.ptr(item_ids), _lib.ptr(targets), N,
+                                           _lib.ptr(self._out), _lib.ptr(self.loss), _lib.ptr(self._ws),
+                                           self._ws.numel(), _stream(self.device)), "ncf_train_step")
+        self.model._table_step = self.step
+        self.outputs = self._out[:N]
+        return self.loss
+
+    def train_step_host(self, user_ids: torch.Tensor, item_ids: torch.Tensor, targets: torch.Tensor) -> float:
+        """End-to-end step from HOST (ideally pinned) buffers: H2D copies of the ids and targets,
+        the step, and the D2H read of the loss (what trainer.py:253-254, 289 do per batch)."""
+        N = user_ids.numel()
+        if self._dev_in is None or self._dev_in[0].numel() < N:
+            self._dev_in = (torch.empty(N, dtype=torch.long, device=self.device),
+                            torch.empty(N, dtype=torch.long, device=self.device),
+                            torch.empty(N, dtype=torch.float32, device=self.device))
+        du, di, dt = (b[:N] for b in self._dev_in)
+        du.copy_(user_ids.reshape(-1), non_blocking=True)
+        di.copy_(item_ids.reshape(-1), non_blocking=True)
+        dt.copy_(targets.reshape(-1), non_blocking=True)
+        return float(self.train_step(du, di, dt).item())
+
+    def state_dict(self):
+        return {"step": self.step, "dense_m": self.dense_m.clone(), "dense_v": self.dense_v.clone(),
+                "tables": self.model.table_optimizer_state_dict(), "hp": dict(self.hp)}
+
+    def load_state_dict(self, sd):
+        self.step = int(sd["step"])
+        self.dense_m.copy_(sd["dense_m"])
+        self.dense_v.copy_(sd["dense_v"])
+        self.model.load_table_optimizer_state_dict(sd["tables"])
+
+
+class ModelTrainer:
+    """Mirror of reference ModelTrainer (trainer.py:27-95, 216-546) on the CUDA model."""
+
+    def __init__(self, model: nn.Module, config: Dict[str, Any], num_gpus: int = 1,
+                 table_mode: str = "fused_dense_equiv"):
+        required = {"num_users", "num_products", "batch_size", "learning_rate"}          # trainer.py:36-61
+        missing = required - set(config.keys())
+        if missing:
+            raise ValueError(f"Missing required parameters in config: {missing}")
+        if not torch.cuda.is_available():
+            raise _lib.NcfError("ModelTrainer needs a CUDA device (no CPU fallback)")
+        self.model = model
+        self.config = config
+        self.device = torch.device("cuda")
+        self.num_gpus = num_gpus
+        self.negative_samples = config.get("negative_samples", 4)
+        self.logger = logging.getLogger(__name__)
+        weight_decay = float(config.get("weight_decay", 1e-5))
+        self.model = self.model.to(self.device)
+        self.optimizer = torch.optim.Adam(self.model.parameters(), lr=config["learning_rate"],
+                                          weight_decay=weight_decay)                        # trainer.py:71-75
+        self.criterion = nn.BCELoss().to(self.device)                                       # trainer.py:78
+        if isinstance(self.model, AdvancedNCF):
+            self.model.configure_table_optimizer(table_mode, optimizer=self.optimizer)
+
+    def train_epoch(self, train_loader) -> float:
+        """trainer.py:216-337."""
+        self.model.train()
+        total_loss, num_batches = 0.0, 0
+        for batch_idx, (features, targets) in enumerate(train_loader):
+            base = len(features.lengths()) // len(features.keys())
+            if base < 2:                                                                    # trainer.py:248-250
+                logging.warning(f"Skipping small batch {batch_idx}: size {base}")
+                continue
+            features = features.to(self.device)
+            targets = targets.to(self.device)
+            outputs = self.model(features)
+            if outputs.shape != targets.shape:
+                targets = targets.view(outputs.shape)
+            loss = self.criterion(outputs, targets)
+            self.optimizer.zero_grad()
+            loss.backward()
+            self.optimizer.step()
+            total_loss += loss.item()
+            num_batches += 1
+        avg = total_loss / num_batches if num_batches > 0 else float("inf")
+        logging.info(f"Epoch complete - Average loss: {avg:.4f}")
+        return avg
+
+    def validate(self, val_loader, negative_samples: int = 0) -> Dict[str, float]:
+        """trainer.py:350-410 (metrics stay on the device until the final scalars)."""
+        self.model.eval()
+        total_loss, outs, tgts, nb = 0.0, [], [], 0
+        with torch.no_grad():
+            for features, targets in val_loader:
+                features = features.to(self.device)
+                targets = targets.to(self.device)
+                outputs = self.model(features)
+                total_loss += self.criterion(outputs, targets.view(outputs.shape)).item()
+                outs.append(outputs)
+                tgts.append(targets.view(outputs.shape))
+                nb += 1
+        all_o, all_t = torch.cat(outs, 0), torch.cat(tgts, 0)
+        groups = all_t.numel() // (1 + negative_samples)
+        metrics = calculate_metrics(all_o, all_t, [1, 5, 10], batch_size=groups, negative_samples=negative_samples)
+        metrics["loss"] = total_loss / max(nb, 1)
+        return metrics
+
+    def train(self, train_loader, val_loader, num_epochs: int, early_stopping_patience: int = 5,
+              checkpoint_dir: Optional[str] = None) -> Dict[str, List[float]]:
+        """trainer.py:412-546: epochs, early stopping on validation loss, best/latest checkpoints."""
+        history: Dict[str, List[float]] = {"train_loss": [], "val_loss": []}
+        best, bad = float("inf"), 0
+        start = 0
+        if checkpoint_dir:
+            os.makedirs(checkpoint_dir, exist_ok=True)
+            latest = self._find_latest_checkpoint(checkpoint_dir)
+            if latest:
+                start = self._load_checkpoint(latest) + 1
+        for epoch in range(start, num_epochs):
+            tl = self.train_epoch(train_loader)
+            vm = self.validate(val_loader)
+            history["train_loss"].append(tl)
+            history["val_loss"].append(vm["loss"])
+            for k, v in vm.items():
+                history.setdefault(f"val_{k}", []).append(v)
+            improved = vm["loss"] < best
+            if improved:
+                best, bad = vm["loss"], 0
+            else:
+                bad += 1
+            if checkpoint_dir:
+                self._save_checkpoint(checkpoint_dir, epoch, vm, is_best=improved)
+            if bad >= early_stopping_patience:
+                logging.info(f"Early stopping after {epoch + 1} epochs")
+                break
+        return history
+
+    # checkpoint format of trainer.py:548-609 plus the fused table-optimizer state
+    def _save_checkpoint(self, checkpoint_dir, epoch, metrics, is_best=False):
+        m = self.model
+        ck = {"epoch": epoch, "model_state_dict": m.state_dict(), "optimizer_state_dict": self.optimizer.state_dict(),
+              "metrics": metrics, "config": self.config,
+              "model_config": {k: getattr(m, k) for k in ("num_users", "num_products", "num_departments", "num_categories",
+                                                          "mf_embedding_dim", "temporal_dim", "num_heads") if hasattr(m, k)},
+              "table_optimizer_state": m.table_optimizer_state_dict() if hasattr(m, "table_optimizer_state_dict") else {}}
+        path = os.path.join(checkpoint_dir, f"checkpoint_epoch_{epoch}.pt")
+        torch.save(ck, path)
+        if is_best:
+            best = os.path.join(checkpoint_dir, "best_model.pt")
+            if os.path.lexists(best):
+                os.remove(best)
+            os.symlink(os.path.basename(path), best)
+        return path
+
+    @staticmethod
+    def _find_latest_checkpoint(checkpoint_dir):
+        """the helper the reference calls but never defines (trainer.py:450)."""
+        best, best_e = None, -1
+        for f in os.listdir(checkpoint_dir):
+            if f.startswith("checkpoint_epoch_") and f.endswith(".pt"):
+                try:
+                    e = int(f[len("checkpoint_epoch_"):-3])
+                except ValueError:
+                    continue
+                if e > best_e:
+                    best, best_e = os.path.join(checkpoint_dir, f), e
+        return best
+
+    def _load_checkpoint(self, path) -> int:
+        ck = torch.load(path, map_location=self.device, weights_only=False)
+        self.model.load_state_dict(ck["model_state_dict"])
+        self.optimizer.load_state_dict(ck["optimizer_state_dict"])
+        if hasattr(self.model, "load_table_optimizer_state_dict"):
+            self.model.load_table_optimizer_state_dict(ck.get("table_optimizer_state", {}))
+        return int(ck["epoch"])
