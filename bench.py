@@ -1,0 +1,389 @@
+#!/usr/bin/env python3
+"""Benchmark of the AdvancedNCF training hot path on B200 (contract: see DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c1|c0|c3shard] [--impl reference]
+
+A "step" = one iteration of the reference's ModelTrainer.train_epoch loop body (forward, BCELoss,
+backward, Adam on dense parameters and on the four embedding tables) over one synthetic batch of B
+interactions x (1 + 4 negatives) sample rows.  metric = train sample rows / s.
+  value     inputs already resident in HBM (NCFTrainEngine.train_step)
+  e2e       the same step from pinned HOST buffers: H2D copies of ids+targets and the D2H read of
+            the loss inside the timed region (NCFTrainEngine.train_step_host)
+  roofline  the embedding-path kernels (HBM-bound) and the towers, timed with CUDA events
+  cpu_baseline / --impl reference: the CPU oracle port of the reference step on the host cores
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+WORKLOADS = {
+    # name: (users, items, default interactions per step, description)
+    "c0": (8031, 366, 256, "config[0] shipped shape 8,031 x 366, batch 256 (config.yaml)"),
+    "c1": (6040, 3706, 65536, "config[1] MovieLens-1M shape 6,040 x 3,706"),
+    "c2": (138493, 26744, 65536, "config[2] MovieLens-20M shape 138,493 x 26,744"),
+    "c3shard": (12500000, 1250000, 65536, "1/8 shard of config[3] (100M x 10M over 8 GPUs): 12.5M x 1.25M per GPU"),
+}
+S = 5                      # 1 + negative_samples (config.yaml:65)
+BYTES_FWD_PER_INTERACTION = 3072 + 80          # (2 user + 2*S item rows) * 256 B + ids
+BYTES_BWD_PER_INTERACTION = 18432              # 12 unique rows * (read w,m,v + write w,m,v)
+FLOP_FWD_PER_ROW = 165e3                       # SURVEY 8d dense towers, forward
+FLOP_TRAIN_PER_ROW = 495e3
+
+
+def peaks():
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_batches(users, items, B, nbatch, seed, device=None, pin=False):
+    """Seeded synthetic interactions: users uniform, positive item ~ Zipf(1.0) over a seeded
+    permutation, 4 uniform negatives per positive; rows interaction-major (positive first), targets
+    [1,0,0,0,0] (data_prep.py:210-212, 286-303)."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    perm = torch.randperm(items, generator=g)
+    w = 1.0 / torch.arange(1, items + 1, dtype=torch.float64)
+    cdf = torch.cumsum(w / w.sum(), 0)
+    out = []
+    for _ in range(nbatch):
+        u = torch.randint(0, users, (B,), generator=g).repeat_interleave(S)
+        pos = perm[torch.searchsorted(cdf, torch.rand(B, generator=g, dtype=torch.float64)).clamp_max(items - 1)]
+        it = torch.randint(0, items, (B, S), generator=g)
+        it[:, 0] = pos
+        t = torch.zeros(B, S)
+        t[:, 0] = 1.0
+        trip = (u.contiguous(), it.reshape(-1).contiguous(), t.reshape(-1).contiguous())
+        if device is not None:
+            trip = tuple(x.to(device) for x in trip)
+        elif pin:
+            trip = tuple(x.pin_memory() for x in trip)
+        out.append(trip)
+    return out
+
+
+def build_model(users, items, device, precision):
+    import torch
+    import ncf_b200
+    torch.manual_seed(1234)
+    m = ncf_b200.AdvancedNCF(users, items, 5, 24, 64, 64, 32, [256, 128, 64], 4, 0.2, 4)
+    m.compute_precision = precision
+    return m.to(device).train()
+
+
+def cpu_reference_rate(users, items, B_sample, steps, warmup, threads):
+    """The CPU oracle port of the reference step (oracle/ncf_oracle.py: forward, BCELoss, dense table
+    gradients, torch-Adam update of every row) on the host cores.  Returns (rows/s, ms/step)."""
+    import torch
+    from oracle import ncf_oracle as O
+    torch.set_num_threads(threads)
+    g = torch.Generator().manual_seed(1234)
+    p = {}
+    dims = {"mf_norm": 64, "mlp_norm": 64}
+    for k, rows in zip(O.TABLE_KEYS, (users, items, users, items)):
+        p[k] = (torch.rand(rows, 64, generator=g) * 2 - 1) * (1.0 / rows) ** 0.5
+    shapes = {"mf_norm.weight": (64,), "mf_norm.bias": (64,), "mlp_norm.weight": (64,), "mlp_norm.bias": (64,),
+              "mlp.0.weight": (256, 96), "mlp.0.bias": (256,), "mlp.2.weight": (256,), "mlp.2.bias": (256,),
+              "mlp.4.weight": (128, 256), "mlp.4.bias": (128,), "mlp.6.weight": (128,), "mlp.6.bias": (128,),
+              "mlp.8.weight": (64, 128), "mlp.8.bias": (64,), "mlp.10.weight": (64,), "mlp.10.bias": (64,),
+              "mf_output.weight": (1, 64), "mf_output.bias": (1,), "mlp_output.weight": (1, 64),
+              "mlp_output.bias": (1,), "final.0.weight": (1, 2), "final.0.bias": (1,)}
+    for n in ("q", "k", "v", "out"):
+        shapes[f"user_product_attention.{n}_proj.weight"] = (64, 64)
+        shapes[f"user_product_attention.{n}_proj.bias"] = (64,)
+    for k, shp in shapes.items():
+        p[k] = torch.ones(shp) if (k.endswith("weight") and len(shp) == 1) else (torch.rand(shp, generator=g) - 0.5) * 0.2
+    batches = make_batches(users, items, B_sample, 2, 99)
+    state = {}
+    times = []
+    masks = None
+    for s in range(warmup + steps):
+        u, i, t = batches[s % len(batches)]
+        N = u.numel()
+        masks = {"attn": torch.rand(N // S, 4, S, S, generator=g) >= 0.2, "mlp0": torch.rand(N, 256, generator=g) >= 0.2,
+                 "mlp1": torch.rand(N, 128, generator=g) >= 0.2, "mlp2": torch.rand(N, 64, generator=g) >= 0.2}
+        t0 = time.perf_counter()
+        O.train_step(p, state, s + 1, u, i, t.view(-1, 1), dropout_p=0.2, masks=masks)
+        dt = time.perf_counter() - t0
+        if s >= warmup:
+            times.append(dt)
+    ms = 1e3 * sum(times) / len(times)
+    return B_sample * S / (ms / 1e3), ms
+
+
+def time_kernel(fn, iters, stream_sync):
+    import torch
+    for _ in range(3):
+        fn()
+    stream_sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    e1.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    users, items, B, desc = WORKLOADS[args.workload]
+    B = args.batch or B
+    threads = os.cpu_count() or 1
+    B_sample = min(B, args.ref_batch)
+    rate, ms = cpu_reference_rate(users, items, B_sample, args.steps, args.warmup, threads)
+    line = {"impl": "reference", "metric": "train_samples_per_s", "value": rate, "unit": "samples/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {desc}", "interactions_per_step": B, "rows_per_interaction": S},
+            "cpu_baseline": {"value": rate, "unit": "samples/s", "cores": threads, "kind": "port",
+                             "sample": f"{B_sample} of the {B} interactions of a step, {args.steps} steps"},
+            "e2e": {"value": rate, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="interactions per step per GPU (default per workload)")
+    ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "bf16"])
+    ap.add_argument("--table-mode", default="auto", choices=["auto", "fused_dense_equiv", "fused_sparse"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--ref-batch", type=int, default=4096, help="interactions per CPU-reference step (bounded sample)")
+    ap.add_argument("--cpu-baseline-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import ncf_b200
+    from ncf_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+
+    users, items, B, desc = WORKLOADS[args.workload]
+    B = args.batch or B
+    N = B * S
+    precision = args.precision
+    if precision == "auto":
+        precision = "bf16" if getattr(_lib, "HAS_BF16_TC", False) else "fp32"
+    table_mode = args.table_mode
+    if table_mode == "auto":
+        table_mode = "fused_sparse" if args.workload == "c3shard" else "fused_dense_equiv"
+
+    model = build_model(users, items, dev, precision)
+    eng = ncf_b200.NCFTrainEngine(model, lr=1e-3, weight_decay=1e-5, table_mode=table_mode, max_rows=N)
+    nb = 4
+    dev_batches = make_batches(users, items, B, nb, 1234 + rank, device=dev)
+    host_batches = make_batches(users, items, B, nb, 4321 + rank, pin=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput ("value") ----
+    for s in range(args.warmup):
+        eng.train_step(*dev_batches[s % nb])
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = int(lib.ncf_launch_count())
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for s in range(args.steps):
+        eng.train_step(*dev_batches[s % nb])
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = int(lib.ncf_launch_count()) - launches0
+    last_loss = float(eng.loss.item())
+
+    # ---- end to end from pinned host buffers ("e2e") ----
+    for s in range(3):
+        eng.train_step_host(*host_batches[s % nb])
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        eng.train_step_host(*host_batches[s % nb])
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+
+    t = torch.tensor([ms_total, e2e_s * 1e3], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, e2e_ms_total = float(t[0]), float(t[1])
+    ms_step = ms_total / args.steps
+    value = world * N * args.steps / (ms_total / 1e3)
+    e2e_value = world * N * args.steps / (e2e_ms_total / 1e3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- per-kernel roofline (rank 0, same inputs, CUDA events on the launch stream) ----
+    pk = peaks()
+    u, it, tg = dev_batches[0]
+    tabs = model._tables_struct()
+    st = torch.cuda.current_stream(dev)
+    sync = torch.cuda.synchronize
+    mf = torch.empty(N, device=dev)
+    xu = torch.empty(N, 64, device=dev)
+    xp = torch.empty(N, 64, device=dev)
+    ypm = torch.empty(N, 64, device=dev)
+    sptr = C.c_void_p(st.cuda_stream)
+
+    def k1():
+        _lib.check(lib.ncf_gather_ln_gmf_fwd(C.byref(tabs), _lib.ptr(model._flat), _lib.ptr(u), _lib.ptr(it), N, None,
+                                             None, _lib.ptr(mf), _lib.ptr(xu), _lib.ptr(xp), _lib.ptr(ypm), sptr))
+    k1_ms = time_kernel(k1, 20, sync)
+    k1_bytes = B * BYTES_FWD_PER_INTERACTION
+    adam = _lib.AdamCfg()
+    adam.lr, adam.beta1, adam.beta2, adam.eps, adam.weight_decay = 1e-3, 0.9, 0.999, 1e-8, 1e-5
+    adam.step, adam.emb_mode = 7, _lib.EMB_ADAM_SPARSE
+    ews_bytes = int(lib.ncf_emb_bwd_workspace_bytes(N))
+    ews = torch.empty(ews_bytes, dtype=torch.uint8, device=dev)
+    dgrad = torch.zeros(model._flat.numel(), device=dev)
+    dmf = torch.randn(N, device=dev) * 1e-6
+    dx = torch.randn(N, 64, device=dev) * 1e-6
+
+    def k6():
+        for side, oy in ((1, None), (0, ypm)):
+            _lib.check(lib.ncf_emb_bwd_adam(C.byref(adam), C.byref(tabs), _lib.ptr(model._flat), _lib.ptr(dgrad), side,
+                                            _lib.ptr(u), _lib.ptr(it), N, _lib.ptr(dmf), _lib.ptr(dx), _lib.ptr(oy),
+                                            _lib.ptr(ews), ews_bytes, sptr))
+    k6_ms = time_kernel(k6, 10, sync)
+    k6_bytes = B * BYTES_BWD_PER_INTERACTION
+    emb_ms = k1_ms + k6_ms
+    tower_ms = max(ms_step - emb_ms, 1e-6)
+    tower_tflops = N * FLOP_TRAIN_PER_ROW / (tower_ms / 1e3) / 1e12
+    kernels = {
+        "K1 gather_ln_gmf_fwd": {"ms": k1_ms, "bound": "hbm", "achieved_gbs": k1_bytes / k1_ms / 1e6,
+                                 "frac": k1_bytes / k1_ms / 1e6 / pk["hbm_gbs"]},
+        "K6 emb_bwd_adam (sort + fused scatter/Adam, both sides)": {
+            "ms": k6_ms, "bound": "hbm", "achieved_gbs": k6_bytes / k6_ms / 1e6,
+            "frac": k6_bytes / k6_ms / 1e6 / pk["hbm_gbs"]},
+        "towers fwd+bwd (step - K1 - K6)": {"ms": tower_ms, "bound": "tensor", "achieved_tflops": tower_tflops,
+                                            "frac": tower_tflops / pk["bf16_tflops_sustained"]},
+    }
+    if tower_ms >= emb_ms:
+        roofline = {"kernel": "dense towers fwd+bwd", "bound": "tensor", "achieved": tower_tflops,
+                    "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                    "frac": tower_tflops / pk["bf16_tflops_sustained"], "traffic": None}
+    else:
+        gbs = (k1_bytes + k6_bytes) / emb_ms / 1e6
+        roofline = {"kernel": "embedding path K1+K6", "bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"],
+                    "unit": "GB/s", "frac": gbs / pk["hbm_gbs"], "traffic": None}
+    roofline["peak_source"] = pk["source"] + (" (sustained bf16)" if roofline["bound"] == "tensor" else " (copy)")
+    roofline["kernels"] = kernels
+
+    cpu_baseline = None
+    if not args.no_cpu_baseline and world == 1:
+        threads = os.cpu_count() or 1
+        Bs = min(B, args.ref_batch)
+        rate, ms = cpu_reference_rate(users, items, Bs, args.cpu_baseline_steps, 1, threads)
+        cpu_baseline = {"value": rate, "unit": "samples/s", "cores": threads, "kind": "port", "ms_per_step": ms,
+                        "sample": f"{Bs} of the {B} interactions of a step, {args.cpu_baseline_steps} steps"}
+
+    line = {
+        "metric": "train_samples_per_s", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16" if precision == "bf16" else "fp32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {desc}", "interactions_per_step_per_gpu": B, "rows_per_interaction": S,
+                   "table_update": table_mode, "towers": precision,
+                   "l2": f"inputs larger than L2: activations+ids of one step {N * 4316.8 / 1e6:.0f} MB algorithmic, "
+                         f"{nb} rotating batches"},
+        "interactions_per_s": value / S,
+        "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": N * (8 + 8 + 4), "d2h_bytes_per_step": 4,
+                "ms_per_step": e2e_ms_total / args.steps},
+        "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+        "last_loss": last_loss,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

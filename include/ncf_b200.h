@@ -113,6 +113,7 @@ typedef struct ncf_adam_cfg {
 /* ---- library ------------------------------------------------------------------------- */
 NCF_API int ncf_version(void);
 NCF_API const char* ncf_last_error(void);
+NCF_API int64_t ncf_launch_count(void);   /* kernels this library has launched so far (process-wide) */
 NCF_API int64_t ncf_dense_numel(void);
 NCF_API int64_t ncf_dense_offset(int32_t dense_id);
 NCF_API int64_t ncf_dense_size(int32_t dense_id);

@@ -56,6 +56,7 @@ _I32 = C.c_int32
 _SIGS = {
     "ncf_version": (C.c_int, []),
     "ncf_last_error": (C.c_char_p, []),
+    "ncf_launch_count": (_I64, []),
     "ncf_dense_numel": (_I64, []),
     "ncf_dense_offset": (_I64, [_I32]),
     "ncf_dense_size": (_I64, [_I32]),

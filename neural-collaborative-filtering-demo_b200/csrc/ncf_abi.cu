@@ -6,6 +6,7 @@
 
 namespace ncf {
 static thread_local char g_err[512] = "";
+unsigned long long g_launches = 0;
 void set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -22,6 +23,7 @@ using namespace ncf;
 
 extern "C" int ncf_version(void) { return NCF_ABI_VERSION; }
 extern "C" const char* ncf_last_error(void) { return g_err; }
+extern "C" int64_t ncf_launch_count(void) { return (int64_t)g_launches; }
 extern "C" int64_t ncf_dense_numel(void) { return kLayout.total; }
 extern "C" int64_t ncf_dense_offset(int32_t id) { return id >= 0 && id < NCF_P_COUNT ? kLayout.off[id] : -1; }
 extern "C" int64_t ncf_dense_size(int32_t id) { return id >= 0 && id < NCF_P_COUNT ? kLayout.size[id] : -1; }

@@ -24,7 +24,12 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
     cudaError_t e__ = (call);                                                   \
     if (e__ != cudaSuccess) return ::ncf::cuda_fail(e__, #call, __FILE__, __LINE__); \
   } while (0)
-#define NCF_LAUNCH_CHECK() NCF_CUDA(cudaGetLastError())
+extern unsigned long long g_launches;   // kernels launched by this library (bench.py's gpu_launches)
+#define NCF_LAUNCH_CHECK()          \
+  do {                              \
+    ++::ncf::g_launches;            \
+    NCF_CUDA(cudaGetLastError());   \
+  } while (0)
 #define NCF_REQUIRE(cond, ...)                 \
   do {                                         \
     if (!(cond)) {                             \
