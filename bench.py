@@ -31,6 +31,7 @@ WORKLOADS = {
     "c1": (6040, 3706, 65536, "config[1] MovieLens-1M shape 6,040 x 3,706"),
     "c2": (138493, 26744, 65536, "config[2] MovieLens-20M shape 138,493 x 26,744"),
     "c3shard": (12500000, 1250000, 65536, "1/8 shard of config[3] (100M x 10M over 8 GPUs): 12.5M x 1.25M per GPU"),
+    "c3": (100000000, 10000000, 65536, "config[3] 100M x 10M row-sharded (needs >= 2 GPUs)"),
 }
 S = 5                      # 1 + negative_samples (config.yaml:65)
 BYTES_FWD_PER_INTERACTION = 3072 + 80          # (2 user + 2*S item rows) * 256 B + ids
@@ -249,8 +250,25 @@ def main():
     if table_mode == "auto":
         table_mode = "fused_sparse" if args.workload == "c3shard" else "fused_dense_equiv"
 
-    model = build_model(users, items, dev, precision)
-    eng = ncf_b200.NCFTrainEngine(model, lr=1e-3, weight_decay=1e-5, table_mode=table_mode, max_rows=N)
+    if world > 1:
+        # row-sharded tables: the model object only carries the replicated dense parameters
+        from ncf_b200.sharding import ShardedNCFEngine
+        model = build_model(1, 1, dev, "fp32")
+        precision = "fp32"
+        eng = ShardedNCFEngine(model, users, items, lr=1e-3, weight_decay=1e-5, table_mode=table_mode)
+        dev_in = [torch.empty(N, dtype=torch.long, device=dev), torch.empty(N, dtype=torch.long, device=dev),
+                  torch.empty(N, dtype=torch.float32, device=dev)]
+
+        def step_host(u, i, t):
+            for d, h in zip(dev_in, (u, i, t)):
+                d.copy_(h, non_blocking=True)
+            return float(eng.train_step(*dev_in).item())
+        eng.train_step_host = step_host
+    else:
+        if args.workload == "c3":
+            raise SystemExit("workload c3 (169 GB of tables + Adam state) needs --gpus >= 2")
+        model = build_model(users, items, dev, precision)
+        eng = ncf_b200.NCFTrainEngine(model, lr=1e-3, weight_decay=1e-5, table_mode=table_mode, max_rows=N)
     nb = 4
     dev_batches = make_batches(users, items, B, nb, 1234 + rank, device=dev)
     host_batches = make_batches(users, items, B, nb, 4321 + rank, pin=True)
@@ -300,6 +318,23 @@ def main():
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
+        return
+    if world > 1:
+        line = {
+            "metric": "train_samples_per_s", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {desc}", "interactions_per_step_per_gpu": B,
+                       "rows_per_interaction": S, "table_update": table_mode, "towers": precision,
+                       "parallelism": f"tables row-sharded over {world} GPUs (all-to-all ids/rows/grads), towers "
+                                      f"data-parallel (dense all-reduce)",
+                       "l2": "per-step working set exceeds L2"},
+            "interactions_per_s": value / S,
+            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": N * (8 + 8 + 4),
+                    "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms_total / args.steps},
+            "gpu_launches": launches, "clocks": clocks, "roofline": None, "cpu_baseline": None, "last_loss": last_loss}
+        print(json.dumps(line))
+        dist.destroy_process_group()
         return
 
     # ---- per-kernel roofline (rank 0, same inputs, CUDA events on the launch stream) ----

@@ -222,6 +222,28 @@ NCF_API int ncf_shard_bucketize(const int64_t* ids, int64_t n, int64_t rows, int
                         int64_t* counts, int64_t* perm, int64_t* local_ids,
                         void* workspace, int64_t workspace_bytes, void* stream);
 
+/* ---- row-sharded step: owner-side and requester-side halves ------------------- */
+/* owner: rows [n,128] = [mf_norm(T_mf[id]) | mlp_norm(T_mlp[id])] of its LOCAL ids for one side. */
+NCF_API int ncf_shard_owner_rows(const ncf_tables* local_tables, const float* dense, int32_t side,
+                         const int64_t* local_ids, int64_t n, float* rows, void* stream);
+/* requester: forward on its own N samples from the received rows; sample n uses rows_u[pos_u[n]]
+ * and rows_i[pos_i[n]].  Same workspace contract as ncf_forward. */
+NCF_API int ncf_shard_forward(const ncf_run_cfg* cfg, const float* dense, const float* rows_u, const float* rows_i,
+                      const int64_t* pos_u, const int64_t* pos_i, int64_t N, float* out,
+                      void* workspace, int64_t workspace_bytes, void* stream);
+/* requester: backward; writes the upstream gradient rows [N,128] = [d/d mf_norm row | d/d mlp_norm row]
+ * at the owner-order positions and accumulates the dense gradients (except the LayerNorm affine
+ * gradients of mf_norm / mlp_norm, which the owners add). */
+NCF_API int ncf_shard_backward(const ncf_run_cfg* cfg, const float* dense, float* dense_grad,
+                       const float* rows_u, const float* rows_i, const int64_t* pos_u, const int64_t* pos_i,
+                       int64_t N, const float* grad_out, float* grad_rows_u, float* grad_rows_i,
+                       void* workspace, int64_t workspace_bytes, void* stream);
+/* owner: sorted-id segment sum of the received gradient rows, LayerNorm backward once per unique
+ * local id, fused Adam (adam->emb_mode as in ncf_backward); workspace: ncf_emb_bwd_workspace_bytes(n). */
+NCF_API int ncf_shard_owner_update(const ncf_adam_cfg* adam, const ncf_tables* local_tables, const float* dense,
+                           float* dense_grad, int32_t side, const int64_t* local_ids, int64_t n,
+                           const float* grad_rows, void* workspace, int64_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

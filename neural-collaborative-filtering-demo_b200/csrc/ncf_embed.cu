@@ -239,6 +239,7 @@ struct EmbBwdArgs {
   uint8_t* touched;
   const float* other_mf;          // other side's MF table (for the GMF product), used when other_y == null
   const float* other_y;           // [N,64] LN'd MF row of the other side saved by the forward (or null)
+  const float* upstream;          // sharded owner path: [N,128] ready-made upstream rows [mf | mlp] (or null)
   const int64_t* other_ids;       // other side's ids, original sample order
   const uint32_t* sorted_ids;     // this side's ids, sorted
   const int32_t* perm;            // sample row of each sorted position
@@ -320,8 +321,8 @@ __global__ void __launch_bounds__(EB_THREADS) emb_bwd_phase1_kernel(EmbBwdArgs A
     // lane i holds sorted position p0+i
     const uint32_t my_id = lane < cnt ? A.sorted_ids[p0 + lane] : 0xffffffffu;
     const int32_t my_row = lane < cnt ? A.perm[p0 + lane] : 0;
-    const int64_t my_other = lane < cnt ? A.other_ids[my_row] : 0;
-    const float my_dmf = lane < cnt ? A.d_mf_pred[my_row] : 0.f;
+    const int64_t my_other = (lane < cnt && !A.upstream) ? A.other_ids[my_row] : 0;
+    const float my_dmf = (lane < cnt && !A.upstream) ? A.d_mf_pred[my_row] : 0.f;
     const uint32_t prev_id = p0 > 0 ? A.sorted_ids[p0 - 1] : 0xffffffffu;             // uniform
     const uint32_t next_id = p0 + cnt < A.N ? A.sorted_ids[p0 + cnt] : 0xffffffffu;   // uniform
     const bool has_prev = p0 > 0, has_next = p0 + cnt < A.N;
@@ -359,8 +360,9 @@ __global__ void __launch_bounds__(EB_THREADS) emb_bwd_phase1_kernel(EmbBwdArgs A
           const int32_t row = __shfl_sync(0xffffffffu, my_row, kk);
           const int64_t oid = __shfl_sync(0xffffffffu, my_other, kk);
           dmf[u] = __shfl_sync(0xffffffffu, my_dmf, kk);
-          const float* src = half ? A.d_x + (int64_t)row * D
-                                  : (A.other_y ? A.other_y + (int64_t)row * D : A.other_mf + oid * D);
+          const float* src = A.upstream ? A.upstream + (int64_t)row * 2 * D + half * D
+                             : half ? A.d_x + (int64_t)row * D
+                                    : (A.other_y ? A.other_y + (int64_t)row * D : A.other_mf + oid * D);
           x[u] = ldg4(src + 4 * l16);
         }
 #pragma unroll
@@ -369,7 +371,7 @@ __global__ void __launch_bounds__(EB_THREADS) emb_bwd_phase1_kernel(EmbBwdArgs A
           float4 yo = affine(ln_normalise(x[u], rs), g_mf, b_mf);   // LN of the other side's MF row
           if (A.other_y) yo = x[u];                                  // already normalised by the forward
           if (ok[u]) {
-            if (half) {
+            if (half || A.upstream) {
               acc = f4_add(acc, x[u]);
             } else {
               const float4 t = make_float4(dmf[u] * yo.x, dmf[u] * yo.y, dmf[u] * yo.z, dmf[u] * yo.w);
@@ -603,27 +605,27 @@ static EmbWs carve_emb_ws(void* ws, int64_t N) {
 
 extern "C" int64_t ncf_emb_bwd_workspace_bytes(int64_t N) { return carve_emb_ws(nullptr, std::max<int64_t>(N, 1)).total; }
 
-extern "C" int ncf_emb_bwd_adam(const ncf_adam_cfg* adam, const ncf_tables* T, const float* dense, float* dense_grad,
-                                int32_t side, const int64_t* user_ids, const int64_t* item_ids, int64_t N,
-                                const float* d_mf_pred, const float* d_x, const float* other_y_mf, void* workspace,
-                                int64_t workspace_bytes, void* stream) {
-  NCF_REQUIRE(adam && T && dense && user_ids && item_ids && d_mf_pred && d_x, "emb_bwd_adam: null argument");
-  NCF_REQUIRE(side == 0 || side == 1, "emb_bwd_adam: side must be 0 or 1");
-  NCF_REQUIRE(N < ((int64_t)1 << 31), "emb_bwd_adam: N too large");
+// shared by the single-GPU backward (ids = this side's global ids, per-sample inputs) and the sharded
+// owner update (ids = local row ids, `upstream` = received gradient rows)
+static int run_emb_bwd(const ncf_adam_cfg* adam, const ncf_tables* T, const float* dense, float* dense_grad,
+                       int32_t side, const int64_t* ids, const int64_t* other_ids, int64_t N, const float* d_mf_pred,
+                       const float* d_x, const float* other_y_mf, const float* upstream, void* workspace,
+                       int64_t workspace_bytes, void* stream) {
+  NCF_REQUIRE(side == 0 || side == 1, "emb_bwd: side must be 0 or 1");
+  NCF_REQUIRE(N < ((int64_t)1 << 31), "emb_bwd: N too large");
   if (N == 0 || adam->emb_mode == NCF_EMB_NONE) return NCF_OK;
   EmbWs w = carve_emb_ws(workspace, N);
   if (workspace_bytes < w.total) {
-    set_error("emb_bwd_adam: workspace %lld < %lld", (long long)workspace_bytes, (long long)w.total);
+    set_error("emb_bwd: workspace %lld < %lld", (long long)workspace_bytes, (long long)w.total);
     return NCF_ERR_WORKSPACE;
   }
   const int64_t rows = side ? T->rows_item : T->rows_user;
-  NCF_REQUIRE(rows > 0 && rows < ((int64_t)1 << 32), "emb_bwd_adam: table rows out of range");
+  NCF_REQUIRE(rows > 0 && rows < ((int64_t)1 << 32), "emb_bwd: table rows out of range");
   if (adam->emb_mode == NCF_EMB_MATERIALIZE)
-    NCF_REQUIRE(T->g[side] && T->g[2 + side], "emb_bwd_adam: materialize mode needs tables->g");
+    NCF_REQUIRE(T->g[side] && T->g[2 + side], "emb_bwd: materialize mode needs tables->g");
   else
-    NCF_REQUIRE(T->m[side] && T->v[side] && T->m[2 + side] && T->v[2 + side], "emb_bwd_adam: Adam mode needs m and v");
+    NCF_REQUIRE(T->m[side] && T->v[side] && T->m[2 + side] && T->v[2 + side], "emb_bwd: Adam mode needs m and v");
   cudaStream_t st = (cudaStream_t)stream;
-  const int64_t* ids = side ? item_ids : user_ids;
   ids_to_keys_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(ids, N, w.keys_in, w.vals_in);
   NCF_LAUNCH_CHECK();
   size_t tmp = w.cub_bytes;
@@ -641,7 +643,8 @@ extern "C" int ncf_emb_bwd_adam(const ncf_adam_cfg* adam, const ncf_tables* T, c
   A.touched = adam->emb_mode == NCF_EMB_ADAM_DENSE_EQUIV ? T->touched[side] : nullptr;
   A.other_mf = T->w[side ? 0 : 1];
   A.other_y = other_y_mf;
-  A.other_ids = side ? user_ids : item_ids;
+  A.upstream = upstream;
+  A.other_ids = other_ids;
   A.sorted_ids = w.keys_out;
   A.perm = w.vals_out;
   A.d_mf_pred = d_mf_pred;
@@ -651,7 +654,7 @@ extern "C" int ncf_emb_bwd_adam(const ncf_adam_cfg* adam, const ncf_tables* T, c
   A.partial = w.partial;
   A.N = N;
   A.mode = adam->emb_mode;
-  A.accumulate_wmf = side == 0;
+  A.accumulate_wmf = (side == 0 && !upstream) ? 1 : 0;
   A.adam = adam_scalars(*adam);
   if (adam->emb_mode == NCF_EMB_ADAM_DENSE_EQUIV) NCF_REQUIRE(A.touched, "dense-equivalent mode needs tables->touched");
   const int64_t nchunks = (N + EB_CHUNK - 1) / EB_CHUNK;
@@ -662,6 +665,25 @@ extern "C" int ncf_emb_bwd_adam(const ncf_adam_cfg* adam, const ncf_tables* T, c
   emb_bwd_phase2_kernel<<<grid, EB_THREADS, 0, st>>>(A);
   NCF_LAUNCH_CHECK();
   return NCF_OK;
+}
+
+extern "C" int ncf_emb_bwd_adam(const ncf_adam_cfg* adam, const ncf_tables* T, const float* dense, float* dense_grad,
+                                int32_t side, const int64_t* user_ids, const int64_t* item_ids, int64_t N,
+                                const float* d_mf_pred, const float* d_x, const float* other_y_mf, void* workspace,
+                                int64_t workspace_bytes, void* stream) {
+  NCF_REQUIRE(adam && T && dense && user_ids && item_ids && d_mf_pred && d_x, "emb_bwd_adam: null argument");
+  return run_emb_bwd(adam, T, dense, dense_grad, side, side ? item_ids : user_ids, side ? user_ids : item_ids, N,
+                     d_mf_pred, d_x, other_y_mf, nullptr, workspace, workspace_bytes, stream);
+}
+
+extern "C" int ncf_shard_owner_update(const ncf_adam_cfg* adam, const ncf_tables* T, const float* dense,
+                                      float* dense_grad, int32_t side, const int64_t* local_ids, int64_t n,
+                                      const float* grad_rows, void* workspace, int64_t workspace_bytes, void* stream) {
+  NCF_REQUIRE(adam && T && dense && n >= 0, "shard_owner_update: bad argument");
+  if (n == 0) return NCF_OK;
+  NCF_REQUIRE(local_ids && grad_rows && workspace, "shard_owner_update: null buffer");
+  return run_emb_bwd(adam, T, dense, dense_grad, side, local_ids, nullptr, n, nullptr, nullptr, nullptr, grad_rows,
+                     workspace, workspace_bytes, stream);
 }
 
 extern "C" int ncf_emb_adam_sweep(const ncf_adam_cfg* adam, const ncf_tables* T, void* stream) {

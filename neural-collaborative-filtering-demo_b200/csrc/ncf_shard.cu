@@ -1,0 +1,161 @@
+// Row-sharded embedding path: the tables live on their owner GPUs, the towers stay
+// data-parallel.  Per step and per side (user / item):
+//   requester: bucketize ids by owner -> all-to-all ids                       (ncf_shard_bucketize)
+//   owner:     gather + LayerNorm its rows -> [n,128] = [mf_norm(row) | mlp_norm(row)]
+//              -> all-to-all rows back                                        (ncf_shard_owner_rows)
+//   requester: GMF product + tower forward / backward on its own samples       (ncf_shard_forward,
+//              upstream gradients per sample, packed in owner order             ncf_shard_backward)
+//              -> all-to-all gradient rows to the owners
+//   owner:     sorted-id segment sum of the upstream rows, LayerNorm backward once per unique id,
+//              fused Adam                                                      (ncf_shard_owner_update)
+// LayerNorm is row-local, so it runs at the owner in both directions; its affine gradients and all
+// tower gradients go through one flat all-reduce.
+#include "ncf_tower.cuh"
+
+namespace ncf {
+
+// [n,128] rows of one side for the owner's local ids
+__global__ void __launch_bounds__(256) owner_rows_kernel(const float* __restrict__ t_mf, const float* __restrict__ t_mlp,
+                                                          const float* __restrict__ dense,
+                                                          const int64_t* __restrict__ local_ids, int64_t n,
+                                                          float* __restrict__ rows) {
+  const int lane = threadIdx.x & 31, half = lane >> 4, l16 = lane & 15;
+  const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const float* tab = half ? t_mlp : t_mf;
+  const float4 g = ldg4(dense + (half ? NCF_OFF(NCF_P_MLP_NORM_W) : NCF_OFF(NCF_P_MF_NORM_W)) + 4 * l16);
+  const float4 b = ldg4(dense + (half ? NCF_OFF(NCF_P_MLP_NORM_B) : NCF_OFF(NCF_P_MF_NORM_B)) + 4 * l16);
+  for (int64_t r = warp; r < n; r += nwarps) {
+    const float4 x = ldg4(tab + local_ids[r] * D + 4 * l16);
+    const float mean = half_warp_sum(f4_hsum(x)) * (1.0f / 64.0f);
+    const float4 d = make_float4(x.x - mean, x.y - mean, x.z - mean, x.w - mean);
+    const float rstd = rsqrtf(half_warp_sum(f4_dot(d, d)) * (1.0f / 64.0f) + LN_EPS);
+    st4(rows + r * 2 * D + half * D + 4 * l16,
+        make_float4(fmaf(d.x * rstd, g.x, b.x), fmaf(d.y * rstd, g.y, b.y), fmaf(d.z * rstd, g.z, b.z),
+                    fmaf(d.w * rstd, g.w, b.w)));
+  }
+}
+
+// requester: sample n reads its user rows at rows_u[pos_u[n]] and its item rows at rows_i[pos_i[n]]
+__global__ void __launch_bounds__(256) gmf_from_rows_kernel(const float* __restrict__ rows_u, const float* __restrict__ rows_i,
+                                                            const int64_t* __restrict__ pos_u, const int64_t* __restrict__ pos_i,
+                                                            const float* __restrict__ dense, int64_t N,
+                                                            float* __restrict__ mf_pred, float* __restrict__ xu,
+                                                            float* __restrict__ xp) {
+  const int lane = threadIdx.x & 31, half = lane >> 4, l16 = lane & 15;
+  const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const float4 w_out = ldg4(dense + NCF_OFF(NCF_P_MF_OUT_W) + 4 * l16);
+  const float b_out = __ldg(dense + NCF_OFF(NCF_P_MF_OUT_B));
+  for (int64_t n = warp; n < N; n += nwarps) {
+    const float* src = half ? rows_i + pos_i[n] * 2 * D : rows_u + pos_u[n] * 2 * D;
+    const float4 y_mf = ldg4(src + 4 * l16), y_ml = ldg4(src + D + 4 * l16);
+    const float4 other = make_float4(__shfl_xor_sync(0xffffffffu, y_mf.x, 16), __shfl_xor_sync(0xffffffffu, y_mf.y, 16),
+                                     __shfl_xor_sync(0xffffffffu, y_mf.z, 16), __shfl_xor_sync(0xffffffffu, y_mf.w, 16));
+    const float dot = half_warp_sum(f4_dot(f4_mul(y_mf, other), w_out));
+    if (lane == 0) mf_pred[n] = dot + b_out;
+    st4((half ? xp : xu) + n * D + 4 * l16, y_ml);
+  }
+}
+
+// requester backward: upstream gradient rows per sample, written at the owner-order position.
+//   gu[pos_u[n]] = [ d_mf[n] * w_mf * y_item_mf[n] | dxu[n] ]     gi[pos_i[n]] = [ d_mf[n] * w_mf * y_user_mf[n] | dxp[n] ]
+// and d mf_output.weight += sum_n d_mf[n] * y_user_mf[n] * y_item_mf[n]
+__global__ void __launch_bounds__(256) pack_grads_kernel(const float* __restrict__ rows_u, const float* __restrict__ rows_i,
+                                                         const int64_t* __restrict__ pos_u, const int64_t* __restrict__ pos_i,
+                                                         const float* __restrict__ dense, const float* __restrict__ d_mf,
+                                                         const float* __restrict__ dxu, const float* __restrict__ dxp,
+                                                         int64_t N, float* __restrict__ gu, float* __restrict__ gi,
+                                                         float* __restrict__ dense_grad) {
+  __shared__ float s_red[8][D];
+  const int lane = threadIdx.x & 31, warpi = threadIdx.x >> 5, half = lane >> 4, l16 = lane & 15;
+  const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + warpi;
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const float4 w_out = ldg4(dense + NCF_OFF(NCF_P_MF_OUT_W) + 4 * l16);
+  float4 dw = make_float4(0, 0, 0, 0);
+  for (int64_t n = warp; n < N; n += nwarps) {
+    const int64_t pu = pos_u[n], pi = pos_i[n];
+    const float4 y_mine = ldg4((half ? rows_i + pi * 2 * D : rows_u + pu * 2 * D) + 4 * l16);
+    const float4 y_other = make_float4(__shfl_xor_sync(0xffffffffu, y_mine.x, 16), __shfl_xor_sync(0xffffffffu, y_mine.y, 16),
+                                       __shfl_xor_sync(0xffffffffu, y_mine.z, 16), __shfl_xor_sync(0xffffffffu, y_mine.w, 16));
+    const float g = d_mf[n];
+    const float4 t = make_float4(g * y_other.x, g * y_other.y, g * y_other.z, g * y_other.w);
+    float* dst = half ? gi + pi * 2 * D : gu + pu * 2 * D;
+    st4(dst + 4 * l16, f4_mul(t, w_out));
+    st4(dst + D + 4 * l16, ldg4((half ? dxp : dxu) + n * D + 4 * l16));
+    if (half == 0) dw = f4_add(dw, f4_mul(t, y_mine));
+  }
+  if (half == 0) {
+    s_red[warpi][4 * l16 + 0] = dw.x; s_red[warpi][4 * l16 + 1] = dw.y;
+    s_red[warpi][4 * l16 + 2] = dw.z; s_red[warpi][4 * l16 + 3] = dw.w;
+  }
+  __syncthreads();
+  if (threadIdx.x < D) {
+    float s = 0.f;
+    for (int w = 0; w < 8; ++w) s += s_red[w][threadIdx.x];
+    atomicAdd(dense_grad + NCF_OFF(NCF_P_MF_OUT_W) + threadIdx.x, s);
+  }
+}
+
+}  // namespace ncf
+
+using namespace ncf;
+
+extern "C" int ncf_shard_owner_rows(const ncf_tables* T, const float* dense, int32_t side, const int64_t* local_ids,
+                                    int64_t n, float* rows, void* stream) {
+  NCF_REQUIRE(T && dense && (side == 0 || side == 1) && n >= 0, "shard_owner_rows: bad argument");
+  if (n == 0) return NCF_OK;
+  NCF_REQUIRE(local_ids && rows, "shard_owner_rows: null buffer");
+  const int grid = (int)std::min<int64_t>((n + 7) / 8, (int64_t)num_sms() * 8);
+  owner_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(T->w[side], T->w[2 + side], dense, local_ids, n, rows);
+  NCF_LAUNCH_CHECK();
+  return NCF_OK;
+}
+
+static int check_shard_cfg(const ncf_run_cfg* cfg, int64_t N) {
+  NCF_REQUIRE(cfg, "null run cfg");
+  NCF_REQUIRE(cfg->S >= 1 && cfg->S <= NCF_MAX_S && N >= 0 && N % cfg->S == 0, "bad S / N");
+  NCF_REQUIRE(cfg->precision == NCF_FP32, "sharded path: precision not available");
+  return NCF_OK;
+}
+
+extern "C" int ncf_shard_forward(const ncf_run_cfg* cfg, const float* dense, const float* rows_u, const float* rows_i,
+                                 const int64_t* pos_u, const int64_t* pos_i, int64_t N, float* out, void* workspace,
+                                 int64_t workspace_bytes, void* stream) {
+  NCF_TRY(check_shard_cfg(cfg, N));
+  if (N == 0) return NCF_OK;
+  NCF_REQUIRE(dense && rows_u && rows_i && pos_u && pos_i && out && workspace, "shard_forward: null argument");
+  TowerWs w = carve_tower_ws(workspace, N, *cfg);
+  if (workspace_bytes < w.total) {
+    set_error("shard_forward: workspace %lld < %lld", (long long)workspace_bytes, (long long)w.total);
+    return NCF_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = (int)std::min<int64_t>((N + 7) / 8, (int64_t)num_sms() * 8);
+  gmf_from_rows_kernel<<<grid, 256, 0, st>>>(rows_u, rows_i, pos_u, pos_i, dense, N, w.mf_pred, w.xu, w.xp);
+  NCF_LAUNCH_CHECK();
+  return tower_f32_forward(*cfg, dense, N, nullptr, nullptr, out, w, st);
+}
+
+extern "C" int ncf_shard_backward(const ncf_run_cfg* cfg, const float* dense, float* dense_grad, const float* rows_u,
+                                  const float* rows_i, const int64_t* pos_u, const int64_t* pos_i, int64_t N,
+                                  const float* grad_out, float* grad_rows_u, float* grad_rows_i, void* workspace,
+                                  int64_t workspace_bytes, void* stream) {
+  NCF_TRY(check_shard_cfg(cfg, N));
+  if (N == 0) return NCF_OK;
+  NCF_REQUIRE(dense && dense_grad && rows_u && rows_i && pos_u && pos_i && grad_out && grad_rows_u && grad_rows_i && workspace,
+              "shard_backward: null argument");
+  NCF_REQUIRE(cfg->training, "shard_backward: needs a training-mode forward");
+  TowerWs w = carve_tower_ws(workspace, N, *cfg);
+  if (workspace_bytes < w.total) {
+    set_error("shard_backward: workspace %lld < %lld", (long long)workspace_bytes, (long long)w.total);
+    return NCF_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  NCF_TRY(tower_f32_backward(*cfg, dense, dense_grad, N, grad_out, w, st));
+  const int grid = (int)std::min<int64_t>((N + 7) / 8, (int64_t)num_sms() * 8);
+  pack_grads_kernel<<<grid, 256, 0, st>>>(rows_u, rows_i, pos_u, pos_i, dense, w.d_mf, w.dxu, w.dxp, N, grad_rows_u,
+                                          grad_rows_i, dense_grad);
+  NCF_LAUNCH_CHECK();
+  return NCF_OK;
+}

@@ -1,0 +1,158 @@
+"""Row-sharded path: the all-to-all routing on CPU with gloo (world_size 2), the bit-exact shard
+arithmetic, and (GPU) an emulated 2-rank cluster against the single-GPU engine."""
+import os
+import tempfile
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import ncf_oracle as O
+from tests.helpers import golden_params
+
+
+def test_shard_arithmetic_bit_exact():
+    from ncf_b200.sharding import shard_block, shard_owner_local, shard_rows
+    g = torch.Generator().manual_seed(0)
+    for rows, world in ((100, 8), (138493, 8), (26744, 4), (7, 4), (100_000_000, 8)):
+        ids = torch.randint(0, rows, (1000,), generator=g)
+        owner, local = shard_owner_local(ids, rows, world)
+        ro, rl, block = O.row_shard(ids, rows, world)
+        assert block == shard_block(rows, world)
+        assert torch.equal(owner, ro) and torch.equal(local, rl)
+        assert sum(shard_rows(rows, world, r) for r in range(world)) == rows
+        assert int(owner.max()) < world
+
+
+def _router_worker(rank, world, init_file, rows, ret):
+    from ncf_b200.sharding import ShardRouter, shard_block, shard_owner_local
+    dist.init_process_group("gloo", init_method=f"file://{init_file}", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(100 + rank)
+        block = shard_block(rows, world)
+        table = torch.arange(rows, dtype=torch.float32).unsqueeze(1) * torch.tensor([1.0, -2.0])   # global [rows,2]
+        my_table = table[rank * block:(rank + 1) * block]
+        n = 57 + 13 * rank
+        ids = torch.randint(0, rows, (n,), generator=g)
+        owner, local = shard_owner_local(ids, rows, world)
+        order = torch.argsort(owner, stable=True)              # what ncf_shard_bucketize produces on the GPU
+        counts = torch.bincount(owner, minlength=world)
+        router = ShardRouter()
+        served = router.exchange_ids(local[order], counts)
+        assert served.numel() == sum(router.recv_counts)
+        got = router.return_rows(my_table[served])             # owner lookup, rows routed back
+        pos = torch.empty_like(order)
+        pos[order] = torch.arange(n)
+        assert torch.equal(got[pos], table[ids])               # every sample received ITS row
+        # gradient direction: every requester sends ones; owners segment-sum per local id
+        recv = router.send_rows(torch.ones(n, 1))
+        acc = torch.zeros(my_table.shape[0], 1).index_add_(0, served, recv)
+        all_ids = [torch.empty(57 + 13 * r, dtype=torch.long) for r in range(world)]
+        for r in range(world):
+            gr = torch.Generator().manual_seed(100 + r)
+            all_ids[r] = torch.randint(0, rows, (57 + 13 * r,), generator=gr)
+        want = torch.bincount(torch.cat(all_ids), minlength=rows)[rank * block:(rank + 1) * block].float()
+        assert torch.equal(acc[:, 0], want)
+        ret[rank] = 1
+    finally:
+        dist.destroy_process_group()
+
+
+def test_router_all_to_all_gloo_world2():
+    world = 2
+    with tempfile.TemporaryDirectory() as d:
+        ret = mp.get_context("spawn").Manager().dict()
+        mp.spawn(_router_worker, args=(world, os.path.join(d, "rdzv"), 101, ret), nprocs=world, join=True)
+        assert dict(ret) == {0: 1, 1: 1}
+
+
+# ------------------------------------------------------------------------------------------------
+def _emulated_exchange(per_rank_bufs, per_rank_counts, world):
+    """all-to-all(v) between `world` in-process ranks: rank r's buffer is split by counts[r][o]."""
+    out = []
+    for o in range(world):
+        parts = []
+        for r in range(world):
+            c = per_rank_counts[r]
+            start = sum(c[:o])
+            parts.append(per_rank_bufs[r][start:start + c[o]])
+        out.append(torch.cat(parts))
+    return out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [1, 2, 3])
+def test_emulated_cluster_matches_single_gpu_engine(world):
+    """`world` ShardedNCFEngine ranks driven phase by phase in one process (the exchanges emulated by
+    copies) must reproduce NCFTrainEngine on the concatenated batch: same loss, same weights."""
+    import ncf_b200
+    from ncf_b200.sharding import ShardedNCFEngine
+    U, I, B = 211, 97, 40
+    pg, _ = golden_params()
+    g = torch.Generator().manual_seed(world)
+    p = {k: v.clone() for k, v in pg.items()}
+    for k, rows in zip(O.TABLE_KEYS, (U, I, U, I)):
+        p[k] = (torch.rand(rows, 64, generator=g) * 2 - 1) * (1.0 / rows) ** 0.5
+
+    def fresh():
+        m = ncf_b200.AdvancedNCF(U, I, 5, 24, dropout=0.0)
+        m.load_state_dict(p)
+        return m.cuda().train()
+
+    ref_model = fresh()
+    ref = ncf_b200.NCFTrainEngine(ref_model, table_mode="fused_dense_equiv")
+    models = [fresh() for _ in range(world)]
+    tabs = [p[k] for k in O.TABLE_KEYS]
+    engines = [ShardedNCFEngine(models[r], U, I, table_mode="fused_dense_equiv", init_tables=tabs, rank=r, world=world)
+               for r in range(world)]
+    for step in range(3):
+        batches = []
+        for r in range(world):
+            u = torch.randint(0, U, (B,), generator=g).repeat_interleave(5)
+            i = torch.randint(0, I, (B * 5,), generator=g)
+            t = torch.zeros(B, 5)
+            t[:, 0] = 1
+            batches.append((u.cuda(), i.cuda(), t.reshape(-1).cuda()))
+        ref_loss = ref.train_step(torch.cat([b[0] for b in batches]), torch.cat([b[1] for b in batches]),
+                                  torch.cat([b[2] for b in batches])).clone()
+        plans = [engines[r].phase_bucketize(batches[r][0], batches[r][1]) for r in range(world)]
+        served = [[None, None] for _ in range(world)]
+        counts = [[plans[r][s][1].tolist() for r in range(world)] for s in (0, 1)]
+        for s in (0, 1):
+            ex = _emulated_exchange([plans[r][s][0] for r in range(world)], counts[s], world)
+            for o in range(world):
+                served[o][s] = ex[o]
+        rows_out = [engines[o].phase_owner_rows(served[o]) for o in range(world)]
+        rows = [[None, None] for _ in range(world)]
+        for s in (0, 1):
+            # reverse direction: owner o holds segments ordered by requester r with sizes counts[s][r][o]
+            rev_counts = [[counts[s][r][o] for r in range(world)] for o in range(world)]
+            back = _emulated_exchange([rows_out[o][s] for o in range(world)], rev_counts, world)
+            for r in range(world):
+                rows[r][s] = back[r]
+        grads = [engines[r].phase_forward_backward(rows[r], batches[r][2], world * B * 5) for r in range(world)]
+        recv = [[None, None] for _ in range(world)]
+        for s in (0, 1):
+            ex = _emulated_exchange([grads[r][s] for r in range(world)], counts[s], world)
+            for o in range(world):
+                recv[o][s] = ex[o]
+        for o in range(world):
+            engines[o].phase_owner_update(recv[o])
+        dsum = sum(e.dense_grad for e in engines)
+        lsum = sum(e.loss for e in engines)
+        for e in engines:
+            e.dense_grad.copy_(dsum)
+            e.phase_dense_adam()
+        assert abs(float(lsum) - float(ref_loss)) < 2e-6
+    block_u, block_i = (U + world - 1) // world, (I + world - 1) // world
+    ref_tabs = ref_model._table_params()
+    for k in range(4):
+        full = torch.cat([e.w[k] for e in engines])
+        d = (full - ref_tabs[k].detach()).abs()
+        assert full.shape == ref_tabs[k].shape
+        assert float((d > 5e-6).float().mean()) < 3e-3 and d.max() < 1.5e-3, (k, float(d.max()))
+    d = (models[0]._flat - ref_model._flat).abs()
+    d[ncf_b200._lib.dense_layout()[0][9][1]:ncf_b200._lib.dense_layout()[0][9][1] + 64] = 0   # k_proj.bias: noise
+    assert float((d > 5e-6).float().mean()) < 3e-3 and d.max() < 1.5e-3
+    assert all(torch.equal(models[0]._flat, m._flat) for m in models[1:])
