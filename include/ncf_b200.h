@@ -244,6 +244,10 @@ NCF_API int ncf_shard_owner_update(const ncf_adam_cfg* adam, const ncf_tables* l
                            float* dense_grad, int32_t side, const int64_t* local_ids, int64_t n,
                            const float* grad_rows, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* ---- tensor-core self test: one 128-row tcgen05 GEMM tile in the three operand arrangements the
+ * towers use (0 forward A.B^T, 1 input-gradient A.B, 2 weight-gradient A^T.B); fp32 in/out. */
+NCF_API int ncf_tc_selftest(int32_t mode, int32_t K, int32_t N, const float* A, const float* B, float* D, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
