@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(HERE, "libncf_b200.so")
 NCF_FP32, NCF_BF16_TC = 0, 1
 EMB_NONE, EMB_MATERIALIZE, EMB_ADAM_SPARSE, EMB_ADAM_DENSE_EQUIV = 0, 1, 2, 3
 MAX_S = 8
+HAS_BF16_TC = True
 
 # dense flat layout ids, in ncf_dense_id order, with the reference state_dict key of each
 DENSE_KEYS = (

@@ -34,8 +34,8 @@ static int check_cfg(const ncf_run_cfg* cfg, int64_t N) {
   NCF_REQUIRE(N >= 0 && N % cfg->S == 0, "N=%lld is not a multiple of S=%d (architecture.py:276)", (long long)N, cfg->S);
   NCF_REQUIRE(N < ((int64_t)1 << 31), "N too large");
   NCF_REQUIRE(cfg->dropout_p >= 0.f && cfg->dropout_p < 1.f, "dropout_p outside [0,1)");
-  if (cfg->precision != NCF_FP32) {
-    set_error("precision %d not available in this build", cfg->precision);
+  if (cfg->precision != NCF_FP32 && cfg->precision != NCF_BF16_TC) {
+    set_error("unknown precision %d", cfg->precision);
     return NCF_ERR_UNSUPPORTED;
   }
   return NCF_OK;

@@ -17,6 +17,8 @@ struct TowerWs {
   float *d_mf;                             // [N]
   float *g64a, *g64b, *g128, *g128b, *g256, *g256b;
   float *dxu, *dxp;                        // aliases set by the backward
+  // bf16 tensors of the tcgen05 path (NCF_BF16_TC): saved activations and pre-activation gradients
+  void *r1b, *y1b, *r2b, *y2b, *r3b, *dz1b, *dz2b, *dz3b;
   char* emb;                               // workspace of the fused embedding backward
   int64_t emb_bytes;
   int64_t total;
@@ -27,6 +29,11 @@ int tower_f32_forward(const ncf_run_cfg& cfg, const float* dense, int64_t N, con
                       float* out, TowerWs& w, cudaStream_t st);
 int tower_f32_backward(const ncf_run_cfg& cfg, const float* dense, float* dense_grad, int64_t N, const float* grad_out,
                        TowerWs& w, cudaStream_t st);
+// tcgen05 MLP tower (ncf_tower_tc.cu): forward from w.a (fills w.y3, w.mlp_pred, w.p_saved, out)
+int mlp_tc_forward(const ncf_run_cfg& cfg, const float* dense, int64_t N, const int64_t* hour, const float* tail1,
+                   float* out, TowerWs& w, cudaStream_t st);
+// backward from dy3 = w.g64a (fp32 [N,64]) to da = w.g64a; accumulates the MLP parameter gradients
+int mlp_tc_backward(const ncf_run_cfg& cfg, const float* dense, float* dense_grad, int64_t N, TowerWs& w, cudaStream_t st);
 int launch_bce(const float* out, const float* targets, int64_t N, float* loss_out, float* grad_out, cudaStream_t st);
 
 }  // namespace ncf

@@ -651,6 +651,16 @@ TowerWs carve_tower_ws(void* ws, int64_t N, const ncf_run_cfg& cfg) {
     w.g128b = c.take<float>(N * 2 * D);
     w.g256 = c.take<float>(N * H1);
     w.g256b = c.take<float>(N * H1);
+    if (cfg.precision == NCF_BF16_TC) {
+      w.r1b = c.take<uint16_t>(N * H1);
+      w.y1b = c.take<uint16_t>(N * H1);
+      w.r2b = c.take<uint16_t>(N * H2);
+      w.y2b = c.take<uint16_t>(N * H2);
+      w.r3b = c.take<uint16_t>(N * H3);
+      w.dz1b = c.take<uint16_t>(N * H1);
+      w.dz2b = c.take<uint16_t>(N * H2);
+      w.dz3b = c.take<uint16_t>(N * H3);
+    }
     w.emb_bytes = ncf_emb_bwd_workspace_bytes(N);
     w.emb = c.take<char>(w.emb_bytes);
   }
@@ -675,6 +685,7 @@ int tower_f32_forward(const ncf_run_cfg& cfg, const float* dense, int64_t N, con
     NCF_TRY((launch_linear<64, false, EPI_NONE>(lin(w.xp, D, P + NCF_OFF(NCF_P_V_W), D, P + NCF_OFF(NCF_P_V_B), w.ctx, D, N, D), st)));
   }
   NCF_TRY((launch_linear<64, false, EPI_NONE>(lin(w.ctx, D, P + NCF_OFF(NCF_P_O_W), D, P + NCF_OFF(NCF_P_O_B), w.a, D, N, D), st)));
+  if (cfg.precision == NCF_BF16_TC) return mlp_tc_forward(cfg, dense, N, hour, tail1, out, w, st);
   // MLP: the 32 temporal input columns are zeros in forward (architecture.py:329-340), so only the
   // first 64 columns of mlp.0.weight take part; forward_simple's hour path adds tail1[hour].
   LinearArgs l1 = lin(w.a, D, P + NCF_OFF(NCF_P_MLP0_W), K0, P + NCF_OFF(NCF_P_MLP0_B), w.y1, H1, N, D);

@@ -29,3 +29,64 @@ def test_tc_selftest_tile(mode, K, N):
     torch.cuda.synchronize()
     err = float((D.cpu() - ref).abs().max() / ref.abs().max())
     assert err < 1e-5, f"mode {mode} K {K} N {N}: rel err {err}"
+
+
+def _logit(p):
+    p = p.double().clamp(1e-12, 1 - 1e-12)
+    return torch.log(p / (1 - p))
+
+
+def _model(p, U, I, dropout=0.0):
+    import ncf_b200
+    m = ncf_b200.AdvancedNCF(U, I, 5, 24, dropout=dropout)
+    m.load_state_dict({k: v.clone() for k, v in p.items()}, strict=True)
+    return m.cuda()
+
+
+def test_bf16_tc_eval_forward_matches_fp32_within_2e2():
+    """bf16 tcgen05 MLP tower vs the fp32 path and the oracle: <= 2e-2 relative on logits
+    (BASELINE north_star tolerance for config 2)."""
+    import ncf_b200
+    from ncf_b200.metrics import calculate_auc
+    from tests.helpers import golden_params
+    p, z = golden_params()
+    m = _model(p, 8031, 366).eval()
+    u = torch.from_numpy(z["pred_user_id"]).cuda()
+    i = torch.from_numpy(z["pred_product_id"]).cuda()
+    with torch.no_grad():
+        ref = m(ncf_b200.make_kjt(u, i)).flatten().cpu()
+        m.compute_precision = "bf16"
+        got = m(ncf_b200.make_kjt(u, i)).flatten().cpu()
+        # ragged sizes: 1 row, a tail tile, many tiles
+        for n in (1, 129, 777):
+            a = m(ncf_b200.make_kjt(u[:n], i[:n])).flatten().cpu()
+            assert float((a - got[:n]).abs().max()) < 1e-6
+    gold = torch.from_numpy(z["pred_prediction"])
+    lr, lg = _logit(gold), _logit(got)
+    rel = float((lg - lr).abs().max() / lr.abs().max())
+    assert rel < 2e-2, rel
+    assert float((got - ref).abs().max()) < 5e-3
+    # ranking quality is preserved (matched AUC on the golden labels)
+    lab = torch.from_numpy(z["pred_label"]).float()
+    assert abs(calculate_auc(ref, lab) - calculate_auc(got, lab)) < 5e-3
+
+
+def test_bf16_tc_train_forward_dropout_masks_match_fp32_path():
+    """Same Philox stream in both paths: with dropout on, the bf16 forward equals the fp32 forward up
+    to bf16 rounding (a different mask would show up as O(1) differences)."""
+    import ncf_b200
+    from tests.helpers import golden_params
+    p, _ = golden_params()
+    g = torch.Generator().manual_seed(4)
+    B = 300
+    u = torch.randint(0, 256, (B,), generator=g).repeat_interleave(5).cuda()
+    i = torch.randint(0, 366, (B * 5,), generator=g).cuda()
+    outs = []
+    for prec in ("fp32", "bf16"):
+        m = _model(p, 8031, 366, dropout=0.2).train()
+        m._dropout_seed = 1234
+        m.compute_precision = prec
+        with torch.no_grad():
+            outs.append(m(ncf_b200.make_kjt(u, i)).flatten().cpu())
+    rel = float((_logit(outs[1]) - _logit(outs[0])).abs().max() / _logit(outs[0]).abs().max())
+    assert rel < 3e-2, rel
