@@ -715,6 +715,9 @@ int tower_f32_backward(const ncf_run_cfg& cfg, const float* dense, float* dg, in
   // head: d_mf, dh3 (-> g64a)
   head_bwd_kernel<<<hgrid, 256, 0, st>>>(grad_out, w.p_saved, w.mf_pred, w.mlp_pred, w.y3, P, w.d_mf, w.g64a, dg, N);
   NCF_LAUNCH_CHECK();
+  if (cfg.precision == NCF_BF16_TC) {
+    NCF_TRY(mlp_tc_backward(cfg, dense, dg, N, w, st));   // dy3 (g64a) -> da (g64a), all MLP parameter gradients
+  } else {
   // layer 3: dz3 (g64b); dW8 += dz3^T y2 ; dy2 (g128) = dz3 . W8
   NCF_TRY(launch_relu_ln_drop_bwd<64>(w.g64a, w.r3, P + NCF_OFF(NCF_P_LN2_W), w.g64b, N, make_rng(cfg, 3),
                                       dg + NCF_OFF(NCF_P_LN2_W), dg + NCF_OFF(NCF_P_LN2_B), dg + NCF_OFF(NCF_P_MLP2_B), st));
@@ -730,6 +733,7 @@ int tower_f32_backward(const ncf_run_cfg& cfg, const float* dense, float* dg, in
                                        dg + NCF_OFF(NCF_P_LN0_W), dg + NCF_OFF(NCF_P_LN0_B), dg + NCF_OFF(NCF_P_MLP0_B), st));
   NCF_TRY(launch_wgrad(w.g256b, H1, H1, w.a, D, D, N, dg + NCF_OFF(NCF_P_MLP0_W), K0, nullptr, st));
   NCF_TRY((launch_linear<64, true, EPI_NONE>(lin(w.g256b, H1, P + NCF_OFF(NCF_P_MLP0_W), K0, nullptr, w.g64a, D, N, H1), st)));
+  }
   // out_proj: dWo += da^T ctx, dbo ; dctx (g64b) = da . Wo
   NCF_TRY(launch_wgrad(w.g64a, D, D, w.ctx, D, D, N, dg + NCF_OFF(NCF_P_O_W), D, dg + NCF_OFF(NCF_P_O_B), st));
   NCF_TRY((launch_linear<64, true, EPI_NONE>(lin(w.g64a, D, P + NCF_OFF(NCF_P_O_W), D, nullptr, w.g64b, D, N, D), st)));

@@ -393,9 +393,421 @@ int mlp_tc_forward(const ncf_run_cfg& cfg, const float* dense, int64_t N, const 
   return launch_mlp_tc_fwd(A, st);
 }
 
-int mlp_tc_backward(const ncf_run_cfg&, const float*, float*, int64_t, TowerWs&, cudaStream_t) {
-  set_error("tcgen05 MLP backward is not built yet");
-  return NCF_ERR_UNSUPPORTED;
+// =============================================================================================
+// MLP tower backward, part 1: the input-gradient chain, fused per 128-row tile.
+//   dy3 [N,64] fp32 -> (LN/ReLU/dropout backward) dz3 -> dy2 = dz3.W2 -> dz2 -> dy1 = dz2.W1 -> dz1
+//   -> da = dz1.W0[:, :64]
+// The forward's weight images serve as MN-major B operands (no transposed copies).  dz tiles are
+// written to global memory (bf16) for the weight-gradient kernel; the LayerNorm-affine and bias
+// gradients are column sums reduced with a shuffle transpose and shared-memory atomics.
+// =============================================================================================
+constexpr uint32_t SMB_STAT = SM_PAR + PAR_COUNT * 4;           // 2 x [128][2][2] floats
+constexpr uint32_t SMB_ACC = SMB_STAT + 2 * 128 * 2 * 2 * 4;    // column-sum accumulators
+constexpr int ACC_L0 = 0, ACC_L1 = 768, ACC_L2 = 1152, ACC_COUNT = 1344;   // per layer: [dgamma | dbeta | dbias]
+constexpr uint32_t SMB_TOTAL = SMB_ACC + ACC_COUNT * 4;
+
+struct MlpBwdArgs {
+  const float* dense;
+  float* dense_grad;
+  float* dy3_da;                               // in: dy3 [N,64] fp32; out: da [N,64] fp32 (in place)
+  const __nv_bfloat16 *r1, *r2, *r3;
+  __nv_bfloat16 *dz1, *dz2, *dz3;
+  int64_t N;
+  DropoutRng rng[3];
+};
+
+// lane l ends up with sum over the warp's 32 lanes of v[l]
+__device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = up ? v[i] : v[i + off];
+      const float keep = up ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
+__device__ __forceinline__ void load_bf16x32(const __nv_bfloat16* __restrict__ p, bool live, float (&v)[32]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint4 q4 = make_uint4(0, 0, 0, 0);
+    if (live) q4 = __ldg(reinterpret_cast<const uint4*>(p) + j);
+    float t[8];
+    unpack_bf16x8(q4, t);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[8 * j + i] = t[i];
+  }
+}
+
+template <int C, bool FROM_TMEM>
+__device__ __forceinline__ void mlp_bwd_layer(uint32_t tmem_dy, const float* __restrict__ dy_global, int q, int h, int lane,
+                                              int64_t grow, bool live, const __nv_bfloat16* __restrict__ r_saved,
+                                              const float* __restrict__ gam, const DropoutRng& rng, float* s_statA,
+                                              float* s_statB, float* s_acc, uint8_t* dztile,
+                                              __nv_bfloat16* __restrict__ dz_out) {
+  constexpr int HALF = C / 2, NCH = HALF / 32;
+  const int rt = q * 32 + lane;
+  const uint32_t taddr = tmem_dy + ((uint32_t)(q * 32) << 16) + h * HALF;
+  const __nv_bfloat16* rrow = r_saved + grow * C + h * HALF;
+  // ---- pass A: LayerNorm statistics of the saved relu output -----------------------------------
+  float sum = 0.f, sq = 0.f;
+#pragma unroll 1
+  for (int ch = 0; ch < NCH; ++ch) {
+    float r[32];
+    load_bf16x32(rrow + ch * 32, live, r);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      sum += r[i];
+      sq = fmaf(r[i], r[i], sq);
+    }
+  }
+  s_statA[(rt * 2 + h) * 2 + 0] = sum;
+  s_statA[(rt * 2 + h) * 2 + 1] = sq;
+  __syncthreads();
+  sum += s_statA[(rt * 2 + (h ^ 1)) * 2 + 0];
+  sq += s_statA[(rt * 2 + (h ^ 1)) * 2 + 1];
+  const float mean = sum * (1.0f / C);
+  const float rstd = rsqrtf(fmaxf(sq * (1.0f / C) - mean * mean, 0.f) + LN_EPS);
+
+  auto load_dy = [&](int ch, float (&dy)[32]) {
+    const int c0 = h * HALF + ch * 32;
+    if (FROM_TMEM) {
+      tmem_ld32(taddr + ch * 32, dy);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4 t = make_float4(0, 0, 0, 0);
+        if (live) t = ld4(dy_global + grow * C + c0 + 4 * j);
+        dy[4 * j] = t.x; dy[4 * j + 1] = t.y; dy[4 * j + 2] = t.z; dy[4 * j + 3] = t.w;
+      }
+    }
+    if (!live) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) dy[i] = 0.f;
+    }
+    if (rng.thresh != 0u) {
+#pragma unroll
+      for (int g4 = 0; g4 < 8; ++g4) {
+        const uint4 rnd = rng.draw4(((uint64_t)grow * C + c0 + 4 * g4) >> 2);
+        dy[4 * g4 + 0] = rnd.x >= rng.thresh ? dy[4 * g4 + 0] * rng.scale : 0.f;
+        dy[4 * g4 + 1] = rnd.y >= rng.thresh ? dy[4 * g4 + 1] * rng.scale : 0.f;
+        dy[4 * g4 + 2] = rnd.z >= rng.thresh ? dy[4 * g4 + 2] * rng.scale : 0.f;
+        dy[4 * g4 + 3] = rnd.w >= rng.thresh ? dy[4 * g4 + 3] * rng.scale : 0.f;
+      }
+    }
+  };
+
+  // ---- pass B: row sums of dy*gamma and dy*gamma*xhat; column sums for d gamma / d beta -----------
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+  for (int ch = 0; ch < NCH; ++ch) {
+    const int c0 = h * HALF + ch * 32;
+    float r[32], dy[32];
+    load_bf16x32(rrow + ch * 32, live, r);
+    load_dy(ch, dy);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const float xh = (r[i] - mean) * rstd;
+      const float dyg = dy[i] * gam[c0 + i];
+      s1 += dyg;
+      s2 = fmaf(dyg, xh, s2);
+      r[i] = dy[i] * xh;          // reuse r[] as the d gamma contribution
+    }
+    const float cg = warp_transpose_sum(r, lane);
+    const float cb = warp_transpose_sum(dy, lane);
+    atomicAdd(s_acc + c0 + lane, cg);
+    atomicAdd(s_acc + C + c0 + lane, cb);
+  }
+  s_statB[(rt * 2 + h) * 2 + 0] = s1;
+  s_statB[(rt * 2 + h) * 2 + 1] = s2;
+  __syncthreads();
+  s1 += s_statB[(rt * 2 + (h ^ 1)) * 2 + 0];
+  s2 += s_statB[(rt * 2 + (h ^ 1)) * 2 + 1];
+  const float m1 = s1 * (1.0f / C), m2 = s2 * (1.0f / C);
+
+  // ---- pass C: dz = relu'(r) * LN_backward -> bf16 tile (A operand) + global + bias column sums ----
+#pragma unroll 1
+  for (int ch = 0; ch < NCH; ++ch) {
+    const int c0 = h * HALF + ch * 32;
+    float r[32], dy[32];
+    load_bf16x32(rrow + ch * 32, live, r);
+    load_dy(ch, dy);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const float xh = (r[i] - mean) * rstd;
+      const float dyg = dy[i] * gam[c0 + i];
+      const float dr = rstd * (dyg - m1 - xh * m2);
+      dy[i] = (r[i] > 0.f && live) ? dr : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint4 pk = make_uint4(pack_bf16(dy[8 * j], dy[8 * j + 1]), pack_bf16(dy[8 * j + 2], dy[8 * j + 3]),
+                                  pack_bf16(dy[8 * j + 4], dy[8 * j + 5]), pack_bf16(dy[8 * j + 6], dy[8 * j + 7]));
+      *reinterpret_cast<uint4*>(dztile + tile_off(rt, c0 + 8 * j, C)) = pk;
+      if (live) *reinterpret_cast<uint4*>(dz_out + grow * C + c0 + 8 * j) = pk;
+    }
+    const float cz = warp_transpose_sum(dy, lane);
+    atomicAdd(s_acc + 2 * C + c0 + lane, cz);
+  }
+}
+
+__global__ void __launch_bounds__(TCM_THREADS, 1) mlp_tc_bwd_kernel(MlpBwdArgs A) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q = warp & 3, h = warp >> 2;
+  float* par = reinterpret_cast<float*>(smem + SM_PAR);
+  float* s_statA = reinterpret_cast<float*>(smem + SMB_STAT);
+  float* s_statB = s_statA + 128 * 2 * 2;
+  float* s_acc = reinterpret_cast<float*>(smem + SMB_ACC);
+  const float* P = A.dense;
+
+  load_weight_image<256, 64>(smem + SM_W0, P + NCF_OFF(NCF_P_MLP0_W), K0, tid, TCM_THREADS);
+  load_weight_image<128, 256>(smem + SM_W1, P + NCF_OFF(NCF_P_MLP1_W), H1, tid, TCM_THREADS);
+  load_weight_image<64, 128>(smem + SM_W2, P + NCF_OFF(NCF_P_MLP2_W), H2, tid, TCM_THREADS);
+  for (int i = tid; i < 256; i += TCM_THREADS) {
+    par[PAR_G0 + i] = P[NCF_OFF(NCF_P_LN0_W) + i];
+    if (i < 128) par[PAR_G1 + i] = P[NCF_OFF(NCF_P_LN1_W) + i];
+    if (i < 64) par[PAR_G2 + i] = P[NCF_OFF(NCF_P_LN2_W) + i];
+  }
+  for (int i = tid; i < ACC_COUNT; i += TCM_THREADS) s_acc[i] = 0.f;
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_slot, 512);
+  fence_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t sW0 = smem_addr(smem + SM_W0), sW1 = smem_addr(smem + SM_W1), sW2 = smem_addr(smem + SM_W2);
+  const uint32_t sZ = smem_addr(smem + SM_Y);
+  uint8_t* ztile = smem + SM_Y;
+  uint32_t phase = 0;
+
+  const int64_t ntiles = (A.N + TCM_ROWS - 1) / TCM_ROWS;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t row0 = tile * TCM_ROWS;
+    const int64_t avail = min((int64_t)TCM_ROWS, A.N - row0);
+    const int rt = q * 32 + lane;
+    const int64_t grow = row0 + rt;
+    const bool live = rt < avail;
+    // layer 3 (64 wide): dy3 from global
+    mlp_bwd_layer<64, false>(0, A.dy3_da, q, h, lane, grow, live, A.r3, par + PAR_G2, A.rng[2], s_statA, s_statB,
+                             s_acc + ACC_L2, ztile, A.dz3);
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+      fence_after_sync();   // dy2[128x128] = dz3[128x64] . W2[64x128]
+      issue_gemm(tmem + 0, sZ, 128, 64 * 16, 256, sW2, 128 * 16, 128, 2 * 128 * 16, make_idesc(128, 128, false, true), 4, false);
+      mma_commit(&bar);
+    }
+    mbar_wait(&bar, phase);
+    phase ^= 1;
+    fence_after_sync();
+    mlp_bwd_layer<128, true>(tmem + 0, nullptr, q, h, lane, grow, live, A.r2, par + PAR_G1, A.rng[1], s_statA, s_statB,
+                             s_acc + ACC_L1, ztile, A.dz2);
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+      fence_after_sync();   // dy1[128x256] = dz2[128x128] . W1[128x256]
+      issue_gemm(tmem + 128, sZ, 128, 128 * 16, 256, sW1, 256 * 16, 128, 2 * 256 * 16, make_idesc(128, 256, false, true), 8, false);
+      mma_commit(&bar);
+    }
+    mbar_wait(&bar, phase);
+    phase ^= 1;
+    fence_after_sync();
+    mlp_bwd_layer<256, true>(tmem + 128, nullptr, q, h, lane, grow, live, A.r1, par + PAR_G0, A.rng[0], s_statA, s_statB,
+                             s_acc + ACC_L0, ztile, A.dz1);
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+      fence_after_sync();   // da[128x64] = dz1[128x256] . W0[256x64]
+      issue_gemm(tmem + 384, sZ, 128, 256 * 16, 256, sW0, 64 * 16, 128, 2 * 64 * 16, make_idesc(128, 64, false, true), 16, false);
+      mma_commit(&bar);
+    }
+    mbar_wait(&bar, phase);
+    phase ^= 1;
+    fence_after_sync();
+    {
+      float v[32];
+      tmem_ld32(tmem + 384 + ((uint32_t)(q * 32) << 16) + h * 32, v);
+      if (live) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          st4(A.dy3_da + grow * D + h * 32 + 4 * j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+      }
+    }
+    fence_before_sync();
+    __syncthreads();
+  }
+  __syncthreads();
+  float* dg = A.dense_grad;
+  for (int i = tid; i < ACC_COUNT; i += TCM_THREADS) {
+    int64_t off;
+    int k = i;
+    if (k < ACC_L1) {
+      off = k < 256 ? NCF_OFF(NCF_P_LN0_W) + k : k < 512 ? NCF_OFF(NCF_P_LN0_B) + (k - 256) : NCF_OFF(NCF_P_MLP0_B) + (k - 512);
+    } else if (k < ACC_L2) {
+      k -= ACC_L1;
+      off = k < 128 ? NCF_OFF(NCF_P_LN1_W) + k : k < 256 ? NCF_OFF(NCF_P_LN1_B) + (k - 128) : NCF_OFF(NCF_P_MLP1_B) + (k - 256);
+    } else {
+      k -= ACC_L2;
+      off = k < 64 ? NCF_OFF(NCF_P_LN2_W) + k : k < 128 ? NCF_OFF(NCF_P_LN2_B) + (k - 64) : NCF_OFF(NCF_P_MLP2_B) + (k - 128);
+    }
+    atomicAdd(dg + off, s_acc[i]);
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+// =============================================================================================
+// MLP tower backward, part 2: weight gradients.  Per 128-row tile the saved tiles are read as MN-major
+// operands (K = the 128 rows) and accumulated over ALL tiles of the CTA in TMEM:
+//   dW2^T [128 x 64] += y2^T . dz3      dW1 [128 x 256] += dz2^T . y1      dW0 [256 x 64] += dz1^T . a
+// =============================================================================================
+constexpr uint32_t SMW_Y2 = 0;                         // [128][128] bf16 32 KB
+constexpr uint32_t SMW_Z3 = SMW_Y2 + 128 * 128 * 2;    // [128][64]       16 KB
+constexpr uint32_t SMW_Z2 = SMW_Z3 + 128 * 64 * 2;     // [128][128]      32 KB
+constexpr uint32_t SMW_Y1 = SMW_Z2 + 128 * 128 * 2;    // [128][256]      64 KB
+constexpr uint32_t SMW_Z1 = SMW_Y1 + 128 * 256 * 2;    // [128][256]      64 KB
+constexpr uint32_t SMW_A = SMW_Z1 + 128 * 256 * 2;     // [128][64]       16 KB
+constexpr uint32_t SMW_TOTAL = SMW_A + 128 * 64 * 2;   // 224 KB
+
+struct MlpWgradArgs {
+  const float* a;                                        // [N,64] fp32
+  const __nv_bfloat16 *y1, *y2, *dz1, *dz2, *dz3;
+  float* dense_grad;
+  int64_t N;
+};
+
+__global__ void __launch_bounds__(TCM_THREADS, 1) mlp_tc_wgrad_kernel(MlpWgradArgs A) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q = warp & 3, h = warp >> 2;
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_slot, 512);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t sY2 = smem_addr(smem + SMW_Y2), sZ3 = smem_addr(smem + SMW_Z3), sZ2 = smem_addr(smem + SMW_Z2);
+  const uint32_t sY1 = smem_addr(smem + SMW_Y1), sZ1 = smem_addr(smem + SMW_Z1), sA = smem_addr(smem + SMW_A);
+  uint32_t phase = 0;
+  bool first = true;
+  const int64_t ntiles = (A.N + TCM_ROWS - 1) / TCM_ROWS;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t row0 = tile * TCM_ROWS;
+    const int64_t avail = min((int64_t)TCM_ROWS, A.N - row0);
+    if (!first) {                    // the previous tile's MMAs must have consumed the operand tiles
+      mbar_wait(&bar, phase);
+      phase ^= 1;
+    }
+    fill_tile_bf16<128>(smem + SMW_Y2, A.y2, H2, row0, avail, TCM_ROWS, tid, TCM_THREADS);
+    fill_tile_bf16<64>(smem + SMW_Z3, A.dz3, H3, row0, avail, TCM_ROWS, tid, TCM_THREADS);
+    fill_tile_bf16<128>(smem + SMW_Z2, A.dz2, H2, row0, avail, TCM_ROWS, tid, TCM_THREADS);
+    fill_tile_bf16<256>(smem + SMW_Y1, A.y1, H1, row0, avail, TCM_ROWS, tid, TCM_THREADS);
+    fill_tile_bf16<256>(smem + SMW_Z1, A.dz1, H1, row0, avail, TCM_ROWS, tid, TCM_THREADS);
+    fill_tile_f32<64>(smem + SMW_A, A.a, D, row0, avail, TCM_ROWS, tid, TCM_THREADS);
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+      fence_after_sync();
+      const bool acc = !first;
+      // dW2^T[k_in 128][n_out 64] += y2^T . dz3
+      issue_gemm(tmem + 0, sY2, 128 * 16, 128, 2 * 128 * 16, sZ3, 64 * 16, 128, 2 * 64 * 16, make_idesc(128, 64, true, true), 8, acc);
+      // dW1[n_out 128][k_in 256] += dz2^T . y1
+      issue_gemm(tmem + 64, sZ2, 128 * 16, 128, 2 * 128 * 16, sY1, 256 * 16, 128, 2 * 256 * 16, make_idesc(128, 256, true, true), 8, acc);
+      // dW0[n_out 256][k_in 64] += dz1^T . a   (two M = 128 halves: +16 MN groups = 2048 B)
+      issue_gemm(tmem + 320, sZ1, 256 * 16, 128, 2 * 256 * 16, sA, 64 * 16, 128, 2 * 64 * 16, make_idesc(128, 64, true, true), 8, acc);
+      issue_gemm(tmem + 384, sZ1 + 2048, 256 * 16, 128, 2 * 256 * 16, sA, 64 * 16, 128, 2 * 64 * 16, make_idesc(128, 64, true, true), 8, acc);
+      mma_commit(&bar);
+    }
+    first = false;
+  }
+  if (!first) {
+    mbar_wait(&bar, phase);
+    fence_after_sync();
+    float* dg = A.dense_grad;
+    const int lane_row = q * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    {  // dW2^T: lane = k_in, 64 columns = n_out; this thread's half: 32 columns
+      float v[32];
+      tmem_ld32(tmem + 0 + lane_addr + h * 32, v);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) atomicAdd(dg + NCF_OFF(NCF_P_MLP2_W) + (int64_t)(h * 32 + i) * H2 + lane_row, v[i]);
+    }
+    for (int ch = 0; ch < 4; ++ch) {  // dW1: lane = n_out, 256 columns = k_in; half = 128 columns
+      float v[32];
+      tmem_ld32(tmem + 64 + lane_addr + h * 128 + ch * 32, v);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) atomicAdd(dg + NCF_OFF(NCF_P_MLP1_W) + (int64_t)lane_row * H1 + h * 128 + ch * 32 + i, v[i]);
+    }
+    for (int hh = 0; hh < 2; ++hh) {  // dW0 halves: lane = n_out - 128 hh, 64 columns = k_in; half = 32 columns
+      float v[32];
+      tmem_ld32(tmem + 320 + hh * 64 + lane_addr + h * 32, v);
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        atomicAdd(dg + NCF_OFF(NCF_P_MLP0_W) + (int64_t)(hh * 128 + lane_row) * K0 + h * 32 + i, v[i]);
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+int mlp_tc_backward(const ncf_run_cfg& cfg, const float* dense, float* dense_grad, int64_t N, TowerWs& w, cudaStream_t st) {
+  if (N == 0) return NCF_OK;
+  static bool configured = false;
+  if (!configured) {
+    NCF_CUDA(cudaFuncSetAttribute(mlp_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMB_TOTAL));
+    NCF_CUDA(cudaFuncSetAttribute(mlp_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMW_TOTAL));
+    configured = true;
+  }
+  const int64_t ntiles = (N + TCM_ROWS - 1) / TCM_ROWS;
+  const int grid = (int)std::min<int64_t>(ntiles, num_sms());
+  MlpBwdArgs B{};
+  B.dense = dense;
+  B.dense_grad = dense_grad;
+  B.dy3_da = w.g64a;
+  B.r1 = (const __nv_bfloat16*)w.r1b;
+  B.r2 = (const __nv_bfloat16*)w.r2b;
+  B.r3 = (const __nv_bfloat16*)w.r3b;
+  B.dz1 = (__nv_bfloat16*)w.dz1b;
+  B.dz2 = (__nv_bfloat16*)w.dz2b;
+  B.dz3 = (__nv_bfloat16*)w.dz3b;
+  B.N = N;
+  for (int l = 0; l < 3; ++l) B.rng[l] = make_rng(cfg, 1 + l);
+  mlp_tc_bwd_kernel<<<grid, TCM_THREADS, SMB_TOTAL, st>>>(B);
+  NCF_LAUNCH_CHECK();
+  MlpWgradArgs W{};
+  W.a = w.a;
+  W.y1 = (const __nv_bfloat16*)w.y1b;
+  W.y2 = (const __nv_bfloat16*)w.y2b;
+  W.dz1 = B.dz1;
+  W.dz2 = B.dz2;
+  W.dz3 = B.dz3;
+  W.dense_grad = dense_grad;
+  W.N = N;
+  mlp_tc_wgrad_kernel<<<grid, TCM_THREADS, SMW_TOTAL, st>>>(W);
+  NCF_LAUNCH_CHECK();
+  return NCF_OK;
 }
 
 }  // namespace ncf

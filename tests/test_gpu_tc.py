@@ -90,3 +90,65 @@ def test_bf16_tc_train_forward_dropout_masks_match_fp32_path():
             outs.append(m(ncf_b200.make_kjt(u, i)).flatten().cpu())
     rel = float((_logit(outs[1]) - _logit(outs[0])).abs().max() / _logit(outs[0]).abs().max())
     assert rel < 3e-2, rel
+
+
+@pytest.mark.parametrize("dropout", [0.0, 0.2])
+def test_bf16_tc_backward_gradients_match_fp32_path(dropout):
+    """tcgen05 MLP backward (dgrad chain + wgrad in TMEM) vs the fp32 CUDA path on the same batch and the
+    same dropout stream: every gradient within bf16 tolerance (relative to the tensor's max) and
+    nearly collinear."""
+    import torch.nn as nn
+    import ncf_b200
+    from oracle import ncf_oracle as O
+    from tests.helpers import golden_params
+    p, _ = golden_params()
+    g = torch.Generator().manual_seed(11)
+    B = 1000                                  # 5000 rows: 39 full tiles + a ragged tail
+    u = torch.randint(0, 256, (B,), generator=g).repeat_interleave(5).cuda()
+    i = torch.randint(0, 366, (B * 5,), generator=g).cuda()
+    t = torch.zeros(B, 5)
+    t[:, 0] = 1
+    t = t.reshape(-1, 1).cuda()
+    grads = {}
+    for prec in ("fp32", "bf16"):
+        m = _model(p, 8031, 366, dropout=dropout).train()
+        m._dropout_seed = 99
+        m.compute_precision = prec
+        loss = nn.BCELoss()(m(ncf_b200.make_kjt(u, i)), t)
+        loss.backward()
+        grads[prec] = {k: v.grad.detach().float().cpu().clone() for k, v in m.named_parameters() if v.grad is not None}
+        grads[prec]["__loss__"] = loss.detach().cpu()
+    assert abs(float(grads["fp32"]["__loss__"] - grads["bf16"]["__loss__"])) < 2e-3
+    for k in list(O.ACTIVE_DENSE_KEYS) + list(O.TABLE_KEYS):
+        if k.endswith("k_proj.bias"):
+            continue
+        a, b = grads["fp32"][k].reshape(-1).double(), grads["bf16"][k].reshape(-1).double()
+        rel = float((a - b).abs().max() / a.abs().max().clamp_min(1e-30))
+        cos = float((a @ b) / (a.norm() * b.norm()).clamp_min(1e-30))
+        assert rel < 6e-2 and cos > 0.999, (k, rel, cos)
+
+
+def test_bf16_tc_engine_trains():
+    """ncf_train_step with the tcgen05 towers: loss trajectory tracks the fp32 engine."""
+    import ncf_b200
+    from tests.helpers import golden_params
+    p, _ = golden_params()
+    g = torch.Generator().manual_seed(2)
+    losses = {}
+    for prec in ("fp32", "bf16"):
+        m = _model(p, 8031, 366, dropout=0.0).train()
+        m.compute_precision = prec
+        eng = ncf_b200.NCFTrainEngine(m, lr=1e-3)
+        gg = torch.Generator().manual_seed(3)
+        ls = []
+        for _ in range(6):
+            B = 512
+            u = torch.randint(0, 256, (B,), generator=gg).repeat_interleave(5).cuda()
+            i = torch.randint(0, 366, (B * 5,), generator=gg).cuda()
+            t = torch.zeros(B, 5)
+            t[:, 0] = 1
+            ls.append(float(eng.train_step(u, i, t.reshape(-1).cuda())))
+        losses[prec] = ls
+    for a, b in zip(losses["fp32"], losses["bf16"]):
+        assert abs(a - b) < 5e-3, (losses)
+    assert losses["bf16"][-1] < losses["bf16"][0]
