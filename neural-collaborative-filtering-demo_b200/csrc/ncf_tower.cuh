@@ -34,6 +34,10 @@ int mlp_tc_forward(const ncf_run_cfg& cfg, const float* dense, int64_t N, const 
                    float* out, TowerWs& w, cudaStream_t st);
 // backward from dy3 = w.g64a (fp32 [N,64]) to da = w.g64a; accumulates the MLP parameter gradients
 int mlp_tc_backward(const ncf_run_cfg& cfg, const float* dense, float* dense_grad, int64_t N, TowerWs& w, cudaStream_t st);
+// tcgen05 projections of the attention block (fp32 tensors, bf16 operands)
+int tc_proj_forward(int which, const float* X, const float* W, const float* bias, float* Y, int64_t N, cudaStream_t st);
+int tc_proj_dgrad(int which, const float* dY, const float* W, float* dX, int64_t N, cudaStream_t st);
+int tc_proj_wgrad(int which, const float* Z, const float* X, float* dW, float* db, int64_t N, cudaStream_t st);
 int launch_bce(const float* out, const float* targets, int64_t N, float* loss_out, float* grad_out, cudaStream_t st);
 
 }  // namespace ncf

@@ -673,18 +673,29 @@ int tower_f32_forward(const ncf_run_cfg& cfg, const float* dense, int64_t N, con
   const bool train = cfg.training != 0;
   const int S = cfg.S;
   const float* P = dense;
+  const bool tc = cfg.precision == NCF_BF16_TC;
   if (train || S > 1) {
     // q = q_proj(xu); [k|v] = [k_proj; v_proj](xp)        (architecture.py:40-42)
-    NCF_TRY((launch_linear<64, false, EPI_NONE>(lin(w.xu, D, P + NCF_OFF(NCF_P_Q_W), D, P + NCF_OFF(NCF_P_Q_B), w.q, D, N, D), st)));
-    NCF_TRY((launch_linear<128, false, EPI_NONE>(lin(w.xp, D, P + NCF_OFF(NCF_P_K_W), D, P + NCF_OFF(NCF_P_K_B), w.kv, 2 * D, N, D), st)));
+    if (tc) {
+      NCF_TRY(tc_proj_forward(0, w.xu, P + NCF_OFF(NCF_P_Q_W), P + NCF_OFF(NCF_P_Q_B), w.q, N, st));
+      NCF_TRY(tc_proj_forward(1, w.xp, P + NCF_OFF(NCF_P_K_W), P + NCF_OFF(NCF_P_K_B), w.kv, N, st));
+    } else {
+      NCF_TRY((launch_linear<64, false, EPI_NONE>(lin(w.xu, D, P + NCF_OFF(NCF_P_Q_W), D, P + NCF_OFF(NCF_P_Q_B), w.q, D, N, D), st)));
+      NCF_TRY((launch_linear<128, false, EPI_NONE>(lin(w.xp, D, P + NCF_OFF(NCF_P_K_W), D, P + NCF_OFF(NCF_P_K_B), w.kv, 2 * D, N, D), st)));
+    }
     const int64_t threads = N * HEADS;
     attn_core_fwd_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(w.q, w.kv, w.ctx, N, S, make_rng(cfg, 0));
     NCF_LAUNCH_CHECK();
+  } else if (tc) {
+    NCF_TRY(tc_proj_forward(0, w.xp, P + NCF_OFF(NCF_P_V_W), P + NCF_OFF(NCF_P_V_B), w.ctx, N, st));
   } else {
     // one key per query: softmax == 1, ctx = v_proj(xp)      (architecture.py:275-276)
     NCF_TRY((launch_linear<64, false, EPI_NONE>(lin(w.xp, D, P + NCF_OFF(NCF_P_V_W), D, P + NCF_OFF(NCF_P_V_B), w.ctx, D, N, D), st)));
   }
-  NCF_TRY((launch_linear<64, false, EPI_NONE>(lin(w.ctx, D, P + NCF_OFF(NCF_P_O_W), D, P + NCF_OFF(NCF_P_O_B), w.a, D, N, D), st)));
+  if (tc)
+    NCF_TRY(tc_proj_forward(0, w.ctx, P + NCF_OFF(NCF_P_O_W), P + NCF_OFF(NCF_P_O_B), w.a, N, st));
+  else
+    NCF_TRY((launch_linear<64, false, EPI_NONE>(lin(w.ctx, D, P + NCF_OFF(NCF_P_O_W), D, P + NCF_OFF(NCF_P_O_B), w.a, D, N, D), st)));
   if (cfg.precision == NCF_BF16_TC) return mlp_tc_forward(cfg, dense, N, hour, tail1, out, w, st);
   // MLP: the 32 temporal input columns are zeros in forward (architecture.py:329-340), so only the
   // first 64 columns of mlp.0.weight take part; forward_simple's hour path adds tail1[hour].
@@ -734,18 +745,31 @@ int tower_f32_backward(const ncf_run_cfg& cfg, const float* dense, float* dg, in
   NCF_TRY(launch_wgrad(w.g256b, H1, H1, w.a, D, D, N, dg + NCF_OFF(NCF_P_MLP0_W), K0, nullptr, st));
   NCF_TRY((launch_linear<64, true, EPI_NONE>(lin(w.g256b, H1, P + NCF_OFF(NCF_P_MLP0_W), K0, nullptr, w.g64a, D, N, H1), st)));
   }
+  const bool tc = cfg.precision == NCF_BF16_TC;
   // out_proj: dWo += da^T ctx, dbo ; dctx (g64b) = da . Wo
-  NCF_TRY(launch_wgrad(w.g64a, D, D, w.ctx, D, D, N, dg + NCF_OFF(NCF_P_O_W), D, dg + NCF_OFF(NCF_P_O_B), st));
-  NCF_TRY((launch_linear<64, true, EPI_NONE>(lin(w.g64a, D, P + NCF_OFF(NCF_P_O_W), D, nullptr, w.g64b, D, N, D), st)));
+  if (tc) {
+    NCF_TRY(tc_proj_wgrad(0, w.g64a, w.ctx, dg + NCF_OFF(NCF_P_O_W), dg + NCF_OFF(NCF_P_O_B), N, st));
+    NCF_TRY(tc_proj_dgrad(0, w.g64a, P + NCF_OFF(NCF_P_O_W), w.g64b, N, st));
+  } else {
+    NCF_TRY(launch_wgrad(w.g64a, D, D, w.ctx, D, D, N, dg + NCF_OFF(NCF_P_O_W), D, dg + NCF_OFF(NCF_P_O_B), st));
+    NCF_TRY((launch_linear<64, true, EPI_NONE>(lin(w.g64a, D, P + NCF_OFF(NCF_P_O_W), D, nullptr, w.g64b, D, N, D), st)));
+  }
   // attention core: dq (g64a), dkv (g128)
   const int64_t threads = N * HEADS;
   attn_core_bwd_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(w.q, w.kv, w.g64b, w.g64a, w.g128, N, S, make_rng(cfg, 0));
   NCF_LAUNCH_CHECK();
   // projections: weights/biases, then dxu (g64b) = dq . Wq and dxp (g256 reused as [N,64]) = dkv . [Wk;Wv]
-  NCF_TRY(launch_wgrad(w.g64a, D, D, w.xu, D, D, N, dg + NCF_OFF(NCF_P_Q_W), D, dg + NCF_OFF(NCF_P_Q_B), st));
-  NCF_TRY(launch_wgrad(w.g128, 2 * D, 2 * D, w.xp, D, D, N, dg + NCF_OFF(NCF_P_K_W), D, dg + NCF_OFF(NCF_P_K_B), st));
-  NCF_TRY((launch_linear<64, true, EPI_NONE>(lin(w.g64a, D, P + NCF_OFF(NCF_P_Q_W), D, nullptr, w.g64b, D, N, D), st)));
-  NCF_TRY((launch_linear<64, true, EPI_NONE>(lin(w.g128, 2 * D, P + NCF_OFF(NCF_P_K_W), D, nullptr, w.g256, D, N, 2 * D), st)));
+  if (tc) {
+    NCF_TRY(tc_proj_wgrad(0, w.g64a, w.xu, dg + NCF_OFF(NCF_P_Q_W), dg + NCF_OFF(NCF_P_Q_B), N, st));
+    NCF_TRY(tc_proj_wgrad(1, w.g128, w.xp, dg + NCF_OFF(NCF_P_K_W), dg + NCF_OFF(NCF_P_K_B), N, st));
+    NCF_TRY(tc_proj_dgrad(0, w.g64a, P + NCF_OFF(NCF_P_Q_W), w.g64b, N, st));
+    NCF_TRY(tc_proj_dgrad(1, w.g128, P + NCF_OFF(NCF_P_K_W), w.g256, N, st));
+  } else {
+    NCF_TRY(launch_wgrad(w.g64a, D, D, w.xu, D, D, N, dg + NCF_OFF(NCF_P_Q_W), D, dg + NCF_OFF(NCF_P_Q_B), st));
+    NCF_TRY(launch_wgrad(w.g128, 2 * D, 2 * D, w.xp, D, D, N, dg + NCF_OFF(NCF_P_K_W), D, dg + NCF_OFF(NCF_P_K_B), st));
+    NCF_TRY((launch_linear<64, true, EPI_NONE>(lin(w.g64a, D, P + NCF_OFF(NCF_P_Q_W), D, nullptr, w.g64b, D, N, D), st)));
+    NCF_TRY((launch_linear<64, true, EPI_NONE>(lin(w.g128, 2 * D, P + NCF_OFF(NCF_P_K_W), D, nullptr, w.g256, D, N, 2 * D), st)));
+  }
   w.dxu = w.g64b;
   w.dxp = w.g256;
   return NCF_OK;

@@ -370,6 +370,234 @@ int launch_mlp_tc_fwd(const MlpFwdArgs& A, cudaStream_t st) {
   return NCF_OK;
 }
 
+// =============================================================================================
+// Generic tcgen05 linear layers for the attention projections (q, k|v, out):
+//   tc_linear_kernel<K, NOUT, false>:  Y[N,NOUT] = X[N,K] . W[NOUT,K]^T + b      (nn.Linear forward)
+//   tc_linear_kernel<K, NOUT, true> :  Y[N,NOUT] = X[N,K] . W[K,NOUT]            (input gradient dX = dY . W)
+//   tc_wgrad64_kernel<CZ>           :  dW[CZ,64] += Z[N,CZ]^T . X[N,64],  db[CZ] += colsum(Z)
+// fp32 tensors in global memory, bf16 operands in shared memory, fp32 accumulation in TMEM.  Several
+// CTAs per SM hide the load -> MMA -> store latency of the short per-tile pipeline.
+// =============================================================================================
+template <int K, int NOUT, bool DGRAD>
+__global__ void __launch_bounds__(TCM_THREADS, 2) tc_linear_kernel(const float* __restrict__ X, const float* __restrict__ W,
+                                                                   const float* __restrict__ bias, float* __restrict__ Y,
+                                                                   int64_t N) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  constexpr int WR = DGRAD ? K : NOUT, WC = DGRAD ? NOUT : K;     // stored weight image [WR][WC]
+  constexpr uint32_t OFF_X = WR * WC * 2;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q = warp & 3, h = warp >> 2;
+  fill_tile_f32<WC>(smem, W, WC, 0, WR, WR, tid, TCM_THREADS);
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_slot, NOUT < 32 ? 32 : NOUT);
+  fence_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t sW = smem_addr(smem), sX = smem_addr(smem + OFF_X);
+  uint32_t phase = 0;
+  const int64_t ntiles = (N + TCM_ROWS - 1) / TCM_ROWS;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t row0 = tile * TCM_ROWS;
+    const int64_t avail = min((int64_t)TCM_ROWS, N - row0);
+    fill_tile_f32<K>(smem + OFF_X, X, K, row0, avail, TCM_ROWS, tid, TCM_THREADS);
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+      fence_after_sync();
+      if (DGRAD)
+        issue_gemm(tmem, sX, 128, K * 16, 256, sW, WC * 16, 128, 2 * WC * 16, make_idesc(128, NOUT, false, true), K / 16, false);
+      else
+        issue_gemm(tmem, sX, 128, K * 16, 256, sW, 128, WC * 16, 256, make_idesc(128, NOUT, false, false), K / 16, false);
+      mma_commit(&bar);
+    }
+    mbar_wait(&bar, phase);
+    phase ^= 1;
+    fence_after_sync();
+    const int rt = q * 32 + lane;
+    const int64_t grow = row0 + rt;
+    constexpr int HALF = NOUT / 2;
+#pragma unroll 1
+    for (int ch = 0; ch < HALF / 32; ++ch) {
+      float v[32];
+      const int c0 = h * HALF + ch * 32;
+      tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + c0, v);
+      if (rt < avail) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          if (bias) {
+            const float4 b = ldg4(bias + c0 + 4 * j);
+            o = f4_add(o, b);
+          }
+          st4(Y + grow * NOUT + c0 + 4 * j, o);
+        }
+      }
+    }
+    fence_before_sync();
+    __syncthreads();     // TMEM and the X tile are free again
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, NOUT < 32 ? 32 : NOUT);
+}
+
+template <int K, int NOUT, bool DGRAD>
+static int launch_tc_linear(const float* X, const float* W, const float* bias, float* Y, int64_t N, cudaStream_t st) {
+  if (N == 0) return NCF_OK;
+  constexpr int smem = K * NOUT * 2 + 128 * K * 2;
+  static bool configured = false;
+  if (!configured) {
+    NCF_CUDA(cudaFuncSetAttribute(tc_linear_kernel<K, NOUT, DGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  const int64_t ntiles = (N + TCM_ROWS - 1) / TCM_ROWS;
+  const int grid = (int)std::min<int64_t>(ntiles, (int64_t)num_sms() * 2);
+  tc_linear_kernel<K, NOUT, DGRAD><<<grid, TCM_THREADS, smem, st>>>(X, W, bias, Y, N);
+  NCF_LAUNCH_CHECK();
+  return NCF_OK;
+}
+
+// Z tile is stored with the 128-column layout (upper half stays zero when CZ == 64) so that M = 128;
+// the X tile carries 16 extra columns whose first one is 1.0: accumulator column 64 = bias gradient.
+template <int CZ>
+__global__ void __launch_bounds__(TCM_THREADS, 2) tc_wgrad64_kernel(const float* __restrict__ Z, const float* __restrict__ X,
+                                                                    float* __restrict__ dW, float* __restrict__ db,
+                                                                    int64_t N) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  constexpr int CXL = 80;                               // X tile layout width: 64 data + 16 (ones | zeros)
+  constexpr uint32_t OFF_X = 128 * 128 * 2;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q = warp & 3, h = warp >> 2;
+  for (int i = tid; i < (128 * 128 * 2 + 128 * CXL * 2) / 16; i += TCM_THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_slot, 128);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t sZ = smem_addr(smem), sX = smem_addr(smem + OFF_X);
+  uint32_t phase = 0;
+  bool first = true;
+  const int64_t ntiles = (N + TCM_ROWS - 1) / TCM_ROWS;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t row0 = tile * TCM_ROWS;
+    const int64_t avail = min((int64_t)TCM_ROWS, N - row0);
+    if (!first) {
+      mbar_wait(&bar, phase);
+      phase ^= 1;
+    }
+    // Z: CZ columns into the 128-wide layout; X: 64 columns into the 80-wide layout + the ones column
+    for (int c = tid; c < 128 * (CZ / 8); c += TCM_THREADS) {
+      const int blk = c >> 5, l = c & 31;
+      const int bpr = (CZ / 8) / 4;
+      const int r = (blk / bpr) * 8 + (l & 7), j = (blk % bpr) * 4 + (l >> 3);
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (r < avail) {
+        const float* p = Z + (row0 + r) * CZ + 8 * j;
+        const float4 a = ldg4(p), b = ldg4(p + 4);
+        v = make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(b.x, b.y), pack_bf16(b.z, b.w));
+      }
+      *reinterpret_cast<uint4*>(smem + tile_off(r, 8 * j, 128)) = v;
+    }
+    for (int c = tid; c < 128 * 9; c += TCM_THREADS) {
+      int r, j;
+      if (c < 128 * 8) {
+        const int blk = c >> 5, l = c & 31;
+        r = (blk / 2) * 8 + (l & 7);
+        j = (blk % 2) * 4 + (l >> 3);
+      } else {
+        r = c - 128 * 8;
+        j = 8;
+      }
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (r < avail) {
+        if (j < 8) {
+          const float* p = X + (row0 + r) * 64 + 8 * j;
+          const float4 a = ldg4(p), b = ldg4(p + 4);
+          v = make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(b.x, b.y), pack_bf16(b.z, b.w));
+        } else {
+          v.x = 0x00003f80u;     // bf16(1.0) in the low half: column 64 = 1, columns 65..71 = 0
+        }
+      }
+      *reinterpret_cast<uint4*>(smem + OFF_X + tile_off(r, 8 * j, CXL)) = v;
+    }
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+      fence_after_sync();
+      issue_gemm(tmem, sZ, 128 * 16, 128, 2 * 128 * 16, sX, CXL * 16, 128, 2 * CXL * 16, make_idesc(128, CXL, true, true), 8, !first);
+      mma_commit(&bar);
+    }
+    first = false;
+  }
+  if (!first) {
+    mbar_wait(&bar, phase);
+    fence_after_sync();
+    const int m = q * 32 + lane;
+    float v[32];
+    tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + h * 32, v);
+    if (m < CZ) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) atomicAdd(dW + (int64_t)m * 64 + h * 32 + i, v[i]);
+    }
+    if (h == 0 && db) {
+      float b[32];
+      tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + 64, b);
+      if (m < CZ) atomicAdd(db + m, b[0]);
+    } else {
+      float b[32];
+      tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + 64, b);   // keep the warp-collective load uniform
+      (void)b;
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 128);
+}
+
+template <int CZ>
+static int launch_tc_wgrad64(const float* Z, const float* X, float* dW, float* db, int64_t N, cudaStream_t st) {
+  if (N == 0) return NCF_OK;
+  constexpr int smem = 128 * 128 * 2 + 128 * 80 * 2;
+  static bool configured = false;
+  if (!configured) {
+    NCF_CUDA(cudaFuncSetAttribute(tc_wgrad64_kernel<CZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  const int64_t ntiles = (N + TCM_ROWS - 1) / TCM_ROWS;
+  const int grid = (int)std::min<int64_t>(ntiles, (int64_t)num_sms() * 2);
+  tc_wgrad64_kernel<CZ><<<grid, TCM_THREADS, smem, st>>>(Z, X, dW, db, N);
+  NCF_LAUNCH_CHECK();
+  return NCF_OK;
+}
+
+// entry points used by the tower orchestration (ncf_tower_f32.cu) when precision == NCF_BF16_TC
+int tc_proj_forward(int which, const float* X, const float* W, const float* bias, float* Y, int64_t N, cudaStream_t st) {
+  // which: 0 = 64 -> 64 (q, v, out), 1 = 64 -> 128 (k|v)
+  return which == 0 ? launch_tc_linear<64, 64, false>(X, W, bias, Y, N, st) : launch_tc_linear<64, 128, false>(X, W, bias, Y, N, st);
+}
+int tc_proj_dgrad(int which, const float* dY, const float* W, float* dX, int64_t N, cudaStream_t st) {
+  // which: 0 = dY[N,64] . W[64,64], 1 = dY[N,128] . W[128,64]
+  return which == 0 ? launch_tc_linear<64, 64, true>(dY, W, nullptr, dX, N, st) : launch_tc_linear<128, 64, true>(dY, W, nullptr, dX, N, st);
+}
+int tc_proj_wgrad(int which, const float* Z, const float* X, float* dW, float* db, int64_t N, cudaStream_t st) {
+  return which == 0 ? launch_tc_wgrad64<64>(Z, X, dW, db, N, st) : launch_tc_wgrad64<128>(Z, X, dW, db, N, st);
+}
+
 int mlp_tc_forward(const ncf_run_cfg& cfg, const float* dense, int64_t N, const int64_t* hour, const float* tail1,
                    float* out, TowerWs& w, cudaStream_t st) {
   MlpFwdArgs A{};
