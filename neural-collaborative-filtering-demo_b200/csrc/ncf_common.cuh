@@ -139,20 +139,46 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
   }
   return ctr;
 }
-// random 32-bit word of dropout element `idx` at `site`
+// Dropout stream: one Philox call yields 8 x 16-bit lanes = the keep decisions of 8 consecutive
+// elements (element idx uses call idx >> 3, lane idx & 7); keep iff lane >= thresh (p quantised to
+// 1/65536; kept values are scaled by 1/(1-p) with the nominal p like nn.Dropout).
 struct DropoutRng {
   uint2 key;
   uint32_t step_lo, step_hi_site;
-  uint32_t thresh;  // keep iff word >= thresh
+  uint32_t thresh;  // 16-bit threshold; 0 = dropout off
   float scale;      // 1/(1-p)
-  __device__ __forceinline__ uint4 draw4(uint64_t group) const {
+  __device__ __forceinline__ uint4 draw8(uint64_t group) const {
     return philox4x32_10(make_uint4((uint32_t)group, (uint32_t)(group >> 32), step_lo, step_hi_site), key);
   }
+  __device__ __forceinline__ float mask(float x, uint32_t lane16) const { return lane16 >= thresh ? x * scale : 0.f; }
   __device__ __forceinline__ bool keep(uint64_t idx) const {
-    const uint4 r = draw4(idx >> 2);
-    const uint32_t c = (uint32_t)idx & 3u;
+    const uint4 r = draw8(idx >> 3);
+    const uint32_t c = ((uint32_t)idx >> 1) & 3u;
     const uint32_t w = c == 0 ? r.x : c == 1 ? r.y : c == 2 ? r.z : r.w;
-    return w >= thresh;
+    return (((uint32_t)idx & 1u) ? (w >> 16) : (w & 0xffffu)) >= thresh;
+  }
+  // 8 consecutive elements starting at e0 (multiple of 8)
+  __device__ __forceinline__ void apply8(uint64_t e0, float* v) const {
+    const uint4 r = draw8(e0 >> 3);
+    v[0] = mask(v[0], r.x & 0xffffu); v[1] = mask(v[1], r.x >> 16);
+    v[2] = mask(v[2], r.y & 0xffffu); v[3] = mask(v[3], r.y >> 16);
+    v[4] = mask(v[4], r.z & 0xffffu); v[5] = mask(v[5], r.z >> 16);
+    v[6] = mask(v[6], r.w & 0xffffu); v[7] = mask(v[7], r.w >> 16);
+  }
+  // 4 consecutive elements starting at e0 (multiple of 4)
+  __device__ __forceinline__ void apply4(uint64_t e0, float* v) const {
+    const uint4 r = draw8(e0 >> 3);
+    const bool hi = (e0 & 4) != 0;
+    const uint32_t a = hi ? r.z : r.x, b = hi ? r.w : r.y;
+    v[0] = mask(v[0], a & 0xffffu); v[1] = mask(v[1], a >> 16);
+    v[2] = mask(v[2], b & 0xffffu); v[3] = mask(v[3], b >> 16);
+  }
+  // 2 consecutive elements starting at e0 (multiple of 2)
+  __device__ __forceinline__ void apply2(uint64_t e0, float* v) const {
+    const uint4 r = draw8(e0 >> 3);
+    const uint32_t c = ((uint32_t)e0 >> 1) & 3u;
+    const uint32_t w = c == 0 ? r.x : c == 1 ? r.y : c == 2 ? r.z : r.w;
+    v[0] = mask(v[0], w & 0xffffu); v[1] = mask(v[1], w >> 16);
   }
 };
 __host__ __device__ inline DropoutRng make_rng(const ncf_run_cfg& cfg, int site) {
@@ -161,9 +187,10 @@ __host__ __device__ inline DropoutRng make_rng(const ncf_run_cfg& cfg, int site)
   r.step_lo = (uint32_t)cfg.step;
   r.step_hi_site = ((uint32_t)(cfg.step >> 32) & 0x00ffffffu) | ((uint32_t)site << 24);
   const double p = (cfg.training && cfg.dropout_p > 0.f) ? (double)cfg.dropout_p : 0.0;
-  double t = p * 4294967296.0;
-  r.thresh = t >= 4294967295.0 ? 0xffffffffu : (uint32_t)t;
-  r.scale = (float)(1.0 / (1.0 - p));
+  double t = p * 65536.0 + 0.5;
+  r.thresh = t >= 65535.0 ? 65535u : (uint32_t)t;
+  if (p == 0.0) r.thresh = 0u;
+  r.scale = (float)(1.0 / (1.0 - p));   // nn.Dropout: kept values / (1-p)
   return r;
 }
 #endif  // __CUDACC__

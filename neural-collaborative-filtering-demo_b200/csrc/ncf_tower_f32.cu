@@ -161,17 +161,8 @@ __global__ void __launch_bounds__(LG_THREADS) linear_kernel(LinearArgs A) {
 #pragma unroll
         for (int g = 0; g < CM::NG; ++g) {
           const uint64_t e0 = (uint64_t)row * J + CM::col(lane, g);
-          const uint4 rnd = A.rng.draw4(e0 >> 2);
-          if (CM::VW == 4) {
-            y[g * 4 + 0] = rnd.x >= A.rng.thresh ? y[g * 4 + 0] * A.rng.scale : 0.f;
-            y[g * 4 + 1] = rnd.y >= A.rng.thresh ? y[g * 4 + 1] * A.rng.scale : 0.f;
-            y[g * 4 + 2] = rnd.z >= A.rng.thresh ? y[g * 4 + 2] * A.rng.scale : 0.f;
-            y[g * 4 + 3] = rnd.w >= A.rng.thresh ? y[g * 4 + 3] * A.rng.scale : 0.f;
-          } else {
-            const bool hi = (e0 & 2) != 0;
-            y[0] = (hi ? rnd.z : rnd.x) >= A.rng.thresh ? y[0] * A.rng.scale : 0.f;
-            y[1] = (hi ? rnd.w : rnd.y) >= A.rng.thresh ? y[1] * A.rng.scale : 0.f;
-          }
+          if (CM::VW == 4) A.rng.apply4(e0, &y[g * 4]);
+          else A.rng.apply2(e0, &y[0]);
         }
       }
     }
@@ -308,17 +299,8 @@ __global__ void __launch_bounds__(256) relu_ln_drop_bwd_kernel(const float* __re
         r[0] = a.x; r[1] = a.y; dy[0] = b.x; dy[1] = b.y;
       }
       if (rng.thresh != 0u) {
-        const uint4 rnd = rng.draw4((uint64_t)o >> 2);
-        if (CM::VW == 4) {
-          dy[g * 4 + 0] = rnd.x >= rng.thresh ? dy[g * 4 + 0] * rng.scale : 0.f;
-          dy[g * 4 + 1] = rnd.y >= rng.thresh ? dy[g * 4 + 1] * rng.scale : 0.f;
-          dy[g * 4 + 2] = rnd.z >= rng.thresh ? dy[g * 4 + 2] * rng.scale : 0.f;
-          dy[g * 4 + 3] = rnd.w >= rng.thresh ? dy[g * 4 + 3] * rng.scale : 0.f;
-        } else {
-          const bool hi = (o & 2) != 0;
-          dy[0] = (hi ? rnd.z : rnd.x) >= rng.thresh ? dy[0] * rng.scale : 0.f;
-          dy[1] = (hi ? rnd.w : rnd.y) >= rng.thresh ? dy[1] * rng.scale : 0.f;
-        }
+        if (CM::VW == 4) rng.apply4((uint64_t)o, &dy[g * 4]);
+        else rng.apply2((uint64_t)o, &dy[0]);
       }
     }
     float s = 0.f;
@@ -452,60 +434,119 @@ __global__ void __launch_bounds__(256) attn_core_fwd_kernel(const float* __restr
   store16(ctx + n * D + h * HD, o);
 }
 
-// backward: thread (row n = g*S+t, head h) produces dq[n], dk[n], dv[n] for its head slice
+// backward: one warp per head, lane = (group slot, row index inside the group).  Phase 1 treats the
+// lane's row as a QUERY (probabilities, d scores, dq); the S x S score-gradient blocks are then
+// exchanged with shuffles and phase 2 treats the row as a KEY (dk, dv).  No redundant recomputation.
+template <int S>
 __global__ void __launch_bounds__(128) attn_core_bwd_kernel(const float* __restrict__ q, const float* __restrict__ kv,
                                                             const float* __restrict__ dctx, float* __restrict__ dq,
-                                                            float* __restrict__ dkv, int64_t N, int S, DropoutRng rng) {
-  const int64_t tt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (tt >= N * HEADS) return;
-  const int64_t n = tt / HEADS;
-  const int h = (int)(tt % HEADS);
-  const int64_t g = n / S;
-  const int t = (int)(n % S);
-  float dqv[16], dkk[16], dvv[16];
+                                                            float* __restrict__ dkv, int64_t N, DropoutRng rng) {
+  constexpr int G = 32 / S;                      // groups per warp
+  const int lane = threadIdx.x & 31, h = threadIdx.x >> 5;
+  const int gl = lane / S, i = lane % S;
+  const int64_t ngroups = N / S;
+  const int64_t g = (int64_t)blockIdx.x * G + gl;
+  const bool live = gl < G && g < ngroups;
+  const int64_t gg = live ? g : 0;
+  const int64_t n = gg * S + i;
+  const int base = gl * S;
+
+  float qv[16], dc[16];
+  load16(q + n * D + h * HD, qv);
+  load16(dctx + n * D + h * HD, dc);
+  // ---- phase 1: this row as query ------------------------------------------------------------
+  float p[S], ds[S], pd[S];
+  {
+    float mx = -INFINITY;
 #pragma unroll
-  for (int c = 0; c < 16; ++c) dqv[c] = dkk[c] = dvv[c] = 0.f;
-  for (int i = 0; i < S; ++i) {   // every query row of the group
-    const int64_t ni = g * S + i;
-    float qv[16], dc[16], p[NCF_MAX_S], dp[NCF_MAX_S];
-    load16(q + ni * D + h * HD, qv);
-    load16(dctx + ni * D + h * HD, dc);
-    attn_probs(qv, kv, g, S, h, p);
-    float dot = 0.f;
-    float pd_t = 0.f;   // dropped probability p'_{i,t}
     for (int j = 0; j < S; ++j) {
-      float vv[16];
-      load16(kv + (g * S + j) * (2 * D) + D + h * HD, vv);
-      float d = dot16(dc, vv);   // dL/dp'_{ij}
-      float keepscale = 1.f;
-      if (rng.thresh != 0u) {
-        const uint64_t e = (((uint64_t)g * HEADS + h) * S + i) * S + j;
-        keepscale = rng.keep(e) ? rng.scale : 0.f;
-      }
-      if (j == t) pd_t = p[j] * keepscale;
-      dp[j] = d * keepscale;     // dL/dp_{ij}
-      dot = fmaf(p[j], dp[j], dot);
+      float kk[16];
+      load16(kv + (gg * S + j) * (2 * D) + h * HD, kk);
+      p[j] = dot16(qv, kk) * 0.25f;
+      mx = fmaxf(mx, p[j]);
     }
-    // ds_{ij} = p_ij (dp_ij - sum_j' p_ij' dp_ij')
-    const float ds_it = p[t] * (dp[t] - dot);
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < S; ++j) {
+      p[j] = expf(p[j] - mx);
+      sum += p[j];
+    }
+    const float inv = 1.0f / sum;
+    float dot = 0.f;
+#pragma unroll
+    for (int j = 0; j < S; ++j) {
+      p[j] *= inv;
+      float vv[16];
+      load16(kv + (gg * S + j) * (2 * D) + D + h * HD, vv);
+      float ks = 1.f;
+      if (rng.thresh != 0u) ks = rng.keep((((uint64_t)gg * HEADS + h) * S + i) * S + j) ? rng.scale : 0.f;
+      pd[j] = p[j] * ks;                 // dropped probability used by the forward
+      ds[j] = dot16(dc, vv) * ks;        // dL/dp_ij
+      dot = fmaf(p[j], ds[j], dot);
+    }
+    float dqv[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) dqv[c] = 0.f;
+#pragma unroll
+    for (int j = 0; j < S; ++j) {
+      ds[j] = p[j] * (ds[j] - dot);      // dL/ds_ij
+      float kk[16];
+      load16(kv + (gg * S + j) * (2 * D) + h * HD, kk);
+#pragma unroll
+      for (int c = 0; c < 16; ++c) dqv[c] = fmaf(ds[j] * 0.25f, kk[c], dqv[c]);
+    }
+    if (live) store16(dq + n * D + h * HD, dqv);
+  }
+  // ---- phase 2: this row as key t = i: needs column t of ds and pd over all queries ii ------------
+  float dkk[16], dvv[16];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) dkk[c] = dvv[c] = 0.f;
+#pragma unroll
+  for (int ii = 0; ii < S; ++ii) {
+    float ds_it = 0.f, pd_it = 0.f;
+#pragma unroll
+    for (int jj = 0; jj < S; ++jj) {
+      const float a = __shfl_sync(0xffffffffu, ds[jj], (base + ii) & 31);
+      const float b = __shfl_sync(0xffffffffu, pd[jj], (base + ii) & 31);
+      if (jj == i) {
+        ds_it = a;
+        pd_it = b;
+      }
+    }
+    float qi[16], dci[16];
+    load16(q + (gg * S + ii) * D + h * HD, qi);
+    load16(dctx + (gg * S + ii) * D + h * HD, dci);
 #pragma unroll
     for (int c = 0; c < 16; ++c) {
-      dkk[c] = fmaf(ds_it * 0.25f, qv[c], dkk[c]);
-      dvv[c] = fmaf(pd_t, dc[c], dvv[c]);
-    }
-    if (i == t) {
-      for (int j = 0; j < S; ++j) {
-        float kk[16];
-        load16(kv + (g * S + j) * (2 * D) + h * HD, kk);
-        const float ds = p[j] * (dp[j] - dot) * 0.25f;
-#pragma unroll
-        for (int c = 0; c < 16; ++c) dqv[c] = fmaf(ds, kk[c], dqv[c]);
-      }
+      dkk[c] = fmaf(ds_it * 0.25f, qi[c], dkk[c]);
+      dvv[c] = fmaf(pd_it, dci[c], dvv[c]);
     }
   }
-  store16(dq + n * D + h * HD, dqv);
-  store16(dkv + n * (2 * D) + h * HD, dkk);
-  store16(dkv + n * (2 * D) + D + h * HD, dvv);
+  if (live) {
+    store16(dkv + n * (2 * D) + h * HD, dkk);
+    store16(dkv + n * (2 * D) + D + h * HD, dvv);
+  }
+}
+
+static int launch_attn_core_bwd(const float* q, const float* kv, const float* dctx, float* dq, float* dkv, int64_t N, int S,
+                                const DropoutRng& rng, cudaStream_t st) {
+  if (N == 0) return NCF_OK;
+  const int64_t ngroups = N / S;
+  const int G = 32 / S;
+  const unsigned grid = (unsigned)((ngroups + G - 1) / G);
+  switch (S) {
+    case 1: attn_core_bwd_kernel<1><<<grid, 128, 0, st>>>(q, kv, dctx, dq, dkv, N, rng); break;
+    case 2: attn_core_bwd_kernel<2><<<grid, 128, 0, st>>>(q, kv, dctx, dq, dkv, N, rng); break;
+    case 3: attn_core_bwd_kernel<3><<<grid, 128, 0, st>>>(q, kv, dctx, dq, dkv, N, rng); break;
+    case 4: attn_core_bwd_kernel<4><<<grid, 128, 0, st>>>(q, kv, dctx, dq, dkv, N, rng); break;
+    case 5: attn_core_bwd_kernel<5><<<grid, 128, 0, st>>>(q, kv, dctx, dq, dkv, N, rng); break;
+    case 6: attn_core_bwd_kernel<6><<<grid, 128, 0, st>>>(q, kv, dctx, dq, dkv, N, rng); break;
+    case 7: attn_core_bwd_kernel<7><<<grid, 128, 0, st>>>(q, kv, dctx, dq, dkv, N, rng); break;
+    case 8: attn_core_bwd_kernel<8><<<grid, 128, 0, st>>>(q, kv, dctx, dq, dkv, N, rng); break;
+    default: set_error("attention backward: S=%d unsupported", S); return NCF_ERR_ARG;
+  }
+  NCF_LAUNCH_CHECK();
+  return NCF_OK;
 }
 
 // =============================================================================================
@@ -755,9 +796,7 @@ int tower_f32_backward(const ncf_run_cfg& cfg, const float* dense, float* dg, in
     NCF_TRY((launch_linear<64, true, EPI_NONE>(lin(w.g64a, D, P + NCF_OFF(NCF_P_O_W), D, nullptr, w.g64b, D, N, D), st)));
   }
   // attention core: dq (g64a), dkv (g128)
-  const int64_t threads = N * HEADS;
-  attn_core_bwd_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(w.q, w.kv, w.g64b, w.g64a, w.g128, N, S, make_rng(cfg, 0));
-  NCF_LAUNCH_CHECK();
+  NCF_TRY(launch_attn_core_bwd(w.q, w.kv, w.g64b, w.g64a, w.g128, N, S, make_rng(cfg, 0), st));
   // projections: weights/biases, then dxu (g64b) = dq . Wq and dxp (g256 reused as [N,64]) = dkv . [Wk;Wv]
   if (tc) {
     NCF_TRY(tc_proj_wgrad(0, w.g64a, w.xu, dg + NCF_OFF(NCF_P_Q_W), dg + NCF_OFF(NCF_P_Q_B), N, st));

@@ -213,13 +213,7 @@ __device__ __forceinline__ void mlp_epilogue(uint32_t tmem_acc, int q, int h, in
     }
     if (rng.thresh != 0u) {
 #pragma unroll
-      for (int g4 = 0; g4 < 8; ++g4) {
-        const uint4 rnd = rng.draw4(((uint64_t)grow * C + c0 + 4 * g4) >> 2);
-        v[4 * g4 + 0] = rnd.x >= rng.thresh ? v[4 * g4 + 0] * rng.scale : 0.f;
-        v[4 * g4 + 1] = rnd.y >= rng.thresh ? v[4 * g4 + 1] * rng.scale : 0.f;
-        v[4 * g4 + 2] = rnd.z >= rng.thresh ? v[4 * g4 + 2] * rng.scale : 0.f;
-        v[4 * g4 + 3] = rnd.w >= rng.thresh ? v[4 * g4 + 3] * rng.scale : 0.f;
-      }
+      for (int g8 = 0; g8 < 4; ++g8) rng.apply8((uint64_t)grow * C + c0 + 8 * g8, &v[8 * g8]);
     }
     if (LAST) {
 #pragma unroll
@@ -719,13 +713,7 @@ __device__ __forceinline__ void mlp_bwd_layer(uint32_t tmem_dy, const float* __r
     }
     if (rng.thresh != 0u) {
 #pragma unroll
-      for (int g4 = 0; g4 < 8; ++g4) {
-        const uint4 rnd = rng.draw4(((uint64_t)grow * C + c0 + 4 * g4) >> 2);
-        dy[4 * g4 + 0] = rnd.x >= rng.thresh ? dy[4 * g4 + 0] * rng.scale : 0.f;
-        dy[4 * g4 + 1] = rnd.y >= rng.thresh ? dy[4 * g4 + 1] * rng.scale : 0.f;
-        dy[4 * g4 + 2] = rnd.z >= rng.thresh ? dy[4 * g4 + 2] * rng.scale : 0.f;
-        dy[4 * g4 + 3] = rnd.w >= rng.thresh ? dy[4 * g4 + 3] * rng.scale : 0.f;
-      }
+      for (int g8 = 0; g8 < 4; ++g8) rng.apply8((uint64_t)grow * C + c0 + 8 * g8, &dy[8 * g8]);
     }
   };
 
