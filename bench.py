@@ -248,13 +248,12 @@ def main():
         precision = "bf16" if getattr(_lib, "HAS_BF16_TC", False) else "fp32"
     table_mode = args.table_mode
     if table_mode == "auto":
-        table_mode = "fused_sparse" if args.workload == "c3shard" else "fused_dense_equiv"
+        table_mode = "fused_sparse" if args.workload in ("c3shard", "c3") else "fused_dense_equiv"
 
     if world > 1:
         # row-sharded tables: the model object only carries the replicated dense parameters
         from ncf_b200.sharding import ShardedNCFEngine
-        model = build_model(1, 1, dev, "fp32")
-        precision = "fp32"
+        model = build_model(1, 1, dev, precision)
         eng = ShardedNCFEngine(model, users, items, lr=1e-3, weight_decay=1e-5, table_mode=table_mode)
         dev_in = [torch.empty(N, dtype=torch.long, device=dev), torch.empty(N, dtype=torch.long, device=dev),
                   torch.empty(N, dtype=torch.float32, device=dev)]
@@ -323,7 +322,7 @@ def main():
         line = {
             "metric": "train_samples_per_s", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+            "vs_baseline": None, "dtype": "bf16" if precision == "bf16" else "fp32", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {desc}", "interactions_per_step_per_gpu": B,
                        "rows_per_interaction": S, "table_update": table_mode, "towers": precision,
                        "parallelism": f"tables row-sharded over {world} GPUs (all-to-all ids/rows/grads), towers "

@@ -115,7 +115,7 @@ extern "C" int ncf_shard_owner_rows(const ncf_tables* T, const float* dense, int
 static int check_shard_cfg(const ncf_run_cfg* cfg, int64_t N) {
   NCF_REQUIRE(cfg, "null run cfg");
   NCF_REQUIRE(cfg->S >= 1 && cfg->S <= NCF_MAX_S && N >= 0 && N % cfg->S == 0, "bad S / N");
-  NCF_REQUIRE(cfg->precision == NCF_FP32, "sharded path: precision not available");
+  NCF_REQUIRE(cfg->precision == NCF_FP32 || cfg->precision == NCF_BF16_TC, "sharded path: unknown precision");
   return NCF_OK;
 }
 

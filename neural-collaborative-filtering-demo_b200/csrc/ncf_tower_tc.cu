@@ -133,9 +133,11 @@ constexpr uint32_t SM_Y = SM_A0 + 128 * 64 * 2;     // [128][256]       64 KB  Y
 constexpr uint32_t SM_PAR = SM_Y + 128 * 256 * 2;   // fp32 parameters
 constexpr int PAR_B0 = 0, PAR_G0 = 256, PAR_E0 = 512, PAR_B1 = 768, PAR_G1 = 896, PAR_E1 = 1024, PAR_B2 = 1152,
               PAR_G2 = 1216, PAR_E2 = 1280, PAR_WOUT = 1344, PAR_SCAL = 1408, PAR_COUNT = 1416;
-constexpr uint32_t SM_STAT = SM_PAR + PAR_COUNT * 4;           // [128][2][2] floats
-constexpr uint32_t SM_HEAD = SM_STAT + 128 * 2 * 2 * 4;        // [128][2] floats
-constexpr uint32_t SM_MLP_TOTAL = SM_HEAD + 128 * 2 * 4;
+constexpr int MLP_THREADS = 512;                               // 16 warps: 4 TMEM lane quarters x 4 column parts
+constexpr int MLP_NH = 4;
+constexpr uint32_t SM_STAT = SM_PAR + PAR_COUNT * 4;           // [128][4][2] floats
+constexpr uint32_t SM_HEAD = SM_STAT + 128 * MLP_NH * 2 * 4;   // [128][4] floats
+constexpr uint32_t SM_MLP_TOTAL = SM_HEAD + 128 * MLP_NH * 4;
 
 struct MlpFwdArgs {
   const float* a;            // [N,64] fp32 attention output
@@ -155,8 +157,8 @@ __device__ __forceinline__ void load_weight_image(uint8_t* img, const float* __r
   fill_tile_f32<COLS>(img, w, ld, 0, ROWS, ROWS, tid, nthreads);
 }
 
-// Epilogue of one layer for this thread's row and column half.  Pass 1: bias (+tail) + ReLU, bf16
-// rounding, row statistics; pass 2: LayerNorm, dropout, bf16 -> next A operand / saved tensors.
+// Epilogue of one layer for this thread's row and column part (C/4 columns).  Pass 1: bias (+tail) +
+// ReLU, bf16 rounding, row statistics; pass 2: LayerNorm, dropout, bf16 -> next A operand / saved tensors.
 template <int C, bool LAST>
 __device__ __forceinline__ void mlp_epilogue(uint32_t tmem_acc, int q, int h, int lane, int64_t grow, bool live,
                                              const float* __restrict__ par_b, const float* __restrict__ par_g,
@@ -165,17 +167,17 @@ __device__ __forceinline__ void mlp_epilogue(uint32_t tmem_acc, int q, int h, in
                                              __nv_bfloat16* __restrict__ r_out, __nv_bfloat16* __restrict__ y_out,
                                              float* __restrict__ y3_out, const float* __restrict__ par_wout,
                                              float& head_partial) {
-  constexpr int HALF = C / 2, NCH = HALF / 32;
+  constexpr int PART = C / MLP_NH, CW = PART >= 32 ? 32 : 16, NCH = PART / CW;
   const int rt = q * 32 + lane;                 // row inside the tile
-  const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) + h * HALF;
+  const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) + h * PART;
   float sum = 0.f, sq = 0.f;
 #pragma unroll 1
   for (int ch = 0; ch < NCH; ++ch) {
-    float v[32];
-    tmem_ld32(taddr + ch * 32, v);
-    const int c0 = h * HALF + ch * 32;
+    float v[CW];
+    tmem_ldw<CW>(taddr + ch * CW, v);
+    const int c0 = h * PART + ch * CW;
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
+    for (int i = 0; i < CW; ++i) {
       float x = v[i] + par_b[c0 + i];
       if (tail_row) x += __ldg(tail_row + c0 + i);
       x = bf16_round(fmaxf(x, 0.f));
@@ -186,26 +188,31 @@ __device__ __forceinline__ void mlp_epilogue(uint32_t tmem_acc, int q, int h, in
     if (r_out && live) {
       uint4* dst = reinterpret_cast<uint4*>(r_out + grow * C + c0);
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
+      for (int j = 0; j < CW / 8; ++j)
         dst[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
                             pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
     }
   }
-  s_stat[(rt * 2 + h) * 2 + 0] = sum;
-  s_stat[(rt * 2 + h) * 2 + 1] = sq;
+  s_stat[(rt * MLP_NH + h) * 2 + 0] = sum;
+  s_stat[(rt * MLP_NH + h) * 2 + 1] = sq;
   __syncthreads();
-  sum += s_stat[(rt * 2 + (h ^ 1)) * 2 + 0];
-  sq += s_stat[(rt * 2 + (h ^ 1)) * 2 + 1];
+  sum = 0.f;
+  sq = 0.f;
+#pragma unroll
+  for (int k = 0; k < MLP_NH; ++k) {
+    sum += s_stat[(rt * MLP_NH + k) * 2 + 0];
+    sq += s_stat[(rt * MLP_NH + k) * 2 + 1];
+  }
   const float mean = sum * (1.0f / C);
   const float rstd = rsqrtf(fmaxf(sq * (1.0f / C) - mean * mean, 0.f) + LN_EPS);
   float hp = 0.f;
 #pragma unroll 1
   for (int ch = 0; ch < NCH; ++ch) {
-    float v[32];
-    tmem_ld32(taddr + ch * 32, v);
-    const int c0 = h * HALF + ch * 32;
+    float v[CW];
+    tmem_ldw<CW>(taddr + ch * CW, v);
+    const int c0 = h * PART + ch * CW;
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
+    for (int i = 0; i < CW; ++i) {
       float x = v[i] + par_b[c0 + i];
       if (tail_row) x += __ldg(tail_row + c0 + i);
       x = bf16_round(fmaxf(x, 0.f));
@@ -213,19 +220,19 @@ __device__ __forceinline__ void mlp_epilogue(uint32_t tmem_acc, int q, int h, in
     }
     if (rng.thresh != 0u) {
 #pragma unroll
-      for (int g8 = 0; g8 < 4; ++g8) rng.apply8((uint64_t)grow * C + c0 + 8 * g8, &v[8 * g8]);
+      for (int g8 = 0; g8 < CW / 8; ++g8) rng.apply8((uint64_t)grow * C + c0 + 8 * g8, &v[8 * g8]);
     }
     if (LAST) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) hp = fmaf(v[i], par_wout[c0 + i], hp);
+      for (int i = 0; i < CW; ++i) hp = fmaf(v[i], par_wout[c0 + i], hp);
       if (y3_out && live) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
+        for (int j = 0; j < CW / 4; ++j)
           st4(y3_out + grow * C + c0 + 4 * j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
       }
     } else {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < CW / 8; ++j) {
         const uint4 pk = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
                                     pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
         *reinterpret_cast<uint4*>(ytile + tile_off(rt, c0 + 8 * j, C)) = pk;
@@ -236,7 +243,7 @@ __device__ __forceinline__ void mlp_epilogue(uint32_t tmem_acc, int q, int h, in
   head_partial = hp;
 }
 
-__global__ void __launch_bounds__(TCM_THREADS, 1) mlp_tc_fwd_kernel(MlpFwdArgs A) {
+__global__ void __launch_bounds__(MLP_THREADS, 1) mlp_tc_fwd_kernel(MlpFwdArgs A) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t tmem_slot;
@@ -247,10 +254,10 @@ __global__ void __launch_bounds__(TCM_THREADS, 1) mlp_tc_fwd_kernel(MlpFwdArgs A
   float* s_head = reinterpret_cast<float*>(smem + SM_HEAD);
   const float* P = A.dense;
 
-  load_weight_image<256, 64>(smem + SM_W0, P + NCF_OFF(NCF_P_MLP0_W), K0, tid, TCM_THREADS);
-  load_weight_image<128, 256>(smem + SM_W1, P + NCF_OFF(NCF_P_MLP1_W), H1, tid, TCM_THREADS);
-  load_weight_image<64, 128>(smem + SM_W2, P + NCF_OFF(NCF_P_MLP2_W), H2, tid, TCM_THREADS);
-  for (int i = tid; i < 256; i += TCM_THREADS) {
+  load_weight_image<256, 64>(smem + SM_W0, P + NCF_OFF(NCF_P_MLP0_W), K0, tid, MLP_THREADS);
+  load_weight_image<128, 256>(smem + SM_W1, P + NCF_OFF(NCF_P_MLP1_W), H1, tid, MLP_THREADS);
+  load_weight_image<64, 128>(smem + SM_W2, P + NCF_OFF(NCF_P_MLP2_W), H2, tid, MLP_THREADS);
+  for (int i = tid; i < 256; i += MLP_THREADS) {
     par[PAR_B0 + i] = P[NCF_OFF(NCF_P_MLP0_B) + i];
     par[PAR_G0 + i] = P[NCF_OFF(NCF_P_LN0_W) + i];
     par[PAR_E0 + i] = P[NCF_OFF(NCF_P_LN0_B) + i];
@@ -291,7 +298,7 @@ __global__ void __launch_bounds__(TCM_THREADS, 1) mlp_tc_fwd_kernel(MlpFwdArgs A
     const int rt = q * 32 + lane;
     const int64_t grow = row0 + rt;
     const bool live = rt < avail;
-    fill_tile_f32<64>(smem + SM_A0, A.a, D, row0, avail, TCM_ROWS, tid, TCM_THREADS);
+    fill_tile_f32<64>(smem + SM_A0, A.a, D, row0, avail, TCM_ROWS, tid, MLP_THREADS);
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
@@ -333,11 +340,12 @@ __global__ void __launch_bounds__(TCM_THREADS, 1) mlp_tc_fwd_kernel(MlpFwdArgs A
     fence_after_sync();
     mlp_epilogue<64, true>(tmem + 384, q, h, lane, grow, live, par + PAR_B2, par + PAR_G2, par + PAR_E2, nullptr, A.rng[2],
                            s_stat, nullptr, A.r3, nullptr, A.y3, par + PAR_WOUT, hp);
-    s_head[rt * 2 + h] = hp;
+    s_head[rt * MLP_NH + h] = hp;
     fence_before_sync();
     __syncthreads();
     if (h == 0 && live) {
-      const float mp = s_head[rt * 2] + s_head[rt * 2 + 1] + par[PAR_SCAL + 0];
+      const float mp = (s_head[rt * MLP_NH] + s_head[rt * MLP_NH + 1]) + (s_head[rt * MLP_NH + 2] + s_head[rt * MLP_NH + 3]) +
+                       par[PAR_SCAL + 0];
       const float z = fmaf(par[PAR_SCAL + 1], A.mf_pred[grow], fmaf(par[PAR_SCAL + 2], mp, par[PAR_SCAL + 3]));
       const float pr = 1.0f / (1.0f + expf(-z));
       A.mlp_pred[grow] = mp;
@@ -359,7 +367,7 @@ int launch_mlp_tc_fwd(const MlpFwdArgs& A, cudaStream_t st) {
   }
   const int64_t ntiles = (A.N + TCM_ROWS - 1) / TCM_ROWS;
   const int grid = (int)std::min<int64_t>(ntiles, num_sms());
-  mlp_tc_fwd_kernel<<<grid, TCM_THREADS, SM_MLP_TOTAL, st>>>(A);
+  mlp_tc_fwd_kernel<<<grid, MLP_THREADS, SM_MLP_TOTAL, st>>>(A);
   NCF_LAUNCH_CHECK();
   return NCF_OK;
 }
@@ -623,8 +631,8 @@ int mlp_tc_forward(const ncf_run_cfg& cfg, const float* dense, int64_t N, const 
 // written to global memory (bf16) for the weight-gradient kernel; the LayerNorm-affine and bias
 // gradients are column sums reduced with a shuffle transpose and shared-memory atomics.
 // =============================================================================================
-constexpr uint32_t SMB_STAT = SM_PAR + PAR_COUNT * 4;           // 2 x [128][2][2] floats
-constexpr uint32_t SMB_ACC = SMB_STAT + 2 * 128 * 2 * 2 * 4;    // column-sum accumulators
+constexpr uint32_t SMB_STAT = SM_PAR + PAR_COUNT * 4;                 // 2 x [128][4][2] floats
+constexpr uint32_t SMB_ACC = SMB_STAT + 2 * 128 * MLP_NH * 2 * 4;     // column-sum accumulators
 constexpr int ACC_L0 = 0, ACC_L1 = 768, ACC_L2 = 1152, ACC_COUNT = 1344;   // per layer: [dgamma | dbeta | dbias]
 constexpr uint32_t SMB_TOTAL = SMB_ACC + ACC_COUNT * 4;
 
@@ -638,10 +646,15 @@ struct MlpBwdArgs {
   DropoutRng rng[3];
 };
 
-// lane l ends up with sum over the warp's 32 lanes of v[l]
-__device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
+// column sums of a [32 rows (lanes) x W cols (registers)] block: lane l (< W) ends up with column l
+template <int W>
+__device__ __forceinline__ float warp_transpose_sum(float (&v)[W], int lane) {
+  if constexpr (W == 16) {
 #pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) {
+    for (int i = 0; i < 16; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], 16);
+  }
+#pragma unroll
+  for (int off = (W == 32 ? 16 : 8); off >= 1; off >>= 1) {
     const bool up = (lane & off) != 0;
 #pragma unroll
     for (int i = 0; i < off; ++i) {
@@ -653,9 +666,10 @@ __device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
   return v[0];
 }
 
-__device__ __forceinline__ void load_bf16x32(const __nv_bfloat16* __restrict__ p, bool live, float (&v)[32]) {
+template <int W>
+__device__ __forceinline__ void load_bf16xw(const __nv_bfloat16* __restrict__ p, bool live, float (&v)[W]) {
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
+  for (int j = 0; j < W / 8; ++j) {
     uint4 q4 = make_uint4(0, 0, 0, 0);
     if (live) q4 = __ldg(reinterpret_cast<const uint4*>(p) + j);
     float t[8];
@@ -671,37 +685,43 @@ __device__ __forceinline__ void mlp_bwd_layer(uint32_t tmem_dy, const float* __r
                                               const float* __restrict__ gam, const DropoutRng& rng, float* s_statA,
                                               float* s_statB, float* s_acc, uint8_t* dztile,
                                               __nv_bfloat16* __restrict__ dz_out) {
-  constexpr int HALF = C / 2, NCH = HALF / 32;
+  constexpr int PART = C / MLP_NH, CW = PART >= 32 ? 32 : 16, NCH = PART / CW;
   const int rt = q * 32 + lane;
-  const uint32_t taddr = tmem_dy + ((uint32_t)(q * 32) << 16) + h * HALF;
-  const __nv_bfloat16* rrow = r_saved + grow * C + h * HALF;
+  const uint32_t taddr = tmem_dy + ((uint32_t)(q * 32) << 16) + h * PART;
+  const __nv_bfloat16* rrow = r_saved + grow * C + h * PART;
+  const bool acc_lane = lane < CW;
   // ---- pass A: LayerNorm statistics of the saved relu output -----------------------------------
   float sum = 0.f, sq = 0.f;
 #pragma unroll 1
   for (int ch = 0; ch < NCH; ++ch) {
-    float r[32];
-    load_bf16x32(rrow + ch * 32, live, r);
+    float r[CW];
+    load_bf16xw<CW>(rrow + ch * CW, live, r);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
+    for (int i = 0; i < CW; ++i) {
       sum += r[i];
       sq = fmaf(r[i], r[i], sq);
     }
   }
-  s_statA[(rt * 2 + h) * 2 + 0] = sum;
-  s_statA[(rt * 2 + h) * 2 + 1] = sq;
+  s_statA[(rt * MLP_NH + h) * 2 + 0] = sum;
+  s_statA[(rt * MLP_NH + h) * 2 + 1] = sq;
   __syncthreads();
-  sum += s_statA[(rt * 2 + (h ^ 1)) * 2 + 0];
-  sq += s_statA[(rt * 2 + (h ^ 1)) * 2 + 1];
+  sum = 0.f;
+  sq = 0.f;
+#pragma unroll
+  for (int k = 0; k < MLP_NH; ++k) {
+    sum += s_statA[(rt * MLP_NH + k) * 2 + 0];
+    sq += s_statA[(rt * MLP_NH + k) * 2 + 1];
+  }
   const float mean = sum * (1.0f / C);
   const float rstd = rsqrtf(fmaxf(sq * (1.0f / C) - mean * mean, 0.f) + LN_EPS);
 
-  auto load_dy = [&](int ch, float (&dy)[32]) {
-    const int c0 = h * HALF + ch * 32;
+  auto load_dy = [&](int ch, float (&dy)[CW]) {
+    const int c0 = h * PART + ch * CW;
     if (FROM_TMEM) {
-      tmem_ld32(taddr + ch * 32, dy);
+      tmem_ldw<CW>(taddr + ch * CW, dy);
     } else {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
+      for (int j = 0; j < CW / 4; ++j) {
         float4 t = make_float4(0, 0, 0, 0);
         if (live) t = ld4(dy_global + grow * C + c0 + 4 * j);
         dy[4 * j] = t.x; dy[4 * j + 1] = t.y; dy[4 * j + 2] = t.z; dy[4 * j + 3] = t.w;
@@ -709,11 +729,11 @@ __device__ __forceinline__ void mlp_bwd_layer(uint32_t tmem_dy, const float* __r
     }
     if (!live) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) dy[i] = 0.f;
+      for (int i = 0; i < CW; ++i) dy[i] = 0.f;
     }
     if (rng.thresh != 0u) {
 #pragma unroll
-      for (int g8 = 0; g8 < 4; ++g8) rng.apply8((uint64_t)grow * C + c0 + 8 * g8, &dy[8 * g8]);
+      for (int g8 = 0; g8 < CW / 8; ++g8) rng.apply8((uint64_t)grow * C + c0 + 8 * g8, &dy[8 * g8]);
     }
   };
 
@@ -721,57 +741,64 @@ __device__ __forceinline__ void mlp_bwd_layer(uint32_t tmem_dy, const float* __r
   float s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
   for (int ch = 0; ch < NCH; ++ch) {
-    const int c0 = h * HALF + ch * 32;
-    float r[32], dy[32];
-    load_bf16x32(rrow + ch * 32, live, r);
+    const int c0 = h * PART + ch * CW;
+    float r[CW], dy[CW];
+    load_bf16xw<CW>(rrow + ch * CW, live, r);
     load_dy(ch, dy);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
+    for (int i = 0; i < CW; ++i) {
       const float xh = (r[i] - mean) * rstd;
       const float dyg = dy[i] * gam[c0 + i];
       s1 += dyg;
       s2 = fmaf(dyg, xh, s2);
       r[i] = dy[i] * xh;          // reuse r[] as the d gamma contribution
     }
-    const float cg = warp_transpose_sum(r, lane);
-    const float cb = warp_transpose_sum(dy, lane);
-    atomicAdd(s_acc + c0 + lane, cg);
-    atomicAdd(s_acc + C + c0 + lane, cb);
+    const float cg = warp_transpose_sum<CW>(r, lane);
+    const float cb = warp_transpose_sum<CW>(dy, lane);
+    if (acc_lane) {
+      atomicAdd(s_acc + c0 + lane, cg);
+      atomicAdd(s_acc + C + c0 + lane, cb);
+    }
   }
-  s_statB[(rt * 2 + h) * 2 + 0] = s1;
-  s_statB[(rt * 2 + h) * 2 + 1] = s2;
+  s_statB[(rt * MLP_NH + h) * 2 + 0] = s1;
+  s_statB[(rt * MLP_NH + h) * 2 + 1] = s2;
   __syncthreads();
-  s1 += s_statB[(rt * 2 + (h ^ 1)) * 2 + 0];
-  s2 += s_statB[(rt * 2 + (h ^ 1)) * 2 + 1];
+  s1 = 0.f;
+  s2 = 0.f;
+#pragma unroll
+  for (int k = 0; k < MLP_NH; ++k) {
+    s1 += s_statB[(rt * MLP_NH + k) * 2 + 0];
+    s2 += s_statB[(rt * MLP_NH + k) * 2 + 1];
+  }
   const float m1 = s1 * (1.0f / C), m2 = s2 * (1.0f / C);
 
   // ---- pass C: dz = relu'(r) * LN_backward -> bf16 tile (A operand) + global + bias column sums ----
 #pragma unroll 1
   for (int ch = 0; ch < NCH; ++ch) {
-    const int c0 = h * HALF + ch * 32;
-    float r[32], dy[32];
-    load_bf16x32(rrow + ch * 32, live, r);
+    const int c0 = h * PART + ch * CW;
+    float r[CW], dy[CW];
+    load_bf16xw<CW>(rrow + ch * CW, live, r);
     load_dy(ch, dy);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
+    for (int i = 0; i < CW; ++i) {
       const float xh = (r[i] - mean) * rstd;
       const float dyg = dy[i] * gam[c0 + i];
       const float dr = rstd * (dyg - m1 - xh * m2);
       dy[i] = (r[i] > 0.f && live) ? dr : 0.f;
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < CW / 8; ++j) {
       const uint4 pk = make_uint4(pack_bf16(dy[8 * j], dy[8 * j + 1]), pack_bf16(dy[8 * j + 2], dy[8 * j + 3]),
                                   pack_bf16(dy[8 * j + 4], dy[8 * j + 5]), pack_bf16(dy[8 * j + 6], dy[8 * j + 7]));
       *reinterpret_cast<uint4*>(dztile + tile_off(rt, c0 + 8 * j, C)) = pk;
       if (live) *reinterpret_cast<uint4*>(dz_out + grow * C + c0 + 8 * j) = pk;
     }
-    const float cz = warp_transpose_sum(dy, lane);
-    atomicAdd(s_acc + 2 * C + c0 + lane, cz);
+    const float cz = warp_transpose_sum<CW>(dy, lane);
+    if (acc_lane) atomicAdd(s_acc + 2 * C + c0 + lane, cz);
   }
 }
 
-__global__ void __launch_bounds__(TCM_THREADS, 1) mlp_tc_bwd_kernel(MlpBwdArgs A) {
+__global__ void __launch_bounds__(MLP_THREADS, 1) mlp_tc_bwd_kernel(MlpBwdArgs A) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t tmem_slot;
@@ -779,19 +806,19 @@ __global__ void __launch_bounds__(TCM_THREADS, 1) mlp_tc_bwd_kernel(MlpBwdArgs A
   const int q = warp & 3, h = warp >> 2;
   float* par = reinterpret_cast<float*>(smem + SM_PAR);
   float* s_statA = reinterpret_cast<float*>(smem + SMB_STAT);
-  float* s_statB = s_statA + 128 * 2 * 2;
+  float* s_statB = s_statA + 128 * MLP_NH * 2;
   float* s_acc = reinterpret_cast<float*>(smem + SMB_ACC);
   const float* P = A.dense;
 
-  load_weight_image<256, 64>(smem + SM_W0, P + NCF_OFF(NCF_P_MLP0_W), K0, tid, TCM_THREADS);
-  load_weight_image<128, 256>(smem + SM_W1, P + NCF_OFF(NCF_P_MLP1_W), H1, tid, TCM_THREADS);
-  load_weight_image<64, 128>(smem + SM_W2, P + NCF_OFF(NCF_P_MLP2_W), H2, tid, TCM_THREADS);
-  for (int i = tid; i < 256; i += TCM_THREADS) {
+  load_weight_image<256, 64>(smem + SM_W0, P + NCF_OFF(NCF_P_MLP0_W), K0, tid, MLP_THREADS);
+  load_weight_image<128, 256>(smem + SM_W1, P + NCF_OFF(NCF_P_MLP1_W), H1, tid, MLP_THREADS);
+  load_weight_image<64, 128>(smem + SM_W2, P + NCF_OFF(NCF_P_MLP2_W), H2, tid, MLP_THREADS);
+  for (int i = tid; i < 256; i += MLP_THREADS) {
     par[PAR_G0 + i] = P[NCF_OFF(NCF_P_LN0_W) + i];
     if (i < 128) par[PAR_G1 + i] = P[NCF_OFF(NCF_P_LN1_W) + i];
     if (i < 64) par[PAR_G2 + i] = P[NCF_OFF(NCF_P_LN2_W) + i];
   }
-  for (int i = tid; i < ACC_COUNT; i += TCM_THREADS) s_acc[i] = 0.f;
+  for (int i = tid; i < ACC_COUNT; i += MLP_THREADS) s_acc[i] = 0.f;
   if (tid == 0) {
     mbar_init(&bar, 1);
     mbar_fence_init();
@@ -855,12 +882,12 @@ __global__ void __launch_bounds__(TCM_THREADS, 1) mlp_tc_bwd_kernel(MlpBwdArgs A
     phase ^= 1;
     fence_after_sync();
     {
-      float v[32];
-      tmem_ld32(tmem + 384 + ((uint32_t)(q * 32) << 16) + h * 32, v);
+      float v[16];
+      tmem_ld16(tmem + 384 + ((uint32_t)(q * 32) << 16) + h * 16, v);
       if (live) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          st4(A.dy3_da + grow * D + h * 32 + 4 * j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+        for (int j = 0; j < 4; ++j)
+          st4(A.dy3_da + grow * D + h * 16 + 4 * j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
       }
     }
     fence_before_sync();
@@ -868,7 +895,7 @@ __global__ void __launch_bounds__(TCM_THREADS, 1) mlp_tc_bwd_kernel(MlpBwdArgs A
   }
   __syncthreads();
   float* dg = A.dense_grad;
-  for (int i = tid; i < ACC_COUNT; i += TCM_THREADS) {
+  for (int i = tid; i < ACC_COUNT; i += MLP_THREADS) {
     int64_t off;
     int k = i;
     if (k < ACC_L1) {
@@ -1010,7 +1037,7 @@ int mlp_tc_backward(const ncf_run_cfg& cfg, const float* dense, float* dense_gra
   B.dz3 = (__nv_bfloat16*)w.dz3b;
   B.N = N;
   for (int l = 0; l < 3; ++l) B.rng[l] = make_rng(cfg, 1 + l);
-  mlp_tc_bwd_kernel<<<grid, TCM_THREADS, SMB_TOTAL, st>>>(B);
+  mlp_tc_bwd_kernel<<<grid, MLP_THREADS, SMB_TOTAL, st>>>(B);
   NCF_LAUNCH_CHECK();
   MlpWgradArgs W{};
   W.a = w.a;

@@ -151,7 +151,7 @@ class ShardedNCFEngine:
         m = self.model
         cfg = _lib.RunCfg()
         cfg.S, cfg.training = self.S, 1
-        cfg.precision = _lib.NCF_FP32
+        cfg.precision = _lib.NCF_BF16_TC if m.compute_precision == "bf16" else _lib.NCF_FP32
         cfg.dropout_p = float(m.dropout)
         cfg.seed = m._dropout_seed + self.rank
         cfg.step = self.step

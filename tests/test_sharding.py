@@ -82,8 +82,8 @@ def _emulated_exchange(per_rank_bufs, per_rank_counts, world):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("world", [1, 2, 3])
-def test_emulated_cluster_matches_single_gpu_engine(world):
+@pytest.mark.parametrize("world,precision", [(1, "fp32"), (2, "fp32"), (3, "fp32"), (2, "bf16")])
+def test_emulated_cluster_matches_single_gpu_engine(world, precision):
     """`world` ShardedNCFEngine ranks driven phase by phase in one process (the exchanges emulated by
     copies) must reproduce NCFTrainEngine on the concatenated batch: same loss, same weights."""
     import ncf_b200
@@ -98,6 +98,7 @@ def test_emulated_cluster_matches_single_gpu_engine(world):
     def fresh():
         m = ncf_b200.AdvancedNCF(U, I, 5, 24, dropout=0.0)
         m.load_state_dict(p)
+        m.compute_precision = precision
         return m.cuda().train()
 
     ref_model = fresh()
@@ -144,14 +145,19 @@ def test_emulated_cluster_matches_single_gpu_engine(world):
         for e in engines:
             e.dense_grad.copy_(dsum)
             e.phase_dense_adam()
-        assert abs(float(lsum) - float(ref_loss)) < 2e-6
+        assert abs(float(lsum) - float(ref_loss)) < (2e-6 if precision == "fp32" else 2e-3)
     block_u, block_i = (U + world - 1) // world, (I + world - 1) // world
     ref_tabs = ref_model._table_params()
     for k in range(4):
         full = torch.cat([e.w[k] for e in engines])
         d = (full - ref_tabs[k].detach()).abs()
         assert full.shape == ref_tabs[k].shape
-        assert float((d > 5e-6).float().mean()) < 3e-3 and d.max() < 1.5e-3, (k, float(d.max()))
+        if precision == "fp32":
+            assert float((d > 5e-6).float().mean()) < 3e-3 and d.max() < 1.5e-3, (k, float(d.max()))
+        else:       # bf16 operands: Adam amplifies rounding noise on small gradients; most elements still agree
+            assert float((d > 2e-4).float().mean()) < 0.15 and d.max() < 7e-3, (k, float(d.max()))
+    if precision != "fp32":
+        return
     d = (models[0]._flat - ref_model._flat).abs()
     d[ncf_b200._lib.dense_layout()[0][9][1]:ncf_b200._lib.dense_layout()[0][9][1] + 64] = 0   # k_proj.bias: noise
     assert float((d > 5e-6).float().mean()) < 3e-3 and d.max() < 1.5e-3
