@@ -693,14 +693,15 @@ TowerWs carve_tower_ws(void* ws, int64_t N, const ncf_run_cfg& cfg) {
     w.g256 = c.take<float>(N * H1);
     w.g256b = c.take<float>(N * H1);
     if (cfg.precision == NCF_BF16_TC) {
-      w.r1b = c.take<uint16_t>(N * H1);
-      w.y1b = c.take<uint16_t>(N * H1);
-      w.r2b = c.take<uint16_t>(N * H2);
-      w.y2b = c.take<uint16_t>(N * H2);
-      w.r3b = c.take<uint16_t>(N * H3);
-      w.dz1b = c.take<uint16_t>(N * H1);
-      w.dz2b = c.take<uint16_t>(N * H2);
-      w.dz3b = c.take<uint16_t>(N * H3);
+      const int64_t Np = align_up(N, 128);      // tile images: whole 128-row tiles
+      w.r1b = c.take<uint16_t>(Np * H1);
+      w.y1b = c.take<uint16_t>(Np * H1);
+      w.r2b = c.take<uint16_t>(Np * H2);
+      w.y2b = c.take<uint16_t>(Np * H2);
+      w.r3b = c.take<uint16_t>(Np * H3);
+      w.dz1b = c.take<uint16_t>(Np * H1);
+      w.dz2b = c.take<uint16_t>(Np * H2);
+      w.dz3b = c.take<uint16_t>(Np * H3);
     }
     w.emb_bytes = ncf_emb_bwd_workspace_bytes(N);
     w.emb = c.take<char>(w.emb_bytes);

@@ -157,14 +157,18 @@ __device__ __forceinline__ void load_weight_image(uint8_t* img, const float* __r
   fill_tile_f32<COLS>(img, w, ld, 0, ROWS, ROWS, tid, nthreads);
 }
 
+// Saved activations live in global memory as TILE IMAGES: tile t of a [N,C] tensor is the 128 x C
+// canonical operand image at byte offset t*128*C*2 (rows beyond N are padding).  A warp store of one
+// 16-byte chunk per lane then covers 4 x 128 contiguous bytes (full sectors), and the consumers
+// (backward, weight gradient) copy tiles linearly.
 // Epilogue of one layer for this thread's row and column part (C/4 columns).  Pass 1: bias (+tail) +
 // ReLU, bf16 rounding, row statistics; pass 2: LayerNorm, dropout, bf16 -> next A operand / saved tensors.
-template <int C, bool LAST>
+template <int C, bool LAST, bool HAS_TAIL>
 __device__ __forceinline__ void mlp_epilogue(uint32_t tmem_acc, int q, int h, int lane, int64_t grow, bool live,
                                              const float* __restrict__ par_b, const float* __restrict__ par_g,
                                              const float* __restrict__ par_e, const float* __restrict__ tail_row,
                                              const DropoutRng& rng, float* s_stat, uint8_t* ytile,
-                                             __nv_bfloat16* __restrict__ r_out, __nv_bfloat16* __restrict__ y_out,
+                                             uint8_t* __restrict__ r_img, uint8_t* __restrict__ y_img,
                                              float* __restrict__ y3_out, const float* __restrict__ par_wout,
                                              float& head_partial) {
   constexpr int PART = C / MLP_NH, CW = PART >= 32 ? 32 : 16, NCH = PART / CW;
@@ -177,20 +181,25 @@ __device__ __forceinline__ void mlp_epilogue(uint32_t tmem_acc, int q, int h, in
     tmem_ldw<CW>(taddr + ch * CW, v);
     const int c0 = h * PART + ch * CW;
 #pragma unroll
-    for (int i = 0; i < CW; ++i) {
-      float x = v[i] + par_b[c0 + i];
-      if (tail_row) x += __ldg(tail_row + c0 + i);
-      x = bf16_round(fmaxf(x, 0.f));
-      v[i] = x;
-      sum += x;
-      sq = fmaf(x, x, sq);
+    for (int i4 = 0; i4 < CW / 4; ++i4) {
+      const float4 b4 = *reinterpret_cast<const float4*>(par_b + c0 + 4 * i4);
+      float4 t4 = make_float4(0, 0, 0, 0);
+      if (HAS_TAIL) t4 = tail_row ? ldg4(tail_row + c0 + 4 * i4) : t4;
+      const float bb[4] = {b4.x + t4.x, b4.y + t4.y, b4.z + t4.z, b4.w + t4.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float x = bf16_round(fmaxf(v[4 * i4 + k] + bb[k], 0.f));
+        v[4 * i4 + k] = x;
+        sum += x;
+        sq = fmaf(x, x, sq);
+      }
     }
-    if (r_out && live) {
-      uint4* dst = reinterpret_cast<uint4*>(r_out + grow * C + c0);
+    if (r_img) {
 #pragma unroll
       for (int j = 0; j < CW / 8; ++j)
-        dst[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
-                            pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+        *reinterpret_cast<uint4*>(r_img + tile_off(rt, c0 + 8 * j, C)) =
+            make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                       pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
     }
   }
   s_stat[(rt * MLP_NH + h) * 2 + 0] = sum;
@@ -212,11 +221,19 @@ __device__ __forceinline__ void mlp_epilogue(uint32_t tmem_acc, int q, int h, in
     tmem_ldw<CW>(taddr + ch * CW, v);
     const int c0 = h * PART + ch * CW;
 #pragma unroll
-    for (int i = 0; i < CW; ++i) {
-      float x = v[i] + par_b[c0 + i];
-      if (tail_row) x += __ldg(tail_row + c0 + i);
-      x = bf16_round(fmaxf(x, 0.f));
-      v[i] = fmaf((x - mean) * rstd, par_g[c0 + i], par_e[c0 + i]);
+    for (int i4 = 0; i4 < CW / 4; ++i4) {
+      const float4 b4 = *reinterpret_cast<const float4*>(par_b + c0 + 4 * i4);
+      const float4 g4 = *reinterpret_cast<const float4*>(par_g + c0 + 4 * i4);
+      const float4 e4 = *reinterpret_cast<const float4*>(par_e + c0 + 4 * i4);
+      float4 t4 = make_float4(0, 0, 0, 0);
+      if (HAS_TAIL) t4 = tail_row ? ldg4(tail_row + c0 + 4 * i4) : t4;
+      const float bb[4] = {b4.x + t4.x, b4.y + t4.y, b4.z + t4.z, b4.w + t4.w};
+      const float gg[4] = {g4.x, g4.y, g4.z, g4.w}, ee[4] = {e4.x, e4.y, e4.z, e4.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float x = bf16_round(fmaxf(v[4 * i4 + k] + bb[k], 0.f));
+        v[4 * i4 + k] = fmaf((x - mean) * rstd, gg[k], ee[k]);
+      }
     }
     if (rng.thresh != 0u) {
 #pragma unroll
@@ -224,7 +241,10 @@ __device__ __forceinline__ void mlp_epilogue(uint32_t tmem_acc, int q, int h, in
     }
     if (LAST) {
 #pragma unroll
-      for (int i = 0; i < CW; ++i) hp = fmaf(v[i], par_wout[c0 + i], hp);
+      for (int i4 = 0; i4 < CW / 4; ++i4) {
+        const float4 w4 = *reinterpret_cast<const float4*>(par_wout + c0 + 4 * i4);
+        hp = fmaf(v[4 * i4], w4.x, fmaf(v[4 * i4 + 1], w4.y, fmaf(v[4 * i4 + 2], w4.z, fmaf(v[4 * i4 + 3], w4.w, hp))));
+      }
       if (y3_out && live) {
 #pragma unroll
         for (int j = 0; j < CW / 4; ++j)
@@ -235,8 +255,9 @@ __device__ __forceinline__ void mlp_epilogue(uint32_t tmem_acc, int q, int h, in
       for (int j = 0; j < CW / 8; ++j) {
         const uint4 pk = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
                                     pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
-        *reinterpret_cast<uint4*>(ytile + tile_off(rt, c0 + 8 * j, C)) = pk;
-        if (y_out && live) *reinterpret_cast<uint4*>(y_out + grow * C + c0 + 8 * j) = pk;
+        const uint32_t off = tile_off(rt, c0 + 8 * j, C);
+        *reinterpret_cast<uint4*>(ytile + off) = pk;
+        if (y_img) *reinterpret_cast<uint4*>(y_img + off) = pk;
       }
     }
   }
@@ -307,13 +328,24 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_tc_fwd_kernel(MlpFwdArgs A
       issue_gemm(tmem + 0, sA0, 128, 64 * 16, 256, sW0, 128, 64 * 16, 256, make_idesc(128, 256, false, false), 4, false);
       mma_commit(&bar);
     }
-    mbar_wait(&bar, phase);
+    if (warp == 0) mbar_wait(&bar, phase);      // one warp polls the mbarrier, the rest park on the CTA barrier
     phase ^= 1;
+    __syncthreads();
     fence_after_sync();
-    const float* tail_row = (A.hour && live) ? A.tail1 + A.hour[grow] * H1 : nullptr;
     float hp;
-    mlp_epilogue<256, false>(tmem + 0, q, h, lane, grow, live, par + PAR_B0, par + PAR_G0, par + PAR_E0, tail_row, A.rng[0],
-                             s_stat, smem + SM_Y, A.r1, A.y1, nullptr, nullptr, hp);
+    uint8_t* r1i = A.r1 ? reinterpret_cast<uint8_t*>(A.r1) + tile * (128 * 256 * 2) : nullptr;
+    uint8_t* y1i = A.y1 ? reinterpret_cast<uint8_t*>(A.y1) + tile * (128 * 256 * 2) : nullptr;
+    uint8_t* r2i = A.r2 ? reinterpret_cast<uint8_t*>(A.r2) + tile * (128 * 128 * 2) : nullptr;
+    uint8_t* y2i = A.y2 ? reinterpret_cast<uint8_t*>(A.y2) + tile * (128 * 128 * 2) : nullptr;
+    uint8_t* r3i = A.r3 ? reinterpret_cast<uint8_t*>(A.r3) + tile * (128 * 64 * 2) : nullptr;
+    if (A.hour) {
+      const float* tail_row = live ? A.tail1 + A.hour[grow] * H1 : nullptr;
+      mlp_epilogue<256, false, true>(tmem + 0, q, h, lane, grow, live, par + PAR_B0, par + PAR_G0, par + PAR_E0, tail_row,
+                                     A.rng[0], s_stat, smem + SM_Y, r1i, y1i, nullptr, nullptr, hp);
+    } else {
+      mlp_epilogue<256, false, false>(tmem + 0, q, h, lane, grow, live, par + PAR_B0, par + PAR_G0, par + PAR_E0, nullptr,
+                                      A.rng[0], s_stat, smem + SM_Y, r1i, y1i, nullptr, nullptr, hp);
+    }
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
@@ -322,11 +354,12 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_tc_fwd_kernel(MlpFwdArgs A
       issue_gemm(tmem + 256, sY, 128, 256 * 16, 256, sW1, 128, 256 * 16, 256, make_idesc(128, 128, false, false), 16, false);
       mma_commit(&bar);
     }
-    mbar_wait(&bar, phase);
+    if (warp == 0) mbar_wait(&bar, phase);      // one warp polls the mbarrier, the rest park on the CTA barrier
     phase ^= 1;
+    __syncthreads();
     fence_after_sync();
-    mlp_epilogue<128, false>(tmem + 256, q, h, lane, grow, live, par + PAR_B1, par + PAR_G1, par + PAR_E1, nullptr, A.rng[1],
-                             s_stat, smem + SM_Y, A.r2, A.y2, nullptr, nullptr, hp);
+    mlp_epilogue<128, false, false>(tmem + 256, q, h, lane, grow, live, par + PAR_B1, par + PAR_G1, par + PAR_E1, nullptr,
+                                    A.rng[1], s_stat, smem + SM_Y, r2i, y2i, nullptr, nullptr, hp);
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
@@ -335,11 +368,12 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_tc_fwd_kernel(MlpFwdArgs A
       issue_gemm(tmem + 384, sY, 128, 128 * 16, 256, sW2, 128, 128 * 16, 256, make_idesc(128, 64, false, false), 8, false);
       mma_commit(&bar);
     }
-    mbar_wait(&bar, phase);
+    if (warp == 0) mbar_wait(&bar, phase);      // one warp polls the mbarrier, the rest park on the CTA barrier
     phase ^= 1;
+    __syncthreads();
     fence_after_sync();
-    mlp_epilogue<64, true>(tmem + 384, q, h, lane, grow, live, par + PAR_B2, par + PAR_G2, par + PAR_E2, nullptr, A.rng[2],
-                           s_stat, nullptr, A.r3, nullptr, A.y3, par + PAR_WOUT, hp);
+    mlp_epilogue<64, true, false>(tmem + 384, q, h, lane, grow, live, par + PAR_B2, par + PAR_G2, par + PAR_E2, nullptr,
+                                  A.rng[2], s_stat, nullptr, r3i, nullptr, A.y3, par + PAR_WOUT, hp);
     s_head[rt * MLP_NH + h] = hp;
     fence_before_sync();
     __syncthreads();
@@ -666,12 +700,12 @@ __device__ __forceinline__ float warp_transpose_sum(float (&v)[W], int lane) {
   return v[0];
 }
 
+// W consecutive bf16 of one row of a tile image: 16-byte chunks sit 128 bytes apart
 template <int W>
-__device__ __forceinline__ void load_bf16xw(const __nv_bfloat16* __restrict__ p, bool live, float (&v)[W]) {
+__device__ __forceinline__ void load_imgw(const uint8_t* __restrict__ p, float (&v)[W]) {
 #pragma unroll
   for (int j = 0; j < W / 8; ++j) {
-    uint4 q4 = make_uint4(0, 0, 0, 0);
-    if (live) q4 = __ldg(reinterpret_cast<const uint4*>(p) + j);
+    const uint4 q4 = __ldg(reinterpret_cast<const uint4*>(p + j * 128));
     float t[8];
     unpack_bf16x8(q4, t);
 #pragma unroll
@@ -681,21 +715,21 @@ __device__ __forceinline__ void load_bf16xw(const __nv_bfloat16* __restrict__ p,
 
 template <int C, bool FROM_TMEM>
 __device__ __forceinline__ void mlp_bwd_layer(uint32_t tmem_dy, const float* __restrict__ dy_global, int q, int h, int lane,
-                                              int64_t grow, bool live, const __nv_bfloat16* __restrict__ r_saved,
+                                              int64_t grow, bool live, const uint8_t* __restrict__ r_img,
                                               const float* __restrict__ gam, const DropoutRng& rng, float* s_statA,
                                               float* s_statB, float* s_acc, uint8_t* dztile,
-                                              __nv_bfloat16* __restrict__ dz_out) {
+                                              uint8_t* __restrict__ dz_img) {
   constexpr int PART = C / MLP_NH, CW = PART >= 32 ? 32 : 16, NCH = PART / CW;
   const int rt = q * 32 + lane;
   const uint32_t taddr = tmem_dy + ((uint32_t)(q * 32) << 16) + h * PART;
-  const __nv_bfloat16* rrow = r_saved + grow * C + h * PART;
+  const uint8_t* rrow = r_img + tile_off(rt, h * PART, C);     // + ch*CW columns = + ch*(CW/8)*128 bytes
   const bool acc_lane = lane < CW;
   // ---- pass A: LayerNorm statistics of the saved relu output -----------------------------------
   float sum = 0.f, sq = 0.f;
 #pragma unroll 1
   for (int ch = 0; ch < NCH; ++ch) {
     float r[CW];
-    load_bf16xw<CW>(rrow + ch * CW, live, r);
+    load_imgw<CW>(rrow + ch * (CW / 8) * 128, r);
 #pragma unroll
     for (int i = 0; i < CW; ++i) {
       sum += r[i];
@@ -743,7 +777,7 @@ __device__ __forceinline__ void mlp_bwd_layer(uint32_t tmem_dy, const float* __r
   for (int ch = 0; ch < NCH; ++ch) {
     const int c0 = h * PART + ch * CW;
     float r[CW], dy[CW];
-    load_bf16xw<CW>(rrow + ch * CW, live, r);
+    load_imgw<CW>(rrow + ch * (CW / 8) * 128, r);
     load_dy(ch, dy);
 #pragma unroll
     for (int i = 0; i < CW; ++i) {
@@ -777,7 +811,7 @@ __device__ __forceinline__ void mlp_bwd_layer(uint32_t tmem_dy, const float* __r
   for (int ch = 0; ch < NCH; ++ch) {
     const int c0 = h * PART + ch * CW;
     float r[CW], dy[CW];
-    load_bf16xw<CW>(rrow + ch * CW, live, r);
+    load_imgw<CW>(rrow + ch * (CW / 8) * 128, r);
     load_dy(ch, dy);
 #pragma unroll
     for (int i = 0; i < CW; ++i) {
@@ -790,8 +824,9 @@ __device__ __forceinline__ void mlp_bwd_layer(uint32_t tmem_dy, const float* __r
     for (int j = 0; j < CW / 8; ++j) {
       const uint4 pk = make_uint4(pack_bf16(dy[8 * j], dy[8 * j + 1]), pack_bf16(dy[8 * j + 2], dy[8 * j + 3]),
                                   pack_bf16(dy[8 * j + 4], dy[8 * j + 5]), pack_bf16(dy[8 * j + 6], dy[8 * j + 7]));
-      *reinterpret_cast<uint4*>(dztile + tile_off(rt, c0 + 8 * j, C)) = pk;
-      if (live) *reinterpret_cast<uint4*>(dz_out + grow * C + c0 + 8 * j) = pk;
+      const uint32_t off = tile_off(rt, c0 + 8 * j, C);
+      *reinterpret_cast<uint4*>(dztile + off) = pk;
+      *reinterpret_cast<uint4*>(dz_img + off) = pk;
     }
     const float cz = warp_transpose_sum<CW>(dy, lane);
     if (acc_lane) atomicAdd(s_acc + 2 * C + c0 + lane, cz);
@@ -842,8 +877,14 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_tc_bwd_kernel(MlpBwdArgs A
     const int64_t grow = row0 + rt;
     const bool live = rt < avail;
     // layer 3 (64 wide): dy3 from global
-    mlp_bwd_layer<64, false>(0, A.dy3_da, q, h, lane, grow, live, A.r3, par + PAR_G2, A.rng[2], s_statA, s_statB,
-                             s_acc + ACC_L2, ztile, A.dz3);
+    const uint8_t* r1i = reinterpret_cast<const uint8_t*>(A.r1) + tile * (128 * 256 * 2);
+    const uint8_t* r2i = reinterpret_cast<const uint8_t*>(A.r2) + tile * (128 * 128 * 2);
+    const uint8_t* r3i = reinterpret_cast<const uint8_t*>(A.r3) + tile * (128 * 64 * 2);
+    uint8_t* z1i = reinterpret_cast<uint8_t*>(A.dz1) + tile * (128 * 256 * 2);
+    uint8_t* z2i = reinterpret_cast<uint8_t*>(A.dz2) + tile * (128 * 128 * 2);
+    uint8_t* z3i = reinterpret_cast<uint8_t*>(A.dz3) + tile * (128 * 64 * 2);
+    mlp_bwd_layer<64, false>(0, A.dy3_da, q, h, lane, grow, live, r3i, par + PAR_G2, A.rng[2], s_statA, s_statB,
+                             s_acc + ACC_L2, ztile, z3i);
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
@@ -852,11 +893,12 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_tc_bwd_kernel(MlpBwdArgs A
       issue_gemm(tmem + 0, sZ, 128, 64 * 16, 256, sW2, 128 * 16, 128, 2 * 128 * 16, make_idesc(128, 128, false, true), 4, false);
       mma_commit(&bar);
     }
-    mbar_wait(&bar, phase);
+    if (warp == 0) mbar_wait(&bar, phase);
     phase ^= 1;
+    __syncthreads();
     fence_after_sync();
-    mlp_bwd_layer<128, true>(tmem + 0, nullptr, q, h, lane, grow, live, A.r2, par + PAR_G1, A.rng[1], s_statA, s_statB,
-                             s_acc + ACC_L1, ztile, A.dz2);
+    mlp_bwd_layer<128, true>(tmem + 0, nullptr, q, h, lane, grow, live, r2i, par + PAR_G1, A.rng[1], s_statA, s_statB,
+                             s_acc + ACC_L1, ztile, z2i);
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
@@ -865,11 +907,12 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_tc_bwd_kernel(MlpBwdArgs A
       issue_gemm(tmem + 128, sZ, 128, 128 * 16, 256, sW1, 256 * 16, 128, 2 * 256 * 16, make_idesc(128, 256, false, true), 8, false);
       mma_commit(&bar);
     }
-    mbar_wait(&bar, phase);
+    if (warp == 0) mbar_wait(&bar, phase);
     phase ^= 1;
+    __syncthreads();
     fence_after_sync();
-    mlp_bwd_layer<256, true>(tmem + 128, nullptr, q, h, lane, grow, live, A.r1, par + PAR_G0, A.rng[0], s_statA, s_statB,
-                             s_acc + ACC_L0, ztile, A.dz1);
+    mlp_bwd_layer<256, true>(tmem + 128, nullptr, q, h, lane, grow, live, r1i, par + PAR_G0, A.rng[0], s_statA, s_statB,
+                             s_acc + ACC_L0, ztile, z1i);
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
@@ -878,8 +921,9 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_tc_bwd_kernel(MlpBwdArgs A
       issue_gemm(tmem + 384, sZ, 128, 256 * 16, 256, sW0, 64 * 16, 128, 2 * 64 * 16, make_idesc(128, 64, false, true), 16, false);
       mma_commit(&bar);
     }
-    mbar_wait(&bar, phase);
+    if (warp == 0) mbar_wait(&bar, phase);
     phase ^= 1;
+    __syncthreads();
     fence_after_sync();
     {
       float v[16];
@@ -927,6 +971,12 @@ constexpr uint32_t SMW_Z1 = SMW_Y1 + 128 * 256 * 2;    // [128][256]      64 KB
 constexpr uint32_t SMW_A = SMW_Z1 + 128 * 256 * 2;     // [128][64]       16 KB
 constexpr uint32_t SMW_TOTAL = SMW_A + 128 * 64 * 2;   // 224 KB
 
+__device__ __forceinline__ void copy_tile_image(uint8_t* dst, const __nv_bfloat16* __restrict__ img, int64_t tile, int bytes,
+                                                int tid, int nthreads) {
+  const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(img) + tile * bytes);
+  for (int i = tid; i < bytes / 16; i += nthreads) reinterpret_cast<uint4*>(dst)[i] = __ldg(src + i);
+}
+
 struct MlpWgradArgs {
   const float* a;                                        // [N,64] fp32
   const __nv_bfloat16 *y1, *y2, *dz1, *dz2, *dz3;
@@ -961,11 +1011,11 @@ __global__ void __launch_bounds__(TCM_THREADS, 1) mlp_tc_wgrad_kernel(MlpWgradAr
       mbar_wait(&bar, phase);
       phase ^= 1;
     }
-    fill_tile_bf16<128>(smem + SMW_Y2, A.y2, H2, row0, avail, TCM_ROWS, tid, TCM_THREADS);
-    fill_tile_bf16<64>(smem + SMW_Z3, A.dz3, H3, row0, avail, TCM_ROWS, tid, TCM_THREADS);
-    fill_tile_bf16<128>(smem + SMW_Z2, A.dz2, H2, row0, avail, TCM_ROWS, tid, TCM_THREADS);
-    fill_tile_bf16<256>(smem + SMW_Y1, A.y1, H1, row0, avail, TCM_ROWS, tid, TCM_THREADS);
-    fill_tile_bf16<256>(smem + SMW_Z1, A.dz1, H1, row0, avail, TCM_ROWS, tid, TCM_THREADS);
+    copy_tile_image(smem + SMW_Y2, A.y2, tile, 128 * 128 * 2, tid, TCM_THREADS);
+    copy_tile_image(smem + SMW_Z3, A.dz3, tile, 128 * 64 * 2, tid, TCM_THREADS);
+    copy_tile_image(smem + SMW_Z2, A.dz2, tile, 128 * 128 * 2, tid, TCM_THREADS);
+    copy_tile_image(smem + SMW_Y1, A.y1, tile, 128 * 256 * 2, tid, TCM_THREADS);
+    copy_tile_image(smem + SMW_Z1, A.dz1, tile, 128 * 256 * 2, tid, TCM_THREADS);
     fill_tile_f32<64>(smem + SMW_A, A.a, D, row0, avail, TCM_ROWS, tid, TCM_THREADS);
     fence_async_smem();
     fence_before_sync();
