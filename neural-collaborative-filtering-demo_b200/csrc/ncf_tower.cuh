@@ -19,6 +19,8 @@ struct TowerWs {
   float *dxu, *dxp;                        // aliases set by the backward
   // bf16 tensors of the tcgen05 path (NCF_BF16_TC): saved activations and pre-activation gradients
   void *r1b, *y1b, *r2b, *y2b, *r3b, *dz1b, *dz2b, *dz3b;
+  void* a_img;                             // attention output as bf16 tile image [ceil(N/128)][128 x 64]
+  float *st1, *st2, *st3;                  // LayerNorm (mean, rstd) per row of the three MLP layers
   char* emb;                               // workspace of the fused embedding backward
   int64_t emb_bytes;
   int64_t total;
@@ -36,6 +38,8 @@ int mlp_tc_forward(const ncf_run_cfg& cfg, const float* dense, int64_t N, const 
 int mlp_tc_backward(const ncf_run_cfg& cfg, const float* dense, float* dense_grad, int64_t N, TowerWs& w, cudaStream_t st);
 // tcgen05 projections of the attention block (fp32 tensors, bf16 operands)
 int tc_proj_forward(int which, const float* X, const float* W, const float* bias, float* Y, int64_t N, cudaStream_t st);
+// 64 -> 64 projection whose output is written as a bf16 tile image (the MLP kernels' A operand)
+int tc_proj_forward_img(const float* X, const float* W, const float* bias, void* img, int64_t N, cudaStream_t st);
 int tc_proj_dgrad(int which, const float* dY, const float* W, float* dX, int64_t N, cudaStream_t st);
 int tc_proj_wgrad(int which, const float* Z, const float* X, float* dW, float* db, int64_t N, cudaStream_t st);
 int launch_bce(const float* out, const float* targets, int64_t N, float* loss_out, float* grad_out, cudaStream_t st);

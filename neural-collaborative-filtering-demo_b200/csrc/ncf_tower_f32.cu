@@ -683,6 +683,13 @@ TowerWs carve_tower_ws(void* ws, int64_t N, const ncf_run_cfg& cfg) {
   w.y2 = c.take<float>(N * H2);
   w.r3 = c.take<float>(N * H3);
   w.y3 = c.take<float>(N * H3);
+  if (cfg.precision == NCF_BF16_TC) {
+    const int64_t Np = align_up(N, 128);
+    w.a_img = c.take<uint16_t>(Np * D);
+    w.st1 = c.take<float>(Np * 2);
+    w.st2 = c.take<float>(Np * 2);
+    w.st3 = c.take<float>(Np * 2);
+  }
   if (train) {
     w.y_pmf = c.take<float>(N * D);
     w.d_mf = c.take<float>(N);
@@ -735,7 +742,7 @@ int tower_f32_forward(const ncf_run_cfg& cfg, const float* dense, int64_t N, con
     NCF_TRY((launch_linear<64, false, EPI_NONE>(lin(w.xp, D, P + NCF_OFF(NCF_P_V_W), D, P + NCF_OFF(NCF_P_V_B), w.ctx, D, N, D), st)));
   }
   if (tc)
-    NCF_TRY(tc_proj_forward(0, w.ctx, P + NCF_OFF(NCF_P_O_W), P + NCF_OFF(NCF_P_O_B), w.a, N, st));
+    NCF_TRY(tc_proj_forward_img(w.ctx, P + NCF_OFF(NCF_P_O_W), P + NCF_OFF(NCF_P_O_B), w.a_img, N, st));
   else
     NCF_TRY((launch_linear<64, false, EPI_NONE>(lin(w.ctx, D, P + NCF_OFF(NCF_P_O_W), D, P + NCF_OFF(NCF_P_O_B), w.a, D, N, D), st)));
   if (cfg.precision == NCF_BF16_TC) return mlp_tc_forward(cfg, dense, N, hour, tail1, out, w, st);

@@ -137,10 +137,12 @@ constexpr int MLP_THREADS = 512;                               // 16 warps: 4 TM
 constexpr int MLP_NH = 4;
 constexpr uint32_t SM_STAT = SM_PAR + PAR_COUNT * 4;           // [128][4][2] floats
 constexpr uint32_t SM_HEAD = SM_STAT + 128 * MLP_NH * 2 * 4;   // [128][4] floats
-constexpr uint32_t SM_MLP_TOTAL = SM_HEAD + 128 * MLP_NH * 4;
+constexpr uint32_t SM_A1 = (SM_HEAD + 128 * MLP_NH * 4 + 1023) / 1024 * 1024;   // second input-tile buffer (TMA double buffering)
+constexpr uint32_t SM_MLP_TOTAL = SM_A1 + 128 * 64 * 2;
 
 struct MlpFwdArgs {
-  const float* a;            // [N,64] fp32 attention output
+  const __nv_bfloat16* a_img; // attention output, bf16 tile image
+  float *st1, *st2, *st3;    // LayerNorm (mean, rstd) per row, saved for the backward (or null)
   const float* dense;
   const int64_t* hour;       // optional (forward_simple hour path)
   const float* tail1;        // [24,256]
@@ -170,7 +172,7 @@ __device__ __forceinline__ void mlp_epilogue(uint32_t tmem_acc, int q, int h, in
                                              const DropoutRng& rng, float* s_stat, uint8_t* ytile,
                                              uint8_t* __restrict__ r_img, uint8_t* __restrict__ y_img,
                                              float* __restrict__ y3_out, const float* __restrict__ par_wout,
-                                             float& head_partial) {
+                                             float& head_partial, float* __restrict__ st_tile) {
   constexpr int PART = C / MLP_NH, CW = PART >= 32 ? 32 : 16, NCH = PART / CW;
   const int rt = q * 32 + lane;                 // row inside the tile
   const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) + h * PART;
@@ -214,6 +216,7 @@ __device__ __forceinline__ void mlp_epilogue(uint32_t tmem_acc, int q, int h, in
   }
   const float mean = sum * (1.0f / C);
   const float rstd = rsqrtf(fmaxf(sq * (1.0f / C) - mean * mean, 0.f) + LN_EPS);
+  if (st_tile && h == 0) *reinterpret_cast<float2*>(st_tile + rt * 2) = make_float2(mean, rstd);
   float hp = 0.f;
 #pragma unroll 1
   for (int ch = 0; ch < NCH; ++ch) {
@@ -267,6 +270,7 @@ __device__ __forceinline__ void mlp_epilogue(uint32_t tmem_acc, int q, int h, in
 __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_tc_fwd_kernel(MlpFwdArgs A) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar;
+  __shared__ __align__(8) uint64_t full[2];
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q = warp & 3, h = warp >> 2;
@@ -300,6 +304,8 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_tc_fwd_kernel(MlpFwdArgs A
     par[PAR_SCAL + 2] = P[NCF_OFF(NCF_P_FINAL_W) + 1];
     par[PAR_SCAL + 3] = P[NCF_OFF(NCF_P_FINAL_B)];
     mbar_init(&bar, 1);
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
     mbar_fence_init();
   }
   if (warp == 0) tmem_alloc(&tmem_slot, 512);
@@ -309,23 +315,34 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_tc_fwd_kernel(MlpFwdArgs A
   fence_after_sync();
   const uint32_t tmem = tmem_slot;
   const uint32_t sW0 = smem_addr(smem + SM_W0), sW1 = smem_addr(smem + SM_W1), sW2 = smem_addr(smem + SM_W2);
-  const uint32_t sA0 = smem_addr(smem + SM_A0), sY = smem_addr(smem + SM_Y);
+  const uint32_t sY = smem_addr(smem + SM_Y);
   uint32_t phase = 0;
 
   const int64_t ntiles = (A.N + TCM_ROWS - 1) / TCM_ROWS;
-  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  constexpr uint32_t A_BYTES = 128 * 64 * 2;
+  const uint8_t* a_img = reinterpret_cast<const uint8_t*>(A.a_img);
+  if (tid == 0 && (int64_t)blockIdx.x < ntiles) {          // TMA bulk copy of the first input tile
+    mbar_arrive_expect_tx(&full[0], A_BYTES);
+    bulk_g2s(smem + SM_A0, a_img + (int64_t)blockIdx.x * A_BYTES, A_BYTES, &full[0]);
+  }
+  int it = 0;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    const int buf = it & 1;
     const int64_t row0 = tile * TCM_ROWS;
     const int64_t avail = min((int64_t)TCM_ROWS, A.N - row0);
     const int rt = q * 32 + lane;
     const int64_t grow = row0 + rt;
     const bool live = rt < avail;
-    fill_tile_f32<64>(smem + SM_A0, A.a, D, row0, avail, TCM_ROWS, tid, MLP_THREADS);
-    fence_async_smem();
-    fence_before_sync();
-    __syncthreads();
     if (tid == 0) {
+      const int64_t next = tile + gridDim.x;
+      if (next < ntiles) {                                  // prefetch the next tile into the other buffer
+        mbar_arrive_expect_tx(&full[buf ^ 1], A_BYTES);
+        bulk_g2s(smem + (buf ? SM_A0 : SM_A1), a_img + next * A_BYTES, A_BYTES, &full[buf ^ 1]);
+      }
+      mbar_wait(&full[buf], (it >> 1) & 1);
       fence_after_sync();
-      issue_gemm(tmem + 0, sA0, 128, 64 * 16, 256, sW0, 128, 64 * 16, 256, make_idesc(128, 256, false, false), 4, false);
+      issue_gemm(tmem + 0, smem_addr(smem + (buf ? SM_A1 : SM_A0)), 128, 64 * 16, 256, sW0, 128, 64 * 16, 256,
+                 make_idesc(128, 256, false, false), 4, false);
       mma_commit(&bar);
     }
     if (warp == 0) mbar_wait(&bar, phase);      // one warp polls the mbarrier, the rest park on the CTA barrier
@@ -338,13 +355,16 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_tc_fwd_kernel(MlpFwdArgs A
     uint8_t* r2i = A.r2 ? reinterpret_cast<uint8_t*>(A.r2) + tile * (128 * 128 * 2) : nullptr;
     uint8_t* y2i = A.y2 ? reinterpret_cast<uint8_t*>(A.y2) + tile * (128 * 128 * 2) : nullptr;
     uint8_t* r3i = A.r3 ? reinterpret_cast<uint8_t*>(A.r3) + tile * (128 * 64 * 2) : nullptr;
+    float* st1 = A.st1 ? A.st1 + tile * 256 : nullptr;
+    float* st2 = A.st2 ? A.st2 + tile * 256 : nullptr;
+    float* st3 = A.st3 ? A.st3 + tile * 256 : nullptr;
     if (A.hour) {
       const float* tail_row = live ? A.tail1 + A.hour[grow] * H1 : nullptr;
       mlp_epilogue<256, false, true>(tmem + 0, q, h, lane, grow, live, par + PAR_B0, par + PAR_G0, par + PAR_E0, tail_row,
-                                     A.rng[0], s_stat, smem + SM_Y, r1i, y1i, nullptr, nullptr, hp);
+                                     A.rng[0], s_stat, smem + SM_Y, r1i, y1i, nullptr, nullptr, hp, st1);
     } else {
       mlp_epilogue<256, false, false>(tmem + 0, q, h, lane, grow, live, par + PAR_B0, par + PAR_G0, par + PAR_E0, nullptr,
-                                      A.rng[0], s_stat, smem + SM_Y, r1i, y1i, nullptr, nullptr, hp);
+                                      A.rng[0], s_stat, smem + SM_Y, r1i, y1i, nullptr, nullptr, hp, st1);
     }
     fence_async_smem();
     fence_before_sync();
@@ -359,7 +379,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_tc_fwd_kernel(MlpFwdArgs A
     __syncthreads();
     fence_after_sync();
     mlp_epilogue<128, false, false>(tmem + 256, q, h, lane, grow, live, par + PAR_B1, par + PAR_G1, par + PAR_E1, nullptr,
-                                    A.rng[1], s_stat, smem + SM_Y, r2i, y2i, nullptr, nullptr, hp);
+                                    A.rng[1], s_stat, smem + SM_Y, r2i, y2i, nullptr, nullptr, hp, st2);
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
@@ -373,7 +393,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_tc_fwd_kernel(MlpFwdArgs A
     __syncthreads();
     fence_after_sync();
     mlp_epilogue<64, true, false>(tmem + 384, q, h, lane, grow, live, par + PAR_B2, par + PAR_G2, par + PAR_E2, nullptr,
-                                  A.rng[2], s_stat, nullptr, r3i, nullptr, A.y3, par + PAR_WOUT, hp);
+                                  A.rng[2], s_stat, nullptr, r3i, nullptr, A.y3, par + PAR_WOUT, hp, st3);
     s_head[rt * MLP_NH + h] = hp;
     fence_before_sync();
     __syncthreads();
@@ -414,7 +434,7 @@ int launch_mlp_tc_fwd(const MlpFwdArgs& A, cudaStream_t st) {
 // fp32 tensors in global memory, bf16 operands in shared memory, fp32 accumulation in TMEM.  Several
 // CTAs per SM hide the load -> MMA -> store latency of the short per-tile pipeline.
 // =============================================================================================
-template <int K, int NOUT, bool DGRAD>
+template <int K, int NOUT, bool DGRAD, bool OUT_IMG = false>
 __global__ void __launch_bounds__(TCM_THREADS, 2) tc_linear_kernel(const float* __restrict__ X, const float* __restrict__ W,
                                                                    const float* __restrict__ bias, float* __restrict__ Y,
                                                                    int64_t N) {
@@ -465,7 +485,17 @@ __global__ void __launch_bounds__(TCM_THREADS, 2) tc_linear_kernel(const float* 
       float v[32];
       const int c0 = h * HALF + ch * 32;
       tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + c0, v);
-      if (rt < avail) {
+      if (OUT_IMG) {     // bf16 tile image (rows beyond N hold the bias: finite padding)
+        uint8_t* img = reinterpret_cast<uint8_t*>(Y) + tile * (128 * NOUT * 2);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float o[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) o[k] = v[8 * j + k] + (bias ? __ldg(bias + c0 + 8 * j + k) : 0.f);
+          *reinterpret_cast<uint4*>(img + tile_off(rt, c0 + 8 * j, NOUT)) =
+              make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+        }
+      } else if (rt < avail) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
@@ -485,18 +515,18 @@ __global__ void __launch_bounds__(TCM_THREADS, 2) tc_linear_kernel(const float* 
   if (warp == 0) tmem_dealloc(tmem, NOUT < 32 ? 32 : NOUT);
 }
 
-template <int K, int NOUT, bool DGRAD>
+template <int K, int NOUT, bool DGRAD, bool OUT_IMG = false>
 static int launch_tc_linear(const float* X, const float* W, const float* bias, float* Y, int64_t N, cudaStream_t st) {
   if (N == 0) return NCF_OK;
   constexpr int smem = K * NOUT * 2 + 128 * K * 2;
   static bool configured = false;
   if (!configured) {
-    NCF_CUDA(cudaFuncSetAttribute(tc_linear_kernel<K, NOUT, DGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    NCF_CUDA(cudaFuncSetAttribute(tc_linear_kernel<K, NOUT, DGRAD, OUT_IMG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
   const int64_t ntiles = (N + TCM_ROWS - 1) / TCM_ROWS;
   const int grid = (int)std::min<int64_t>(ntiles, (int64_t)num_sms() * 2);
-  tc_linear_kernel<K, NOUT, DGRAD><<<grid, TCM_THREADS, smem, st>>>(X, W, bias, Y, N);
+  tc_linear_kernel<K, NOUT, DGRAD, OUT_IMG><<<grid, TCM_THREADS, smem, st>>>(X, W, bias, Y, N);
   NCF_LAUNCH_CHECK();
   return NCF_OK;
 }
@@ -626,6 +656,9 @@ int tc_proj_forward(int which, const float* X, const float* W, const float* bias
   // which: 0 = 64 -> 64 (q, v, out), 1 = 64 -> 128 (k|v)
   return which == 0 ? launch_tc_linear<64, 64, false>(X, W, bias, Y, N, st) : launch_tc_linear<64, 128, false>(X, W, bias, Y, N, st);
 }
+int tc_proj_forward_img(const float* X, const float* W, const float* bias, void* img, int64_t N, cudaStream_t st) {
+  return launch_tc_linear<64, 64, false, true>(X, W, bias, reinterpret_cast<float*>(img), N, st);
+}
 int tc_proj_dgrad(int which, const float* dY, const float* W, float* dX, int64_t N, cudaStream_t st) {
   // which: 0 = dY[N,64] . W[64,64], 1 = dY[N,128] . W[128,64]
   return which == 0 ? launch_tc_linear<64, 64, true>(dY, W, nullptr, dX, N, st) : launch_tc_linear<128, 64, true>(dY, W, nullptr, dX, N, st);
@@ -638,7 +671,10 @@ int mlp_tc_forward(const ncf_run_cfg& cfg, const float* dense, int64_t N, const 
                    float* out, TowerWs& w, cudaStream_t st) {
   MlpFwdArgs A{};
   const bool train = cfg.training != 0;
-  A.a = w.a;
+  A.a_img = (const __nv_bfloat16*)w.a_img;
+  A.st1 = train ? w.st1 : nullptr;
+  A.st2 = train ? w.st2 : nullptr;
+  A.st3 = train ? w.st3 : nullptr;
   A.dense = dense;
   A.hour = hour;
   A.tail1 = tail1;
@@ -675,6 +711,7 @@ struct MlpBwdArgs {
   float* dense_grad;
   float* dy3_da;                               // in: dy3 [N,64] fp32; out: da [N,64] fp32 (in place)
   const __nv_bfloat16 *r1, *r2, *r3;
+  const float *st1, *st2, *st3;                // LayerNorm (mean, rstd) per row from the forward
   __nv_bfloat16 *dz1, *dz2, *dz3;
   int64_t N;
   DropoutRng rng[3];
@@ -718,36 +755,15 @@ __device__ __forceinline__ void mlp_bwd_layer(uint32_t tmem_dy, const float* __r
                                               int64_t grow, bool live, const uint8_t* __restrict__ r_img,
                                               const float* __restrict__ gam, const DropoutRng& rng, float* s_statA,
                                               float* s_statB, float* s_acc, uint8_t* dztile,
-                                              uint8_t* __restrict__ dz_img) {
+                                              uint8_t* __restrict__ dz_img, const float* __restrict__ st_tile) {
   constexpr int PART = C / MLP_NH, CW = PART >= 32 ? 32 : 16, NCH = PART / CW;
   const int rt = q * 32 + lane;
   const uint32_t taddr = tmem_dy + ((uint32_t)(q * 32) << 16) + h * PART;
   const uint8_t* rrow = r_img + tile_off(rt, h * PART, C);     // + ch*CW columns = + ch*(CW/8)*128 bytes
   const bool acc_lane = lane < CW;
-  // ---- pass A: LayerNorm statistics of the saved relu output -----------------------------------
-  float sum = 0.f, sq = 0.f;
-#pragma unroll 1
-  for (int ch = 0; ch < NCH; ++ch) {
-    float r[CW];
-    load_imgw<CW>(rrow + ch * (CW / 8) * 128, r);
-#pragma unroll
-    for (int i = 0; i < CW; ++i) {
-      sum += r[i];
-      sq = fmaf(r[i], r[i], sq);
-    }
-  }
-  s_statA[(rt * MLP_NH + h) * 2 + 0] = sum;
-  s_statA[(rt * MLP_NH + h) * 2 + 1] = sq;
-  __syncthreads();
-  sum = 0.f;
-  sq = 0.f;
-#pragma unroll
-  for (int k = 0; k < MLP_NH; ++k) {
-    sum += s_statA[(rt * MLP_NH + k) * 2 + 0];
-    sq += s_statA[(rt * MLP_NH + k) * 2 + 1];
-  }
-  const float mean = sum * (1.0f / C);
-  const float rstd = rsqrtf(fmaxf(sq * (1.0f / C) - mean * mean, 0.f) + LN_EPS);
+  // LayerNorm statistics of the saved relu output come from the forward
+  const float2 ms = *reinterpret_cast<const float2*>(st_tile + rt * 2);
+  const float mean = ms.x, rstd = ms.y;
 
   auto load_dy = [&](int ch, float (&dy)[CW]) {
     const int c0 = h * PART + ch * CW;
@@ -884,7 +900,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_tc_bwd_kernel(MlpBwdArgs A
     uint8_t* z2i = reinterpret_cast<uint8_t*>(A.dz2) + tile * (128 * 128 * 2);
     uint8_t* z3i = reinterpret_cast<uint8_t*>(A.dz3) + tile * (128 * 64 * 2);
     mlp_bwd_layer<64, false>(0, A.dy3_da, q, h, lane, grow, live, r3i, par + PAR_G2, A.rng[2], s_statA, s_statB,
-                             s_acc + ACC_L2, ztile, z3i);
+                             s_acc + ACC_L2, ztile, z3i, A.st3 + tile * 256);
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
@@ -898,7 +914,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_tc_bwd_kernel(MlpBwdArgs A
     __syncthreads();
     fence_after_sync();
     mlp_bwd_layer<128, true>(tmem + 0, nullptr, q, h, lane, grow, live, r2i, par + PAR_G1, A.rng[1], s_statA, s_statB,
-                             s_acc + ACC_L1, ztile, z2i);
+                             s_acc + ACC_L1, ztile, z2i, A.st2 + tile * 256);
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
@@ -912,7 +928,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_tc_bwd_kernel(MlpBwdArgs A
     __syncthreads();
     fence_after_sync();
     mlp_bwd_layer<256, true>(tmem + 128, nullptr, q, h, lane, grow, live, r1i, par + PAR_G0, A.rng[0], s_statA, s_statB,
-                             s_acc + ACC_L0, ztile, z1i);
+                             s_acc + ACC_L0, ztile, z1i, A.st1 + tile * 256);
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
@@ -978,20 +994,26 @@ __device__ __forceinline__ void copy_tile_image(uint8_t* dst, const __nv_bfloat1
 }
 
 struct MlpWgradArgs {
-  const float* a;                                        // [N,64] fp32
+  const __nv_bfloat16* a_img;                            // MLP input, bf16 tile image
   const __nv_bfloat16 *y1, *y2, *dz1, *dz2, *dz3;
   float* dense_grad;
   int64_t N;
 };
 
+// Warp-specialised: one producer thread streams the tile images with TMA bulk copies into two stages
+// (A: y2, dz3, dz2, y1 = 144 KB; B: dz1, a = 80 KB), one MMA thread consumes them; a stage is refilled
+// as soon as the MMAs that read it have committed, so loads and tensor work overlap.
 __global__ void __launch_bounds__(TCM_THREADS, 1) mlp_tc_wgrad_kernel(MlpWgradArgs A) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ __align__(8) uint64_t bar;
+  __shared__ __align__(8) uint64_t fullA, fullB, emptyA, emptyB;
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q = warp & 3, h = warp >> 2;
   if (tid == 0) {
-    mbar_init(&bar, 1);
+    mbar_init(&fullA, 1);
+    mbar_init(&fullB, 1);
+    mbar_init(&emptyA, 1);
+    mbar_init(&emptyB, 1);
     mbar_fence_init();
   }
   if (warp == 0) tmem_alloc(&tmem_slot, 512);
@@ -999,43 +1021,54 @@ __global__ void __launch_bounds__(TCM_THREADS, 1) mlp_tc_wgrad_kernel(MlpWgradAr
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem = tmem_slot;
-  const uint32_t sY2 = smem_addr(smem + SMW_Y2), sZ3 = smem_addr(smem + SMW_Z3), sZ2 = smem_addr(smem + SMW_Z2);
-  const uint32_t sY1 = smem_addr(smem + SMW_Y1), sZ1 = smem_addr(smem + SMW_Z1), sA = smem_addr(smem + SMW_A);
-  uint32_t phase = 0;
-  bool first = true;
   const int64_t ntiles = (A.N + TCM_ROWS - 1) / TCM_ROWS;
-  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int64_t row0 = tile * TCM_ROWS;
-    const int64_t avail = min((int64_t)TCM_ROWS, A.N - row0);
-    if (!first) {                    // the previous tile's MMAs must have consumed the operand tiles
-      mbar_wait(&bar, phase);
-      phase ^= 1;
+  const int64_t my_tiles = (int64_t)blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  constexpr uint32_t B_Y2 = 128 * 128 * 2, B_Z3 = 128 * 64 * 2, B_Z2 = 128 * 128 * 2, B_Y1 = 128 * 256 * 2,
+                     B_Z1 = 128 * 256 * 2, B_A = 128 * 64 * 2;
+  if (tid == 0) {
+    // ---- producer --------------------------------------------------------------------------
+    const uint8_t *y2 = (const uint8_t*)A.y2, *z3 = (const uint8_t*)A.dz3, *z2 = (const uint8_t*)A.dz2,
+                  *y1 = (const uint8_t*)A.y1, *z1 = (const uint8_t*)A.dz1, *ai = (const uint8_t*)A.a_img;
+    for (int64_t k = 0; k < my_tiles; ++k) {
+      const int64_t tile = blockIdx.x + k * gridDim.x;
+      if (k > 0) mbar_wait(&emptyA, (k - 1) & 1);
+      mbar_arrive_expect_tx(&fullA, B_Y2 + B_Z3 + B_Z2 + B_Y1);
+      bulk_g2s(smem + SMW_Y2, y2 + tile * B_Y2, B_Y2, &fullA);
+      bulk_g2s(smem + SMW_Z3, z3 + tile * B_Z3, B_Z3, &fullA);
+      bulk_g2s(smem + SMW_Z2, z2 + tile * B_Z2, B_Z2, &fullA);
+      bulk_g2s(smem + SMW_Y1, y1 + tile * B_Y1, B_Y1, &fullA);
+      if (k > 0) mbar_wait(&emptyB, (k - 1) & 1);
+      mbar_arrive_expect_tx(&fullB, B_Z1 + B_A);
+      bulk_g2s(smem + SMW_Z1, z1 + tile * B_Z1, B_Z1, &fullB);
+      bulk_g2s(smem + SMW_A, ai + tile * B_A, B_A, &fullB);
     }
-    copy_tile_image(smem + SMW_Y2, A.y2, tile, 128 * 128 * 2, tid, TCM_THREADS);
-    copy_tile_image(smem + SMW_Z3, A.dz3, tile, 128 * 64 * 2, tid, TCM_THREADS);
-    copy_tile_image(smem + SMW_Z2, A.dz2, tile, 128 * 128 * 2, tid, TCM_THREADS);
-    copy_tile_image(smem + SMW_Y1, A.y1, tile, 128 * 256 * 2, tid, TCM_THREADS);
-    copy_tile_image(smem + SMW_Z1, A.dz1, tile, 128 * 256 * 2, tid, TCM_THREADS);
-    fill_tile_f32<64>(smem + SMW_A, A.a, D, row0, avail, TCM_ROWS, tid, TCM_THREADS);
-    fence_async_smem();
-    fence_before_sync();
-    __syncthreads();
-    if (tid == 0) {
+  } else if (tid == 32) {
+    // ---- MMA issuer ---------------------------------------------------------------------------
+    const uint32_t sY2 = smem_addr(smem + SMW_Y2), sZ3 = smem_addr(smem + SMW_Z3), sZ2 = smem_addr(smem + SMW_Z2);
+    const uint32_t sY1 = smem_addr(smem + SMW_Y1), sZ1 = smem_addr(smem + SMW_Z1), sA = smem_addr(smem + SMW_A);
+    for (int64_t k = 0; k < my_tiles; ++k) {
+      const bool acc = k > 0;
+      mbar_wait(&fullA, k & 1);
       fence_after_sync();
-      const bool acc = !first;
       // dW2^T[k_in 128][n_out 64] += y2^T . dz3
       issue_gemm(tmem + 0, sY2, 128 * 16, 128, 2 * 128 * 16, sZ3, 64 * 16, 128, 2 * 64 * 16, make_idesc(128, 64, true, true), 8, acc);
       // dW1[n_out 128][k_in 256] += dz2^T . y1
       issue_gemm(tmem + 64, sZ2, 128 * 16, 128, 2 * 128 * 16, sY1, 256 * 16, 128, 2 * 256 * 16, make_idesc(128, 256, true, true), 8, acc);
+      mma_commit(&emptyA);
+      mbar_wait(&fullB, k & 1);
+      fence_after_sync();
       // dW0[n_out 256][k_in 64] += dz1^T . a   (two M = 128 halves: +16 MN groups = 2048 B)
       issue_gemm(tmem + 320, sZ1, 256 * 16, 128, 2 * 256 * 16, sA, 64 * 16, 128, 2 * 64 * 16, make_idesc(128, 64, true, true), 8, acc);
       issue_gemm(tmem + 384, sZ1 + 2048, 256 * 16, 128, 2 * 256 * 16, sA, 64 * 16, 128, 2 * 64 * 16, make_idesc(128, 64, true, true), 8, acc);
-      mma_commit(&bar);
+      mma_commit(&emptyB);
     }
-    first = false;
+    if (my_tiles > 0) {          // all accumulation done before the flush below
+      mbar_wait(&emptyA, (my_tiles - 1) & 1);
+      mbar_wait(&emptyB, (my_tiles - 1) & 1);
+    }
   }
-  if (!first) {
-    mbar_wait(&bar, phase);
+  __syncthreads();
+  if (my_tiles > 0) {
     fence_after_sync();
     float* dg = A.dense_grad;
     const int lane_row = q * 32 + lane;
@@ -1082,6 +1115,9 @@ int mlp_tc_backward(const ncf_run_cfg& cfg, const float* dense, float* dense_gra
   B.r1 = (const __nv_bfloat16*)w.r1b;
   B.r2 = (const __nv_bfloat16*)w.r2b;
   B.r3 = (const __nv_bfloat16*)w.r3b;
+  B.st1 = w.st1;
+  B.st2 = w.st2;
+  B.st3 = w.st3;
   B.dz1 = (__nv_bfloat16*)w.dz1b;
   B.dz2 = (__nv_bfloat16*)w.dz2b;
   B.dz3 = (__nv_bfloat16*)w.dz3b;
@@ -1090,7 +1126,7 @@ int mlp_tc_backward(const ncf_run_cfg& cfg, const float* dense, float* dense_gra
   mlp_tc_bwd_kernel<<<grid, MLP_THREADS, SMB_TOTAL, st>>>(B);
   NCF_LAUNCH_CHECK();
   MlpWgradArgs W{};
-  W.a = w.a;
+  W.a_img = (const __nv_bfloat16*)w.a_img;
   W.y1 = (const __nv_bfloat16*)w.y1b;
   W.y2 = (const __nv_bfloat16*)w.y2b;
   W.dz1 = B.dz1;
