@@ -192,8 +192,9 @@ __global__ void __launch_bounds__(256) gather_ln_kernel(const float* __restrict_
 //   upstream(MF row)  = sum_n d_mf_pred[n] * w_mf * LN(other side's MF row of sample n)
 //   upstream(MLP row) = sum_n d_x[n]
 // A warp owns a chunk of EB_CHUNK sorted positions; half 0 works on the MF tower, half 1 on the MLP
-// tower.  Runs that cross chunk borders leave per-chunk partial sums that phase 2 adds in a fixed
-// order (deterministic, no float atomics on table rows).
+// tower.  Phase 1 streams the samples and leaves one upstream sum per run piece (512 B per unique
+// id); phase 2 adds the pieces of a run in a fixed order and applies LayerNorm backward + Adam
+// (deterministic, no float atomics on table rows).
 // =============================================================================================
 constexpr int EB_CHUNK = 32;
 constexpr int EB_THREADS = 256;
@@ -247,37 +248,12 @@ struct EmbBwdArgs {
   const float* d_x;               // [N,64] gradient wrt this side's LN'd MLP row
   const float* dense;
   float* dense_grad;
-  float* partial;                 // [nchunks][2][128]
+  float* acc_buf;                 // [N][2][64] upstream sum of the run piece that starts at each sorted position
   int64_t N;
   int32_t mode;                   // ncf_emb_mode
   int32_t accumulate_wmf;         // only one side adds d mf_output.weight
   AdamScalars adam;
 };
-
-// Finish one unique id: LayerNorm backward of the summed upstream gradient, then Adam / store.
-// `acc` = summed upstream gradient of this lane's 4 columns (half 0: MF tower, half 1: MLP tower).
-__device__ __forceinline__ void emb_finalize(const EmbBwdArgs& A, int64_t id, float4 acc, float4 xhat, float rstd,
-                                             float4 wrow, float4 gamma, float4& dgamma, float4& dbeta, int half,
-                                             int l16) {
-  dgamma = f4_add(dgamma, f4_mul(acc, xhat));
-  dbeta = f4_add(dbeta, acc);
-  const float4 dyg = f4_mul(acc, gamma);
-  const float m1 = half_warp_sum(f4_hsum(dyg)) * (1.0f / 64.0f);
-  const float m2 = half_warp_sum(f4_dot(dyg, xhat)) * (1.0f / 64.0f);
-  float4 graw = make_float4(rstd * (dyg.x - m1 - xhat.x * m2), rstd * (dyg.y - m1 - xhat.y * m2),
-                            rstd * (dyg.z - m1 - xhat.z * m2), rstd * (dyg.w - m1 - xhat.w * m2));
-  const int64_t o = id * D + 4 * l16;
-  if (A.mode == NCF_EMB_MATERIALIZE) {
-    st4(A.g[half] + o, graw);
-  } else {
-    float4 mm = ld4(A.m[half] + o), vv = ld4(A.v[half] + o);
-    adam_update4(wrow, mm, vv, graw, A.adam);
-    st4(A.w[half] + o, wrow);
-    st4(A.m[half] + o, mm);
-    st4(A.v[half] + o, vv);
-    if (A.touched && l16 == 0 && half == 0) A.touched[id] = 1;
-  }
-}
 
 __device__ __forceinline__ void block_flush(float* s_red, float4 val, float* dst, int lane, int warp, int nwarps,
                                             bool active_half, int l16) {
@@ -301,110 +277,85 @@ __device__ __forceinline__ void block_flush(float* s_red, float4 val, float* dst
   }
 }
 
+// Phase 1 - streaming segment sum.  A warp owns a chunk of 32 sorted positions and adds up the
+// upstream gradients of every run piece inside it (a piece = a run of equal ids cut at chunk borders).
+// All loads depend only on the ids, so four sample rows are in flight per lane and nothing waits on a
+// table row.  The sum of a piece is written to acc_buf[first sorted position of the piece].
 __global__ void __launch_bounds__(EB_THREADS) emb_bwd_phase1_kernel(EmbBwdArgs A) {
   __shared__ float s_red[(EB_THREADS / 32) * 32 * 4];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = EB_THREADS / 32;
   const int half = lane >> 4, l16 = lane & 15;
   const int64_t nchunks = (A.N + EB_CHUNK - 1) / EB_CHUNK;
   const int64_t gw = (int64_t)blockIdx.x * nwarps + warp, gstride = (int64_t)gridDim.x * nwarps;
+  const bool wmf = A.accumulate_wmf != 0;
 
-  const float4 gamma = ldg4(A.dense + (half ? NCF_OFF(NCF_P_MLP_NORM_W) : NCF_OFF(NCF_P_MF_NORM_W)) + 4 * l16);
-  const float4 beta = ldg4(A.dense + (half ? NCF_OFF(NCF_P_MLP_NORM_B) : NCF_OFF(NCF_P_MF_NORM_B)) + 4 * l16);
-  const float4 g_mf = ldg4(A.dense + NCF_OFF(NCF_P_MF_NORM_W) + 4 * l16);   // for the other side's MF row
+  const float4 g_mf = ldg4(A.dense + NCF_OFF(NCF_P_MF_NORM_W) + 4 * l16);
   const float4 b_mf = ldg4(A.dense + NCF_OFF(NCF_P_MF_NORM_B) + 4 * l16);
   const float4 w_out = ldg4(A.dense + NCF_OFF(NCF_P_MF_OUT_W) + 4 * l16);
-  float4 dgamma = make_float4(0, 0, 0, 0), dbeta = dgamma, dwout = dgamma;
+  float4 dwout = make_float4(0, 0, 0, 0);
 
   for (int64_t c = gw; c < nchunks; c += gstride) {
     const int64_t p0 = c * EB_CHUNK;
     const int cnt = (int)min((int64_t)EB_CHUNK, A.N - p0);
-    // lane i holds sorted position p0+i
     const uint32_t my_id = lane < cnt ? A.sorted_ids[p0 + lane] : 0xffffffffu;
     const int32_t my_row = lane < cnt ? A.perm[p0 + lane] : 0;
-    const int64_t my_other = (lane < cnt && !A.upstream) ? A.other_ids[my_row] : 0;
+    const int64_t my_other = (lane < cnt && !A.upstream && !A.other_y) ? A.other_ids[my_row] : 0;
     const float my_dmf = (lane < cnt && !A.upstream) ? A.d_mf_pred[my_row] : 0.f;
-    const uint32_t prev_id = p0 > 0 ? A.sorted_ids[p0 - 1] : 0xffffffffu;             // uniform
-    const uint32_t next_id = p0 + cnt < A.N ? A.sorted_ids[p0 + cnt] : 0xffffffffu;   // uniform
-    const bool has_prev = p0 > 0, has_next = p0 + cnt < A.N;
 
-    int i = 0;
-    while (i < cnt) {
-      const uint32_t id = __shfl_sync(0xffffffffu, my_id, i);
-      // run [i, j) of equal ids inside this chunk
-      const uint32_t same = __ballot_sync(0xffffffffu, my_id == id && lane >= i && lane < cnt);
-      int e;
-      {  // ids are sorted, so the run is the contiguous set of lanes with my_id == id starting at i
-        const uint32_t m = same >> i;                                  // bit k <-> lane i+k
-        e = i + (m == 0xffffffffu ? 32 : __ffs(~m) - 1);               // trailing ones = run length
-        if (e > cnt) e = cnt;
+    float4 acc = make_float4(0, 0, 0, 0);
+    int piece_first = 0;
+    uint32_t id_prev = __shfl_sync(0xffffffffu, my_id, 0);
+    for (int k0 = 0; k0 < cnt; k0 += 4) {
+      float4 x[4], sf[4];
+      float dmf[4];
+      uint32_t idk[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int kk = min(k0 + u, cnt - 1);
+        const int32_t row = __shfl_sync(0xffffffffu, my_row, kk);
+        const int64_t oid = __shfl_sync(0xffffffffu, my_other, kk);
+        dmf[u] = __shfl_sync(0xffffffffu, my_dmf, kk);
+        idk[u] = __shfl_sync(0xffffffffu, my_id, kk);
+        const float* src = A.upstream ? A.upstream + (int64_t)row * 2 * D + half * D
+                           : half ? A.d_x + (int64_t)row * D
+                                  : (A.other_y ? A.other_y + (int64_t)row * D : A.other_mf + oid * D);
+        x[u] = ldg4(src + 4 * l16);
+        sf[u] = wmf ? ld4(A.w[0] + (int64_t)idk[u] * D + 4 * l16) : make_float4(0, 0, 0, 0);   // own MF row (d mf_output.weight)
       }
-      const bool starts_here = !(i == 0 && has_prev && prev_id == id);
-      const bool ends_here = !(e == cnt && has_next && next_id == id);
-
-      // this side's own rows: needed for d mf_output.weight (user pass) and to finalise
-      float rstd;
-      const float4 wrow = ld4(A.w[half] + (int64_t)id * D + 4 * l16);
-      const float4 xhat = ln_normalise(wrow, rstd);
-      const float4 y_self_mf_lane = affine(xhat, gamma, beta);  // meaningful on half 0 (MF tower)
-
-      float4 acc = make_float4(0, 0, 0, 0);
-      for (int k = i; k < e; k += 2) {
-        // two sample rows per iteration (independent 128-bit loads in flight)
-        float4 x[2];
-        float dmf[2];
-        bool ok[2];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const int kk = min(k + u, e - 1);
-          ok[u] = k + u < e;
-          const int32_t row = __shfl_sync(0xffffffffu, my_row, kk);
-          const int64_t oid = __shfl_sync(0xffffffffu, my_other, kk);
-          dmf[u] = __shfl_sync(0xffffffffu, my_dmf, kk);
-          const float* src = A.upstream ? A.upstream + (int64_t)row * 2 * D + half * D
-                             : half ? A.d_x + (int64_t)row * D
-                                    : (A.other_y ? A.other_y + (int64_t)row * D : A.other_mf + oid * D);
-          x[u] = ldg4(src + 4 * l16);
-        }
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
+      for (int u = 0; u < 4; ++u) {
+        if (k0 + u < cnt) {                                   // warp-uniform
+          if (idk[u] != id_prev) {                            // a new run starts: flush the piece
+            st4(A.acc_buf + ((p0 + piece_first) * 2 + half) * D + 4 * l16, acc);
+            acc = make_float4(0, 0, 0, 0);
+            piece_first = k0 + u;
+            id_prev = idk[u];
+          }
+          // the LayerNorms use full-warp shuffles: every lane runs them, only half 0 keeps the result
           float rs;
-          float4 yo = affine(ln_normalise(x[u], rs), g_mf, b_mf);   // LN of the other side's MF row
-          if (A.other_y) yo = x[u];                                  // already normalised by the forward
-          if (ok[u]) {
-            if (half || A.upstream) {
-              acc = f4_add(acc, x[u]);
-            } else {
-              const float4 t = make_float4(dmf[u] * yo.x, dmf[u] * yo.y, dmf[u] * yo.z, dmf[u] * yo.w);
-              acc = f4_add(acc, f4_mul(t, w_out));
-              dwout = f4_add(dwout, f4_mul(t, y_self_mf_lane));
-            }
+          float4 yo = x[u];
+          if (!A.other_y && !A.upstream) yo = affine(ln_normalise(x[u], rs), g_mf, b_mf);   // LN of the other side's MF row
+          float4 ys = make_float4(0, 0, 0, 0);
+          if (wmf) ys = affine(ln_normalise(sf[u], rs), g_mf, b_mf);
+          if (half || A.upstream) {
+            acc = f4_add(acc, x[u]);
+          } else {
+            const float4 t = make_float4(dmf[u] * yo.x, dmf[u] * yo.y, dmf[u] * yo.z, dmf[u] * yo.w);
+            acc = f4_add(acc, f4_mul(t, w_out));
+            dwout = f4_add(dwout, f4_mul(t, ys));
           }
         }
       }
-
-      if (starts_here && ends_here) {
-        if (A.mode != NCF_EMB_NONE) emb_finalize(A, id, acc, xhat, rstd, wrow, gamma, dgamma, dbeta, half, l16);
-      } else {
-        // piece of a run that crosses a chunk border: slot 1 if it continues into the next chunk,
-        // else slot 0 (it came from the previous chunk and ends here)
-        const int slot = ends_here ? 0 : 1;
-        st4(A.partial + ((c * 2 + slot) * 2 + half) * D + 4 * l16, acc);
-      }
-      i = e;
     }
+    st4(A.acc_buf + ((p0 + piece_first) * 2 + half) * D + 4 * l16, acc);
   }
-  // LayerNorm affine gradients (half 0 -> mf_norm, half 1 -> mlp_norm) and d mf_output.weight
-  float* dg = A.dense_grad;
-  block_flush(s_red, dgamma, dg ? dg + NCF_OFF(NCF_P_MF_NORM_W) : nullptr, lane, warp, nwarps, half == 0, l16);
-  block_flush(s_red, dgamma, dg ? dg + NCF_OFF(NCF_P_MLP_NORM_W) : nullptr, lane, warp, nwarps, half == 1, l16);
-  block_flush(s_red, dbeta, dg ? dg + NCF_OFF(NCF_P_MF_NORM_B) : nullptr, lane, warp, nwarps, half == 0, l16);
-  block_flush(s_red, dbeta, dg ? dg + NCF_OFF(NCF_P_MLP_NORM_B) : nullptr, lane, warp, nwarps, half == 1, l16);
-  if (A.accumulate_wmf)
-    block_flush(s_red, dwout, dg ? dg + NCF_OFF(NCF_P_MF_OUT_W) : nullptr, lane, warp, nwarps, half == 0, l16);
+  if (wmf) block_flush(s_red, dwout, A.dense_grad ? A.dense_grad + NCF_OFF(NCF_P_MF_OUT_W) : nullptr, lane, warp, nwarps,
+                       half == 0, l16);
 }
 
-// Phase 2: a warp per chunk in which a border-crossing run ENDS; adds the run's partials in a fixed
-// order (its own slot 0, then slot 1 of the preceding chunks walking backwards) and finalises.
+// Phase 2 - apply.  For every run START in the warp's chunk: add the run's pieces (its own plus the
+// chunk-start pieces it continues into, fixed order), LayerNorm backward once, fused Adam.  The table
+// row, its moments and the first piece are independent loads issued together.
 __global__ void __launch_bounds__(EB_THREADS) emb_bwd_phase2_kernel(EmbBwdArgs A) {
   __shared__ float s_red[(EB_THREADS / 32) * 32 * 4];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = EB_THREADS / 32;
@@ -413,27 +364,51 @@ __global__ void __launch_bounds__(EB_THREADS) emb_bwd_phase2_kernel(EmbBwdArgs A
   const int64_t gw = (int64_t)blockIdx.x * nwarps + warp, gstride = (int64_t)gridDim.x * nwarps;
   const float4 gamma = ldg4(A.dense + (half ? NCF_OFF(NCF_P_MLP_NORM_W) : NCF_OFF(NCF_P_MF_NORM_W)) + 4 * l16);
   float4 dgamma = make_float4(0, 0, 0, 0), dbeta = dgamma;
+  const bool adam = A.mode != NCF_EMB_MATERIALIZE;
 
   for (int64_t c = gw; c < nchunks; c += gstride) {
-    if (c == 0) continue;
     const int64_t p0 = c * EB_CHUNK;
     const int cnt = (int)min((int64_t)EB_CHUNK, A.N - p0);
-    const uint32_t id = A.sorted_ids[p0];
-    if (A.sorted_ids[p0 - 1] != id) continue;                      // nothing crosses into this chunk
-    const uint32_t last = A.sorted_ids[p0 + cnt - 1];
-    const bool continues = last == id && p0 + cnt < A.N && A.sorted_ids[p0 + cnt] == id;
-    if (continues) continue;                                        // the run ends in a later chunk
-    float4 acc = ld4(A.partial + ((c * 2 + 0) * 2 + half) * D + 4 * l16);
-    for (int64_t cc = c - 1; cc >= 0; --cc) {
-      acc = f4_add(acc, ld4(A.partial + ((cc * 2 + 1) * 2 + half) * D + 4 * l16));
-      const int64_t q0 = cc * EB_CHUNK;
-      if (!(A.sorted_ids[q0] == id && q0 > 0 && A.sorted_ids[q0 - 1] == id)) break;
-    }
-    if (A.mode != NCF_EMB_NONE) {
+    const uint32_t my_id = lane < cnt ? A.sorted_ids[p0 + lane] : 0xffffffffu;
+    const uint32_t before = (p0 + lane > 0 && lane < cnt) ? A.sorted_ids[p0 + lane - 1] : 0xfffffffeu;
+    uint32_t starts = __ballot_sync(0xffffffffu, lane < cnt && (p0 + lane == 0 || before != my_id));
+    while (starts) {
+      const int i = __ffs(starts) - 1;
+      starts &= starts - 1;
+      const uint32_t id = __shfl_sync(0xffffffffu, my_id, i);
+      const int64_t o = (int64_t)id * D + 4 * l16;
+      const float4 wrow = ld4(A.w[half] + o);
+      float4 mm = make_float4(0, 0, 0, 0), vv = mm;
+      if (adam) {
+        mm = ld4(A.m[half] + o);
+        vv = ld4(A.v[half] + o);
+      }
+      float4 acc = ld4(A.acc_buf + ((p0 + i) * 2 + half) * D + 4 * l16);
+      // does the run leave this chunk?  (its last in-chunk element is the chunk's last element)
+      const uint32_t last_id = __shfl_sync(0xffffffffu, my_id, cnt - 1);
+      if (last_id == id) {
+        for (int64_t cs = p0 + EB_CHUNK; cs < A.N && A.sorted_ids[cs] == id; cs += EB_CHUNK)
+          acc = f4_add(acc, ld4(A.acc_buf + (cs * 2 + half) * D + 4 * l16));
+      }
       float rstd;
-      const float4 wrow = ld4(A.w[half] + (int64_t)id * D + 4 * l16);
       const float4 xhat = ln_normalise(wrow, rstd);
-      emb_finalize(A, id, acc, xhat, rstd, wrow, gamma, dgamma, dbeta, half, l16);
+      dgamma = f4_add(dgamma, f4_mul(acc, xhat));
+      dbeta = f4_add(dbeta, acc);
+      const float4 dyg = f4_mul(acc, gamma);
+      const float m1 = half_warp_sum(f4_hsum(dyg)) * (1.0f / 64.0f);
+      const float m2 = half_warp_sum(f4_dot(dyg, xhat)) * (1.0f / 64.0f);
+      const float4 graw = make_float4(rstd * (dyg.x - m1 - xhat.x * m2), rstd * (dyg.y - m1 - xhat.y * m2),
+                                      rstd * (dyg.z - m1 - xhat.z * m2), rstd * (dyg.w - m1 - xhat.w * m2));
+      if (!adam) {
+        st4(A.g[half] + o, graw);
+      } else {
+        float4 wn = wrow;
+        adam_update4(wn, mm, vv, graw, A.adam);
+        st4(A.w[half] + o, wn);
+        st4(A.m[half] + o, mm);
+        st4(A.v[half] + o, vv);
+        if (A.touched && lane == 0) A.touched[id] = 1;
+      }
     }
   }
   float* dg = A.dense_grad;
@@ -581,7 +556,7 @@ static int bits_for(int64_t rows) {
 struct EmbWs {
   uint32_t *keys_in, *keys_out;
   int32_t *vals_in, *vals_out;
-  float* partial;
+  float* acc_buf;
   void* cub_tmp;
   size_t cub_bytes;
   int64_t total;
@@ -593,8 +568,7 @@ static EmbWs carve_emb_ws(void* ws, int64_t N) {
   w.keys_out = c.take<uint32_t>(N);
   w.vals_in = c.take<int32_t>(N);
   w.vals_out = c.take<int32_t>(N);
-  const int64_t nchunks = (N + EB_CHUNK - 1) / EB_CHUNK;
-  w.partial = c.take<float>(nchunks * 2 * 2 * D);
+  w.acc_buf = c.take<float>(N * 2 * D);
   w.cub_bytes = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, w.cub_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr,
                                   (const int32_t*)nullptr, (int32_t*)nullptr, (int)std::max<int64_t>(N, 1), 0, 32);
@@ -651,7 +625,7 @@ static int run_emb_bwd(const ncf_adam_cfg* adam, const ncf_tables* T, const floa
   A.d_x = d_x;
   A.dense = dense;
   A.dense_grad = dense_grad;
-  A.partial = w.partial;
+  A.acc_buf = w.acc_buf;
   A.N = N;
   A.mode = adam->emb_mode;
   A.accumulate_wmf = (side == 0 && !upstream) ? 1 : 0;

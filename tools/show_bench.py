@@ -1,0 +1,15 @@
+#!/usr/bin/env python3
+"""Print the essentials of a bench.py JSON line read from stdin (or the error text)."""
+import json
+import sys
+
+txt = sys.stdin.read().strip().splitlines()
+line = next((ln for ln in reversed(txt) if ln.startswith("{")), None)
+if line is None:
+    print("NO JSON LINE:\n" + "\n".join(txt[-15:]))
+    sys.exit(0)
+d = json.loads(line)
+print(f"value {d['value']:.4g} {d['unit']}  ms/step {d['ms_per_step']:.3f}  e2e {d['e2e']['value']:.4g}  dtype {d['dtype']}  launches {d.get('gpu_launches')}")
+rf = d.get("roofline") or {}
+for k, v in (rf.get("kernels") or {}).items():
+    print(f"   {k}: {v['ms']:.3f} ms  frac {v['frac']:.3f}")
