@@ -372,18 +372,47 @@ __global__ void __launch_bounds__(EB_THREADS) emb_bwd_phase2_kernel(EmbBwdArgs A
     const uint32_t my_id = lane < cnt ? A.sorted_ids[p0 + lane] : 0xffffffffu;
     const uint32_t before = (p0 + lane > 0 && lane < cnt) ? A.sorted_ids[p0 + lane - 1] : 0xfffffffeu;
     uint32_t starts = __ballot_sync(0xffffffffu, lane < cnt && (p0 + lane == 0 || before != my_id));
-    while (starts) {
-      const int i = __ffs(starts) - 1;
-      starts &= starts - 1;
-      const uint32_t id = __shfl_sync(0xffffffffu, my_id, i);
+    // software pipeline over the run starts: the loads of the NEXT run are in flight while this one is applied
+    struct Loads { float4 w, m, v, a; };
+    auto issue = [&](int i, uint32_t id) {
+      Loads L;
       const int64_t o = (int64_t)id * D + 4 * l16;
-      const float4 wrow = ld4(A.w[half] + o);
-      float4 mm = make_float4(0, 0, 0, 0), vv = mm;
+      L.w = ld4(A.w[half] + o);
+      L.m = make_float4(0, 0, 0, 0);
+      L.v = L.m;
       if (adam) {
-        mm = ld4(A.m[half] + o);
-        vv = ld4(A.v[half] + o);
+        L.m = ld4(A.m[half] + o);
+        L.v = ld4(A.v[half] + o);
       }
-      float4 acc = ld4(A.acc_buf + ((p0 + i) * 2 + half) * D + 4 * l16);
+      L.a = ld4(A.acc_buf + ((p0 + i) * 2 + half) * D + 4 * l16);
+      return L;
+    };
+    Loads nxt{};
+    int ni = -1;
+    uint32_t nid = 0;
+    if (starts) {
+      ni = __ffs(starts) - 1;
+      starts &= starts - 1;
+      nid = __shfl_sync(0xffffffffu, my_id, ni);
+      nxt = issue(ni, nid);
+    }
+    while (ni >= 0) {
+      const int i = ni;
+      const uint32_t id = nid;
+      const Loads cur = nxt;
+      if (starts) {
+        ni = __ffs(starts) - 1;
+        starts &= starts - 1;
+        nid = __shfl_sync(0xffffffffu, my_id, ni);
+        nxt = issue(ni, nid);
+      } else {
+        ni = -1;
+      }
+      const int64_t o = (int64_t)id * D + 4 * l16;
+      const float4 wrow = cur.w;
+      float4 mm = cur.m, vv = cur.v;
+      float4 acc = cur.a;
+      (void)i;
       // does the run leave this chunk?  (its last in-chunk element is the chunk's last element)
       const uint32_t last_id = __shfl_sync(0xffffffffu, my_id, cnt - 1);
       if (last_id == id) {

@@ -368,101 +368,108 @@ static int launch_relu_ln_drop_bwd(const float* dY, const float* Rsv, const floa
 }
 
 // =============================================================================================
-// attention core over the S rows of one interaction (architecture.py:40-55); thread = (row, head)
+// attention core over the S rows of one interaction (architecture.py:40-55)
 //   q [N,64]; kv [N,128] = [k | v]; ctx [N,64]
+// 16 lanes own one (interaction, head): lane d holds element d of the head slice of every row, so
+// each row slice is ONE coalesced 64-byte load per half warp (instead of every thread re-reading whole
+// rows), the S x S dot products are 16-lane shuffle all-reduces, and the outputs are written the
+// same way.  The keep mask of the probability dropout is drawn once per element and shared by ballot.
 // =============================================================================================
-__device__ __forceinline__ void load16(const float* p, float* d) {
+__device__ __forceinline__ float hw_allreduce(float v) {      // sum over the 16 lanes of a half warp
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float4 t = ldg4(p + 4 * i);
-    d[4 * i] = t.x; d[4 * i + 1] = t.y; d[4 * i + 2] = t.z; d[4 * i + 3] = t.w;
-  }
-}
-__device__ __forceinline__ void store16(float* p, const float* d) {
-#pragma unroll
-  for (int i = 0; i < 4; ++i) st4(p + 4 * i, make_float4(d[4 * i], d[4 * i + 1], d[4 * i + 2], d[4 * i + 3]));
-}
-__device__ __forceinline__ float dot16(const float* a, const float* b) {
-  float s = 0.f;
-#pragma unroll
-  for (int i = 0; i < 16; ++i) s = fmaf(a[i], b[i], s);
-  return s;
-}
-// softmax probabilities of query row (group g, index i) for head h; returns p[0..S)
-__device__ __forceinline__ void attn_probs(const float* qv, const float* __restrict__ kv, int64_t g, int S, int h,
-                                           float* p) {
-  float mx = -INFINITY;
-  for (int j = 0; j < S; ++j) {
-    float kk[16];
-    load16(kv + (g * S + j) * (2 * D) + h * HD, kk);
-    p[j] = dot16(qv, kk) * 0.25f;   // / sqrt(head_dim = 16)
-    mx = fmaxf(mx, p[j]);
-  }
-  float sum = 0.f;
-  for (int j = 0; j < S; ++j) {
-    p[j] = expf(p[j] - mx);
-    sum += p[j];
-  }
-  const float inv = 1.0f / sum;
-  for (int j = 0; j < S; ++j) p[j] *= inv;
+  for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
 }
 
-__global__ void __launch_bounds__(256) attn_core_fwd_kernel(const float* __restrict__ q, const float* __restrict__ kv,
-                                                            float* __restrict__ ctx, int64_t N, int S, DropoutRng rng) {
-  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= N * HEADS) return;
-  const int64_t n = t / HEADS;
-  const int h = (int)(t % HEADS);
-  const int64_t g = n / S;
-  const int i = (int)(n % S);
-  float qv[16], p[NCF_MAX_S], o[16];
-  load16(q + n * D + h * HD, qv);
-  attn_probs(qv, kv, g, S, h, p);
-#pragma unroll
-  for (int c = 0; c < 16; ++c) o[c] = 0.f;
-  for (int j = 0; j < S; ++j) {
-    float pj = p[j];
-    if (rng.thresh != 0u) {
-      const uint64_t e = (((uint64_t)g * HEADS + h) * S + i) * S + j;
-      pj = rng.keep(e) ? pj * rng.scale : 0.f;
-    }
-    float vv[16];
-    load16(kv + (g * S + j) * (2 * D) + D + h * HD, vv);
-#pragma unroll
-    for (int c = 0; c < 16; ++c) o[c] = fmaf(pj, vv[c], o[c]);
-  }
-  store16(ctx + n * D + h * HD, o);
-}
-
-// backward: one warp per head, lane = (group slot, row index inside the group).  Phase 1 treats the
-// lane's row as a QUERY (probabilities, d scores, dq); the S x S score-gradient blocks are then
-// exchanged with shuffles and phase 2 treats the row as a KEY (dk, dv).  No redundant recomputation.
+// bit e of the result = keep decision of element base + e (e < S*S), identical on all 16 lanes
 template <int S>
-__global__ void __launch_bounds__(128) attn_core_bwd_kernel(const float* __restrict__ q, const float* __restrict__ kv,
-                                                            const float* __restrict__ dctx, float* __restrict__ dq,
-                                                            float* __restrict__ dkv, int64_t N, DropoutRng rng) {
-  constexpr int G = 32 / S;                      // groups per warp
-  const int lane = threadIdx.x & 31, h = threadIdx.x >> 5;
-  const int gl = lane / S, i = lane % S;
-  const int64_t ngroups = N / S;
-  const int64_t g = (int64_t)blockIdx.x * G + gl;
-  const bool live = gl < G && g < ngroups;
-  const int64_t gg = live ? g : 0;
-  const int64_t n = gg * S + i;
-  const int base = gl * S;
+__device__ __forceinline__ uint64_t attn_keep_mask(const DropoutRng& rng, uint64_t base, int d, int lane) {
+  uint64_t m = ~0ull;
+  if (rng.thresh != 0u) {
+    m = 0;
+#pragma unroll
+    for (int r = 0; r < (S * S + 15) / 16; ++r) {
+      const int e = r * 16 + d;
+      const bool k = e < S * S ? rng.keep(base + e) : false;
+      const uint32_t b = __ballot_sync(0xffffffffu, k);
+      m |= (uint64_t)((lane & 16) ? (b >> 16) : (b & 0xffffu)) << (16 * r);
+    }
+  }
+  return m;
+}
 
-  float qv[16], dc[16];
-  load16(q + n * D + h * HD, qv);
-  load16(dctx + n * D + h * HD, dc);
-  // ---- phase 1: this row as query ------------------------------------------------------------
-  float p[S], ds[S], pd[S];
-  {
-    float mx = -INFINITY;
+template <int S>
+__global__ void __launch_bounds__(256) attn_core_fwd_kernel(const float* __restrict__ q, const float* __restrict__ kv,
+                                                            float* __restrict__ ctx, int64_t N, DropoutRng rng) {
+  const int lane = threadIdx.x & 31, d = lane & 15;
+  const int64_t hw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4;     // (group, head)
+  const int64_t ngh = (N / S) * HEADS;
+  const bool live = hw < ngh;
+  const int64_t g = live ? hw / HEADS : 0;
+  const int h = live ? (int)(hw % HEADS) : 0;
+  float qv[S], kk[S], vv[S];
+#pragma unroll
+  for (int i = 0; i < S; ++i) {
+    const int64_t n = g * S + i;
+    qv[i] = __ldg(q + n * D + h * HD + d);
+    kk[i] = __ldg(kv + n * (2 * D) + h * HD + d);
+    vv[i] = __ldg(kv + n * (2 * D) + D + h * HD + d);
+  }
+  const uint64_t keep = attn_keep_mask<S>(rng, ((uint64_t)g * HEADS + h) * (S * S), d, lane);
+#pragma unroll
+  for (int i = 0; i < S; ++i) {
+    float p[S], mx = -INFINITY;
 #pragma unroll
     for (int j = 0; j < S; ++j) {
-      float kk[16];
-      load16(kv + (gg * S + j) * (2 * D) + h * HD, kk);
-      p[j] = dot16(qv, kk) * 0.25f;
+      p[j] = hw_allreduce(qv[i] * kk[j]) * 0.25f;       // / sqrt(head_dim = 16)
+      mx = fmaxf(mx, p[j]);
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < S; ++j) {
+      p[j] = expf(p[j] - mx);
+      sum += p[j];
+    }
+    const float inv = 1.0f / sum;
+    float o = 0.f;
+#pragma unroll
+    for (int j = 0; j < S; ++j) {
+      const float pj = ((keep >> (i * S + j)) & 1ull) ? p[j] * inv * rng.scale : 0.f;
+      o = fmaf(pj, vv[j], o);
+    }
+    if (live) ctx[(g * S + i) * D + h * HD + d] = o;
+  }
+}
+
+template <int S>
+__global__ void __launch_bounds__(256) attn_core_bwd_kernel(const float* __restrict__ q, const float* __restrict__ kv,
+                                                            const float* __restrict__ dctx, float* __restrict__ dq,
+                                                            float* __restrict__ dkv, int64_t N, DropoutRng rng) {
+  const int lane = threadIdx.x & 31, d = lane & 15;
+  const int64_t hw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+  const int64_t ngh = (N / S) * HEADS;
+  const bool live = hw < ngh;
+  const int64_t g = live ? hw / HEADS : 0;
+  const int h = live ? (int)(hw % HEADS) : 0;
+  float qv[S], kk[S], vv[S], dc[S], dk[S], dv[S];
+#pragma unroll
+  for (int i = 0; i < S; ++i) {
+    const int64_t n = g * S + i;
+    qv[i] = __ldg(q + n * D + h * HD + d);
+    kk[i] = __ldg(kv + n * (2 * D) + h * HD + d);
+    vv[i] = __ldg(kv + n * (2 * D) + D + h * HD + d);
+    dc[i] = __ldg(dctx + n * D + h * HD + d);
+    dk[i] = 0.f;
+    dv[i] = 0.f;
+  }
+  const uint64_t keep = attn_keep_mask<S>(rng, ((uint64_t)g * HEADS + h) * (S * S), d, lane);
+#pragma unroll
+  for (int i = 0; i < S; ++i) {
+    float p[S], dp[S], mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < S; ++j) {
+      p[j] = hw_allreduce(qv[i] * kk[j]) * 0.25f;
+      dp[j] = hw_allreduce(dc[i] * vv[j]);              // dL/dp'_ij
       mx = fmaxf(mx, p[j]);
     }
     float sum = 0.f;
@@ -476,75 +483,57 @@ __global__ void __launch_bounds__(128) attn_core_bwd_kernel(const float* __restr
 #pragma unroll
     for (int j = 0; j < S; ++j) {
       p[j] *= inv;
-      float vv[16];
-      load16(kv + (gg * S + j) * (2 * D) + D + h * HD, vv);
-      float ks = 1.f;
-      if (rng.thresh != 0u) ks = rng.keep((((uint64_t)gg * HEADS + h) * S + i) * S + j) ? rng.scale : 0.f;
-      pd[j] = p[j] * ks;                 // dropped probability used by the forward
-      ds[j] = dot16(dc, vv) * ks;        // dL/dp_ij
-      dot = fmaf(p[j], ds[j], dot);
+      const float ks = ((keep >> (i * S + j)) & 1ull) ? rng.scale : 0.f;
+      dv[j] = fmaf(p[j] * ks, dc[i], dv[j]);            // dv_j += p'_ij dctx_i
+      dp[j] *= ks;                                      // dL/dp_ij
+      dot = fmaf(p[j], dp[j], dot);
     }
-    float dqv[16];
-#pragma unroll
-    for (int c = 0; c < 16; ++c) dqv[c] = 0.f;
+    float dqi = 0.f;
 #pragma unroll
     for (int j = 0; j < S; ++j) {
-      ds[j] = p[j] * (ds[j] - dot);      // dL/ds_ij
-      float kk[16];
-      load16(kv + (gg * S + j) * (2 * D) + h * HD, kk);
-#pragma unroll
-      for (int c = 0; c < 16; ++c) dqv[c] = fmaf(ds[j] * 0.25f, kk[c], dqv[c]);
+      const float ds = p[j] * (dp[j] - dot) * 0.25f;    // dL/ds_ij (scaled by 1/sqrt(16))
+      dqi = fmaf(ds, kk[j], dqi);
+      dk[j] = fmaf(ds, qv[i], dk[j]);
     }
-    if (live) store16(dq + n * D + h * HD, dqv);
-  }
-  // ---- phase 2: this row as key t = i: needs column t of ds and pd over all queries ii ------------
-  float dkk[16], dvv[16];
-#pragma unroll
-  for (int c = 0; c < 16; ++c) dkk[c] = dvv[c] = 0.f;
-#pragma unroll
-  for (int ii = 0; ii < S; ++ii) {
-    float ds_it = 0.f, pd_it = 0.f;
-#pragma unroll
-    for (int jj = 0; jj < S; ++jj) {
-      const float a = __shfl_sync(0xffffffffu, ds[jj], (base + ii) & 31);
-      const float b = __shfl_sync(0xffffffffu, pd[jj], (base + ii) & 31);
-      if (jj == i) {
-        ds_it = a;
-        pd_it = b;
-      }
-    }
-    float qi[16], dci[16];
-    load16(q + (gg * S + ii) * D + h * HD, qi);
-    load16(dctx + (gg * S + ii) * D + h * HD, dci);
-#pragma unroll
-    for (int c = 0; c < 16; ++c) {
-      dkk[c] = fmaf(ds_it * 0.25f, qi[c], dkk[c]);
-      dvv[c] = fmaf(pd_it, dci[c], dvv[c]);
-    }
+    if (live) dq[(g * S + i) * D + h * HD + d] = dqi;
   }
   if (live) {
-    store16(dkv + n * (2 * D) + h * HD, dkk);
-    store16(dkv + n * (2 * D) + D + h * HD, dvv);
+#pragma unroll
+    for (int j = 0; j < S; ++j) {
+      dkv[(g * S + j) * (2 * D) + h * HD + d] = dk[j];
+      dkv[(g * S + j) * (2 * D) + D + h * HD + d] = dv[j];
+    }
   }
 }
 
+#define NCF_DISPATCH_S(S_, CALL)                                     \
+  switch (S_) {                                                      \
+    case 1: { constexpr int SS = 1; CALL; break; }                   \
+    case 2: { constexpr int SS = 2; CALL; break; }                   \
+    case 3: { constexpr int SS = 3; CALL; break; }                   \
+    case 4: { constexpr int SS = 4; CALL; break; }                   \
+    case 5: { constexpr int SS = 5; CALL; break; }                   \
+    case 6: { constexpr int SS = 6; CALL; break; }                   \
+    case 7: { constexpr int SS = 7; CALL; break; }                   \
+    case 8: { constexpr int SS = 8; CALL; break; }                   \
+    default: set_error("attention: S=%d unsupported", S_); return NCF_ERR_ARG; \
+  }
+
+static int launch_attn_core_fwd(const float* q, const float* kv, float* ctx, int64_t N, int S, const DropoutRng& rng,
+                                cudaStream_t st) {
+  if (N == 0) return NCF_OK;
+  const int64_t threads = (N / S) * HEADS * 16;
+  const unsigned grid = (unsigned)((threads + 255) / 256);
+  NCF_DISPATCH_S(S, (attn_core_fwd_kernel<SS><<<grid, 256, 0, st>>>(q, kv, ctx, N, rng)));
+  NCF_LAUNCH_CHECK();
+  return NCF_OK;
+}
 static int launch_attn_core_bwd(const float* q, const float* kv, const float* dctx, float* dq, float* dkv, int64_t N, int S,
                                 const DropoutRng& rng, cudaStream_t st) {
   if (N == 0) return NCF_OK;
-  const int64_t ngroups = N / S;
-  const int G = 32 / S;
-  const unsigned grid = (unsigned)((ngroups + G - 1) / G);
-  switch (S) {
-    case 1: attn_core_bwd_kernel<1><<<grid, 128, 0, st>>>(q, kv, dctx, dq, dkv, N, rng); break;
-    case 2: attn_core_bwd_kernel<2><<<grid, 128, 0, st>>>(q, kv, dctx, dq, dkv, N, rng); break;
-    case 3: attn_core_bwd_kernel<3><<<grid, 128, 0, st>>>(q, kv, dctx, dq, dkv, N, rng); break;
-    case 4: attn_core_bwd_kernel<4><<<grid, 128, 0, st>>>(q, kv, dctx, dq, dkv, N, rng); break;
-    case 5: attn_core_bwd_kernel<5><<<grid, 128, 0, st>>>(q, kv, dctx, dq, dkv, N, rng); break;
-    case 6: attn_core_bwd_kernel<6><<<grid, 128, 0, st>>>(q, kv, dctx, dq, dkv, N, rng); break;
-    case 7: attn_core_bwd_kernel<7><<<grid, 128, 0, st>>>(q, kv, dctx, dq, dkv, N, rng); break;
-    case 8: attn_core_bwd_kernel<8><<<grid, 128, 0, st>>>(q, kv, dctx, dq, dkv, N, rng); break;
-    default: set_error("attention backward: S=%d unsupported", S); return NCF_ERR_ARG;
-  }
+  const int64_t threads = (N / S) * HEADS * 16;
+  const unsigned grid = (unsigned)((threads + 255) / 256);
+  NCF_DISPATCH_S(S, (attn_core_bwd_kernel<SS><<<grid, 256, 0, st>>>(q, kv, dctx, dq, dkv, N, rng)));
   NCF_LAUNCH_CHECK();
   return NCF_OK;
 }
@@ -732,9 +721,7 @@ int tower_f32_forward(const ncf_run_cfg& cfg, const float* dense, int64_t N, con
       NCF_TRY((launch_linear<64, false, EPI_NONE>(lin(w.xu, D, P + NCF_OFF(NCF_P_Q_W), D, P + NCF_OFF(NCF_P_Q_B), w.q, D, N, D), st)));
       NCF_TRY((launch_linear<128, false, EPI_NONE>(lin(w.xp, D, P + NCF_OFF(NCF_P_K_W), D, P + NCF_OFF(NCF_P_K_B), w.kv, 2 * D, N, D), st)));
     }
-    const int64_t threads = N * HEADS;
-    attn_core_fwd_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(w.q, w.kv, w.ctx, N, S, make_rng(cfg, 0));
-    NCF_LAUNCH_CHECK();
+    NCF_TRY(launch_attn_core_fwd(w.q, w.kv, w.ctx, N, S, make_rng(cfg, 0), st));
   } else if (tc) {
     NCF_TRY(tc_proj_forward(0, w.xp, P + NCF_OFF(NCF_P_V_W), P + NCF_OFF(NCF_P_V_B), w.ctx, N, st));
   } else {
