@@ -140,8 +140,14 @@ def cpu_reference_rate(users, items, B_sample, steps, warmup, threads):
     from oracle import ncf_oracle as O
     torch.set_num_threads(threads)
     g = torch.Generator().manual_seed(1234)
+    p = cpu_params(users, items, g)
+    return _cpu_train_rate(p, users, items, B_sample, steps, warmup, g)
+
+
+def cpu_params(users, items, g):
+    import torch
+    from oracle import ncf_oracle as O
     p = {}
-    dims = {"mf_norm": 64, "mlp_norm": 64}
     for k, rows in zip(O.TABLE_KEYS, (users, items, users, items)):
         p[k] = (torch.rand(rows, 64, generator=g) * 2 - 1) * (1.0 / rows) ** 0.5
     shapes = {"mf_norm.weight": (64,), "mf_norm.bias": (64,), "mlp_norm.weight": (64,), "mlp_norm.bias": (64,),
@@ -155,6 +161,13 @@ def cpu_reference_rate(users, items, B_sample, steps, warmup, threads):
         shapes[f"user_product_attention.{n}_proj.bias"] = (64,)
     for k, shp in shapes.items():
         p[k] = torch.ones(shp) if (k.endswith("weight") and len(shp) == 1) else (torch.rand(shp, generator=g) - 0.5) * 0.2
+    p["temporal_encoding.hour_embed.weight"] = torch.zeros(24, 32)
+    return p
+
+
+def _cpu_train_rate(p, users, items, B_sample, steps, warmup, g):
+    import torch
+    from oracle import ncf_oracle as O
     batches = make_batches(users, items, B_sample, 2, 99)
     state = {}
     times = []
@@ -187,6 +200,109 @@ def time_kernel(fn, iters, stream_sync):
     return e0.elapsed_time(e1) / iters
 
 
+SCORE_SHAPES = {"score": (1000000, 10000000, "config[4] full-catalogue scoring + top-100: 1M users x 10M items"),
+                "score_small": (138493, 26744, "full-catalogue scoring + top-100 at the config[2] shape")}
+
+
+def run_score(args):
+    """Full-catalogue scoring + top-100 (app.py:43-77 at scale).  A step scores `--batch` users (default 256
+    per GPU) against ALL items; metric = (user,item) pairs scored per second.  Users are sharded over the
+    ranks, the folded item side is replicated."""
+    import torch
+    import torch.distributed as dist
+    import ncf_b200
+    from ncf_b200 import _lib
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    users, items, desc = SCORE_SHAPES[args.workload]
+    n = args.batch or 256
+    k = 100
+    users_local = (users + world - 1) // world
+    model = build_model(users_local, items, dev, "fp32").eval()      # same seed on every rank: replicated item side
+    scorer = ncf_b200.CatalogueScorer(model)
+    g = torch.Generator().manual_seed(77 + rank)
+    dev_b = [torch.randint(0, users_local, (n,), generator=g).to(dev) for _ in range(4)]
+    host_b = [torch.randint(0, users_local, (n,), generator=g).pin_memory() for _ in range(4)]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    for s in range(args.warmup):
+        scorer.topk(dev_b[s % 4], k)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = int(lib.ncf_launch_count())
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for s in range(args.steps):
+        scorer.topk(dev_b[s % 4], k)
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = int(lib.ncf_launch_count()) - l0
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        idx, sc = scorer.topk(host_b[s % 4].to(dev, non_blocking=True), k)
+        idx_h, sc_h = idx.cpu(), sc.cpu()
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms_total, e2e_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, e2e_ms = float(t[0]), float(t[1])
+    if rank == 0:
+        pairs = world * n * items * args.steps
+        pk = peaks()
+        value = pairs / (ms_total / 1e3)
+        tflops = value * 128 / 1e12
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cpu = cpu_score_rate(items, os.cpu_count() or 1)
+        line = {"metric": "scoring_samples_per_s", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+                "config": {"workload": f"{args.workload}: {desc}", "users_per_step_per_gpu": n, "items": items, "top_k": k,
+                           "l2": f"folded item table {items * 260 / 1e6:.0f} MB streamed per user tile"},
+                "users_per_s": world * n * args.steps / (ms_total / 1e3),
+                "e2e": {"value": pairs / (e2e_ms / 1e3), "unit": "pairs/s", "h2d_bytes_per_step": n * 8,
+                        "d2h_bytes_per_step": n * k * 12, "ms_per_step": e2e_ms / args.steps},
+                "gpu_launches": launches, "clocks": clocks,
+                "roofline": {"kernel": "score_topk_kernel", "bound": "tensor", "achieved": tflops, "peak": pk["bf16_tflops"],
+                             "unit": "TFLOP/s", "frac": tflops / pk["bf16_tflops"], "traffic": None,
+                             "peak_source": pk["source"] + " (bf16 burst); kernel is fp32 CUDA-core in this round"},
+                "cpu_baseline": cpu}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_score_rate(items, threads):
+    """Reference scoring on the host: forward_simple over the catalogue for one user (app.py:48-67) + stable
+    top-100, through the oracle port, on a bounded sample of the catalogue."""
+    import torch
+    from oracle import ncf_oracle as O
+    torch.set_num_threads(threads)
+    g = torch.Generator().manual_seed(5)
+    sample = min(items, 200000)
+    p = cpu_params(1000, sample, g)
+    t0 = time.perf_counter()
+    s = O.forward_simple(p, torch.zeros(sample, dtype=torch.long), torch.arange(sample))
+    O.topk_stable(s, 100)
+    dt = time.perf_counter() - t0
+    return {"value": sample / dt, "unit": "pairs/s", "cores": threads, "kind": "port",
+            "sample": f"1 user x {sample} of the {items} items (forward_simple + stable top-100)"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -211,7 +327,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS) + sorted(SCORE_SHAPES))
     ap.add_argument("--batch", type=int, default=0, help="interactions per step per GPU (default per workload)")
     ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "bf16"])
     ap.add_argument("--table-mode", default="auto", choices=["auto", "fused_dense_equiv", "fused_sparse"])
@@ -222,6 +338,20 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
+    if args.workload in SCORE_SHAPES:
+        if args.impl == "reference":
+            if int(os.environ.get("RANK", "0")) == 0:
+                users, items, desc = SCORE_SHAPES[args.workload]
+                cpu = cpu_score_rate(items, os.cpu_count() or 1)
+                print(json.dumps({"impl": "reference", "metric": "scoring_samples_per_s", "value": cpu["value"],
+                                  "unit": "pairs/s", "n_gpus": args.gpus, "steps": 1, "warmup": 0, "higher_is_better": True,
+                                  "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+                                  "config": {"workload": f"{args.workload}: {desc}"}, "cpu_baseline": cpu,
+                                  "e2e": {"value": cpu["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0,
+                                          "d2h_bytes_per_step": 0}}))
+            return
+        run_score(args)
+        return
     if args.impl == "reference":
         run_reference(args)
         return

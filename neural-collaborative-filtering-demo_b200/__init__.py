@@ -9,8 +9,8 @@ from .kjt import KeyedJaggedTensor, make_kjt  # noqa: F401
 from .metrics import calculate_metrics  # noqa: F401
 from .scoring import CatalogueScorer, get_recommendations  # noqa: F401
 from .trainer import ModelTrainer, NCFTrainEngine  # noqa: F401
-from .sharding import ShardedNCFEngine, ShardRouter  # noqa: F401
+from .sharding import ShardedCatalogueScorer, ShardedNCFEngine, ShardRouter  # noqa: F401
 
 __all__ = ["AdvancedNCF", "MultiHeadAttention", "TemporalEncoding", "CategoryHierarchy", "KeyedJaggedTensor",
            "make_kjt", "NcfError", "load_library", "calculate_metrics", "CatalogueScorer", "get_recommendations",
-           "ModelTrainer", "NCFTrainEngine", "ShardedNCFEngine", "ShardRouter"]
+           "ModelTrainer", "NCFTrainEngine", "ShardedNCFEngine", "ShardRouter", "ShardedCatalogueScorer"]

@@ -13,9 +13,9 @@
 
 namespace ncf {
 
-__global__ void iota_kernel(int64_t* p, int64_t n) {
+__global__ void iota_kernel(int64_t* p, int64_t n, int64_t start) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) p[i] = i;
+  if (i < n) p[i] = start + i;
 }
 
 __global__ void item_fold_kernel(const float* __restrict__ ymf, const float* __restrict__ mlp_pred,
@@ -218,6 +218,8 @@ static ncf_run_cfg eval_cfg() {
   return c;
 }
 
+constexpr int64_t FOLD_CHUNK = 1 << 20;      // items folded per pass (bounds the tower workspace)
+
 struct FoldWs {
   int64_t* ids;
   float* ymf;
@@ -225,40 +227,46 @@ struct FoldWs {
   void* tower;
   int64_t tower_bytes, total;
 };
-static FoldWs carve_fold(void* ws, int64_t I) {
+static FoldWs carve_fold(void* ws, int64_t chunk) {
   FoldWs f;
   Carver c(ws);
-  f.ids = c.take<int64_t>(I);
-  f.ymf = c.take<float>(I * D);
-  f.out = c.take<float>(I);
-  f.tower_bytes = carve_tower_ws(nullptr, I, eval_cfg()).total;
+  f.ids = c.take<int64_t>(chunk);
+  f.ymf = c.take<float>(chunk * D);
+  f.out = c.take<float>(chunk);
+  f.tower_bytes = carve_tower_ws(nullptr, chunk, eval_cfg()).total;
   f.tower = c.take<char>(f.tower_bytes);
   f.total = align_up(c.used, 256);
   return f;
 }
 
-extern "C" int64_t ncf_item_fold_workspace_bytes(int64_t I) { return carve_fold(nullptr, std::max<int64_t>(I, 1)).total; }
+extern "C" int64_t ncf_item_fold_workspace_bytes(int64_t I) {
+  return carve_fold(nullptr, std::min<int64_t>(std::max<int64_t>(I, 1), FOLD_CHUNK)).total;
+}
 
 extern "C" int ncf_item_fold(const ncf_tables* T, const float* dense, float* p_hat, float* g, void* workspace,
                              int64_t workspace_bytes, void* stream) {
   NCF_REQUIRE(T && dense && p_hat && g && workspace, "item_fold: null argument");
   const int64_t I = T->rows_item;
-  NCF_REQUIRE(I > 0 && I < ((int64_t)1 << 31), "item_fold: bad item count");
-  FoldWs f = carve_fold(workspace, I);
+  NCF_REQUIRE(I > 0 && I < ((int64_t)1 << 32) - 1, "item_fold: bad item count");
+  const int64_t chunk = std::min<int64_t>(I, FOLD_CHUNK);
+  FoldWs f = carve_fold(workspace, chunk);
   if (workspace_bytes < f.total) {
     set_error("item_fold: workspace %lld < %lld", (long long)workspace_bytes, (long long)f.total);
     return NCF_ERR_WORKSPACE;
   }
   cudaStream_t st = (cudaStream_t)stream;
   const ncf_run_cfg cfg = eval_cfg();
-  TowerWs w = carve_tower_ws(f.tower, I, cfg);
-  iota_kernel<<<(unsigned)((I + 255) / 256), 256, 0, st>>>(f.ids, I);
-  NCF_LAUNCH_CHECK();
-  NCF_TRY(ncf_gather_ln(T, dense, 1, f.ids, I, f.ymf, w.xp, stream));
-  NCF_CUDA(cudaMemsetAsync(w.mf_pred, 0, sizeof(float) * I, st));
-  NCF_TRY(tower_f32_forward(cfg, dense, I, nullptr, nullptr, f.out, w, st));
-  item_fold_kernel<<<(unsigned)((I * 16 + 255) / 256), 256, 0, st>>>(f.ymf, w.mlp_pred, dense, p_hat, g, I);
-  NCF_LAUNCH_CHECK();
+  for (int64_t start = 0; start < I; start += chunk) {
+    const int64_t n = std::min<int64_t>(chunk, I - start);
+    TowerWs w = carve_tower_ws(f.tower, n, cfg);
+    iota_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(f.ids, n, start);
+    NCF_LAUNCH_CHECK();
+    NCF_TRY(ncf_gather_ln(T, dense, 1, f.ids, n, f.ymf, w.xp, stream));
+    NCF_CUDA(cudaMemsetAsync(w.mf_pred, 0, sizeof(float) * n, st));
+    NCF_TRY(tower_f32_forward(cfg, dense, n, nullptr, nullptr, f.out, w, st));
+    item_fold_kernel<<<(unsigned)((n * 16 + 255) / 256), 256, 0, st>>>(f.ymf, w.mlp_pred, dense, p_hat + start * D, g + start, n);
+    NCF_LAUNCH_CHECK();
+  }
   return NCF_OK;
 }
 

@@ -278,3 +278,59 @@ class ShardedNCFEngine:
             dist.all_gather(parts, pad, group=self.group)
             out.append(torch.cat(parts)[:self.U if k % 2 == 0 else self.I])
         return out
+
+
+class ShardedCatalogueScorer:
+    """Full-catalogue top-k with the tables of a ShardedNCFEngine (scoring): USERS stay
+    sharded, the folded item side (P_hat [I,64], g [I]) is replicated by one all-gather, and every rank
+    ranks the users it owns against the whole catalogue - no merge step, so the result does not depend
+    on the number of GPUs."""
+
+    def __init__(self, engine: ShardedNCFEngine):
+        self.e = engine
+        self.lib = engine.lib
+        self.p_hat = None
+        self.g = None
+        self.refresh()
+
+    @torch.no_grad()
+    def refresh(self):
+        e = self.e
+        dev = e.device
+        rows = max(e.rows_i, 1)
+        p_local = torch.zeros(shard_block(e.I, e.world), 64, device=dev)
+        g_local = torch.zeros(shard_block(e.I, e.world), device=dev)
+        if e.rows_i:
+            nbytes = int(self.lib.ncf_item_fold_workspace_bytes(rows))
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            tabs = e._tables()
+            _lib.check(self.lib.ncf_item_fold(C.byref(tabs), _lib.ptr(e.model._flat), _lib.ptr(p_local), _lib.ptr(g_local),
+                                              _lib.ptr(ws), nbytes, e._s()), "ncf_item_fold")
+        if e.world > 1:
+            ps = [torch.empty_like(p_local) for _ in range(e.world)]
+            gs = [torch.empty_like(g_local) for _ in range(e.world)]
+            dist.all_gather(ps, p_local, group=e.group)
+            dist.all_gather(gs, g_local, group=e.group)
+            self.p_hat = torch.cat(ps)[:e.I].contiguous()
+            self.g = torch.cat(gs)[:e.I].contiguous()
+        else:
+            self.p_hat, self.g = p_local[:e.I].contiguous(), g_local[:e.I].contiguous()
+
+    @torch.no_grad()
+    def topk_local_users(self, local_user_ids: torch.Tensor, k: int):
+        """(global item indices [n,k], scores [n,k]) for users given by their LOCAL row on this rank."""
+        e = self.e
+        u = local_user_ids.reshape(-1).to(device=e.device, dtype=torch.long).contiguous()
+        n = u.numel()
+        k_eff = min(k, e.I)
+        idx = torch.empty(n, k_eff, dtype=torch.long, device=e.device)
+        sc = torch.empty(n, k_eff, dtype=torch.float32, device=e.device)
+        if n == 0:
+            return idx, sc
+        nbytes = int(self.lib.ncf_score_topk_workspace_bytes(n, e.I, k_eff))
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=e.device)
+        tabs = e._tables()
+        _lib.check(self.lib.ncf_score_topk(C.byref(tabs), _lib.ptr(e.model._flat), _lib.ptr(self.p_hat), _lib.ptr(self.g),
+                                           _lib.ptr(u), n, e.I, k_eff, _lib.ptr(idx), _lib.ptr(sc), _lib.ptr(ws), nbytes,
+                                           e._s()), "ncf_score_topk")
+        return idx, sc

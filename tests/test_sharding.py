@@ -162,3 +162,32 @@ def test_emulated_cluster_matches_single_gpu_engine(world, precision):
     d[ncf_b200._lib.dense_layout()[0][9][1]:ncf_b200._lib.dense_layout()[0][9][1] + 64] = 0   # k_proj.bias: noise
     assert float((d > 5e-6).float().mean()) < 3e-3 and d.max() < 1.5e-3
     assert all(torch.equal(models[0]._flat, m._flat) for m in models[1:])
+
+
+@pytest.mark.gpu
+def test_sharded_scorer_equals_single_gpu_scorer():
+    """Users sharded / item side replicated: a world-size-1 ShardedCatalogueScorer on the engine's tables
+    returns exactly the single-GPU CatalogueScorer result (indices bit-exact)."""
+    import ncf_b200
+    from ncf_b200.sharding import ShardedCatalogueScorer, ShardedNCFEngine
+    U, I = 300, 1500
+    pg, _ = golden_params()
+    g = torch.Generator().manual_seed(8)
+    p = {k: v.clone() for k, v in pg.items()}
+    for k, rows in zip(O.TABLE_KEYS, (U, I, U, I)):
+        p[k] = (torch.rand(rows, 64, generator=g) * 2 - 1) * 0.05
+    m = ncf_b200.AdvancedNCF(U, I, 5, 24, dropout=0.0)
+    m.load_state_dict(p)
+    m = m.cuda().eval()
+    users = torch.arange(0, 40).cuda()
+    ref_idx, ref_sc = ncf_b200.CatalogueScorer(m).topk(users, 100)
+    eng = ShardedNCFEngine(m, U, I, init_tables=[p[k] for k in O.TABLE_KEYS], rank=0, world=1)
+    idx, sc = ShardedCatalogueScorer(eng).topk_local_users(users, 100)
+    assert torch.equal(idx, ref_idx) and torch.equal(sc, ref_sc)
+    # and against the oracle's stable order on the oracle's own scores
+    p_hat, gg = O.item_fold(p)
+    um = O.layer_norm(p[O.K_UMF][:40], p["mf_norm.weight"], p["mf_norm.bias"])
+    full = torch.sigmoid(um @ p_hat.t() + gg)
+    want = O.topk_stable(full, 100)
+    agree = (idx.cpu() == want).float().mean()
+    assert agree > 0.98          # only near-ties (gap below fp32 resolution of the two summation orders) may swap
