@@ -79,10 +79,7 @@ extern "C" int ncf_backward(const ncf_run_cfg* cfg, const ncf_adam_cfg* adam, co
   cudaStream_t st = (cudaStream_t)stream;
   NCF_TRY(tower_f32_backward(*cfg, dense, dense_grad, N, grad_out, w, st));
   if (adam->emb_mode != NCF_EMB_NONE) {
-    // item side first: it gathers the user MF rows, which the user-side pass then overwrites (Adam);
-    // the user side reads the item rows the forward saved.
-    NCF_TRY(ncf_emb_bwd_adam(adam, T, dense, dense_grad, 1, user_ids, item_ids, N, w.d_mf, w.dxp, nullptr, w.emb, w.emb_bytes, stream));
-    NCF_TRY(ncf_emb_bwd_adam(adam, T, dense, dense_grad, 0, user_ids, item_ids, N, w.d_mf, w.dxu, w.y_pmf, w.emb, w.emb_bytes, stream));
+    NCF_TRY(emb_bwd_both(adam, T, dense, dense_grad, user_ids, item_ids, N, w.d_mf, w.dxu, w.dxp, w.y_pmf, w.emb, w.emb_bytes, st));
     if (adam->emb_mode == NCF_EMB_ADAM_DENSE_EQUIV) NCF_TRY(ncf_emb_adam_sweep(adam, T, stream));
   }
   return NCF_OK;

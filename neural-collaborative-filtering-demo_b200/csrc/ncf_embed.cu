@@ -250,6 +250,7 @@ struct EmbBwdArgs {
   float* dense_grad;
   float* acc_buf;                 // [N][2][64] upstream sum of the run piece that starts at each sorted position
   int64_t N;
+  uint32_t id_off;                // sorted keys hold id + id_off (combined two-side sort)
   int32_t mode;                   // ncf_emb_mode
   int32_t accumulate_wmf;         // only one side adds d mf_output.weight
   AdamScalars adam;
@@ -320,7 +321,7 @@ __global__ void __launch_bounds__(EB_THREADS) emb_bwd_phase1_kernel(EmbBwdArgs A
                            : half ? A.d_x + (int64_t)row * D
                                   : (A.other_y ? A.other_y + (int64_t)row * D : A.other_mf + oid * D);
         x[u] = ldg4(src + 4 * l16);
-        sf[u] = wmf ? ld4(A.w[0] + (int64_t)idk[u] * D + 4 * l16) : make_float4(0, 0, 0, 0);   // own MF row (d mf_output.weight)
+        sf[u] = wmf ? ld4(A.w[0] + (int64_t)(idk[u] - A.id_off) * D + 4 * l16) : make_float4(0, 0, 0, 0);   // own MF row (d mf_output.weight)
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
@@ -376,7 +377,7 @@ __global__ void __launch_bounds__(EB_THREADS) emb_bwd_phase2_kernel(EmbBwdArgs A
     struct Loads { float4 w, m, v, a; };
     auto issue = [&](int i, uint32_t id) {
       Loads L;
-      const int64_t o = (int64_t)id * D + 4 * l16;
+      const int64_t o = (int64_t)(id - A.id_off) * D + 4 * l16;
       L.w = ld4(A.w[half] + o);
       L.m = make_float4(0, 0, 0, 0);
       L.v = L.m;
@@ -408,7 +409,7 @@ __global__ void __launch_bounds__(EB_THREADS) emb_bwd_phase2_kernel(EmbBwdArgs A
       } else {
         ni = -1;
       }
-      const int64_t o = (int64_t)id * D + 4 * l16;
+      const int64_t o = (int64_t)(id - A.id_off) * D + 4 * l16;
       const float4 wrow = cur.w;
       float4 mm = cur.m, vv = cur.v;
       float4 acc = cur.a;
@@ -436,7 +437,7 @@ __global__ void __launch_bounds__(EB_THREADS) emb_bwd_phase2_kernel(EmbBwdArgs A
         st4(A.w[half] + o, wn);
         st4(A.m[half] + o, mm);
         st4(A.v[half] + o, vv);
-        if (A.touched && lane == 0) A.touched[id] = 1;
+        if (A.touched && lane == 0) A.touched[id - A.id_off] = 1;
       }
     }
   }
@@ -590,17 +591,18 @@ struct EmbWs {
   size_t cub_bytes;
   int64_t total;
 };
+// sized for the combined two-side sort (2N keys); the one-side entry points use the first half
 static EmbWs carve_emb_ws(void* ws, int64_t N) {
   EmbWs w;
   Carver c(ws);
-  w.keys_in = c.take<uint32_t>(N);
-  w.keys_out = c.take<uint32_t>(N);
-  w.vals_in = c.take<int32_t>(N);
-  w.vals_out = c.take<int32_t>(N);
+  w.keys_in = c.take<uint32_t>(2 * N);
+  w.keys_out = c.take<uint32_t>(2 * N);
+  w.vals_in = c.take<int32_t>(2 * N);
+  w.vals_out = c.take<int32_t>(2 * N);
   w.acc_buf = c.take<float>(N * 2 * D);
   w.cub_bytes = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, w.cub_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr,
-                                  (const int32_t*)nullptr, (int32_t*)nullptr, (int)std::max<int64_t>(N, 1), 0, 32);
+                                  (const int32_t*)nullptr, (int32_t*)nullptr, (int)std::max<int64_t>(2 * N, 1), 0, 32);
   w.cub_tmp = c.take<char>((int64_t)w.cub_bytes);
   w.total = align_up(c.used, 256);
   return w;
@@ -656,6 +658,7 @@ static int run_emb_bwd(const ncf_adam_cfg* adam, const ncf_tables* T, const floa
   A.dense_grad = dense_grad;
   A.acc_buf = w.acc_buf;
   A.N = N;
+  A.id_off = 0;
   A.mode = adam->emb_mode;
   A.accumulate_wmf = (side == 0 && !upstream) ? 1 : 0;
   A.adam = adam_scalars(*adam);
@@ -669,6 +672,82 @@ static int run_emb_bwd(const ncf_adam_cfg* adam, const ncf_tables* T, const floa
   NCF_LAUNCH_CHECK();
   return NCF_OK;
 }
+
+__global__ void ids_to_keys2_kernel(const int64_t* __restrict__ user_ids, const int64_t* __restrict__ item_ids, int64_t n,
+                                    uint32_t item_off, uint32_t* __restrict__ keys, int32_t* __restrict__ vals) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    keys[i] = (uint32_t)user_ids[i];
+    keys[n + i] = (uint32_t)item_ids[i] + item_off;
+    vals[i] = (int32_t)i;
+    vals[n + i] = (int32_t)i;
+  }
+}
+
+namespace ncf {
+// Both sides of the single-GPU backward with ONE radix sort: keys = user id | item id + rows_user, so the
+// sorted array holds the users' runs in [0,N) and the items' runs in [N,2N).  Item side first (it gathers the
+// user MF rows before the user side overwrites them), user side second (reads the saved item rows).
+int emb_bwd_both(const ncf_adam_cfg* adam, const ncf_tables* T, const float* dense, float* dense_grad,
+                 const int64_t* user_ids, const int64_t* item_ids, int64_t N, const float* d_mf_pred, const float* dxu,
+                 const float* dxp, const float* y_item_mf, void* workspace, int64_t workspace_bytes, cudaStream_t st) {
+  if (N == 0 || adam->emb_mode == NCF_EMB_NONE) return NCF_OK;
+  NCF_REQUIRE(2 * N < ((int64_t)1 << 31), "emb_bwd: N too large");
+  NCF_REQUIRE(T->rows_user + T->rows_item < ((int64_t)1 << 32), "emb_bwd: too many table rows for 32-bit keys");
+  EmbWs w = carve_emb_ws(workspace, N);
+  if (workspace_bytes < w.total) {
+    set_error("emb_bwd: workspace %lld < %lld", (long long)workspace_bytes, (long long)w.total);
+    return NCF_ERR_WORKSPACE;
+  }
+  if (adam->emb_mode == NCF_EMB_MATERIALIZE) {
+    NCF_REQUIRE(T->g[0] && T->g[1] && T->g[2] && T->g[3], "emb_bwd: materialize mode needs tables->g");
+  } else {
+    for (int k = 0; k < 4; ++k) NCF_REQUIRE(T->m[k] && T->v[k], "emb_bwd: Adam mode needs m and v");
+  }
+  if (adam->emb_mode == NCF_EMB_ADAM_DENSE_EQUIV) NCF_REQUIRE(T->touched[0] && T->touched[1], "dense-equivalent mode needs tables->touched");
+  ids_to_keys2_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(user_ids, item_ids, N, (uint32_t)T->rows_user, w.keys_in, w.vals_in);
+  NCF_LAUNCH_CHECK();
+  size_t tmp = w.cub_bytes;
+  NCF_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tmp, w.keys_in, w.keys_out, w.vals_in, w.vals_out, (int)(2 * N), 0,
+                                           bits_for(T->rows_user + T->rows_item), st));
+  const int64_t nchunks = (N + EB_CHUNK - 1) / EB_CHUNK;
+  const int wpb = EB_THREADS / 32;
+  const int grid = (int)std::min<int64_t>((nchunks + wpb - 1) / wpb, (int64_t)num_sms() * 8);
+  for (int side = 1; side >= 0; --side) {
+    EmbBwdArgs A;
+    A.w[0] = T->w[side];
+    A.w[1] = T->w[2 + side];
+    A.m[0] = T->m[side];
+    A.m[1] = T->m[2 + side];
+    A.v[0] = T->v[side];
+    A.v[1] = T->v[2 + side];
+    A.g[0] = T->g[side];
+    A.g[1] = T->g[2 + side];
+    A.touched = adam->emb_mode == NCF_EMB_ADAM_DENSE_EQUIV ? T->touched[side] : nullptr;
+    A.other_mf = T->w[side ? 0 : 1];
+    A.other_y = side ? nullptr : y_item_mf;
+    A.upstream = nullptr;
+    A.other_ids = side ? user_ids : item_ids;
+    A.sorted_ids = w.keys_out + (side ? N : 0);
+    A.perm = w.vals_out + (side ? N : 0);
+    A.d_mf_pred = d_mf_pred;
+    A.d_x = side ? dxp : dxu;
+    A.dense = dense;
+    A.dense_grad = dense_grad;
+    A.acc_buf = w.acc_buf;
+    A.N = N;
+    A.id_off = side ? (uint32_t)T->rows_user : 0u;
+    A.mode = adam->emb_mode;
+    A.accumulate_wmf = side == 0 ? 1 : 0;
+    A.adam = adam_scalars(*adam);
+    emb_bwd_phase1_kernel<<<grid, EB_THREADS, 0, st>>>(A);
+    NCF_LAUNCH_CHECK();
+    emb_bwd_phase2_kernel<<<grid, EB_THREADS, 0, st>>>(A);
+    NCF_LAUNCH_CHECK();
+  }
+  return NCF_OK;
+}
+}  // namespace ncf
 
 extern "C" int ncf_emb_bwd_adam(const ncf_adam_cfg* adam, const ncf_tables* T, const float* dense, float* dense_grad,
                                 int32_t side, const int64_t* user_ids, const int64_t* item_ids, int64_t N,

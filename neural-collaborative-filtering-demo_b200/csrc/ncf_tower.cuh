@@ -42,6 +42,13 @@ int tc_proj_forward(int which, const float* X, const float* W, const float* bias
 int tc_proj_forward_img(const float* X, const float* W, const float* bias, void* img, int64_t N, cudaStream_t st);
 int tc_proj_dgrad(int which, const float* dY, const float* W, float* dX, int64_t N, cudaStream_t st);
 int tc_proj_wgrad(int which, const float* Z, const float* X, float* dW, float* db, int64_t N, cudaStream_t st);
+// fused embedding backward of both sides with a single radix sort (ncf_embed.cu)
+int emb_bwd_both(const ncf_adam_cfg* adam, const ncf_tables* T, const float* dense, float* dense_grad,
+                 const int64_t* user_ids, const int64_t* item_ids, int64_t N, const float* d_mf_pred, const float* dxu,
+                 const float* dxp, const float* y_item_mf, void* workspace, int64_t workspace_bytes, cudaStream_t st);
+// fused backward of one projection: dX = dY.W and dW += dY^T.X, db += colsum(dY) (which: 0 = 64 cols, 1 = 128)
+int tc_proj_backward(int which, const float* dY, const float* X, const float* W, float* dX, float* dW, float* db, int64_t N,
+                     cudaStream_t st);
 int launch_bce(const float* out, const float* targets, int64_t N, float* loss_out, float* grad_out, cudaStream_t st);
 
 }  // namespace ncf

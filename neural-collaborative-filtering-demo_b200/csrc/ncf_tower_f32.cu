@@ -784,8 +784,7 @@ int tower_f32_backward(const ncf_run_cfg& cfg, const float* dense, float* dg, in
   const bool tc = cfg.precision == NCF_BF16_TC;
   // out_proj: dWo += da^T ctx, dbo ; dctx (g64b) = da . Wo
   if (tc) {
-    NCF_TRY(tc_proj_wgrad(0, w.g64a, w.ctx, dg + NCF_OFF(NCF_P_O_W), dg + NCF_OFF(NCF_P_O_B), N, st));
-    NCF_TRY(tc_proj_dgrad(0, w.g64a, P + NCF_OFF(NCF_P_O_W), w.g64b, N, st));
+    NCF_TRY(tc_proj_backward(0, w.g64a, w.ctx, P + NCF_OFF(NCF_P_O_W), w.g64b, dg + NCF_OFF(NCF_P_O_W), dg + NCF_OFF(NCF_P_O_B), N, st));
   } else {
     NCF_TRY(launch_wgrad(w.g64a, D, D, w.ctx, D, D, N, dg + NCF_OFF(NCF_P_O_W), D, dg + NCF_OFF(NCF_P_O_B), st));
     NCF_TRY((launch_linear<64, true, EPI_NONE>(lin(w.g64a, D, P + NCF_OFF(NCF_P_O_W), D, nullptr, w.g64b, D, N, D), st)));
@@ -794,10 +793,8 @@ int tower_f32_backward(const ncf_run_cfg& cfg, const float* dense, float* dg, in
   NCF_TRY(launch_attn_core_bwd(w.q, w.kv, w.g64b, w.g64a, w.g128, N, S, make_rng(cfg, 0), st));
   // projections: weights/biases, then dxu (g64b) = dq . Wq and dxp (g256 reused as [N,64]) = dkv . [Wk;Wv]
   if (tc) {
-    NCF_TRY(tc_proj_wgrad(0, w.g64a, w.xu, dg + NCF_OFF(NCF_P_Q_W), dg + NCF_OFF(NCF_P_Q_B), N, st));
-    NCF_TRY(tc_proj_wgrad(1, w.g128, w.xp, dg + NCF_OFF(NCF_P_K_W), dg + NCF_OFF(NCF_P_K_B), N, st));
-    NCF_TRY(tc_proj_dgrad(0, w.g64a, P + NCF_OFF(NCF_P_Q_W), w.g64b, N, st));
-    NCF_TRY(tc_proj_dgrad(1, w.g128, P + NCF_OFF(NCF_P_K_W), w.g256, N, st));
+    NCF_TRY(tc_proj_backward(0, w.g64a, w.xu, P + NCF_OFF(NCF_P_Q_W), w.g64b, dg + NCF_OFF(NCF_P_Q_W), dg + NCF_OFF(NCF_P_Q_B), N, st));
+    NCF_TRY(tc_proj_backward(1, w.g128, w.xp, P + NCF_OFF(NCF_P_K_W), w.g256, dg + NCF_OFF(NCF_P_K_W), dg + NCF_OFF(NCF_P_K_B), N, st));
   } else {
     NCF_TRY(launch_wgrad(w.g64a, D, D, w.xu, D, D, N, dg + NCF_OFF(NCF_P_Q_W), D, dg + NCF_OFF(NCF_P_Q_B), st));
     NCF_TRY(launch_wgrad(w.g128, 2 * D, 2 * D, w.xp, D, D, N, dg + NCF_OFF(NCF_P_K_W), D, dg + NCF_OFF(NCF_P_K_B), st));

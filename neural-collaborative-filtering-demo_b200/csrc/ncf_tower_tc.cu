@@ -651,6 +651,142 @@ static int launch_tc_wgrad64(const float* Z, const float* X, float* dW, float* d
   return NCF_OK;
 }
 
+// Backward of one projection Y = X.W^T + b in ONE pass over the rows: the dY tile is loaded once and used
+// as K-major A operand of the input gradient (dX = dY.W, fresh TMEM columns per tile) and as MN-major A
+// operand of the weight gradient (dW += dY^T.X, bias gradient through the ones column; TMEM columns that
+// accumulate over all tiles of the CTA).
+template <int CZ>
+__global__ void __launch_bounds__(TCM_THREADS, 2) tc_proj_bwd_kernel(const float* __restrict__ Z, const float* __restrict__ X,
+                                                                     const float* __restrict__ W, float* __restrict__ dX,
+                                                                     float* __restrict__ dW, float* __restrict__ db,
+                                                                     int64_t N) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  constexpr int CXL = 80;
+  constexpr uint32_t OFF_X = 128 * 128 * 2, OFF_W = OFF_X + 128 * CXL * 2;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q = warp & 3, h = warp >> 2;
+  for (int i = tid; i < (int)OFF_W / 16; i += TCM_THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  fill_tile_f32<64>(smem + OFF_W, W, 64, 0, CZ, CZ, tid, TCM_THREADS);          // W image [CZ rows][64 cols]
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_slot, 256);
+  fence_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t sZ = smem_addr(smem), sX = smem_addr(smem + OFF_X), sW = smem_addr(smem + OFF_W);
+  uint32_t phase = 0;
+  bool first = true;
+  const int64_t ntiles = (N + TCM_ROWS - 1) / TCM_ROWS;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t row0 = tile * TCM_ROWS;
+    const int64_t avail = min((int64_t)TCM_ROWS, N - row0);
+    for (int c = tid; c < 128 * (CZ / 8); c += TCM_THREADS) {
+      const int blk = c >> 5, l = c & 31;
+      const int bpr = (CZ / 8) / 4;
+      const int r = (blk / bpr) * 8 + (l & 7), j = (blk % bpr) * 4 + (l >> 3);
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (r < avail) {
+        const float* p = Z + (row0 + r) * CZ + 8 * j;
+        const float4 a = ldg4(p), b = ldg4(p + 4);
+        v = make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(b.x, b.y), pack_bf16(b.z, b.w));
+      }
+      *reinterpret_cast<uint4*>(smem + tile_off(r, 8 * j, 128)) = v;
+    }
+    for (int c = tid; c < 128 * 9; c += TCM_THREADS) {
+      int r, j;
+      if (c < 128 * 8) {
+        const int blk = c >> 5, l = c & 31;
+        r = (blk / 2) * 8 + (l & 7);
+        j = (blk % 2) * 4 + (l >> 3);
+      } else {
+        r = c - 128 * 8;
+        j = 8;
+      }
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (r < avail) {
+        if (j < 8) {
+          const float* p = X + (row0 + r) * 64 + 8 * j;
+          const float4 a = ldg4(p), b = ldg4(p + 4);
+          v = make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(b.x, b.y), pack_bf16(b.z, b.w));
+        } else {
+          v.x = 0x00003f80u;     // bf16(1.0): accumulator column 64 = bias gradient
+        }
+      }
+      *reinterpret_cast<uint4*>(smem + OFF_X + tile_off(r, 8 * j, CXL)) = v;
+    }
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+      fence_after_sync();
+      // dX[128 x 64] = dY[128 x CZ] . W[CZ x 64]      (A K-major on the 128-wide layout, B MN-major)
+      issue_gemm(tmem + 0, sZ, 128, 128 * 16, 256, sW, 64 * 16, 128, 2 * 64 * 16, make_idesc(128, 64, false, true), CZ / 16, false);
+      // dW[CZ x 64 (+bias col)] += dY^T . [X | 1]
+      issue_gemm(tmem + 64, sZ, 128 * 16, 128, 2 * 128 * 16, sX, CXL * 16, 128, 2 * CXL * 16, make_idesc(128, CXL, true, true), 8, !first);
+      mma_commit(&bar);
+    }
+    first = false;
+    if (warp == 0) mbar_wait(&bar, phase);
+    phase ^= 1;
+    __syncthreads();
+    fence_after_sync();
+    {
+      const int rt = q * 32 + lane;
+      float v[32];
+      tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + h * 32, v);
+      if (rt < avail) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          st4(dX + (row0 + rt) * 64 + h * 32 + 4 * j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+      }
+    }
+    fence_before_sync();
+    __syncthreads();
+  }
+  if (!first) {
+    const int m = q * 32 + lane;
+    float v[32];
+    tmem_ld32(tmem + 64 + ((uint32_t)(q * 32) << 16) + h * 32, v);
+    if (m < CZ) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) atomicAdd(dW + (int64_t)m * 64 + h * 32 + i, v[i]);
+    }
+    float b[32];
+    tmem_ld32(tmem + 64 + ((uint32_t)(q * 32) << 16) + 64, b);
+    if (h == 0 && db && m < CZ) atomicAdd(db + m, b[0]);
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
+template <int CZ>
+static int launch_tc_proj_bwd(const float* Z, const float* X, const float* W, float* dX, float* dW, float* db, int64_t N,
+                              cudaStream_t st) {
+  if (N == 0) return NCF_OK;
+  constexpr int smem = 128 * 128 * 2 + 128 * 80 * 2 + CZ * 64 * 2;
+  static bool configured = false;
+  if (!configured) {
+    NCF_CUDA(cudaFuncSetAttribute(tc_proj_bwd_kernel<CZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  const int64_t ntiles = (N + TCM_ROWS - 1) / TCM_ROWS;
+  const int grid = (int)std::min<int64_t>(ntiles, (int64_t)num_sms() * 2);
+  tc_proj_bwd_kernel<CZ><<<grid, TCM_THREADS, smem, st>>>(Z, X, W, dX, dW, db, N);
+  NCF_LAUNCH_CHECK();
+  return NCF_OK;
+}
+int tc_proj_backward(int which, const float* dY, const float* X, const float* W, float* dX, float* dW, float* db, int64_t N,
+                     cudaStream_t st) {
+  return which == 0 ? launch_tc_proj_bwd<64>(dY, X, W, dX, dW, db, N, st) : launch_tc_proj_bwd<128>(dY, X, W, dX, dW, db, N, st);
+}
+
 // entry points used by the tower orchestration (ncf_tower_f32.cu) when precision == NCF_BF16_TC
 int tc_proj_forward(int which, const float* X, const float* W, const float* bias, float* Y, int64_t N, cudaStream_t st) {
   // which: 0 = 64 -> 64 (q, v, out), 1 = 64 -> 128 (k|v)
