@@ -182,6 +182,13 @@ NCF_API int ncf_emb_bwd_adam(const ncf_adam_cfg* adam, const ncf_tables* tables,
                      const float* d_mf_pred, const float* d_x, const float* other_y_mf,
                      void* workspace, int64_t workspace_bytes, void* stream);
 
+/* Both sides in one call with a single radix sort (what ncf_backward runs): item side first, then the
+ * user side with y_item_mf = the item rows saved by ncf_gather_ln_gmf_fwd. */
+NCF_API int ncf_emb_bwd_adam_both(const ncf_adam_cfg* adam, const ncf_tables* tables, const float* dense,
+                          float* dense_grad, const int64_t* user_ids, const int64_t* item_ids, int64_t N,
+                          const float* d_mf_pred, const float* d_xu, const float* d_xp, const float* y_item_mf,
+                          void* workspace, int64_t workspace_bytes, void* stream);
+
 /* the "every untouched row" half of NCF_EMB_ADAM_DENSE_EQUIV; clears tables->touched. */
 NCF_API int ncf_emb_adam_sweep(const ncf_adam_cfg* adam, const ncf_tables* tables, void* stream);
 

@@ -749,6 +749,16 @@ int emb_bwd_both(const ncf_adam_cfg* adam, const ncf_tables* T, const float* den
 }
 }  // namespace ncf
 
+extern "C" int ncf_emb_bwd_adam_both(const ncf_adam_cfg* adam, const ncf_tables* T, const float* dense, float* dense_grad,
+                                     const int64_t* user_ids, const int64_t* item_ids, int64_t N, const float* d_mf_pred,
+                                     const float* d_xu, const float* d_xp, const float* y_item_mf, void* workspace,
+                                     int64_t workspace_bytes, void* stream) {
+  NCF_REQUIRE(adam && T && dense && user_ids && item_ids && d_mf_pred && d_xu && d_xp && y_item_mf && workspace,
+              "emb_bwd_adam_both: null argument");
+  return emb_bwd_both(adam, T, dense, dense_grad, user_ids, item_ids, N, d_mf_pred, d_xu, d_xp, y_item_mf, workspace,
+                      workspace_bytes, (cudaStream_t)stream);
+}
+
 extern "C" int ncf_emb_bwd_adam(const ncf_adam_cfg* adam, const ncf_tables* T, const float* dense, float* dense_grad,
                                 int32_t side, const int64_t* user_ids, const int64_t* item_ids, int64_t N,
                                 const float* d_mf_pred, const float* d_x, const float* other_y_mf, void* workspace,

@@ -12,4 +12,7 @@ d = json.loads(line)
 print(f"value {d['value']:.4g} {d['unit']}  ms/step {d['ms_per_step']:.3f}  e2e {d['e2e']['value']:.4g}  dtype {d['dtype']}  launches {d.get('gpu_launches')}")
 rf = d.get("roofline") or {}
 for k, v in (rf.get("kernels") or {}).items():
-    print(f"   {k}: {v['ms']:.3f} ms  frac {v['frac']:.3f}")
+    print(f"   {k}: {v['ms']:.3f} ms  {v.get('achieved', 0):.1f} {v.get('unit', '')}  frac {v['frac']:.3f}")
+if rf.get("embedding_path"):
+    ep = rf["embedding_path"]
+    print(f"   embedding path K1+K6: {ep['ms']:.3f} ms  {ep['achieved']:.0f} GB/s  frac {ep['frac']:.3f}; dominant: {rf['kernel']}")
