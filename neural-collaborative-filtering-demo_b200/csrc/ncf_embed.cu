@@ -245,6 +245,8 @@ struct EmbBwdArgs {
   const uint32_t* sorted_ids;     // this side's ids, sorted
   const int32_t* perm;            // sample row of each sorted position
   const float* d_mf_pred;         // [N]
+  const uint32_t* other_sorted;   // optional: other side's id per SORTED position (pre-gathered, coalesced)
+  const float* dmf_sorted;        // optional: d_mf_pred per sorted position
   const float* d_x;               // [N,64] gradient wrt this side's LN'd MLP row
   const float* dense;
   float* dense_grad;
@@ -282,7 +284,7 @@ __device__ __forceinline__ void block_flush(float* s_red, float4 val, float* dst
 // upstream gradients of every run piece inside it (a piece = a run of equal ids cut at chunk borders).
 // All loads depend only on the ids, so four sample rows are in flight per lane and nothing waits on a
 // table row.  The sum of a piece is written to acc_buf[first sorted position of the piece].
-__global__ void __launch_bounds__(EB_THREADS) emb_bwd_phase1_kernel(EmbBwdArgs A) {
+__global__ void __launch_bounds__(EB_THREADS, 3) emb_bwd_phase1_kernel(EmbBwdArgs A) {
   __shared__ float s_red[(EB_THREADS / 32) * 32 * 4];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = EB_THREADS / 32;
   const int half = lane >> 4, l16 = lane & 15;
@@ -300,8 +302,17 @@ __global__ void __launch_bounds__(EB_THREADS) emb_bwd_phase1_kernel(EmbBwdArgs A
     const int cnt = (int)min((int64_t)EB_CHUNK, A.N - p0);
     const uint32_t my_id = lane < cnt ? A.sorted_ids[p0 + lane] : 0xffffffffu;
     const int32_t my_row = lane < cnt ? A.perm[p0 + lane] : 0;
-    const int64_t my_other = (lane < cnt && !A.upstream && !A.other_y) ? A.other_ids[my_row] : 0;
-    const float my_dmf = (lane < cnt && !A.upstream) ? A.d_mf_pred[my_row] : 0.f;
+    int64_t my_other = 0;
+    float my_dmf = 0.f;
+    if (lane < cnt && !A.upstream) {
+      if (A.other_sorted) {
+        my_other = A.other_sorted[p0 + lane];
+        my_dmf = A.dmf_sorted[p0 + lane];
+      } else {
+        if (!A.other_y) my_other = A.other_ids[my_row];
+        my_dmf = A.d_mf_pred[my_row];
+      }
+    }
 
     float4 acc = make_float4(0, 0, 0, 0);
     int piece_first = 0;
@@ -357,7 +368,7 @@ __global__ void __launch_bounds__(EB_THREADS) emb_bwd_phase1_kernel(EmbBwdArgs A
 // Phase 2 - apply.  For every run START in the warp's chunk: add the run's pieces (its own plus the
 // chunk-start pieces it continues into, fixed order), LayerNorm backward once, fused Adam.  The table
 // row, its moments and the first piece are independent loads issued together.
-__global__ void __launch_bounds__(EB_THREADS) emb_bwd_phase2_kernel(EmbBwdArgs A) {
+__global__ void __launch_bounds__(EB_THREADS, 3) emb_bwd_phase2_kernel(EmbBwdArgs A) {
   __shared__ float s_red[(EB_THREADS / 32) * 32 * 4];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = EB_THREADS / 32;
   const int half = lane >> 4, l16 = lane & 15;
@@ -586,6 +597,8 @@ static int bits_for(int64_t rows) {
 struct EmbWs {
   uint32_t *keys_in, *keys_out;
   int32_t *vals_in, *vals_out;
+  uint32_t* other_sorted;
+  float* dmf_sorted;
   float* acc_buf;
   void* cub_tmp;
   size_t cub_bytes;
@@ -599,6 +612,8 @@ static EmbWs carve_emb_ws(void* ws, int64_t N) {
   w.keys_out = c.take<uint32_t>(2 * N);
   w.vals_in = c.take<int32_t>(2 * N);
   w.vals_out = c.take<int32_t>(2 * N);
+  w.other_sorted = c.take<uint32_t>(2 * N);
+  w.dmf_sorted = c.take<float>(2 * N);
   w.acc_buf = c.take<float>(N * 2 * D);
   w.cub_bytes = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, w.cub_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr,
@@ -657,6 +672,8 @@ static int run_emb_bwd(const ncf_adam_cfg* adam, const ncf_tables* T, const floa
   A.dense = dense;
   A.dense_grad = dense_grad;
   A.acc_buf = w.acc_buf;
+  A.other_sorted = nullptr;
+  A.dmf_sorted = nullptr;
   A.N = N;
   A.id_off = 0;
   A.mode = adam->emb_mode;
@@ -681,6 +698,18 @@ __global__ void ids_to_keys2_kernel(const int64_t* __restrict__ user_ids, const 
     keys[n + i] = (uint32_t)item_ids[i] + item_off;
     vals[i] = (int32_t)i;
     vals[n + i] = (int32_t)i;
+  }
+}
+
+// per sorted position: the other side's id and d_mf_pred of the sample, so phase 1 reads them coalesced
+__global__ void gather_sorted_kernel(const int32_t* __restrict__ perm, const int64_t* __restrict__ user_ids,
+                                     const int64_t* __restrict__ item_ids, const float* __restrict__ d_mf, int64_t n,
+                                     uint32_t* __restrict__ other_sorted, float* __restrict__ dmf_sorted) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < 2 * n) {
+    const int32_t row = perm[p];
+    other_sorted[p] = (uint32_t)(p < n ? item_ids[row] : user_ids[row]);
+    dmf_sorted[p] = d_mf[row];
   }
 }
 
@@ -710,6 +739,9 @@ int emb_bwd_both(const ncf_adam_cfg* adam, const ncf_tables* T, const float* den
   size_t tmp = w.cub_bytes;
   NCF_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tmp, w.keys_in, w.keys_out, w.vals_in, w.vals_out, (int)(2 * N), 0,
                                            bits_for(T->rows_user + T->rows_item), st));
+  gather_sorted_kernel<<<(unsigned)((2 * N + 255) / 256), 256, 0, st>>>(w.vals_out, user_ids, item_ids, d_mf_pred, N,
+                                                                        w.other_sorted, w.dmf_sorted);
+  NCF_LAUNCH_CHECK();
   const int64_t nchunks = (N + EB_CHUNK - 1) / EB_CHUNK;
   const int wpb = EB_THREADS / 32;
   const int grid = (int)std::min<int64_t>((nchunks + wpb - 1) / wpb, (int64_t)num_sms() * 8);
@@ -731,6 +763,8 @@ int emb_bwd_both(const ncf_adam_cfg* adam, const ncf_tables* T, const float* den
     A.sorted_ids = w.keys_out + (side ? N : 0);
     A.perm = w.vals_out + (side ? N : 0);
     A.d_mf_pred = d_mf_pred;
+    A.other_sorted = w.other_sorted + (side ? N : 0);
+    A.dmf_sorted = w.dmf_sorted + (side ? N : 0);
     A.d_x = side ? dxp : dxu;
     A.dense = dense;
     A.dense_grad = dense_grad;
