@@ -251,6 +251,17 @@ NCF_API int ncf_shard_owner_update(const ncf_adam_cfg* adam, const ncf_tables* l
                            float* dense_grad, int32_t side, const int64_t* local_ids, int64_t n,
                            const float* grad_rows, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* ---- input pipeline on the device --------------------------------------------
+ * SheetzDataset.__getitem__ + _sample_negative (data_prep.py:134-161, 181-212) + collate_recommender_batch
+ * (:230-320) for B positive interactions: writes the key-major id columns user_ids / item_ids [B*S] (row
+ * b*S = positive, b*S+1.. = negatives of the same user) and targets [B*S] = [1,0,..,0].
+ * cdf [I] = cumulative inverse-popularity weights (float64); hist_off [U+1] / hist_items = sorted CSR of
+ * every user's training items (NULL, NULL = no rejection by history). */
+NCF_API int ncf_sample_batch(const int64_t* pos_user, const int64_t* pos_item, int64_t B, int32_t S,
+                     const double* cdf, int64_t I, const int64_t* hist_off, const int64_t* hist_items,
+                     uint64_t seed, uint64_t step, int64_t* user_ids, int64_t* item_ids, float* targets,
+                     void* stream);
+
 /* ---- tensor-core self test: one 128-row tcgen05 GEMM tile in the three operand arrangements the
  * towers use (0 forward A.B^T, 1 input-gradient A.B, 2 weight-gradient A^T.B); fp32 in/out. */
 NCF_API int ncf_tc_selftest(int32_t mode, int32_t K, int32_t N, const float* A, const float* B, float* D, void* stream);

@@ -6,6 +6,7 @@ Import as `ncf_b200` (the directory name carries a hyphen, so the repo root hold
 from ._lib import NcfError, load as load_library  # noqa: F401
 from .architecture import AdvancedNCF, CategoryHierarchy, MultiHeadAttention, TemporalEncoding  # noqa: F401
 from .kjt import KeyedJaggedTensor, make_kjt  # noqa: F401
+from .data_prep import InteractionSampler, first_appearance_index, remap_cardnumber, remap_product_id  # noqa: F401
 from .metrics import calculate_metrics  # noqa: F401
 from .scoring import CatalogueScorer, get_recommendations  # noqa: F401
 from .trainer import ModelTrainer, NCFTrainEngine  # noqa: F401
@@ -13,4 +14,5 @@ from .sharding import ShardedCatalogueScorer, ShardedNCFEngine, ShardRouter  # n
 
 __all__ = ["AdvancedNCF", "MultiHeadAttention", "TemporalEncoding", "CategoryHierarchy", "KeyedJaggedTensor",
            "make_kjt", "NcfError", "load_library", "calculate_metrics", "CatalogueScorer", "get_recommendations",
-           "ModelTrainer", "NCFTrainEngine", "ShardedNCFEngine", "ShardRouter", "ShardedCatalogueScorer"]
+           "ModelTrainer", "NCFTrainEngine", "ShardedNCFEngine", "ShardRouter", "ShardedCatalogueScorer", "InteractionSampler", "first_appearance_index",
+           "remap_cardnumber", "remap_product_id"]

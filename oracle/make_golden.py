@@ -23,6 +23,7 @@ Fixtures
                            eval forward, get_user/product_embeddings on the shipped checkpoint.
   topk.npz                 app.py:get_recommendations order (pandas nlargest) for 16 users.
   metrics.npz              utils/metrics.calculate_metrics on seeded score matrices.
+  sampler.npz              SheetzDataset negative sampling (np.random seeded), ConsistentBatchSampler, collate.
 """
 import io
 import json
@@ -273,6 +274,37 @@ def metrics_fixture():
     np.savez_compressed(os.path.join(OUT, "metrics.npz"), **arrays)
 
 
+def sampler_fixture():
+    """SheetzDataset (train mode) on small synthetic frames: negative sampling with np.random.seed, the padded
+    batch sampler and collate_recommender_batch, all from the unmodified reference."""
+    from src.model.data_prep import ConsistentBatchSampler, SheetzDataset, collate_recommender_batch
+    rng = np.random.RandomState(3)
+    U, I, M = 20, 15, 240
+    users = [f"{6011000000000000 + u}" for u in range(U)]
+    prods = [f"P{(i * 2654435761) % (1 << 32):08X}" for i in range(I)]
+    ts = pd.Timestamp("2024-01-01") + pd.to_timedelta(rng.randint(0, 90 * 24 * 3600, M), unit="s")
+    pop = rng.zipf(1.5, M) % I
+    inter = pd.DataFrame({"user_id": [users[u] for u in rng.randint(0, U, M)], "product_id": [prods[i] for i in pop],
+                          "amount": rng.rand(M), "transaction_timestamp": ts})
+    uf = pd.DataFrame({"cardnumber": users, "recent_interactions": ["{}"] * U, "preferred_categories": ["[]"] * U})
+    pf = pd.DataFrame({"product_id": prods, "total_purchases": [1] * I, "total_revenue": [1.0] * I})
+    ds = SheetzDataset(inter, uf, pf, mode="train", validation_days=10, negative_samples=4)
+    il = np.array([(u, p) for u, p, _ in ds.interaction_list], dtype=np.int64)
+    np.random.seed(123)
+    samples = [ds[i] for i in range(40)]
+    prod_ids = np.stack([s[0]["product_id"].numpy() for s in samples])
+    user_ids = np.stack([s[0]["user_id"].numpy() for s in samples])
+    targets = np.stack([s[1].numpy() for s in samples])
+    np.random.seed(5)
+    batches = np.array(list(ConsistentBatchSampler(23, 8, shuffle=True)), dtype=np.int64)
+    kjt_b, tgt_b = collate_recommender_batch(samples[:6])
+    np.savez_compressed(os.path.join(OUT, "sampler.npz"), interactions=il, num_users=np.int64(ds.num_users),
+                        num_products=np.int64(ds.num_products), weights=ds.product_weights, sample_user_ids=user_ids,
+                        sample_product_ids=prod_ids, sample_targets=targets, batches=batches,
+                        collate_values=kjt_b.values().numpy(), collate_lengths=kjt_b.lengths().numpy(),
+                        collate_targets=tgt_b.numpy())
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(1)
@@ -283,6 +315,7 @@ def main():
     forward_simple_fixture(m)
     topk_fixture(m)
     metrics_fixture()
+    sampler_fixture()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -394,3 +394,57 @@ def auc(pred: torch.Tensor, target: torch.Tensor) -> float:
     r = torch.empty_like(ranks)
     r[order] = ranks
     return float((r[pos].sum() - n_pos * (n_pos + 1) / 2.0) / (n_pos * n_neg))
+
+
+# --------------------------------------------------------------------------------------------
+# input pipeline (data_prep.py) - next-row N1
+# --------------------------------------------------------------------------------------------
+def product_weights(item_idx, num_products: int):
+    """inverse-popularity sampling weights (data_prep.py:95-102)."""
+    import numpy as np
+    counts = np.zeros(num_products)
+    for i in item_idx:
+        counts[int(i)] += 1
+    counts = np.maximum(counts, 1)
+    w = 1 / counts
+    return w / w.sum()
+
+
+def sample_negative(user_idx: int, positive_product: int, weights, history: dict, num_products: int) -> int:
+    """SheetzDataset._sample_negative (data_prep.py:134-161), drawing from numpy's global RNG like the reference."""
+    import numpy as np
+    user_positives = history.get(user_idx, set())
+    for _ in range(10):
+        product_idx = np.random.choice(num_products, p=weights)
+        if product_idx != positive_product and product_idx not in user_positives:
+            return int(product_idx)
+    valid = list(set(range(num_products)) - user_positives - {positive_product})
+    if not valid:
+        while True:
+            idx = np.random.randint(0, num_products)
+            if idx != positive_product:
+                return int(idx)
+    return int(np.random.choice(valid))
+
+
+def consistent_batches(dataset_size: int, batch_size: int, shuffle: bool = True):
+    """ConsistentBatchSampler.__iter__ (data_prep.py:419-440)."""
+    import numpy as np
+    indices = list(range(dataset_size))
+    if shuffle:
+        np.random.shuffle(indices)
+    for i in range((dataset_size + batch_size - 1) // batch_size):
+        b = indices[i * batch_size:min((i + 1) * batch_size, dataset_size)]
+        if len(b) < batch_size:
+            b = b + b[:batch_size - len(b)]
+        yield b
+
+
+def collate(samples):
+    """collate_recommender_batch (data_prep.py:230-320): samples = [(user_ids[M], item_ids[M], targets[M])];
+    returns (values key-major, lengths, targets [N,1])."""
+    users = [int(u) for s in samples for u in s[0]]
+    items = [int(i) for s in samples for i in s[1]]
+    targets = [float(t) for s in samples for t in s[2]]
+    values = torch.tensor(users + items, dtype=torch.long)
+    return values, torch.ones(values.numel(), dtype=torch.long), torch.tensor(targets, dtype=torch.float32).unsqueeze(1)
