@@ -24,6 +24,8 @@ gloo); every compute phase is a libncf_b200 call.
 from __future__ import annotations
 
 import ctypes as C
+import glob
+import os
 from typing import List, Optional, Tuple
 
 import torch
@@ -264,6 +266,49 @@ class ShardedNCFEngine:
             dist.all_reduce(self.loss, group=self.group)
         self.phase_dense_adam()
         return self.loss
+
+    # ---- sharded checkpoints -------------------------------------------------------
+    def save_checkpoint(self, directory: str) -> None:
+        """Every rank writes its table shard (weights + Adam moments) to `shard_<rank>_of_<world>.pt`; rank 0 also
+        writes `dense.pt` (the reference state_dict keys of the replicated parameters, their Adam state, step)."""
+        os.makedirs(directory, exist_ok=True)
+        torch.save({"rank": self.rank, "world": self.world, "num_users": self.U, "num_products": self.I,
+                    "w": [t.cpu() for t in self.w], "m": [t.cpu() for t in self.m], "v": [t.cpu() for t in self.v]},
+                   os.path.join(directory, f"shard_{self.rank}_of_{self.world}.pt"))
+        if self.rank == 0:
+            dense = {k: v.detach().cpu() for k, v in self.model.state_dict().items() if "embedding_collection" not in k}
+            torch.save({"model_state_dict": dense, "dense_m": self.dense_m.cpu(), "dense_v": self.dense_v.cpu(),
+                        "step": self.step, "hp": dict(self.hp), "table_mode": self.table_mode, "world": self.world},
+                       os.path.join(directory, "dense.pt"))
+
+    def load_checkpoint(self, directory: str) -> None:
+        """Resume from `save_checkpoint` output written with ANY world size: each rank reads the saved shards that
+        overlap its own row range (re-sharding on load)."""
+        d = torch.load(os.path.join(directory, "dense.pt"), map_location="cpu", weights_only=False)
+        self.model.load_state_dict(d["model_state_dict"], strict=False)
+        self.model._ensure_flat()
+        self.dense_m.copy_(d["dense_m"])
+        self.dense_v.copy_(d["dense_v"])
+        self.step = int(d["step"])
+        files = sorted(glob.glob(os.path.join(directory, "shard_*_of_*.pt")))
+        if not files:
+            raise FileNotFoundError(f"no table shards under {directory}")
+        for f in files:
+            sh = torch.load(f, map_location="cpu", weights_only=False)
+            if sh["num_users"] != self.U or sh["num_products"] != self.I:
+                raise ValueError("checkpoint was written for different table sizes")
+            for k in range(4):
+                rows = self.U if k % 2 == 0 else self.I
+                src_block, dst_block = shard_block(rows, sh["world"]), shard_block(rows, self.world)
+                src0 = sh["rank"] * src_block
+                src1 = src0 + sh["w"][k].shape[0]
+                dst0 = self.rank * dst_block
+                dst1 = dst0 + self.w[k].shape[0]
+                lo, hi = max(src0, dst0), min(src1, dst1)
+                if lo >= hi:
+                    continue
+                for mine, theirs in ((self.w, sh["w"]), (self.m, sh["m"]), (self.v, sh["v"])):
+                    mine[k][lo - dst0:hi - dst0].copy_(theirs[k][lo - src0:hi - src0])
 
     def gather_tables(self) -> List[torch.Tensor]:
         """Reassemble the global tables on every rank (tests / checkpointing of small models)."""

@@ -191,3 +191,40 @@ def test_sharded_scorer_equals_single_gpu_scorer():
     want = O.topk_stable(full, 100)
     agree = (idx.cpu() == want).float().mean()
     assert agree > 0.98          # only near-ties (gap below fp32 resolution of the two summation orders) may swap
+
+
+@pytest.mark.gpu
+def test_sharded_checkpoint_reshards_on_load(tmp_path):
+    """Save from 2 ranks (after a training step), load into 1 and 3 ranks: tables, moments, dense state equal."""
+    import ncf_b200
+    from ncf_b200.sharding import ShardedNCFEngine
+    U, I = 101, 37
+    pg, _ = golden_params()
+    g = torch.Generator().manual_seed(1)
+    p = {k: v.clone() for k, v in pg.items()}
+    for k, rows in zip(O.TABLE_KEYS, (U, I, U, I)):
+        p[k] = torch.rand(rows, 64, generator=g) * 0.1
+    tabs = [p[k] for k in O.TABLE_KEYS]
+
+    def model():
+        m = ncf_b200.AdvancedNCF(U, I, 5, 24, dropout=0.0)
+        m.load_state_dict(p)
+        return m.cuda().train()
+
+    src = [ShardedNCFEngine(model(), U, I, init_tables=tabs, rank=r, world=2) for r in range(2)]
+    for e in src:                                   # make the state non-trivial
+        for k in range(4):
+            e.m[k].uniform_(-1, 1, generator=None)
+            e.v[k].uniform_(0, 1)
+        e.dense_m.normal_()
+        e.step = 17
+        e.save_checkpoint(str(tmp_path))
+    full = lambda engines, attr, k: torch.cat([getattr(e, attr)[k] for e in engines])
+    for world in (1, 3):
+        dst = [ShardedNCFEngine(model(), U, I, rank=r, world=world, seed=99) for r in range(world)]
+        for e in dst:
+            e.load_checkpoint(str(tmp_path))
+            assert e.step == 17 and torch.equal(e.dense_m, src[0].dense_m)
+        for attr in ("w", "m", "v"):
+            for k in range(4):
+                assert torch.equal(full(dst, attr, k), full(src, attr, k)), (world, attr, k)
