@@ -36,10 +36,26 @@ __global__ void item_fold_kernel(const float* __restrict__ ymf, const float* __r
 }
 
 // ---- top-k -------------------------------------------------------------------------------------
+// Register-tiled fp32 scoring: a CTA owns 32 users and streams 128-item tiles of P_hat through shared
+// memory (cp.async, double buffered).  Warp w holds users 4w..4w+3, lane l items l, l+32, l+64, l+96 of the
+// tile: 16 accumulators per thread, every shared-memory word feeds 4 FMAs.  Each dot product is summed in
+// ascending-k order with fmaf, so a score does not depend on the tiling.  Scores above the user's
+// running k-th best are appended to that user's candidate buffer (shared memory), which is
+// bitonic-merged into the running list when it could overflow.
 constexpr int TK_THREADS = 256;
-constexpr int TK_UT = 4;        // users per CTA (share every P_hat row load)
+constexpr int TK_UT = 32;       // users per CTA
+constexpr int TK_IT = 128;      // items per tile
+constexpr int TK_LD = 68;       // padded row length (floats): 16-byte aligned, conflict-free float4 reads
 constexpr int TK_KMAX = 128;    // running list length (k <= 128)
 constexpr int TK_BUF = 512;     // list + candidate buffer, power of two for the bitonic network
+constexpr uint32_t TKS_U = 0;
+constexpr uint32_t TKS_P = TKS_U + TK_UT * TK_LD * 4;
+constexpr uint32_t TKS_G = TKS_P + 2 * TK_IT * TK_LD * 4;
+constexpr uint32_t TKS_BUF = TKS_G + 2 * TK_IT * 4;
+constexpr uint32_t TKS_CNT = TKS_BUF + TK_UT * TK_BUF * 8;
+constexpr uint32_t TKS_THR = TKS_CNT + TK_UT * 4;
+constexpr uint32_t TKS_LTHR = TKS_THR + TK_UT * 8;      // per-user logit pre-filter (float)
+constexpr uint32_t TKS_TOTAL = TKS_LTHR + TK_UT * 4;
 
 // larger key == better: fp32 score bits (scores are positive) then lower item index
 __device__ __forceinline__ unsigned long long tk_key(float score, uint32_t idx) {
@@ -67,24 +83,189 @@ __device__ void bitonic_sort_desc(unsigned long long* a, int n) {
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(TK_THREADS) score_topk_kernel(const float* __restrict__ t_umf,
+__device__ __forceinline__ void cp_async16(void* dst, const void* src, uint32_t src_bytes) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__global__ void __launch_bounds__(TK_THREADS, 1) score_topk_kernel(const float* __restrict__ t_umf,
+                                                                   const float* __restrict__ dense,
+                                                                   const float* __restrict__ p_hat, const float* __restrict__ g,
+                                                                   const int64_t* __restrict__ user_ids, int64_t n_users,
+                                                                   int64_t I, int nsplit,
+                                                                   unsigned long long* __restrict__ part /*[n_users][nsplit][KMAX]*/) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  float* s_u = reinterpret_cast<float*>(smem + TKS_U);
+  float* s_p = reinterpret_cast<float*>(smem + TKS_P);
+  float* s_g = reinterpret_cast<float*>(smem + TKS_G);
+  unsigned long long* s_buf = reinterpret_cast<unsigned long long*>(smem + TKS_BUF);
+  int* s_cnt = reinterpret_cast<int*>(smem + TKS_CNT);
+  unsigned long long* s_thr = reinterpret_cast<unsigned long long*>(smem + TKS_THR);
+  float* s_lthr = reinterpret_cast<float*>(smem + TKS_LTHR);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t u0 = (int64_t)blockIdx.x * TK_UT;
+  const int split = blockIdx.y;
+  const int nu = (int)min((int64_t)TK_UT, n_users - u0);
+
+  // LN_mf of the tile's user rows: one warp per user (4 rounds), two-pass variance like nn.LayerNorm
+  for (int uu = warp; uu < TK_UT; uu += TK_THREADS / 32) {
+    float x0 = 0.f, x1 = 0.f;
+    if (uu < nu) {
+      const float* row = t_umf + user_ids[u0 + uu] * D;
+      x0 = row[lane];
+      x1 = row[lane + 32];
+    }
+    const float mean = warp_sum(x0 + x1) * (1.0f / D);
+    const float d0 = x0 - mean, d1 = x1 - mean;
+    const float rstd = rsqrtf(warp_sum(d0 * d0 + d1 * d1) * (1.0f / D) + LN_EPS);
+    s_u[uu * TK_LD + lane] = fmaf(d0 * rstd, __ldg(dense + NCF_OFF(NCF_P_MF_NORM_W) + lane), __ldg(dense + NCF_OFF(NCF_P_MF_NORM_B) + lane));
+    s_u[uu * TK_LD + lane + 32] =
+        fmaf(d1 * rstd, __ldg(dense + NCF_OFF(NCF_P_MF_NORM_W) + lane + 32), __ldg(dense + NCF_OFF(NCF_P_MF_NORM_B) + lane + 32));
+  }
+  for (int i = tid; i < TK_UT * TK_BUF; i += TK_THREADS) s_buf[i] = 0ull;
+  if (tid < TK_UT) {
+    s_cnt[tid] = TK_KMAX;   // slots [0,KMAX) hold the running list (zeros = empty)
+    s_thr[tid] = 0ull;
+    s_lthr[tid] = -INFINITY;
+  }
+
+  const int64_t per = (I + nsplit - 1) / nsplit;
+  const int64_t i_begin = split * per, i_end = min(I, i_begin + per);
+  const int64_t ntile = i_begin < i_end ? (i_end - i_begin + TK_IT - 1) / TK_IT : 0;
+
+  auto stage = [&](int64_t t, int buf) {      // cp.async one 128 x 64 tile of P_hat (+ g) into buffer `buf`
+    const int64_t base = i_begin + t * TK_IT;
+    float* dst = s_p + buf * TK_IT * TK_LD;
+    for (int c = tid; c < TK_IT * 16; c += TK_THREADS) {
+      const int r = c >> 4, q = c & 15;
+      const int64_t i = base + r;
+      const bool ok = i < i_end;
+      cp_async16(dst + r * TK_LD + 4 * q, p_hat + (ok ? i : i_begin) * D + 4 * q, ok ? 16u : 0u);
+    }
+    if (tid < TK_IT) {
+      const int64_t i = base + tid;
+      s_g[buf * TK_IT + tid] = i < i_end ? __ldg(g + i) : 0.f;
+    }
+    cp_async_commit();
+  };
+
+  if (ntile > 0) stage(0, 0);
+  for (int64_t t = 0; t < ntile; ++t) {
+    const int buf = (int)(t & 1);
+    if (t + 1 < ntile) {
+      stage(t + 1, buf ^ 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const float* pt = s_p + buf * TK_IT * TK_LD;
+    float acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+#pragma unroll 4
+    for (int k4 = 0; k4 < D / 4; ++k4) {
+      float4 uv[4], pv[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) uv[a] = *reinterpret_cast<const float4*>(s_u + (warp * 4 + a) * TK_LD + 4 * k4);
+#pragma unroll
+      for (int b = 0; b < 4; ++b) pv[b] = *reinterpret_cast<const float4*>(pt + (lane + 32 * b) * TK_LD + 4 * k4);
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          acc[a][b] = fmaf(uv[a].x, pv[b].x, acc[a][b]);
+          acc[a][b] = fmaf(uv[a].y, pv[b].y, acc[a][b]);
+          acc[a][b] = fmaf(uv[a].z, pv[b].z, acc[a][b]);
+          acc[a][b] = fmaf(uv[a].w, pv[b].w, acc[a][b]);
+        }
+    }
+    const int64_t base = i_begin + t * TK_IT;
+    // sigmoid is monotone: a logit below the user's pre-filter (the logit of the running k-th best score minus
+    // a rounding margin) cannot enter the list, so the exact score / key is only formed for the few survivors
+    float lthr[4];
+    unsigned long long kthr[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      lthr[a] = s_lthr[warp * 4 + a];
+      kthr[a] = s_thr[warp * 4 + a];
+    }
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int64_t i = base + lane + 32 * b;
+      if (i < i_end) {
+        const float gi = s_g[buf * TK_IT + lane + 32 * b];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          const int uu = warp * 4 + a;
+          const float z = acc[a][b] + gi;
+          if (uu < nu && z >= lthr[a]) {
+            const float sc = 1.0f / (1.0f + expf(-z));
+            const unsigned long long key = tk_key(sc, (uint32_t)i);
+            if (key > kthr[a]) {
+              const int pos = atomicAdd(&s_cnt[uu], 1);
+              s_buf[uu * TK_BUF + pos] = key;
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // merge any list whose buffer might overflow during the next tile (<= 128 new candidates per user)
+    for (int uu = 0; uu < nu; ++uu) {
+      if (s_cnt[uu] > TK_BUF - TK_IT) {   // uniform: s_cnt read after the barrier
+        bitonic_sort_desc(s_buf + uu * TK_BUF, TK_BUF);
+        for (int k = TK_KMAX + tid; k < TK_BUF; k += TK_THREADS) s_buf[uu * TK_BUF + k] = 0ull;
+        if (tid == 0) {
+          s_cnt[uu] = TK_KMAX;
+          const unsigned long long kth = s_buf[uu * TK_BUF + TK_KMAX - 1];
+          s_thr[uu] = kth;
+          const float sk = __uint_as_float((uint32_t)(kth >> 32));
+          float lt = -INFINITY;
+          if (kth != 0ull && sk > 0.f && sk < 1.f) {
+            lt = logf(sk / (1.0f - sk));
+            lt -= 1e-4f + 1e-4f * fabsf(lt);
+          }
+          s_lthr[uu] = lt;
+        }
+        __syncthreads();
+      }
+    }
+  }
+  __syncthreads();
+  for (int uu = 0; uu < nu; ++uu) {
+    bitonic_sort_desc(s_buf + uu * TK_BUF, TK_BUF);
+    unsigned long long* dst = part + ((u0 + uu) * nsplit + split) * TK_KMAX;
+    for (int k = tid; k < TK_KMAX; k += TK_THREADS) dst[k] = s_buf[uu * TK_BUF + k];
+  }
+}
+
+// Small catalogues (below ~1M items): 4 users per CTA, one P_hat row per thread - less work per CTA, so the grid
+// fills the machine and the per-user merges do not dominate.
+constexpr int TKS_UT = 4;
+__global__ void __launch_bounds__(TK_THREADS) score_topk_small_kernel(const float* __restrict__ t_umf,
                                                                 const float* __restrict__ dense,
                                                                 const float* __restrict__ p_hat, const float* __restrict__ g,
                                                                 const int64_t* __restrict__ user_ids, int64_t n_users,
                                                                 int64_t I, int nsplit,
                                                                 unsigned long long* __restrict__ part /*[n_users][nsplit][KMAX]*/) {
-  __shared__ __align__(16) float s_u[TK_UT][D];
-  __shared__ unsigned long long s_buf[TK_UT][TK_BUF];
-  __shared__ int s_cnt[TK_UT];
-  __shared__ unsigned long long s_thr[TK_UT];
-  const int64_t u0 = (int64_t)blockIdx.x * TK_UT;
+  __shared__ __align__(16) float s_u[TKS_UT][D];
+  __shared__ unsigned long long s_buf[TKS_UT][TK_BUF];
+  __shared__ int s_cnt[TKS_UT];
+  __shared__ unsigned long long s_thr[TKS_UT];
+  const int64_t u0 = (int64_t)blockIdx.x * TKS_UT;
   const int split = blockIdx.y;
-  const int nu = (int)min((int64_t)TK_UT, n_users - u0);
+  const int nu = (int)min((int64_t)TKS_UT, n_users - u0);
 
   // LN_mf of the tile's user rows (64 threads per user; two-pass variance like nn.LayerNorm)
   {
     const int uu = threadIdx.x >> 6, c = threadIdx.x & 63;
-    __shared__ float s_tmp[TK_UT][D];
+    __shared__ float s_tmp[TKS_UT][D];
     float x = 0.f;
     if (uu < nu) x = t_umf[user_ids[u0 + uu] * D + c];
     s_tmp[uu][c] = x;
@@ -97,8 +278,8 @@ __global__ void __launch_bounds__(TK_THREADS) score_topk_kernel(const float* __r
     const float rstd = rsqrtf(var * (1.0f / D) + LN_EPS);
     s_u[uu][c] = fmaf((x - mean) * rstd, __ldg(dense + NCF_OFF(NCF_P_MF_NORM_W) + c), __ldg(dense + NCF_OFF(NCF_P_MF_NORM_B) + c));
   }
-  for (int i = threadIdx.x; i < TK_UT * TK_BUF; i += TK_THREADS) (&s_buf[0][0])[i] = 0ull;
-  if (threadIdx.x < TK_UT) {
+  for (int i = threadIdx.x; i < TKS_UT * TK_BUF; i += TK_THREADS) (&s_buf[0][0])[i] = 0ull;
+  if (threadIdx.x < TKS_UT) {
     s_cnt[threadIdx.x] = TK_KMAX;   // slots [0,KMAX) hold the running list (zeros = empty)
     s_thr[threadIdx.x] = 0ull;
   }
@@ -109,15 +290,15 @@ __global__ void __launch_bounds__(TK_THREADS) score_topk_kernel(const float* __r
   for (int64_t base = i_begin; base < i_end; base += TK_THREADS) {
     const int64_t i = base + threadIdx.x;
     if (i < i_end) {
-      float acc[TK_UT];
+      float acc[TKS_UT];
 #pragma unroll
-      for (int uu = 0; uu < TK_UT; ++uu) acc[uu] = 0.f;
+      for (int uu = 0; uu < TKS_UT; ++uu) acc[uu] = 0.f;
       const float* row = p_hat + i * D;
 #pragma unroll
       for (int q = 0; q < D / 4; ++q) {
         const float4 p = ldg4(row + 4 * q);
 #pragma unroll
-        for (int uu = 0; uu < TK_UT; ++uu) {
+        for (int uu = 0; uu < TKS_UT; ++uu) {
           const float4 uv = *reinterpret_cast<const float4*>(&s_u[uu][4 * q]);
           acc[uu] = fmaf(uv.x, p.x, acc[uu]);
           acc[uu] = fmaf(uv.y, p.y, acc[uu]);
@@ -127,7 +308,7 @@ __global__ void __launch_bounds__(TK_THREADS) score_topk_kernel(const float* __r
       }
       const float gi = __ldg(g + i);
 #pragma unroll
-      for (int uu = 0; uu < TK_UT; ++uu) {
+      for (int uu = 0; uu < TKS_UT; ++uu) {
         if (uu < nu) {
           const float s = 1.0f / (1.0f + expf(-(acc[uu] + gi)));
           const unsigned long long key = tk_key(s, (uint32_t)i);
@@ -270,10 +451,17 @@ extern "C" int ncf_item_fold(const ncf_tables* T, const float* dense, float* p_h
   return NCF_OK;
 }
 
+constexpr int64_t TK_SMALL_CATALOGUE = 1 << 20;
 static int topk_splits(int64_t n_users, int64_t I) {
+  if (I < TK_SMALL_CATALOGUE) {
+    const int64_t tiles = (n_users + TKS_UT - 1) / TKS_UT;
+    int64_t want = std::max<int64_t>(1, (2 * (int64_t)num_sms() + tiles - 1) / tiles);
+    want = std::min<int64_t>(std::min<int64_t>(want, std::max<int64_t>(1, I / (4 * TK_THREADS))), TM_MAX / TK_KMAX);
+    return (int)want;
+  }
   const int64_t tiles = (n_users + TK_UT - 1) / TK_UT;
   int64_t want = std::max<int64_t>(1, (2 * (int64_t)num_sms() + tiles - 1) / tiles);
-  const int64_t max_by_items = std::max<int64_t>(1, I / (4 * TK_THREADS));
+  const int64_t max_by_items = std::max<int64_t>(1, I / (8 * TK_IT));
   want = std::min<int64_t>(std::min<int64_t>(want, max_by_items), TM_MAX / TK_KMAX);
   return (int)want;
 }
@@ -298,10 +486,25 @@ extern "C" int ncf_score_topk(const ncf_tables* T, const float* dense, const flo
   }
   cudaStream_t st = (cudaStream_t)stream;
   unsigned long long* part = static_cast<unsigned long long*>(workspace);
+  if (I < TK_SMALL_CATALOGUE) {
+    const int64_t tiles_s = (n_users + TKS_UT - 1) / TKS_UT;
+    NCF_REQUIRE(tiles_s < ((int64_t)1 << 31), "score_topk: too many users in one call");
+    dim3 grid_s((unsigned)tiles_s, nsplit);
+    score_topk_small_kernel<<<grid_s, TK_THREADS, 0, st>>>(T->w[0], dense, p_hat, g, user_ids, n_users, I, nsplit, part);
+    NCF_LAUNCH_CHECK();
+    topk_merge_kernel<<<(unsigned)n_users, 256, 0, st>>>(part, nsplit, k, topk_idx, topk_score);
+    NCF_LAUNCH_CHECK();
+    return NCF_OK;
+  }
   const int64_t tiles = (n_users + TK_UT - 1) / TK_UT;
   NCF_REQUIRE(tiles < ((int64_t)1 << 31), "score_topk: too many users in one call");
   dim3 grid((unsigned)tiles, nsplit);
-  score_topk_kernel<<<grid, TK_THREADS, 0, st>>>(T->w[0], dense, p_hat, g, user_ids, n_users, I, nsplit, part);
+  static bool configured = false;
+  if (!configured) {
+    NCF_CUDA(cudaFuncSetAttribute(score_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TKS_TOTAL));
+    configured = true;
+  }
+  score_topk_kernel<<<grid, TK_THREADS, TKS_TOTAL, st>>>(T->w[0], dense, p_hat, g, user_ids, n_users, I, nsplit, part);
   NCF_LAUNCH_CHECK();
   topk_merge_kernel<<<(unsigned)n_users, 256, 0, st>>>(part, nsplit, k, topk_idx, topk_score);
   NCF_LAUNCH_CHECK();

@@ -383,3 +383,34 @@ def test_errors_are_loud():
     m.cpu()
     with pytest.raises(ncf_b200.NcfError):
         m.eval()(ncf_b200.make_kjt(torch.arange(4), torch.arange(4)))   # no CPU fallback
+
+
+def test_topk_large_catalogue_tiled_kernel():
+    """> 1M items selects the register-tiled cp.async scoring kernel: indices equal the oracle's stable
+    order up to fp32 near-ties, scores within 1e-5, order property exact."""
+    import ncf_b200
+    p, _ = golden_params()
+    g = torch.Generator().manual_seed(21)
+    I = (1 << 20) + 777
+    q = {k: v.clone() for k, v in p.items()}
+    q[O.K_PMF] = (torch.rand(I, 64, generator=g) * 2 - 1) * 0.05
+    q[O.K_PMLP] = (torch.rand(I, 64, generator=g) * 2 - 1) * 0.05
+    m = _model(q, 8031, I).eval()
+    users = torch.arange(0, 37)
+    idx, sc = ncf_b200.CatalogueScorer(m).topk(users.cuda(), 100)
+    p_hat, gg = O.item_fold(q)
+    um = O.layer_norm(q[O.K_UMF][users], q["mf_norm.weight"], q["mf_norm.bias"])
+    full = torch.sigmoid(um @ p_hat.t() + gg)
+    want = O.topk_stable(full, 100)
+    got_i, got_s = idx.cpu(), sc.cpu()
+    _close(got_s, torch.gather(full, 1, got_i), what="tiled top-100 scores")
+    assert float((got_i == want).float().mean()) > 0.97
+    for r in range(users.numel()):
+        s_r, i_r = got_s[r], got_i[r]
+        assert torch.all(s_r[:-1] >= s_r[1:])
+        tie = s_r[:-1] == s_r[1:]
+        assert torch.all(i_r[:-1][tie] < i_r[1:][tie])
+        missing = set(want[r].tolist()) - set(i_r.tolist())
+        thr = full[r][want[r][-1]]
+        for mi in missing:
+            assert abs(float(full[r][mi] - thr)) < 1e-6
