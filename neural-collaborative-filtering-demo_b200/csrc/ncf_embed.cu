@@ -427,9 +427,24 @@ __global__ void __launch_bounds__(EB_THREADS, 3) emb_bwd_phase2_kernel(EmbBwdArg
       (void)i;
       // does the run leave this chunk?  (its last in-chunk element is the chunk's last element)
       const uint32_t last_id = __shfl_sync(0xffffffffu, my_id, cnt - 1);
-      if (last_id == id) {
-        for (int64_t cs = p0 + EB_CHUNK; cs < A.N && A.sorted_ids[cs] == id; cs += EB_CHUNK)
-          acc = f4_add(acc, ld4(A.acc_buf + (cs * 2 + half) * D + 4 * l16));
+      if (last_id == id && p0 + EB_CHUNK < A.N && A.sorted_ids[p0 + EB_CHUNK] == id) {
+        // long run: find its end by binary search in the sorted ids, then add the chunk-start pieces with
+        // independent loads (fixed order)
+        int64_t lo = p0 + EB_CHUNK, hi = A.N;               // first position > lo whose id differs
+        while (lo < hi) {
+          const int64_t mid = (lo + hi) >> 1;
+          if (A.sorted_ids[mid] == id) lo = mid + 1; else hi = mid;
+        }
+        const int64_t end = lo;
+        int64_t cs = p0 + EB_CHUNK;
+        for (; cs + 3 * EB_CHUNK < end; cs += 4 * EB_CHUNK) {
+          const float4 a0 = ld4(A.acc_buf + (cs * 2 + half) * D + 4 * l16);
+          const float4 a1 = ld4(A.acc_buf + ((cs + EB_CHUNK) * 2 + half) * D + 4 * l16);
+          const float4 a2 = ld4(A.acc_buf + ((cs + 2 * EB_CHUNK) * 2 + half) * D + 4 * l16);
+          const float4 a3 = ld4(A.acc_buf + ((cs + 3 * EB_CHUNK) * 2 + half) * D + 4 * l16);
+          acc = f4_add(f4_add(f4_add(f4_add(acc, a0), a1), a2), a3);
+        }
+        for (; cs < end; cs += EB_CHUNK) acc = f4_add(acc, ld4(A.acc_buf + (cs * 2 + half) * D + 4 * l16));
       }
       float rstd;
       const float4 xhat = ln_normalise(wrow, rstd);

@@ -426,6 +426,47 @@ int launch_mlp_tc_fwd(const MlpFwdArgs& A, cudaStream_t st) {
   return NCF_OK;
 }
 
+
+// Register-staged operand tiles: the global loads of the NEXT tile are issued before the current tile's MMA
+// is awaited, so their latency overlaps the tensor work and the epilogue; the bf16 conversion and the
+// shared-memory stores happen when the buffer is free again.
+template <int C, int NT>      // C source columns (fp32, row-major, ld = C); NT threads
+struct TileRegs {
+  static constexpr int CHUNKS = 128 * (C / 8) / NT;
+  float4 a[CHUNKS], b[CHUNKS];
+  __device__ __forceinline__ static void rc(int c, int& r, int& j) {
+    const int blk = c >> 5, l = c & 31;
+    constexpr int bpr = (C / 8) / 4;
+    r = (blk / bpr) * 8 + (l & 7);
+    j = (blk % bpr) * 4 + (l >> 3);
+  }
+  __device__ __forceinline__ void load(const float* __restrict__ src, int64_t row0, int64_t avail, int tid) {
+#pragma unroll
+    for (int k = 0; k < CHUNKS; ++k) {
+      int r, j;
+      rc(tid + k * NT, r, j);
+      a[k] = make_float4(0, 0, 0, 0);
+      b[k] = a[k];
+      if (r < avail) {
+        const float* p = src + (row0 + r) * C + 8 * j;
+        a[k] = ldg4(p);
+        b[k] = ldg4(p + 4);
+      }
+    }
+  }
+  // LAYOUT = column count of the shared-memory tile layout (>= C)
+  template <int LAYOUT>
+  __device__ __forceinline__ void store(uint8_t* tile, int tid) const {
+#pragma unroll
+    for (int k = 0; k < CHUNKS; ++k) {
+      int r, j;
+      rc(tid + k * NT, r, j);
+      *reinterpret_cast<uint4*>(tile + tile_off(r, 8 * j, LAYOUT)) =
+          make_uint4(pack_bf16(a[k].x, a[k].y), pack_bf16(a[k].z, a[k].w), pack_bf16(b[k].x, b[k].y), pack_bf16(b[k].z, b[k].w));
+    }
+  }
+};
+
 // =============================================================================================
 // Generic tcgen05 linear layers for the attention projections (q, k|v, out):
 //   tc_linear_kernel<K, NOUT, false>:  Y[N,NOUT] = X[N,K] . W[NOUT,K]^T + b      (nn.Linear forward)
@@ -459,10 +500,13 @@ __global__ void __launch_bounds__(TCM_THREADS, 2) tc_linear_kernel(const float* 
   const uint32_t sW = smem_addr(smem), sX = smem_addr(smem + OFF_X);
   uint32_t phase = 0;
   const int64_t ntiles = (N + TCM_ROWS - 1) / TCM_ROWS;
+  TileRegs<K, TCM_THREADS> xr;
+  if ((int64_t)blockIdx.x < ntiles)
+    xr.load(X, (int64_t)blockIdx.x * TCM_ROWS, min((int64_t)TCM_ROWS, N - (int64_t)blockIdx.x * TCM_ROWS), tid);
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int64_t row0 = tile * TCM_ROWS;
     const int64_t avail = min((int64_t)TCM_ROWS, N - row0);
-    fill_tile_f32<K>(smem + OFF_X, X, K, row0, avail, TCM_ROWS, tid, TCM_THREADS);
+    xr.template store<K>(smem + OFF_X, tid);
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
@@ -473,6 +517,10 @@ __global__ void __launch_bounds__(TCM_THREADS, 2) tc_linear_kernel(const float* 
       else
         issue_gemm(tmem, sX, 128, K * 16, 256, sW, 128, WC * 16, 256, make_idesc(128, NOUT, false, false), K / 16, false);
       mma_commit(&bar);
+    }
+    {
+      const int64_t next = tile + gridDim.x;
+      if (next < ntiles) xr.load(X, next * TCM_ROWS, min((int64_t)TCM_ROWS, N - next * TCM_ROWS), tid);
     }
     mbar_wait(&bar, phase);
     phase ^= 1;
@@ -683,42 +731,22 @@ __global__ void __launch_bounds__(TCM_THREADS, 2) tc_proj_bwd_kernel(const float
   uint32_t phase = 0;
   bool first = true;
   const int64_t ntiles = (N + TCM_ROWS - 1) / TCM_ROWS;
+  TileRegs<CZ, TCM_THREADS> zr;
+  TileRegs<64, TCM_THREADS> xr;
+  if ((int64_t)blockIdx.x < ntiles) {
+    const int64_t r0 = (int64_t)blockIdx.x * TCM_ROWS;
+    zr.load(Z, r0, min((int64_t)TCM_ROWS, N - r0), tid);
+    xr.load(X, r0, min((int64_t)TCM_ROWS, N - r0), tid);
+  }
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int64_t row0 = tile * TCM_ROWS;
     const int64_t avail = min((int64_t)TCM_ROWS, N - row0);
-    for (int c = tid; c < 128 * (CZ / 8); c += TCM_THREADS) {
-      const int blk = c >> 5, l = c & 31;
-      const int bpr = (CZ / 8) / 4;
-      const int r = (blk / bpr) * 8 + (l & 7), j = (blk % bpr) * 4 + (l >> 3);
+    zr.template store<128>(smem, tid);
+    xr.template store<CXL>(smem + OFF_X, tid);
+    if (tid < 128) {      // the ones column (bias gradient): 1.0 for live rows
       uint4 v = make_uint4(0, 0, 0, 0);
-      if (r < avail) {
-        const float* p = Z + (row0 + r) * CZ + 8 * j;
-        const float4 a = ldg4(p), b = ldg4(p + 4);
-        v = make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(b.x, b.y), pack_bf16(b.z, b.w));
-      }
-      *reinterpret_cast<uint4*>(smem + tile_off(r, 8 * j, 128)) = v;
-    }
-    for (int c = tid; c < 128 * 9; c += TCM_THREADS) {
-      int r, j;
-      if (c < 128 * 8) {
-        const int blk = c >> 5, l = c & 31;
-        r = (blk / 2) * 8 + (l & 7);
-        j = (blk % 2) * 4 + (l >> 3);
-      } else {
-        r = c - 128 * 8;
-        j = 8;
-      }
-      uint4 v = make_uint4(0, 0, 0, 0);
-      if (r < avail) {
-        if (j < 8) {
-          const float* p = X + (row0 + r) * 64 + 8 * j;
-          const float4 a = ldg4(p), b = ldg4(p + 4);
-          v = make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(b.x, b.y), pack_bf16(b.z, b.w));
-        } else {
-          v.x = 0x00003f80u;     // bf16(1.0): accumulator column 64 = bias gradient
-        }
-      }
-      *reinterpret_cast<uint4*>(smem + OFF_X + tile_off(r, 8 * j, CXL)) = v;
+      if (tid < avail) v.x = 0x00003f80u;
+      *reinterpret_cast<uint4*>(smem + OFF_X + tile_off(tid, 64, CXL)) = v;
     }
     fence_async_smem();
     fence_before_sync();
@@ -732,6 +760,13 @@ __global__ void __launch_bounds__(TCM_THREADS, 2) tc_proj_bwd_kernel(const float
       mma_commit(&bar);
     }
     first = false;
+    {
+      const int64_t next = tile + gridDim.x;
+      if (next < ntiles) {
+        zr.load(Z, next * TCM_ROWS, min((int64_t)TCM_ROWS, N - next * TCM_ROWS), tid);
+        xr.load(X, next * TCM_ROWS, min((int64_t)TCM_ROWS, N - next * TCM_ROWS), tid);
+      }
+    }
     if (warp == 0) mbar_wait(&bar, phase);
     phase ^= 1;
     __syncthreads();
