@@ -19,6 +19,7 @@ struct TowerWs {
   float *dxu, *dxp;                        // aliases set by the backward
   // bf16 tensors of the tcgen05 path (NCF_BF16_TC): saved activations and pre-activation gradients
   void *r1b, *y1b, *r2b, *y2b, *r3b, *dz1b, *dz2b, *dz3b;
+  float* wg_partial;                       // per-CTA weight-gradient accumulators of the tcgen05 MLP wgrad kernel
   void* a_img;                             // attention output as bf16 tile image [ceil(N/128)][128 x 64]
   float *st1, *st2, *st3;                  // LayerNorm (mean, rstd) per row of the three MLP layers
   char* emb;                               // workspace of the fused embedding backward

@@ -398,47 +398,56 @@ __device__ __forceinline__ uint64_t attn_keep_mask(const DropoutRng& rng, uint64
   return m;
 }
 
+// forward: thread = (row, head); each thread reads its query slice and the S key / value slices of its group
+__device__ __forceinline__ void load16(const float* p, float* d) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 t = ldg4(p + 4 * i);
+    d[4 * i] = t.x; d[4 * i + 1] = t.y; d[4 * i + 2] = t.z; d[4 * i + 3] = t.w;
+  }
+}
 template <int S>
 __global__ void __launch_bounds__(256) attn_core_fwd_kernel(const float* __restrict__ q, const float* __restrict__ kv,
                                                             float* __restrict__ ctx, int64_t N, DropoutRng rng) {
-  const int lane = threadIdx.x & 31, d = lane & 15;
-  const int64_t hw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4;     // (group, head)
-  const int64_t ngh = (N / S) * HEADS;
-  const bool live = hw < ngh;
-  const int64_t g = live ? hw / HEADS : 0;
-  const int h = live ? (int)(hw % HEADS) : 0;
-  float qv[S], kk[S], vv[S];
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= N * HEADS) return;
+  const int64_t n = t / HEADS;
+  const int h = (int)(t % HEADS);
+  const int64_t g = n / S;
+  const int i = (int)(n % S);
+  float qv[16], p[S], o[16];
+  load16(q + n * D + h * HD, qv);
+  float mx = -INFINITY;
 #pragma unroll
-  for (int i = 0; i < S; ++i) {
-    const int64_t n = g * S + i;
-    qv[i] = __ldg(q + n * D + h * HD + d);
-    kk[i] = __ldg(kv + n * (2 * D) + h * HD + d);
-    vv[i] = __ldg(kv + n * (2 * D) + D + h * HD + d);
+  for (int j = 0; j < S; ++j) {
+    float kk[16];
+    load16(kv + (g * S + j) * (2 * D) + h * HD, kk);
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) s = fmaf(qv[c], kk[c], s);
+    p[j] = s * 0.25f;   // / sqrt(head_dim = 16)
+    mx = fmaxf(mx, p[j]);
   }
-  const uint64_t keep = attn_keep_mask<S>(rng, ((uint64_t)g * HEADS + h) * (S * S), d, lane);
+  float sum = 0.f;
 #pragma unroll
-  for (int i = 0; i < S; ++i) {
-    float p[S], mx = -INFINITY;
-#pragma unroll
-    for (int j = 0; j < S; ++j) {
-      p[j] = hw_allreduce(qv[i] * kk[j]) * 0.25f;       // / sqrt(head_dim = 16)
-      mx = fmaxf(mx, p[j]);
-    }
-    float sum = 0.f;
-#pragma unroll
-    for (int j = 0; j < S; ++j) {
-      p[j] = expf(p[j] - mx);
-      sum += p[j];
-    }
-    const float inv = 1.0f / sum;
-    float o = 0.f;
-#pragma unroll
-    for (int j = 0; j < S; ++j) {
-      const float pj = ((keep >> (i * S + j)) & 1ull) ? p[j] * inv * rng.scale : 0.f;
-      o = fmaf(pj, vv[j], o);
-    }
-    if (live) ctx[(g * S + i) * D + h * HD + d] = o;
+  for (int j = 0; j < S; ++j) {
+    p[j] = expf(p[j] - mx);
+    sum += p[j];
   }
+  const float inv = 1.0f / sum;
+#pragma unroll
+  for (int c = 0; c < 16; ++c) o[c] = 0.f;
+#pragma unroll
+  for (int j = 0; j < S; ++j) {
+    float pj = p[j] * inv;
+    if (rng.thresh != 0u) pj = rng.keep((((uint64_t)g * HEADS + h) * S + i) * S + j) ? pj * rng.scale : 0.f;
+    float vv[16];
+    load16(kv + (g * S + j) * (2 * D) + D + h * HD, vv);
+#pragma unroll
+    for (int c = 0; c < 16; ++c) o[c] = fmaf(pj, vv[c], o[c]);
+  }
+#pragma unroll
+  for (int c4 = 0; c4 < 4; ++c4) st4(ctx + n * D + h * HD + 4 * c4, make_float4(o[4 * c4], o[4 * c4 + 1], o[4 * c4 + 2], o[4 * c4 + 3]));
 }
 
 template <int S>
@@ -522,7 +531,7 @@ __global__ void __launch_bounds__(256) attn_core_bwd_kernel(const float* __restr
 static int launch_attn_core_fwd(const float* q, const float* kv, float* ctx, int64_t N, int S, const DropoutRng& rng,
                                 cudaStream_t st) {
   if (N == 0) return NCF_OK;
-  const int64_t threads = (N / S) * HEADS * 16;
+  const int64_t threads = N * HEADS;
   const unsigned grid = (unsigned)((threads + 255) / 256);
   NCF_DISPATCH_S(S, (attn_core_fwd_kernel<SS><<<grid, 256, 0, st>>>(q, kv, ctx, N, rng)));
   NCF_LAUNCH_CHECK();
@@ -698,6 +707,7 @@ TowerWs carve_tower_ws(void* ws, int64_t N, const ncf_run_cfg& cfg) {
       w.dz1b = c.take<uint16_t>(Np * H1);
       w.dz2b = c.take<uint16_t>(Np * H2);
       w.dz3b = c.take<uint16_t>(Np * H3);
+      w.wg_partial = c.take<float>((int64_t)num_sms() * 448 * 128);
     }
     w.emb_bytes = ncf_emb_bwd_workspace_bytes(N);
     w.emb = c.take<char>(w.emb_bytes);

@@ -448,9 +448,14 @@ struct TileRegs {
       a[k] = make_float4(0, 0, 0, 0);
       b[k] = a[k];
       if (r < avail) {
+        // volatile asm: the compiler must not sink these loads towards their first use (the point of the prefetch)
         const float* p = src + (row0 + r) * C + 8 * j;
-        a[k] = ldg4(p);
-        b[k] = ldg4(p + 4);
+        asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(a[k].x), "=f"(a[k].y), "=f"(a[k].z), "=f"(a[k].w)
+                     : "l"(p));
+        asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(b[k].x), "=f"(b[k].y), "=f"(b[k].z), "=f"(b[k].w)
+                     : "l"(p + 4));
       }
     }
   }
@@ -1164,10 +1169,13 @@ __device__ __forceinline__ void copy_tile_image(uint8_t* dst, const __nv_bfloat1
   for (int i = tid; i < bytes / 16; i += nthreads) reinterpret_cast<uint4*>(dst)[i] = __ldg(src + i);
 }
 
+constexpr int WG_PART = 448 * 128;     // accumulator words per CTA (TMEM columns x lanes)
+
 struct MlpWgradArgs {
   const __nv_bfloat16* a_img;                            // MLP input, bf16 tile image
   const __nv_bfloat16 *y1, *y2, *dz1, *dz2, *dz3;
   float* dense_grad;
+  float* partial;                                         // [grid][WG_PART]
   int64_t N;
 };
 
@@ -1239,34 +1247,39 @@ __global__ void __launch_bounds__(TCM_THREADS, 1) mlp_tc_wgrad_kernel(MlpWgradAr
     }
   }
   __syncthreads();
-  if (my_tiles > 0) {
+  {
+    // flush: this CTA's accumulators go to its own slice of a partial buffer (coalesced stores, no atomics);
+    // mlp_wgrad_reduce_kernel adds the slices into the gradient.  CTAs without tiles store zeros.
     fence_after_sync();
-    float* dg = A.dense_grad;
+    float* part = A.partial + (int64_t)blockIdx.x * WG_PART;
     const int lane_row = q * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    {  // dW2^T: lane = k_in, 64 columns = n_out; this thread's half: 32 columns
+    for (int ch = 0; ch < 7; ++ch) {          // 448 columns: this thread's half = 7 chunks of 32
       float v[32];
-      tmem_ld32(tmem + 0 + lane_addr + h * 32, v);
+      const int c0 = h * 224 + ch * 32;
+      tmem_ld32(tmem + lane_addr + c0, v);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) atomicAdd(dg + NCF_OFF(NCF_P_MLP2_W) + (int64_t)(h * 32 + i) * H2 + lane_row, v[i]);
-    }
-    for (int ch = 0; ch < 4; ++ch) {  // dW1: lane = n_out, 256 columns = k_in; half = 128 columns
-      float v[32];
-      tmem_ld32(tmem + 64 + lane_addr + h * 128 + ch * 32, v);
-#pragma unroll
-      for (int i = 0; i < 32; ++i) atomicAdd(dg + NCF_OFF(NCF_P_MLP1_W) + (int64_t)lane_row * H1 + h * 128 + ch * 32 + i, v[i]);
-    }
-    for (int hh = 0; hh < 2; ++hh) {  // dW0 halves: lane = n_out - 128 hh, 64 columns = k_in; half = 32 columns
-      float v[32];
-      tmem_ld32(tmem + 320 + hh * 64 + lane_addr + h * 32, v);
-#pragma unroll
-      for (int i = 0; i < 32; ++i)
-        atomicAdd(dg + NCF_OFF(NCF_P_MLP0_W) + (int64_t)(hh * 128 + lane_row) * K0 + h * 32 + i, v[i]);
+      for (int i = 0; i < 32; ++i) part[(int64_t)(c0 + i) * 128 + lane_row] = my_tiles > 0 ? v[i] : 0.f;
     }
   }
   fence_before_sync();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+// dense_grad += sum over CTAs of the partial accumulators; e = column * 128 + lane
+__global__ void __launch_bounds__(256) mlp_wgrad_reduce_kernel(const float* __restrict__ partial, int nparts,
+                                                               float* __restrict__ dg) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= WG_PART) return;
+  float s = 0.f;
+  for (int p = 0; p < nparts; ++p) s += partial[(int64_t)p * WG_PART + e];
+  const int col = e >> 7, lane = e & 127;
+  int64_t off;
+  if (col < 64) off = NCF_OFF(NCF_P_MLP2_W) + (int64_t)col * H2 + lane;                       // dW2^T: lane = k_in
+  else if (col < 320) off = NCF_OFF(NCF_P_MLP1_W) + (int64_t)lane * H1 + (col - 64);           // dW1: lane = n_out
+  else off = NCF_OFF(NCF_P_MLP0_W) + (int64_t)(((col - 320) >> 6) * 128 + lane) * K0 + ((col - 320) & 63);
+  dg[off] += s;
 }
 
 int mlp_tc_backward(const ncf_run_cfg& cfg, const float* dense, float* dense_grad, int64_t N, TowerWs& w, cudaStream_t st) {
@@ -1304,8 +1317,11 @@ int mlp_tc_backward(const ncf_run_cfg& cfg, const float* dense, float* dense_gra
   W.dz2 = B.dz2;
   W.dz3 = B.dz3;
   W.dense_grad = dense_grad;
+  W.partial = w.wg_partial;
   W.N = N;
   mlp_tc_wgrad_kernel<<<grid, TCM_THREADS, SMW_TOTAL, st>>>(W);
+  NCF_LAUNCH_CHECK();
+  mlp_wgrad_reduce_kernel<<<(WG_PART + 255) / 256, 256, 0, st>>>(w.wg_partial, grid, dense_grad);
   NCF_LAUNCH_CHECK();
   return NCF_OK;
 }
