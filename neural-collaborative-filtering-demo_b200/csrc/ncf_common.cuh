@@ -140,22 +140,31 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
   return ctr;
 }
 // Dropout stream: one Philox call yields 8 x 16-bit lanes = the keep decisions of 8 consecutive
-// elements (element idx uses call idx >> 3, lane idx & 7); keep iff lane >= thresh (p quantised to
-// 1/65536; kept values are scaled by 1/(1-p) with the nominal p like nn.Dropout).
+// elements (element idx uses call idx >> 3, lane idx & 7).  The low 15 bits of a lane are the uniform
+// draw: keep iff (lane & 0x7fff) >= thresh (p quantised to 1/32768; kept values are scaled by 1/(1-p)
+// with the nominal p like nn.Dropout).  15-bit draws leave a guard bit per lane, so the two decisions of
+// a 32-bit Philox word come out of ONE subtraction (drop_signs) - the tensor-core MLP stores them in the
+// sign bits of its saved (non-negative) ReLU outputs and the backward never regenerates the stream.
 struct DropoutRng {
   uint2 key;
   uint32_t step_lo, step_hi_site;
-  uint32_t thresh;  // 16-bit threshold; 0 = dropout off
+  uint32_t thresh;  // 15-bit threshold; 0 = dropout off
   float scale;      // 1/(1-p)
   __device__ __forceinline__ uint4 draw8(uint64_t group) const {
     return philox4x32_10(make_uint4((uint32_t)group, (uint32_t)(group >> 32), step_lo, step_hi_site), key);
   }
-  __device__ __forceinline__ float mask(float x, uint32_t lane16) const { return lane16 >= thresh ? x * scale : 0.f; }
+  __device__ __forceinline__ bool keep16(uint32_t lane16) const { return (lane16 & 0x7fffu) >= thresh; }
+  __device__ __forceinline__ float mask(float x, uint32_t lane16) const { return keep16(lane16) ? x * scale : 0.f; }
+  // 0x8000 in each half of the result whose lane is DROPPED (w = one Philox word = two lanes)
+  __device__ __forceinline__ uint32_t drop_signs(uint32_t w) const {
+    const uint32_t d = ((w & 0x7fff7fffu) | 0x80008000u) - (thresh * 0x10001u);
+    return ~d & 0x80008000u;
+  }
   __device__ __forceinline__ bool keep(uint64_t idx) const {
     const uint4 r = draw8(idx >> 3);
     const uint32_t c = ((uint32_t)idx >> 1) & 3u;
     const uint32_t w = c == 0 ? r.x : c == 1 ? r.y : c == 2 ? r.z : r.w;
-    return (((uint32_t)idx & 1u) ? (w >> 16) : (w & 0xffffu)) >= thresh;
+    return keep16(((uint32_t)idx & 1u) ? (w >> 16) : (w & 0xffffu));
   }
   // 8 consecutive elements starting at e0 (multiple of 8)
   __device__ __forceinline__ void apply8(uint64_t e0, float* v) const {
@@ -187,8 +196,8 @@ __host__ __device__ inline DropoutRng make_rng(const ncf_run_cfg& cfg, int site)
   r.step_lo = (uint32_t)cfg.step;
   r.step_hi_site = ((uint32_t)(cfg.step >> 32) & 0x00ffffffu) | ((uint32_t)site << 24);
   const double p = (cfg.training && cfg.dropout_p > 0.f) ? (double)cfg.dropout_p : 0.0;
-  double t = p * 65536.0 + 0.5;
-  r.thresh = t >= 65535.0 ? 65535u : (uint32_t)t;
+  double t = p * 32768.0 + 0.5;
+  r.thresh = t >= 32767.0 ? 32767u : (uint32_t)t;
   if (p == 0.0) r.thresh = 0u;
   r.scale = (float)(1.0 / (1.0 - p));   // nn.Dropout: kept values / (1-p)
   return r;

@@ -163,8 +163,11 @@ __device__ __forceinline__ void load_weight_image(uint8_t* img, const float* __r
 // canonical operand image at byte offset t*128*C*2 (rows beyond N are padding).  A warp store of one
 // 16-byte chunk per lane then covers 4 x 128 contiguous bytes (full sectors), and the consumers
 // (backward, weight gradient) copy tiles linearly.
-// Epilogue of one layer for this thread's row and column part (C/4 columns).  Pass 1: bias (+tail) +
-// ReLU, bf16 rounding, row statistics; pass 2: LayerNorm, dropout, bf16 -> next A operand / saved tensors.
+// Epilogue of one layer for this thread's row and column part (C/4 columns).
+// Pass 1: bias (+tail) + ReLU, bf16 rounding (packed pairs), row statistics, dropout decisions.  The packed
+// ReLU outputs stay in registers; a DROPPED element carries its decision in the (otherwise unused) sign bit,
+// and that is also the form the saved r tensor takes, so the backward needs no random numbers.
+// Pass 2: LayerNorm (gamma/beta pre-multiplied by 1/(1-p)), dropout select, bf16 -> next A operand / saved y.
 template <int C, bool LAST, bool HAS_TAIL>
 __device__ __forceinline__ void mlp_epilogue(uint32_t tmem_acc, int q, int h, int lane, int64_t grow, bool live,
                                              const float* __restrict__ par_b, const float* __restrict__ par_g,
@@ -176,8 +179,9 @@ __device__ __forceinline__ void mlp_epilogue(uint32_t tmem_acc, int q, int h, in
   constexpr int PART = C / MLP_NH, CW = PART >= 32 ? 32 : 16, NCH = PART / CW;
   const int rt = q * 32 + lane;                 // row inside the tile
   const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) + h * PART;
+  uint32_t pk[PART / 2];
   float sum = 0.f, sq = 0.f;
-#pragma unroll 1
+#pragma unroll
   for (int ch = 0; ch < NCH; ++ch) {
     float v[CW];
     tmem_ldw<CW>(taddr + ch * CW, v);
@@ -189,19 +193,25 @@ __device__ __forceinline__ void mlp_epilogue(uint32_t tmem_acc, int q, int h, in
       if (HAS_TAIL) t4 = tail_row ? ldg4(tail_row + c0 + 4 * i4) : t4;
       const float bb[4] = {b4.x + t4.x, b4.y + t4.y, b4.z + t4.z, b4.w + t4.w};
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float x = bf16_round(fmaxf(v[4 * i4 + k] + bb[k], 0.f));
-        v[4 * i4 + k] = x;
-        sum += x;
-        sq = fmaf(x, x, sq);
+      for (int k2 = 0; k2 < 2; ++k2) {
+        const uint32_t w = pack_bf16(fmaxf(v[4 * i4 + 2 * k2] + bb[2 * k2], 0.f), fmaxf(v[4 * i4 + 2 * k2 + 1] + bb[2 * k2 + 1], 0.f));
+        const float x0 = __uint_as_float(w << 16), x1 = __uint_as_float(w & 0xffff0000u);
+        sum += x0 + x1;
+        sq = fmaf(x0, x0, fmaf(x1, x1, sq));
+        pk[ch * (CW / 2) + i4 * 2 + k2] = w;
       }
     }
-    if (r_img) {
 #pragma unroll
-      for (int j = 0; j < CW / 8; ++j)
-        *reinterpret_cast<uint4*>(r_img + tile_off(rt, c0 + 8 * j, C)) =
-            make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
-                       pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+    for (int g8 = 0; g8 < CW / 8; ++g8) {
+      uint32_t* w4 = &pk[ch * (CW / 2) + 4 * g8];
+      if (rng.thresh != 0u) {
+        const uint4 r = rng.draw8(((uint64_t)grow * C + c0 + 8 * g8) >> 3);
+        w4[0] |= rng.drop_signs(r.x);
+        w4[1] |= rng.drop_signs(r.y);
+        w4[2] |= rng.drop_signs(r.z);
+        w4[3] |= rng.drop_signs(r.w);
+      }
+      if (r_img) *reinterpret_cast<uint4*>(r_img + tile_off(rt, c0 + 8 * g8, C)) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
     }
   }
   s_stat[(rt * MLP_NH + h) * 2 + 0] = sum;
@@ -216,52 +226,44 @@ __device__ __forceinline__ void mlp_epilogue(uint32_t tmem_acc, int q, int h, in
   }
   const float mean = sum * (1.0f / C);
   const float rstd = rsqrtf(fmaxf(sq * (1.0f / C) - mean * mean, 0.f) + LN_EPS);
+  const float nmr = -mean * rstd;
   if (st_tile && h == 0) *reinterpret_cast<float2*>(st_tile + rt * 2) = make_float2(mean, rstd);
   float hp = 0.f;
-#pragma unroll 1
-  for (int ch = 0; ch < NCH; ++ch) {
-    float v[CW];
-    tmem_ldw<CW>(taddr + ch * CW, v);
-    const int c0 = h * PART + ch * CW;
 #pragma unroll
-    for (int i4 = 0; i4 < CW / 4; ++i4) {
-      const float4 b4 = *reinterpret_cast<const float4*>(par_b + c0 + 4 * i4);
+  for (int g8 = 0; g8 < PART / 8; ++g8) {
+    const int c0 = h * PART + 8 * g8;
+    float y[8];
+#pragma unroll
+    for (int i4 = 0; i4 < 2; ++i4) {
       const float4 g4 = *reinterpret_cast<const float4*>(par_g + c0 + 4 * i4);
       const float4 e4 = *reinterpret_cast<const float4*>(par_e + c0 + 4 * i4);
-      float4 t4 = make_float4(0, 0, 0, 0);
-      if (HAS_TAIL) t4 = tail_row ? ldg4(tail_row + c0 + 4 * i4) : t4;
-      const float bb[4] = {b4.x + t4.x, b4.y + t4.y, b4.z + t4.z, b4.w + t4.w};
       const float gg[4] = {g4.x, g4.y, g4.z, g4.w}, ee[4] = {e4.x, e4.y, e4.z, e4.w};
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float x = bf16_round(fmaxf(v[4 * i4 + k] + bb[k], 0.f));
-        v[4 * i4 + k] = fmaf((x - mean) * rstd, gg[k], ee[k]);
+      for (int k2 = 0; k2 < 2; ++k2) {
+        const uint32_t w = pk[4 * g8 + 2 * i4 + k2];
+        const uint32_t lo = w << 16;
+        const float x0 = fabsf(__uint_as_float(lo)), x1 = fabsf(__uint_as_float(w & 0xffff0000u));
+        const float y0 = fmaf(fmaf(x0, rstd, nmr), gg[2 * k2], ee[2 * k2]);
+        const float y1 = fmaf(fmaf(x1, rstd, nmr), gg[2 * k2 + 1], ee[2 * k2 + 1]);
+        y[4 * i4 + 2 * k2] = (int32_t)lo < 0 ? 0.f : y0;
+        y[4 * i4 + 2 * k2 + 1] = (int32_t)w < 0 ? 0.f : y1;
       }
-    }
-    if (rng.thresh != 0u) {
-#pragma unroll
-      for (int g8 = 0; g8 < CW / 8; ++g8) rng.apply8((uint64_t)grow * C + c0 + 8 * g8, &v[8 * g8]);
     }
     if (LAST) {
 #pragma unroll
-      for (int i4 = 0; i4 < CW / 4; ++i4) {
+      for (int i4 = 0; i4 < 2; ++i4) {
         const float4 w4 = *reinterpret_cast<const float4*>(par_wout + c0 + 4 * i4);
-        hp = fmaf(v[4 * i4], w4.x, fmaf(v[4 * i4 + 1], w4.y, fmaf(v[4 * i4 + 2], w4.z, fmaf(v[4 * i4 + 3], w4.w, hp))));
+        hp = fmaf(y[4 * i4], w4.x, fmaf(y[4 * i4 + 1], w4.y, fmaf(y[4 * i4 + 2], w4.z, fmaf(y[4 * i4 + 3], w4.w, hp))));
       }
       if (y3_out && live) {
-#pragma unroll
-        for (int j = 0; j < CW / 4; ++j)
-          st4(y3_out + grow * C + c0 + 4 * j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+        st4(y3_out + grow * C + c0, make_float4(y[0], y[1], y[2], y[3]));
+        st4(y3_out + grow * C + c0 + 4, make_float4(y[4], y[5], y[6], y[7]));
       }
     } else {
-#pragma unroll
-      for (int j = 0; j < CW / 8; ++j) {
-        const uint4 pk = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
-                                    pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
-        const uint32_t off = tile_off(rt, c0 + 8 * j, C);
-        *reinterpret_cast<uint4*>(ytile + off) = pk;
-        if (y_img) *reinterpret_cast<uint4*>(y_img + off) = pk;
-      }
+      const uint4 o = make_uint4(pack_bf16(y[0], y[1]), pack_bf16(y[2], y[3]), pack_bf16(y[4], y[5]), pack_bf16(y[6], y[7]));
+      const uint32_t off = tile_off(rt, c0, C);
+      *reinterpret_cast<uint4*>(ytile + off) = o;
+      if (y_img) *reinterpret_cast<uint4*>(y_img + off) = o;
     }
   }
   head_partial = hp;
@@ -282,19 +284,22 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_tc_fwd_kernel(MlpFwdArgs A
   load_weight_image<256, 64>(smem + SM_W0, P + NCF_OFF(NCF_P_MLP0_W), K0, tid, MLP_THREADS);
   load_weight_image<128, 256>(smem + SM_W1, P + NCF_OFF(NCF_P_MLP1_W), H1, tid, MLP_THREADS);
   load_weight_image<64, 128>(smem + SM_W2, P + NCF_OFF(NCF_P_MLP2_W), H2, tid, MLP_THREADS);
+  // LayerNorm gamma / beta carry the dropout scale 1/(1-p): y = keep ? LN(x) * scale : 0
+  const float sc0 = A.rng[0].thresh ? A.rng[0].scale : 1.f, sc1 = A.rng[1].thresh ? A.rng[1].scale : 1.f,
+              sc2 = A.rng[2].thresh ? A.rng[2].scale : 1.f;
   for (int i = tid; i < 256; i += MLP_THREADS) {
     par[PAR_B0 + i] = P[NCF_OFF(NCF_P_MLP0_B) + i];
-    par[PAR_G0 + i] = P[NCF_OFF(NCF_P_LN0_W) + i];
-    par[PAR_E0 + i] = P[NCF_OFF(NCF_P_LN0_B) + i];
+    par[PAR_G0 + i] = P[NCF_OFF(NCF_P_LN0_W) + i] * sc0;
+    par[PAR_E0 + i] = P[NCF_OFF(NCF_P_LN0_B) + i] * sc0;
     if (i < 128) {
       par[PAR_B1 + i] = P[NCF_OFF(NCF_P_MLP1_B) + i];
-      par[PAR_G1 + i] = P[NCF_OFF(NCF_P_LN1_W) + i];
-      par[PAR_E1 + i] = P[NCF_OFF(NCF_P_LN1_B) + i];
+      par[PAR_G1 + i] = P[NCF_OFF(NCF_P_LN1_W) + i] * sc1;
+      par[PAR_E1 + i] = P[NCF_OFF(NCF_P_LN1_B) + i] * sc1;
     }
     if (i < 64) {
       par[PAR_B2 + i] = P[NCF_OFF(NCF_P_MLP2_B) + i];
-      par[PAR_G2 + i] = P[NCF_OFF(NCF_P_LN2_W) + i];
-      par[PAR_E2 + i] = P[NCF_OFF(NCF_P_LN2_B) + i];
+      par[PAR_G2 + i] = P[NCF_OFF(NCF_P_LN2_W) + i] * sc2;
+      par[PAR_E2 + i] = P[NCF_OFF(NCF_P_LN2_B) + i] * sc2;
       par[PAR_WOUT + i] = P[NCF_OFF(NCF_P_MLP_OUT_W) + i];
     }
   }
@@ -926,60 +931,72 @@ __device__ __forceinline__ void load_imgw(const uint8_t* __restrict__ p, float (
   }
 }
 
+// One layer of the backward chain for this thread's row and column part.
+// The saved r tile carries relu(z) as non-negative bf16 with the dropout decision in the sign bit (set =
+// dropped), so no random numbers are drawn here.  `gam` = gamma * 1/(1-p) (dropout scale folded in); the
+// column sums for d gamma / d beta are accumulated WITHOUT that scale and multiplied once at the flush.
+// Pass B: row sums of dy*gamma and dy*gamma*xhat, column sums for d gamma / d beta.
+// Pass C: dz = relu'(r) * LayerNorm backward -> bf16 tile (next A operand) + global + bias column sums.
 template <int C, bool FROM_TMEM>
 __device__ __forceinline__ void mlp_bwd_layer(uint32_t tmem_dy, const float* __restrict__ dy_global, int q, int h, int lane,
                                               int64_t grow, bool live, const uint8_t* __restrict__ r_img,
-                                              const float* __restrict__ gam, const DropoutRng& rng, float* s_statA,
-                                              float* s_statB, float* s_acc, uint8_t* dztile,
-                                              uint8_t* __restrict__ dz_img, const float* __restrict__ st_tile) {
+                                              const float* __restrict__ gam, float* s_statB, float* s_acc,
+                                              uint8_t* dztile, uint8_t* __restrict__ dz_img,
+                                              const float* __restrict__ st_tile) {
   constexpr int PART = C / MLP_NH, CW = PART >= 32 ? 32 : 16, NCH = PART / CW;
   const int rt = q * 32 + lane;
   const uint32_t taddr = tmem_dy + ((uint32_t)(q * 32) << 16) + h * PART;
-  const uint8_t* rrow = r_img + tile_off(rt, h * PART, C);     // + ch*CW columns = + ch*(CW/8)*128 bytes
+  const uint8_t* rrow = r_img + tile_off(rt, h * PART, C);     // 16-byte chunks of a row sit 128 bytes apart
   const bool acc_lane = lane < CW;
   // LayerNorm statistics of the saved relu output come from the forward
   const float2 ms = *reinterpret_cast<const float2*>(st_tile + rt * 2);
-  const float mean = ms.x, rstd = ms.y;
-
+  const float rstd = ms.y, nmr = -ms.x * ms.y;
+  auto load_r = [&](int ch, uint32_t (&rw)[CW / 2]) {          // the second pass finds the chunk in L1 / L2
+#pragma unroll
+    for (int j = 0; j < CW / 8; ++j) {
+      const uint4 t = __ldg(reinterpret_cast<const uint4*>(rrow + (ch * (CW / 8) + j) * 128));
+      rw[4 * j] = t.x; rw[4 * j + 1] = t.y; rw[4 * j + 2] = t.z; rw[4 * j + 3] = t.w;
+    }
+  };
   auto load_dy = [&](int ch, float (&dy)[CW]) {
-    const int c0 = h * PART + ch * CW;
     if (FROM_TMEM) {
       tmem_ldw<CW>(taddr + ch * CW, dy);
     } else {
+      const int c0 = h * PART + ch * CW;
 #pragma unroll
       for (int j = 0; j < CW / 4; ++j) {
-        float4 t = make_float4(0, 0, 0, 0);
-        if (live) t = ld4(dy_global + grow * C + c0 + 4 * j);
-        dy[4 * j] = t.x; dy[4 * j + 1] = t.y; dy[4 * j + 2] = t.z; dy[4 * j + 3] = t.w;
+        float4 v = make_float4(0, 0, 0, 0);
+        if (live) v = ld4(dy_global + grow * C + c0 + 4 * j);
+        dy[4 * j] = v.x; dy[4 * j + 1] = v.y; dy[4 * j + 2] = v.z; dy[4 * j + 3] = v.w;
       }
-    }
-    if (!live) {
-#pragma unroll
-      for (int i = 0; i < CW; ++i) dy[i] = 0.f;
-    }
-    if (rng.thresh != 0u) {
-#pragma unroll
-      for (int g8 = 0; g8 < CW / 8; ++g8) rng.apply8((uint64_t)grow * C + c0 + 8 * g8, &dy[8 * g8]);
     }
   };
 
-  // ---- pass B: row sums of dy*gamma and dy*gamma*xhat; column sums for d gamma / d beta -----------
   float s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
   for (int ch = 0; ch < NCH; ++ch) {
     const int c0 = h * PART + ch * CW;
-    float r[CW], dy[CW];
-    load_imgw<CW>(rrow + ch * (CW / 8) * 128, r);
+    float dy[CW], t[CW];
+    uint32_t rw[CW / 2];
+    load_r(ch, rw);
     load_dy(ch, dy);
 #pragma unroll
-    for (int i = 0; i < CW; ++i) {
-      const float xh = (r[i] - mean) * rstd;
-      const float dyg = dy[i] * gam[c0 + i];
-      s1 += dyg;
-      s2 = fmaf(dyg, xh, s2);
-      r[i] = dy[i] * xh;          // reuse r[] as the d gamma contribution
+    for (int i2 = 0; i2 < CW / 2; ++i2) {
+      const uint32_t w = rw[i2];
+      const uint32_t lo = w << 16;
+      const float2 g2 = *reinterpret_cast<const float2*>(gam + c0 + 2 * i2);
+      const float d0 = (int32_t)lo < 0 ? 0.f : dy[2 * i2], d1 = (int32_t)w < 0 ? 0.f : dy[2 * i2 + 1];
+      const float xh0 = fmaf(fabsf(__uint_as_float(lo)), rstd, nmr);
+      const float xh1 = fmaf(fabsf(__uint_as_float(w & 0xffff0000u)), rstd, nmr);
+      const float dg0 = d0 * g2.x, dg1 = d1 * g2.y;
+      s1 += dg0 + dg1;
+      s2 = fmaf(dg0, xh0, fmaf(dg1, xh1, s2));
+      t[2 * i2] = d0 * xh0;
+      t[2 * i2 + 1] = d1 * xh1;
+      dy[2 * i2] = d0;
+      dy[2 * i2 + 1] = d1;
     }
-    const float cg = warp_transpose_sum<CW>(r, lane);
+    const float cg = warp_transpose_sum<CW>(t, lane);
     const float cb = warp_transpose_sum<CW>(dy, lane);
     if (acc_lane) {
       atomicAdd(s_acc + c0 + lane, cg);
@@ -996,21 +1013,27 @@ __device__ __forceinline__ void mlp_bwd_layer(uint32_t tmem_dy, const float* __r
     s1 += s_statB[(rt * MLP_NH + k) * 2 + 0];
     s2 += s_statB[(rt * MLP_NH + k) * 2 + 1];
   }
-  const float m1 = s1 * (1.0f / C), m2 = s2 * (1.0f / C);
+  const float nm2 = -s2 * (1.0f / C), nm1r = -s1 * (1.0f / C) * rstd;
 
-  // ---- pass C: dz = relu'(r) * LN_backward -> bf16 tile (A operand) + global + bias column sums ----
 #pragma unroll 1
   for (int ch = 0; ch < NCH; ++ch) {
     const int c0 = h * PART + ch * CW;
-    float r[CW], dy[CW];
-    load_imgw<CW>(rrow + ch * (CW / 8) * 128, r);
+    float dy[CW];
+    uint32_t rw[CW / 2];
+    load_r(ch, rw);
     load_dy(ch, dy);
 #pragma unroll
-    for (int i = 0; i < CW; ++i) {
-      const float xh = (r[i] - mean) * rstd;
-      const float dyg = dy[i] * gam[c0 + i];
-      const float dr = rstd * (dyg - m1 - xh * m2);
-      dy[i] = (r[i] > 0.f && live) ? dr : 0.f;
+    for (int i2 = 0; i2 < CW / 2; ++i2) {
+      const uint32_t w = rw[i2];
+      const uint32_t lo = w << 16;
+      const float2 g2 = *reinterpret_cast<const float2*>(gam + c0 + 2 * i2);
+      const float r0 = fabsf(__uint_as_float(lo)), r1 = fabsf(__uint_as_float(w & 0xffff0000u));
+      const float dg0 = ((int32_t)lo < 0 ? 0.f : dy[2 * i2]) * g2.x, dg1 = ((int32_t)w < 0 ? 0.f : dy[2 * i2 + 1]) * g2.y;
+      // dr = rstd * (dyg - mean(dyg) - xhat * mean(dyg * xhat))
+      const float dr0 = fmaf(fmaf(fmaf(r0, rstd, nmr), nm2, dg0), rstd, nm1r);
+      const float dr1 = fmaf(fmaf(fmaf(r1, rstd, nmr), nm2, dg1), rstd, nm1r);
+      dy[2 * i2] = r0 > 0.f ? dr0 : 0.f;
+      dy[2 * i2 + 1] = r1 > 0.f ? dr1 : 0.f;
     }
 #pragma unroll
     for (int j = 0; j < CW / 8; ++j) {
@@ -1040,10 +1063,13 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_tc_bwd_kernel(MlpBwdArgs A
   load_weight_image<256, 64>(smem + SM_W0, P + NCF_OFF(NCF_P_MLP0_W), K0, tid, MLP_THREADS);
   load_weight_image<128, 256>(smem + SM_W1, P + NCF_OFF(NCF_P_MLP1_W), H1, tid, MLP_THREADS);
   load_weight_image<64, 128>(smem + SM_W2, P + NCF_OFF(NCF_P_MLP2_W), H2, tid, MLP_THREADS);
+  // gamma carries the dropout scale 1/(1-p) (see mlp_bwd_layer)
+  const float sc0 = A.rng[0].thresh ? A.rng[0].scale : 1.f, sc1 = A.rng[1].thresh ? A.rng[1].scale : 1.f,
+              sc2 = A.rng[2].thresh ? A.rng[2].scale : 1.f;
   for (int i = tid; i < 256; i += MLP_THREADS) {
-    par[PAR_G0 + i] = P[NCF_OFF(NCF_P_LN0_W) + i];
-    if (i < 128) par[PAR_G1 + i] = P[NCF_OFF(NCF_P_LN1_W) + i];
-    if (i < 64) par[PAR_G2 + i] = P[NCF_OFF(NCF_P_LN2_W) + i];
+    par[PAR_G0 + i] = P[NCF_OFF(NCF_P_LN0_W) + i] * sc0;
+    if (i < 128) par[PAR_G1 + i] = P[NCF_OFF(NCF_P_LN1_W) + i] * sc1;
+    if (i < 64) par[PAR_G2 + i] = P[NCF_OFF(NCF_P_LN2_W) + i] * sc2;
   }
   for (int i = tid; i < ACC_COUNT; i += MLP_THREADS) s_acc[i] = 0.f;
   if (tid == 0) {
@@ -1075,8 +1101,8 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_tc_bwd_kernel(MlpBwdArgs A
     uint8_t* z1i = reinterpret_cast<uint8_t*>(A.dz1) + tile * (128 * 256 * 2);
     uint8_t* z2i = reinterpret_cast<uint8_t*>(A.dz2) + tile * (128 * 128 * 2);
     uint8_t* z3i = reinterpret_cast<uint8_t*>(A.dz3) + tile * (128 * 64 * 2);
-    mlp_bwd_layer<64, false>(0, A.dy3_da, q, h, lane, grow, live, r3i, par + PAR_G2, A.rng[2], s_statA, s_statB,
-                             s_acc + ACC_L2, ztile, z3i, A.st3 + tile * 256);
+    mlp_bwd_layer<64, false>(0, A.dy3_da, q, h, lane, grow, live, r3i, par + PAR_G2, s_statB, s_acc + ACC_L2, ztile, z3i,
+                             A.st3 + tile * 256);
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
@@ -1089,8 +1115,8 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_tc_bwd_kernel(MlpBwdArgs A
     phase ^= 1;
     __syncthreads();
     fence_after_sync();
-    mlp_bwd_layer<128, true>(tmem + 0, nullptr, q, h, lane, grow, live, r2i, par + PAR_G1, A.rng[1], s_statA, s_statB,
-                             s_acc + ACC_L1, ztile, z2i, A.st2 + tile * 256);
+    mlp_bwd_layer<128, true>(tmem + 0, nullptr, q, h, lane, grow, live, r2i, par + PAR_G1, s_statB, s_acc + ACC_L1, ztile,
+                             z2i, A.st2 + tile * 256);
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
@@ -1103,8 +1129,8 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_tc_bwd_kernel(MlpBwdArgs A
     phase ^= 1;
     __syncthreads();
     fence_after_sync();
-    mlp_bwd_layer<256, true>(tmem + 128, nullptr, q, h, lane, grow, live, r1i, par + PAR_G0, A.rng[0], s_statA, s_statB,
-                             s_acc + ACC_L0, ztile, z1i, A.st1 + tile * 256);
+    mlp_bwd_layer<256, true>(tmem + 128, nullptr, q, h, lane, grow, live, r1i, par + PAR_G0, s_statB, s_acc + ACC_L0, ztile,
+                             z1i, A.st1 + tile * 256);
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
@@ -1134,16 +1160,20 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_tc_bwd_kernel(MlpBwdArgs A
   for (int i = tid; i < ACC_COUNT; i += MLP_THREADS) {
     int64_t off;
     int k = i;
+    float sc;          // d gamma / d beta sums were taken without the dropout scale; the bias sums carry it already
     if (k < ACC_L1) {
       off = k < 256 ? NCF_OFF(NCF_P_LN0_W) + k : k < 512 ? NCF_OFF(NCF_P_LN0_B) + (k - 256) : NCF_OFF(NCF_P_MLP0_B) + (k - 512);
+      sc = k < 512 ? sc0 : 1.f;
     } else if (k < ACC_L2) {
       k -= ACC_L1;
       off = k < 128 ? NCF_OFF(NCF_P_LN1_W) + k : k < 256 ? NCF_OFF(NCF_P_LN1_B) + (k - 128) : NCF_OFF(NCF_P_MLP1_B) + (k - 256);
+      sc = k < 256 ? sc1 : 1.f;
     } else {
       k -= ACC_L2;
       off = k < 64 ? NCF_OFF(NCF_P_LN2_W) + k : k < 128 ? NCF_OFF(NCF_P_LN2_B) + (k - 64) : NCF_OFF(NCF_P_MLP2_B) + (k - 128);
+      sc = k < 128 ? sc2 : 1.f;
     }
-    atomicAdd(dg + off, s_acc[i]);
+    atomicAdd(dg + off, s_acc[i] * sc);
   }
   fence_before_sync();
   __syncthreads();

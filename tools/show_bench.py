@@ -1,9 +1,9 @@
 #!/usr/bin/env python3
-"""Print the essentials of a bench.py JSON line read from stdin (or the error text)."""
+"""Print the essentials of a bench.py JSON line read from a file argument or stdin (or the error text)."""
 import json
 import sys
 
-txt = sys.stdin.read().strip().splitlines()
+txt = (open(sys.argv[1]).read() if len(sys.argv) > 1 else sys.stdin.read()).strip().splitlines()
 line = next((ln for ln in reversed(txt) if ln.startswith("{")), None)
 if line is None:
     print("NO JSON LINE:\n" + "\n".join(txt[-15:]))
