@@ -271,7 +271,7 @@ __device__ __forceinline__ void mlp_epilogue(uint32_t tmem_acc, int q, int h, in
 
 __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_tc_fwd_kernel(MlpFwdArgs A) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ __align__(8) uint64_t bar;
+  __shared__ __align__(8) uint64_t bar, bar1;
   __shared__ __align__(8) uint64_t full[2];
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -309,6 +309,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_tc_fwd_kernel(MlpFwdArgs A
     par[PAR_SCAL + 2] = P[NCF_OFF(NCF_P_FINAL_W) + 1];
     par[PAR_SCAL + 3] = P[NCF_OFF(NCF_P_FINAL_B)];
     mbar_init(&bar, 1);
+    mbar_init(&bar1, 1);
     mbar_init(&full[0], 1);
     mbar_init(&full[1], 1);
     mbar_fence_init();
@@ -326,9 +327,25 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_tc_fwd_kernel(MlpFwdArgs A
   const int64_t ntiles = (A.N + TCM_ROWS - 1) / TCM_ROWS;
   constexpr uint32_t A_BYTES = 128 * 64 * 2;
   const uint8_t* a_img = reinterpret_cast<const uint8_t*>(A.a_img);
-  if (tid == 0 && (int64_t)blockIdx.x < ntiles) {          // TMA bulk copy of the first input tile
+  // Layer-1 GEMMs run ONE TILE AHEAD: the accumulator columns [0,256) are free as soon as epilogue 1 of the
+  // current tile is done, so the next tile's GEMM is issued together with the current tile's layer-2 GEMM
+  // and its latency (and the TMA load feeding it) hides behind epilogues 2 and 3.
+  auto issue_l1 = [&](int b) {
+    issue_gemm(tmem + 0, smem_addr(smem + (b ? SM_A1 : SM_A0)), 128, 64 * 16, 256, sW0, 128, 64 * 16, 256,
+               make_idesc(128, 256, false, false), 4, false);
+    mma_commit(&bar1);
+  };
+  if (tid == 0 && (int64_t)blockIdx.x < ntiles) {          // TMA bulk copies of the first two input tiles
     mbar_arrive_expect_tx(&full[0], A_BYTES);
     bulk_g2s(smem + SM_A0, a_img + (int64_t)blockIdx.x * A_BYTES, A_BYTES, &full[0]);
+    const int64_t second = (int64_t)blockIdx.x + gridDim.x;
+    if (second < ntiles) {
+      mbar_arrive_expect_tx(&full[1], A_BYTES);
+      bulk_g2s(smem + SM_A1, a_img + second * A_BYTES, A_BYTES, &full[1]);
+    }
+    mbar_wait(&full[0], 0);
+    fence_after_sync();
+    issue_l1(0);
   }
   int it = 0;
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
@@ -338,20 +355,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_tc_fwd_kernel(MlpFwdArgs A
     const int rt = q * 32 + lane;
     const int64_t grow = row0 + rt;
     const bool live = rt < avail;
-    if (tid == 0) {
-      const int64_t next = tile + gridDim.x;
-      if (next < ntiles) {                                  // prefetch the next tile into the other buffer
-        mbar_arrive_expect_tx(&full[buf ^ 1], A_BYTES);
-        bulk_g2s(smem + (buf ? SM_A0 : SM_A1), a_img + next * A_BYTES, A_BYTES, &full[buf ^ 1]);
-      }
-      mbar_wait(&full[buf], (it >> 1) & 1);
-      fence_after_sync();
-      issue_gemm(tmem + 0, smem_addr(smem + (buf ? SM_A1 : SM_A0)), 128, 64 * 16, 256, sW0, 128, 64 * 16, 256,
-                 make_idesc(128, 256, false, false), 4, false);
-      mma_commit(&bar);
-    }
-    if (warp == 0) mbar_wait(&bar, phase);      // one warp polls the mbarrier, the rest park on the CTA barrier
-    phase ^= 1;
+    if (warp == 0) mbar_wait(&bar1, it & 1);    // one warp polls the mbarrier, the rest park on the CTA barrier
     __syncthreads();
     fence_after_sync();
     float hp;
@@ -378,6 +382,17 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_tc_fwd_kernel(MlpFwdArgs A
       fence_after_sync();
       issue_gemm(tmem + 256, sY, 128, 256 * 16, 256, sW1, 128, 256 * 16, 256, make_idesc(128, 128, false, false), 16, false);
       mma_commit(&bar);
+      const int64_t next = tile + gridDim.x;
+      if (next < ntiles) {
+        mbar_wait(&full[buf ^ 1], ((it + 1) >> 1) & 1);
+        fence_after_sync();
+        issue_l1(buf ^ 1);
+        const int64_t next2 = next + gridDim.x;
+        if (next2 < ntiles) {                               // this tile's input buffer is free: layer-1 GEMM done
+          mbar_arrive_expect_tx(&full[buf], A_BYTES);
+          bulk_g2s(smem + (buf ? SM_A1 : SM_A0), a_img + next2 * A_BYTES, A_BYTES, &full[buf]);
+        }
+      }
     }
     if (warp == 0) mbar_wait(&bar, phase);      // one warp polls the mbarrier, the rest park on the CTA barrier
     phase ^= 1;
@@ -937,27 +952,36 @@ __device__ __forceinline__ void load_imgw(const uint8_t* __restrict__ p, float (
 // column sums for d gamma / d beta are accumulated WITHOUT that scale and multiplied once at the flush.
 // Pass B: row sums of dy*gamma and dy*gamma*xhat, column sums for d gamma / d beta.
 // Pass C: dz = relu'(r) * LayerNorm backward -> bf16 tile (next A operand) + global + bias column sums.
+// chunk `ch` (CW columns) of this thread's part of a saved r tile: CW/8 16-byte pieces, 128 bytes apart
+template <int C>
+struct BwdGeom {
+  static constexpr int PART = C / MLP_NH, CW = PART >= 32 ? 32 : 16, NCH = PART / CW;
+};
+template <int C>
+__device__ __forceinline__ void load_r_chunk(const uint8_t* __restrict__ r_img, int rt, int h, int ch,
+                                             uint32_t (&rw)[BwdGeom<C>::CW / 2]) {
+  constexpr int PART = BwdGeom<C>::PART, CW = BwdGeom<C>::CW;
+  const uint8_t* p = r_img + tile_off(rt, h * PART + ch * CW, C);
+#pragma unroll
+  for (int j = 0; j < CW / 8; ++j) {
+    const uint4 t = __ldg(reinterpret_cast<const uint4*>(p + j * 128));
+    rw[4 * j] = t.x; rw[4 * j + 1] = t.y; rw[4 * j + 2] = t.z; rw[4 * j + 3] = t.w;
+  }
+}
+
 template <int C, bool FROM_TMEM>
 __device__ __forceinline__ void mlp_bwd_layer(uint32_t tmem_dy, const float* __restrict__ dy_global, int q, int h, int lane,
                                               int64_t grow, bool live, const uint8_t* __restrict__ r_img,
-                                              const float* __restrict__ gam, float* s_statB, float* s_acc,
-                                              uint8_t* dztile, uint8_t* __restrict__ dz_img,
+                                              uint32_t (&rw)[BwdGeom<C>::CW / 2], const float* __restrict__ gam,
+                                              float* s_statB, float* s_acc, uint8_t* dztile, uint8_t* __restrict__ dz_img,
                                               const float* __restrict__ st_tile) {
-  constexpr int PART = C / MLP_NH, CW = PART >= 32 ? 32 : 16, NCH = PART / CW;
+  constexpr int PART = BwdGeom<C>::PART, CW = BwdGeom<C>::CW, NCH = BwdGeom<C>::NCH;
   const int rt = q * 32 + lane;
   const uint32_t taddr = tmem_dy + ((uint32_t)(q * 32) << 16) + h * PART;
-  const uint8_t* rrow = r_img + tile_off(rt, h * PART, C);     // 16-byte chunks of a row sit 128 bytes apart
   const bool acc_lane = lane < CW;
   // LayerNorm statistics of the saved relu output come from the forward
   const float2 ms = *reinterpret_cast<const float2*>(st_tile + rt * 2);
   const float rstd = ms.y, nmr = -ms.x * ms.y;
-  auto load_r = [&](int ch, uint32_t (&rw)[CW / 2]) {          // the second pass finds the chunk in L1 / L2
-#pragma unroll
-    for (int j = 0; j < CW / 8; ++j) {
-      const uint4 t = __ldg(reinterpret_cast<const uint4*>(rrow + (ch * (CW / 8) + j) * 128));
-      rw[4 * j] = t.x; rw[4 * j + 1] = t.y; rw[4 * j + 2] = t.z; rw[4 * j + 3] = t.w;
-    }
-  };
   auto load_dy = [&](int ch, float (&dy)[CW]) {
     if (FROM_TMEM) {
       tmem_ldw<CW>(taddr + ch * CW, dy);
@@ -972,13 +996,15 @@ __device__ __forceinline__ void mlp_bwd_layer(uint32_t tmem_dy, const float* __r
     }
   };
 
+  // `rw` arrives holding chunk 0 (loaded by the caller BEFORE it waited for the upstream MMA); with more than
+  // one chunk the next one is requested before the current one is consumed, wrapping around to chunk 0 for pass C.
   float s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
   for (int ch = 0; ch < NCH; ++ch) {
     const int c0 = h * PART + ch * CW;
     float dy[CW], t[CW];
-    uint32_t rw[CW / 2];
-    load_r(ch, rw);
+    uint32_t rn[CW / 2];
+    if (NCH > 1) load_r_chunk<C>(r_img, rt, h, ch + 1 < NCH ? ch + 1 : 0, rn);
     load_dy(ch, dy);
 #pragma unroll
     for (int i2 = 0; i2 < CW / 2; ++i2) {
@@ -995,6 +1021,10 @@ __device__ __forceinline__ void mlp_bwd_layer(uint32_t tmem_dy, const float* __r
       t[2 * i2 + 1] = d1 * xh1;
       dy[2 * i2] = d0;
       dy[2 * i2 + 1] = d1;
+    }
+    if (NCH > 1) {
+#pragma unroll
+      for (int i = 0; i < CW / 2; ++i) rw[i] = rn[i];
     }
     const float cg = warp_transpose_sum<CW>(t, lane);
     const float cb = warp_transpose_sum<CW>(dy, lane);
@@ -1019,8 +1049,8 @@ __device__ __forceinline__ void mlp_bwd_layer(uint32_t tmem_dy, const float* __r
   for (int ch = 0; ch < NCH; ++ch) {
     const int c0 = h * PART + ch * CW;
     float dy[CW];
-    uint32_t rw[CW / 2];
-    load_r(ch, rw);
+    uint32_t rn[CW / 2];
+    if (NCH > 1 && ch + 1 < NCH) load_r_chunk<C>(r_img, rt, h, ch + 1, rn);
     load_dy(ch, dy);
 #pragma unroll
     for (int i2 = 0; i2 < CW / 2; ++i2) {
@@ -1034,6 +1064,10 @@ __device__ __forceinline__ void mlp_bwd_layer(uint32_t tmem_dy, const float* __r
       const float dr1 = fmaf(fmaf(fmaf(r1, rstd, nmr), nm2, dg1), rstd, nm1r);
       dy[2 * i2] = r0 > 0.f ? dr0 : 0.f;
       dy[2 * i2 + 1] = r1 > 0.f ? dr1 : 0.f;
+    }
+    if (NCH > 1 && ch + 1 < NCH) {
+#pragma unroll
+      for (int i = 0; i < CW / 2; ++i) rw[i] = rn[i];
     }
 #pragma unroll
     for (int j = 0; j < CW / 8; ++j) {
@@ -1101,8 +1135,21 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_tc_bwd_kernel(MlpBwdArgs A
     uint8_t* z1i = reinterpret_cast<uint8_t*>(A.dz1) + tile * (128 * 256 * 2);
     uint8_t* z2i = reinterpret_cast<uint8_t*>(A.dz2) + tile * (128 * 128 * 2);
     uint8_t* z3i = reinterpret_cast<uint8_t*>(A.dz3) + tile * (128 * 64 * 2);
-    mlp_bwd_layer<64, false>(0, A.dy3_da, q, h, lane, grow, live, r3i, par + PAR_G2, s_statB, s_acc + ACC_L2, ztile, z3i,
-                             A.st3 + tile * 256);
+    uint32_t rw3[BwdGeom<64>::CW / 2], rw2[BwdGeom<128>::CW / 2], rw1[BwdGeom<256>::CW / 2];
+    if (tid == 0) {       // pull the NEXT tile's saved tensors into L2 while this one is processed
+      const int64_t nt = tile + gridDim.x;
+      if (nt < ntiles) {
+        bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(A.r1) + nt * (128 * 256 * 2), 128 * 256 * 2);
+        bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(A.r2) + nt * (128 * 128 * 2), 128 * 128 * 2);
+        bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(A.r3) + nt * (128 * 64 * 2), 128 * 64 * 2);
+        const int64_t live_next = min((int64_t)TCM_ROWS, A.N - nt * TCM_ROWS);
+        bulk_prefetch_l2(A.dy3_da + nt * TCM_ROWS * D, (uint32_t)(live_next * D * 4));
+      }
+    }
+    load_r_chunk<64>(r3i, rt, h, 0, rw3);
+    load_r_chunk<128>(r2i, rt, h, 0, rw2);       // consumed after the first MMA: its latency hides behind layer 3
+    mlp_bwd_layer<64, false>(0, A.dy3_da, q, h, lane, grow, live, r3i, rw3, par + PAR_G2, s_statB, s_acc + ACC_L2, ztile,
+                             z3i, A.st3 + tile * 256);
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
@@ -1115,8 +1162,9 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_tc_bwd_kernel(MlpBwdArgs A
     phase ^= 1;
     __syncthreads();
     fence_after_sync();
-    mlp_bwd_layer<128, true>(tmem + 0, nullptr, q, h, lane, grow, live, r2i, par + PAR_G1, s_statB, s_acc + ACC_L1, ztile,
-                             z2i, A.st2 + tile * 256);
+    load_r_chunk<256>(r1i, rt, h, 0, rw1);       // consumed after the second MMA
+    mlp_bwd_layer<128, true>(tmem + 0, nullptr, q, h, lane, grow, live, r2i, rw2, par + PAR_G1, s_statB, s_acc + ACC_L1,
+                             ztile, z2i, A.st2 + tile * 256);
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
@@ -1129,8 +1177,8 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_tc_bwd_kernel(MlpBwdArgs A
     phase ^= 1;
     __syncthreads();
     fence_after_sync();
-    mlp_bwd_layer<256, true>(tmem + 128, nullptr, q, h, lane, grow, live, r1i, par + PAR_G0, s_statB, s_acc + ACC_L0, ztile,
-                             z1i, A.st1 + tile * 256);
+    mlp_bwd_layer<256, true>(tmem + 128, nullptr, q, h, lane, grow, live, r1i, rw1, par + PAR_G0, s_statB, s_acc + ACC_L0,
+                             ztile, z1i, A.st1 + tile * 256);
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
