@@ -20,6 +20,7 @@ struct TowerWs {
   // bf16 tensors of the tcgen05 path (NCF_BF16_TC): saved activations and pre-activation gradients
   void *r1b, *y1b, *r2b, *y2b, *r3b, *dz1b, *dz2b, *dz3b;
   float* wg_partial;                       // per-CTA weight-gradient accumulators of the tcgen05 MLP wgrad kernel
+  float* at_partial;                       // same for the fused attention backward
   void* a_img;                             // attention output as bf16 tile image [ceil(N/128)][128 x 64]
   float *st1, *st2, *st3;                  // LayerNorm (mean, rstd) per row of the three MLP layers
   char* emb;                               // workspace of the fused embedding backward
@@ -43,6 +44,11 @@ int tc_proj_forward(int which, const float* X, const float* W, const float* bias
 int tc_proj_forward_img(const float* X, const float* W, const float* bias, void* img, int64_t N, cudaStream_t st);
 int tc_proj_dgrad(int which, const float* dY, const float* W, float* dX, int64_t N, cudaStream_t st);
 int tc_proj_wgrad(int which, const float* Z, const float* X, float* dW, float* db, int64_t N, cudaStream_t st);
+// fused attention block on tcgen05 for S = 5 (ncf_attn_tc.cu): forward xu, xp -> a_img; backward da (w.g64a) ->
+// dxu (w.g64b), dxp (w.g256) + the attention parameter gradients, recomputing q, k, v and the probabilities
+int attn_tc_forward(const ncf_run_cfg& cfg, const float* dense, int64_t N, TowerWs& w, cudaStream_t st);
+int attn_tc_backward(const ncf_run_cfg& cfg, const float* dense, float* dense_grad, int64_t N, TowerWs& w, cudaStream_t st);
+int64_t attn_tc_partial_floats();
 // fused embedding backward of both sides with a single radix sort (ncf_embed.cu)
 int emb_bwd_both(const ncf_adam_cfg* adam, const ncf_tables* T, const float* dense, float* dense_grad,
                  const int64_t* user_ids, const int64_t* item_ids, int64_t N, const float* d_mf_pred, const float* dxu,

@@ -5,6 +5,8 @@
 //
 // Reference: architecture.py:18-57 (MultiHeadAttention), :230-252 (mlp, heads), :311-354 (forward),
 // trainer.py:78,271 (BCELoss).
+#include <cstdlib>
+
 #include "ncf_tower.cuh"
 
 namespace ncf {
@@ -662,6 +664,16 @@ __global__ void __launch_bounds__(256) bce_kernel(const float* __restrict__ out,
 // =============================================================================================
 // orchestration
 // =============================================================================================
+// NCF_ATTN_FUSED: 1 (default) = fused tcgen05 attention block for S = 5; 0 = separate projection / core kernels;
+// 2 = debug: unfused path runs too (keeps q, kv, ctx for the unfused backward), the fused forward output is used
+static int attn_fused_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("NCF_ATTN_FUSED");
+    mode = e ? atoi(e) : 1;
+  }
+  return mode;
+}
 TowerWs carve_tower_ws(void* ws, int64_t N, const ncf_run_cfg& cfg) {
   TowerWs w{};
   Carver c(ws);
@@ -708,6 +720,7 @@ TowerWs carve_tower_ws(void* ws, int64_t N, const ncf_run_cfg& cfg) {
       w.dz2b = c.take<uint16_t>(Np * H2);
       w.dz3b = c.take<uint16_t>(Np * H3);
       w.wg_partial = c.take<float>((int64_t)num_sms() * 448 * 128);
+      w.at_partial = c.take<float>(attn_tc_partial_floats());
     }
     w.emb_bytes = ncf_emb_bwd_workspace_bytes(N);
     w.emb = c.take<char>(w.emb_bytes);
@@ -722,7 +735,10 @@ int tower_f32_forward(const ncf_run_cfg& cfg, const float* dense, int64_t N, con
   const int S = cfg.S;
   const float* P = dense;
   const bool tc = cfg.precision == NCF_BF16_TC;
-  if (train || S > 1) {
+  const bool fused_attn = tc && S == 5 && attn_fused_mode() != 0;
+  if (fused_attn && attn_fused_mode() == 1) {
+    NCF_TRY(attn_tc_forward(cfg, dense, N, w, st));       // xu, xp -> a_img in one kernel; nothing else is kept
+  } else if (train || S > 1) {
     // q = q_proj(xu); [k|v] = [k_proj; v_proj](xp)        (architecture.py:40-42)
     if (tc) {
       NCF_TRY(tc_proj_forward(0, w.xu, P + NCF_OFF(NCF_P_Q_W), P + NCF_OFF(NCF_P_Q_B), w.q, N, st));
@@ -738,9 +754,11 @@ int tower_f32_forward(const ncf_run_cfg& cfg, const float* dense, int64_t N, con
     // one key per query: softmax == 1, ctx = v_proj(xp)      (architecture.py:275-276)
     NCF_TRY((launch_linear<64, false, EPI_NONE>(lin(w.xp, D, P + NCF_OFF(NCF_P_V_W), D, P + NCF_OFF(NCF_P_V_B), w.ctx, D, N, D), st)));
   }
-  if (tc)
+  if (fused_attn && attn_fused_mode() == 1) {
+  } else if (tc) {
     NCF_TRY(tc_proj_forward_img(w.ctx, P + NCF_OFF(NCF_P_O_W), P + NCF_OFF(NCF_P_O_B), w.a_img, N, st));
-  else
+    if (fused_attn) NCF_TRY(attn_tc_forward(cfg, dense, N, w, st));   // debug mode 2: both paths, fused output wins
+  } else
     NCF_TRY((launch_linear<64, false, EPI_NONE>(lin(w.ctx, D, P + NCF_OFF(NCF_P_O_W), D, P + NCF_OFF(NCF_P_O_B), w.a, D, N, D), st)));
   if (cfg.precision == NCF_BF16_TC) return mlp_tc_forward(cfg, dense, N, hour, tail1, out, w, st);
   // MLP: the 32 temporal input columns are zeros in forward (architecture.py:329-340), so only the
@@ -792,6 +810,12 @@ int tower_f32_backward(const ncf_run_cfg& cfg, const float* dense, float* dg, in
   NCF_TRY((launch_linear<64, true, EPI_NONE>(lin(w.g256b, H1, P + NCF_OFF(NCF_P_MLP0_W), K0, nullptr, w.g64a, D, N, H1), st)));
   }
   const bool tc = cfg.precision == NCF_BF16_TC;
+  if (tc && S == 5 && attn_fused_mode() == 1) {
+    NCF_TRY(attn_tc_backward(cfg, dense, dg, N, w, st));
+    w.dxu = w.g64b;
+    w.dxp = w.g256;
+    return NCF_OK;
+  }
   // out_proj: dWo += da^T ctx, dbo ; dctx (g64b) = da . Wo
   if (tc) {
     NCF_TRY(tc_proj_backward(0, w.g64a, w.ctx, P + NCF_OFF(NCF_P_O_W), w.g64b, dg + NCF_OFF(NCF_P_O_W), dg + NCF_OFF(NCF_P_O_B), N, st));

@@ -12,6 +12,8 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 
+#include "ncf_common.cuh"
+
 namespace ncf {
 namespace umma {
 
@@ -174,6 +176,58 @@ __device__ __forceinline__ void unpack_bf16x8(uint4 q, float (&v)[8]) {
     v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
   }
 }
+
+// ---- operand tiles and GEMM issue ---------------------------------------------------------------
+// Fill a [R x C] bf16 operand tile (canonical layout, see ncf_umma.cuh) from an fp32 row-major source.
+// Thread mapping: each quarter warp writes one 128-byte core matrix (8 rows x 16 B, conflict-free) and
+// the four quarters of a warp read four adjacent 32-byte chunks of the same 8 rows (full sectors).
+template <int C>
+__device__ __forceinline__ void fill_tile_f32(uint8_t* tile, const float* __restrict__ src, int64_t ld, int64_t row0,
+                                              int64_t rows_avail, int R, int tid, int nthreads) {
+  constexpr int CH = C / 8;                       // 16-byte chunks per row
+  const int total = R * CH;
+  for (int q = tid; q < total; q += nthreads) {
+    const int blk = q >> 5, l = q & 31;           // 32 chunks per (8 rows x 4 chunks) block
+    const int blocks_per_rowgroup = CH / 4;
+    const int rg = blk / blocks_per_rowgroup, cb = blk % blocks_per_rowgroup;
+    const int r = rg * 8 + (l & 7), j = cb * 4 + (l >> 3);
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (r < rows_avail) {
+      const float* p = src + (row0 + r) * ld + 8 * j;
+      const float4 a = ldg4(p), b = ldg4(p + 4);
+      v = make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(b.x, b.y), pack_bf16(b.z, b.w));
+    }
+    *reinterpret_cast<uint4*>(tile + tile_off(r, 8 * j, C)) = v;
+  }
+}
+// same, bf16 row-major source
+template <int C>
+__device__ __forceinline__ void fill_tile_bf16(uint8_t* tile, const __nv_bfloat16* __restrict__ src, int64_t ld,
+                                               int64_t row0, int64_t rows_avail, int R, int tid, int nthreads) {
+  constexpr int CH = C / 8;
+  const int total = R * CH;
+  for (int q = tid; q < total; q += nthreads) {
+    const int blk = q >> 5, l = q & 31;
+    const int blocks_per_rowgroup = CH / 4;
+    const int rg = blk / blocks_per_rowgroup, cb = blk % blocks_per_rowgroup;
+    const int r = rg * 8 + (l & 7), j = cb * 4 + (l >> 3);
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (r < rows_avail) v = __ldg(reinterpret_cast<const uint4*>(src + (row0 + r) * ld + 8 * j));
+    *reinterpret_cast<uint4*>(tile + tile_off(r, 8 * j, C)) = v;
+  }
+}
+
+// One GEMM = `ksteps` tcgen05.mma of K=16 each.  a_step / b_step: byte advance of the operand start
+// address per K step (2 core matrices along K).
+__device__ __forceinline__ void issue_gemm(uint32_t tmem_d, uint32_t a_addr, uint32_t a_lbo, uint32_t a_sbo,
+                                           uint32_t a_step, uint32_t b_addr, uint32_t b_lbo, uint32_t b_sbo,
+                                           uint32_t b_step, uint32_t idesc, int ksteps, bool accumulate_first) {
+  for (int k = 0; k < ksteps; ++k) {
+    mma_bf16(tmem_d, make_desc(a_addr + k * a_step, a_lbo, a_sbo), make_desc(b_addr + k * b_step, b_lbo, b_sbo), idesc,
+             accumulate_first || k > 0);
+  }
+}
+
 
 }  // namespace umma
 }  // namespace ncf
