@@ -103,7 +103,7 @@ __device__ __forceinline__ void attn_load_params(uint8_t* smem, uint32_t off_wq,
   }
 }
 
-__global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_fwd_kernel(AttnFwdArgs A) {
+__global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_fwd_kernel(AttnFwdArgs A) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t tmem_slot;
@@ -135,6 +135,14 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_fwd_kernel(AttnFwdArgs 
     const int64_t n = n0 + row;
     const int64_t avail = max((int64_t)0, min((int64_t)AT_RT, A.N - n0));
     const bool live = row < avail;
+    if (tid == 0) {       // pull the next tile's rows into L2 while this one is processed
+      const int64_t nn0 = (tile + gridDim.x) * AT_RT;
+      const int64_t nav = min((int64_t)AT_RT, A.N - nn0);
+      if (nav > 0) {
+        bulk_prefetch_l2(A.xu + nn0 * 64, (uint32_t)(nav * 256));
+        bulk_prefetch_l2(A.xp + nn0 * 64, (uint32_t)(nav * 256));
+      }
+    }
     fill_tile_f32<64>(smem + AF_XU, A.xu, 64, n0, avail, 128, tid, AT_THREADS);
     fill_tile_f32<64>(smem + AF_XP, A.xp, 64, n0, avail, 128, tid, AT_THREADS);
     fence_async_smem();
@@ -268,26 +276,50 @@ struct AttnBwdArgs {
   DropoutRng rng;
 };
 
-// fp32 rows -> bf16 tile with LAYOUT columns per row group; ONES adds the [1 | 0...] chunk at column 64
-template <int LAYOUT, bool ONES>
-__device__ __forceinline__ void attn_fill(uint8_t* tile, const float* __restrict__ src, int64_t row0, int64_t avail, int tid) {
-  for (int c = tid; c < 128 * 8; c += AT_THREADS) {
+// Register-staged [128 x 64] fp32 rows: the global loads of the NEXT tile are issued while the tensor core works
+// on the current one; the bf16 conversion and the shared-memory stores happen when the tile buffer is free.
+// Each thread owns 2 chunks of 8 columns (the four quarters of a warp read four adjacent 32-byte pieces of the
+// same 8 rows; each quarter writes one 128-byte core matrix).
+struct AttnStage {
+  float4 a[2], b[2];
+  __device__ __forceinline__ static void rc(int c, int& r, int& j) {
     const int blk = c >> 5, l = c & 31;
-    const int r = (blk >> 1) * 8 + (l & 7), j = (blk & 1) * 4 + (l >> 3);
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (r < avail) {
-      const float* p = src + (row0 + r) * 64 + 8 * j;
-      const float4 a = ldg4(p), b = ldg4(p + 4);
-      v = make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(b.x, b.y), pack_bf16(b.z, b.w));
+    r = (blk >> 1) * 8 + (l & 7);
+    j = (blk & 1) * 4 + (l >> 3);
+  }
+  __device__ __forceinline__ void load(const float* __restrict__ src, int64_t row0, int64_t avail, int tid) {
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      int r, j;
+      rc(tid + k * AT_THREADS, r, j);
+      a[k] = make_float4(0, 0, 0, 0);
+      b[k] = a[k];
+      if (r < avail) {
+        const float* p = src + (row0 + r) * 64 + 8 * j;
+        asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(a[k].x), "=f"(a[k].y), "=f"(a[k].z), "=f"(a[k].w) : "l"(p));
+        asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(b[k].x), "=f"(b[k].y), "=f"(b[k].z), "=f"(b[k].w) : "l"(p + 4));
+      }
     }
-    *reinterpret_cast<uint4*>(tile + tile_off(r, 8 * j, LAYOUT)) = v;
   }
-  if (ONES && tid < 128) {
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (tid < avail) v.x = 0x00003f80u;     // bf16(1.0): column 64 = 1, columns 65..71 = 0
-    *reinterpret_cast<uint4*>(tile + tile_off(tid, 64, LAYOUT)) = v;
+  // LAYOUT columns per row group; ONES adds the [1 | 0...] chunk at column 64 (bias gradient)
+  template <int LAYOUT, bool ONES>
+  __device__ __forceinline__ void store(uint8_t* tile, int64_t avail, int tid) const {
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      int r, j;
+      rc(tid + k * AT_THREADS, r, j);
+      *reinterpret_cast<uint4*>(tile + tile_off(r, 8 * j, LAYOUT)) =
+          make_uint4(pack_bf16(a[k].x, a[k].y), pack_bf16(a[k].z, a[k].w), pack_bf16(b[k].x, b[k].y), pack_bf16(b[k].z, b[k].w));
+    }
+    if (ONES && tid < 128) {
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (tid < avail) v.x = 0x00003f80u;     // bf16(1.0): column 64 = 1, columns 65..71 = 0
+      *reinterpret_cast<uint4*>(tile + tile_off(tid, 64, LAYOUT)) = v;
+    }
   }
-}
+};
 
 __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_bwd_kernel(AttnBwdArgs A) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -322,14 +354,27 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_bwd_kernel(AttnBwdArgs 
   const int64_t ntiles = (A.N + AT_RT - 1) / AT_RT;
   const int gl = row / AT_S, i_q = row - gl * AT_S, gb = gl * AT_S;
 
+  AttnStage su, sp, sa;
+  if ((int64_t)blockIdx.x < ntiles) {
+    const int64_t n0 = (int64_t)blockIdx.x * AT_RT, avail = min((int64_t)AT_RT, A.N - n0);
+    su.load(A.xu, n0, avail, tid);
+    sp.load(A.xp, n0, avail, tid);
+    sa.load(A.da, n0, avail, tid);
+  }
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int64_t n0 = tile * AT_RT;
     const int64_t n = n0 + row;
     const int64_t avail = max((int64_t)0, min((int64_t)AT_RT, A.N - n0));
     const bool live = row < avail;
-    attn_fill<AT_CXL, true>(smem + AB_XU, A.xu, n0, avail, tid);
-    attn_fill<AT_CXL, true>(smem + AB_XP, A.xp, n0, avail, tid);
-    attn_fill<128, false>(smem + AB_DA, A.da, n0, avail, tid);
+    const int64_t nn0 = (tile + gridDim.x) * AT_RT, nav = max((int64_t)0, min((int64_t)AT_RT, A.N - nn0));
+    if (tid == 0 && nav > 0) {      // the register prefetch below then finds the next tile in L2
+      bulk_prefetch_l2(A.xu + nn0 * 64, (uint32_t)(nav * 256));
+      bulk_prefetch_l2(A.xp + nn0 * 64, (uint32_t)(nav * 256));
+      bulk_prefetch_l2(A.da + nn0 * 64, (uint32_t)(nav * 256));
+    }
+    su.store<AT_CXL, true>(smem + AB_XU, avail, tid);
+    sp.store<AT_CXL, true>(smem + AB_XP, avail, tid);
+    sa.store<128, false>(smem + AB_DA, avail, tid);
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
@@ -391,6 +436,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_bwd_kernel(AttnBwdArgs 
           load_bf16x16(smem + AB_KB + ((gb + j) * AT_XS + h * 16) * 2, kk);
           p[j] = dot16(qv, kk) * 0.25f;
           mx = fmaxf(mx, p[j]);
+          asm volatile("" ::: "memory");      // keep the shared-memory loads of later rows from piling up in registers
         }
         float sum = 0.f;
 #pragma unroll
@@ -414,6 +460,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_bwd_kernel(AttnBwdArgs 
           for (int c = 0; c < 16; ++c) o[c] = fmaf(pp[j], vv[c], o[c]);
           dp[j] = dot16(dc, vv) * kj;                      // dL/dp_ij
           dot = fmaf(p[j], dp[j], dot);
+          asm volatile("" ::: "memory");
         }
 #pragma unroll
         for (int j = 0; j < AT_S; ++j) {
@@ -422,6 +469,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_bwd_kernel(AttnBwdArgs 
           load_bf16x16(smem + AB_KB + ((gb + j) * AT_XS + h * 16) * 2, kk);
 #pragma unroll
           for (int c = 0; c < 16; ++c) dq[c] = fmaf(ds[j], kk[c], dq[c]);
+          asm volatile("" ::: "memory");
         }
       }
 #pragma unroll
@@ -455,6 +503,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_bwd_kernel(AttnBwdArgs 
         load_bf16x16(smem + AB_CB + ((gb + i) * AT_XS + h * 16) * 2, t);
 #pragma unroll
         for (int c = 0; c < 16; ++c) dv[c] = fmaf(ppi, t[c], dv[c]);
+        asm volatile("" ::: "memory");
       }
     }
     __syncthreads();     // the exchange arrays are dead: the operand tiles take their place
@@ -485,6 +534,11 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_bwd_kernel(AttnBwdArgs 
       mma_commit(&bar);
     }
     first = false;
+    if (nav > 0) {       // next tile's rows: in flight during the GEMMs and the dx stores
+      su.load(A.xu, nn0, nav, tid);
+      sp.load(A.xp, nn0, nav, tid);
+      sa.load(A.da, nn0, nav, tid);
+    }
     if (warp == 0) mbar_wait(&bar, phase);
     phase ^= 1;
     __syncthreads();
