@@ -38,6 +38,14 @@ BYTES_FWD_PER_INTERACTION = 3072 + 80          # (2 user + 2*S item r
 BYTES_BWD_PER_INTERACTION = 18432              # 12 unique rows * (read w,m,v + write w,m,v)
 FLOP_FWD_PER_ROW = 165e3                       # SURVEY 8d dense towers, forward
 FLOP_TRAIN_PER_ROW = 495e3
+FLOP_ATTN_FWD = 32.8e3 + 1.3e3                 # projections + scores/AV per row; backward = 2x, + 1x recompute
+FLOP_MLP_FWD = 131.1e3 + 0.5e3                 # MLP + heads/LN per row; backward = 2x
+# bytes per sample row a fused implementation has to move: fp32 row vectors in and out,
+# bf16 saved activations between forward and backward
+BYTES_ATTN_FWD = 2 * 256 + 128                 # xu, xp in; a (bf16) out
+BYTES_MLP_FWD = 128 + 2 * (512 + 256) + 128 + 24 + 256 + 16        # a in; r1,y1,r2,y2,r3 (bf16), LN stats, y3, scalars out
+BYTES_MLP_BWD = (256 + 16 + 256) + (256 + 896 + 24 + 896 + 256) + (128 + 768 + 896)   # head; chain; weight gradients
+BYTES_ATTN_BWD = 3 * 256 + 2 * 256             # xu, xp, da in; dxu, dxp out
 
 
 def peaks():
@@ -462,6 +470,16 @@ def main():
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": N * (8 + 8 + 4),
                     "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms_total / args.steps},
             "gpu_launches": launches, "clocks": clocks, "roofline": None, "cpu_baseline": None, "last_loss": last_loss}
+        # whole-step HBM view over all ranks (per-kernel pieces are measured by the N=1 run): algorithmic bytes
+        # of the towers + embedding path per sample row, sparse table update
+        pk = peaks()
+        row_bytes = (BYTES_ATTN_FWD + BYTES_MLP_FWD + BYTES_MLP_BWD + BYTES_ATTN_BWD
+                     + (BYTES_FWD_PER_INTERACTION + BYTES_BWD_PER_INTERACTION) / S)
+        gbs = world * N * row_bytes / ms_step / 1e6
+        line["roofline"] = {"kernel": "whole step, all ranks (NVLink exchange not counted)", "bound": "hbm", "achieved": gbs,
+                            "peak": world * pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / (world * pk["hbm_gbs"]),
+                            "traffic": None, "peak_source": pk["source"] + " (copy) x n_gpus",
+                            "algorithmic_bytes_per_row": row_bytes}
         print(json.dumps(line))
         dist.destroy_process_group()
         return
@@ -504,10 +522,17 @@ def main():
         _lib.check(lib.ncf_forward(C.byref(cfg), C.byref(tabs), _lib.ptr(flat), _lib.ptr(u), _lib.ptr(it), N, None, None,
                                    None, _lib.ptr(out), _lib.ptr(ws), wsb, sptr))
 
-    def bwd_towers():
-        adam.emb_mode = _lib.EMB_NONE
-        _lib.check(lib.ncf_backward(C.byref(cfg), C.byref(adam), C.byref(tabs), _lib.ptr(flat), _lib.ptr(dgrad), _lib.ptr(u),
-                                    _lib.ptr(it), N, _lib.ptr(gout), _lib.ptr(ws), wsb, sptr))
+    def attn_fwd():
+        _lib.check(lib.ncf_attn_fwd(C.byref(cfg), _lib.ptr(flat), N, _lib.ptr(ws), wsb, sptr))
+
+    def mlp_fwd():
+        _lib.check(lib.ncf_mlp_fwd(C.byref(cfg), _lib.ptr(flat), N, _lib.ptr(out), _lib.ptr(ws), wsb, sptr))
+
+    def mlp_bwd():
+        _lib.check(lib.ncf_mlp_bwd(C.byref(cfg), _lib.ptr(flat), _lib.ptr(dgrad), N, _lib.ptr(gout), _lib.ptr(ws), wsb, sptr))
+
+    def attn_bwd():
+        _lib.check(lib.ncf_attn_bwd(C.byref(cfg), _lib.ptr(flat), _lib.ptr(dgrad), N, _lib.ptr(ws), wsb, sptr))
 
     def k6():
         adam.emb_mode = _lib.EMB_ADAM_SPARSE
@@ -519,36 +544,51 @@ def main():
         adam.emb_mode = _lib.EMB_ADAM_DENSE_EQUIV
         _lib.check(lib.ncf_emb_adam_sweep(C.byref(adam), C.byref(tabs), sptr))
 
+    # Stage calls run in place on the workspace a full forward left behind (include/ncf_b200.h); every stage moves
+    # more bytes per call than the 126 MB L2 holds except K1/K6/sweep at this table size (noted below).
+    fwd()
     k1_ms = time_kernel(k1, 20, sync)
-    fwd_ms = time_kernel(fwd, 10, sync)
-    bwdt_ms = time_kernel(bwd_towers, 10, sync)
+    afwd_ms = time_kernel(attn_fwd, 10, sync)
+    mfwd_ms = time_kernel(mlp_fwd, 10, sync)
+    mbwd_ms = time_kernel(mlp_bwd, 10, sync)
+    abwd_ms = time_kernel(attn_bwd, 10, sync)
     k6_ms = time_kernel(k6, 10, sync)
     sweep_ms = time_kernel(sweep, 10, sync) if table_mode == "fused_dense_equiv" else 0.0
-    tfwd_ms = max(fwd_ms - k1_ms, 1e-6)
+    sus = pk["bf16_tflops_sustained"]
+    hbm = pk["hbm_gbs"]
+
+    def hbm_piece(ms, nbytes, **extra):
+        d = {"ms": ms, "bound": "hbm", "achieved": nbytes / ms / 1e6, "unit": "GB/s", "peak": hbm,
+             "frac": nbytes / ms / 1e6 / hbm, "algorithmic_bytes": nbytes}
+        d.update(extra)
+        return d
+
+    def tensor_piece(ms, flop_per_row, bytes_per_row):
+        # SURVEY 8d counts the towers against the tensor pipe; their arithmetic intensity (flop / byte of
+        # activations a fused kernel has to move) is far below the bf16 ridge, so the HBM view is given as well
+        tf = N * flop_per_row / ms / 1e9
+        gb = N * bytes_per_row / ms / 1e6
+        return {"ms": ms, "bound": "tensor", "achieved": tf, "unit": "TFLOP/s", "peak": sus, "frac": tf / sus,
+                "algorithmic_flop": N * flop_per_row, "hbm_view": {"algorithmic_bytes": N * bytes_per_row, "achieved": gb,
+                                                                   "unit": "GB/s", "peak": hbm, "frac": gb / hbm,
+                                                                   "flop_per_byte": flop_per_row / bytes_per_row}}
+
     k1_bytes = B * BYTES_FWD_PER_INTERACTION
     k6_bytes = B * BYTES_BWD_PER_INTERACTION
     sweep_bytes = 2 * (users + items) * 1536
-    sus = pk["bf16_tflops_sustained"]
+    tcp = precision == "bf16"
     kernels = {
-        "K1 gather_ln_gmf_fwd": {"ms": k1_ms, "bound": "hbm", "achieved": k1_bytes / k1_ms / 1e6, "unit": "GB/s",
-                                 "peak": pk["hbm_gbs"], "frac": k1_bytes / k1_ms / 1e6 / pk["hbm_gbs"],
-                                 "algorithmic_bytes": k1_bytes},
-        "K6 emb_bwd_adam_both (1 sort + segment-sum + apply, both sides)": {
-            "ms": k6_ms, "bound": "hbm", "achieved": k6_bytes / k6_ms / 1e6, "unit": "GB/s", "peak": pk["hbm_gbs"],
-            "frac": k6_bytes / k6_ms / 1e6 / pk["hbm_gbs"], "algorithmic_bytes": k6_bytes},
-        "towers forward (ncf_forward - K1)": {
-            "ms": tfwd_ms, "bound": "tensor", "achieved": N * FLOP_FWD_PER_ROW / tfwd_ms / 1e9, "unit": "TFLOP/s", "peak": sus,
-            "frac": N * FLOP_FWD_PER_ROW / tfwd_ms / 1e9 / sus},
-        "towers backward (ncf_backward, emb_mode none)": {
-            "ms": bwdt_ms, "bound": "tensor", "achieved": N * (FLOP_TRAIN_PER_ROW - FLOP_FWD_PER_ROW) / bwdt_ms / 1e9,
-            "unit": "TFLOP/s", "peak": sus, "frac": N * (FLOP_TRAIN_PER_ROW - FLOP_FWD_PER_ROW) / bwdt_ms / 1e9 / sus},
+        "K1 gather_ln_gmf_fwd": hbm_piece(k1_ms, k1_bytes),
+        "attention forward" + (" (attn_tc_fwd_kernel)" if tcp else " (fp32 kernels)"): tensor_piece(afwd_ms, FLOP_ATTN_FWD, BYTES_ATTN_FWD),
+        "MLP forward" + (" (mlp_tc_fwd_kernel)" if tcp else " (fp32 kernels)"): tensor_piece(mfwd_ms, FLOP_MLP_FWD, BYTES_MLP_FWD),
+        "MLP backward" + (" (head_bwd + mlp_tc_bwd + mlp_tc_wgrad kernels)" if tcp else " (fp32 kernels)"):
+            tensor_piece(mbwd_ms, 2 * FLOP_MLP_FWD, BYTES_MLP_BWD),
+        "attention backward" + (" (attn_tc_bwd_kernel)" if tcp else " (fp32 kernels)"): tensor_piece(abwd_ms, 3 * FLOP_ATTN_FWD, BYTES_ATTN_BWD),
+        "K6 emb_bwd_adam_both (1 sort + segment-sum + apply, both sides)": hbm_piece(k6_ms, k6_bytes),
     }
     if sweep_ms:
-        kernels["dense-equivalent Adam sweep"] = {"ms": sweep_ms, "bound": "hbm", "achieved": sweep_bytes / sweep_ms / 1e6,
-                                                 "unit": "GB/s", "peak": pk["hbm_gbs"],
-                                                 "frac": sweep_bytes / sweep_ms / 1e6 / pk["hbm_gbs"],
-                                                 "algorithmic_bytes": sweep_bytes,
-                                                 "note": "tables that fit the 126 MB L2 read above the HBM copy peak"}
+        kernels["dense-equivalent Adam sweep"] = hbm_piece(sweep_ms, sweep_bytes,
+                                                           note="tables that fit the 126 MB L2 read above the HBM copy peak")
     top = max(kernels, key=lambda k: kernels[k]["ms"])
     kt = kernels[top]
     traffic = None
@@ -556,12 +596,17 @@ def main():
     if os.path.exists(tpath):
         with open(tpath) as f:
             traffic = json.load(f).get(args.workload, {}).get(top)
+    emb_ms, emb_bytes = k1_ms + k6_ms, k1_bytes + k6_bytes
+    pieces_ms = k1_ms + afwd_ms + mfwd_ms + mbwd_ms + abwd_ms + k6_ms + sweep_ms
+    step_bytes = N * (BYTES_ATTN_FWD + BYTES_MLP_FWD + BYTES_MLP_BWD + BYTES_ATTN_BWD) + emb_bytes + (sweep_bytes if sweep_ms else 0)
     roofline = {"kernel": top, "bound": kt["bound"], "achieved": kt["achieved"], "peak": kt["peak"], "unit": kt["unit"],
                 "frac": kt["frac"], "traffic": traffic,
                 "peak_source": pk["source"] + (" (sustained bf16)" if kt["bound"] == "tensor" else " (copy)"),
-                "embedding_path": {"ms": k1_ms + k6_ms, "achieved": (k1_bytes + k6_bytes) / (k1_ms + k6_ms) / 1e6,
-                                   "unit": "GB/s", "frac": (k1_bytes + k6_bytes) / (k1_ms + k6_ms) / 1e6 / pk["hbm_gbs"]},
-                "pieces_sum_ms": k1_ms + tfwd_ms + bwdt_ms + k6_ms + sweep_ms, "kernels": kernels}
+                "embedding_path": {"ms": emb_ms, "achieved": emb_bytes / emb_ms / 1e6, "unit": "GB/s",
+                                   "frac": emb_bytes / emb_ms / 1e6 / hbm},
+                "whole_step_hbm_view": {"algorithmic_bytes": step_bytes, "ms": ms_step, "achieved": step_bytes / ms_step / 1e6,
+                                        "unit": "GB/s", "frac": step_bytes / ms_step / 1e6 / hbm},
+                "pieces_sum_ms": pieces_ms, "kernels": kernels}
 
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:

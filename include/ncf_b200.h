@@ -138,6 +138,23 @@ NCF_API int ncf_backward(const ncf_run_cfg* cfg, const ncf_adam_cfg* adam, const
                  const int64_t* user_ids, const int64_t* item_ids, int64_t N,
                  const float* grad_out, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* The four stages of the dense towers on their own, operating IN PLACE on the workspace of a
+ * training- or eval-mode ncf_forward (same N, cfg, workspace): what ncf_forward / ncf_backward run
+ * after K1 / before K6.  They exist for profiling and unit tests (bench.py times each against its
+ * roofline); a caller that wants the model output uses ncf_forward.
+ *   ncf_attn_fwd  MultiHeadAttention block (architecture.py:18-57, 315-326): xu, xp -> a
+ *   ncf_mlp_fwd   self.mlp + mlp_output + final (architecture.py:230-252, 329-354): a, mf_pred -> out
+ *   ncf_mlp_bwd   backward of the head and the MLP: grad_out -> d mf_pred, da (+ parameter gradients)
+ *   ncf_attn_bwd  backward of the attention block: da -> dxu, dxp (+ parameter gradients) */
+NCF_API int ncf_attn_fwd(const ncf_run_cfg* cfg, const float* dense, int64_t N,
+                 void* workspace, int64_t workspace_bytes, void* stream);
+NCF_API int ncf_mlp_fwd(const ncf_run_cfg* cfg, const float* dense, int64_t N, float* out,
+                void* workspace, int64_t workspace_bytes, void* stream);
+NCF_API int ncf_mlp_bwd(const ncf_run_cfg* cfg, const float* dense, float* dense_grad, int64_t N,
+                const float* grad_out, void* workspace, int64_t workspace_bytes, void* stream);
+NCF_API int ncf_attn_bwd(const ncf_run_cfg* cfg, const float* dense, float* dense_grad, int64_t N,
+                 void* workspace, int64_t workspace_bytes, void* stream);
+
 /* nn.BCELoss() mean reduction with torch's log clamp at -100 (trainer.py:78, 271) and its
  * gradient: loss_out[0] = mean loss, grad_out[n] = dL/d out[n]. */
 NCF_API int ncf_bce_loss(const float* out, const float* targets, int64_t N, float* loss_out,

@@ -85,6 +85,45 @@ extern "C" int ncf_backward(const ncf_run_cfg* cfg, const ncf_adam_cfg* adam, co
   return NCF_OK;
 }
 
+// stage entry points on the workspace of an earlier ncf_forward (profiling / unit tests)
+static int stage_ws(const ncf_run_cfg* cfg, const float* dense, int64_t N, void* workspace, int64_t workspace_bytes, TowerWs* w) {
+  NCF_TRY(check_cfg(cfg, N));
+  NCF_REQUIRE(dense && workspace && N > 0, "stage call: null argument or empty batch");
+  *w = carve_tower_ws(workspace, N, *cfg);
+  if (workspace_bytes < w->total) {
+    set_error("stage call: workspace %lld < %lld bytes", (long long)workspace_bytes, (long long)w->total);
+    return NCF_ERR_WORKSPACE;
+  }
+  return NCF_OK;
+}
+extern "C" int ncf_attn_fwd(const ncf_run_cfg* cfg, const float* dense, int64_t N, void* workspace, int64_t workspace_bytes,
+                            void* stream) {
+  TowerWs w;
+  NCF_TRY(stage_ws(cfg, dense, N, workspace, workspace_bytes, &w));
+  return tower_attn_forward(*cfg, dense, N, w, (cudaStream_t)stream);
+}
+extern "C" int ncf_mlp_fwd(const ncf_run_cfg* cfg, const float* dense, int64_t N, float* out, void* workspace,
+                           int64_t workspace_bytes, void* stream) {
+  TowerWs w;
+  NCF_TRY(stage_ws(cfg, dense, N, workspace, workspace_bytes, &w));
+  NCF_REQUIRE(out, "mlp_fwd: null out");
+  return tower_mlp_forward(*cfg, dense, N, nullptr, nullptr, out, w, (cudaStream_t)stream);
+}
+extern "C" int ncf_mlp_bwd(const ncf_run_cfg* cfg, const float* dense, float* dense_grad, int64_t N, const float* grad_out,
+                           void* workspace, int64_t workspace_bytes, void* stream) {
+  TowerWs w;
+  NCF_TRY(stage_ws(cfg, dense, N, workspace, workspace_bytes, &w));
+  NCF_REQUIRE(dense_grad && grad_out, "mlp_bwd: null argument");
+  return tower_mlp_backward(*cfg, dense, dense_grad, N, grad_out, w, (cudaStream_t)stream);
+}
+extern "C" int ncf_attn_bwd(const ncf_run_cfg* cfg, const float* dense, float* dense_grad, int64_t N, void* workspace,
+                            int64_t workspace_bytes, void* stream) {
+  TowerWs w;
+  NCF_TRY(stage_ws(cfg, dense, N, workspace, workspace_bytes, &w));
+  NCF_REQUIRE(dense_grad, "attn_bwd: null argument");
+  return tower_attn_backward(*cfg, dense, dense_grad, N, w, (cudaStream_t)stream);
+}
+
 extern "C" int ncf_bce_loss(const float* out, const float* targets, int64_t N, float* loss_out, float* grad_out,
                             void* stream) {
   NCF_REQUIRE(out && targets && loss_out && N >= 0, "bce_loss: bad argument");

@@ -14,7 +14,7 @@ struct TowerWs {
   float *q, *kv, *ctx, *a;                 // [N,64] [N,128] [N,64] [N,64]
   float *r1, *y1, *r2, *y2, *r3, *y3;      // relu outputs / layer outputs of the 3 MLP layers
   // backward scratch (training only)
-  float *d_mf;                             // [N]
+  float *d_mf, *d_mlp;                     // [N] dL/d mf_pred, dL/d mlp_pred
   float *g64a, *g64b, *g128, *g128b, *g256, *g256b;
   float *dxu, *dxp;                        // aliases set by the backward
   // bf16 tensors of the tcgen05 path (NCF_BF16_TC): saved activations and pre-activation gradients
@@ -33,6 +33,13 @@ int tower_f32_forward(const ncf_run_cfg& cfg, const float* dense, int64_t N, con
                       float* out, TowerWs& w, cudaStream_t st);
 int tower_f32_backward(const ncf_run_cfg& cfg, const float* dense, float* dense_grad, int64_t N, const float* grad_out,
                        TowerWs& w, cudaStream_t st);
+// the two halves of each direction (also exported one by one: ncf_attn_fwd / ncf_mlp_fwd / ncf_mlp_bwd / ncf_attn_bwd)
+int tower_attn_forward(const ncf_run_cfg& cfg, const float* dense, int64_t N, TowerWs& w, cudaStream_t st);
+int tower_mlp_forward(const ncf_run_cfg& cfg, const float* dense, int64_t N, const int64_t* hour, const float* tail1,
+                      float* out, TowerWs& w, cudaStream_t st);
+int tower_mlp_backward(const ncf_run_cfg& cfg, const float* dense, float* dense_grad, int64_t N, const float* grad_out,
+                       TowerWs& w, cudaStream_t st);
+int tower_attn_backward(const ncf_run_cfg& cfg, const float* dense, float* dense_grad, int64_t N, TowerWs& w, cudaStream_t st);
 // tcgen05 MLP tower (ncf_tower_tc.cu): forward from w.a (fills w.y3, w.mlp_pred, w.p_saved, out)
 int mlp_tc_forward(const ncf_run_cfg& cfg, const float* dense, int64_t N, const int64_t* hour, const float* tail1,
                    float* out, TowerWs& w, cudaStream_t st);

@@ -579,7 +579,8 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
                                                        const float* __restrict__ mf_pred, const float* __restrict__ mlp_pred,
                                                        const float* __restrict__ h3, const float* __restrict__ dense,
                                                        float* __restrict__ d_mf_pred, float* __restrict__ dh3,
-                                                       float* __restrict__ dense_grad, int64_t N) {
+                                                       float* __restrict__ d_mlp_pred, float* __restrict__ dense_grad,
+                                                       int64_t N) {
   __shared__ float s_w[8][H3];
   __shared__ float s_sc[8][5];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, l16 = lane & 15, half = lane >> 4;
@@ -596,9 +597,10 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
     const float dmf = dz * a, dml = dz * c;
     const float4 h = ldg4(h3 + n * H3 + 4 * l16);
     dw = f4_fma(dml, h, dw);
-    st4(dh3 + n * H3 + 4 * l16, make_float4(dml * w.x, dml * w.y, dml * w.z, dml * w.w));
+    if (dh3) st4(dh3 + n * H3 + 4 * l16, make_float4(dml * w.x, dml * w.y, dml * w.z, dml * w.w));
     if (l16 == 0) {
       d_mf_pred[n] = dmf;
+      if (d_mlp_pred) d_mlp_pred[n] = dml;     // the tcgen05 MLP backward forms dh3 = d_mlp_pred * w itself
       s_a = fmaf(dz, mf_pred[n], s_a);
       s_c = fmaf(dz, mlp_pred[n], s_c);
       s_d += dz;
@@ -703,6 +705,7 @@ TowerWs carve_tower_ws(void* ws, int64_t N, const ncf_run_cfg& cfg) {
   if (train) {
     w.y_pmf = c.take<float>(N * D);
     w.d_mf = c.take<float>(N);
+    w.d_mlp = c.take<float>(N);
     w.g64a = c.take<float>(N * D);
     w.g64b = c.take<float>(N * D);
     w.g128 = c.take<float>(N * 2 * D);
@@ -731,6 +734,12 @@ TowerWs carve_tower_ws(void* ws, int64_t N, const ncf_run_cfg& cfg) {
 
 int tower_f32_forward(const ncf_run_cfg& cfg, const float* dense, int64_t N, const int64_t* hour, const float* tail1,
                       float* out, TowerWs& w, cudaStream_t st) {
+  NCF_TRY(tower_attn_forward(cfg, dense, N, w, st));
+  return tower_mlp_forward(cfg, dense, N, hour, tail1, out, w, st);
+}
+
+// attention block: w.xu, w.xp -> w.a (fp32 path) / w.a_img (tcgen05 path)
+int tower_attn_forward(const ncf_run_cfg& cfg, const float* dense, int64_t N, TowerWs& w, cudaStream_t st) {
   const bool train = cfg.training != 0;
   const int S = cfg.S;
   const float* P = dense;
@@ -760,6 +769,14 @@ int tower_f32_forward(const ncf_run_cfg& cfg, const float* dense, int64_t N, con
     if (fused_attn) NCF_TRY(attn_tc_forward(cfg, dense, N, w, st));   // debug mode 2: both paths, fused output wins
   } else
     NCF_TRY((launch_linear<64, false, EPI_NONE>(lin(w.ctx, D, P + NCF_OFF(NCF_P_O_W), D, P + NCF_OFF(NCF_P_O_B), w.a, D, N, D), st)));
+  return NCF_OK;
+}
+
+// MLP tower + output head: w.a / w.a_img (+ w.mf_pred) -> out
+int tower_mlp_forward(const ncf_run_cfg& cfg, const float* dense, int64_t N, const int64_t* hour, const float* tail1,
+                      float* out, TowerWs& w, cudaStream_t st) {
+  const bool train = cfg.training != 0;
+  const float* P = dense;
   if (cfg.precision == NCF_BF16_TC) return mlp_tc_forward(cfg, dense, N, hour, tail1, out, w, st);
   // MLP: the 32 temporal input columns are zeros in forward (architecture.py:329-340), so only the
   // first 64 columns of mlp.0.weight take part; forward_simple's hour path adds tail1[hour].
@@ -780,15 +797,23 @@ int tower_f32_forward(const ncf_run_cfg& cfg, const float* dense, int64_t N, con
   return NCF_OK;
 }
 
-// produces w.d_mf [N], dxu = w.g64a, dxp = w.g64b and accumulates every dense gradient
+// produces w.d_mf [N], dxu = w.g64b, dxp = w.g256 and accumulates every dense gradient
 int tower_f32_backward(const ncf_run_cfg& cfg, const float* dense, float* dg, int64_t N, const float* grad_out,
                        TowerWs& w, cudaStream_t st) {
-  const int S = cfg.S;
+  NCF_TRY(tower_mlp_backward(cfg, dense, dg, N, grad_out, w, st));
+  return tower_attn_backward(cfg, dense, dg, N, w, st);
+}
+
+// head + MLP tower: grad_out -> w.d_mf, da (w.g64a) + their parameter gradients
+int tower_mlp_backward(const ncf_run_cfg& cfg, const float* dense, float* dg, int64_t N, const float* grad_out,
+                       TowerWs& w, cudaStream_t st) {
   const float* P = dense;
   if (!cfg.training) { set_error("backward needs a training-mode forward"); return NCF_ERR_ARG; }
   const int hgrid = (int)std::min<int64_t>((N * 16 + 255) / 256, (int64_t)num_sms() * 8);
   // head: d_mf, dh3 (-> g64a)
-  head_bwd_kernel<<<hgrid, 256, 0, st>>>(grad_out, w.p_saved, w.mf_pred, w.mlp_pred, w.y3, P, w.d_mf, w.g64a, dg, N);
+  const bool tcm = cfg.precision == NCF_BF16_TC;
+  head_bwd_kernel<<<hgrid, 256, 0, st>>>(grad_out, w.p_saved, w.mf_pred, w.mlp_pred, w.y3, P, w.d_mf, tcm ? nullptr : w.g64a,
+                                         tcm ? w.d_mlp : nullptr, dg, N);
   NCF_LAUNCH_CHECK();
   if (cfg.precision == NCF_BF16_TC) {
     NCF_TRY(mlp_tc_backward(cfg, dense, dg, N, w, st));   // dy3 (g64a) -> da (g64a), all MLP parameter gradients
@@ -809,6 +834,14 @@ int tower_f32_backward(const ncf_run_cfg& cfg, const float* dense, float* dg, in
   NCF_TRY(launch_wgrad(w.g256b, H1, H1, w.a, D, D, N, dg + NCF_OFF(NCF_P_MLP0_W), K0, nullptr, st));
   NCF_TRY((launch_linear<64, true, EPI_NONE>(lin(w.g256b, H1, P + NCF_OFF(NCF_P_MLP0_W), K0, nullptr, w.g64a, D, N, H1), st)));
   }
+  return NCF_OK;
+}
+
+// attention block: da (w.g64a) -> dxu (w.g64b), dxp (w.g256) + the projection gradients
+int tower_attn_backward(const ncf_run_cfg& cfg, const float* dense, float* dg, int64_t N, TowerWs& w, cudaStream_t st) {
+  const int S = cfg.S;
+  const float* P = dense;
+  if (!cfg.training) { set_error("backward needs a training-mode forward"); return NCF_ERR_ARG; }
   const bool tc = cfg.precision == NCF_BF16_TC;
   if (tc && S == 5 && attn_fused_mode() == 1) {
     NCF_TRY(attn_tc_backward(cfg, dense, dg, N, w, st));

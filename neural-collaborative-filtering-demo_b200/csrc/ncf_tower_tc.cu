@@ -855,7 +855,8 @@ constexpr uint32_t SMB_TOTAL = SMB_ACC + ACC_COUNT * 4;
 struct MlpBwdArgs {
   const float* dense;
   float* dense_grad;
-  float* dy3_da;                               // in: dy3 [N,64] fp32; out: da [N,64] fp32 (in place)
+  float* da;                                   // out: da [N,64] fp32
+  const float* d_mlp_pred;                     // [N] dL/d mlp_pred from head_bwd_kernel
   const __nv_bfloat16 *r1, *r2, *r3;
   const float *st1, *st2, *st3;                // LayerNorm (mean, rstd) per row from the forward
   __nv_bfloat16 *dz1, *dz2, *dz3;
@@ -920,7 +921,7 @@ __device__ __forceinline__ void load_r_chunk(const uint8_t* __restrict__ r_img, 
 }
 
 template <int C, bool FROM_TMEM>
-__device__ __forceinline__ void mlp_bwd_layer(uint32_t tmem_dy, const float* __restrict__ dy_global, int q, int h, int lane,
+__device__ __forceinline__ void mlp_bwd_layer(uint32_t tmem_dy, float dml, const float* __restrict__ wout, int q, int h, int lane,
                                               int64_t grow, bool live, const uint8_t* __restrict__ r_img,
                                               uint32_t (&rw)[BwdGeom<C>::CW / 2], const float* __restrict__ gam,
                                               float* s_statB, float* s_acc, uint8_t* dztile, uint8_t* __restrict__ dz_img,
@@ -936,13 +937,11 @@ __device__ __forceinline__ void mlp_bwd_layer(uint32_t tmem_dy, const float* __r
     if (FROM_TMEM) {
       tmem_ldw<CW>(taddr + ch * CW, dy);
     } else {
+      // layer 3: dL/dy3 = dL/d mlp_pred * mlp_output.weight (backward of the output head, architecture.py:345);
+      // dml is 0 for rows beyond N
       const int c0 = h * PART + ch * CW;
 #pragma unroll
-      for (int j = 0; j < CW / 4; ++j) {
-        float4 v = make_float4(0, 0, 0, 0);
-        if (live) v = ld4(dy_global + grow * C + c0 + 4 * j);
-        dy[4 * j] = v.x; dy[4 * j + 1] = v.y; dy[4 * j + 2] = v.z; dy[4 * j + 3] = v.w;
-      }
+      for (int i = 0; i < CW; ++i) dy[i] = dml * wout[c0 + i];
     }
   };
 
@@ -1053,7 +1052,10 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_tc_bwd_kernel(MlpBwdArgs A
   for (int i = tid; i < 256; i += MLP_THREADS) {
     par[PAR_G0 + i] = P[NCF_OFF(NCF_P_LN0_W) + i] * sc0;
     if (i < 128) par[PAR_G1 + i] = P[NCF_OFF(NCF_P_LN1_W) + i] * sc1;
-    if (i < 64) par[PAR_G2 + i] = P[NCF_OFF(NCF_P_LN2_W) + i] * sc2;
+    if (i < 64) {
+      par[PAR_G2 + i] = P[NCF_OFF(NCF_P_LN2_W) + i] * sc2;
+      par[PAR_WOUT + i] = P[NCF_OFF(NCF_P_MLP_OUT_W) + i];
+    }
   }
   for (int i = tid; i < ACC_COUNT; i += MLP_THREADS) s_acc[i] = 0.f;
   if (tid == 0) {
@@ -1092,13 +1094,11 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_tc_bwd_kernel(MlpBwdArgs A
         bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(A.r1) + nt * (128 * 256 * 2), 128 * 256 * 2);
         bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(A.r2) + nt * (128 * 128 * 2), 128 * 128 * 2);
         bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(A.r3) + nt * (128 * 64 * 2), 128 * 64 * 2);
-        const int64_t live_next = min((int64_t)TCM_ROWS, A.N - nt * TCM_ROWS);
-        bulk_prefetch_l2(A.dy3_da + nt * TCM_ROWS * D, (uint32_t)(live_next * D * 4));
       }
     }
     load_r_chunk<64>(r3i, rt, h, 0, rw3);
     load_r_chunk<128>(r2i, rt, h, 0, rw2);       // consumed after the first MMA: its latency hides behind layer 3
-    mlp_bwd_layer<64, false>(0, A.dy3_da, q, h, lane, grow, live, r3i, rw3, par + PAR_G2, s_statB, s_acc + ACC_L2, ztile,
+    mlp_bwd_layer<64, false>(0, live ? A.d_mlp_pred[grow] : 0.f, par + PAR_WOUT, q, h, lane, grow, live, r3i, rw3, par + PAR_G2, s_statB, s_acc + ACC_L2, ztile,
                              z3i, A.st3 + tile * 256);
     fence_async_smem();
     fence_before_sync();
@@ -1113,7 +1113,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_tc_bwd_kernel(MlpBwdArgs A
     __syncthreads();
     fence_after_sync();
     load_r_chunk<256>(r1i, rt, h, 0, rw1);       // consumed after the second MMA
-    mlp_bwd_layer<128, true>(tmem + 0, nullptr, q, h, lane, grow, live, r2i, rw2, par + PAR_G1, s_statB, s_acc + ACC_L1,
+    mlp_bwd_layer<128, true>(tmem + 0, 0.f, nullptr, q, h, lane, grow, live, r2i, rw2, par + PAR_G1, s_statB, s_acc + ACC_L1,
                              ztile, z2i, A.st2 + tile * 256);
     fence_async_smem();
     fence_before_sync();
@@ -1127,7 +1127,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_tc_bwd_kernel(MlpBwdArgs A
     phase ^= 1;
     __syncthreads();
     fence_after_sync();
-    mlp_bwd_layer<256, true>(tmem + 128, nullptr, q, h, lane, grow, live, r1i, rw1, par + PAR_G0, s_statB, s_acc + ACC_L0,
+    mlp_bwd_layer<256, true>(tmem + 128, 0.f, nullptr, q, h, lane, grow, live, r1i, rw1, par + PAR_G0, s_statB, s_acc + ACC_L0,
                              ztile, z1i, A.st1 + tile * 256);
     fence_async_smem();
     fence_before_sync();
@@ -1147,7 +1147,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_tc_bwd_kernel(MlpBwdArgs A
       if (live) {
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          st4(A.dy3_da + grow * D + h * 16 + 4 * j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+          st4(A.da + grow * D + h * 16 + 4 * j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
       }
     }
     fence_before_sync();
@@ -1323,7 +1323,8 @@ int mlp_tc_backward(const ncf_run_cfg& cfg, const float* dense, float* dense_gra
   MlpBwdArgs B{};
   B.dense = dense;
   B.dense_grad = dense_grad;
-  B.dy3_da = w.g64a;
+  B.da = w.g64a;
+  B.d_mlp_pred = w.d_mlp;
   B.r1 = (const __nv_bfloat16*)w.r1b;
   B.r2 = (const __nv_bfloat16*)w.r2b;
   B.r3 = (const __nv_bfloat16*)w.r3b;
