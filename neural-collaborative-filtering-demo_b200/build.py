@@ -46,7 +46,8 @@ def build(force=False, verbose=False):
     if failed:
         raise RuntimeError("nvcc compilation failed")
     if force or procs or _stale(LIB, objs):
-        cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
+        cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart",
+                                                      "-Xlinker", "--no-undefined"]
         subprocess.check_call(cmd)
     return LIB
 

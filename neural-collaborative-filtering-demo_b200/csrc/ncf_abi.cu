@@ -59,8 +59,8 @@ extern "C" int ncf_forward(const ncf_run_cfg* cfg, const ncf_tables* T, const fl
     return NCF_ERR_WORKSPACE;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  NCF_TRY(ncf_gather_ln_gmf_fwd(T, dense, user_ids, item_ids, N, hour, tmod, w.mf_pred, w.xu, w.xp,
-                                cfg->training ? w.y_pmf : nullptr, stream));
+  NCF_TRY(gather_ln_gmf_fwd_rows(tower_bf16_rows(*cfg), T, dense, user_ids, item_ids, N, hour, tmod, w.mf_pred, w.xu, w.xp,
+                                 cfg->training ? w.y_pmf : nullptr, stream));
   return tower_f32_forward(*cfg, dense, N, hour, tail1, out, w, st);
 }
 

@@ -70,6 +70,28 @@ __device__ __forceinline__ float dot16(const float (&a)[16], const float (&b)[16
   return s0 + s1;
 }
 
+// bf16 rows [N,64] -> operand tile with LAYOUT columns per row group: plain 16-byte copies (the four quarters of
+// a warp read four adjacent 16-byte pieces of the same 8 rows; each quarter writes one 128-byte core matrix).
+// ONES adds the [1 | 0...] chunk at column 64 (bias gradient through the GEMM).
+template <int LAYOUT, bool ONES>
+__device__ __forceinline__ void attn_fill_rows(uint8_t* tile, const __nv_bfloat16* __restrict__ src, int64_t row0, int64_t avail,
+                                               int tid) {
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int c = tid + k * AT_THREADS;
+    const int blk = c >> 5, l = c & 31;
+    const int r = (blk >> 1) * 8 + (l & 7), j = (blk & 1) * 4 + (l >> 3);
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (r < avail) v = __ldg(reinterpret_cast<const uint4*>(src + (row0 + r) * 64 + 8 * j));
+    *reinterpret_cast<uint4*>(tile + tile_off(r, 8 * j, LAYOUT)) = v;
+  }
+  if (ONES && tid < 128) {
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (tid < avail) v.x = 0x00003f80u;     // bf16(1.0): column 64 = 1, columns 65..71 = 0
+    *reinterpret_cast<uint4*>(tile + tile_off(tid, 64, LAYOUT)) = v;
+  }
+}
+
 // =============================================================================================
 // forward
 // =============================================================================================
@@ -84,7 +106,7 @@ constexpr uint32_t AF_BIAS = AF_VB + 128 * AT_XS * 2;  // bq | bk | bv | bo
 constexpr uint32_t AF_TOTAL = AF_BIAS + 256 * 4;
 
 struct AttnFwdArgs {
-  const float *xu, *xp;     // [N,64] fp32: mlp_norm(user row), mlp_norm(item row)
+  const __nv_bfloat16 *xu, *xp;     // [N,64] bf16 rows: mlp_norm(user row), mlp_norm(item row)
   const float* dense;
   void* a_img;              // out: bf16 tile image [ceil(N/128)][128 x 64]
   int64_t N;
@@ -139,12 +161,12 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_fwd_kernel(AttnFwdArgs 
       const int64_t nn0 = (tile + gridDim.x) * AT_RT;
       const int64_t nav = min((int64_t)AT_RT, A.N - nn0);
       if (nav > 0) {
-        bulk_prefetch_l2(A.xu + nn0 * 64, (uint32_t)(nav * 256));
-        bulk_prefetch_l2(A.xp + nn0 * 64, (uint32_t)(nav * 256));
+        bulk_prefetch_l2(A.xu + nn0 * 64, (uint32_t)(nav * 128));
+        bulk_prefetch_l2(A.xp + nn0 * 64, (uint32_t)(nav * 128));
       }
     }
-    fill_tile_f32<64>(smem + AF_XU, A.xu, 64, n0, avail, 128, tid, AT_THREADS);
-    fill_tile_f32<64>(smem + AF_XP, A.xp, 64, n0, avail, 128, tid, AT_THREADS);
+    attn_fill_rows<64, false>(smem + AF_XU, A.xu, n0, avail, tid);
+    attn_fill_rows<64, false>(smem + AF_XP, A.xp, n0, avail, tid);
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
@@ -267,8 +289,8 @@ constexpr uint32_t AB_TOTAL = AB_BIAS + 256 * 4;
 constexpr int AB_ACC = 3 * AT_CXL * 128;                     // weight-gradient accumulator words per CTA
 
 struct AttnBwdArgs {
-  const float *xu, *xp;     // [N,64]
-  const float* da;          // [N,64] gradient wrt the block output
+  const __nv_bfloat16 *xu, *xp;     // [N,64] bf16 rows
+  const __nv_bfloat16* da;          // [N,64] bf16 rows: gradient wrt the block output
   const float* dense;
   float *dxu, *dxp;         // [N,64] out
   float* partial;           // [grid][AB_ACC] per-CTA weight-gradient sums
@@ -276,30 +298,25 @@ struct AttnBwdArgs {
   DropoutRng rng;
 };
 
-// Register-staged [128 x 64] fp32 rows: the global loads of the NEXT tile are issued while the tensor core works
-// on the current one; the bf16 conversion and the shared-memory stores happen when the tile buffer is free.
-// Each thread owns 2 chunks of 8 columns (the four quarters of a warp read four adjacent 32-byte pieces of the
-// same 8 rows; each quarter writes one 128-byte core matrix).
+// Register-staged [128 x 64] bf16 rows: the global loads of the NEXT tile are issued while the tensor core works
+// on the current one; the shared-memory stores happen when the tile buffer is free.  Each thread owns 2 chunks of
+// 8 columns (same mapping as attn_fill_rows).
 struct AttnStage {
-  float4 a[2], b[2];
+  uint4 v[2];
   __device__ __forceinline__ static void rc(int c, int& r, int& j) {
     const int blk = c >> 5, l = c & 31;
     r = (blk >> 1) * 8 + (l & 7);
     j = (blk & 1) * 4 + (l >> 3);
   }
-  __device__ __forceinline__ void load(const float* __restrict__ src, int64_t row0, int64_t avail, int tid) {
+  __device__ __forceinline__ void load(const __nv_bfloat16* __restrict__ src, int64_t row0, int64_t avail, int tid) {
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
       int r, j;
       rc(tid + k * AT_THREADS, r, j);
-      a[k] = make_float4(0, 0, 0, 0);
-      b[k] = a[k];
+      v[k] = make_uint4(0, 0, 0, 0);
       if (r < avail) {
-        const float* p = src + (row0 + r) * 64 + 8 * j;
-        asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
-                     : "=f"(a[k].x), "=f"(a[k].y), "=f"(a[k].z), "=f"(a[k].w) : "l"(p));
-        asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
-                     : "=f"(b[k].x), "=f"(b[k].y), "=f"(b[k].z), "=f"(b[k].w) : "l"(p + 4));
+        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(v[k].x), "=r"(v[k].y), "=r"(v[k].z), "=r"(v[k].w) : "l"(src + (row0 + r) * 64 + 8 * j));
       }
     }
   }
@@ -310,13 +327,12 @@ struct AttnStage {
     for (int k = 0; k < 2; ++k) {
       int r, j;
       rc(tid + k * AT_THREADS, r, j);
-      *reinterpret_cast<uint4*>(tile + tile_off(r, 8 * j, LAYOUT)) =
-          make_uint4(pack_bf16(a[k].x, a[k].y), pack_bf16(a[k].z, a[k].w), pack_bf16(b[k].x, b[k].y), pack_bf16(b[k].z, b[k].w));
+      *reinterpret_cast<uint4*>(tile + tile_off(r, 8 * j, LAYOUT)) = v[k];
     }
     if (ONES && tid < 128) {
-      uint4 v = make_uint4(0, 0, 0, 0);
-      if (tid < avail) v.x = 0x00003f80u;     // bf16(1.0): column 64 = 1, columns 65..71 = 0
-      *reinterpret_cast<uint4*>(tile + tile_off(tid, 64, LAYOUT)) = v;
+      uint4 o = make_uint4(0, 0, 0, 0);
+      if (tid < avail) o.x = 0x00003f80u;     // bf16(1.0): column 64 = 1, columns 65..71 = 0
+      *reinterpret_cast<uint4*>(tile + tile_off(tid, 64, LAYOUT)) = o;
     }
   }
 };
@@ -368,9 +384,9 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_bwd_kernel(AttnBwdArgs 
     const bool live = row < avail;
     const int64_t nn0 = (tile + gridDim.x) * AT_RT, nav = max((int64_t)0, min((int64_t)AT_RT, A.N - nn0));
     if (tid == 0 && nav > 0) {      // the register prefetch below then finds the next tile in L2
-      bulk_prefetch_l2(A.xu + nn0 * 64, (uint32_t)(nav * 256));
-      bulk_prefetch_l2(A.xp + nn0 * 64, (uint32_t)(nav * 256));
-      bulk_prefetch_l2(A.da + nn0 * 64, (uint32_t)(nav * 256));
+      bulk_prefetch_l2(A.xu + nn0 * 64, (uint32_t)(nav * 128));
+      bulk_prefetch_l2(A.xp + nn0 * 64, (uint32_t)(nav * 128));
+      bulk_prefetch_l2(A.da + nn0 * 64, (uint32_t)(nav * 128));
     }
     su.store<AT_CXL, true>(smem + AB_XU, avail, tid);
     sp.store<AT_CXL, true>(smem + AB_XP, avail, tid);
@@ -603,8 +619,8 @@ int attn_tc_forward(const ncf_run_cfg& cfg, const float* dense, int64_t N, Tower
     configured = true;
   }
   AttnFwdArgs A{};
-  A.xu = w.xu;
-  A.xp = w.xp;
+  A.xu = reinterpret_cast<const __nv_bfloat16*>(w.xu);      // bf16 rows (tower_bf16_rows)
+  A.xp = reinterpret_cast<const __nv_bfloat16*>(w.xp);
   A.dense = dense;
   A.a_img = w.a_img;
   A.N = N;
@@ -624,9 +640,9 @@ int attn_tc_backward(const ncf_run_cfg& cfg, const float* dense, float* dense_gr
     configured = true;
   }
   AttnBwdArgs A{};
-  A.xu = w.xu;
-  A.xp = w.xp;
-  A.da = w.g64a;
+  A.xu = reinterpret_cast<const __nv_bfloat16*>(w.xu);      // bf16 rows (tower_bf16_rows)
+  A.xp = reinterpret_cast<const __nv_bfloat16*>(w.xp);
+  A.da = reinterpret_cast<const __nv_bfloat16*>(w.g64a);
   A.dense = dense;
   A.dxu = w.g64b;
   A.dxp = w.g256;

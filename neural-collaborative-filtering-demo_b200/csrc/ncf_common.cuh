@@ -1,5 +1,6 @@
 // Shared device/host helpers for libncf_b200.so (sm_100a only).
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -117,6 +118,16 @@ __device__ __forceinline__ float half_warp_sum(float v) {
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+// 4 consecutive values of a [N,64] row: fp32 (16 B) or, for the tcgen05 attention block, bf16 (8 B)
+__device__ __forceinline__ void st_row4(float* base, int64_t n, int c, float4 v, bool bf16_rows) {
+  if (bf16_rows) {
+    const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+    *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(base) + n * 64 + c) =
+        make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+  } else {
+    *reinterpret_cast<float4*>(base + n * 64 + c) = v;
+  }
+}
 __device__ __forceinline__ float4 f4_fma(float a, float4 x, float4 y) {
   return make_float4(fmaf(a, x.x, y.x), fmaf(a, x.y, y.y), fmaf(a, x.z, y.z), fmaf(a, x.w, y.w));
 }

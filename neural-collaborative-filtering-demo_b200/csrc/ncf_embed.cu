@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(K1_THREADS) gather_ln_gmf_fwd_kernel(
     const float* __restrict__ t_pmlp, const float* __restrict__ dense, const int64_t* __restrict__ user_ids,
     const int64_t* __restrict__ item_ids, int64_t N, const int64_t* __restrict__ hour,
     const float* __restrict__ tmod, float* __restrict__ mf_pred, float* __restrict__ xu, float* __restrict__ xp,
-    float* __restrict__ y_item_mf) {
+    float* __restrict__ y_item_mf, bool bf16_rows) {
   __shared__ __align__(16) int64_t s_ids[2][2][K1_TILE];
   __shared__ __align__(8) uint64_t s_bar[2];
 
@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(K1_THREADS) gather_ln_gmf_fwd_kernel(
         if (r < rows) {
           const int64_t n = n0 + r;
           if (lane == 0) mf_pred[n] = dot + b_out;
-          st4((half ? xp : xu) + n * D + 4 * l16, y_ml);
+          st_row4(half ? xp : xu, n, 4 * l16, y_ml, bf16_rows);
           if (y_item_mf && half) st4(y_item_mf + n * D + 4 * l16, y_mf);   // kept for the backward
         }
       }
@@ -573,7 +573,9 @@ __global__ void dropout_mask_kernel(DropoutRng rng, int64_t numel, uint8_t* __re
 using namespace ncf;
 
 // ---- host entry points ------------------------------------------------------------------------
-extern "C" int ncf_gather_ln_gmf_fwd(const ncf_tables* T, const float* dense, const int64_t* user_ids,
+// xu / xp rows as fp32 (the C-ABI contract) or bf16 (internal: input of the tcgen05 attention block)
+namespace ncf {
+int gather_ln_gmf_fwd_rows(bool bf16_rows, const ncf_tables* T, const float* dense, const int64_t* user_ids,
                                      const int64_t* item_ids, int64_t N, const int64_t* hour, const float* tmod,
                                      float* mf_pred, float* xu, float* xp, float* y_item_mf, void* stream) {
   NCF_REQUIRE(T && dense && user_ids && item_ids && mf_pred && xu && xp, "gather_ln_gmf_fwd: null argument");
@@ -585,12 +587,19 @@ extern "C" int ncf_gather_ln_gmf_fwd(const ncf_tables* T, const float* dense, co
   cudaStream_t st = (cudaStream_t)stream;
   if (hour)
     gather_ln_gmf_fwd_kernel<true><<<grid, K1_THREADS, 0, st>>>(T->w[0], T->w[1], T->w[2], T->w[3], dense, user_ids,
-                                                                item_ids, N, hour, tmod, mf_pred, xu, xp, y_item_mf);
+                                                                item_ids, N, hour, tmod, mf_pred, xu, xp, y_item_mf, bf16_rows);
   else
     gather_ln_gmf_fwd_kernel<false><<<grid, K1_THREADS, 0, st>>>(T->w[0], T->w[1], T->w[2], T->w[3], dense, user_ids,
-                                                                 item_ids, N, nullptr, nullptr, mf_pred, xu, xp, y_item_mf);
+                                                                 item_ids, N, nullptr, nullptr, mf_pred, xu, xp, y_item_mf, bf16_rows);
   NCF_LAUNCH_CHECK();
   return NCF_OK;
+}
+}  // namespace ncf
+
+extern "C" int ncf_gather_ln_gmf_fwd(const ncf_tables* T, const float* dense, const int64_t* user_ids,
+                                     const int64_t* item_ids, int64_t N, const int64_t* hour, const float* tmod,
+                                     float* mf_pred, float* xu, float* xp, float* y_item_mf, void* stream) {
+  return gather_ln_gmf_fwd_rows(false, T, dense, user_ids, item_ids, N, hour, tmod, mf_pred, xu, xp, y_item_mf, stream);
 }
 
 extern "C" int ncf_gather_ln(const ncf_tables* T, const float* dense, int32_t side, const int64_t* ids, int64_t n,

@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(256) gmf_from_rows_kernel(const float* __restr
                                                             const int64_t* __restrict__ pos_u, const int64_t* __restrict__ pos_i,
                                                             const float* __restrict__ dense, int64_t N,
                                                             float* __restrict__ mf_pred, float* __restrict__ xu,
-                                                            float* __restrict__ xp) {
+                                                            float* __restrict__ xp, bool bf16_rows) {
   const int lane = threadIdx.x & 31, half = lane >> 4, l16 = lane & 15;
   const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(256) gmf_from_rows_kernel(const float* __restr
                                      __shfl_xor_sync(0xffffffffu, y_mf.z, 16), __shfl_xor_sync(0xffffffffu, y_mf.w, 16));
     const float dot = half_warp_sum(f4_dot(f4_mul(y_mf, other), w_out));
     if (lane == 0) mf_pred[n] = dot + b_out;
-    st4((half ? xp : xu) + n * D + 4 * l16, y_ml);
+    st_row4(half ? xp : xu, n, 4 * l16, y_ml, bf16_rows);
   }
 }
 
@@ -132,7 +132,7 @@ extern "C" int ncf_shard_forward(const ncf_run_cfg* cfg, const float* dense, con
   }
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = (int)std::min<int64_t>((N + 7) / 8, (int64_t)num_sms() * 8);
-  gmf_from_rows_kernel<<<grid, 256, 0, st>>>(rows_u, rows_i, pos_u, pos_i, dense, N, w.mf_pred, w.xu, w.xp);
+  gmf_from_rows_kernel<<<grid, 256, 0, st>>>(rows_u, rows_i, pos_u, pos_i, dense, N, w.mf_pred, w.xu, w.xp, tower_bf16_rows(*cfg));
   NCF_LAUNCH_CHECK();
   return tower_f32_forward(*cfg, dense, N, nullptr, nullptr, out, w, st);
 }

@@ -33,6 +33,14 @@ int tower_f32_forward(const ncf_run_cfg& cfg, const float* dense, int64_t N, con
                       float* out, TowerWs& w, cudaStream_t st);
 int tower_f32_backward(const ncf_run_cfg& cfg, const float* dense, float* dense_grad, int64_t N, const float* grad_out,
                        TowerWs& w, cudaStream_t st);
+// True when the attention block runs as the fused tcgen05 kernels (bf16 towers, S = 5): then its row-vector
+// interfaces w.xu, w.xp (from K1 / the sharded requester) and da = w.g64a (from the MLP backward) hold bf16
+// [N,64] rows instead of fp32 - the same values the operand tiles would be rounded to anyway, half the traffic.
+bool tower_bf16_rows(const ncf_run_cfg& cfg);
+// K1 with selectable row format (ncf_embed.cu); the C-ABI export ncf_gather_ln_gmf_fwd is the fp32 case
+int gather_ln_gmf_fwd_rows(bool bf16_rows, const ncf_tables* T, const float* dense, const int64_t* user_ids,
+                           const int64_t* item_ids, int64_t N, const int64_t* hour, const float* tmod, float* mf_pred,
+                           float* xu, float* xp, float* y_item_mf, void* stream);
 // the two halves of each direction (also exported one by one: ncf_attn_fwd / ncf_mlp_fwd / ncf_mlp_bwd / ncf_attn_bwd)
 int tower_attn_forward(const ncf_run_cfg& cfg, const float* dense, int64_t N, TowerWs& w, cudaStream_t st);
 int tower_mlp_forward(const ncf_run_cfg& cfg, const float* dense, int64_t N, const int64_t* hour, const float* tail1,

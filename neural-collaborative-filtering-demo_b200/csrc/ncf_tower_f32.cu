@@ -666,8 +666,7 @@ __global__ void __launch_bounds__(256) bce_kernel(const float* __restrict__ out,
 // =============================================================================================
 // orchestration
 // =============================================================================================
-// NCF_ATTN_FUSED: 1 (default) = fused tcgen05 attention block for S = 5; 0 = separate projection / core kernels;
-// 2 = debug: unfused path runs too (keeps q, kv, ctx for the unfused backward), the fused forward output is used
+// NCF_ATTN_FUSED: 1 (default) = fused tcgen05 attention block for S = 5; 0 = separate projection / core kernels
 static int attn_fused_mode() {
   static int mode = -1;
   if (mode < 0) {
@@ -676,6 +675,8 @@ static int attn_fused_mode() {
   }
   return mode;
 }
+bool tower_bf16_rows(const ncf_run_cfg& cfg) { return cfg.precision == NCF_BF16_TC && cfg.S == 5 && attn_fused_mode() == 1; }
+
 TowerWs carve_tower_ws(void* ws, int64_t N, const ncf_run_cfg& cfg) {
   TowerWs w{};
   Carver c(ws);
@@ -744,8 +745,8 @@ int tower_attn_forward(const ncf_run_cfg& cfg, const float* dense, int64_t N, To
   const int S = cfg.S;
   const float* P = dense;
   const bool tc = cfg.precision == NCF_BF16_TC;
-  const bool fused_attn = tc && S == 5 && attn_fused_mode() != 0;
-  if (fused_attn && attn_fused_mode() == 1) {
+  const bool fused_attn = tower_bf16_rows(cfg);
+  if (fused_attn) {
     NCF_TRY(attn_tc_forward(cfg, dense, N, w, st));       // xu, xp -> a_img in one kernel; nothing else is kept
   } else if (train || S > 1) {
     // q = q_proj(xu); [k|v] = [k_proj; v_proj](xp)        (architecture.py:40-42)
@@ -763,10 +764,9 @@ int tower_attn_forward(const ncf_run_cfg& cfg, const float* dense, int64_t N, To
     // one key per query: softmax == 1, ctx = v_proj(xp)      (architecture.py:275-276)
     NCF_TRY((launch_linear<64, false, EPI_NONE>(lin(w.xp, D, P + NCF_OFF(NCF_P_V_W), D, P + NCF_OFF(NCF_P_V_B), w.ctx, D, N, D), st)));
   }
-  if (fused_attn && attn_fused_mode() == 1) {
+  if (fused_attn) {
   } else if (tc) {
     NCF_TRY(tc_proj_forward_img(w.ctx, P + NCF_OFF(NCF_P_O_W), P + NCF_OFF(NCF_P_O_B), w.a_img, N, st));
-    if (fused_attn) NCF_TRY(attn_tc_forward(cfg, dense, N, w, st));   // debug mode 2: both paths, fused output wins
   } else
     NCF_TRY((launch_linear<64, false, EPI_NONE>(lin(w.ctx, D, P + NCF_OFF(NCF_P_O_W), D, P + NCF_OFF(NCF_P_O_B), w.a, D, N, D), st)));
   return NCF_OK;
@@ -843,7 +843,7 @@ int tower_attn_backward(const ncf_run_cfg& cfg, const float* dense, float* dg, i
   const float* P = dense;
   if (!cfg.training) { set_error("backward needs a training-mode forward"); return NCF_ERR_ARG; }
   const bool tc = cfg.precision == NCF_BF16_TC;
-  if (tc && S == 5 && attn_fused_mode() == 1) {
+  if (tower_bf16_rows(cfg)) {
     NCF_TRY(attn_tc_backward(cfg, dense, dg, N, w, st));
     w.dxu = w.g64b;
     w.dxp = w.g256;

@@ -855,7 +855,8 @@ constexpr uint32_t SMB_TOTAL = SMB_ACC + ACC_COUNT * 4;
 struct MlpBwdArgs {
   const float* dense;
   float* dense_grad;
-  float* da;                                   // out: da [N,64] fp32
+  float* da;                                   // out: da [N,64] fp32, or bf16 rows when da_bf16 (fused attention backward)
+  bool da_bf16;
   const float* d_mlp_pred;                     // [N] dL/d mlp_pred from head_bwd_kernel
   const __nv_bfloat16 *r1, *r2, *r3;
   const float *st1, *st2, *st3;                // LayerNorm (mean, rstd) per row from the forward
@@ -1147,7 +1148,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_tc_bwd_kernel(MlpBwdArgs A
       if (live) {
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          st4(A.da + grow * D + h * 16 + 4 * j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+          st_row4(A.da, grow, h * 16 + 4 * j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]), A.da_bf16);
       }
     }
     fence_before_sync();
@@ -1324,6 +1325,7 @@ int mlp_tc_backward(const ncf_run_cfg& cfg, const float* dense, float* dense_gra
   B.dense = dense;
   B.dense_grad = dense_grad;
   B.da = w.g64a;
+  B.da_bf16 = tower_bf16_rows(cfg);
   B.d_mlp_pred = w.d_mlp;
   B.r1 = (const __nv_bfloat16*)w.r1b;
   B.r2 = (const __nv_bfloat16*)w.r2b;

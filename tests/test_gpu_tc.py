@@ -152,3 +152,36 @@ def test_bf16_tc_engine_trains():
     for a, b in zip(losses["fp32"], losses["bf16"]):
         assert abs(a - b) < 5e-3, (losses)
     assert losses["bf16"][-1] < losses["bf16"][0]
+
+
+def test_stage_exports_reproduce_the_forward():
+    """ncf_attn_fwd + ncf_mlp_fwd on the workspace of an ncf_forward give the same probabilities again
+    (the stage entry points bench.py times are the kernels the step runs)."""
+    import ctypes as C
+    import ncf_b200
+    from ncf_b200 import _lib
+    from tests.helpers import golden_params
+    lib = _lib.load()
+    p, _ = golden_params()
+    m = _model(p, 8031, 366, dropout=0.2).train()
+    g = torch.Generator().manual_seed(5)
+    B, S = 333, 5
+    N = B * S
+    u = torch.randint(0, 8031, (B,), generator=g).repeat_interleave(S).cuda()
+    i = torch.randint(0, 366, (N,), generator=g).cuda()
+    cfg = _lib.RunCfg()
+    cfg.S, cfg.training, cfg.dropout_p, cfg.seed, cfg.step, cfg.precision = S, 1, 0.2, 11, 2, _lib.NCF_BF16_TC
+    wsb = int(lib.ncf_workspace_bytes(N, C.byref(cfg)))
+    ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
+    m._ensure_flat()
+    tabs, flat = m._tables_struct(), m._flat
+    out = torch.empty(N, device="cuda")
+    _lib.check(lib.ncf_forward(C.byref(cfg), C.byref(tabs), _lib.ptr(flat), _lib.ptr(u), _lib.ptr(i), N, None, None, None,
+                               _lib.ptr(out), _lib.ptr(ws), wsb, None))
+    ref = out.clone()
+    out.zero_()
+    _lib.check(lib.ncf_attn_fwd(C.byref(cfg), _lib.ptr(flat), N, _lib.ptr(ws), wsb, None))
+    _lib.check(lib.ncf_mlp_fwd(C.byref(cfg), _lib.ptr(flat), N, _lib.ptr(out), _lib.ptr(ws), wsb, None))
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref)
+    assert float(ref.min()) > 0 and float(ref.max()) < 1
