@@ -13,13 +13,14 @@ using namespace umma;
 //   mode 0: D = A[128,K] . B[N,K]^T            (A K-major, B K-major)         forward
 //   mode 1: D = A[128,K] . B[K,N]              (A K-major, B = [K rows, N cols] read MN-major)  dgrad
 //   mode 2: D = A[128r,128]^T . B[128r,N]      (both read MN-major, K = 128 rows)               wgrad
+//   mode 3: as mode 0 with A staged in TENSOR MEMORY (packed bf16 pairs written by tcgen05.st)   MLP forward
 // ---------------------------------------------------------------------------------------------
 template <int MODE, int K, int N>
 __global__ void __launch_bounds__(128) tc_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B,
                                                           float* __restrict__ Dout) {
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int AR = 128, AC = MODE == 2 ? 128 : K;            // A tile rows x cols as stored
-  constexpr int BR = MODE == 0 ? N : (MODE == 1 ? K : 128), BC = MODE == 0 ? K : N;
+  constexpr int BR = (MODE == 0 || MODE == 3) ? N : (MODE == 1 ? K : 128), BC = (MODE == 0 || MODE == 3) ? K : N;
   uint8_t* sA = smem;
   uint8_t* sB = smem + AR * AC * 2;
   __shared__ __align__(8) uint64_t bar;
@@ -38,9 +39,24 @@ __global__ void __launch_bounds__(128) tc_selftest_kernel(const float* __restric
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem = tmem_slot;
+  if (MODE == 3) {      // A operand through tensor memory: thread = row writes its K bf16 values as packed pairs
+    const int row = warp * 32 + lane;
+    for (int c0 = 0; c0 < K; c0 += 32) {
+      uint32_t w[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) w[i] = pack_bf16(A[row * K + c0 + 2 * i], A[row * K + c0 + 2 * i + 1]);
+      tmem_st16u(tmem + 128 + ((uint32_t)(warp * 32) << 16) + c0 / 2, w);
+    }
+    tmem_st_wait();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+  }
   if (tid == 0) {
     const uint32_t a = smem_addr(sA), b = smem_addr(sB);
-    if (MODE == 0) {
+    if (MODE == 3) {
+      issue_gemm_ts(tmem, tmem + 128, b, 128, BC * 16, 256, make_idesc(128, N, false, false), K / 16, false);
+    } else if (MODE == 0) {
       issue_gemm(tmem, a, 128, AC * 16, 256, b, 128, BC * 16, 256, make_idesc(128, N, false, false), K / 16, false);
     } else if (MODE == 1) {
       issue_gemm(tmem, a, 128, AC * 16, 256, b, BC * 16, 128, 2 * BC * 16, make_idesc(128, N, false, true), K / 16, false);
@@ -1364,7 +1380,7 @@ using namespace ncf;
 template <int MODE, int K, int N>
 static int run_selftest(const float* A, const float* B, float* D, cudaStream_t st) {
   constexpr int AC = MODE == 2 ? 128 : K;
-  constexpr int BR = MODE == 0 ? N : (MODE == 1 ? K : 128), BC = MODE == 0 ? K : N;
+  constexpr int BR = (MODE == 0 || MODE == 3) ? N : (MODE == 1 ? K : 128), BC = (MODE == 0 || MODE == 3) ? K : N;
   const int smem = 128 * AC * 2 + BR * BC * 2;
   NCF_CUDA(cudaFuncSetAttribute(tc_selftest_kernel<MODE, K, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   tc_selftest_kernel<MODE, K, N><<<1, 128, smem, st>>>(A, B, D);
@@ -1373,7 +1389,7 @@ static int run_selftest(const float* A, const float* B, float* D, cudaStream_t s
 }
 
 // A, B, D: fp32 device buffers; shapes by mode (see kernel).  (mode, K, N) in {(0,64,256),(0,256,128),
-// (1,64,128),(1,128,256),(2,128,64),(2,128,256)}.
+// (1,64,128),(1,128,256),(2,128,64),(2,128,256),(3,256,128),(3,128,64)}.
 extern "C" int ncf_tc_selftest(int32_t mode, int32_t K, int32_t N, const float* A, const float* B, float* D, void* stream) {
   NCF_REQUIRE(A && B && D, "tc_selftest: null argument");
   cudaStream_t st = (cudaStream_t)stream;
@@ -1383,6 +1399,8 @@ extern "C" int ncf_tc_selftest(int32_t mode, int32_t K, int32_t N, const float* 
   if (mode == 1 && K == 128 && N == 256) return run_selftest<1, 128, 256>(A, B, D, st);
   if (mode == 2 && K == 128 && N == 64) return run_selftest<2, 128, 64>(A, B, D, st);
   if (mode == 2 && K == 128 && N == 256) return run_selftest<2, 128, 256>(A, B, D, st);
+  if (mode == 3 && K == 256 && N == 128) return run_selftest<3, 256, 128>(A, B, D, st);
+  if (mode == 3 && K == 128 && N == 64) return run_selftest<3, 128, 64>(A, B, D, st);
   set_error("tc_selftest: unsupported (mode,K,N) = (%d,%d,%d)", mode, K, N);
   return NCF_ERR_UNSUPPORTED;
 }

@@ -9,12 +9,13 @@ def _bf(x):
     return x.to(torch.bfloat16).float()
 
 
-@pytest.mark.parametrize("mode,K,N", [(0, 64, 256), (0, 256, 128), (1, 64, 128), (1, 128, 256), (2, 128, 64), (2, 128, 256)])
+@pytest.mark.parametrize("mode,K,N", [(0, 64, 256), (0, 256, 128), (1, 64, 128), (1, 128, 256), (2, 128, 64), (2, 128, 256),
+                                      (3, 256, 128), (3, 128, 64)])
 def test_tc_selftest_tile(mode, K, N):
     from ncf_b200 import _lib
     lib = _lib.load()
     g = torch.Generator().manual_seed(mode * 100 + K + N)
-    if mode == 0:
+    if mode in (0, 3):       # 3: the A operand goes through tensor memory
         A, B = torch.randn(128, K, generator=g), torch.randn(N, K, generator=g)
         ref = _bf(A) @ _bf(B).t()
     elif mode == 1:
