@@ -2,6 +2,8 @@
 //   ncf_tc_selftest   one 128-row GEMM tile in the three operand arrangements the towers use
 //                     (forward, input-gradient, weight-gradient); unit-tested against fp32.
 //   mlp_tc_*          the 3-layer MLP tower (architecture.py:230-242) forward / dgrad / wgrad.
+#include <cstdlib>
+
 #include "ncf_tower.cuh"
 #include "ncf_umma.cuh"
 
@@ -134,17 +136,20 @@ __device__ __forceinline__ void load_weight_image(uint8_t* img, const float* __r
 // ReLU outputs stay in registers; a DROPPED element carries its decision in the (otherwise unused) sign bit,
 // and that is also the form the saved r tensor takes, so the backward needs no random numbers.
 // Pass 2: LayerNorm (gamma/beta pre-multiplied by 1/(1-p)), dropout select, bf16 -> next A operand / saved y.
-template <int C, bool LAST, bool HAS_TAIL>
+template <int C, bool LAST, bool HAS_TAIL, bool Y_TMEM = false>
 __device__ __forceinline__ void mlp_epilogue(uint32_t tmem_acc, int q, int h, int lane, int64_t grow, bool live,
                                              const float* __restrict__ par_b, const float* __restrict__ par_g,
                                              const float* __restrict__ par_e, const float* __restrict__ tail_row,
                                              const DropoutRng& rng, float* s_stat, uint8_t* ytile,
                                              uint8_t* __restrict__ r_img, uint8_t* __restrict__ y_img,
                                              float* __restrict__ y3_out, const float* __restrict__ par_wout,
-                                             float& head_partial, float* __restrict__ st_tile) {
+                                             float& head_partial, float* __restrict__ st_tile, uint32_t tmem_y = 0) {
   constexpr int PART = C / MLP_NH, CW = PART >= 32 ? 32 : 16, NCH = PART / CW;
   const int rt = q * 32 + lane;                 // row inside the tile
   const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) + h * PART;
+  // Y_TMEM: the layer output becomes the next GEMM's A operand IN TENSOR MEMORY (packed bf16 pairs, lane = row)
+  const uint32_t yaddr = tmem_y + ((uint32_t)(q * 32) << 16) + (h * PART) / 2;
+  uint32_t yw[16];
   uint32_t pk[PART / 2];
   float sum = 0.f, sq = 0.f;
 #pragma unroll
@@ -228,10 +233,16 @@ __device__ __forceinline__ void mlp_epilogue(uint32_t tmem_acc, int q, int h, in
     } else {
       const uint4 o = make_uint4(pack_bf16(y[0], y[1]), pack_bf16(y[2], y[3]), pack_bf16(y[4], y[5]), pack_bf16(y[6], y[7]));
       const uint32_t off = tile_off(rt, c0, C);
-      *reinterpret_cast<uint4*>(ytile + off) = o;
+      if (Y_TMEM) {
+        yw[4 * (g8 & 3)] = o.x; yw[4 * (g8 & 3) + 1] = o.y; yw[4 * (g8 & 3) + 2] = o.z; yw[4 * (g8 & 3) + 3] = o.w;
+        if ((g8 & 3) == 3) tmem_st16u(yaddr + (g8 >> 2) * 16, yw);
+      } else {
+        *reinterpret_cast<uint4*>(ytile + off) = o;
+      }
       if (y_img) *reinterpret_cast<uint4*>(y_img + off) = o;
     }
   }
+  if (Y_TMEM && !LAST) tmem_st_wait();
   head_partial = hp;
 }
 
@@ -398,16 +409,216 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_tc_fwd_kernel(MlpFwdArgs A
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Two tiles in flight per CTA.  Each tile owns a 256-column TMEM slot; the layer outputs y1 / y2 are written
+// back to the slot as packed bf16 and consumed by the next GEMM as its A operand straight from tensor memory,
+// so no activation tile lives in shared memory and the two slots never compete for it:
+//   [0,256) layer-1 accumulator -> [0,128) y1 bf16 | [128,256) layer-2 accumulator -> [0,64) y2 bf16 |
+//   [64,128) layer-3 accumulator.
+// All 16 warps work on ONE epilogue at a time, alternating between the slots, and every GEMM is issued one
+// epilogue ahead of its consumer: the tensor-core round trip of a tile hides behind the other tile's epilogue.
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t SM2_A0 = SM_W2 + 64 * 128 * 2;               // input tile of slot 0 (16 KB)
+constexpr uint32_t SM2_A1 = SM2_A0 + 128 * 64 * 2;              // input tile of slot 1
+constexpr uint32_t SM2_PAR = SM2_A1 + 128 * 64 * 2;
+constexpr uint32_t SM2_STAT = SM2_PAR + PAR_COUNT * 4;
+constexpr uint32_t SM2_HEAD = SM2_STAT + 128 * MLP_NH * 2 * 4;
+constexpr uint32_t SM2_TOTAL = SM2_HEAD + 128 * MLP_NH * 4;
+
+__global__ void __launch_bounds__(MLP_THREADS, 1) mlp_tc_fwd2_kernel(MlpFwdArgs A) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t full[2], bl1[2], bl2[2], bl3[2];
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q = warp & 3, h = warp >> 2;
+  float* par = reinterpret_cast<float*>(smem + SM2_PAR);
+  float* s_stat = reinterpret_cast<float*>(smem + SM2_STAT);
+  float* s_head = reinterpret_cast<float*>(smem + SM2_HEAD);
+  const float* P = A.dense;
+
+  load_weight_image<256, 64>(smem + SM_W0, P + NCF_OFF(NCF_P_MLP0_W), K0, tid, MLP_THREADS);
+  load_weight_image<128, 256>(smem + SM_W1, P + NCF_OFF(NCF_P_MLP1_W), H1, tid, MLP_THREADS);
+  load_weight_image<64, 128>(smem + SM_W2, P + NCF_OFF(NCF_P_MLP2_W), H2, tid, MLP_THREADS);
+  // LayerNorm gamma / beta carry the dropout scale 1/(1-p): y = keep ? LN(x) * scale : 0
+  const float sc0 = A.rng[0].thresh ? A.rng[0].scale : 1.f, sc1 = A.rng[1].thresh ? A.rng[1].scale : 1.f,
+              sc2 = A.rng[2].thresh ? A.rng[2].scale : 1.f;
+  for (int i = tid; i < 256; i += MLP_THREADS) {
+    par[PAR_B0 + i] = P[NCF_OFF(NCF_P_MLP0_B) + i];
+    par[PAR_G0 + i] = P[NCF_OFF(NCF_P_LN0_W) + i] * sc0;
+    par[PAR_E0 + i] = P[NCF_OFF(NCF_P_LN0_B) + i] * sc0;
+    if (i < 128) {
+      par[PAR_B1 + i] = P[NCF_OFF(NCF_P_MLP1_B) + i];
+      par[PAR_G1 + i] = P[NCF_OFF(NCF_P_LN1_W) + i] * sc1;
+      par[PAR_E1 + i] = P[NCF_OFF(NCF_P_LN1_B) + i] * sc1;
+    }
+    if (i < 64) {
+      par[PAR_B2 + i] = P[NCF_OFF(NCF_P_MLP2_B) + i];
+      par[PAR_G2 + i] = P[NCF_OFF(NCF_P_LN2_W) + i] * sc2;
+      par[PAR_E2 + i] = P[NCF_OFF(NCF_P_LN2_B) + i] * sc2;
+      par[PAR_WOUT + i] = P[NCF_OFF(NCF_P_MLP_OUT_W) + i];
+    }
+  }
+  if (tid == 0) {
+    par[PAR_SCAL + 0] = P[NCF_OFF(NCF_P_MLP_OUT_B)];
+    par[PAR_SCAL + 1] = P[NCF_OFF(NCF_P_FINAL_W)];
+    par[PAR_SCAL + 2] = P[NCF_OFF(NCF_P_FINAL_W) + 1];
+    par[PAR_SCAL + 3] = P[NCF_OFF(NCF_P_FINAL_B)];
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&bl1[s], 1);
+      mbar_init(&bl2[s], 1);
+      mbar_init(&bl3[s], 1);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_slot, 512);
+  fence_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t sW0 = smem_addr(smem + SM_W0), sW1 = smem_addr(smem + SM_W1), sW2 = smem_addr(smem + SM_W2);
+  const int64_t ntiles = (A.N + TCM_ROWS - 1) / TCM_ROWS;
+  const int64_t nk = (int64_t)blockIdx.x < ntiles ? (ntiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;   // my tiles
+  constexpr uint32_t A_BYTES = 128 * 64 * 2;
+  const uint8_t* a_img = reinterpret_cast<const uint8_t*>(A.a_img);
+  const int rt = q * 32 + lane;
+
+  auto tile_of = [&](int64_t k) { return (int64_t)blockIdx.x + k * gridDim.x; };
+  auto load_input = [&](int s, int64_t k) {          // tid 0: TMA bulk copy of tile k's input into slot s
+    mbar_arrive_expect_tx(&full[s], A_BYTES);
+    bulk_g2s(smem + (s ? SM2_A1 : SM2_A0), a_img + tile_of(k) * A_BYTES, A_BYTES, &full[s]);
+  };
+  auto issue_l1 = [&](int s) {                        // tid 0
+    issue_gemm(tmem + 256 * s, smem_addr(smem + (s ? SM2_A1 : SM2_A0)), 128, 64 * 16, 256, sW0, 128, 64 * 16, 256,
+               make_idesc(128, 256, false, false), 4, false);
+    mma_commit(&bl1[s]);
+  };
+  auto wait_sync = [&](uint64_t* b, uint32_t parity) {
+    if (warp == 0) mbar_wait(b, parity);               // one warp polls the mbarrier, the rest park on the CTA barrier
+    __syncthreads();
+    fence_after_sync();
+  };
+
+  if (tid == 0 && nk > 0) {
+    load_input(0, 0);
+    if (nk > 1) load_input(1, 1);
+    mbar_wait(&full[0], 0);
+    fence_after_sync();
+    issue_l1(0);
+    if (nk > 1) {
+      mbar_wait(&full[1], 0);
+      fence_after_sync();
+      issue_l1(1);
+    }
+  }
+
+  // ---- the three epilogues of one tile; each ends by publishing its output and issuing the next GEMM ----
+  auto phase1 = [&](int s, int64_t k, uint32_t par_bit) {
+    const int64_t tile = tile_of(k), grow = tile * TCM_ROWS + rt;
+    const bool live = grow < A.N;
+    wait_sync(&bl1[s], par_bit);
+    if (tid == 0 && k + 2 < nk) load_input(s, k + 2);   // the layer-1 GEMM is done with this slot's input tile
+    uint8_t* r1i = A.r1 ? reinterpret_cast<uint8_t*>(A.r1) + tile * (128 * 256 * 2) : nullptr;
+    uint8_t* y1i = A.y1 ? reinterpret_cast<uint8_t*>(A.y1) + tile * (128 * 256 * 2) : nullptr;
+    float* st1 = A.st1 ? A.st1 + tile * 256 : nullptr;
+    float hp;
+    const uint32_t slot = tmem + 256 * s;
+    if (A.hour) {
+      const float* tail_row = live ? A.tail1 + A.hour[grow] * H1 : nullptr;
+      mlp_epilogue<256, false, true, true>(slot, q, h, lane, grow, live, par + PAR_B0, par + PAR_G0, par + PAR_E0, tail_row,
+                                           A.rng[0], s_stat, nullptr, r1i, y1i, nullptr, nullptr, hp, st1, slot);
+    } else {
+      mlp_epilogue<256, false, false, true>(slot, q, h, lane, grow, live, par + PAR_B0, par + PAR_G0, par + PAR_E0, nullptr,
+                                            A.rng[0], s_stat, nullptr, r1i, y1i, nullptr, nullptr, hp, st1, slot);
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+      fence_after_sync();
+      issue_gemm_ts(slot + 128, slot, sW1, 128, 256 * 16, 256, make_idesc(128, 128, false, false), 16, false);
+      mma_commit(&bl2[s]);
+    }
+  };
+  auto phase2 = [&](int s, int64_t k, uint32_t par_bit) {
+    const int64_t tile = tile_of(k), grow = tile * TCM_ROWS + rt;
+    const bool live = grow < A.N;
+    wait_sync(&bl2[s], par_bit);
+    uint8_t* r2i = A.r2 ? reinterpret_cast<uint8_t*>(A.r2) + tile * (128 * 128 * 2) : nullptr;
+    uint8_t* y2i = A.y2 ? reinterpret_cast<uint8_t*>(A.y2) + tile * (128 * 128 * 2) : nullptr;
+    float* st2 = A.st2 ? A.st2 + tile * 256 : nullptr;
+    float hp;
+    const uint32_t slot = tmem + 256 * s;
+    mlp_epilogue<128, false, false, true>(slot + 128, q, h, lane, grow, live, par + PAR_B1, par + PAR_G1, par + PAR_E1, nullptr,
+                                          A.rng[1], s_stat, nullptr, r2i, y2i, nullptr, nullptr, hp, st2, slot);
+    fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+      fence_after_sync();
+      issue_gemm_ts(slot + 64, slot, sW2, 128, 128 * 16, 256, make_idesc(128, 64, false, false), 8, false);
+      mma_commit(&bl3[s]);
+    }
+  };
+  auto phase3 = [&](int s, int64_t k, uint32_t par_bit) {
+    const int64_t tile = tile_of(k), grow = tile * TCM_ROWS + rt;
+    const bool live = grow < A.N;
+    wait_sync(&bl3[s], par_bit);
+    uint8_t* r3i = A.r3 ? reinterpret_cast<uint8_t*>(A.r3) + tile * (128 * 64 * 2) : nullptr;
+    float* st3 = A.st3 ? A.st3 + tile * 256 : nullptr;
+    float hp;
+    const uint32_t slot = tmem + 256 * s;
+    mlp_epilogue<64, true, false, true>(slot + 64, q, h, lane, grow, live, par + PAR_B2, par + PAR_G2, par + PAR_E2, nullptr,
+                                        A.rng[2], s_stat, nullptr, r3i, nullptr, A.y3, par + PAR_WOUT, hp, st3, 0);
+    s_head[rt * MLP_NH + h] = hp;
+    fence_before_sync();
+    __syncthreads();
+    if (tid == 0 && k + 2 < nk) {      // the slot is free: layer-1 GEMM of its next tile (input prefetched in phase 1)
+      mbar_wait(&full[s], par_bit ^ 1u);
+      fence_after_sync();
+      issue_l1(s);
+    }
+    if (h == 0 && live) {
+      const float mp = (s_head[rt * MLP_NH] + s_head[rt * MLP_NH + 1]) + (s_head[rt * MLP_NH + 2] + s_head[rt * MLP_NH + 3]) +
+                       par[PAR_SCAL + 0];
+      const float z = fmaf(par[PAR_SCAL + 1], A.mf_pred[grow], fmaf(par[PAR_SCAL + 2], mp, par[PAR_SCAL + 3]));
+      const float pr = 1.0f / (1.0f + expf(-z));
+      A.mlp_pred[grow] = mp;
+      A.out[grow] = pr;
+      if (A.out2) A.out2[grow] = pr;
+    }
+    // s_head is next written two CTA barriers later at the earliest (stats barrier + publish barrier of the
+    // following epilogue), after every h == 0 thread has passed them: no extra barrier needed here
+  };
+
+  uint32_t it = 0;
+  for (int64_t k0 = 0; k0 < nk; k0 += 2, ++it) {
+    const bool two = k0 + 1 < nk;
+    const uint32_t pb = it & 1u;
+    phase1(0, k0, pb);
+    if (two) phase1(1, k0 + 1, pb);
+    phase2(0, k0, pb);
+    if (two) phase2(1, k0 + 1, pb);
+    phase3(0, k0, pb);
+    if (two) phase3(1, k0 + 1, pb);
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
 int launch_mlp_tc_fwd(const MlpFwdArgs& A, cudaStream_t st) {
   if (A.N == 0) return NCF_OK;
-  static bool configured = false;
-  if (!configured) {
+  static int variant = -1;      // NCF_MLP_FWD=1 selects the single-tile kernel (activation tiles in shared memory)
+  if (variant < 0) {
+    const char* e = getenv("NCF_MLP_FWD");
+    variant = e ? atoi(e) : 2;
     NCF_CUDA(cudaFuncSetAttribute(mlp_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_MLP_TOTAL));
-    configured = true;
+    NCF_CUDA(cudaFuncSetAttribute(mlp_tc_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM2_TOTAL));
   }
   const int64_t ntiles = (A.N + TCM_ROWS - 1) / TCM_ROWS;
   const int grid = (int)std::min<int64_t>(ntiles, num_sms());
-  mlp_tc_fwd_kernel<<<grid, MLP_THREADS, SM_MLP_TOTAL, st>>>(A);
+  if (variant == 1) mlp_tc_fwd_kernel<<<grid, MLP_THREADS, SM_MLP_TOTAL, st>>>(A);
+  else mlp_tc_fwd2_kernel<<<grid, MLP_THREADS, SM2_TOTAL, st>>>(A);
   NCF_LAUNCH_CHECK();
   return NCF_OK;
 }
