@@ -507,6 +507,7 @@ def main():
     xu = torch.empty(N, 64, device=dev)
     xp = torch.empty(N, 64, device=dev)
     ypm = torch.empty(N, 64, device=dev)
+    yum = torch.empty(N, 64, device=dev)
     adam = _lib.AdamCfg()
     adam.lr, adam.beta1, adam.beta2, adam.eps, adam.weight_decay, adam.step = 1e-3, 0.9, 0.999, 1e-8, 1e-5, 7
     ews_bytes = int(lib.ncf_emb_bwd_workspace_bytes(N))
@@ -516,7 +517,7 @@ def main():
 
     def k1():
         _lib.check(lib.ncf_gather_ln_gmf_fwd(C.byref(tabs), _lib.ptr(flat), _lib.ptr(u), _lib.ptr(it), N, None, None,
-                                             _lib.ptr(mf), _lib.ptr(xu), _lib.ptr(xp), _lib.ptr(ypm), sptr))
+                                             _lib.ptr(mf), _lib.ptr(xu), _lib.ptr(xp), _lib.ptr(ypm), _lib.ptr(yum), sptr))
 
     def fwd():
         _lib.check(lib.ncf_forward(C.byref(cfg), C.byref(tabs), _lib.ptr(flat), _lib.ptr(u), _lib.ptr(it), N, None, None,
@@ -538,7 +539,7 @@ def main():
         adam.emb_mode = _lib.EMB_ADAM_SPARSE
         _lib.check(lib.ncf_emb_bwd_adam_both(C.byref(adam), C.byref(tabs), _lib.ptr(flat), _lib.ptr(dgrad), _lib.ptr(u),
                                              _lib.ptr(it), N, _lib.ptr(dmf), _lib.ptr(dx), _lib.ptr(dx), _lib.ptr(ypm),
-                                             _lib.ptr(ews), ews_bytes, sptr))
+                                             _lib.ptr(yum), _lib.ptr(ews), ews_bytes, sptr))
 
     def sweep():
         adam.emb_mode = _lib.EMB_ADAM_DENSE_EQUIV

@@ -175,11 +175,12 @@ NCF_API int ncf_train_step(const ncf_run_cfg* cfg, const ncf_adam_cfg* adam, con
 /* ---- individual kernels (also used by the unit tests) ---------------------------------- */
 /* K1: fused dual-tower gather + LayerNorm + GMF product (architecture.py:286-287, 305-312).
  * mf_pred[N] = mf_output(LN(U_mf[u]) * LN(P_mf[p])); xu/xp [N,64] = mlp_norm of the MLP rows.
- * y_item_mf (optional, [N,64]) receives mf_norm(P_mf[p]) for the backward. */
+ * y_item_mf / y_user_mf (optional, [N,64]) receive mf_norm(P_mf[p]) / mf_norm(U_mf[u]) for the backward. */
 NCF_API int ncf_gather_ln_gmf_fwd(const ncf_tables* tables, const float* dense,
                           const int64_t* user_ids, const int64_t* item_ids, int64_t N,
                           const int64_t* hour, const float* tmod,
-                          float* mf_pred, float* xu, float* xp, float* y_item_mf, void* stream);
+                          float* mf_pred, float* xu, float* xp, float* y_item_mf, float* y_user_mf,
+                          void* stream);
 
 /* get_user_embeddings / get_product_embeddings rows (architecture.py:383-407): LN'd rows of one
  * side. side 0 = user, 1 = item. */
@@ -200,11 +201,12 @@ NCF_API int ncf_emb_bwd_adam(const ncf_adam_cfg* adam, const ncf_tables* tables,
                      void* workspace, int64_t workspace_bytes, void* stream);
 
 /* Both sides in one call with a single radix sort (what ncf_backward runs): item side first, then the
- * user side with y_item_mf = the item rows saved by ncf_gather_ln_gmf_fwd. */
+ * user side with y_item_mf = the item rows saved by ncf_gather_ln_gmf_fwd.  y_user_mf (optional) = the
+ * user rows it saved: with them no table row is gathered or LayerNorm-ed a second time. */
 NCF_API int ncf_emb_bwd_adam_both(const ncf_adam_cfg* adam, const ncf_tables* tables, const float* dense,
                           float* dense_grad, const int64_t* user_ids, const int64_t* item_ids, int64_t N,
                           const float* d_mf_pred, const float* d_xu, const float* d_xp, const float* y_item_mf,
-                          void* workspace, int64_t workspace_bytes, void* stream);
+                          const float* y_user_mf, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* the "every untouched row" half of NCF_EMB_ADAM_DENSE_EQUIV; clears tables->touched. */
 NCF_API int ncf_emb_adam_sweep(const ncf_adam_cfg* adam, const ncf_tables* tables, void* stream);

@@ -73,12 +73,12 @@ _SIGS = {
     "ncf_dense_adam": (C.c_int, [_P, _P, _P, _P, _I64, C.POINTER(AdamCfg), _P]),
     "ncf_train_step": (C.c_int, [C.POINTER(RunCfg), C.POINTER(AdamCfg), C.POINTER(Tables), _P, _P, _P, _P, _P, _P, _P,
                                  _I64, _P, _P, _P, _I64, _P]),
-    "ncf_gather_ln_gmf_fwd": (C.c_int, [C.POINTER(Tables), _P, _P, _P, _I64, _P, _P, _P, _P, _P, _P, _P]),
+    "ncf_gather_ln_gmf_fwd": (C.c_int, [C.POINTER(Tables), _P, _P, _P, _I64, _P, _P, _P, _P, _P, _P, _P, _P]),
     "ncf_gather_ln": (C.c_int, [C.POINTER(Tables), _P, _I32, _P, _I64, _P, _P, _P]),
     "ncf_emb_bwd_workspace_bytes": (_I64, [_I64]),
     "ncf_emb_bwd_adam": (C.c_int, [C.POINTER(AdamCfg), C.POINTER(Tables), _P, _P, _I32, _P, _P, _I64, _P, _P, _P, _P,
                                    _I64, _P]),
-    "ncf_emb_bwd_adam_both": (C.c_int, [C.POINTER(AdamCfg), C.POINTER(Tables), _P, _P, _P, _P, _I64, _P, _P, _P, _P, _P,
+    "ncf_emb_bwd_adam_both": (C.c_int, [C.POINTER(AdamCfg), C.POINTER(Tables), _P, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _P,
                                         _I64, _P]),
     "ncf_emb_adam_sweep": (C.c_int, [C.POINTER(AdamCfg), C.POINTER(Tables), _P]),
     "ncf_temporal_fwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _P, _P]),

@@ -60,7 +60,7 @@ extern "C" int ncf_forward(const ncf_run_cfg* cfg, const ncf_tables* T, const fl
   }
   cudaStream_t st = (cudaStream_t)stream;
   NCF_TRY(gather_ln_gmf_fwd_rows(tower_bf16_rows(*cfg), T, dense, user_ids, item_ids, N, hour, tmod, w.mf_pred, w.xu, w.xp,
-                                 cfg->training ? w.y_pmf : nullptr, stream));
+                                 cfg->training ? w.y_pmf : nullptr, cfg->training ? w.y_umf : nullptr, stream));
   return tower_f32_forward(*cfg, dense, N, hour, tail1, out, w, st);
 }
 
@@ -79,7 +79,7 @@ extern "C" int ncf_backward(const ncf_run_cfg* cfg, const ncf_adam_cfg* adam, co
   cudaStream_t st = (cudaStream_t)stream;
   NCF_TRY(tower_f32_backward(*cfg, dense, dense_grad, N, grad_out, w, st));
   if (adam->emb_mode != NCF_EMB_NONE) {
-    NCF_TRY(emb_bwd_both(adam, T, dense, dense_grad, user_ids, item_ids, N, w.d_mf, w.dxu, w.dxp, w.y_pmf, w.emb, w.emb_bytes, st));
+    NCF_TRY(emb_bwd_both(adam, T, dense, dense_grad, user_ids, item_ids, N, w.d_mf, w.dxu, w.dxp, w.y_pmf, w.y_umf, w.emb, w.emb_bytes, st));
     if (adam->emb_mode == NCF_EMB_ADAM_DENSE_EQUIV) NCF_TRY(ncf_emb_adam_sweep(adam, T, stream));
   }
   return NCF_OK;

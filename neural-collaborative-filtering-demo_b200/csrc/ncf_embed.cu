@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(K1_THREADS) gather_ln_gmf_fwd_kernel(
     const float* __restrict__ t_pmlp, const float* __restrict__ dense, const int64_t* __restrict__ user_ids,
     const int64_t* __restrict__ item_ids, int64_t N, const int64_t* __restrict__ hour,
     const float* __restrict__ tmod, float* __restrict__ mf_pred, float* __restrict__ xu, float* __restrict__ xp,
-    float* __restrict__ y_item_mf, bool bf16_rows) {
+    float* __restrict__ y_item_mf, float* __restrict__ y_user_mf, bool bf16_rows) {
   __shared__ __align__(16) int64_t s_ids[2][2][K1_TILE];
   __shared__ __align__(8) uint64_t s_bar[2];
 
@@ -154,7 +154,8 @@ __global__ void __launch_bounds__(K1_THREADS) gather_ln_gmf_fwd_kernel(
           const int64_t n = n0 + r;
           if (lane == 0) mf_pred[n] = dot + b_out;
           st_row4(half ? xp : xu, n, 4 * l16, y_ml, bf16_rows);
-          if (y_item_mf && half) st4(y_item_mf + n * D + 4 * l16, y_mf);   // kept for the backward
+          float* ykeep = half ? y_item_mf : y_user_mf;                      // mf_norm rows kept for the backward
+          if (ykeep) st4(ykeep + n * D + 4 * l16, y_mf);
         }
       }
     }
@@ -240,6 +241,7 @@ struct EmbBwdArgs {
   uint8_t* touched;
   const float* other_mf;          // other side's MF table (for the GMF product), used when other_y == null
   const float* other_y;           // [N,64] LN'd MF row of the other side saved by the forward (or null)
+  const float* own_y;             // [N,64] LN'd MF row of THIS side saved by the forward (or null): d mf_output.weight
   const float* upstream;          // sharded owner path: [N,128] ready-made upstream rows [mf | mlp] (or null)
   const int64_t* other_ids;       // other side's ids, original sample order
   const uint32_t* sorted_ids;     // this side's ids, sorted
@@ -332,7 +334,9 @@ __global__ void __launch_bounds__(EB_THREADS, 3) emb_bwd_phase1_kernel(EmbBwdArg
                            : half ? A.d_x + (int64_t)row * D
                                   : (A.other_y ? A.other_y + (int64_t)row * D : A.other_mf + oid * D);
         x[u] = ldg4(src + 4 * l16);
-        sf[u] = wmf ? ld4(A.w[0] + (int64_t)(idk[u] - A.id_off) * D + 4 * l16) : make_float4(0, 0, 0, 0);   // own MF row (d mf_output.weight)
+        sf[u] = !wmf ? make_float4(0, 0, 0, 0)                    // own MF row (d mf_output.weight): saved LN'd row or table row
+                : A.own_y ? ldg4(A.own_y + (int64_t)row * D + 4 * l16)
+                          : ld4(A.w[0] + (int64_t)(idk[u] - A.id_off) * D + 4 * l16);
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
@@ -348,7 +352,7 @@ __global__ void __launch_bounds__(EB_THREADS, 3) emb_bwd_phase1_kernel(EmbBwdArg
           float4 yo = x[u];
           if (!A.other_y && !A.upstream) yo = affine(ln_normalise(x[u], rs), g_mf, b_mf);   // LN of the other side's MF row
           float4 ys = make_float4(0, 0, 0, 0);
-          if (wmf) ys = affine(ln_normalise(sf[u], rs), g_mf, b_mf);
+          if (wmf) ys = A.own_y ? sf[u] : affine(ln_normalise(sf[u], rs), g_mf, b_mf);
           if (half || A.upstream) {
             acc = f4_add(acc, x[u]);
           } else {
@@ -577,7 +581,7 @@ using namespace ncf;
 namespace ncf {
 int gather_ln_gmf_fwd_rows(bool bf16_rows, const ncf_tables* T, const float* dense, const int64_t* user_ids,
                                      const int64_t* item_ids, int64_t N, const int64_t* hour, const float* tmod,
-                                     float* mf_pred, float* xu, float* xp, float* y_item_mf, void* stream) {
+                                     float* mf_pred, float* xu, float* xp, float* y_item_mf, float* y_user_mf, void* stream) {
   NCF_REQUIRE(T && dense && user_ids && item_ids && mf_pred && xu && xp, "gather_ln_gmf_fwd: null argument");
   NCF_REQUIRE(N >= 0, "gather_ln_gmf_fwd: N < 0");
   NCF_REQUIRE(!hour || tmod, "gather_ln_gmf_fwd: hour needs tmod");
@@ -587,10 +591,10 @@ int gather_ln_gmf_fwd_rows(bool bf16_rows, const ncf_tables* T, const float* den
   cudaStream_t st = (cudaStream_t)stream;
   if (hour)
     gather_ln_gmf_fwd_kernel<true><<<grid, K1_THREADS, 0, st>>>(T->w[0], T->w[1], T->w[2], T->w[3], dense, user_ids,
-                                                                item_ids, N, hour, tmod, mf_pred, xu, xp, y_item_mf, bf16_rows);
+                                                                item_ids, N, hour, tmod, mf_pred, xu, xp, y_item_mf, y_user_mf, bf16_rows);
   else
     gather_ln_gmf_fwd_kernel<false><<<grid, K1_THREADS, 0, st>>>(T->w[0], T->w[1], T->w[2], T->w[3], dense, user_ids,
-                                                                 item_ids, N, nullptr, nullptr, mf_pred, xu, xp, y_item_mf, bf16_rows);
+                                                                 item_ids, N, nullptr, nullptr, mf_pred, xu, xp, y_item_mf, y_user_mf, bf16_rows);
   NCF_LAUNCH_CHECK();
   return NCF_OK;
 }
@@ -598,8 +602,9 @@ int gather_ln_gmf_fwd_rows(bool bf16_rows, const ncf_tables* T, const float* den
 
 extern "C" int ncf_gather_ln_gmf_fwd(const ncf_tables* T, const float* dense, const int64_t* user_ids,
                                      const int64_t* item_ids, int64_t N, const int64_t* hour, const float* tmod,
-                                     float* mf_pred, float* xu, float* xp, float* y_item_mf, void* stream) {
-  return gather_ln_gmf_fwd_rows(false, T, dense, user_ids, item_ids, N, hour, tmod, mf_pred, xu, xp, y_item_mf, stream);
+                                     float* mf_pred, float* xu, float* xp, float* y_item_mf, float* y_user_mf,
+                                     void* stream) {
+  return gather_ln_gmf_fwd_rows(false, T, dense, user_ids, item_ids, N, hour, tmod, mf_pred, xu, xp, y_item_mf, y_user_mf, stream);
 }
 
 extern "C" int ncf_gather_ln(const ncf_tables* T, const float* dense, int32_t side, const int64_t* ids, int64_t n,
@@ -687,6 +692,7 @@ static int run_emb_bwd(const ncf_adam_cfg* adam, const ncf_tables* T, const floa
   A.touched = adam->emb_mode == NCF_EMB_ADAM_DENSE_EQUIV ? T->touched[side] : nullptr;
   A.other_mf = T->w[side ? 0 : 1];
   A.other_y = other_y_mf;
+  A.own_y = nullptr;
   A.upstream = upstream;
   A.other_ids = other_ids;
   A.sorted_ids = w.keys_out;
@@ -743,7 +749,8 @@ namespace ncf {
 // user MF rows before the user side overwrites them), user side second (reads the saved item rows).
 int emb_bwd_both(const ncf_adam_cfg* adam, const ncf_tables* T, const float* dense, float* dense_grad,
                  const int64_t* user_ids, const int64_t* item_ids, int64_t N, const float* d_mf_pred, const float* dxu,
-                 const float* dxp, const float* y_item_mf, void* workspace, int64_t workspace_bytes, cudaStream_t st) {
+                 const float* dxp, const float* y_item_mf, const float* y_user_mf, void* workspace, int64_t workspace_bytes,
+                 cudaStream_t st) {
   if (N == 0 || adam->emb_mode == NCF_EMB_NONE) return NCF_OK;
   NCF_REQUIRE(2 * N < ((int64_t)1 << 31), "emb_bwd: N too large");
   NCF_REQUIRE(T->rows_user + T->rows_item < ((int64_t)1 << 32), "emb_bwd: too many table rows for 32-bit keys");
@@ -781,7 +788,8 @@ int emb_bwd_both(const ncf_adam_cfg* adam, const ncf_tables* T, const float* den
     A.g[1] = T->g[2 + side];
     A.touched = adam->emb_mode == NCF_EMB_ADAM_DENSE_EQUIV ? T->touched[side] : nullptr;
     A.other_mf = T->w[side ? 0 : 1];
-    A.other_y = side ? nullptr : y_item_mf;
+    A.other_y = side ? y_user_mf : y_item_mf;       // null: gather the other side's table row and LayerNorm it again
+    A.own_y = side ? nullptr : y_user_mf;
     A.upstream = nullptr;
     A.other_ids = side ? user_ids : item_ids;
     A.sorted_ids = w.keys_out + (side ? N : 0);
@@ -809,12 +817,12 @@ int emb_bwd_both(const ncf_adam_cfg* adam, const ncf_tables* T, const float* den
 
 extern "C" int ncf_emb_bwd_adam_both(const ncf_adam_cfg* adam, const ncf_tables* T, const float* dense, float* dense_grad,
                                      const int64_t* user_ids, const int64_t* item_ids, int64_t N, const float* d_mf_pred,
-                                     const float* d_xu, const float* d_xp, const float* y_item_mf, void* workspace,
-                                     int64_t workspace_bytes, void* stream) {
+                                     const float* d_xu, const float* d_xp, const float* y_item_mf, const float* y_user_mf,
+                                     void* workspace, int64_t workspace_bytes, void* stream) {
   NCF_REQUIRE(adam && T && dense && user_ids && item_ids && d_mf_pred && d_xu && d_xp && y_item_mf && workspace,
               "emb_bwd_adam_both: null argument");
-  return emb_bwd_both(adam, T, dense, dense_grad, user_ids, item_ids, N, d_mf_pred, d_xu, d_xp, y_item_mf, workspace,
-                      workspace_bytes, (cudaStream_t)stream);
+  return emb_bwd_both(adam, T, dense, dense_grad, user_ids, item_ids, N, d_mf_pred, d_xu, d_xp, y_item_mf, y_user_mf,
+                      workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 extern "C" int ncf_emb_bwd_adam(const ncf_adam_cfg* adam, const ncf_tables* T, const float* dense, float* dense_grad,

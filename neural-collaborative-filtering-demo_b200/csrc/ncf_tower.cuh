@@ -10,7 +10,7 @@ namespace ncf {
 struct TowerWs {
   float *mf_pred, *mlp_pred, *p_saved;     // [N]
   float *xu, *xp;                          // [N,64]  mlp_norm(user row), mlp_norm(item row)
-  float *y_pmf;                            // [N,64]  mf_norm(item row), training only
+  float *y_pmf, *y_umf;                    // [N,64]  mf_norm(item row), mf_norm(user row): training only
   float *q, *kv, *ctx, *a;                 // [N,64] [N,128] [N,64] [N,64]
   float *r1, *y1, *r2, *y2, *r3, *y3;      // relu outputs / layer outputs of the 3 MLP layers
   // backward scratch (training only)
@@ -40,7 +40,7 @@ bool tower_bf16_rows(const ncf_run_cfg& cfg);
 // K1 with selectable row format (ncf_embed.cu); the C-ABI export ncf_gather_ln_gmf_fwd is the fp32 case
 int gather_ln_gmf_fwd_rows(bool bf16_rows, const ncf_tables* T, const float* dense, const int64_t* user_ids,
                            const int64_t* item_ids, int64_t N, const int64_t* hour, const float* tmod, float* mf_pred,
-                           float* xu, float* xp, float* y_item_mf, void* stream);
+                           float* xu, float* xp, float* y_item_mf, float* y_user_mf, void* stream);
 // the two halves of each direction (also exported one by one: ncf_attn_fwd / ncf_mlp_fwd / ncf_mlp_bwd / ncf_attn_bwd)
 int tower_attn_forward(const ncf_run_cfg& cfg, const float* dense, int64_t N, TowerWs& w, cudaStream_t st);
 int tower_mlp_forward(const ncf_run_cfg& cfg, const float* dense, int64_t N, const int64_t* hour, const float* tail1,
@@ -67,7 +67,8 @@ int64_t attn_tc_partial_floats();
 // fused embedding backward of both sides with a single radix sort (ncf_embed.cu)
 int emb_bwd_both(const ncf_adam_cfg* adam, const ncf_tables* T, const float* dense, float* dense_grad,
                  const int64_t* user_ids, const int64_t* item_ids, int64_t N, const float* d_mf_pred, const float* dxu,
-                 const float* dxp, const float* y_item_mf, void* workspace, int64_t workspace_bytes, cudaStream_t st);
+                 const float* dxp, const float* y_item_mf, const float* y_user_mf, void* workspace, int64_t workspace_bytes,
+                 cudaStream_t st);
 // fused backward of one projection: dX = dY.W and dW += dY^T.X, db += colsum(dY) (which: 0 = 64 cols, 1 = 128)
 int tc_proj_backward(int which, const float* dY, const float* X, const float* W, float* dX, float* dW, float* db, int64_t N,
                      cudaStream_t st);

@@ -705,6 +705,7 @@ TowerWs carve_tower_ws(void* ws, int64_t N, const ncf_run_cfg& cfg) {
   }
   if (train) {
     w.y_pmf = c.take<float>(N * D);
+    w.y_umf = c.take<float>(N * D);
     w.d_mf = c.take<float>(N);
     w.d_mlp = c.take<float>(N);
     w.g64a = c.take<float>(N * D);

@@ -592,14 +592,16 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_tc_fwd2_kernel(MlpFwdArgs 
 
   uint32_t it = 0;
   for (int64_t k0 = 0; k0 < nk; k0 += 2, ++it) {
-    const bool two = k0 + 1 < nk;
+    const int ns = k0 + 1 < nk ? 2 : 1;
     const uint32_t pb = it & 1u;
-    phase1(0, k0, pb);
-    if (two) phase1(1, k0 + 1, pb);
-    phase2(0, k0, pb);
-    if (two) phase2(1, k0 + 1, pb);
-    phase3(0, k0, pb);
-    if (two) phase3(1, k0 + 1, pb);
+    // one copy of each epilogue in the instruction stream (the slot is a run-time value): the kernel stays
+    // inside the instruction cache
+#pragma unroll 1
+    for (int s = 0; s < ns; ++s) phase1(s, k0 + s, pb);
+#pragma unroll 1
+    for (int s = 0; s < ns; ++s) phase2(s, k0 + s, pb);
+#pragma unroll 1
+    for (int s = 0; s < ns; ++s) phase3(s, k0 + s, pb);
   }
   fence_before_sync();
   __syncthreads();
