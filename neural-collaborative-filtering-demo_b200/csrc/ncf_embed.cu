@@ -253,6 +253,7 @@ struct EmbBwdArgs {
   const float* dense;
   float* dense_grad;
   float* acc_buf;                 // [N][2][64] upstream sum of the run piece that starts at each sorted position
+  int32_t* chunk_counter;         // phase 2: next chunk to hand out (zeroed before the launch)
   int64_t N;
   uint32_t id_off;                // sorted keys hold id + id_off (combined two-side sort)
   int32_t mode;                   // ncf_emb_mode
@@ -382,7 +383,14 @@ __global__ void __launch_bounds__(EB_THREADS, 3) emb_bwd_phase2_kernel(EmbBwdArg
   float4 dgamma = make_float4(0, 0, 0, 0), dbeta = dgamma;
   const bool adam = A.mode != NCF_EMB_MATERIALIZE;
 
-  for (int64_t c = gw; c < nchunks; c += gstride) {
+  // Chunks are handed out dynamically (one atomic per chunk): chunks that start long runs cost far more than the
+  // rest, and a static assignment leaves most warps of a block waiting for one at the final reduction.
+  (void)gw; (void)gstride;
+  for (;;) {
+    int64_t c = 0;
+    if (lane == 0) c = atomicAdd(A.chunk_counter, 1);
+    c = __shfl_sync(0xffffffffu, c, 0);
+    if (c >= nchunks) break;
     const int64_t p0 = c * EB_CHUNK;
     const int cnt = (int)min((int64_t)EB_CHUNK, A.N - p0);
     const uint32_t my_id = lane < cnt ? A.sorted_ids[p0 + lane] : 0xffffffffu;
@@ -431,24 +439,28 @@ __global__ void __launch_bounds__(EB_THREADS, 3) emb_bwd_phase2_kernel(EmbBwdArg
       (void)i;
       // does the run leave this chunk?  (its last in-chunk element is the chunk's last element)
       const uint32_t last_id = __shfl_sync(0xffffffffu, my_id, cnt - 1);
-      if (last_id == id && p0 + EB_CHUNK < A.N && A.sorted_ids[p0 + EB_CHUNK] == id) {
-        // long run: find its end by binary search in the sorted ids, then add the chunk-start pieces with
-        // independent loads (fixed order)
-        int64_t lo = p0 + EB_CHUNK, hi = A.N;               // first position > lo whose id differs
-        while (lo < hi) {
-          const int64_t mid = (lo + hi) >> 1;
-          if (A.sorted_ids[mid] == id) lo = mid + 1; else hi = mid;
-        }
-        const int64_t end = lo;
+      if (last_id == id) {
+        // the run may continue into the following chunks: walk their first pieces four at a time with speculative,
+        // independent loads and add those that still belong to the run, in order (deterministic sum)
         int64_t cs = p0 + EB_CHUNK;
-        for (; cs + 3 * EB_CHUNK < end; cs += 4 * EB_CHUNK) {
-          const float4 a0 = ld4(A.acc_buf + (cs * 2 + half) * D + 4 * l16);
-          const float4 a1 = ld4(A.acc_buf + ((cs + EB_CHUNK) * 2 + half) * D + 4 * l16);
-          const float4 a2 = ld4(A.acc_buf + ((cs + 2 * EB_CHUNK) * 2 + half) * D + 4 * l16);
-          const float4 a3 = ld4(A.acc_buf + ((cs + 3 * EB_CHUNK) * 2 + half) * D + 4 * l16);
-          acc = f4_add(f4_add(f4_add(f4_add(acc, a0), a1), a2), a3);
+        bool more = cs < A.N;
+        while (more) {
+          uint32_t idn[4];
+          float4 a[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int64_t pos = cs + (int64_t)u * EB_CHUNK;
+            const bool ok = pos < A.N;
+            idn[u] = ok ? A.sorted_ids[pos] : ~id;
+            a[u] = ok ? ld4(A.acc_buf + (pos * 2 + half) * D + 4 * l16) : make_float4(0, 0, 0, 0);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            more = more && idn[u] == id;
+            if (more) acc = f4_add(acc, a[u]);
+          }
+          cs += 4 * EB_CHUNK;
         }
-        for (; cs < end; cs += EB_CHUNK) acc = f4_add(acc, ld4(A.acc_buf + (cs * 2 + half) * D + 4 * l16));
       }
       float rstd;
       const float4 xhat = ln_normalise(wrow, rstd);
@@ -629,6 +641,7 @@ struct EmbWs {
   uint32_t* other_sorted;
   float* dmf_sorted;
   float* acc_buf;
+  int32_t* counters;        // dynamic chunk schedulers of the two phase-2 launches
   void* cub_tmp;
   size_t cub_bytes;
   int64_t total;
@@ -644,6 +657,7 @@ static EmbWs carve_emb_ws(void* ws, int64_t N) {
   w.other_sorted = c.take<uint32_t>(2 * N);
   w.dmf_sorted = c.take<float>(2 * N);
   w.acc_buf = c.take<float>(N * 2 * D);
+  w.counters = c.take<int32_t>(4);
   w.cub_bytes = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, w.cub_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr,
                                   (const int32_t*)nullptr, (int32_t*)nullptr, (int)std::max<int64_t>(2 * N, 1), 0, 32);
@@ -713,9 +727,11 @@ static int run_emb_bwd(const ncf_adam_cfg* adam, const ncf_tables* T, const floa
   const int64_t nchunks = (N + EB_CHUNK - 1) / EB_CHUNK;
   const int wpb = EB_THREADS / 32;
   const int grid = (int)std::min<int64_t>((nchunks + wpb - 1) / wpb, (int64_t)num_sms() * 8);
+  A.chunk_counter = w.counters;
+  NCF_CUDA(cudaMemsetAsync(w.counters, 0, 4 * sizeof(int32_t), st));
   emb_bwd_phase1_kernel<<<grid, EB_THREADS, 0, st>>>(A);
   NCF_LAUNCH_CHECK();
-  emb_bwd_phase2_kernel<<<grid, EB_THREADS, 0, st>>>(A);
+  emb_bwd_phase2_kernel<<<std::min(grid, num_sms() * 3), EB_THREADS, 0, st>>>(A);
   NCF_LAUNCH_CHECK();
   return NCF_OK;
 }
@@ -776,6 +792,7 @@ int emb_bwd_both(const ncf_adam_cfg* adam, const ncf_tables* T, const float* den
   const int64_t nchunks = (N + EB_CHUNK - 1) / EB_CHUNK;
   const int wpb = EB_THREADS / 32;
   const int grid = (int)std::min<int64_t>((nchunks + wpb - 1) / wpb, (int64_t)num_sms() * 8);
+  NCF_CUDA(cudaMemsetAsync(w.counters, 0, 4 * sizeof(int32_t), st));
   for (int side = 1; side >= 0; --side) {
     EmbBwdArgs A;
     A.w[0] = T->w[side];
@@ -806,9 +823,10 @@ int emb_bwd_both(const ncf_adam_cfg* adam, const ncf_tables* T, const float* den
     A.mode = adam->emb_mode;
     A.accumulate_wmf = side == 0 ? 1 : 0;
     A.adam = adam_scalars(*adam);
+    A.chunk_counter = w.counters + side;
     emb_bwd_phase1_kernel<<<grid, EB_THREADS, 0, st>>>(A);
     NCF_LAUNCH_CHECK();
-    emb_bwd_phase2_kernel<<<grid, EB_THREADS, 0, st>>>(A);
+    emb_bwd_phase2_kernel<<<std::min(grid, num_sms() * 3), EB_THREADS, 0, st>>>(A);     // resident blocks pull chunks
     NCF_LAUNCH_CHECK();
   }
   return NCF_OK;

@@ -590,22 +590,37 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
   const float4 w = ldg4(dense + NCF_OFF(NCF_P_MLP_OUT_W) + 4 * l16);
   float4 dw = make_float4(0, 0, 0, 0);
   float s_a = 0.f, s_c = 0.f, s_d = 0.f, s_bmf = 0.f, s_bmlp = 0.f;
-  // all 16 lanes of a half warp walk the same rows
-  for (int64_t n = hw0; n < N; n += hstride) {
-    const float p = p_saved[n];
-    const float dz = grad_out[n] * p * (1.0f - p);
-    const float dmf = dz * a, dml = dz * c;
-    const float4 h = ldg4(h3 + n * H3 + 4 * l16);
-    dw = f4_fma(dml, h, dw);
-    if (dh3) st4(dh3 + n * H3 + 4 * l16, make_float4(dml * w.x, dml * w.y, dml * w.z, dml * w.w));
-    if (l16 == 0) {
-      d_mf_pred[n] = dmf;
-      if (d_mlp_pred) d_mlp_pred[n] = dml;     // the tcgen05 MLP backward forms dh3 = d_mlp_pred * w itself
-      s_a = fmaf(dz, mf_pred[n], s_a);
-      s_c = fmaf(dz, mlp_pred[n], s_c);
-      s_d += dz;
-      s_bmf += dmf;
-      s_bmlp += dml;
+  // all 16 lanes of a half warp walk the same rows, four rows per trip so that their loads are in flight together
+  for (int64_t n0 = hw0; n0 < N; n0 += 4 * hstride) {
+    float p[4], go[4], mfp[4], mlpp[4];
+    float4 h[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t n = min(n0 + u * hstride, N - 1);
+      p[u] = p_saved[n];
+      go[u] = grad_out[n];
+      mfp[u] = mf_pred[n];
+      mlpp[u] = mlp_pred[n];
+      h[u] = ldg4(h3 + n * H3 + 4 * l16);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t n = n0 + u * hstride;
+      if (n < N) {
+        const float dz = go[u] * p[u] * (1.0f - p[u]);
+        const float dmf = dz * a, dml = dz * c;
+        dw = f4_fma(dml, h[u], dw);
+        if (dh3) st4(dh3 + n * H3 + 4 * l16, make_float4(dml * w.x, dml * w.y, dml * w.z, dml * w.w));
+        if (l16 == 0) {
+          d_mf_pred[n] = dmf;
+          if (d_mlp_pred) d_mlp_pred[n] = dml;     // the tcgen05 MLP backward forms dh3 = d_mlp_pred * w itself
+          s_a = fmaf(dz, mfp[u], s_a);
+          s_c = fmaf(dz, mlpp[u], s_c);
+          s_d += dz;
+          s_bmf += dmf;
+          s_bmlp += dml;
+        }
+      }
     }
   }
   // combine the two half warps, then the block
