@@ -419,6 +419,8 @@ def main():
     for s in range(args.warmup):
         eng.train_step(*dev_batches[s % nb])
     barrier()
+    if getattr(eng, "phase_ms", None):
+        eng.phase_ms.clear()                 # NCF_SHARD_PROFILE: steady state only
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -452,6 +454,9 @@ def main():
     value = world * N * args.steps / (ms_total / 1e3)
     e2e_value = world * N * args.steps / (e2e_ms_total / 1e3)
 
+    if rank == 0 and getattr(eng, "phase_ms", None):
+        n = eng.phase_ms.pop("steps")
+        sys.stderr.write("sharded phases, ms per step (rank 0): " + ", ".join(f"{k} {v / n:.3f}" for k, v in eng.phase_ms.items()) + "\n")
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

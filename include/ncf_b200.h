@@ -248,6 +248,15 @@ NCF_API int ncf_shard_bucketize(const int64_t* ids, int64_t n, int64_t rows, int
                         int64_t* counts, int64_t* perm, int64_t* local_ids,
                         void* workspace, int64_t workspace_bytes, void* stream);
 
+/* Same with adjacent-run compression: equal ADJACENT ids (the user id repeated over the S rows of an
+ * interaction, data_prep.py:286-303) are exchanged once.  counts[world] = run heads per owner;
+ * local_ids: the run heads' local ids in owner-major order (first sum(counts) entries valid);
+ * pos[n] = index into that order (= into the exchanged row buffers) for EVERY sample. */
+NCF_API int64_t ncf_shard_bucketize_runs_workspace_bytes(int64_t n, int32_t world);
+NCF_API int ncf_shard_bucketize_runs(const int64_t* ids, int64_t n, int64_t rows, int32_t world,
+                             int64_t* counts, int64_t* local_ids, int64_t* pos,
+                             void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---- row-sharded step: owner-side and requester-side halves ------------------- */
 /* owner: rows [n,128] = [mf_norm(T_mf[id]) | mlp_norm(T_mlp[id])] of its LOCAL ids for one side. */
 NCF_API int ncf_shard_owner_rows(const ncf_tables* local_tables, const float* dense, int32_t side,
@@ -257,9 +266,10 @@ NCF_API int ncf_shard_owner_rows(const ncf_tables* local_tables, const float* de
 NCF_API int ncf_shard_forward(const ncf_run_cfg* cfg, const float* dense, const float* rows_u, const float* rows_i,
                       const int64_t* pos_u, const int64_t* pos_i, int64_t N, float* out,
                       void* workspace, int64_t workspace_bytes, void* stream);
-/* requester: backward; writes the upstream gradient rows [N,128] = [d/d mf_norm row | d/d mlp_norm row]
- * at the owner-order positions and accumulates the dense gradients (except the LayerNorm affine
- * gradients of mf_norm / mlp_norm, which the owners add). */
+/* requester: backward; writes ONE upstream gradient row [128] = [d/d mf_norm row | d/d mlp_norm row] per
+ * exchanged row at its owner-order position (samples that share a position must be adjacent, as
+ * ncf_shard_bucketize_runs arranges: their gradients are summed here) and accumulates the dense
+ * gradients (except the LayerNorm affine gradients of mf_norm / mlp_norm, which the owners add). */
 NCF_API int ncf_shard_backward(const ncf_run_cfg* cfg, const float* dense, float* dense_grad,
                        const float* rows_u, const float* rows_i, const int64_t* pos_u, const int64_t* pos_i,
                        int64_t N, const float* grad_out, float* grad_rows_u, float* grad_rows_i,

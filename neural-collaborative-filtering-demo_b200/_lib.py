@@ -90,6 +90,8 @@ _SIGS = {
     "ncf_score_topk": (C.c_int, [C.POINTER(Tables), _P, _P, _P, _P, _I64, _I64, _I32, _P, _P, _P, _I64, _P]),
     "ncf_shard_bucketize_workspace_bytes": (_I64, [_I64, _I32]),
     "ncf_shard_bucketize": (C.c_int, [_P, _I64, _I64, _I32, _P, _P, _P, _P, _I64, _P]),
+    "ncf_shard_bucketize_runs_workspace_bytes": (_I64, [_I64, _I32]),
+    "ncf_shard_bucketize_runs": (C.c_int, [_P, _I64, _I64, _I32, _P, _P, _P, _P, _I64, _P]),
     "ncf_shard_owner_rows": (C.c_int, [C.POINTER(Tables), _P, _I32, _P, _I64, _P, _P]),
     "ncf_shard_forward": (C.c_int, [C.POINTER(RunCfg), _P, _P, _P, _P, _P, _I64, _P, _P, _I64, _P]),
     "ncf_shard_backward": (C.c_int, [C.POINTER(RunCfg), _P, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _P, _I64, _P]),

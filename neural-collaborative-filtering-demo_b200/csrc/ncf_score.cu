@@ -8,6 +8,7 @@
 // in shared memory: candidates that beat the current k-th best are appended to a buffer that is
 // bitonic-merged into the running list when it fills up.
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include "ncf_tower.cuh"
 
@@ -387,6 +388,45 @@ __global__ void bucket_finish_kernel(const int64_t* __restrict__ ids, const uint
   }
 }
 
+// ---- bucketize with adjacent-run compression (ncf_shard_bucketize_runs) --------------------------------
+// Training batches repeat the user id over the S rows of an interaction (data_prep.py:286-303): equal ADJACENT
+// ids are served by one exchanged row.  A sample is a run head when its id differs from its predecessor's;
+// heads are bucketed by owner (stable), the other samples go to an extra bucket `world` that is never sent.
+__global__ void run_keys_kernel(const int64_t* __restrict__ ids, int64_t n, int64_t block, uint32_t world,
+                                uint32_t* __restrict__ keys, int32_t* __restrict__ vals, int32_t* __restrict__ head_idx) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const bool head = i == 0 || ids[i] != ids[i - 1];
+    keys[i] = head ? (uint32_t)(ids[i] / block) : world;
+    vals[i] = (int32_t)i;
+    head_idx[i] = head ? (int32_t)i : 0;      // inclusive max-scan -> index of the run head of every sample
+  }
+}
+__global__ void run_finish_kernel(const int64_t* __restrict__ ids, const uint32_t* __restrict__ skeys,
+                                  const int32_t* __restrict__ svals, int64_t n, int64_t block, int world,
+                                  int64_t* __restrict__ counts, int64_t* __restrict__ local_ids,
+                                  int32_t* __restrict__ slot_of_head) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && skeys[i] < (uint32_t)world) {
+    const int64_t src = svals[i];
+    local_ids[i] = ids[src] % block;
+    slot_of_head[src] = (int32_t)i;
+  }
+  if (i < world) {   // counts[w] = upper_bound(w) - lower_bound(w) in the sorted keys
+    int64_t lo = 0, hi = n;
+    while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (skeys[mid] < (uint32_t)i) lo = mid + 1; else hi = mid; }
+    const int64_t lb = lo;
+    hi = n;
+    while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (skeys[mid] <= (uint32_t)i) lo = mid + 1; else hi = mid; }
+    counts[i] = lo - lb;
+  }
+}
+__global__ void run_pos_kernel(const int32_t* __restrict__ head_idx, const int32_t* __restrict__ slot_of_head, int64_t n,
+                               int64_t* __restrict__ pos) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) pos[i] = slot_of_head[head_idx[i]];
+}
+
 }  // namespace ncf
 
 using namespace ncf;
@@ -562,6 +602,68 @@ extern "C" int ncf_shard_bucketize(const int64_t* ids, int64_t n, int64_t rows, 
   const int64_t threads = std::max<int64_t>(n, world);
   bucket_finish_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(ids, b.keys_out, b.vals_out, n, block, world,
                                                                            counts, order, local_ids);
+  NCF_LAUNCH_CHECK();
+  return NCF_OK;
+}
+
+struct RunBucketWs {
+  uint32_t *keys_in, *keys_out;
+  int32_t *vals_in, *vals_out, *head_idx, *slot_of_head;
+  void* cub_tmp;
+  size_t cub_bytes;
+  int64_t total;
+};
+static RunBucketWs carve_run_bucket(void* ws, int64_t n) {
+  RunBucketWs b;
+  Carver c(ws);
+  b.keys_in = c.take<uint32_t>(n);
+  b.keys_out = c.take<uint32_t>(n);
+  b.vals_in = c.take<int32_t>(n);
+  b.vals_out = c.take<int32_t>(n);
+  b.head_idx = c.take<int32_t>(n);
+  b.slot_of_head = c.take<int32_t>(n);
+  size_t sort_bytes = 0, scan_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const int32_t*)nullptr,
+                                  (int32_t*)nullptr, (int)std::max<int64_t>(n, 1), 0, 32);
+  cub::DeviceScan::InclusiveScan(nullptr, scan_bytes, (int32_t*)nullptr, (int32_t*)nullptr, cub::Max(), (int)std::max<int64_t>(n, 1));
+  b.cub_bytes = std::max(sort_bytes, scan_bytes);
+  b.cub_tmp = c.take<char>((int64_t)b.cub_bytes);
+  b.total = align_up(c.used, 256);
+  return b;
+}
+
+extern "C" int64_t ncf_shard_bucketize_runs_workspace_bytes(int64_t n, int32_t world) {
+  (void)world;
+  return carve_run_bucket(nullptr, std::max<int64_t>(n, 1)).total;
+}
+
+extern "C" int ncf_shard_bucketize_runs(const int64_t* ids, int64_t n, int64_t rows, int32_t world, int64_t* counts,
+                                        int64_t* local_ids, int64_t* pos, void* workspace, int64_t workspace_bytes,
+                                        void* stream) {
+  NCF_REQUIRE(ids && counts && local_ids && pos && workspace, "shard_bucketize_runs: null argument");
+  NCF_REQUIRE(world >= 1 && world <= 1024 && rows >= 1, "shard_bucketize_runs: bad world/rows");
+  NCF_REQUIRE(n >= 0 && n < ((int64_t)1 << 31), "shard_bucketize_runs: bad n");
+  cudaStream_t st = (cudaStream_t)stream;
+  NCF_CUDA(cudaMemsetAsync(counts, 0, sizeof(int64_t) * world, st));
+  if (n == 0) return NCF_OK;
+  RunBucketWs b = carve_run_bucket(workspace, n);
+  if (workspace_bytes < b.total) {
+    set_error("shard_bucketize_runs: workspace %lld < %lld", (long long)workspace_bytes, (long long)b.total);
+    return NCF_ERR_WORKSPACE;
+  }
+  const int64_t block = (rows + world - 1) / world;
+  const unsigned grid = (unsigned)((std::max<int64_t>(n, world) + 255) / 256);
+  run_keys_kernel<<<grid, 256, 0, st>>>(ids, n, block, (uint32_t)world, b.keys_in, b.vals_in, b.head_idx);
+  NCF_LAUNCH_CHECK();
+  size_t tmp = b.cub_bytes;
+  NCF_CUDA(cub::DeviceScan::InclusiveScan(b.cub_tmp, tmp, b.head_idx, b.head_idx, cub::Max(), (int)n, st));
+  int bits = 1;
+  while ((1 << bits) < world + 1) ++bits;
+  tmp = b.cub_bytes;
+  NCF_CUDA(cub::DeviceRadixSort::SortPairs(b.cub_tmp, tmp, b.keys_in, b.keys_out, b.vals_in, b.vals_out, (int)n, 0, bits, st));
+  run_finish_kernel<<<grid, 256, 0, st>>>(ids, b.keys_out, b.vals_out, n, block, world, counts, local_ids, b.slot_of_head);
+  NCF_LAUNCH_CHECK();
+  run_pos_kernel<<<grid, 256, 0, st>>>(b.head_idx, b.slot_of_head, n, pos);
   NCF_LAUNCH_CHECK();
   return NCF_OK;
 }

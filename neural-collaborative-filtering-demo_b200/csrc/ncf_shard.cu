@@ -58,9 +58,11 @@ __global__ void __launch_bounds__(256) gmf_from_rows_kernel(const float* __restr
   }
 }
 
-// requester backward: upstream gradient rows per sample, written at the owner-order position.
-//   gu[pos_u[n]] = [ d_mf[n] * w_mf * y_item_mf[n] | dxu[n] ]     gi[pos_i[n]] = [ d_mf[n] * w_mf * y_user_mf[n] | dxp[n] ]
-// and d mf_output.weight += sum_n d_mf[n] * y_user_mf[n] * y_item_mf[n]
+// requester backward: upstream gradient rows, one per EXCHANGED row (= run of adjacent samples that share it,
+// ncf_shard_bucketize_runs), written at the owner-order position:
+//   gu[p] = [ sum_j d_mf[j] * w_mf * y_item_mf[j] | sum_j dxu[j] ]  over the samples j of the run with pos_u[j] == p
+//   gi[p] likewise with the user rows, and d mf_output.weight += sum_n d_mf[n] * y_user_mf[n] * y_item_mf[n].
+// Half warp = (first sample of a run, side); the samples of a run are adjacent, so the sum is a short loop.
 __global__ void __launch_bounds__(256) pack_grads_kernel(const float* __restrict__ rows_u, const float* __restrict__ rows_i,
                                                          const int64_t* __restrict__ pos_u, const int64_t* __restrict__ pos_i,
                                                          const float* __restrict__ dense, const float* __restrict__ d_mf,
@@ -72,18 +74,28 @@ __global__ void __launch_bounds__(256) pack_grads_kernel(const float* __restrict
   const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + warpi;
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
   const float4 w_out = ldg4(dense + NCF_OFF(NCF_P_MF_OUT_W) + 4 * l16);
+  const int64_t* pos_mine = half ? pos_i : pos_u;
+  const int64_t* pos_other = half ? pos_u : pos_i;
+  const float* rows_mine = half ? rows_i : rows_u;
+  const float* rows_other = half ? rows_u : rows_i;
+  const float* dx = half ? dxp : dxu;
+  float* dst = half ? gi : gu;
   float4 dw = make_float4(0, 0, 0, 0);
   for (int64_t n = warp; n < N; n += nwarps) {
-    const int64_t pu = pos_u[n], pi = pos_i[n];
-    const float4 y_mine = ldg4((half ? rows_i + pi * 2 * D : rows_u + pu * 2 * D) + 4 * l16);
-    const float4 y_other = make_float4(__shfl_xor_sync(0xffffffffu, y_mine.x, 16), __shfl_xor_sync(0xffffffffu, y_mine.y, 16),
-                                       __shfl_xor_sync(0xffffffffu, y_mine.z, 16), __shfl_xor_sync(0xffffffffu, y_mine.w, 16));
-    const float g = d_mf[n];
-    const float4 t = make_float4(g * y_other.x, g * y_other.y, g * y_other.z, g * y_other.w);
-    float* dst = half ? gi + pi * 2 * D : gu + pu * 2 * D;
-    st4(dst + 4 * l16, f4_mul(t, w_out));
-    st4(dst + D + 4 * l16, ldg4((half ? dxp : dxu) + n * D + 4 * l16));
-    if (half == 0) dw = f4_add(dw, f4_mul(t, y_mine));
+    const int64_t p = pos_mine[n];
+    if (n > 0 && pos_mine[n - 1] == p) continue;            // not the first sample of its run (uniform per half warp)
+    const float4 y_mine = ldg4(rows_mine + p * 2 * D + 4 * l16);
+    float4 a_mf = make_float4(0, 0, 0, 0), a_ml = a_mf;
+    for (int64_t j = n; j < N && pos_mine[j] == p; ++j) {
+      const float4 y_other = ldg4(rows_other + pos_other[j] * 2 * D + 4 * l16);
+      const float g = d_mf[j];
+      const float4 t = make_float4(g * y_other.x, g * y_other.y, g * y_other.z, g * y_other.w);
+      a_mf = f4_add(a_mf, f4_mul(t, w_out));
+      a_ml = f4_add(a_ml, ldg4(dx + j * D + 4 * l16));
+      if (half == 0) dw = f4_add(dw, f4_mul(t, y_mine));
+    }
+    st4(dst + p * 2 * D + 4 * l16, a_mf);
+    st4(dst + p * 2 * D + D + 4 * l16, a_ml);
   }
   if (half == 0) {
     s_red[warpi][4 * l16 + 0] = dw.x; s_red[warpi][4 * l16 + 1] = dw.y;

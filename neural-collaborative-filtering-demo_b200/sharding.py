@@ -60,20 +60,35 @@ class ShardRouter:
         self.recv_counts: List[int] = []
 
     def exchange_ids(self, local_ids_owner_major: torch.Tensor, counts: torch.Tensor) -> torch.Tensor:
-        """counts[w] ids go to rank w (ids already in owner-major order); returns the ids this rank
-        must serve, grouped by requesting rank."""
-        if self.world == 1:
-            self.send_counts = [int(local_ids_owner_major.numel())]
-            self.recv_counts = list(self.send_counts)
-            return local_ids_owner_major
+        """counts[w] ids go to rank w (the first sum(counts) entries of the owner-major id buffer); returns the
+        ids this rank must serve, grouped by requesting rank."""
+        return ShardRouter.exchange_ids_multi([self], [(local_ids_owner_major, counts)])[0]
+
+    @staticmethod
+    def exchange_ids_multi(routers, plans):
+        """The id exchange of several sides at once: ONE all-to-all of all the counts and one host sync (the split
+        sizes), then the id all-to-alls are launched back to back."""
+        first = routers[0]
+        counts = torch.stack([c for _, c in plans], dim=1).contiguous()              # [world, sides]
+        if first.world == 1:
+            tot = counts.cpu()[0].tolist()
+            for r, n in zip(routers, tot):
+                r.send_counts, r.recv_counts = [int(n)], [int(n)]
+            return [ids[:int(n)] for (ids, _), n in zip(plans, tot)]
         recv = torch.empty_like(counts)
-        dist.all_to_all_single(recv, counts, group=self.group)
-        both = torch.stack([counts, recv]).cpu()          # the one host sync of the side: split sizes
-        self.send_counts = both[0].tolist()
-        self.recv_counts = both[1].tolist()
-        out = local_ids_owner_major.new_empty(sum(self.recv_counts))
-        dist.all_to_all_single(out, local_ids_owner_major, self.recv_counts, self.send_counts, group=self.group)
-        return out
+        dist.all_to_all_single(recv, counts, group=first.group)
+        both = torch.stack([counts, recv]).cpu()                                      # the one host sync of the step
+        outs, works = [], []
+        for k, (r, (ids, _)) in enumerate(zip(routers, plans)):
+            r.send_counts = both[0, :, k].tolist()
+            r.recv_counts = both[1, :, k].tolist()
+            out = ids.new_empty(sum(r.recv_counts))
+            works.append(dist.all_to_all_single(out, ids[:sum(r.send_counts)], r.recv_counts, r.send_counts, group=r.group,
+                                                async_op=True))
+            outs.append(out)
+        for w in works:
+            w.wait()
+        return outs
 
     def return_rows(self, rows: torch.Tensor) -> torch.Tensor:
         """owner -> requester: rows [sum(recv_counts), W] come back in the order the ids were sent."""
@@ -82,6 +97,21 @@ class ShardRouter:
         out = rows.new_empty((sum(self.send_counts),) + tuple(rows.shape[1:]))
         dist.all_to_all_single(out, rows, self.send_counts, self.recv_counts, group=self.group)
         return out
+
+    @staticmethod
+    def exchange_rows_multi(routers, rows_list, to_owner: bool):
+        """return_rows (to_owner=False) / send_rows (to_owner=True) of several sides launched back to back."""
+        if routers[0].world == 1:
+            return list(rows_list)
+        outs, works = [], []
+        for r, rows in zip(routers, rows_list):
+            out_counts, in_counts = (r.recv_counts, r.send_counts) if to_owner else (r.send_counts, r.recv_counts)
+            out = rows.new_empty((sum(out_counts),) + tuple(rows.shape[1:]))
+            works.append(dist.all_to_all_single(out, rows, out_counts, in_counts, group=r.group, async_op=True))
+            outs.append(out)
+        for w in works:
+            w.wait()
+        return outs
 
     def send_rows(self, rows: torch.Tensor) -> torch.Tensor:
         """requester -> owner: rows [sum(send_counts), W] in owner-major order (gradient rows)."""
@@ -171,21 +201,21 @@ class ShardedNCFEngine:
 
     # ---- phases (the emulated-cluster test drives these one by one) -----------------------------
     def phase_bucketize(self, user_ids, item_ids):
-        """requester: owner-major local ids + per-owner counts + the position of every sample."""
+        """requester: owner-major local ids of the run heads (adjacent equal ids are exchanged once: the user id is
+        repeated over the S rows of an interaction) + per-owner counts + the exchanged-row position of every sample."""
         self.step += 1
         self.N = user_ids.numel()
         self._plan = []
         for ids, rows in ((user_ids, self.U), (item_ids, self.I)):
             n = ids.numel()
             counts = torch.empty(self.world, dtype=torch.long, device=self.device)
-            order = torch.empty(n, dtype=torch.long, device=self.device)
             local = torch.empty(n, dtype=torch.long, device=self.device)
-            nbytes = int(self.lib.ncf_shard_bucketize_workspace_bytes(n, self.world))
+            pos = torch.empty(n, dtype=torch.long, device=self.device)
+            nbytes = int(self.lib.ncf_shard_bucketize_runs_workspace_bytes(n, self.world))
             ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
-            _lib.check(self.lib.ncf_shard_bucketize(_lib.ptr(ids), n, rows, self.world, _lib.ptr(counts), _lib.ptr(order),
-                                                    _lib.ptr(local), _lib.ptr(ws), nbytes, self._s()), "ncf_shard_bucketize")
-            pos = torch.empty_like(order)
-            pos[order] = torch.arange(n, device=self.device)
+            _lib.check(self.lib.ncf_shard_bucketize_runs(_lib.ptr(ids), n, rows, self.world, _lib.ptr(counts), _lib.ptr(local),
+                                                         _lib.ptr(pos), _lib.ptr(ws), nbytes, self._s()),
+                       "ncf_shard_bucketize_runs")
             self._plan.append((counts, local, pos))
         return [(p[1], p[0]) for p in self._plan]        # [(local ids owner-major, counts)] per side
 
@@ -220,8 +250,8 @@ class ShardedNCFEngine:
         grad_out.mul_(scale)
         self.loss.mul_(scale)
         self.dense_grad.zero_()
-        gu = torch.empty(N, 128, device=self.device)
-        gi = torch.empty(N, 128, device=self.device)
+        gu = torch.empty(rows[0].shape[0], 128, device=self.device)     # one gradient row per exchanged row
+        gi = torch.empty(rows[1].shape[0], 128, device=self.device)
         _lib.check(self.lib.ncf_shard_backward(C.byref(cfg), _lib.ptr(flat), _lib.ptr(self.dense_grad), _lib.ptr(rows[0]),
                                                _lib.ptr(rows[1]), _lib.ptr(pos_u), _lib.ptr(pos_i), N, _lib.ptr(grad_out),
                                                _lib.ptr(gu), _lib.ptr(gi), _lib.ptr(ws), nbytes, self._s()),
@@ -254,18 +284,45 @@ class ShardedNCFEngine:
     def train_step(self, user_ids: torch.Tensor, item_ids: torch.Tensor, targets: torch.Tensor) -> torch.Tensor:
         """Global ids int64 [N] and targets fp32 [N] of THIS rank's batch (device tensors).  Returns the
         global mean loss (device scalar, identical on all ranks)."""
+        mark = self._mark
+        mark(None)
         plan = self.phase_bucketize(user_ids, item_ids)
-        served = [self.routers[s].exchange_ids(*plan[s]) for s in (0, 1)]
+        mark("bucketize")
+        served = ShardRouter.exchange_ids_multi(self.routers, plan)
+        mark("a2a ids")
         rows_out = self.phase_owner_rows(served)
-        rows = [self.routers[s].return_rows(rows_out[s]) for s in (0, 1)]
+        mark("owner rows")
+        rows = ShardRouter.exchange_rows_multi(self.routers, rows_out, to_owner=False)
+        mark("a2a rows")
         grads = self.phase_forward_backward(rows, targets, self.N * self.world)
-        recv = [self.routers[s].send_rows(grads[s]) for s in (0, 1)]
+        mark("forward+backward")
+        recv = ShardRouter.exchange_rows_multi(self.routers, grads, to_owner=True)
+        mark("a2a grads")
         self.phase_owner_update(recv)
+        mark("owner update")
         if self.world > 1:
             dist.all_reduce(self.dense_grad, group=self.group)
             dist.all_reduce(self.loss, group=self.group)
         self.phase_dense_adam()
+        mark("dense allreduce+adam")
         return self.loss
+
+    # NCF_SHARD_PROFILE=1: CUDA-event time of every phase, summed over the steps (bench.py prints it to stderr)
+    def _mark(self, name):
+        if not os.environ.get("NCF_SHARD_PROFILE"):
+            return
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        if name is None:
+            self._ev = [(None, ev)]
+        else:
+            self._ev.append((name, ev))
+        if name == "dense allreduce+adam":
+            torch.cuda.synchronize()
+            prof = self.__dict__.setdefault("phase_ms", {})
+            for (_, a), (n, b) in zip(self._ev[:-1], self._ev[1:]):
+                prof[n] = prof.get(n, 0.0) + a.elapsed_time(b)
+            prof["steps"] = prof.get("steps", 0) + 1
 
     # ---- sharded checkpoints (SURVEY 8f N4) -------------------------------------------------------
     def save_checkpoint(self, directory: str) -> None:

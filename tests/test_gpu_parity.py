@@ -374,6 +374,38 @@ def test_shard_bucketize_bit_exact():
         assert torch.equal(counts.cpu(), torch.bincount(owner, minlength=world))
 
 
+def test_shard_bucketize_runs_bit_exact():
+    """Adjacent-run compression: only the first sample of a run of equal adjacent ids is exchanged; every sample
+    points at its run's slot.  Checked against torch.unique_consecutive + a stable argsort by owner."""
+    from ncf_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(5)
+    cases = [(torch.randint(0, 10, (1,), generator=g), 10, 2),
+             (torch.randint(0, 100, (200,), generator=g).repeat_interleave(5), 100, 8),          # training layout (users)
+             (torch.randint(0, 138493, (4097,), generator=g), 138493, 8),                       # no repeats (items)
+             (torch.randint(0, 3, (513,), generator=g), 7, 4),                                  # long runs
+             (torch.zeros(300, dtype=torch.long), 5, 3)]                                        # a single run
+    for ids, rows, world in cases:
+        n = ids.numel()
+        d = ids.cuda()
+        counts = torch.empty(world, dtype=torch.long, device="cuda")
+        local = torch.full((n,), -1, dtype=torch.long, device="cuda")
+        pos = torch.empty(n, dtype=torch.long, device="cuda")
+        nbytes = int(lib.ncf_shard_bucketize_runs_workspace_bytes(n, world))
+        ws = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+        _lib.check(lib.ncf_shard_bucketize_runs(_lib.ptr(d), n, rows, world, _lib.ptr(counts), _lib.ptr(local), _lib.ptr(pos),
+                                                _lib.ptr(ws), nbytes, None))
+        heads, inverse = torch.unique_consecutive(ids, return_inverse=True)
+        owner, loc, block = O.row_shard(heads, rows, world)
+        order = torch.argsort(owner, stable=True)                 # owner-major order of the run heads
+        slot = torch.empty_like(order)
+        slot[order] = torch.arange(order.numel())
+        nr = heads.numel()
+        assert torch.equal(counts.cpu(), torch.bincount(owner, minlength=world))
+        assert torch.equal(local.cpu()[:nr], loc[order])
+        assert torch.equal(pos.cpu(), slot[inverse])
+
+
 def test_errors_are_loud():
     import ncf_b200
     p, _ = golden_params()
