@@ -454,9 +454,9 @@ def main():
     value = world * N * args.steps / (ms_total / 1e3)
     e2e_value = world * N * args.steps / (e2e_ms_total / 1e3)
 
-    if rank == 0 and getattr(eng, "phase_ms", None):
+    if getattr(eng, "phase_ms", None):
         n = eng.phase_ms.pop("steps")
-        sys.stderr.write("sharded phases, ms per step (rank 0): " + ", ".join(f"{k} {v / n:.3f}" for k, v in eng.phase_ms.items()) + "\n")
+        sys.stderr.write(f"sharded phases, ms per step (rank {rank}): " + ", ".join(f"{k} {v / n:.3f}" for k, v in eng.phase_ms.items()) + "\n")
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
