@@ -257,6 +257,16 @@ NCF_API int ncf_shard_bucketize_runs(const int64_t* ids, int64_t n, int64_t rows
                              int64_t* counts, int64_t* local_ids, int64_t* pos,
                              void* workspace, int64_t workspace_bytes, void* stream);
 
+/* Full de-duplication of BOTH sides with one radix sort: every distinct id of the batch is exchanged once.
+ * counts [2][world] (side-major) = distinct ids per owner; local_ids [2][N]: the distinct ids' local ids in
+ * owner-major (= ascending id) order, first sum(counts[side]) entries of each half valid; pos [2][N] =
+ * index of every sample's id in that order.  route_ws keeps the sorted ids for ncf_shard_backward. */
+NCF_API int64_t ncf_shard_route_workspace_bytes(int64_t N);
+NCF_API int ncf_shard_route(const int64_t* user_ids, const int64_t* item_ids, int64_t N,
+                    int64_t rows_user, int64_t rows_item, int32_t world,
+                    int64_t* counts, int64_t* local_ids, int64_t* pos,
+                    void* route_ws, int64_t route_ws_bytes, void* stream);
+
 /* ---- row-sharded step: owner-side and requester-side halves ------------------- */
 /* owner: rows [n,128] = [mf_norm(T_mf[id]) | mlp_norm(T_mlp[id])] of its LOCAL ids for one side. */
 NCF_API int ncf_shard_owner_rows(const ncf_tables* local_tables, const float* dense, int32_t side,
@@ -268,12 +278,13 @@ NCF_API int ncf_shard_forward(const ncf_run_cfg* cfg, const float* dense, const 
                       void* workspace, int64_t workspace_bytes, void* stream);
 /* requester: backward; writes ONE upstream gradient row [128] = [d/d mf_norm row | d/d mlp_norm row] per
  * exchanged row at its owner-order position (samples that share a position must be adjacent, as
- * ncf_shard_bucketize_runs arranges: their gradients are summed here) and accumulates the dense
+ * ncf_shard_bucketize_runs arranges: their gradients are summed here; or anywhere in the batch when
+ * route_ws = the buffer ncf_shard_route filled for this batch, NULL otherwise) and accumulates the dense
  * gradients (except the LayerNorm affine gradients of mf_norm / mlp_norm, which the owners add). */
 NCF_API int ncf_shard_backward(const ncf_run_cfg* cfg, const float* dense, float* dense_grad,
                        const float* rows_u, const float* rows_i, const int64_t* pos_u, const int64_t* pos_i,
                        int64_t N, const float* grad_out, float* grad_rows_u, float* grad_rows_i,
-                       void* workspace, int64_t workspace_bytes, void* stream);
+                       const void* route_ws, void* workspace, int64_t workspace_bytes, void* stream);
 /* owner: sorted-id segment sum of the received gradient rows, LayerNorm backward once per unique
  * local id, fused Adam (adam->emb_mode as in ncf_backward); workspace: ncf_emb_bwd_workspace_bytes(n). */
 NCF_API int ncf_shard_owner_update(const ncf_adam_cfg* adam, const ncf_tables* local_tables, const float* dense,

@@ -94,7 +94,9 @@ _SIGS = {
     "ncf_shard_bucketize_runs": (C.c_int, [_P, _I64, _I64, _I32, _P, _P, _P, _P, _I64, _P]),
     "ncf_shard_owner_rows": (C.c_int, [C.POINTER(Tables), _P, _I32, _P, _I64, _P, _P]),
     "ncf_shard_forward": (C.c_int, [C.POINTER(RunCfg), _P, _P, _P, _P, _P, _I64, _P, _P, _I64, _P]),
-    "ncf_shard_backward": (C.c_int, [C.POINTER(RunCfg), _P, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _P, _I64, _P]),
+    "ncf_shard_backward": (C.c_int, [C.POINTER(RunCfg), _P, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _I64, _P]),
+    "ncf_shard_route_workspace_bytes": (_I64, [_I64]),
+    "ncf_shard_route": (C.c_int, [_P, _P, _I64, _I64, _I64, _I32, _P, _P, _P, _P, _I64, _P]),
     "ncf_sample_batch": (C.c_int, [_P, _P, _I64, _I32, _P, _I64, _P, _P, C.c_uint64, C.c_uint64, _P, _P, _P, _P]),
     "ncf_tc_selftest": (C.c_int, [_I32, _I32, _I32, _P, _P, _P, _P]),
     "ncf_shard_owner_update": (C.c_int, [C.POINTER(AdamCfg), C.POINTER(Tables), _P, _P, _I32, _P, _I64, _P, _P, _I64, _P]),

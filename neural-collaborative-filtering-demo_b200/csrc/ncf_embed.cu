@@ -4,6 +4,7 @@
 // 128-bit vectors by half warps (16 lanes x 16 B = one row), id blocks staged into shared memory
 // by cp.async.bulk (TMA bulk copy) with an mbarrier, reductions by warp shuffles.
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include "ncf_common.cuh"
 
@@ -243,6 +244,13 @@ struct EmbBwdArgs {
   const float* other_y;           // [N,64] LN'd MF row of the other side saved by the forward (or null)
   const float* own_y;             // [N,64] LN'd MF row of THIS side saved by the forward (or null): d mf_output.weight
   const float* upstream;          // sharded owner path: [N,128] ready-made upstream rows [mf | mlp] (or null)
+  // sharded requester path: the LN'd rows live in the exchanged row buffers [n_unique,128] = [mf | mlp]
+  const float* other_rows;        // other side's exchanged rows (or null)
+  const int64_t* other_pos;       // [N] exchanged-row index of each sample on the other side
+  const float* own_rows;          // this side's exchanged rows (d mf_output.weight)
+  const int64_t* own_pos;
+  float* out_rows;                // phase 2 output mode: [n_unique,128] summed upstream row per unique id, no update
+  const int32_t* out_slot;        // [N] unique-id index of every sorted position
   const int64_t* other_ids;       // other side's ids, original sample order
   const uint32_t* sorted_ids;     // this side's ids, sorted
   const int32_t* perm;            // sample row of each sorted position
@@ -307,8 +315,13 @@ __global__ void __launch_bounds__(EB_THREADS, 3) emb_bwd_phase1_kernel(EmbBwdArg
     const int32_t my_row = lane < cnt ? A.perm[p0 + lane] : 0;
     int64_t my_other = 0;
     float my_dmf = 0.f;
+    int64_t my_own = 0;
     if (lane < cnt && !A.upstream) {
-      if (A.other_sorted) {
+      if (A.other_rows) {
+        my_other = A.other_pos[my_row];
+        my_own = A.own_pos[my_row];
+        my_dmf = A.d_mf_pred[my_row];
+      } else if (A.other_sorted) {
         my_other = A.other_sorted[p0 + lane];
         my_dmf = A.dmf_sorted[p0 + lane];
       } else {
@@ -333,9 +346,11 @@ __global__ void __launch_bounds__(EB_THREADS, 3) emb_bwd_phase1_kernel(EmbBwdArg
         idk[u] = __shfl_sync(0xffffffffu, my_id, kk);
         const float* src = A.upstream ? A.upstream + (int64_t)row * 2 * D + half * D
                            : half ? A.d_x + (int64_t)row * D
+                           : A.other_rows ? A.other_rows + oid * 2 * D
                                   : (A.other_y ? A.other_y + (int64_t)row * D : A.other_mf + oid * D);
         x[u] = ldg4(src + 4 * l16);
         sf[u] = !wmf ? make_float4(0, 0, 0, 0)                    // own MF row (d mf_output.weight): saved LN'd row or table row
+                : A.own_rows ? ldg4(A.own_rows + __shfl_sync(0xffffffffu, my_own, kk) * 2 * D + 4 * l16)
                 : A.own_y ? ldg4(A.own_y + (int64_t)row * D + 4 * l16)
                           : ld4(A.w[0] + (int64_t)(idk[u] - A.id_off) * D + 4 * l16);
       }
@@ -351,9 +366,10 @@ __global__ void __launch_bounds__(EB_THREADS, 3) emb_bwd_phase1_kernel(EmbBwdArg
           // the LayerNorms use full-warp shuffles: every lane runs them, only half 0 keeps the result
           float rs;
           float4 yo = x[u];
-          if (!A.other_y && !A.upstream) yo = affine(ln_normalise(x[u], rs), g_mf, b_mf);   // LN of the other side's MF row
+          const bool ready = A.other_y || A.upstream || A.other_rows;     // the rows are LayerNorm-ed already
+          if (!ready) yo = affine(ln_normalise(x[u], rs), g_mf, b_mf);   // LN of the other side's MF row
           float4 ys = make_float4(0, 0, 0, 0);
-          if (wmf) ys = A.own_y ? sf[u] : affine(ln_normalise(sf[u], rs), g_mf, b_mf);
+          if (wmf) ys = (A.own_y || A.own_rows) ? sf[u] : affine(ln_normalise(sf[u], rs), g_mf, b_mf);
           if (half || A.upstream) {
             acc = f4_add(acc, x[u]);
           } else {
@@ -401,10 +417,11 @@ __global__ void __launch_bounds__(EB_THREADS, 3) emb_bwd_phase2_kernel(EmbBwdArg
     auto issue = [&](int i, uint32_t id) {
       Loads L;
       const int64_t o = (int64_t)(id - A.id_off) * D + 4 * l16;
-      L.w = ld4(A.w[half] + o);
       L.m = make_float4(0, 0, 0, 0);
       L.v = L.m;
-      if (adam) {
+      L.w = L.m;
+      if (!A.out_rows) L.w = ld4(A.w[half] + o);
+      if (adam && !A.out_rows) {
         L.m = ld4(A.m[half] + o);
         L.v = ld4(A.v[half] + o);
       }
@@ -436,7 +453,6 @@ __global__ void __launch_bounds__(EB_THREADS, 3) emb_bwd_phase2_kernel(EmbBwdArg
       const float4 wrow = cur.w;
       float4 mm = cur.m, vv = cur.v;
       float4 acc = cur.a;
-      (void)i;
       // does the run leave this chunk?  (its last in-chunk element is the chunk's last element)
       const uint32_t last_id = __shfl_sync(0xffffffffu, my_id, cnt - 1);
       if (last_id == id) {
@@ -461,6 +477,10 @@ __global__ void __launch_bounds__(EB_THREADS, 3) emb_bwd_phase2_kernel(EmbBwdArg
           }
           cs += 4 * EB_CHUNK;
         }
+      }
+      if (A.out_rows) {        // sharded requester: the summed upstream row of this unique id goes to the exchange buffer
+        st4(A.out_rows + (int64_t)A.out_slot[p0 + i] * 2 * D + half * D + 4 * l16, acc);
+        continue;
       }
       float rstd;
       const float4 xhat = ln_normalise(wrow, rstd);
@@ -707,6 +727,10 @@ static int run_emb_bwd(const ncf_adam_cfg* adam, const ncf_tables* T, const floa
   A.other_mf = T->w[side ? 0 : 1];
   A.other_y = other_y_mf;
   A.own_y = nullptr;
+  A.other_rows = A.own_rows = nullptr;
+  A.other_pos = A.own_pos = nullptr;
+  A.out_rows = nullptr;
+  A.out_slot = nullptr;
   A.upstream = upstream;
   A.other_ids = other_ids;
   A.sorted_ids = w.keys_out;
@@ -807,6 +831,10 @@ int emb_bwd_both(const ncf_adam_cfg* adam, const ncf_tables* T, const float* den
     A.other_mf = T->w[side ? 0 : 1];
     A.other_y = side ? y_user_mf : y_item_mf;       // null: gather the other side's table row and LayerNorm it again
     A.own_y = side ? nullptr : y_user_mf;
+    A.other_rows = A.own_rows = nullptr;
+    A.other_pos = A.own_pos = nullptr;
+    A.out_rows = nullptr;
+    A.out_slot = nullptr;
     A.upstream = nullptr;
     A.other_ids = side ? user_ids : item_ids;
     A.sorted_ids = w.keys_out + (side ? N : 0);
@@ -850,6 +878,149 @@ extern "C" int ncf_emb_bwd_adam(const ncf_adam_cfg* adam, const ncf_tables* T, c
   NCF_REQUIRE(adam && T && dense && user_ids && item_ids && d_mf_pred && d_x, "emb_bwd_adam: null argument");
   return run_emb_bwd(adam, T, dense, dense_grad, side, side ? item_ids : user_ids, side ? user_ids : item_ids, N,
                      d_mf_pred, d_x, other_y_mf, nullptr, workspace, workspace_bytes, stream);
+}
+
+// =============================================================================================
+// Sharded requester: full de-duplication of the ids a rank asks for.  ONE radix sort of both sides
+// (sorted ids are owner-major already: owner = id / block is monotonic in the id): every distinct id is exchanged
+// once, pos[n] points each sample at its row, and the backward sums the per-sample upstream gradients per distinct
+// id with the K6 segment-sum kernels before they travel (deterministic order, no atomics on the rows).
+// =============================================================================================
+namespace ncf {
+struct RouteWs {
+  uint32_t *keys_in, *keys_out;
+  int32_t *vals_in, *vals_out, *slot, *incl;   // keys_out / vals_out / slot stay valid for the backward
+  void* cub_tmp;
+  size_t cub_bytes;
+  int64_t total;
+};
+static RouteWs carve_route_ws(void* ws, int64_t N) {
+  RouteWs w;
+  Carver c(ws);
+  w.keys_out = c.take<uint32_t>(2 * N);
+  w.vals_out = c.take<int32_t>(2 * N);
+  w.slot = c.take<int32_t>(2 * N);
+  w.incl = c.take<int32_t>(2 * N);
+  w.keys_in = c.take<uint32_t>(2 * N);
+  w.vals_in = c.take<int32_t>(2 * N);
+  size_t sort_bytes = 0, scan_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const int32_t*)nullptr,
+                                  (int32_t*)nullptr, (int)std::max<int64_t>(2 * N, 1), 0, 32);
+  cub::DeviceScan::InclusiveSum(nullptr, scan_bytes, (int32_t*)nullptr, (int32_t*)nullptr, (int)std::max<int64_t>(2 * N, 1));
+  w.cub_bytes = std::max(sort_bytes, scan_bytes);
+  w.cub_tmp = c.take<char>((int64_t)w.cub_bytes);
+  w.total = align_up(c.used, 256);
+  return w;
+}
+
+__global__ void route_flags_kernel(const uint32_t* __restrict__ skeys, int64_t N, int32_t* __restrict__ flag) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < 2 * N) flag[p] = (p == 0 || p == N || skeys[p] != skeys[p - 1]) ? 1 : 0;
+}
+// incl = inclusive sum of the head flags over both sides; slot = index of the distinct id inside its side
+__global__ void route_finish_kernel(const uint32_t* __restrict__ skeys, const int32_t* __restrict__ perm,
+                                    const int32_t* __restrict__ incl, int64_t N, uint32_t item_off, int64_t block_u,
+                                    int64_t block_i, int world, int32_t* __restrict__ slot,
+                                    unsigned long long* __restrict__ counts, int64_t* __restrict__ local_ids,
+                                    int64_t* __restrict__ pos) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= 2 * N) return;
+  const int side = p >= N;
+  const int32_t s = incl[p] - 1 - (side ? __ldg(incl + N - 1) : 0);
+  slot[p] = s;
+  pos[(int64_t)side * N + perm[p]] = s;
+  const bool head = p == 0 || p == N || skeys[p] != skeys[p - 1];
+  if (head) {
+    const int64_t id = (int64_t)skeys[p] - (side ? item_off : 0u);
+    const int64_t block = side ? block_i : block_u;
+    local_ids[(int64_t)side * N + s] = id % block;
+    atomicAdd(counts + side * world + (int)(id / block), 1ull);
+  }
+}
+
+int64_t shard_route_ws_bytes(int64_t N) { return carve_route_ws(nullptr, std::max<int64_t>(N, 1)).total; }
+
+int shard_route(const int64_t* user_ids, const int64_t* item_ids, int64_t N, int64_t rows_user, int64_t rows_item, int32_t world,
+                int64_t* counts, int64_t* local_ids, int64_t* pos, void* route_ws, int64_t route_ws_bytes, cudaStream_t st) {
+  NCF_REQUIRE(user_ids && item_ids && counts && local_ids && pos && route_ws, "shard_route: null argument");
+  NCF_REQUIRE(world >= 1 && world <= 1024 && rows_user >= 1 && rows_item >= 1, "shard_route: bad world / rows");
+  NCF_REQUIRE(N >= 0 && 2 * N < ((int64_t)1 << 31), "shard_route: bad N");
+  NCF_REQUIRE(rows_user + rows_item < ((int64_t)1 << 32), "shard_route: too many table rows for 32-bit keys");
+  NCF_CUDA(cudaMemsetAsync(counts, 0, sizeof(int64_t) * 2 * world, st));
+  if (N == 0) return NCF_OK;
+  RouteWs w = carve_route_ws(route_ws, N);
+  if (route_ws_bytes < w.total) {
+    set_error("shard_route: workspace %lld < %lld", (long long)route_ws_bytes, (long long)w.total);
+    return NCF_ERR_WORKSPACE;
+  }
+  ids_to_keys2_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(user_ids, item_ids, N, (uint32_t)rows_user, w.keys_in, w.vals_in);
+  NCF_LAUNCH_CHECK();
+  size_t tmp = w.cub_bytes;
+  NCF_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tmp, w.keys_in, w.keys_out, w.vals_in, w.vals_out, (int)(2 * N), 0,
+                                           bits_for(rows_user + rows_item), st));
+  const unsigned grid = (unsigned)((2 * N + 255) / 256);
+  route_flags_kernel<<<grid, 256, 0, st>>>(w.keys_out, N, w.slot);
+  NCF_LAUNCH_CHECK();
+  tmp = w.cub_bytes;
+  NCF_CUDA(cub::DeviceScan::InclusiveSum(w.cub_tmp, tmp, w.slot, w.incl, (int)(2 * N), st));
+  route_finish_kernel<<<grid, 256, 0, st>>>(w.keys_out, w.vals_out, w.incl, N, (uint32_t)rows_user, (rows_user + world - 1) / world,
+                                            (rows_item + world - 1) / world, world, w.slot,
+                                            reinterpret_cast<unsigned long long*>(counts), local_ids, pos);
+  NCF_LAUNCH_CHECK();
+  return NCF_OK;
+}
+
+// gu[slot] / gi[slot] = sum over the samples of each distinct id of [ d_mf * w_mf * y_other_mf | d_x ]; also adds
+// d mf_output.weight.  route_ws = the buffer shard_route filled for the same batch.
+int shard_requester_grads(const float* dense, float* dense_grad, const float* rows_u, const float* rows_i, const int64_t* pos_u,
+                          const int64_t* pos_i, int64_t N, const float* d_mf, const float* dxu, const float* dxp,
+                          const void* route_ws, float* gu, float* gi, void* emb_ws, int64_t emb_ws_bytes, cudaStream_t st) {
+  if (N == 0) return NCF_OK;
+  RouteWs r = carve_route_ws(const_cast<void*>(route_ws), N);
+  EmbWs w = carve_emb_ws(emb_ws, N);
+  if (emb_ws_bytes < w.total) {
+    set_error("shard_requester_grads: workspace %lld < %lld", (long long)emb_ws_bytes, (long long)w.total);
+    return NCF_ERR_WORKSPACE;
+  }
+  NCF_CUDA(cudaMemsetAsync(w.counters, 0, 4 * sizeof(int32_t), st));
+  const int64_t nchunks = (N + EB_CHUNK - 1) / EB_CHUNK;
+  const int wpb = EB_THREADS / 32;
+  const int grid = (int)std::min<int64_t>((nchunks + wpb - 1) / wpb, (int64_t)num_sms() * 8);
+  for (int side = 0; side < 2; ++side) {
+    EmbBwdArgs A{};
+    A.sorted_ids = r.keys_out + (side ? N : 0);
+    A.perm = r.vals_out + (side ? N : 0);
+    A.d_mf_pred = d_mf;
+    A.d_x = side ? dxp : dxu;
+    A.other_rows = side ? rows_u : rows_i;
+    A.other_pos = side ? pos_u : pos_i;
+    A.own_rows = side ? rows_i : rows_u;
+    A.own_pos = side ? pos_i : pos_u;
+    A.out_rows = side ? gi : gu;
+    A.out_slot = r.slot + (side ? N : 0);
+    A.dense = dense;
+    A.dense_grad = dense_grad;
+    A.acc_buf = w.acc_buf;
+    A.chunk_counter = w.counters + side;
+    A.N = N;
+    A.mode = NCF_EMB_ADAM_SPARSE;
+    A.accumulate_wmf = side == 0 ? 1 : 0;
+    emb_bwd_phase1_kernel<<<grid, EB_THREADS, 0, st>>>(A);
+    NCF_LAUNCH_CHECK();
+    A.dense_grad = nullptr;                  // output mode: no LayerNorm-affine gradients here (the owners add them)
+    emb_bwd_phase2_kernel<<<std::min(grid, num_sms() * 3), EB_THREADS, 0, st>>>(A);
+    NCF_LAUNCH_CHECK();
+  }
+  return NCF_OK;
+}
+}  // namespace ncf
+
+extern "C" int64_t ncf_shard_route_workspace_bytes(int64_t N) { return ncf::shard_route_ws_bytes(N); }
+extern "C" int ncf_shard_route(const int64_t* user_ids, const int64_t* item_ids, int64_t N, int64_t rows_user, int64_t rows_item,
+                               int32_t world, int64_t* counts, int64_t* local_ids, int64_t* pos, void* route_ws,
+                               int64_t route_ws_bytes, void* stream) {
+  return ncf::shard_route(user_ids, item_ids, N, rows_user, rows_item, world, counts, local_ids, pos, route_ws, route_ws_bytes,
+                          (cudaStream_t)stream);
 }
 
 extern "C" int ncf_shard_owner_update(const ncf_adam_cfg* adam, const ncf_tables* T, const float* dense,

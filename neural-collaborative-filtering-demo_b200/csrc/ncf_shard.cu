@@ -151,8 +151,8 @@ extern "C" int ncf_shard_forward(const ncf_run_cfg* cfg, const float* dense, con
 
 extern "C" int ncf_shard_backward(const ncf_run_cfg* cfg, const float* dense, float* dense_grad, const float* rows_u,
                                   const float* rows_i, const int64_t* pos_u, const int64_t* pos_i, int64_t N,
-                                  const float* grad_out, float* grad_rows_u, float* grad_rows_i, void* workspace,
-                                  int64_t workspace_bytes, void* stream) {
+                                  const float* grad_out, float* grad_rows_u, float* grad_rows_i, const void* route_ws,
+                                  void* workspace, int64_t workspace_bytes, void* stream) {
   NCF_TRY(check_shard_cfg(cfg, N));
   if (N == 0) return NCF_OK;
   NCF_REQUIRE(dense && dense_grad && rows_u && rows_i && pos_u && pos_i && grad_out && grad_rows_u && grad_rows_i && workspace,
@@ -165,6 +165,9 @@ extern "C" int ncf_shard_backward(const ncf_run_cfg* cfg, const float* dense, fl
   }
   cudaStream_t st = (cudaStream_t)stream;
   NCF_TRY(tower_f32_backward(*cfg, dense, dense_grad, N, grad_out, w, st));
+  if (route_ws)     // ids routed by ncf_shard_route: samples that share a row are scattered -> sorted segment sum
+    return shard_requester_grads(dense, dense_grad, rows_u, rows_i, pos_u, pos_i, N, w.d_mf, w.dxu, w.dxp, route_ws, grad_rows_u,
+                                 grad_rows_i, w.emb, w.emb_bytes, st);
   const int grid = (int)std::min<int64_t>((N + 7) / 8, (int64_t)num_sms() * 8);
   pack_grads_kernel<<<grid, 256, 0, st>>>(rows_u, rows_i, pos_u, pos_i, dense, w.d_mf, w.dxu, w.dxp, N, grad_rows_u,
                                           grad_rows_i, dense_grad);

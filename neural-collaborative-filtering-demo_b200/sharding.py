@@ -7,7 +7,7 @@ cannot run; this module defines the sharding it intended, torchrec ROW_WISE styl
 
 Tables (both towers of a side together) live on their owner; the batch is data-parallel.  One step:
 
-    requester  bucketize ids by owner                      ncf_shard_bucketize
+    requester  sort + de-duplicate ids, bucket by owner    ncf_shard_route
     ---------  all-to-all(v) ids ------------------------  ShardRouter.exchange_ids
     owner      gather + LayerNorm local rows -> [n,128]    ncf_shard_owner_rows
     ---------  all-to-all(v) rows back ------------------  ShardRouter.return_rows
@@ -201,22 +201,20 @@ class ShardedNCFEngine:
 
     # ---- phases (the emulated-cluster test drives these one by one) -----------------------------
     def phase_bucketize(self, user_ids, item_ids):
-        """requester: owner-major local ids of the run heads (adjacent equal ids are exchanged once: the user id is
-        repeated over the S rows of an interaction) + per-owner counts + the exchanged-row position of every sample."""
+        """requester: every DISTINCT id of the batch is exchanged once (one radix sort of both sides): owner-major
+        local ids + per-owner counts + the exchanged-row position of every sample."""
         self.step += 1
-        self.N = user_ids.numel()
-        self._plan = []
-        for ids, rows in ((user_ids, self.U), (item_ids, self.I)):
-            n = ids.numel()
-            counts = torch.empty(self.world, dtype=torch.long, device=self.device)
-            local = torch.empty(n, dtype=torch.long, device=self.device)
-            pos = torch.empty(n, dtype=torch.long, device=self.device)
-            nbytes = int(self.lib.ncf_shard_bucketize_runs_workspace_bytes(n, self.world))
-            ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
-            _lib.check(self.lib.ncf_shard_bucketize_runs(_lib.ptr(ids), n, rows, self.world, _lib.ptr(counts), _lib.ptr(local),
-                                                         _lib.ptr(pos), _lib.ptr(ws), nbytes, self._s()),
-                       "ncf_shard_bucketize_runs")
-            self._plan.append((counts, local, pos))
+        self.N = n = user_ids.numel()
+        dev = self.device
+        counts = torch.empty(2, self.world, dtype=torch.long, device=dev)
+        local = torch.empty(2, max(n, 1), dtype=torch.long, device=dev)
+        pos = torch.empty(2, max(n, 1), dtype=torch.long, device=dev)
+        nbytes = int(self.lib.ncf_shard_route_workspace_bytes(n))
+        self._route_ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        _lib.check(self.lib.ncf_shard_route(_lib.ptr(user_ids), _lib.ptr(item_ids), n, self.U, self.I, self.world,
+                                            _lib.ptr(counts), _lib.ptr(local), _lib.ptr(pos), _lib.ptr(self._route_ws), nbytes,
+                                            self._s()), "ncf_shard_route")
+        self._plan = [(counts[0], local[0], pos[0]), (counts[1], local[1], pos[1])]
         return [(p[1], p[0]) for p in self._plan]        # [(local ids owner-major, counts)] per side
 
     def phase_owner_rows(self, served_ids: List[torch.Tensor]):
@@ -254,7 +252,8 @@ class ShardedNCFEngine:
         gi = torch.empty(rows[1].shape[0], 128, device=self.device)
         _lib.check(self.lib.ncf_shard_backward(C.byref(cfg), _lib.ptr(flat), _lib.ptr(self.dense_grad), _lib.ptr(rows[0]),
                                                _lib.ptr(rows[1]), _lib.ptr(pos_u), _lib.ptr(pos_i), N, _lib.ptr(grad_out),
-                                               _lib.ptr(gu), _lib.ptr(gi), _lib.ptr(ws), nbytes, self._s()),
+                                               _lib.ptr(gu), _lib.ptr(gi), _lib.ptr(self._route_ws), _lib.ptr(ws), nbytes,
+                                               self._s()),
                    "ncf_shard_backward")
         return [gu, gi]
 

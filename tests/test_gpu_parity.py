@@ -406,6 +406,31 @@ def test_shard_bucketize_runs_bit_exact():
         assert torch.equal(pos.cpu(), slot[inverse])
 
 
+def test_shard_route_bit_exact():
+    """Full de-duplication of both sides: distinct ids in ascending (= owner-major) order, counts per owner, and the
+    position of every sample - against torch.unique(sorted) + row_shard."""
+    from ncf_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(9)
+    for n, U, I, world in ((5, 10, 7, 2), (1000, 100, 50, 8), (4095, 138493, 26744, 8), (777, 3, 2, 3)):
+        u = torch.randint(0, U, (n,), generator=g)
+        i = torch.randint(0, I, (n,), generator=g)
+        counts = torch.empty(2, world, dtype=torch.long, device="cuda")
+        local = torch.full((2, n), -1, dtype=torch.long, device="cuda")
+        pos = torch.empty(2, n, dtype=torch.long, device="cuda")
+        nbytes = int(lib.ncf_shard_route_workspace_bytes(n))
+        ws = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+        du, di = u.cuda(), i.cuda()
+        _lib.check(lib.ncf_shard_route(_lib.ptr(du), _lib.ptr(di), n, U, I, world, _lib.ptr(counts), _lib.ptr(local),
+                                       _lib.ptr(pos), _lib.ptr(ws), nbytes, None))
+        for side, (ids, rows) in enumerate(((u, U), (i, I))):
+            uniq, inverse = torch.unique(ids, sorted=True, return_inverse=True)
+            owner, loc, block = O.row_shard(uniq, rows, world)
+            assert torch.equal(counts[side].cpu(), torch.bincount(owner, minlength=world))
+            assert torch.equal(local[side].cpu()[:uniq.numel()], loc)
+            assert torch.equal(pos[side].cpu(), inverse)
+
+
 def test_errors_are_loud():
     import ncf_b200
     p, _ = golden_params()
