@@ -393,13 +393,26 @@ def main():
         from ncf_b200.sharding import ShardedNCFEngine
         model = build_model(1, 1, dev, precision)
         eng = ShardedNCFEngine(model, users, items, lr=1e-3, weight_decay=1e-5, table_mode=table_mode)
-        dev_in = [torch.empty(N, dtype=torch.long, device=dev), torch.empty(N, dtype=torch.long, device=dev),
-                  torch.empty(N, dtype=torch.float32, device=dev)]
+        # two sets of device staging buffers: while step s runs, the ids of step s+1 are already on the device, so
+        # the engine can route them ahead (ShardedNCFEngine.train_step next_ids)
+        dev_in = [[torch.empty(N, dtype=torch.long, device=dev), torch.empty(N, dtype=torch.long, device=dev),
+                   torch.empty(N, dtype=torch.float32, device=dev)] for _ in range(2)]
+        staged = {"slot": 0, "have": False}
 
-        def step_host(u, i, t):
-            for d, h in zip(dev_in, (u, i, t)):
+        def stage(slot, batch):
+            for d, h in zip(dev_in[slot], batch):
                 d.copy_(h, non_blocking=True)
-            return float(eng.train_step(*dev_in).item())
+
+        def step_host(u, i, t, nxt=None):
+            cur = staged["slot"]
+            if not staged["have"]:
+                stage(cur, (u, i, t))
+            nids = None
+            if nxt is not None:
+                stage(cur ^ 1, nxt)
+                nids = tuple(dev_in[cur ^ 1][:2])
+            staged["slot"], staged["have"] = cur ^ 1, nxt is not None
+            return float(eng.train_step(*dev_in[cur], next_ids=nids).item())
         eng.train_step_host = step_host
     else:
         if args.workload == "c3":
@@ -428,7 +441,10 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for s in range(args.steps):
-        eng.train_step(*dev_batches[s % nb])
+        if world > 1:      # sharded engine: the next batch's ids are known (input-pipeline look-ahead)
+            eng.train_step(*dev_batches[s % nb], next_ids=dev_batches[(s + 1) % nb][:2] if s + 1 < args.steps else None)
+        else:
+            eng.train_step(*dev_batches[s % nb])
     e1.record()
     barrier()
     ms_total = e0.elapsed_time(e1)
@@ -441,7 +457,10 @@ def main():
     barrier()
     t0 = time.perf_counter()
     for s in range(args.steps):
-        eng.train_step_host(*host_batches[s % nb])
+        if world > 1:
+            eng.train_step_host(*host_batches[s % nb], nxt=host_batches[(s + 1) % nb] if s + 1 < args.steps else None)
+        else:
+            eng.train_step_host(*host_batches[s % nb])
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None

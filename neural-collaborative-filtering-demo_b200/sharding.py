@@ -50,6 +50,16 @@ def shard_rows(rows: int, world: int, rank: int) -> int:
     return max(0, min(rows, (rank + 1) * block) - rank * block)
 
 
+def _alltoallv_many(items, group) -> None:
+    """Several all-to-all(v) exchanges launched back to back (async) and awaited together.
+    items = [(out, inp, recv_counts, send_counts)].  (A single batched point-to-point group was tried instead of one
+    NCCL call per exchange: slower on NVSwitch.)"""
+    works = [dist.all_to_all_single(out, inp, recv_counts, send_counts, group=group, async_op=True)
+             for out, inp, recv_counts, send_counts in items]
+    for w in works:
+        w.wait()
+
+
 class ShardRouter:
     """all-to-all(v) routing of one side's ids / rows between requesters and owners."""
 
@@ -68,26 +78,49 @@ class ShardRouter:
     def exchange_ids_multi(routers, plans):
         """The id exchange of several sides at once: ONE all-to-all of all the counts and one host sync (the split
         sizes), then the id all-to-alls are launched back to back."""
+        return ShardRouter.finish_id_exchange(ShardRouter.begin_id_exchange(routers, plans))
+
+    @staticmethod
+    def begin_id_exchange(routers, plans):
+        """Enqueue the count exchange and the device->host copy of the split sizes; nothing waits yet, so the caller
+        can queue more GPU work before finish_id_exchange blocks the CPU."""
         first = routers[0]
         counts = torch.stack([c for _, c in plans], dim=1).contiguous()              # [world, sides]
         if first.world == 1:
-            tot = counts.cpu()[0].tolist()
-            for r, n in zip(routers, tot):
-                r.send_counts, r.recv_counts = [int(n)], [int(n)]
-            return [ids[:int(n)] for (ids, _), n in zip(plans, tot)]
-        recv = torch.empty_like(counts)
-        dist.all_to_all_single(recv, counts, group=first.group)
-        both = torch.stack([counts, recv]).cpu()                                      # the one host sync of the step
-        outs, works = [], []
+            both = torch.stack([counts, counts])
+        else:
+            recv = torch.empty_like(counts)
+            dist.all_to_all_single(recv, counts, group=first.group)
+            both = torch.stack([counts, recv])
+        if both.is_cuda:
+            host = torch.empty(both.shape, dtype=both.dtype, pin_memory=True)
+            host.copy_(both, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+        else:
+            host, ev = both, None
+        return dict(routers=routers, plans=plans, host=host, event=ev)
+
+    @staticmethod
+    def finish_id_exchange(h):
+        routers, plans = h["routers"], h["plans"]
+        if h["event"] is not None:
+            h["event"].synchronize()                                                  # the one host sync of the step
+        both = h["host"]
+        outs, items, counts = [], [], []
         for k, (r, (ids, _)) in enumerate(zip(routers, plans)):
-            r.send_counts = both[0, :, k].tolist()
-            r.recv_counts = both[1, :, k].tolist()
-            out = ids.new_empty(sum(r.recv_counts))
-            works.append(dist.all_to_all_single(out, ids[:sum(r.send_counts)], r.recv_counts, r.send_counts, group=r.group,
-                                                async_op=True))
+            send, recv = both[0, :, k].tolist(), both[1, :, k].tolist()
+            counts.append((send, recv))
+            if r.world == 1:
+                outs.append(ids[:send[0]])
+                continue
+            out = ids.new_empty(sum(recv))
+            items.append((out, ids[:sum(send)], recv, send))
             outs.append(out)
-        for w in works:
-            w.wait()
+        if items:
+            _alltoallv_many(items, routers[0].group)
+        for r, (send, recv) in zip(routers, counts):
+            r.send_counts, r.recv_counts = send, recv
         return outs
 
     def return_rows(self, rows: torch.Tensor) -> torch.Tensor:
@@ -103,14 +136,13 @@ class ShardRouter:
         """return_rows (to_owner=False) / send_rows (to_owner=True) of several sides launched back to back."""
         if routers[0].world == 1:
             return list(rows_list)
-        outs, works = [], []
+        outs, items = [], []
         for r, rows in zip(routers, rows_list):
             out_counts, in_counts = (r.recv_counts, r.send_counts) if to_owner else (r.send_counts, r.recv_counts)
             out = rows.new_empty((sum(out_counts),) + tuple(rows.shape[1:]))
-            works.append(dist.all_to_all_single(out, rows, out_counts, in_counts, group=r.group, async_op=True))
+            items.append((out, rows, out_counts, in_counts))
             outs.append(out)
-        for w in works:
-            w.wait()
+        _alltoallv_many(items, routers[0].group)
         return outs
 
     def send_rows(self, rows: torch.Tensor) -> torch.Tensor:
@@ -161,11 +193,13 @@ class ShardedNCFEngine:
         self.touched = [torch.zeros(max(self.rows_u, 1), dtype=torch.uint8, device=dev),
                         torch.zeros(max(self.rows_i, 1), dtype=torch.uint8, device=dev)]
         n = model._flat.numel()
-        self.dense_grad = torch.zeros(n, device=dev)
+        self._dense_and_loss = torch.zeros(n + 1, device=dev)             # [dense gradients | loss]: one all-reduce
+        self.dense_grad = self._dense_and_loss[:n]
         self.dense_m = torch.zeros(n, device=dev)
         self.dense_v = torch.zeros(n, device=dev)
         self.loss = torch.zeros(1, device=dev)
         self.routers = [ShardRouter(group), ShardRouter(group)]
+        self._prefetched = None
         if self.world == 1 or not dist.is_initialized():
             for r in self.routers:
                 r.world = 1
@@ -280,14 +314,28 @@ class ShardedNCFEngine:
                                            _lib.ptr(self.dense_v), flat.numel(), C.byref(adam), self._s()), "ncf_dense_adam")
 
     # ---- the real step ----------------------------------------------------------------------------
-    def train_step(self, user_ids: torch.Tensor, item_ids: torch.Tensor, targets: torch.Tensor) -> torch.Tensor:
+    def train_step(self, user_ids: torch.Tensor, item_ids: torch.Tensor, targets: torch.Tensor,
+                   next_ids: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> torch.Tensor:
         """Global ids int64 [N] and targets fp32 [N] of THIS rank's batch (device tensors).  Returns the
-        global mean loss (device scalar, identical on all ranks)."""
+        global mean loss (device scalar, identical on all ranks).
+
+        next_ids = (user_ids, item_ids) the NEXT call will be given (input-pipeline look-ahead; all ranks must pass it
+        or none): that batch is routed (sort, de-duplication, count exchange) right after this step's gradient exchange
+        is queued, so the one host synchronisation of a step - reading the split sizes - waits while the GPU still has
+        the owner update of this step to do, instead of draining the queue."""
         mark = self._mark
         mark(None)
-        plan = self.phase_bucketize(user_ids, item_ids)
-        mark("bucketize")
-        served = ShardRouter.exchange_ids_multi(self.routers, plan)
+        pre, self._prefetched = self._prefetched, None
+        key = (user_ids.data_ptr(), item_ids.data_ptr(), user_ids.numel())
+        if pre is not None and pre["key"] == key:
+            self.step += 1
+            self._plan, self.N, self._route_ws = pre["plan"], pre["N"], pre["route_ws"]
+            mark("bucketize")
+            served = ShardRouter.finish_id_exchange(pre["handle"])
+        else:
+            plan = self.phase_bucketize(user_ids, item_ids)
+            mark("bucketize")
+            served = ShardRouter.exchange_ids_multi(self.routers, plan)
         mark("a2a ids")
         rows_out = self.phase_owner_rows(served)
         mark("owner rows")
@@ -297,11 +345,20 @@ class ShardedNCFEngine:
         mark("forward+backward")
         recv = ShardRouter.exchange_rows_multi(self.routers, grads, to_owner=True)
         mark("a2a grads")
+        if next_ids is not None:
+            keep = (self.step, self._plan, self.N, self._route_ws, self._served)
+            plan = self.phase_bucketize(*next_ids)
+            handle = ShardRouter.begin_id_exchange(self.routers, plan)
+            self._prefetched = dict(key=(next_ids[0].data_ptr(), next_ids[1].data_ptr(), next_ids[0].numel()), plan=self._plan,
+                                    N=self.N, route_ws=self._route_ws, handle=handle)
+            self.step, self._plan, self.N, self._route_ws, self._served = keep
+            mark("route next")
         self.phase_owner_update(recv)
         mark("owner update")
         if self.world > 1:
-            dist.all_reduce(self.dense_grad, group=self.group)
-            dist.all_reduce(self.loss, group=self.group)
+            self._dense_and_loss[-1:].copy_(self.loss)
+            dist.all_reduce(self._dense_and_loss, group=self.group)      # dense gradients + the loss in one call
+            self.loss.copy_(self._dense_and_loss[-1:])
         self.phase_dense_adam()
         mark("dense allreduce+adam")
         return self.loss
