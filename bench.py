@@ -323,7 +323,9 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "train_samples_per_s", "value": rate, "unit": "samples/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {desc}", "interactions_per_step": B, "rows_per_interaction": S},
+            "config": {"workload": f"{args.workload}: {desc}", "interactions_per_step_per_gpu": B, "rows_per_interaction": S,
+                       "table_update": "dense torch.optim.Adam on every row (the reference's own semantics)", "towers": "fp32",
+                       "l2": "host DRAM; bounded sample of the step"},
             "cpu_baseline": {"value": rate, "unit": "samples/s", "cores": threads, "kind": "port",
                              "sample": f"{B_sample} of the {B} interactions of a step, {args.steps} steps"},
             "e2e": {"value": rate, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
