@@ -462,7 +462,7 @@ def main():
         if world > 1:
             eng.train_step_host(*host_batches[s % nb], nxt=host_batches[(s + 1) % nb] if s + 1 < args.steps else None)
         else:
-            eng.train_step_host(*host_batches[s % nb])
+            eng.train_step_host(*host_batches[s % nb], next_batch=host_batches[(s + 1) % nb] if s + 1 < args.steps else None)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None

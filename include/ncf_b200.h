@@ -114,6 +114,10 @@ typedef struct ncf_adam_cfg {
 NCF_API int ncf_version(void);
 NCF_API const char* ncf_last_error(void);
 NCF_API int64_t ncf_launch_count(void);   /* kernels this library has launched so far (process-wide) */
+/* Every call enqueues on its `stream` argument only and never synchronises.  One opt-in exception: with an
+ * auxiliary stream set here, ncf_train_step forks the id sort of the embedding backward (which depends on the
+ * ids alone) onto it, ordered with events against the stream argument.  NULL (default) switches that off. */
+NCF_API int ncf_set_aux_stream(void* stream);
 NCF_API int64_t ncf_dense_numel(void);
 NCF_API int64_t ncf_dense_offset(int32_t dense_id);
 NCF_API int64_t ncf_dense_size(int32_t dense_id);

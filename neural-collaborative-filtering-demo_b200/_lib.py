@@ -63,6 +63,7 @@ _SIGS = {
     "ncf_dense_size": (_I64, [_I32]),
     "ncf_workspace_bytes": (_I64, [_I64, C.POINTER(RunCfg)]),
     "ncf_forward": (C.c_int, [C.POINTER(RunCfg), C.POINTER(Tables), _P, _P, _P, _I64, _P, _P, _P, _P, _P, _I64, _P]),
+    "ncf_set_aux_stream": (C.c_int, [_P]),
     "ncf_attn_fwd": (C.c_int, [C.POINTER(RunCfg), _P, _I64, _P, _I64, _P]),
     "ncf_mlp_fwd": (C.c_int, [C.POINTER(RunCfg), _P, _I64, _P, _P, _I64, _P]),
     "ncf_mlp_bwd": (C.c_int, [C.POINTER(RunCfg), _P, _P, _I64, _P, _P, _I64, _P]),

@@ -24,6 +24,15 @@ using namespace ncf;
 extern "C" int ncf_version(void) { return NCF_ABI_VERSION; }
 extern "C" const char* ncf_last_error(void) { return g_err; }
 extern "C" int64_t ncf_launch_count(void) { return (int64_t)g_launches; }
+
+// optional auxiliary stream for work that is independent of the main stream's kernels (ncf_train_step forks the
+// id sort of the embedding backward onto it); NULL = everything on the stream argument (default)
+static cudaStream_t g_aux_stream = nullptr;
+static cudaEvent_t g_ev_fork = nullptr, g_ev_sorted = nullptr;
+extern "C" int ncf_set_aux_stream(void* stream) {
+  g_aux_stream = (cudaStream_t)stream;
+  return NCF_OK;
+}
 extern "C" int64_t ncf_dense_numel(void) { return kLayout.total; }
 extern "C" int64_t ncf_dense_offset(int32_t id) { return id >= 0 && id < NCF_P_COUNT ? kLayout.off[id] : -1; }
 extern "C" int64_t ncf_dense_size(int32_t id) { return id >= 0 && id < NCF_P_COUNT ? kLayout.size[id] : -1; }
@@ -64,9 +73,21 @@ extern "C" int ncf_forward(const ncf_run_cfg* cfg, const ncf_tables* T, const fl
   return tower_f32_forward(*cfg, dense, N, hour, tail1, out, w, st);
 }
 
+static int backward_impl(const ncf_run_cfg* cfg, const ncf_adam_cfg* adam, const ncf_tables* T, const float* dense,
+                         float* dense_grad, const int64_t* user_ids, const int64_t* item_ids, int64_t N,
+                         const float* grad_out, void* workspace, int64_t workspace_bytes, void* stream, cudaEvent_t sorted);
+
 extern "C" int ncf_backward(const ncf_run_cfg* cfg, const ncf_adam_cfg* adam, const ncf_tables* T, const float* dense,
                             float* dense_grad, const int64_t* user_ids, const int64_t* item_ids, int64_t N,
                             const float* grad_out, void* workspace, int64_t workspace_bytes, void* stream) {
+  return backward_impl(cfg, adam, T, dense, dense_grad, user_ids, item_ids, N, grad_out, workspace, workspace_bytes, stream,
+                       nullptr);
+}
+
+// sorted != null: the id sort of the embedding backward already runs on the auxiliary stream and signals this event
+static int backward_impl(const ncf_run_cfg* cfg, const ncf_adam_cfg* adam, const ncf_tables* T, const float* dense,
+                         float* dense_grad, const int64_t* user_ids, const int64_t* item_ids, int64_t N,
+                         const float* grad_out, void* workspace, int64_t workspace_bytes, void* stream, cudaEvent_t sorted) {
   NCF_TRY(check_cfg(cfg, N));
   NCF_REQUIRE(adam && T && dense && dense_grad && user_ids && item_ids && grad_out && workspace, "backward: null argument");
   NCF_REQUIRE(cfg->training, "backward: needs the workspace of a training-mode forward");
@@ -79,7 +100,9 @@ extern "C" int ncf_backward(const ncf_run_cfg* cfg, const ncf_adam_cfg* adam, co
   cudaStream_t st = (cudaStream_t)stream;
   NCF_TRY(tower_f32_backward(*cfg, dense, dense_grad, N, grad_out, w, st));
   if (adam->emb_mode != NCF_EMB_NONE) {
-    NCF_TRY(emb_bwd_both(adam, T, dense, dense_grad, user_ids, item_ids, N, w.d_mf, w.dxu, w.dxp, w.y_pmf, w.y_umf, w.emb, w.emb_bytes, st));
+    if (sorted) NCF_CUDA(cudaStreamWaitEvent(st, sorted, 0));
+    NCF_TRY(emb_bwd_both(adam, T, dense, dense_grad, user_ids, item_ids, N, w.d_mf, w.dxu, w.dxp, w.y_pmf, w.y_umf, w.emb, w.emb_bytes, st,
+                         sorted != nullptr));
     if (adam->emb_mode == NCF_EMB_ADAM_DENSE_EQUIV) NCF_TRY(ncf_emb_adam_sweep(adam, T, stream));
   }
   return NCF_OK;
@@ -144,10 +167,24 @@ extern "C" int ncf_train_step(const ncf_run_cfg* cfg, const ncf_adam_cfg* adam, 
     set_error("train_step: workspace %lld < %lld bytes", (long long)workspace_bytes, (long long)w.total);
     return NCF_ERR_WORKSPACE;
   }
+  // The id sort of the embedding backward depends on the ids only: with an auxiliary stream (ncf_set_aux_stream) it
+  // is forked off here and runs next to the gather / attention kernels, which leave SM resources free.
+  cudaEvent_t sorted = nullptr;
+  if (g_aux_stream && adam->emb_mode != NCF_EMB_NONE && adam->emb_mode != NCF_EMB_MATERIALIZE) {
+    if (!g_ev_fork) {
+      NCF_CUDA(cudaEventCreateWithFlags(&g_ev_fork, cudaEventDisableTiming));
+      NCF_CUDA(cudaEventCreateWithFlags(&g_ev_sorted, cudaEventDisableTiming));
+    }
+    NCF_CUDA(cudaEventRecord(g_ev_fork, st));                  // the previous step's K6 has released the sort buffers
+    NCF_CUDA(cudaStreamWaitEvent(g_aux_stream, g_ev_fork, 0));
+    NCF_TRY(emb_sort_both(T, user_ids, item_ids, N, w.emb, w.emb_bytes, g_aux_stream));
+    NCF_CUDA(cudaEventRecord(g_ev_sorted, g_aux_stream));
+    sorted = g_ev_sorted;
+  }
   NCF_CUDA(cudaMemsetAsync(dense_grad, 0, sizeof(float) * kLayout.total, st));                       // optimizer.zero_grad()
   NCF_TRY(ncf_forward(cfg, T, dense, user_ids, item_ids, N, nullptr, nullptr, nullptr, out, workspace, workspace_bytes, stream));
   // BCELoss gradient goes into the (not yet used) backward scratch g128b
   NCF_TRY(launch_bce(out, targets, N, loss_out, w.g128b, st));
-  NCF_TRY(ncf_backward(cfg, adam, T, dense, dense_grad, user_ids, item_ids, N, w.g128b, workspace, workspace_bytes, stream));
+  NCF_TRY(backward_impl(cfg, adam, T, dense, dense_grad, user_ids, item_ids, N, w.g128b, workspace, workspace_bytes, stream, sorted));
   return ncf_dense_adam(dense, dense_grad, dense_m, dense_v, kLayout.total, adam, stream);
 }

@@ -787,10 +787,30 @@ namespace ncf {
 // Both sides of the single-GPU backward with ONE radix sort: keys = user id | item id + rows_user, so the
 // sorted array holds the users' runs in [0,N) and the items' runs in [N,2N).  Item side first (it gathers the
 // user MF rows before the user side overwrites them), user side second (reads the saved item rows).
+// the id-only part of emb_bwd_both: keys = user id | item id + rows_user, one radix sort.  It depends on nothing the
+// forward or backward computes, so ncf_train_step may run it on an auxiliary stream next to the forward.
+int emb_sort_both(const ncf_tables* T, const int64_t* user_ids, const int64_t* item_ids, int64_t N, void* workspace,
+                  int64_t workspace_bytes, cudaStream_t st) {
+  if (N == 0) return NCF_OK;
+  NCF_REQUIRE(2 * N < ((int64_t)1 << 31), "emb_bwd: N too large");
+  NCF_REQUIRE(T->rows_user + T->rows_item < ((int64_t)1 << 32), "emb_bwd: too many table rows for 32-bit keys");
+  EmbWs w = carve_emb_ws(workspace, N);
+  if (workspace_bytes < w.total) {
+    set_error("emb_bwd: workspace %lld < %lld", (long long)workspace_bytes, (long long)w.total);
+    return NCF_ERR_WORKSPACE;
+  }
+  ids_to_keys2_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(user_ids, item_ids, N, (uint32_t)T->rows_user, w.keys_in, w.vals_in);
+  NCF_LAUNCH_CHECK();
+  size_t tmp = w.cub_bytes;
+  NCF_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tmp, w.keys_in, w.keys_out, w.vals_in, w.vals_out, (int)(2 * N), 0,
+                                           bits_for(T->rows_user + T->rows_item), st));
+  return NCF_OK;
+}
+
 int emb_bwd_both(const ncf_adam_cfg* adam, const ncf_tables* T, const float* dense, float* dense_grad,
                  const int64_t* user_ids, const int64_t* item_ids, int64_t N, const float* d_mf_pred, const float* dxu,
                  const float* dxp, const float* y_item_mf, const float* y_user_mf, void* workspace, int64_t workspace_bytes,
-                 cudaStream_t st) {
+                 cudaStream_t st, bool presorted) {
   if (N == 0 || adam->emb_mode == NCF_EMB_NONE) return NCF_OK;
   NCF_REQUIRE(2 * N < ((int64_t)1 << 31), "emb_bwd: N too large");
   NCF_REQUIRE(T->rows_user + T->rows_item < ((int64_t)1 << 32), "emb_bwd: too many table rows for 32-bit keys");
@@ -805,11 +825,7 @@ int emb_bwd_both(const ncf_adam_cfg* adam, const ncf_tables* T, const float* den
     for (int k = 0; k < 4; ++k) NCF_REQUIRE(T->m[k] && T->v[k], "emb_bwd: Adam mode needs m and v");
   }
   if (adam->emb_mode == NCF_EMB_ADAM_DENSE_EQUIV) NCF_REQUIRE(T->touched[0] && T->touched[1], "dense-equivalent mode needs tables->touched");
-  ids_to_keys2_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(user_ids, item_ids, N, (uint32_t)T->rows_user, w.keys_in, w.vals_in);
-  NCF_LAUNCH_CHECK();
-  size_t tmp = w.cub_bytes;
-  NCF_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tmp, w.keys_in, w.keys_out, w.vals_in, w.vals_out, (int)(2 * N), 0,
-                                           bits_for(T->rows_user + T->rows_item), st));
+  if (!presorted) NCF_TRY(emb_sort_both(T, user_ids, item_ids, N, workspace, workspace_bytes, st));
   gather_sorted_kernel<<<(unsigned)((2 * N + 255) / 256), 256, 0, st>>>(w.vals_out, user_ids, item_ids, d_mf_pred, N,
                                                                         w.other_sorted, w.dmf_sorted);
   NCF_LAUNCH_CHECK();
@@ -868,7 +884,7 @@ extern "C" int ncf_emb_bwd_adam_both(const ncf_adam_cfg* adam, const ncf_tables*
   NCF_REQUIRE(adam && T && dense && user_ids && item_ids && d_mf_pred && d_xu && d_xp && y_item_mf && workspace,
               "emb_bwd_adam_both: null argument");
   return emb_bwd_both(adam, T, dense, dense_grad, user_ids, item_ids, N, d_mf_pred, d_xu, d_xp, y_item_mf, y_user_mf,
-                      workspace, workspace_bytes, (cudaStream_t)stream);
+                      workspace, workspace_bytes, (cudaStream_t)stream, false);
 }
 
 extern "C" int ncf_emb_bwd_adam(const ncf_adam_cfg* adam, const ncf_tables* T, const float* dense, float* dense_grad,

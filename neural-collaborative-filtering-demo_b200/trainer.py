@@ -47,6 +47,8 @@ class NCFTrainEngine:
         self._out = None
         self._dev_in = None
         self.S = 1 + model.negative_samples
+        # the id sort of the embedding backward runs on this stream, next to the forward (ncf_set_aux_stream)
+        self._aux_stream = torch.cuda.Stream(device=dev) if os.environ.get("NCF_AUX_STREAM", "1") != "0" else None
         if max_rows:
             self._reserve(max_rows)
 
@@ -83,6 +85,7 @@ class NCFTrainEngine:
         adam.eps, adam.weight_decay, adam.step = self.hp["eps"], self.hp["weight_decay"], self.step
         adam.emb_mode = _lib.EMB_ADAM_DENSE_EQUIV if self.table_mode == "fused_dense_equiv" else _lib.EMB_ADAM_SPARSE
         tables = self.model._tables_struct()
+        self.lib.ncf_set_aux_stream(C.c_void_p(self._aux_stream.cuda_stream) if self._aux_stream is not None else None)
         _lib.check(self.lib.ncf_train_step(C.byref(cfg), C.byref(adam), C.byref(tables), _lib.ptr(self.model._flat),
                                            _lib.ptr(self.dense_grad), _lib.ptr(self.dense_m), _lib.ptr(self.dense_v),
                                            _lib.ptr(user_ids), _lib.ptr(item_ids), _lib.ptr(targets), N,
@@ -92,19 +95,44 @@ class NCFTrainEngine:
         self.outputs = self._out[:N]
         return self.loss
 
-    def train_step_host(self, user_ids: torch.Tensor, item_ids: torch.Tensor, targets: torch.Tensor) -> float:
+    def train_step_host(self, user_ids: torch.Tensor, item_ids: torch.Tensor, targets: torch.Tensor,
+                        next_batch=None) -> float:
         """End-to-end step from HOST (ideally pinned) buffers: H2D copies of the ids and targets,
-        the step, and the D2H read of the loss (what trainer.py:253-254, 289 do per batch)."""
+        the step, and the D2H read of the loss (what trainer.py:253-254, 289 do per batch).
+
+        next_batch = the (user_ids, item_ids, targets) host tensors the NEXT call will pass: their H2D copies are
+        queued on a copy stream into the second set of staging buffers while this step computes (plain input-pipeline
+        double buffering; every step still copies its inputs and reads its loss)."""
         N = user_ids.numel()
-        if self._dev_in is None or self._dev_in[0].numel() < N:
-            self._dev_in = (torch.empty(N, dtype=torch.long, device=self.device),
-                            torch.empty(N, dtype=torch.long, device=self.device),
-                            torch.empty(N, dtype=torch.float32, device=self.device))
-        du, di, dt = (b[:N] for b in self._dev_in)
-        du.copy_(user_ids.reshape(-1), non_blocking=True)
-        di.copy_(item_ids.reshape(-1), non_blocking=True)
-        dt.copy_(targets.reshape(-1), non_blocking=True)
-        return float(self.train_step(du, di, dt).item())
+        if self._dev_in is None or self._dev_in[0][0].numel() < N:
+            self._dev_in = [(torch.empty(N, dtype=torch.long, device=self.device),
+                             torch.empty(N, dtype=torch.long, device=self.device),
+                             torch.empty(N, dtype=torch.float32, device=self.device)) for _ in range(2)]
+            self._stage_slot, self._staged_key, self._staged_event = 0, None, None
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        cur = self._stage_slot
+        du, di, dt = (b[:N] for b in self._dev_in[cur])
+        key = (user_ids.data_ptr(), item_ids.data_ptr(), targets.data_ptr(), N)
+        if self._staged_key == key:
+            torch.cuda.current_stream(self.device).wait_event(self._staged_event)
+        else:
+            du.copy_(user_ids.reshape(-1), non_blocking=True)
+            di.copy_(item_ids.reshape(-1), non_blocking=True)
+            dt.copy_(targets.reshape(-1), non_blocking=True)
+        loss = self.train_step(du, di, dt)
+        self._staged_key = None
+        if next_batch is not None:
+            # the other staging set was last read by the previous step, whose loss has been read back: it is free
+            nu, ni, nt = next_batch
+            M = nu.numel()
+            if M <= self._dev_in[cur ^ 1][0].numel():
+                with torch.cuda.stream(self._copy_stream):
+                    for d, h in zip(self._dev_in[cur ^ 1], (nu, ni, nt)):
+                        d[:M].copy_(h.reshape(-1), non_blocking=True)
+                    self._staged_event = self._copy_stream.record_event()
+                self._staged_key = (nu.data_ptr(), ni.data_ptr(), nt.data_ptr(), M)
+        self._stage_slot = cur ^ 1
+        return float(loss.item())
 
     def state_dict(self):
         return {"step": self.step, "dense_m": self.dense_m.clone(), "dense_v": self.dense_v.clone(),
