@@ -291,6 +291,69 @@ __device__ __forceinline__ void block_flush(float* s_red, float4 val, float* dst
   }
 }
 
+// Phase 1, lean variant for the single-GPU step (both LayerNorm-ed MF rows were saved by K1, d_mf was gathered
+// into sorted order): every per-sample input is a [N,64] row indexed by the sample row, so a position costs three
+// shuffles (row, d_mf, id), one 128-bit load per half (two for the side that also forms d mf_output.weight) and
+// the multiply-adds - none of the source-selection logic of the general kernel below.
+template <bool WMF>
+__global__ void __launch_bounds__(EB_THREADS, 3) emb_bwd_phase1_lean_kernel(EmbBwdArgs A) {
+  __shared__ float s_red[(EB_THREADS / 32) * 32 * 4];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = EB_THREADS / 32;
+  const int half = lane >> 4, l16 = lane & 15;
+  const int64_t nchunks = (A.N + EB_CHUNK - 1) / EB_CHUNK;
+  const int64_t gw = (int64_t)blockIdx.x * nwarps + warp, gstride = (int64_t)gridDim.x * nwarps;
+  const float4 w_out = ldg4(A.dense + NCF_OFF(NCF_P_MF_OUT_W) + 4 * l16);
+  const float* src = (half ? A.d_x : A.other_y) + 4 * l16;
+  const float* own = A.own_y + 4 * l16;
+  float4 dwout = make_float4(0, 0, 0, 0);
+
+  for (int64_t c = gw; c < nchunks; c += gstride) {
+    const int64_t p0 = c * EB_CHUNK;
+    const int cnt = (int)min((int64_t)EB_CHUNK, A.N - p0);
+    const uint32_t my_id = lane < cnt ? A.sorted_ids[p0 + lane] : 0xffffffffu;
+    const int32_t my_row = lane < cnt ? A.perm[p0 + lane] : 0;
+    const float my_dmf = lane < cnt ? A.dmf_sorted[p0 + lane] : 0.f;
+    float4 acc = make_float4(0, 0, 0, 0);
+    int piece_first = 0;
+    uint32_t id_prev = __shfl_sync(0xffffffffu, my_id, 0);
+    for (int k0 = 0; k0 < cnt; k0 += 4) {
+      float4 x[4], sf[4];
+      float dmf[4];
+      uint32_t idk[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int kk = min(k0 + u, cnt - 1);
+        const int64_t off = (int64_t)__shfl_sync(0xffffffffu, my_row, kk) * D;
+        dmf[u] = __shfl_sync(0xffffffffu, my_dmf, kk);
+        idk[u] = __shfl_sync(0xffffffffu, my_id, kk);
+        x[u] = ldg4(src + off);
+        if (WMF) sf[u] = half ? make_float4(0, 0, 0, 0) : ldg4(own + off);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (k0 + u < cnt) {                                   // warp-uniform
+          if (idk[u] != id_prev) {                            // a new run starts: flush the piece
+            st4(A.acc_buf + ((p0 + piece_first) * 2 + half) * D + 4 * l16, acc);
+            acc = make_float4(0, 0, 0, 0);
+            piece_first = k0 + u;
+            id_prev = idk[u];
+          }
+          if (half) {
+            acc = f4_add(acc, x[u]);
+          } else {
+            const float4 t = make_float4(dmf[u] * x[u].x, dmf[u] * x[u].y, dmf[u] * x[u].z, dmf[u] * x[u].w);
+            acc = f4_add(acc, f4_mul(t, w_out));
+            if (WMF) dwout = f4_add(dwout, f4_mul(t, sf[u]));
+          }
+        }
+      }
+    }
+    st4(A.acc_buf + ((p0 + piece_first) * 2 + half) * D + 4 * l16, acc);
+  }
+  if (WMF) block_flush(s_red, dwout, A.dense_grad ? A.dense_grad + NCF_OFF(NCF_P_MF_OUT_W) : nullptr, lane, warp, nwarps,
+                       half == 0, l16);
+}
+
 // Phase 1 - streaming segment sum.  A warp owns a chunk of 32 sorted positions and adds up the
 // upstream gradients of every run piece inside it (a piece = a run of equal ids cut at chunk borders).
 // All loads depend only on the ids, so four sample rows are in flight per lane and nothing waits on a
@@ -868,7 +931,12 @@ int emb_bwd_both(const ncf_adam_cfg* adam, const ncf_tables* T, const float* den
     A.accumulate_wmf = side == 0 ? 1 : 0;
     A.adam = adam_scalars(*adam);
     A.chunk_counter = w.counters + side;
-    emb_bwd_phase1_kernel<<<grid, EB_THREADS, 0, st>>>(A);
+    if (A.other_y && (!A.accumulate_wmf || A.own_y)) {      // the usual case: K1 saved both LayerNorm-ed MF rows
+      if (A.accumulate_wmf) emb_bwd_phase1_lean_kernel<true><<<grid, EB_THREADS, 0, st>>>(A);
+      else emb_bwd_phase1_lean_kernel<false><<<grid, EB_THREADS, 0, st>>>(A);
+    } else {
+      emb_bwd_phase1_kernel<<<grid, EB_THREADS, 0, st>>>(A);
+    }
     NCF_LAUNCH_CHECK();
     emb_bwd_phase2_kernel<<<std::min(grid, num_sms() * 3), EB_THREADS, 0, st>>>(A);     // resident blocks pull chunks
     NCF_LAUNCH_CHECK();

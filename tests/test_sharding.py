@@ -228,3 +228,37 @@ def test_sharded_checkpoint_reshards_on_load(tmp_path):
         for attr in ("w", "m", "v"):
             for k in range(4):
                 assert torch.equal(full(dst, attr, k), full(src, attr, k)), (world, attr, k)
+
+
+@pytest.mark.gpu
+def test_lookahead_routing_does_not_change_results():
+    """train_step(next_ids=...) routes the next batch early; the trajectory is identical to routing it on demand."""
+    import ncf_b200
+    from ncf_b200.sharding import ShardedNCFEngine
+    U, I, B = 300, 120, 64
+    pg, _ = golden_params()
+    g = torch.Generator().manual_seed(3)
+    p = {k: v.clone() for k, v in pg.items()}
+    for k, rows in zip(O.TABLE_KEYS, (U, I, U, I)):
+        p[k] = (torch.rand(rows, 64, generator=g) * 2 - 1) * (1.0 / rows) ** 0.5
+    batches = []
+    for _ in range(4):
+        u = torch.randint(0, U, (B,), generator=g).repeat_interleave(5)
+        i = torch.randint(0, I, (B * 5,), generator=g)
+        t = torch.zeros(B, 5)
+        t[:, 0] = 1
+        batches.append((u.cuda(), i.cuda(), t.reshape(-1).cuda()))
+    out = []
+    for look in (False, True):
+        m = ncf_b200.AdvancedNCF(U, I, 5, 24, dropout=0.0)
+        m.load_state_dict(p)
+        m = m.cuda().train()
+        eng = ShardedNCFEngine(m, U, I, table_mode="fused_sparse", init_tables=[p[k] for k in O.TABLE_KEYS], rank=0, world=1)
+        losses = []
+        for s, b in enumerate(batches):
+            nxt = batches[s + 1][:2] if (look and s + 1 < len(batches)) else None
+            losses.append(float(eng.train_step(*b, next_ids=nxt)))
+        out.append((losses, [t.clone() for t in eng.w]))
+    assert max(abs(a - b) for a, b in zip(out[0][0], out[1][0])) < 1e-5
+    for a, b in zip(out[0][1], out[1][1]):
+        assert float((a - b).abs().mean()) < 1e-6
