@@ -46,6 +46,9 @@ class NCFTrainEngine:
         self._ws = None
         self._out = None
         self._dev_in = None
+        self._model_sig = None
+        self._dense_ends = None
+        self._tables = None
         self.S = 1 + model.negative_samples
         # the id sort of the embedding backward runs on this stream, next to the forward (ncf_set_aux_stream)
         self._aux_stream = torch.cuda.Stream(device=dev) if os.environ.get("NCF_AUX_STREAM", "1") != "0" else None
@@ -70,13 +73,33 @@ class NCFTrainEngine:
         cfg.step = self.step
         return cfg
 
+    def _validate_model(self):
+        """The full check (every dense parameter still a view of the flat buffer, tables contiguous fp32) walks all
+        named parameters - too slow for every step of a loop that synchronises per batch.  It runs when the cheap
+        signature (flat buffer, first / last dense view, the four table pointers) changes."""
+        m = self.model
+        tabs = m._table_params()
+        flat = m._flat
+        def signature():
+            st = m._table_state or {}
+            return ((m._flat.data_ptr(), self._dense_ends[0].data_ptr(), self._dense_ends[1].data_ptr())
+                    + tuple(t.data_ptr() for t in tabs)
+                    + tuple(t.data_ptr() for k in ("m", "v", "touched") for t in st.get(k, ())))
+        if flat is None or self._dense_ends is None or signature() != self._model_sig:
+            m._ensure_flat()
+            dp = m._dense_params()
+            self._dense_ends = (dp[0], dp[-1])
+            self._tables = m._tables_struct()
+            tabs = m._table_params()
+            self._model_sig = signature()
+
     def train_step(self, user_ids: torch.Tensor, item_ids: torch.Tensor, targets: torch.Tensor) -> torch.Tensor:
         """ids int64 [N] and targets fp32 [N] on the device; returns the loss as a device scalar
         (no host sync).  Probabilities of this step stay in `self.outputs`."""
         N = user_ids.numel()
         if N % self.S:
             raise ValueError(f"{N} rows are not groups of {self.S}")
-        self.model._ensure_flat()
+        self._validate_model()
         self.step += 1
         self._reserve(N)
         cfg = self._cfg()
@@ -84,7 +107,7 @@ class NCFTrainEngine:
         adam.lr, (adam.beta1, adam.beta2) = self.hp["lr"], self.hp["betas"]
         adam.eps, adam.weight_decay, adam.step = self.hp["eps"], self.hp["weight_decay"], self.step
         adam.emb_mode = _lib.EMB_ADAM_DENSE_EQUIV if self.table_mode == "fused_dense_equiv" else _lib.EMB_ADAM_SPARSE
-        tables = self.model._tables_struct()
+        tables = self._tables
         self.lib.ncf_set_aux_stream(C.c_void_p(self._aux_stream.cuda_stream) if self._aux_stream is not None else None)
         _lib.check(self.lib.ncf_train_step(C.byref(cfg), C.byref(adam), C.byref(tables), _lib.ptr(self.model._flat),
                                            _lib.ptr(self.dense_grad), _lib.ptr(self.dense_m), _lib.ptr(self.dense_v),
