@@ -32,7 +32,7 @@ STAGES = {
     "MLP backward (head_bwd + mlp_tc_bwd + mlp_tc_wgrad kernels)": ["head_bwd_kernel", "mlp_tc_bwd_kernel", "mlp_tc_wgrad_kernel",
                                                                     "mlp_wgrad_reduce_kernel"],
     "attention backward (attn_tc_bwd_kernel)": ["attn_tc_bwd_kernel", "attn_wgrad_reduce_kernel"],
-    "K6 emb_bwd_adam_both (1 sort + segment-sum + apply, both sides)": ["emb_bwd_phase1_kernel", "emb_bwd_phase2_kernel", "DeviceRadixSort",
+    "K6 emb_bwd_adam_both (1 sort + segment-sum + apply, both sides)": ["emb_bwd_phase1", "emb_bwd_phase2_kernel", "DeviceRadixSort",
                                                                         "gather_sorted_kernel", "ids_to_keys2_kernel"],
     "dense-equivalent Adam sweep": ["emb_adam_sweep_kernel"],
 }
