@@ -133,7 +133,7 @@ def forward(p: Params, user_ids: torch.Tensor, item_ids: torch.Tensor, *, traini
     i_mlp = layer_norm(p[K_PMLP][item_ids], p["mlp_norm.weight"], p["mlp_norm.bias"]).view(B, S, -1)   # :312,316
     attn = multi_head_attention(p, "user_product_attention", u_mlp, i_mlp, i_mlp, num_heads,
                                 masks.get("attn"), dp).reshape(N, -1)                  # :319-326
-    x = torch.cat([attn, torch.zeros(N, temporal_dim, dtype=attn.dtype)], dim=1)       # :329-340
+    x = torch.cat([attn, torch.zeros(N, temporal_dim, dtype=attn.dtype, device=attn.device)], dim=1)   # :329-340
     h = mlp_tower(p, x, [masks.get("mlp0"), masks.get("mlp1"), masks.get("mlp2")], dp) # :344
     mlp_pred = linear(h, p["mlp_output.weight"], p["mlp_output.bias"])                 # :345
     z = linear(torch.cat([mf_pred, mlp_pred], dim=1), p["final.0.weight"], p["final.0.bias"])  # :353
@@ -165,7 +165,7 @@ def forward_simple(p: Params, user_ids: torch.Tensor, item_ids: torch.Tensor,
         i_mlp = i_mlp * (1 + 0.3 * tt)                                                 # :456
         tail = t                                                                       # :467
     else:
-        tail = torch.zeros(n, temporal_dim, dtype=u_mf.dtype)                          # :471-476
+        tail = torch.zeros(n, temporal_dim, dtype=u_mf.dtype, device=u_mf.device)     # :471-476
     mf_pred = linear(u_mf * i_mf, p["mf_output.weight"], p["mf_output.bias"])          # :447-448
     attn = multi_head_attention(p, "user_product_attention", u_mlp.unsqueeze(1), i_mlp.unsqueeze(1),
                                 i_mlp.unsqueeze(1), num_heads).squeeze(1)              # :459-463
