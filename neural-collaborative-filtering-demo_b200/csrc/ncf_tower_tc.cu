@@ -151,7 +151,7 @@ __device__ __forceinline__ void mlp_epilogue(uint32_t tmem_acc, int q, int h, in
   const uint32_t yaddr = tmem_y + ((uint32_t)(q * 32) << 16) + (h * PART) / 2;
   uint32_t yw[16];
   uint32_t pk[PART / 2];
-  float sum = 0.f, sq = 0.f;
+  float sum4[2] = {0.f, 0.f}, sq4[2] = {0.f, 0.f};     // independent chains: the adds do not serialise
 #pragma unroll
   for (int ch = 0; ch < NCH; ++ch) {
     float v[CW];
@@ -167,8 +167,8 @@ __device__ __forceinline__ void mlp_epilogue(uint32_t tmem_acc, int q, int h, in
       for (int k2 = 0; k2 < 2; ++k2) {
         const uint32_t w = pack_bf16(fmaxf(v[4 * i4 + 2 * k2] + bb[2 * k2], 0.f), fmaxf(v[4 * i4 + 2 * k2 + 1] + bb[2 * k2 + 1], 0.f));
         const float x0 = __uint_as_float(w << 16), x1 = __uint_as_float(w & 0xffff0000u);
-        sum += x0 + x1;
-        sq = fmaf(x0, x0, fmaf(x1, x1, sq));
+        sum4[k2] += x0 + x1;
+        sq4[k2] = fmaf(x0, x0, fmaf(x1, x1, sq4[k2]));
         pk[ch * (CW / 2) + i4 * 2 + k2] = w;
       }
     }
@@ -185,6 +185,7 @@ __device__ __forceinline__ void mlp_epilogue(uint32_t tmem_acc, int q, int h, in
       if (r_img) *reinterpret_cast<uint4*>(r_img + tile_off(rt, c0 + 8 * g8, C)) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
     }
   }
+  float sum = sum4[0] + sum4[1], sq = sq4[0] + sq4[1];
   s_stat[(rt * MLP_NH + h) * 2 + 0] = sum;
   s_stat[(rt * MLP_NH + h) * 2 + 1] = sq;
   __syncthreads();
@@ -1178,6 +1179,7 @@ __device__ __forceinline__ void mlp_bwd_layer(uint32_t tmem_dy, float dml, const
   // `rw` arrives holding chunk 0 (loaded by the caller BEFORE it waited for the upstream MMA); with more than
   // one chunk the next one is requested before the current one is consumed, wrapping around to chunk 0 for pass C.
   float s1 = 0.f, s2 = 0.f;
+  float s1p[4] = {0.f, 0.f, 0.f, 0.f}, s2p[4] = {0.f, 0.f, 0.f, 0.f};      // independent chains
 #pragma unroll 1
   for (int ch = 0; ch < NCH; ++ch) {
     const int c0 = h * PART + ch * CW;
@@ -1194,8 +1196,8 @@ __device__ __forceinline__ void mlp_bwd_layer(uint32_t tmem_dy, float dml, const
       const float xh0 = fmaf(fabsf(__uint_as_float(lo)), rstd, nmr);
       const float xh1 = fmaf(fabsf(__uint_as_float(w & 0xffff0000u)), rstd, nmr);
       const float dg0 = d0 * g2.x, dg1 = d1 * g2.y;
-      s1 += dg0 + dg1;
-      s2 = fmaf(dg0, xh0, fmaf(dg1, xh1, s2));
+      s1p[i2 & 3] += dg0 + dg1;
+      s2p[i2 & 3] = fmaf(dg0, xh0, fmaf(dg1, xh1, s2p[i2 & 3]));
       t[2 * i2] = d0 * xh0;
       t[2 * i2 + 1] = d1 * xh1;
       dy[2 * i2] = d0;
@@ -1212,6 +1214,8 @@ __device__ __forceinline__ void mlp_bwd_layer(uint32_t tmem_dy, float dml, const
       atomicAdd(s_acc + C + c0 + lane, cb);
     }
   }
+  s1 = (s1p[0] + s1p[1]) + (s1p[2] + s1p[3]);
+  s2 = (s2p[0] + s2p[1]) + (s2p[2] + s2p[3]);
   s_statB[(rt * MLP_NH + h) * 2 + 0] = s1;
   s_statB[(rt * MLP_NH + h) * 2 + 1] = s2;
   __syncthreads();
