@@ -243,6 +243,18 @@ NCF_API int ncf_score_topk(const ncf_tables* tables, const float* dense, const f
                    int64_t* topk_idx, float* topk_score,
                    void* workspace, int64_t workspace_bytes, void* stream);
 
+/* The same result through a tensor-core pre-filter (large catalogues, many users per call): item tiles as
+ * bf16 operand images + per-item error margin (ncf_item_image, built once per fold); a tcgen05 GEMM bounds
+ * every logit from above (|error| <= 2^-7 ||u|| ||p_i||) and only pairs that can enter a list are re-scored
+ * with the exact fp32 arithmetic of ncf_score_topk: bit-identical indices and scores. */
+NCF_API int64_t ncf_item_image_bytes(int64_t I);
+NCF_API int ncf_item_image(const float* p_hat, const float* g, int64_t I, void* image, void* stream);
+NCF_API int64_t ncf_score_topk_tc_workspace_bytes(int64_t n_users, int64_t I, int32_t k);
+NCF_API int ncf_score_topk_tc(const ncf_tables* tables, const float* dense, const float* p_hat, const float* g,
+                      const void* image, const int64_t* user_ids, int64_t n_users, int64_t I, int32_t k,
+                      int64_t* topk_idx, float* topk_score,
+                      void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---- row-wise sharding (torchrec ROW_WISE convention) ------------------------- */
 /* block = ceil(rows/world); owner = id / block; local = id % block.  Buckets ids by owner:
  * counts[world], perm[n] (stable: position of each id in owner-major order), local_ids[n]

@@ -359,6 +359,13 @@ __global__ void __launch_bounds__(256) topk_merge_kernel(const unsigned long lon
   }
 }
 
+int launch_topk_merge(const unsigned long long* part, int nsplit, int k, int64_t n_users, int64_t* idx, float* score,
+                      cudaStream_t st) {
+  topk_merge_kernel<<<(unsigned)n_users, 256, 0, st>>>(part, nsplit, k, idx, score);
+  NCF_LAUNCH_CHECK();
+  return NCF_OK;
+}
+
 // ---- shard bucketize ---------------------------------------------------------------------------
 __global__ void owner_keys_kernel(const int64_t* __restrict__ ids, int64_t n, int64_t block, uint32_t* __restrict__ keys,
                                   int32_t* __restrict__ vals) {

@@ -1,0 +1,385 @@
+// Full-catalogue scoring + top-k with a tensor-core PRE-FILTER (app.py:43-77 at the config[4] scale).
+//
+// The exact kernel (ncf_score.cu) forms every logit LN(U_mf[u]) . P_hat[i] + g[i] with 64 fp32 FMAs; almost all
+// of them lose against the user's running k-th best.  Here a tcgen05 bf16 GEMM (128 users x 256 items per tile,
+// accumulators double-buffered in TMEM) produces APPROXIMATE logits with a rigorous error bound
+//     |z_bf16 - z| <= 2^-7 * ||u||_2 * ||p_i||_2          (bf16 rounding of both operands, Cauchy-Schwarz, 2x slack)
+// and only pairs whose upper bound reaches the running threshold are re-scored EXACTLY - same fp32 FMA order, same
+// sigmoid, same (score desc, index asc) key as the exact kernel - so the result is bit-identical to it while the
+// CUDA cores touch a tiny fraction of the 10^13 pairs.  Item tiles arrive as ready operand images
+// (ncf_item_image: bf16 canonical layout + g + 2^-7 ||p_i||) by one TMA bulk copy each.
+#include "ncf_tower.cuh"
+#include "ncf_umma.cuh"
+
+namespace ncf {
+using namespace umma;
+
+constexpr int SC_THREADS = 512;            // 16 warps: TMEM lane quarter x accumulator column quarter
+constexpr int SC_UT = 128;                 // users per CTA (M)
+constexpr int SC_IT = 256;                 // items per tile (N)
+constexpr int SC_KMAX = 128;               // running list length (k <= 128), same as the exact kernel
+constexpr int SC_CAP = 512;                // list + candidates per user
+constexpr uint32_t SC_IMG = SC_IT * 64 * 2;                 // bf16 operand image of one item tile
+constexpr uint32_t SC_TILE_BYTES = SC_IMG + 2 * SC_IT * 4;  // + g[256] + margin[256]
+constexpr float SC_EPS = 0.0078125f;       // 2^-7
+
+constexpr uint32_t SCS_A = 0;                               // [128][64] bf16 image            16 KB
+constexpr uint32_t SCS_U = SCS_A + SC_UT * 64 * 2;          // [128][64] fp32 LN'd user rows   32 KB
+constexpr uint32_t SCS_B = SCS_U + SC_UT * 64 * 4;          // 2 x item tile                    68 KB
+constexpr uint32_t SCS_SORT = SCS_B + 2 * SC_TILE_BYTES;    // 16 warps x 512 keys              64 KB
+constexpr uint32_t SCS_NU = SCS_SORT + 16 * SC_CAP * 8;     // ||u|| per user
+constexpr uint32_t SCS_LTHR = SCS_NU + SC_UT * 4;           // logit pre-filter per user
+constexpr uint32_t SCS_KTHR = SCS_LTHR + SC_UT * 4;         // key of the running k-th best
+constexpr uint32_t SCS_CNT = SCS_KTHR + SC_UT * 8;
+constexpr int SC_QCAP = 2048;                               // survivors of one tile queued for exact re-scoring
+constexpr uint32_t SCS_QUEUE = SCS_CNT + SC_UT * 4;         // (row << 8 | column) per survivor
+constexpr uint32_t SCS_TOTAL = SCS_QUEUE + SC_QCAP * 4;
+
+__device__ __forceinline__ unsigned long long sc_key(float score, uint32_t idx) {
+  return ((unsigned long long)__float_as_uint(score) << 32) | (unsigned long long)(0xffffffffu - idx);
+}
+
+// ---- item tile images ----------------------------------------------------------------------------------
+// thread = (item, 8-column chunk); the 8 chunk threads of an item are adjacent lanes
+__global__ void __launch_bounds__(256) item_image_kernel(const float* __restrict__ p_hat, const float* __restrict__ g, int64_t I,
+                                                         uint8_t* __restrict__ img) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t i = t >> 3;
+  const int j = (int)(t & 7);
+  const int64_t ntiles = (I + SC_IT - 1) / SC_IT;
+  if (i >= ntiles * SC_IT) return;
+  float4 a = make_float4(0, 0, 0, 0), b = a;
+  if (i < I) {
+    a = ldg4(p_hat + i * 64 + 8 * j);
+    b = ldg4(p_hat + i * 64 + 8 * j + 4);
+  }
+  float ss = f4_dot(a, a) + f4_dot(b, b);
+  ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+  ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+  ss += __shfl_xor_sync(0xffffffffu, ss, 4);
+  uint8_t* tile = img + (i / SC_IT) * SC_TILE_BYTES;
+  const uint32_t r = (uint32_t)(i % SC_IT);
+  *reinterpret_cast<uint4*>(tile + tile_off(r, 8 * j, 64)) =
+      make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(b.x, b.y), pack_bf16(b.z, b.w));
+  if (j == 0) {
+    float* tail = reinterpret_cast<float*>(tile + SC_IMG);
+    tail[r] = i < I ? __ldg(g + i) : -INFINITY;          // padding items can never pass the filter
+    tail[SC_IT + r] = SC_EPS * sqrtf(ss) * 1.0001f;      // rounded up a little: the bound must stay a bound
+  }
+}
+
+// descending bitonic sort of 512 keys in shared memory by ONE warp
+__device__ __forceinline__ void warp_sort512_desc(unsigned long long* a, int lane) {
+  for (int k = 2; k <= SC_CAP; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      __syncwarp();
+#pragma unroll 4
+      for (int m = 0; m < SC_CAP / 64; ++m) {
+        // the m-th compare-exchange of this lane: enumerate the indices whose bit j is clear
+        const int p = lane + 32 * m;                       // 0..255
+        const int i = ((p & ~(j - 1)) << 1) | (p & (j - 1));
+        const int l = i | j;
+        const unsigned long long x = a[i], y = a[l];
+        const bool desc = (i & k) == 0;
+        if (desc ? x < y : x > y) {
+          a[i] = y;
+          a[l] = x;
+        }
+      }
+    }
+  }
+  __syncwarp();
+}
+
+struct ScoreTcArgs {
+  const float* t_umf;
+  const float* dense;
+  const float* p_hat;      // [I,64] fp32 (exact re-scoring)
+  const uint8_t* img;      // item tile images
+  const int64_t* user_ids;
+  int64_t n_users, I;
+  int nsplit;
+  unsigned long long* cand;   // [gridDim.x * gridDim.y][128][512]
+  unsigned long long* part;   // [n_users][nsplit][128]
+};
+
+__global__ void __launch_bounds__(SC_THREADS, 1) score_tc_kernel(ScoreTcArgs A) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t full[2], accb[2];
+  __shared__ uint32_t tmem_slot;
+  __shared__ int s_qn;
+  uint32_t* s_queue = reinterpret_cast<uint32_t*>(smem + SCS_QUEUE);
+  float* s_u = reinterpret_cast<float*>(smem + SCS_U);
+  float* s_nu = reinterpret_cast<float*>(smem + SCS_NU);
+  float* s_lthr = reinterpret_cast<float*>(smem + SCS_LTHR);
+  unsigned long long* s_kthr = reinterpret_cast<unsigned long long*>(smem + SCS_KTHR);
+  int* s_cnt = reinterpret_cast<int*>(smem + SCS_CNT);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int q = warp & 3, cq = warp >> 2;
+  const int row = q * 32 + lane;
+  const int64_t u0 = (int64_t)blockIdx.x * SC_UT;
+  const int split = blockIdx.y;
+  const int nu = (int)min((int64_t)SC_UT, A.n_users - u0);
+  unsigned long long* cand = A.cand + ((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * SC_UT * SC_CAP;
+
+  // LN_mf of the tile's user rows: one warp per user, two-pass variance like nn.LayerNorm (same arithmetic as the
+  // exact kernel); fp32 row for the exact re-scoring, bf16 operand image, ||u||
+  for (int uu = warp; uu < SC_UT; uu += SC_THREADS / 32) {
+    float x0 = 0.f, x1 = 0.f;
+    if (uu < nu) {
+      const float* r = A.t_umf + A.user_ids[u0 + uu] * D;
+      x0 = r[lane];
+      x1 = r[lane + 32];
+    }
+    const float mean = warp_sum(x0 + x1) * (1.0f / D);
+    const float d0 = x0 - mean, d1 = x1 - mean;
+    const float rstd = rsqrtf(warp_sum(d0 * d0 + d1 * d1) * (1.0f / D) + LN_EPS);
+    float y0 = fmaf(d0 * rstd, __ldg(A.dense + NCF_OFF(NCF_P_MF_NORM_W) + lane), __ldg(A.dense + NCF_OFF(NCF_P_MF_NORM_B) + lane));
+    float y1 = fmaf(d1 * rstd, __ldg(A.dense + NCF_OFF(NCF_P_MF_NORM_W) + lane + 32),
+                    __ldg(A.dense + NCF_OFF(NCF_P_MF_NORM_B) + lane + 32));
+    if (uu >= nu) {
+      y0 = 0.f;
+      y1 = 0.f;
+    }
+    s_u[uu * 64 + lane] = y0;
+    s_u[uu * 64 + lane + 32] = y1;
+    reinterpret_cast<__nv_bfloat16*>(smem + SCS_A + tile_off(uu, lane, 64))[0] = __float2bfloat16_rn(y0);
+    reinterpret_cast<__nv_bfloat16*>(smem + SCS_A + tile_off(uu, lane + 32, 64))[0] = __float2bfloat16_rn(y1);
+    const float nn = sqrtf(warp_sum(y0 * y0 + y1 * y1)) * 1.0001f;
+    if (lane == 0) {
+      s_nu[uu] = nn;
+      s_lthr[uu] = uu < nu ? -INFINITY : INFINITY;      // rows without a user never pass
+      s_kthr[uu] = 0ull;
+      s_cnt[uu] = SC_KMAX;                              // slots [0,KMAX) = the running list (zeros = empty)
+    }
+  }
+  for (int i = tid; i < SC_UT * SC_KMAX; i += SC_THREADS) cand[(i / SC_KMAX) * SC_CAP + (i % SC_KMAX)] = 0ull;
+  if (tid == 0) {
+    s_qn = 0;
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    mbar_init(&accb[0], 1);
+    mbar_init(&accb[1], 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_slot, 512);
+  fence_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+  const uint32_t sA = smem_addr(smem + SCS_A);
+
+  const int64_t ntile_all = (A.I + SC_IT - 1) / SC_IT;
+  const int64_t per = (ntile_all + A.nsplit - 1) / A.nsplit;
+  const int64_t t_begin = split * per, t_end = min(ntile_all, t_begin + per);
+  const int64_t ntile = t_begin < t_end ? t_end - t_begin : 0;
+
+  auto load_tile = [&](int b, int64_t t) {            // tid 0
+    mbar_arrive_expect_tx(&full[b], SC_TILE_BYTES);
+    bulk_g2s(smem + SCS_B + b * SC_TILE_BYTES, A.img + (t_begin + t) * SC_TILE_BYTES, SC_TILE_BYTES, &full[b]);
+  };
+  auto issue_mma = [&](int b) {                        // tid 0
+    issue_gemm(tmem + 256 * b, sA, 128, 64 * 16, 256, smem_addr(smem + SCS_B + b * SC_TILE_BYTES), 128, 64 * 16, 256,
+               make_idesc(128, SC_IT, false, false), 4, false);
+    mma_commit(&accb[b]);
+  };
+  // merge the candidate buffer of one user into its running list (one warp): sort, keep the best KMAX, refresh the
+  // thresholds
+  unsigned long long* s_sort = reinterpret_cast<unsigned long long*>(smem + SCS_SORT) + warp * SC_CAP;
+  auto merge_user = [&](int uu) {
+    const int cnt = s_cnt[uu];
+    unsigned long long* c = cand + (int64_t)uu * SC_CAP;
+    for (int i = lane; i < SC_CAP; i += 32) s_sort[i] = i < cnt ? c[i] : 0ull;
+    warp_sort512_desc(s_sort, lane);
+    for (int i = lane; i < SC_KMAX; i += 32) c[i] = s_sort[i];
+    if (lane == 0) {
+      s_cnt[uu] = SC_KMAX;
+      const unsigned long long kth = s_sort[SC_KMAX - 1];
+      s_kthr[uu] = kth;
+      const float sk = __uint_as_float((uint32_t)(kth >> 32));
+      float lt = -INFINITY;
+      if (kth != 0ull && sk > 0.f && sk < 1.f) {          // same pre-filter as the exact kernel
+        lt = logf(sk / (1.0f - sk));
+        lt -= 1e-4f + 1e-4f * fabsf(lt);
+      }
+      s_lthr[uu] = lt;
+    }
+    __syncwarp();
+  };
+
+  // exact logit of (user row r, item base + col) with the exact kernel's arithmetic; pushes the key if it can enter
+  auto rescore = [&](int r, int col, int64_t base, float gi, float lthr, unsigned long long kthr) {
+    const int64_t i = base + col;
+    const float* pr = A.p_hat + i * 64;
+    const float* ur = s_u + r * 64;
+    float4 p[16];
+#pragma unroll
+    for (int k4 = 0; k4 < 16; ++k4) p[k4] = ldg4(pr + 4 * k4);
+    float acc = 0.f;
+#pragma unroll
+    for (int k4 = 0; k4 < 16; ++k4) {            // ascending k with fmaf: the exact kernel's order
+      const float4 uv = *reinterpret_cast<const float4*>(ur + 4 * k4);
+      acc = fmaf(uv.x, p[k4].x, acc);
+      acc = fmaf(uv.y, p[k4].y, acc);
+      acc = fmaf(uv.z, p[k4].z, acc);
+      acc = fmaf(uv.w, p[k4].w, acc);
+    }
+    const float ze = acc + gi;
+    if (ze >= lthr) {
+      const float sc = 1.0f / (1.0f + expf(-ze));
+      const unsigned long long key = sc_key(sc, (uint32_t)i);
+      if (key > kthr) {
+        const int pos = atomicAdd(&s_cnt[r], 1);
+        cand[(int64_t)r * SC_CAP + pos] = key;
+      }
+    }
+  };
+
+  if (tid == 0 && ntile > 0) {
+    load_tile(0, 0);
+    if (ntile > 1) load_tile(1, 1);
+    mbar_wait(&full[0], 0);
+    fence_after_sync();
+    issue_mma(0);
+  }
+  for (int64_t t = 0; t < ntile; ++t) {
+    const int b = (int)(t & 1);
+    if (tid == 0 && t + 1 < ntile) {                    // the other accumulator was drained by the previous epilogue
+      mbar_wait(&full[b ^ 1], (uint32_t)(((t + 1) >> 1) & 1));
+      fence_after_sync();
+      issue_mma(b ^ 1);
+    }
+    if (warp == 0) mbar_wait(&accb[b], (uint32_t)((t >> 1) & 1));
+    __syncthreads();
+    fence_after_sync();
+    const float* tail = reinterpret_cast<const float*>(smem + SCS_B + b * SC_TILE_BYTES + SC_IMG);
+    const float lthr = s_lthr[row], nrm = s_nu[row];
+    const unsigned long long kthr = s_kthr[row];
+    const int64_t base = (t_begin + t) * SC_IT;
+#pragma unroll 1
+    for (int ch = 0; ch < 2; ++ch) {
+      float z[32];
+      tmem_ld32(tmem + 256 * b + lane_addr + cq * 64 + ch * 32, z);
+      const int j0 = cq * 64 + ch * 32;
+#pragma unroll
+      for (int j4 = 0; j4 < 8; ++j4) {
+        const float4 g4 = *reinterpret_cast<const float4*>(tail + j0 + 4 * j4);
+        const float4 m4 = *reinterpret_cast<const float4*>(tail + SC_IT + j0 + 4 * j4);
+        const float gg[4] = {g4.x, g4.y, g4.z, g4.w}, mm[4] = {m4.x, m4.y, m4.z, m4.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float bound = fmaf(nrm, mm[e], z[4 * j4 + e] + gg[e]);
+          if (bound >= lthr) {                           // rare after the first tiles
+            const int col = j0 + 4 * j4 + e;
+            const int qp = atomicAdd(&s_qn, 1);
+            if (qp < SC_QCAP) s_queue[qp] = ((uint32_t)row << 8) | (uint32_t)col;      // re-scored below, one thread each
+            else rescore(row, col, base, gg[e], lthr, kthr);                            // queue full (warm-up): in place
+          }
+        }
+      }
+    }
+    // exact re-scoring of the queued survivors: every thread takes one (independent 128-bit loads + the FMA chain),
+    // instead of one diverged lane stalling its whole warp per survivor
+    __syncthreads();
+    {
+      const int qn = min(s_qn, SC_QCAP);
+      for (int e = tid; e < qn; e += SC_THREADS) {
+        const uint32_t v = s_queue[e];
+        const int r = (int)(v >> 8), col = (int)(v & 255u);
+        rescore(r, col, base, tail[col], s_lthr[r], s_kthr[r]);
+      }
+    }
+    fence_before_sync();
+    __syncthreads();                                     // accumulator b and the tile's g / margin are free
+    if (tid == 0) s_qn = 0;
+    if (tid == 0 && t + 2 < ntile) load_tile(b, t + 2);
+    // a tile adds at most 256 candidates per user: merge every list that could overflow during the next one
+    __threadfence_block();
+    for (int uu = warp; uu < nu; uu += SC_THREADS / 32)
+      if (s_cnt[uu] > SC_CAP - SC_IT) merge_user(uu);
+    __syncthreads();
+  }
+  for (int uu = warp; uu < nu; uu += SC_THREADS / 32) {
+    merge_user(uu);
+    unsigned long long* dst = A.part + ((u0 + uu) * A.nsplit + split) * SC_KMAX;
+    for (int k = lane; k < SC_KMAX; k += 32) dst[k] = s_sort[k];
+    __syncwarp();
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+static int sc_splits(int64_t n_users, int64_t I) {
+  const int64_t tiles = (n_users + SC_UT - 1) / SC_UT;
+  int64_t want = std::max<int64_t>(1, (int64_t)num_sms() / tiles);          // one CTA per SM: whole waves only
+  const int64_t ntile = (I + SC_IT - 1) / SC_IT;
+  want = std::min<int64_t>(std::min<int64_t>(want, std::max<int64_t>(1, ntile / 16)), 32);    // 32 x 128 keys = the merge kernel's limit
+  return (int)want;
+}
+}  // namespace ncf
+
+using namespace ncf;
+
+// defined in ncf_score.cu
+namespace ncf {
+int launch_topk_merge(const unsigned long long* part, int nsplit, int k, int64_t n_users, int64_t* idx, float* score, cudaStream_t st);
+}
+
+extern "C" int64_t ncf_item_image_bytes(int64_t I) { return ((std::max<int64_t>(I, 1) + SC_IT - 1) / SC_IT) * (int64_t)SC_TILE_BYTES; }
+
+extern "C" int ncf_item_image(const float* p_hat, const float* g, int64_t I, void* img, void* stream) {
+  NCF_REQUIRE(p_hat && g && img && I >= 1, "item_image: bad argument");
+  const int64_t threads = ((I + SC_IT - 1) / SC_IT) * SC_IT * 8;
+  item_image_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p_hat, g, I, static_cast<uint8_t*>(img));
+  NCF_LAUNCH_CHECK();
+  return NCF_OK;
+}
+
+extern "C" int64_t ncf_score_topk_tc_workspace_bytes(int64_t n_users, int64_t I, int32_t k) {
+  (void)k;
+  const int64_t n = std::max<int64_t>(n_users, 1);
+  const int64_t tiles = (n + SC_UT - 1) / SC_UT;
+  const int ns = sc_splits(n, I);
+  return align_up(n * ns * SC_KMAX * 8, 256) + align_up(tiles * ns * SC_UT * SC_CAP * 8, 256);
+}
+
+extern "C" int ncf_score_topk_tc(const ncf_tables* T, const float* dense, const float* p_hat, const float* g, const void* img,
+                                 const int64_t* user_ids, int64_t n_users, int64_t I, int32_t k, int64_t* topk_idx,
+                                 float* topk_score, void* workspace, int64_t workspace_bytes, void* stream) {
+  NCF_REQUIRE(T && dense && p_hat && g && img && user_ids && topk_idx && topk_score && workspace, "score_topk_tc: null argument");
+  NCF_REQUIRE(k >= 1 && k <= SC_KMAX, "score_topk_tc: k=%d outside [1,%d]", k, SC_KMAX);
+  NCF_REQUIRE(I >= 1 && I < ((int64_t)1 << 32) - 1, "score_topk_tc: bad catalogue size");
+  if (n_users == 0) return NCF_OK;
+  const int64_t need = ncf_score_topk_tc_workspace_bytes(n_users, I, k);
+  if (workspace_bytes < need) {
+    set_error("score_topk_tc: workspace %lld < %lld", (long long)workspace_bytes, (long long)need);
+    return NCF_ERR_WORKSPACE;
+  }
+  const int ns = sc_splits(n_users, I);
+  const int64_t tiles = (n_users + SC_UT - 1) / SC_UT;
+  NCF_REQUIRE(tiles < ((int64_t)1 << 31), "score_topk_tc: too many users in one call");
+  cudaStream_t st = (cudaStream_t)stream;
+  static bool configured = false;
+  if (!configured) {
+    NCF_CUDA(cudaFuncSetAttribute(score_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCS_TOTAL));
+    configured = true;
+  }
+  ScoreTcArgs A{};
+  A.t_umf = T->w[0];
+  A.dense = dense;
+  A.p_hat = p_hat;
+  A.img = static_cast<const uint8_t*>(img);
+  A.user_ids = user_ids;
+  A.n_users = n_users;
+  A.I = I;
+  A.nsplit = ns;
+  A.part = static_cast<unsigned long long*>(workspace);
+  A.cand = reinterpret_cast<unsigned long long*>(static_cast<char*>(workspace) + align_up(n_users * ns * SC_KMAX * 8, 256));
+  dim3 grid((unsigned)tiles, ns);
+  score_tc_kernel<<<grid, SC_THREADS, SCS_TOTAL, st>>>(A);
+  NCF_LAUNCH_CHECK();
+  return launch_topk_merge(A.part, ns, k, n_users, topk_idx, topk_score, st);
+}

@@ -3,10 +3,15 @@
 `CatalogueScorer` folds the item side once (`ncf_item_fold`: eval-mode attention sees one key, so
 logit(u,i) = LN_mf(U_mf[u]).P_hat[i] + g[i]) and then ranks users against the whole catalogue with
 `ncf_score_topk`; order = score descending, ties -> lowest item index (pandas nlargest keep='first').
+
+Large catalogues with many users per call go through `ncf_score_topk_tc`: a tcgen05 bf16 GEMM bounds every logit
+from above and only the pairs that could enter a user's list are re-scored exactly, so the output is bit-identical
+to `ncf_score_topk` (tests/test_gpu_parity.py) at a fraction of the CUDA-core work.
 """
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Tuple
 
 import torch
@@ -21,6 +26,8 @@ class CatalogueScorer:
         self.lib = _lib.load()
         self.p_hat = None
         self.g = None
+        self.img = None            # item tile images of the tensor-core pre-filter (large catalogues)
+        self.use_tc = os.environ.get("NCF_SCORE_TC", "1") != "0"
         self.refresh()
 
     @torch.no_grad()
@@ -37,6 +44,14 @@ class CatalogueScorer:
         tables = m._tables_struct()
         _lib.check(self.lib.ncf_item_fold(C.byref(tables), _lib.ptr(m._flat), _lib.ptr(self.p_hat), _lib.ptr(self.g),
                                           _lib.ptr(ws), nbytes, _stream(dev)), "ncf_item_fold")
+        self.img = None
+        if self.use_tc and I >= self.TC_MIN_ITEMS:
+            self.img = torch.empty(int(self.lib.ncf_item_image_bytes(I)), dtype=torch.uint8, device=dev)
+            _lib.check(self.lib.ncf_item_image(_lib.ptr(self.p_hat), _lib.ptr(self.g), I, _lib.ptr(self.img), _stream(dev)),
+                       "ncf_item_image")
+
+    TC_MIN_ITEMS = 1 << 16      # below this the per-CTA warm-up of the pre-filter does not pay
+    TC_MIN_USERS = 64
 
     @torch.no_grad()
     def topk(self, user_ids: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -50,9 +65,16 @@ class CatalogueScorer:
         sc = torch.empty(n, k_eff, dtype=torch.float32, device=dev)
         if n == 0:
             return idx, sc
+        tables = m._tables_struct()
+        if self.img is not None and n >= self.TC_MIN_USERS:
+            nbytes = int(self.lib.ncf_score_topk_tc_workspace_bytes(n, I, k_eff))
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            _lib.check(self.lib.ncf_score_topk_tc(C.byref(tables), _lib.ptr(m._flat), _lib.ptr(self.p_hat), _lib.ptr(self.g),
+                                                  _lib.ptr(self.img), _lib.ptr(u), n, I, k_eff, _lib.ptr(idx), _lib.ptr(sc),
+                                                  _lib.ptr(ws), nbytes, _stream(dev)), "ncf_score_topk_tc")
+            return idx, sc
         nbytes = int(self.lib.ncf_score_topk_workspace_bytes(n, I, k_eff))
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        tables = m._tables_struct()
         _lib.check(self.lib.ncf_score_topk(C.byref(tables), _lib.ptr(m._flat), _lib.ptr(self.p_hat), _lib.ptr(self.g),
                                            _lib.ptr(u), n, I, k_eff, _lib.ptr(idx), _lib.ptr(sc), _lib.ptr(ws), nbytes,
                                            _stream(dev)), "ncf_score_topk")

@@ -471,3 +471,32 @@ def test_topk_large_catalogue_tiled_kernel():
         thr = full[r][want[r][-1]]
         for mi in missing:
             assert abs(float(full[r][mi] - thr)) < 1e-6
+
+
+def test_topk_tensor_core_prefilter_is_bit_identical_to_the_exact_kernel():
+    """ncf_score_topk_tc (tcgen05 bf16 upper bound + exact re-scoring of the survivors) returns exactly the indices
+    and scores of ncf_score_topk: ragged user count, catalogue not a multiple of the 256-item tile, several splits."""
+    import os
+    import ncf_b200
+    p, _ = golden_params()
+    g = torch.Generator().manual_seed(33)
+    I = (1 << 20) + 333        # above the exact path's small-catalogue switch: both sides normalise the user rows alike
+    U = 2000
+    q = {k: v.clone() for k, v in p.items()}
+    for k, rows in zip(O.TABLE_KEYS, (U, I, U, I)):
+        q[k] = (torch.rand(rows, 64, generator=g) * 2 - 1) * (1.0 / rows) ** 0.5 * (30.0 if "product" in k else 1.0)
+    m = _model(q, U, I).eval()
+    users = torch.randint(0, U, (300,), generator=g).cuda()
+    tc = ncf_b200.CatalogueScorer(m)
+    assert tc.img is not None
+    idx_tc, sc_tc = tc.topk(users, 100)
+    os.environ["NCF_SCORE_TC"] = "0"
+    try:
+        ex = ncf_b200.CatalogueScorer(m)
+    finally:
+        os.environ.pop("NCF_SCORE_TC", None)
+    assert ex.img is None
+    idx_ex, sc_ex = ex.topk(users, 100)
+    assert torch.equal(idx_tc, idx_ex)
+    assert torch.equal(sc_tc, sc_ex)
+    assert int(idx_tc.min()) >= 0 and int(idx_tc.max()) < I
