@@ -32,8 +32,11 @@ constexpr uint32_t SCS_LTHR = SCS_NU + SC_UT * 4;           // logit pre-filter 
 constexpr uint32_t SCS_KTHR = SCS_LTHR + SC_UT * 4;         // key of the running k-th best
 constexpr uint32_t SCS_CNT = SCS_KTHR + SC_UT * 8;
 constexpr int SC_QCAP = 2048;                               // survivors of one tile queued for exact re-scoring
+constexpr int SC_HIGH = SC_CAP - 64;                        // merge a list when it holds more than this
+constexpr int SC_RCAP = SC_UT * SC_IT;                      // pairs whose candidate buffer was full: at most one tile's worth
 constexpr uint32_t SCS_QUEUE = SCS_CNT + SC_UT * 4;         // (row << 8 | column) per survivor
 constexpr uint32_t SCS_TOTAL = SCS_QUEUE + SC_QCAP * 4;
+constexpr int64_t SC_CTA_WS = (int64_t)SC_UT * SC_CAP * 8 + 2 * ((int64_t)SC_RCAP * 8 + SC_RCAP);   // candidates + 2 retry lists
 
 __device__ __forceinline__ unsigned long long sc_key(float score, uint32_t idx) {
   return ((unsigned long long)__float_as_uint(score) << 32) | (unsigned long long)(0xffffffffu - idx);
@@ -107,8 +110,9 @@ __global__ void __launch_bounds__(SC_THREADS, 1) score_tc_kernel(ScoreTcArgs A) 
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t full[2], accb[2];
   __shared__ uint32_t tmem_slot;
-  __shared__ int s_qn;
+  __shared__ int s_qn, s_rn;
   uint32_t* s_queue = reinterpret_cast<uint32_t*>(smem + SCS_QUEUE);
+
   float* s_u = reinterpret_cast<float*>(smem + SCS_U);
   float* s_nu = reinterpret_cast<float*>(smem + SCS_NU);
   float* s_lthr = reinterpret_cast<float*>(smem + SCS_LTHR);
@@ -120,7 +124,16 @@ __global__ void __launch_bounds__(SC_THREADS, 1) score_tc_kernel(ScoreTcArgs A) 
   const int64_t u0 = (int64_t)blockIdx.x * SC_UT;
   const int split = blockIdx.y;
   const int nu = (int)min((int64_t)SC_UT, A.n_users - u0);
-  unsigned long long* cand = A.cand + ((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * SC_UT * SC_CAP;
+  // this CTA's slice of the workspace: candidate buffers, then two retry lists (keys, rows) used alternately
+  uint8_t* cta_ws = reinterpret_cast<uint8_t*>(A.cand) + ((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * SC_CTA_WS;
+  unsigned long long* cand = reinterpret_cast<unsigned long long*>(cta_ws);
+  unsigned long long* retry_key[2];
+  uint8_t* retry_row[2];
+  retry_key[0] = cand + (int64_t)SC_UT * SC_CAP;
+  retry_key[1] = retry_key[0] + SC_RCAP;
+  retry_row[0] = reinterpret_cast<uint8_t*>(retry_key[1] + SC_RCAP);
+  retry_row[1] = retry_row[0] + SC_RCAP;
+  int rsel = 0;                                          // list that receives the overflowing pairs (uniform)
 
   // LN_mf of the tile's user rows: one warp per user, two-pass variance like nn.LayerNorm (same arithmetic as the
   // exact kernel); fp32 row for the exact re-scoring, bf16 operand image, ||u||
@@ -156,6 +169,7 @@ __global__ void __launch_bounds__(SC_THREADS, 1) score_tc_kernel(ScoreTcArgs A) 
   for (int i = tid; i < SC_UT * SC_KMAX; i += SC_THREADS) cand[(i / SC_KMAX) * SC_CAP + (i % SC_KMAX)] = 0ull;
   if (tid == 0) {
     s_qn = 0;
+    s_rn = 0;
     mbar_init(&full[0], 1);
     mbar_init(&full[1], 1);
     mbar_init(&accb[0], 1);
@@ -209,8 +223,10 @@ __global__ void __launch_bounds__(SC_THREADS, 1) score_tc_kernel(ScoreTcArgs A) 
     __syncwarp();
   };
 
-  // exact logit of (user row r, item base + col) with the exact kernel's arithmetic; pushes the key if it can enter
-  auto rescore = [&](int r, int col, int64_t base, float gi, float lthr, unsigned long long kthr) {
+  // exact logit of (user row r, item base + col) with the exact kernel's arithmetic; pushes the key if it can enter.
+  // A full candidate buffer (possible while the thresholds are still loose) parks the pair on the retry list, which is
+  // drained after the merges below.
+  auto rescore = [&](int r, int col, int64_t base, float gi) {
     const int64_t i = base + col;
     const float* pr = A.p_hat + i * 64;
     const float* ur = s_u + r * 64;
@@ -227,12 +243,19 @@ __global__ void __launch_bounds__(SC_THREADS, 1) score_tc_kernel(ScoreTcArgs A) 
       acc = fmaf(uv.w, p[k4].w, acc);
     }
     const float ze = acc + gi;
-    if (ze >= lthr) {
+    if (ze >= s_lthr[r]) {
       const float sc = 1.0f / (1.0f + expf(-ze));
       const unsigned long long key = sc_key(sc, (uint32_t)i);
-      if (key > kthr) {
+      if (key > s_kthr[r]) {
         const int pos = atomicAdd(&s_cnt[r], 1);
-        cand[(int64_t)r * SC_CAP + pos] = key;
+        if (pos < SC_CAP) {
+          cand[(int64_t)r * SC_CAP + pos] = key;
+        } else {
+          atomicSub(&s_cnt[r], 1);
+          const int rp = atomicAdd(&s_rn, 1);     // < SC_RCAP: a tile has SC_UT x SC_IT pairs
+          retry_key[rsel][rp] = key;
+          retry_row[rsel][rp] = (uint8_t)r;
+        }
       }
     }
   };
@@ -263,21 +286,22 @@ __global__ void __launch_bounds__(SC_THREADS, 1) score_tc_kernel(ScoreTcArgs A) 
       float z[32];
       tmem_ld32(tmem + 256 * b + lane_addr + cq * 64 + ch * 32, z);
       const int j0 = cq * 64 + ch * 32;
+      uint32_t hit = 0;                                  // bit j: the upper bound of column j0 + j reaches the threshold
 #pragma unroll
       for (int j4 = 0; j4 < 8; ++j4) {
         const float4 g4 = *reinterpret_cast<const float4*>(tail + j0 + 4 * j4);
         const float4 m4 = *reinterpret_cast<const float4*>(tail + SC_IT + j0 + 4 * j4);
-        const float gg[4] = {g4.x, g4.y, g4.z, g4.w}, mm[4] = {m4.x, m4.y, m4.z, m4.w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float bound = fmaf(nrm, mm[e], z[4 * j4 + e] + gg[e]);
-          if (bound >= lthr) {                           // rare after the first tiles
-            const int col = j0 + 4 * j4 + e;
-            const int qp = atomicAdd(&s_qn, 1);
-            if (qp < SC_QCAP) s_queue[qp] = ((uint32_t)row << 8) | (uint32_t)col;      // re-scored below, one thread each
-            else rescore(row, col, base, gg[e], lthr, kthr);                            // queue full (warm-up): in place
-          }
-        }
+        hit |= (fmaf(nrm, m4.x, z[4 * j4 + 0] + g4.x) >= lthr ? 1u : 0u) << (4 * j4 + 0);
+        hit |= (fmaf(nrm, m4.y, z[4 * j4 + 1] + g4.y) >= lthr ? 1u : 0u) << (4 * j4 + 1);
+        hit |= (fmaf(nrm, m4.z, z[4 * j4 + 2] + g4.z) >= lthr ? 1u : 0u) << (4 * j4 + 2);
+        hit |= (fmaf(nrm, m4.w, z[4 * j4 + 3] + g4.w) >= lthr ? 1u : 0u) << (4 * j4 + 3);
+      }
+      while (hit) {                                      // rare after the first tiles
+        const int col = j0 + __ffs(hit) - 1;
+        hit &= hit - 1;
+        const int qp = atomicAdd(&s_qn, 1);
+        if (qp < SC_QCAP) s_queue[qp] = ((uint32_t)row << 8) | (uint32_t)col;        // re-scored below, one thread each
+        else rescore(row, col, base, tail[col]);                                      // queue full (warm-up): in place
       }
     }
     // exact re-scoring of the queued survivors: every thread takes one (independent 128-bit loads + the FMA chain),
@@ -287,19 +311,45 @@ __global__ void __launch_bounds__(SC_THREADS, 1) score_tc_kernel(ScoreTcArgs A) 
       const int qn = min(s_qn, SC_QCAP);
       for (int e = tid; e < qn; e += SC_THREADS) {
         const uint32_t v = s_queue[e];
-        const int r = (int)(v >> 8), col = (int)(v & 255u);
-        rescore(r, col, base, tail[col], s_lthr[r], s_kthr[r]);
+        const int col = (int)(v & 255u);
+        rescore((int)(v >> 8), col, base, tail[col]);
       }
     }
     fence_before_sync();
     __syncthreads();                                     // accumulator b and the tile's g / margin are free
     if (tid == 0) s_qn = 0;
     if (tid == 0 && t + 2 < ntile) load_tile(b, t + 2);
-    // a tile adds at most 256 candidates per user: merge every list that could overflow during the next one
-    __threadfence_block();
-    for (int uu = warp; uu < nu; uu += SC_THREADS / 32)
-      if (s_cnt[uu] > SC_CAP - SC_IT) merge_user(uu);
-    __syncthreads();
+    // merge the lists that are getting full; pairs that found their buffer full are retried after the merge
+    for (;;) {
+      for (int uu = warp; uu < nu; uu += SC_THREADS / 32)
+        if (s_cnt[uu] > SC_HIGH) merge_user(uu);
+      __syncthreads();
+      const int rn = s_rn;
+      if (rn == 0) break;
+      __syncthreads();
+      if (tid == 0) s_rn = 0;
+      const int src = rsel;
+      rsel ^= 1;
+      __syncthreads();
+      // the keys are final, only their buffer was full: re-insert (warm-up only); a pair that meets a full buffer
+      // again goes to the other list and waits for the next merge round
+      for (int e = tid; e < rn; e += SC_THREADS) {
+        const int r = retry_row[src][e];
+        const unsigned long long key = retry_key[src][e];
+        if (key > s_kthr[r]) {
+          const int pos = atomicAdd(&s_cnt[r], 1);
+          if (pos < SC_CAP) {
+            cand[(int64_t)r * SC_CAP + pos] = key;
+          } else {
+            atomicSub(&s_cnt[r], 1);
+            const int rp = atomicAdd(&s_rn, 1);
+            retry_key[rsel][rp] = key;
+            retry_row[rsel][rp] = (uint8_t)r;
+          }
+        }
+      }
+      __syncthreads();
+    }
   }
   for (int uu = warp; uu < nu; uu += SC_THREADS / 32) {
     merge_user(uu);
@@ -343,7 +393,7 @@ extern "C" int64_t ncf_score_topk_tc_workspace_bytes(int64_t n_users, int64_t I,
   const int64_t n = std::max<int64_t>(n_users, 1);
   const int64_t tiles = (n + SC_UT - 1) / SC_UT;
   const int ns = sc_splits(n, I);
-  return align_up(n * ns * SC_KMAX * 8, 256) + align_up(tiles * ns * SC_UT * SC_CAP * 8, 256);
+  return align_up(n * ns * SC_KMAX * 8, 256) + align_up(tiles * ns * SC_CTA_WS, 256);
 }
 
 extern "C" int ncf_score_topk_tc(const ncf_tables* T, const float* dense, const float* p_hat, const float* g, const void* img,
