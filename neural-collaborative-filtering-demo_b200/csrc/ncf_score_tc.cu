@@ -26,16 +26,16 @@ constexpr float SC_EPS = 0.0078125f;       // 2^-7
 constexpr uint32_t SCS_A = 0;                               // [128][64] bf16 image            16 KB
 constexpr uint32_t SCS_U = SCS_A + SC_UT * 64 * 2;          // [128][64] fp32 LN'd user rows   32 KB
 constexpr uint32_t SCS_B = SCS_U + SC_UT * 64 * 4;          // 2 x item tile                    68 KB
-constexpr uint32_t SCS_SORT = SCS_B + 2 * SC_TILE_BYTES;    // 16 warps x 512 keys              64 KB
-constexpr uint32_t SCS_NU = SCS_SORT + 16 * SC_CAP * 8;     // ||u|| per user
+constexpr uint32_t SCS_SORT = SCS_B + 2 * SC_TILE_BYTES;    // 512 keys being merged             4 KB
+constexpr uint32_t SCS_NU = SCS_SORT + SC_CAP * 8;          // ||u|| per user
 constexpr uint32_t SCS_LTHR = SCS_NU + SC_UT * 4;           // logit pre-filter per user
 constexpr uint32_t SCS_KTHR = SCS_LTHR + SC_UT * 4;         // key of the running k-th best
 constexpr uint32_t SCS_CNT = SCS_KTHR + SC_UT * 8;
-constexpr int SC_QCAP = 2048;                               // survivors of one tile queued for exact re-scoring
+constexpr int SC_QCAP = 4096;                               // survivors queued for exact re-scoring (flushed when half full)
 constexpr int SC_HIGH = SC_CAP - 64;                        // merge a list when it holds more than this
-constexpr int SC_RCAP = SC_UT * SC_IT;                      // pairs whose candidate buffer was full: at most one tile's worth
+constexpr int SC_RCAP = SC_UT * SC_IT + SC_QCAP;            // keys whose candidate buffer was full: one tile + the queue
 constexpr uint32_t SCS_QUEUE = SCS_CNT + SC_UT * 4;         // (row << 8 | column) per survivor
-constexpr uint32_t SCS_TOTAL = SCS_QUEUE + SC_QCAP * 4;
+constexpr uint32_t SCS_TOTAL = SCS_QUEUE + SC_QCAP * 8;     // (row, item index) per survivor
 constexpr int64_t SC_CTA_WS = (int64_t)SC_UT * SC_CAP * 8 + 2 * ((int64_t)SC_RCAP * 8 + SC_RCAP);   // candidates + 2 retry lists
 
 __device__ __forceinline__ unsigned long long sc_key(float score, uint32_t idx) {
@@ -71,16 +71,13 @@ __global__ void __launch_bounds__(256) item_image_kernel(const float* __restrict
   }
 }
 
-// descending bitonic sort of 512 keys in shared memory by ONE warp
-__device__ __forceinline__ void warp_sort512_desc(unsigned long long* a, int lane) {
+// descending bitonic sort of SC_CAP keys in shared memory by the whole CTA (one compare-exchange per thread and stage)
+__device__ __forceinline__ void cta_sort_desc(unsigned long long* a, int tid) {
   for (int k = 2; k <= SC_CAP; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
-      __syncwarp();
-#pragma unroll 4
-      for (int m = 0; m < SC_CAP / 64; ++m) {
-        // the m-th compare-exchange of this lane: enumerate the indices whose bit j is clear
-        const int p = lane + 32 * m;                       // 0..255
-        const int i = ((p & ~(j - 1)) << 1) | (p & (j - 1));
+      __syncthreads();
+      if (tid < SC_CAP / 2) {
+        const int i = ((tid & ~(j - 1)) << 1) | (tid & (j - 1));     // the tid-th index whose bit j is clear
         const int l = i | j;
         const unsigned long long x = a[i], y = a[l];
         const bool desc = (i & k) == 0;
@@ -91,13 +88,14 @@ __device__ __forceinline__ void warp_sort512_desc(unsigned long long* a, int lan
       }
     }
   }
-  __syncwarp();
+  __syncthreads();
 }
 
 struct ScoreTcArgs {
   const float* t_umf;
   const float* dense;
   const float* p_hat;      // [I,64] fp32 (exact re-scoring)
+  const float* g;          // [I]
   const uint8_t* img;      // item tile images
   const int64_t* user_ids;
   int64_t n_users, I;
@@ -111,7 +109,8 @@ __global__ void __launch_bounds__(SC_THREADS, 1) score_tc_kernel(ScoreTcArgs A) 
   __shared__ __align__(8) uint64_t full[2], accb[2];
   __shared__ uint32_t tmem_slot;
   __shared__ int s_qn, s_rn;
-  uint32_t* s_queue = reinterpret_cast<uint32_t*>(smem + SCS_QUEUE);
+  __shared__ uint32_t s_mmask[SC_UT / 32];               // users whose list has to be merged
+  unsigned long long* s_queue = reinterpret_cast<unsigned long long*>(smem + SCS_QUEUE);
 
   float* s_u = reinterpret_cast<float*>(smem + SCS_U);
   float* s_nu = reinterpret_cast<float*>(smem + SCS_NU);
@@ -170,6 +169,7 @@ __global__ void __launch_bounds__(SC_THREADS, 1) score_tc_kernel(ScoreTcArgs A) 
   if (tid == 0) {
     s_qn = 0;
     s_rn = 0;
+    for (int i = 0; i < SC_UT / 32; ++i) s_mmask[i] = 0u;
     mbar_init(&full[0], 1);
     mbar_init(&full[1], 1);
     mbar_init(&accb[0], 1);
@@ -199,16 +199,17 @@ __global__ void __launch_bounds__(SC_THREADS, 1) score_tc_kernel(ScoreTcArgs A) 
                make_idesc(128, SC_IT, false, false), 4, false);
     mma_commit(&accb[b]);
   };
-  // merge the candidate buffer of one user into its running list (one warp): sort, keep the best KMAX, refresh the
-  // thresholds
-  unsigned long long* s_sort = reinterpret_cast<unsigned long long*>(smem + SCS_SORT) + warp * SC_CAP;
+  // merge the candidate buffer of one user into its running list (whole CTA): sort, keep the best KMAX, refresh the
+  // thresholds.  Called by all threads with the same uu.
+  unsigned long long* s_sort = reinterpret_cast<unsigned long long*>(smem + SCS_SORT);
   auto merge_user = [&](int uu) {
-    const int cnt = s_cnt[uu];
+    const int cnt = min(s_cnt[uu], SC_CAP);
     unsigned long long* c = cand + (int64_t)uu * SC_CAP;
-    for (int i = lane; i < SC_CAP; i += 32) s_sort[i] = i < cnt ? c[i] : 0ull;
-    warp_sort512_desc(s_sort, lane);
-    for (int i = lane; i < SC_KMAX; i += 32) c[i] = s_sort[i];
-    if (lane == 0) {
+    __syncthreads();
+    for (int i = tid; i < SC_CAP; i += SC_THREADS) s_sort[i] = i < cnt ? c[i] : 0ull;
+    cta_sort_desc(s_sort, tid);
+    for (int i = tid; i < SC_KMAX; i += SC_THREADS) c[i] = s_sort[i];
+    if (tid == 0) {
       s_cnt[uu] = SC_KMAX;
       const unsigned long long kth = s_sort[SC_KMAX - 1];
       s_kthr[uu] = kth;
@@ -220,19 +221,47 @@ __global__ void __launch_bounds__(SC_THREADS, 1) score_tc_kernel(ScoreTcArgs A) 
       }
       s_lthr[uu] = lt;
     }
-    __syncwarp();
+    __syncthreads();
+  };
+  auto mark_merge = [&](int r) { atomicOr(&s_mmask[r >> 5], 1u << (r & 31)); };
+  auto run_merges = [&]() {            // all threads; merges every marked user
+    __syncthreads();
+    for (int wd = 0; wd < SC_UT / 32; ++wd) {
+      uint32_t m = s_mmask[wd];
+      __syncthreads();
+      if (tid == 0) s_mmask[wd] = 0u;
+      while (m) {
+        const int uu = wd * 32 + __ffs(m) - 1;
+        m &= m - 1;
+        merge_user(uu);
+      }
+    }
+    __syncthreads();
   };
 
-  // exact logit of (user row r, item base + col) with the exact kernel's arithmetic; pushes the key if it can enter.
-  // A full candidate buffer (possible while the thresholds are still loose) parks the pair on the retry list, which is
-  // drained after the merges below.
-  auto rescore = [&](int r, int col, int64_t base, float gi) {
-    const int64_t i = base + col;
+  // exact logit of (user row r, item i) with the exact kernel's arithmetic; pushes the key if it can enter.  A full
+  // candidate buffer (possible while the thresholds are still loose) parks the key on the retry list, which is drained
+  // after the merges.
+  auto push_key = [&](int r, unsigned long long key) {
+    const int pos = atomicAdd(&s_cnt[r], 1);
+    if (pos < SC_CAP) {
+      cand[(int64_t)r * SC_CAP + pos] = key;
+      if (pos >= SC_HIGH) mark_merge(r);
+    } else {
+      atomicSub(&s_cnt[r], 1);
+      mark_merge(r);
+      const int rp = atomicAdd(&s_rn, 1);     // < SC_RCAP per round (see the flush policy)
+      retry_key[rsel][rp] = key;
+      retry_row[rsel][rp] = (uint8_t)r;
+    }
+  };
+  auto rescore = [&](int r, int64_t i) {
     const float* pr = A.p_hat + i * 64;
     const float* ur = s_u + r * 64;
     float4 p[16];
 #pragma unroll
     for (int k4 = 0; k4 < 16; ++k4) p[k4] = ldg4(pr + 4 * k4);
+    const float gi = __ldg(A.g + i);
     float acc = 0.f;
 #pragma unroll
     for (int k4 = 0; k4 < 16; ++k4) {            // ascending k with fmaf: the exact kernel's order
@@ -246,16 +275,33 @@ __global__ void __launch_bounds__(SC_THREADS, 1) score_tc_kernel(ScoreTcArgs A) 
     if (ze >= s_lthr[r]) {
       const float sc = 1.0f / (1.0f + expf(-ze));
       const unsigned long long key = sc_key(sc, (uint32_t)i);
-      if (key > s_kthr[r]) {
-        const int pos = atomicAdd(&s_cnt[r], 1);
-        if (pos < SC_CAP) {
-          cand[(int64_t)r * SC_CAP + pos] = key;
-        } else {
-          atomicSub(&s_cnt[r], 1);
-          const int rp = atomicAdd(&s_rn, 1);     // < SC_RCAP: a tile has SC_UT x SC_IT pairs
-          retry_key[rsel][rp] = key;
-          retry_row[rsel][rp] = (uint8_t)r;
-        }
+      if (key > s_kthr[r]) push_key(r, key);
+    }
+  };
+  // drain the survivor queue (every thread takes one pair), merge the lists that filled up, retry the keys that found
+  // their buffer full - until nothing is left
+  auto flush = [&]() {
+    __syncthreads();
+    const int qn = min(s_qn, SC_QCAP);
+    for (int e = tid; e < qn; e += SC_THREADS) {
+      const unsigned long long v = s_queue[e];
+      rescore((int)(v >> 32), (int64_t)(v & 0xffffffffull));
+    }
+    __syncthreads();
+    if (tid == 0) s_qn = 0;
+    for (;;) {
+      run_merges();
+      const int rn = s_rn;
+      if (rn == 0) break;
+      __syncthreads();
+      if (tid == 0) s_rn = 0;
+      const int src = rsel;
+      rsel ^= 1;
+      __syncthreads();
+      for (int e = tid; e < rn; e += SC_THREADS) {
+        const int r = retry_row[src][e];
+        const unsigned long long key = retry_key[src][e];
+        if (key > s_kthr[r]) push_key(r, key);
       }
     }
   };
@@ -279,7 +325,6 @@ __global__ void __launch_bounds__(SC_THREADS, 1) score_tc_kernel(ScoreTcArgs A) 
     fence_after_sync();
     const float* tail = reinterpret_cast<const float*>(smem + SCS_B + b * SC_TILE_BYTES + SC_IMG);
     const float lthr = s_lthr[row], nrm = s_nu[row];
-    const unsigned long long kthr = s_kthr[row];
     const int64_t base = (t_begin + t) * SC_IT;
 #pragma unroll 1
     for (int ch = 0; ch < 2; ++ch) {
@@ -297,65 +342,25 @@ __global__ void __launch_bounds__(SC_THREADS, 1) score_tc_kernel(ScoreTcArgs A) 
         hit |= (fmaf(nrm, m4.w, z[4 * j4 + 3] + g4.w) >= lthr ? 1u : 0u) << (4 * j4 + 3);
       }
       while (hit) {                                      // rare after the first tiles
-        const int col = j0 + __ffs(hit) - 1;
+        const int64_t i = base + j0 + __ffs(hit) - 1;
         hit &= hit - 1;
         const int qp = atomicAdd(&s_qn, 1);
-        if (qp < SC_QCAP) s_queue[qp] = ((uint32_t)row << 8) | (uint32_t)col;        // re-scored below, one thread each
-        else rescore(row, col, base, tail[col]);                                      // queue full (warm-up): in place
-      }
-    }
-    // exact re-scoring of the queued survivors: every thread takes one (independent 128-bit loads + the FMA chain),
-    // instead of one diverged lane stalling its whole warp per survivor
-    __syncthreads();
-    {
-      const int qn = min(s_qn, SC_QCAP);
-      for (int e = tid; e < qn; e += SC_THREADS) {
-        const uint32_t v = s_queue[e];
-        const int col = (int)(v & 255u);
-        rescore((int)(v >> 8), col, base, tail[col]);
+        if (qp < SC_QCAP) s_queue[qp] = ((unsigned long long)row << 32) | (unsigned long long)i;   // re-scored at the flush
+        else rescore(row, i);                                                                      // queue full: in place
       }
     }
     fence_before_sync();
     __syncthreads();                                     // accumulator b and the tile's g / margin are free
-    if (tid == 0) s_qn = 0;
     if (tid == 0 && t + 2 < ntile) load_tile(b, t + 2);
-    // merge the lists that are getting full; pairs that found their buffer full are retried after the merge
-    for (;;) {
-      for (int uu = warp; uu < nu; uu += SC_THREADS / 32)
-        if (s_cnt[uu] > SC_HIGH) merge_user(uu);
-      __syncthreads();
-      const int rn = s_rn;
-      if (rn == 0) break;
-      __syncthreads();
-      if (tid == 0) s_rn = 0;
-      const int src = rsel;
-      rsel ^= 1;
-      __syncthreads();
-      // the keys are final, only their buffer was full: re-insert (warm-up only); a pair that meets a full buffer
-      // again goes to the other list and waits for the next merge round
-      for (int e = tid; e < rn; e += SC_THREADS) {
-        const int r = retry_row[src][e];
-        const unsigned long long key = retry_key[src][e];
-        if (key > s_kthr[r]) {
-          const int pos = atomicAdd(&s_cnt[r], 1);
-          if (pos < SC_CAP) {
-            cand[(int64_t)r * SC_CAP + pos] = key;
-          } else {
-            atomicSub(&s_cnt[r], 1);
-            const int rp = atomicAdd(&s_rn, 1);
-            retry_key[rsel][rp] = key;
-            retry_row[rsel][rp] = (uint8_t)r;
-          }
-        }
-      }
-      __syncthreads();
-    }
+    // Survivors wait in the queue until it is half full (a tile can add SC_UT x SC_IT, but then the overflow is
+    // re-scored in place), so late in the run a flush - and the barriers it costs - happens once in many tiles.
+    if (s_qn > SC_QCAP / 2 || s_rn > 0 || t + 1 == ntile) flush();     // uniform: read after the barrier
   }
-  for (int uu = warp; uu < nu; uu += SC_THREADS / 32) {
+  // final lists: merge every user once more and emit the best KMAX keys
+  for (int uu = 0; uu < nu; ++uu) {
     merge_user(uu);
     unsigned long long* dst = A.part + ((u0 + uu) * A.nsplit + split) * SC_KMAX;
-    for (int k = lane; k < SC_KMAX; k += 32) dst[k] = s_sort[k];
-    __syncwarp();
+    for (int k = tid; k < SC_KMAX; k += SC_THREADS) dst[k] = s_sort[k];
   }
   fence_before_sync();
   __syncthreads();
@@ -421,6 +426,7 @@ extern "C" int ncf_score_topk_tc(const ncf_tables* T, const float* dense, const 
   A.t_umf = T->w[0];
   A.dense = dense;
   A.p_hat = p_hat;
+  A.g = g;
   A.img = static_cast<const uint8_t*>(img);
   A.user_ids = user_ids;
   A.n_users = n_users;
