@@ -25,8 +25,9 @@ constexpr float SC_EPS = 0.0078125f;       // 2^-7
 
 constexpr uint32_t SCS_A = 0;                               // [128][64] bf16 image            16 KB
 constexpr uint32_t SCS_U = SCS_A + SC_UT * 64 * 2;          // [128][64] fp32 LN'd user rows   32 KB
-constexpr uint32_t SCS_B = SCS_U + SC_UT * 64 * 4;          // 2 x item tile                    68 KB
-constexpr uint32_t SCS_SORT = SCS_B + 2 * SC_TILE_BYTES;    // 512 keys being merged             4 KB
+constexpr int SC_NB = 3;                                    // item tile buffers: a load has a whole iteration to land
+constexpr uint32_t SCS_B = SCS_U + SC_UT * 64 * 4;          // 3 x item tile                   102 KB
+constexpr uint32_t SCS_SORT = SCS_B + SC_NB * SC_TILE_BYTES;    // 512 keys being merged         4 KB
 constexpr uint32_t SCS_NU = SCS_SORT + SC_CAP * 8;          // ||u|| per user
 constexpr uint32_t SCS_LTHR = SCS_NU + SC_UT * 4;           // logit pre-filter per user
 constexpr uint32_t SCS_KTHR = SCS_LTHR + SC_UT * 4;         // key of the running k-th best
@@ -106,7 +107,7 @@ struct ScoreTcArgs {
 
 __global__ void __launch_bounds__(SC_THREADS, 1) score_tc_kernel(ScoreTcArgs A) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ __align__(8) uint64_t full[2], accb[2];
+  __shared__ __align__(8) uint64_t full[SC_NB], accb[2];
   __shared__ uint32_t tmem_slot;
   __shared__ int s_qn, s_rn;
   __shared__ uint32_t s_mmask[SC_UT / 32];               // users whose list has to be merged
@@ -170,8 +171,7 @@ __global__ void __launch_bounds__(SC_THREADS, 1) score_tc_kernel(ScoreTcArgs A) 
     s_qn = 0;
     s_rn = 0;
     for (int i = 0; i < SC_UT / 32; ++i) s_mmask[i] = 0u;
-    mbar_init(&full[0], 1);
-    mbar_init(&full[1], 1);
+    for (int i = 0; i < SC_NB; ++i) mbar_init(&full[i], 1);
     mbar_init(&accb[0], 1);
     mbar_init(&accb[1], 1);
     mbar_fence_init();
@@ -190,12 +190,16 @@ __global__ void __launch_bounds__(SC_THREADS, 1) score_tc_kernel(ScoreTcArgs A) 
   const int64_t t_begin = split * per, t_end = min(ntile_all, t_begin + per);
   const int64_t ntile = t_begin < t_end ? t_end - t_begin : 0;
 
-  auto load_tile = [&](int b, int64_t t) {            // tid 0
-    mbar_arrive_expect_tx(&full[b], SC_TILE_BYTES);
-    bulk_g2s(smem + SCS_B + b * SC_TILE_BYTES, A.img + (t_begin + t) * SC_TILE_BYTES, SC_TILE_BYTES, &full[b]);
+  auto load_tile = [&](int64_t t) {                    // tid 0: tile t of this split into buffer t % SC_NB
+    const int nb = (int)(t % SC_NB);
+    mbar_arrive_expect_tx(&full[nb], SC_TILE_BYTES);
+    bulk_g2s(smem + SCS_B + nb * SC_TILE_BYTES, A.img + (t_begin + t) * SC_TILE_BYTES, SC_TILE_BYTES, &full[nb]);
   };
-  auto issue_mma = [&](int b) {                        // tid 0
-    issue_gemm(tmem + 256 * b, sA, 128, 64 * 16, 256, smem_addr(smem + SCS_B + b * SC_TILE_BYTES), 128, 64 * 16, 256,
+  auto issue_mma = [&](int64_t t) {                    // tid 0: tile t -> accumulator t & 1
+    const int nb = (int)(t % SC_NB), b = (int)(t & 1);
+    mbar_wait(&full[nb], (uint32_t)((t / SC_NB) & 1));
+    fence_after_sync();
+    issue_gemm(tmem + 256 * b, sA, 128, 64 * 16, 256, smem_addr(smem + SCS_B + nb * SC_TILE_BYTES), 128, 64 * 16, 256,
                make_idesc(128, SC_IT, false, false), 4, false);
     mma_commit(&accb[b]);
   };
@@ -307,23 +311,20 @@ __global__ void __launch_bounds__(SC_THREADS, 1) score_tc_kernel(ScoreTcArgs A) 
   };
 
   if (tid == 0 && ntile > 0) {
-    load_tile(0, 0);
-    if (ntile > 1) load_tile(1, 1);
-    mbar_wait(&full[0], 0);
-    fence_after_sync();
+    load_tile(0);
+    if (ntile > 1) load_tile(1);
     issue_mma(0);
   }
   for (int64_t t = 0; t < ntile; ++t) {
     const int b = (int)(t & 1);
-    if (tid == 0 && t + 1 < ntile) {                    // the other accumulator was drained by the previous epilogue
-      mbar_wait(&full[b ^ 1], (uint32_t)(((t + 1) >> 1) & 1));
-      fence_after_sync();
-      issue_mma(b ^ 1);
+    if (tid == 0) {
+      if (t + 2 < ntile) load_tile(t + 2);              // its buffer held tile t - 1: GEMM and epilogue are done
+      if (t + 1 < ntile) issue_mma(t + 1);              // the other accumulator was drained by the previous epilogue
     }
     if (warp == 0) mbar_wait(&accb[b], (uint32_t)((t >> 1) & 1));
     __syncthreads();
     fence_after_sync();
-    const float* tail = reinterpret_cast<const float*>(smem + SCS_B + b * SC_TILE_BYTES + SC_IMG);
+    const float* tail = reinterpret_cast<const float*>(smem + SCS_B + (int)(t % SC_NB) * SC_TILE_BYTES + SC_IMG);
     const float lthr = s_lthr[row], nrm = s_nu[row];
     const int64_t base = (t_begin + t) * SC_IT;
 #pragma unroll 1
@@ -331,19 +332,24 @@ __global__ void __launch_bounds__(SC_THREADS, 1) score_tc_kernel(ScoreTcArgs A) 
       float z[32];
       tmem_ld32(tmem + 256 * b + lane_addr + cq * 64 + ch * 32, z);
       const int j0 = cq * 64 + ch * 32;
-      uint32_t hit = 0;                                  // bit j: the upper bound of column j0 + j reaches the threshold
+      // three instructions per pair: d = (g - lthr) + z, diff = nrm * margin + d = bound - lthr, and a funnel shift
+      // that appends diff's sign bit to the mask (element j ends up at bit 31 - j; set = below the threshold)
+      uint32_t miss = 0;
 #pragma unroll
       for (int j4 = 0; j4 < 8; ++j4) {
         const float4 g4 = *reinterpret_cast<const float4*>(tail + j0 + 4 * j4);
         const float4 m4 = *reinterpret_cast<const float4*>(tail + SC_IT + j0 + 4 * j4);
-        hit |= (fmaf(nrm, m4.x, z[4 * j4 + 0] + g4.x) >= lthr ? 1u : 0u) << (4 * j4 + 0);
-        hit |= (fmaf(nrm, m4.y, z[4 * j4 + 1] + g4.y) >= lthr ? 1u : 0u) << (4 * j4 + 1);
-        hit |= (fmaf(nrm, m4.z, z[4 * j4 + 2] + g4.z) >= lthr ? 1u : 0u) << (4 * j4 + 2);
-        hit |= (fmaf(nrm, m4.w, z[4 * j4 + 3] + g4.w) >= lthr ? 1u : 0u) << (4 * j4 + 3);
+        miss = __funnelshift_l(__float_as_uint(fmaf(nrm, m4.x, (g4.x - lthr) + z[4 * j4 + 0])), miss, 1);
+        miss = __funnelshift_l(__float_as_uint(fmaf(nrm, m4.y, (g4.y - lthr) + z[4 * j4 + 1])), miss, 1);
+        miss = __funnelshift_l(__float_as_uint(fmaf(nrm, m4.z, (g4.z - lthr) + z[4 * j4 + 2])), miss, 1);
+        miss = __funnelshift_l(__float_as_uint(fmaf(nrm, m4.w, (g4.w - lthr) + z[4 * j4 + 3])), miss, 1);
       }
+      uint32_t hit = ~miss;
       while (hit) {                                      // rare after the first tiles
-        const int64_t i = base + j0 + __ffs(hit) - 1;
-        hit &= hit - 1;
+        const int j = __clz(hit);                        // element j sits at bit 31 - j
+        hit &= ~(0x80000000u >> j);
+        const int64_t i = base + j0 + j;
+        if (i >= A.I) continue;                          // padding of the last tile (its -inf bias can turn into NaN above)
         const int qp = atomicAdd(&s_qn, 1);
         if (qp < SC_QCAP) s_queue[qp] = ((unsigned long long)row << 32) | (unsigned long long)i;   // re-scored at the flush
         else rescore(row, i);                                                                      // queue full: in place
@@ -351,7 +357,6 @@ __global__ void __launch_bounds__(SC_THREADS, 1) score_tc_kernel(ScoreTcArgs A) 
     }
     fence_before_sync();
     __syncthreads();                                     // accumulator b and the tile's g / margin are free
-    if (tid == 0 && t + 2 < ntile) load_tile(b, t + 2);
     // Survivors wait in the queue until it is half full (a tile can add SC_UT x SC_IT, but then the overflow is
     // re-scored in place), so late in the run a flush - and the barriers it costs - happens once in many tiles.
     if (s_qn > SC_QCAP / 2 || s_rn > 0 || t + 1 == ntile) flush();     // uniform: read after the barrier
