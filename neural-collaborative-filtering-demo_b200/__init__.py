@@ -11,8 +11,9 @@ from .metrics import calculate_metrics  # noqa: F401
 from .scoring import CatalogueScorer, get_recommendations  # noqa: F401
 from .trainer import ModelTrainer, NCFTrainEngine  # noqa: F401
 from .sharding import ShardedCatalogueScorer, ShardedNCFEngine, ShardRouter  # noqa: F401
+from .export import CosineIndex, export_product_embeddings, product_embedding_records  # noqa: F401
 
 __all__ = ["AdvancedNCF", "MultiHeadAttention", "TemporalEncoding", "CategoryHierarchy", "KeyedJaggedTensor",
            "make_kjt", "NcfError", "load_library", "calculate_metrics", "CatalogueScorer", "get_recommendations",
            "ModelTrainer", "NCFTrainEngine", "ShardedNCFEngine", "ShardRouter", "ShardedCatalogueScorer", "InteractionSampler", "first_appearance_index",
-           "remap_cardnumber", "remap_product_id"]
+           "remap_cardnumber", "remap_product_id", "CosineIndex", "export_product_embeddings", "product_embedding_records"]

@@ -500,3 +500,37 @@ def test_topk_tensor_core_prefilter_is_bit_identical_to_the_exact_kernel():
     assert torch.equal(idx_tc, idx_ex)
     assert torch.equal(sc_tc, sc_ex)
     assert int(idx_tc.min()) >= 0 and int(idx_tc.max()) < I
+
+
+def test_embedding_export_and_exact_cosine_index(tmp_path):
+    """generate_embeddings.py:184-236 in batches: ids hashed like the reference, first occurrence wins, vectors equal
+    the oracle's get_product_embeddings (mlp) L2-normalised; the exact cosine index returns numpy's stable order."""
+    import json
+    import ncf_b200
+    p, _ = golden_params()
+    m = _model(p, 8031, 366).eval()
+    g = torch.Generator().manual_seed(12)
+    pids = ["P%08X" % int(v) for v in torch.randint(0, 1 << 31, (500,), generator=g)]
+    pids += pids[:40]                                    # duplicates are skipped
+    cats = [str(int(v)) for v in torch.randint(0, 24, (len(pids),), generator=g)]
+    deps = [str(int(v)) for v in torch.randint(0, 5, (len(pids),), generator=g)]
+    cmap = {c: k for k, c in enumerate(sorted(set(cats)))}
+    dmap = {d: k for k, d in enumerate(sorted(set(deps)))}
+    path = str(tmp_path / "emb.jsonl")
+    n = ncf_b200.export_product_embeddings(m, pids, path, category_ids=cats, department_ids=deps, category_map=cmap,
+                                           department_map=dmap, batch=128)
+    assert n == len(set(pids))
+    recs = [json.loads(l) for l in open(path)]
+    assert [r["id"] for r in recs] == list(dict.fromkeys(pids))
+    rows = torch.tensor([O.remap_product_id(r["id"], 366) for r in recs])
+    ref = O.get_product_embeddings(p, rows, torch.zeros(len(rows), dtype=torch.long), torch.zeros(len(rows), dtype=torch.long))["mlp"]
+    ref = ref / ref.norm(dim=1, keepdim=True)
+    got = torch.tensor([r["embedding"] for r in recs])
+    assert float((got - ref).abs().max()) < 1e-6
+    index = ncf_b200.CosineIndex.from_jsonl(path)
+    q = torch.randn(7, 64, generator=g)
+    pos, sim = index.query(q, 10, chunk=97)
+    full = (q / q.norm(dim=1, keepdim=True)) @ ref.t()
+    want = torch.argsort(full, dim=1, descending=True, stable=True)[:, :10]
+    assert torch.equal(pos.cpu(), want) or float((torch.gather(full, 1, pos.cpu()) - torch.gather(full, 1, want)).abs().max()) < 1e-6
+    assert float((sim.cpu() - torch.gather(full, 1, pos.cpu())).abs().max()) < 1e-5
