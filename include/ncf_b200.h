@@ -245,7 +245,7 @@ NCF_API int ncf_score_topk(const ncf_tables* tables, const float* dense, const f
 
 /* The same result through a tensor-core pre-filter (large catalogues, many users per call): item tiles as
  * bf16 operand images + per-item error margin (ncf_item_image, built once per fold); a tcgen05 GEMM bounds
- * every logit from above (|error| <= 2^-7 ||u|| ||p_i||) and only pairs that can enter a list are re-scored
+ * every logit from above (|error| <= 1.01 * 2^-7 ||u|| ||p_i||) and only pairs that can enter a list are re-scored
  * with the exact fp32 arithmetic of ncf_score_topk: bit-identical indices and scores. */
 NCF_API int64_t ncf_item_image_bytes(int64_t I);
 NCF_API int ncf_item_image(const float* p_hat, const float* g, int64_t I, void* image, void* stream);

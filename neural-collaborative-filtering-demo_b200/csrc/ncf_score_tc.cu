@@ -3,7 +3,10 @@
 // The exact kernel (ncf_score.cu) forms every logit LN(U_mf[u]) . P_hat[i] + g[i] with 64 fp32 FMAs; almost all
 // of them lose against the user's running k-th best.  Here a tcgen05 bf16 GEMM (128 users x 256 items per tile,
 // accumulators double-buffered in TMEM) produces APPROXIMATE logits with a rigorous error bound
-//     |z_bf16 - z| <= 2^-7 * ||u||_2 * ||p_i||_2          (bf16 rounding of both operands, Cauchy-Schwarz, 2x slack)
+//     |z_bf16 - z| <= 1.01 * 2^-7 * ||u||_2 * ||p_i||_2
+// (bf16 keeps 8 significant bits: each operand is off by at most 2^-8 relative, a product by 2^-7 (1 + 2^-9); the
+// products are exact in fp32; the fp32 accumulation of 64 terms - on the tensor core and in the exact kernel's FMA
+// chain - adds less than 1e-5 relative; Cauchy-Schwarz turns sum |u_k p_k| into the two norms; 1 % covers the rest)
 // and only pairs whose upper bound reaches the running threshold are re-scored EXACTLY - same fp32 FMA order, same
 // sigmoid, same (score desc, index asc) key as the exact kernel - so the result is bit-identical to it while the
 // CUDA cores touch a tiny fraction of the 10^13 pairs.  Item tiles arrive as ready operand images
@@ -21,7 +24,7 @@ constexpr int SC_KMAX = 128;               // running list length (k <= 128), sa
 constexpr int SC_CAP = 512;                // list + candidates per user
 constexpr uint32_t SC_IMG = SC_IT * 64 * 2;                 // bf16 operand image of one item tile
 constexpr uint32_t SC_TILE_BYTES = SC_IMG + 2 * SC_IT * 4;  // + g[256] + margin[256]
-constexpr float SC_EPS = 0.0078125f;       // 2^-7
+constexpr float SC_EPS = 0.0078125f * 1.01f;   // 1.01 * 2^-7, see the bound above
 
 constexpr uint32_t SCS_A = 0;                               // [128][64] bf16 image            16 KB
 constexpr uint32_t SCS_U = SCS_A + SC_UT * 64 * 2;          // [128][64] fp32 LN'd user rows   32 KB
