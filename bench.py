@@ -544,9 +544,11 @@ def main():
     dmf = torch.randn(N, device=dev) * 1e-6
     dx = torch.randn(N, 64, device=dev) * 1e-6
 
+    k1_fn = lib.ncf_gather_ln_gmf_fwd_bf16 if precision == "bf16" else lib.ncf_gather_ln_gmf_fwd    # the variant the step runs
+
     def k1():
-        _lib.check(lib.ncf_gather_ln_gmf_fwd(C.byref(tabs), _lib.ptr(flat), _lib.ptr(u), _lib.ptr(it), N, None, None,
-                                             _lib.ptr(mf), _lib.ptr(xu), _lib.ptr(xp), _lib.ptr(ypm), _lib.ptr(yum), sptr))
+        _lib.check(k1_fn(C.byref(tabs), _lib.ptr(flat), _lib.ptr(u), _lib.ptr(it), N, None, None,
+                         _lib.ptr(mf), _lib.ptr(xu), _lib.ptr(xp), _lib.ptr(ypm), _lib.ptr(yum), sptr))
 
     def fwd():
         _lib.check(lib.ncf_forward(C.byref(cfg), C.byref(tabs), _lib.ptr(flat), _lib.ptr(u), _lib.ptr(it), N, None, None,

@@ -186,6 +186,14 @@ NCF_API int ncf_gather_ln_gmf_fwd(const ncf_tables* tables, const float* dense,
                           float* mf_pred, float* xu, float* xp, float* y_item_mf, float* y_user_mf,
                           void* stream);
 
+/* The same kernel writing xu / xp as bf16 rows [N,64] (128 B per row): the form ncf_forward hands to the fused
+ * tcgen05 attention block (precision NCF_BF16_TC, S = 5), which would round them to bf16 anyway. */
+NCF_API int ncf_gather_ln_gmf_fwd_bf16(const ncf_tables* tables, const float* dense,
+                               const int64_t* user_ids, const int64_t* item_ids, int64_t N,
+                               const int64_t* hour, const float* tmod,
+                               float* mf_pred, void* xu_bf16, void* xp_bf16, float* y_item_mf, float* y_user_mf,
+                               void* stream);
+
 /* get_user_embeddings / get_product_embeddings rows (architecture.py:383-407): LN'd rows of one
  * side. side 0 = user, 1 = item. */
 NCF_API int ncf_gather_ln(const ncf_tables* tables, const float* dense, int32_t side,

@@ -75,6 +75,7 @@ _SIGS = {
     "ncf_train_step": (C.c_int, [C.POINTER(RunCfg), C.POINTER(AdamCfg), C.POINTER(Tables), _P, _P, _P, _P, _P, _P, _P,
                                  _I64, _P, _P, _P, _I64, _P]),
     "ncf_gather_ln_gmf_fwd": (C.c_int, [C.POINTER(Tables), _P, _P, _P, _I64, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "ncf_gather_ln_gmf_fwd_bf16": (C.c_int, [C.POINTER(Tables), _P, _P, _P, _I64, _P, _P, _P, _P, _P, _P, _P, _P]),
     "ncf_gather_ln": (C.c_int, [C.POINTER(Tables), _P, _I32, _P, _I64, _P, _P, _P]),
     "ncf_emb_bwd_workspace_bytes": (_I64, [_I64]),
     "ncf_emb_bwd_adam": (C.c_int, [C.POINTER(AdamCfg), C.POINTER(Tables), _P, _P, _I32, _P, _P, _I64, _P, _P, _P, _P,

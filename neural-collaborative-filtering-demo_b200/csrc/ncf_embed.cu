@@ -702,6 +702,14 @@ extern "C" int ncf_gather_ln_gmf_fwd(const ncf_tables* T, const float* dense, co
   return gather_ln_gmf_fwd_rows(false, T, dense, user_ids, item_ids, N, hour, tmod, mf_pred, xu, xp, y_item_mf, y_user_mf, stream);
 }
 
+extern "C" int ncf_gather_ln_gmf_fwd_bf16(const ncf_tables* T, const float* dense, const int64_t* user_ids,
+                                          const int64_t* item_ids, int64_t N, const int64_t* hour, const float* tmod,
+                                          float* mf_pred, void* xu_bf16, void* xp_bf16, float* y_item_mf, float* y_user_mf,
+                                          void* stream) {
+  return gather_ln_gmf_fwd_rows(true, T, dense, user_ids, item_ids, N, hour, tmod, mf_pred, static_cast<float*>(xu_bf16),
+                                static_cast<float*>(xp_bf16), y_item_mf, y_user_mf, stream);
+}
+
 extern "C" int ncf_gather_ln(const ncf_tables* T, const float* dense, int32_t side, const int64_t* ids, int64_t n,
                              float* mf_out, float* mlp_out, void* stream) {
   NCF_REQUIRE(T && dense && ids && (side == 0 || side == 1), "gather_ln: bad argument");
