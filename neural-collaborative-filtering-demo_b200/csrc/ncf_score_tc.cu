@@ -246,6 +246,7 @@ __global__ void __launch_bounds__(SC_THREADS, 1) score_tc_kernel(ScoreTcArgs A) 
     __syncthreads();
   };
 
+  bool want_flush = false;      // this thread saw the queue pass its half mark or parked a key on the retry list
   // exact logit of (user row r, item i) with the exact kernel's arithmetic; pushes the key if it can enter.  A full
   // candidate buffer (possible while the thresholds are still loose) parks the key on the retry list, which is drained
   // after the merges.
@@ -257,6 +258,7 @@ __global__ void __launch_bounds__(SC_THREADS, 1) score_tc_kernel(ScoreTcArgs A) 
     } else {
       atomicSub(&s_cnt[r], 1);
       mark_merge(r);
+      want_flush = true;
       const int rp = atomicAdd(&s_rn, 1);     // < SC_RCAP per round (see the flush policy)
       retry_key[rsel][rp] = key;
       retry_row[rsel][rp] = (uint8_t)r;
@@ -299,8 +301,8 @@ __global__ void __launch_bounds__(SC_THREADS, 1) score_tc_kernel(ScoreTcArgs A) 
     for (;;) {
       run_merges();
       const int rn = s_rn;
+      __syncthreads();                 // everybody has read rn before anyone moves on (and may park new keys)
       if (rn == 0) break;
-      __syncthreads();
       if (tid == 0) s_rn = 0;
       const int src = rsel;
       rsel ^= 1;
@@ -324,8 +326,7 @@ __global__ void __launch_bounds__(SC_THREADS, 1) score_tc_kernel(ScoreTcArgs A) 
       if (t + 2 < ntile) load_tile(t + 2);              // its buffer held tile t - 1: GEMM and epilogue are done
       if (t + 1 < ntile) issue_mma(t + 1);              // the other accumulator was drained by the previous epilogue
     }
-    if (warp == 0) mbar_wait(&accb[b], (uint32_t)((t >> 1) & 1));
-    __syncthreads();
+    mbar_wait(&accb[b], (uint32_t)((t >> 1) & 1));       // every warp polls for itself: one CTA barrier per tile, below
     fence_after_sync();
     const float* tail = reinterpret_cast<const float*>(smem + SCS_B + (int)(t % SC_NB) * SC_TILE_BYTES + SC_IMG);
     const float lthr = s_lthr[row], nrm = s_nu[row];
@@ -354,15 +355,18 @@ __global__ void __launch_bounds__(SC_THREADS, 1) score_tc_kernel(ScoreTcArgs A) 
         const int64_t i = base + j0 + j;
         if (i >= A.I) continue;                          // padding of the last tile (its -inf bias can turn into NaN above)
         const int qp = atomicAdd(&s_qn, 1);
+        if (qp >= SC_QCAP / 2) want_flush = true;
         if (qp < SC_QCAP) s_queue[qp] = ((unsigned long long)row << 32) | (unsigned long long)i;   // re-scored at the flush
         else rescore(row, i);                                                                      // queue full: in place
       }
     }
     fence_before_sync();
-    __syncthreads();                                     // accumulator b and the tile's g / margin are free
-    // Survivors wait in the queue until it is half full (a tile can add SC_UT x SC_IT, but then the overflow is
-    // re-scored in place), so late in the run a flush - and the barriers it costs - happens once in many tiles.
-    if (s_qn > SC_QCAP / 2 || s_rn > 0 || t + 1 == ntile) flush();     // uniform: read after the barrier
+    // The one CTA barrier of a tile: accumulator b and the tile's g / margin are free after it, and it carries the
+    // flush decision (a thread that pushed past the queue's half mark, or parked a key, votes yes).  Survivors wait
+    // in the queue until then, so late in the run a flush - and the barriers it costs - happens once in many tiles.
+    const int do_flush = __syncthreads_or((want_flush || t + 1 == ntile) ? 1 : 0);
+    want_flush = false;
+    if (do_flush) flush();
   }
   // final lists: merge every user once more and emit the best KMAX keys
   for (int uu = 0; uu < nu; ++uu) {
