@@ -176,9 +176,8 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_fwd_kernel(AttnFwdArgs 
       issue_gemm(tmem + 64, sXP, 128, 64 * 16, 256, sWKV, 128, 64 * 16, 256, make_idesc(128, 128, false, false), 4, false);
       mma_commit(&bar);
     }
-    if (warp == 0) mbar_wait(&bar, phase);
+    mbar_wait(&bar, phase);                     // every warp polls for itself
     phase ^= 1;
-    __syncthreads();
     fence_after_sync();
     float qv[16];
     {
@@ -239,9 +238,8 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_fwd_kernel(AttnFwdArgs 
       issue_gemm(tmem + 192, sXU, 128, 64 * 16, 256, sWO, 128, 64 * 16, 256, make_idesc(128, 64, false, false), 4, false);
       mma_commit(&bar);
     }
-    if (warp == 0) mbar_wait(&bar, phase);
+    mbar_wait(&bar, phase);                     // every warp polls for itself
     phase ^= 1;
-    __syncthreads();
     fence_after_sync();
     {
       float t[16];
@@ -402,9 +400,8 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_bwd_kernel(AttnBwdArgs 
       issue_gemm(tmem + T_DC, sDA, 128, 128 * 16, 256, sWO, 64 * 16, 128, 2 * 64 * 16, make_idesc(128, 64, false, true), 4, false);
       mma_commit(&bar);
     }
-    if (warp == 0) mbar_wait(&bar, phase);
+    mbar_wait(&bar, phase);                     // every warp polls for itself
     phase ^= 1;
-    __syncthreads();
     fence_after_sync();
     float qv[16], dc[16];
     {
@@ -555,9 +552,8 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_bwd_kernel(AttnBwdArgs 
       sp.load(A.xp, nn0, nav, tid);
       sa.load(A.da, nn0, nav, tid);
     }
-    if (warp == 0) mbar_wait(&bar, phase);
+    mbar_wait(&bar, phase);                     // every warp polls for itself
     phase ^= 1;
-    __syncthreads();
     fence_after_sync();
     {
       float t[16];

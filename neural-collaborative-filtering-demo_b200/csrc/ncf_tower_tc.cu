@@ -496,8 +496,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_tc_fwd2_kernel(MlpFwdArgs 
     mma_commit(&bl1[s]);
   };
   auto wait_sync = [&](uint64_t* b, uint32_t parity) {
-    if (warp == 0) mbar_wait(b, parity);               // one warp polls the mbarrier, the rest park on the CTA barrier
-    __syncthreads();
+    mbar_wait(b, parity);                              // every warp polls for itself: no CTA barrier just to wait
     fence_after_sync();
   };
 
@@ -1342,9 +1341,8 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_tc_bwd_kernel(MlpBwdArgs A
       issue_gemm(tmem + 0, sZ, 128, 64 * 16, 256, sW2, 128 * 16, 128, 2 * 128 * 16, make_idesc(128, 128, false, true), 4, false);
       mma_commit(&bar);
     }
-    if (warp == 0) mbar_wait(&bar, phase);
+    mbar_wait(&bar, phase);                     // every warp polls for itself
     phase ^= 1;
-    __syncthreads();
     fence_after_sync();
     load_r_chunk<256>(r1i, rt, h, 0, rw1);       // consumed after the second MMA
     mlp_bwd_layer<128, true>(tmem + 0, 0.f, nullptr, q, h, lane, grow, live, r2i, rw2, par + PAR_G1, s_statB, s_acc + ACC_L1,
@@ -1357,9 +1355,8 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_tc_bwd_kernel(MlpBwdArgs A
       issue_gemm(tmem + 128, sZ, 128, 128 * 16, 256, sW1, 256 * 16, 128, 2 * 256 * 16, make_idesc(128, 256, false, true), 8, false);
       mma_commit(&bar);
     }
-    if (warp == 0) mbar_wait(&bar, phase);
+    mbar_wait(&bar, phase);                     // every warp polls for itself
     phase ^= 1;
-    __syncthreads();
     fence_after_sync();
     mlp_bwd_layer<256, true>(tmem + 128, 0.f, nullptr, q, h, lane, grow, live, r1i, rw1, par + PAR_G0, s_statB, s_acc + ACC_L0,
                              ztile, z1i, A.st1 + tile * 256);
@@ -1371,9 +1368,8 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_tc_bwd_kernel(MlpBwdArgs A
       issue_gemm(tmem + 384, sZ, 128, 256 * 16, 256, sW0, 64 * 16, 128, 2 * 64 * 16, make_idesc(128, 64, false, true), 16, false);
       mma_commit(&bar);
     }
-    if (warp == 0) mbar_wait(&bar, phase);
+    mbar_wait(&bar, phase);                     // every warp polls for itself
     phase ^= 1;
-    __syncthreads();
     fence_after_sync();
     {
       float v[16];
