@@ -121,6 +121,9 @@ struct MlpFwdArgs {
   DropoutRng rng[3];
 };
 
+// named barrier of the 4 warps (128 threads) that own TMEM lane quarter q in the 16-warp MLP kernels
+__device__ __forceinline__ void quarter_sync(int q) { asm volatile("bar.sync %0, 128;" ::"r"(q + 1) : "memory"); }
+
 // weights fp32 [ROWS, ld] (first COLS columns) -> bf16 canonical image
 template <int ROWS, int COLS>
 __device__ __forceinline__ void load_weight_image(uint8_t* img, const float* __restrict__ w, int ld, int tid, int nthreads) {
@@ -188,7 +191,7 @@ __device__ __forceinline__ void mlp_epilogue(uint32_t tmem_acc, int q, int h, in
   float sum = sum4[0] + sum4[1], sq = sq4[0] + sq4[1];
   s_stat[(rt * MLP_NH + h) * 2 + 0] = sum;
   s_stat[(rt * MLP_NH + h) * 2 + 1] = sq;
-  __syncthreads();
+  quarter_sync(q);          // only the four warps that share these 32 rows exchange statistics
   sum = 0.f;
   sq = 0.f;
 #pragma unroll
@@ -1217,7 +1220,7 @@ __device__ __forceinline__ void mlp_bwd_layer(uint32_t tmem_dy, float dml, const
   s2 = (s2p[0] + s2p[1]) + (s2p[2] + s2p[3]);
   s_statB[(rt * MLP_NH + h) * 2 + 0] = s1;
   s_statB[(rt * MLP_NH + h) * 2 + 1] = s2;
-  __syncthreads();
+  quarter_sync(q);          // only the four warps that share these 32 rows exchange their sums
   s1 = 0.f;
   s2 = 0.f;
 #pragma unroll
