@@ -639,6 +639,8 @@ def main():
                 "whole_step_hbm_view": {"algorithmic_bytes": step_bytes, "ms": ms_step, "achieved": step_bytes / ms_step / 1e6,
                                         "unit": "GB/s", "frac": step_bytes / ms_step / 1e6 / hbm},
                 "pieces_sum_ms": pieces_ms, "kernels": kernels}
+    if "hbm_view" in kt:          # tower stages: SURVEY 8d counts them against the tensor pipe; their intensity says HBM
+        roofline["hbm_view"] = kt["hbm_view"]
 
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:
