@@ -1,5 +1,6 @@
 // extern "C" boundary of libncf_b200.so: argument checking, workspace carving, kernel sequencing.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "ncf_tower.cuh"
@@ -75,19 +76,22 @@ extern "C" int ncf_forward(const ncf_run_cfg* cfg, const ncf_tables* T, const fl
 
 static int backward_impl(const ncf_run_cfg* cfg, const ncf_adam_cfg* adam, const ncf_tables* T, const float* dense,
                          float* dense_grad, const int64_t* user_ids, const int64_t* item_ids, int64_t N,
-                         const float* grad_out, void* workspace, int64_t workspace_bytes, void* stream, cudaEvent_t sorted);
+                         const float* grad_out, void* workspace, int64_t workspace_bytes, void* stream, cudaEvent_t sorted,
+                         bool preswept);
 
 extern "C" int ncf_backward(const ncf_run_cfg* cfg, const ncf_adam_cfg* adam, const ncf_tables* T, const float* dense,
                             float* dense_grad, const int64_t* user_ids, const int64_t* item_ids, int64_t N,
                             const float* grad_out, void* workspace, int64_t workspace_bytes, void* stream) {
   return backward_impl(cfg, adam, T, dense, dense_grad, user_ids, item_ids, N, grad_out, workspace, workspace_bytes, stream,
-                       nullptr);
+                       nullptr, false);
 }
 
-// sorted != null: the id sort of the embedding backward already runs on the auxiliary stream and signals this event
+// sorted != null: the id sort of the embedding backward already runs on the auxiliary stream and signals this event;
+// preswept: so does the dense-equivalent sweep of the rows this batch does not touch (before the event)
 static int backward_impl(const ncf_run_cfg* cfg, const ncf_adam_cfg* adam, const ncf_tables* T, const float* dense,
                          float* dense_grad, const int64_t* user_ids, const int64_t* item_ids, int64_t N,
-                         const float* grad_out, void* workspace, int64_t workspace_bytes, void* stream, cudaEvent_t sorted) {
+                         const float* grad_out, void* workspace, int64_t workspace_bytes, void* stream, cudaEvent_t sorted,
+                         bool preswept) {
   NCF_TRY(check_cfg(cfg, N));
   NCF_REQUIRE(adam && T && dense && dense_grad && user_ids && item_ids && grad_out && workspace, "backward: null argument");
   NCF_REQUIRE(cfg->training, "backward: needs the workspace of a training-mode forward");
@@ -102,8 +106,8 @@ static int backward_impl(const ncf_run_cfg* cfg, const ncf_adam_cfg* adam, const
   if (adam->emb_mode != NCF_EMB_NONE) {
     if (sorted) NCF_CUDA(cudaStreamWaitEvent(st, sorted, 0));
     NCF_TRY(emb_bwd_both(adam, T, dense, dense_grad, user_ids, item_ids, N, w.d_mf, w.dxu, w.dxp, w.y_pmf, w.y_umf, w.emb, w.emb_bytes, st,
-                         sorted != nullptr));
-    if (adam->emb_mode == NCF_EMB_ADAM_DENSE_EQUIV) NCF_TRY(ncf_emb_adam_sweep(adam, T, stream));
+                         sorted != nullptr, preswept));
+    if (adam->emb_mode == NCF_EMB_ADAM_DENSE_EQUIV && !preswept) NCF_TRY(ncf_emb_adam_sweep(adam, T, stream));
   }
   return NCF_OK;
 }
@@ -168,8 +172,11 @@ extern "C" int ncf_train_step(const ncf_run_cfg* cfg, const ncf_adam_cfg* adam, 
     return NCF_ERR_WORKSPACE;
   }
   // The id sort of the embedding backward depends on the ids only: with an auxiliary stream (ncf_set_aux_stream) it
-  // is forked off here and runs next to the gather / attention kernels, which leave SM resources free.
+  // is forked off here and runs next to the gather / attention kernels, which leave SM resources free.  So does the
+  // dense-equivalent sweep: it updates exactly the rows this batch does NOT name, which nothing else in the step reads
+  // or writes, and the tower kernels it overlaps are not HBM-bound.
   cudaEvent_t sorted = nullptr;
+  bool preswept = false;
   if (g_aux_stream && adam->emb_mode != NCF_EMB_NONE && adam->emb_mode != NCF_EMB_MATERIALIZE) {
     if (!g_ev_fork) {
       NCF_CUDA(cudaEventCreateWithFlags(&g_ev_fork, cudaEventDisableTiming));
@@ -178,6 +185,11 @@ extern "C" int ncf_train_step(const ncf_run_cfg* cfg, const ncf_adam_cfg* adam, 
     NCF_CUDA(cudaEventRecord(g_ev_fork, st));                  // the previous step's K6 has released the sort buffers
     NCF_CUDA(cudaStreamWaitEvent(g_aux_stream, g_ev_fork, 0));
     NCF_TRY(emb_sort_both(T, user_ids, item_ids, N, w.emb, w.emb_bytes, g_aux_stream));
+    static const bool early_sweep = !(getenv("NCF_EARLY_SWEEP") && getenv("NCF_EARLY_SWEEP")[0] == '0');   // A/B switch
+    if (adam->emb_mode == NCF_EMB_ADAM_DENSE_EQUIV && early_sweep) {
+      NCF_TRY(emb_sweep_early(adam, T, user_ids, item_ids, N, g_aux_stream));
+      preswept = true;
+    }
     NCF_CUDA(cudaEventRecord(g_ev_sorted, g_aux_stream));
     sorted = g_ev_sorted;
   }
@@ -185,6 +197,7 @@ extern "C" int ncf_train_step(const ncf_run_cfg* cfg, const ncf_adam_cfg* adam, 
   NCF_TRY(ncf_forward(cfg, T, dense, user_ids, item_ids, N, nullptr, nullptr, nullptr, out, workspace, workspace_bytes, stream));
   // BCELoss gradient goes into the (not yet used) backward scratch g128b
   NCF_TRY(launch_bce(out, targets, N, loss_out, w.g128b, st));
-  NCF_TRY(backward_impl(cfg, adam, T, dense, dense_grad, user_ids, item_ids, N, w.g128b, workspace, workspace_bytes, stream, sorted));
+  NCF_TRY(backward_impl(cfg, adam, T, dense, dense_grad, user_ids, item_ids, N, w.g128b, workspace, workspace_bytes, stream, sorted,
+                        preswept));
   return ncf_dense_adam(dense, dense_grad, dense_m, dense_v, kLayout.total, adam, stream);
 }

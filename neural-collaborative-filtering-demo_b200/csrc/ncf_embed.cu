@@ -240,6 +240,8 @@ struct EmbBwdArgs {
   float* v[2];
   float* g[2];
   uint8_t* touched;
+  uint8_t touched_val;            // what phase 2 stores for an updated row: 1 = mark for the sweep that follows, 0 = the
+                                  // sweep already ran on the pre-marked flags (ncf_train_step, auxiliary stream): clear
   const float* other_mf;          // other side's MF table (for the GMF product), used when other_y == null
   const float* other_y;           // [N,64] LN'd MF row of the other side saved by the forward (or null)
   const float* own_y;             // [N,64] LN'd MF row of THIS side saved by the forward (or null): d mf_output.weight
@@ -562,7 +564,7 @@ __global__ void __launch_bounds__(EB_THREADS, 3) emb_bwd_phase2_kernel(EmbBwdArg
         st4(A.w[half] + o, wn);
         st4(A.m[half] + o, mm);
         st4(A.v[half] + o, vv);
-        if (A.touched && lane == 0) A.touched[id - A.id_off] = 1;
+        if (A.touched && lane == 0) A.touched[id - A.id_off] = A.touched_val;
       }
     }
   }
@@ -587,7 +589,7 @@ __global__ void __launch_bounds__(256) emb_adam_sweep_kernel(float* __restrict__
                                                               float* __restrict__ v0, float* __restrict__ w1,
                                                               float* __restrict__ m1, float* __restrict__ v1,
                                                               uint8_t* __restrict__ touched, int64_t rows,
-                                                              AdamScalars s) {
+                                                              AdamScalars s, bool keep_flags) {
   const int lane = threadIdx.x & 31, half = lane >> 4, l16 = lane & 15;
   const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
@@ -598,7 +600,7 @@ __global__ void __launch_bounds__(256) emb_adam_sweep_kernel(float* __restrict__
     const uint8_t t = touched ? touched[r] : 0;
     if (t) {
       __syncwarp();
-      if (lane == 0) touched[r] = 0;
+      if (lane == 0 && !keep_flags) touched[r] = 0;
       continue;
     }
     const int64_t o = r * D + 4 * l16;
@@ -607,6 +609,16 @@ __global__ void __launch_bounds__(256) emb_adam_sweep_kernel(float* __restrict__
     st4(w + o, ww);
     st4(m + o, mm);
     st4(v + o, vv);
+  }
+}
+
+// flags of the rows a batch will update, straight from its ids (benign write races: every writer stores 1)
+__global__ void mark_touched_kernel(const int64_t* __restrict__ user_ids, const int64_t* __restrict__ item_ids, int64_t n,
+                                    uint8_t* __restrict__ touched_user, uint8_t* __restrict__ touched_item) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    touched_user[user_ids[i]] = 1;
+    touched_item[item_ids[i]] = 1;
   }
 }
 
@@ -795,6 +807,7 @@ static int run_emb_bwd(const ncf_adam_cfg* adam, const ncf_tables* T, const floa
   A.g[0] = T->g[side];
   A.g[1] = T->g[2 + side];
   A.touched = adam->emb_mode == NCF_EMB_ADAM_DENSE_EQUIV ? T->touched[side] : nullptr;
+  A.touched_val = 1;
   A.other_mf = T->w[side ? 0 : 1];
   A.other_y = other_y_mf;
   A.own_y = nullptr;
@@ -881,7 +894,7 @@ int emb_sort_both(const ncf_tables* T, const int64_t* user_ids, const int64_t* i
 int emb_bwd_both(const ncf_adam_cfg* adam, const ncf_tables* T, const float* dense, float* dense_grad,
                  const int64_t* user_ids, const int64_t* item_ids, int64_t N, const float* d_mf_pred, const float* dxu,
                  const float* dxp, const float* y_item_mf, const float* y_user_mf, void* workspace, int64_t workspace_bytes,
-                 cudaStream_t st, bool presorted) {
+                 cudaStream_t st, bool presorted, bool preswept) {
   if (N == 0 || adam->emb_mode == NCF_EMB_NONE) return NCF_OK;
   NCF_REQUIRE(2 * N < ((int64_t)1 << 31), "emb_bwd: N too large");
   NCF_REQUIRE(T->rows_user + T->rows_item < ((int64_t)1 << 32), "emb_bwd: too many table rows for 32-bit keys");
@@ -915,6 +928,7 @@ int emb_bwd_both(const ncf_adam_cfg* adam, const ncf_tables* T, const float* den
     A.g[0] = T->g[side];
     A.g[1] = T->g[2 + side];
     A.touched = adam->emb_mode == NCF_EMB_ADAM_DENSE_EQUIV ? T->touched[side] : nullptr;
+    A.touched_val = preswept ? 0 : 1;
     A.other_mf = T->w[side ? 0 : 1];
     A.other_y = side ? y_user_mf : y_item_mf;       // null: gather the other side's table row and LayerNorm it again
     A.own_y = side ? nullptr : y_user_mf;
@@ -960,7 +974,7 @@ extern "C" int ncf_emb_bwd_adam_both(const ncf_adam_cfg* adam, const ncf_tables*
   NCF_REQUIRE(adam && T && dense && user_ids && item_ids && d_mf_pred && d_xu && d_xp && y_item_mf && workspace,
               "emb_bwd_adam_both: null argument");
   return emb_bwd_both(adam, T, dense, dense_grad, user_ids, item_ids, N, d_mf_pred, d_xu, d_xp, y_item_mf, y_user_mf,
-                      workspace, workspace_bytes, (cudaStream_t)stream, false);
+                      workspace, workspace_bytes, (cudaStream_t)stream, false, false);
 }
 
 extern "C" int ncf_emb_bwd_adam(const ncf_adam_cfg* adam, const ncf_tables* T, const float* dense, float* dense_grad,
@@ -1125,20 +1139,38 @@ extern "C" int ncf_shard_owner_update(const ncf_adam_cfg* adam, const ncf_tables
                      workspace, workspace_bytes, stream);
 }
 
-extern "C" int ncf_emb_adam_sweep(const ncf_adam_cfg* adam, const ncf_tables* T, void* stream) {
-  NCF_REQUIRE(adam && T, "emb_adam_sweep: null argument");
+namespace ncf {
+static int launch_sweep(const ncf_adam_cfg* adam, const ncf_tables* T, bool keep_flags, cudaStream_t st) {
   const AdamScalars s = adam_scalars(*adam);
   for (int side = 0; side < 2; ++side) {
     const int64_t rows = side ? T->rows_item : T->rows_user;
     if (rows == 0) continue;
     NCF_REQUIRE(T->m[side] && T->v[side] && T->m[2 + side] && T->v[2 + side], "emb_adam_sweep: needs m and v");
     const int grid = (int)std::min<int64_t>((rows + 7) / 8, (int64_t)num_sms() * 8);
-    emb_adam_sweep_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(T->w[side], T->m[side], T->v[side], T->w[2 + side],
-                                                                  T->m[2 + side], T->v[2 + side], T->touched[side],
-                                                                  rows, s);
+    emb_adam_sweep_kernel<<<grid, 256, 0, st>>>(T->w[side], T->m[side], T->v[side], T->w[2 + side], T->m[2 + side],
+                                                T->v[2 + side], T->touched[side], rows, s, keep_flags);
     NCF_LAUNCH_CHECK();
   }
   return NCF_OK;
+}
+
+// The sweep depends on WHICH rows a batch updates, not on anything the step computes, and it writes only rows the step
+// neither reads nor writes: flags are set from the ids, the sweep leaves them alone, and emb_bwd_both(preswept) clears
+// the flag of every row it updates.  Same per-row arithmetic as sweep-after-K6, so the tables come out bit-identical.
+int emb_sweep_early(const ncf_adam_cfg* adam, const ncf_tables* T, const int64_t* user_ids, const int64_t* item_ids, int64_t N,
+                    cudaStream_t st) {
+  NCF_REQUIRE(T->touched[0] && T->touched[1], "dense-equivalent mode needs tables->touched");
+  if (N > 0) {
+    mark_touched_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(user_ids, item_ids, N, T->touched[0], T->touched[1]);
+    NCF_LAUNCH_CHECK();
+  }
+  return launch_sweep(adam, T, true, st);
+}
+}  // namespace ncf
+
+extern "C" int ncf_emb_adam_sweep(const ncf_adam_cfg* adam, const ncf_tables* T, void* stream) {
+  NCF_REQUIRE(adam && T, "emb_adam_sweep: null argument");
+  return ncf::launch_sweep(adam, T, false, (cudaStream_t)stream);
 }
 
 extern "C" int ncf_dense_adam(float* w, const float* g, float* m, float* v, int64_t n, const ncf_adam_cfg* adam,
