@@ -115,8 +115,10 @@ NCF_API int ncf_version(void);
 NCF_API const char* ncf_last_error(void);
 NCF_API int64_t ncf_launch_count(void);   /* kernels this library has launched so far (process-wide) */
 /* Every call enqueues on its `stream` argument only and never synchronises.  One opt-in exception: with an
- * auxiliary stream set here, ncf_train_step forks the id sort of the embedding backward (which depends on the
- * ids alone) onto it, ordered with events against the stream argument.  NULL (default) switches that off. */
+ * auxiliary stream set here, ncf_train_step forks the id sort of the embedding backward and, in
+ * NCF_EMB_ADAM_DENSE_EQUIV mode, the sweep of the rows the batch does not name (both depend on the ids alone and
+ * touch nothing the rest of the step reads or writes) onto it, ordered with events against the stream argument;
+ * the fork is joined again before ncf_train_step's embedding backward.  NULL (default) switches that off. */
 NCF_API int ncf_set_aux_stream(void* stream);
 NCF_API int64_t ncf_dense_numel(void);
 NCF_API int64_t ncf_dense_offset(int32_t dense_id);

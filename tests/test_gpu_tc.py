@@ -222,12 +222,20 @@ def _engine_losses(aux, host_prefetch, steps=5):
     return losses, m.mf_embedding_collection.embedding_bags["user_id"].weight.detach().cpu().clone()
 
 
+def _initial_user_mf():
+    from tests.helpers import golden_params
+    p, _ = golden_params()
+    return p["mf_embedding_collection.embedding_bags.user_id.weight"].detach().cpu()
+
+
 def test_aux_stream_and_host_prefetch_do_not_change_results():
-    """The id sort forked onto the auxiliary stream and the double-buffered H2D staging are pure scheduling: same
-    losses and updated tables with and without them (up to the run-to-run noise of the float atomics that flush
-    the per-CTA bias / LayerNorm gradient sums)."""
+    """The id sort and the dense-equivalent sweep forked onto the auxiliary stream and the double-buffered H2D staging
+    are pure scheduling: same losses and updated tables with and without them (up to the run-to-run noise of the float
+    atomics that flush the per-CTA bias / LayerNorm gradient sums); rows no batch names (users >= 300) only ever see
+    the sweep, so they must come out bit-identical whether it runs before or after K6."""
     base_l, base_w = _engine_losses(aux=False, host_prefetch=None)
     for aux, pf in ((True, None), (True, False), (True, True), (False, True)):
         l, w = _engine_losses(aux=aux, host_prefetch=pf)
         assert max(abs(a - b) for a, b in zip(l, base_l)) < 2e-4, (aux, pf, l, base_l)
         assert float((w - base_w).abs().mean()) < 1e-5
+        assert torch.equal(w[300:], base_w[300:]) and not torch.equal(w[300:], _initial_user_mf()[300:])
