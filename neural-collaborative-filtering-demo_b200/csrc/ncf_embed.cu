@@ -743,7 +743,7 @@ struct EmbWs {
   int32_t *vals_in, *vals_out;
   uint32_t* other_sorted;
   float* dmf_sorted;
-  float* acc_buf;
+  float *acc_buf, *acc_buf2;      // second buffer: the two sides running side by side (emb_bwd_both with a side stream)
   int32_t* counters;        // dynamic chunk schedulers of the two phase-2 launches
   void* cub_tmp;
   size_t cub_bytes;
@@ -765,6 +765,7 @@ static EmbWs carve_emb_ws(void* ws, int64_t N) {
   cub::DeviceRadixSort::SortPairs(nullptr, w.cub_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr,
                                   (const int32_t*)nullptr, (int32_t*)nullptr, (int)std::max<int64_t>(2 * N, 1), 0, 32);
   w.cub_tmp = c.take<char>((int64_t)w.cub_bytes);
+  w.acc_buf2 = c.take<float>(N * 2 * D);
   w.total = align_up(c.used, 256);
   return w;
 }
@@ -894,7 +895,7 @@ int emb_sort_both(const ncf_tables* T, const int64_t* user_ids, const int64_t* i
 int emb_bwd_both(const ncf_adam_cfg* adam, const ncf_tables* T, const float* dense, float* dense_grad,
                  const int64_t* user_ids, const int64_t* item_ids, int64_t N, const float* d_mf_pred, const float* dxu,
                  const float* dxp, const float* y_item_mf, const float* y_user_mf, void* workspace, int64_t workspace_bytes,
-                 cudaStream_t st, bool presorted, bool preswept) {
+                 cudaStream_t st, bool presorted, bool preswept, cudaStream_t side_stream) {
   if (N == 0 || adam->emb_mode == NCF_EMB_NONE) return NCF_OK;
   NCF_REQUIRE(2 * N < ((int64_t)1 << 31), "emb_bwd: N too large");
   NCF_REQUIRE(T->rows_user + T->rows_item < ((int64_t)1 << 32), "emb_bwd: too many table rows for 32-bit keys");
@@ -917,7 +918,21 @@ int emb_bwd_both(const ncf_adam_cfg* adam, const ncf_tables* T, const float* den
   const int wpb = EB_THREADS / 32;
   const int grid = (int)std::min<int64_t>((nchunks + wpb - 1) / wpb, (int64_t)num_sms() * 8);
   NCF_CUDA(cudaMemsetAsync(w.counters, 0, 4 * sizeof(int32_t), st));
+  // With the forward's saved rows (the lean phase 1) the two sides share nothing but the read-only inputs and the
+  // atomically flushed dense gradients: given a side stream, the item side runs there next to the user side, each
+  // with its own segment-sum buffer.  Phase 2 is latency-bound (long runs of popular ids), so the overlap pays.
+  static cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  const bool two_streams = side_stream && side_stream != st && y_item_mf && y_user_mf;
+  if (two_streams) {
+    if (!ev_fork) {
+      NCF_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+      NCF_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+    }
+    NCF_CUDA(cudaEventRecord(ev_fork, st));
+    NCF_CUDA(cudaStreamWaitEvent(side_stream, ev_fork, 0));
+  }
   for (int side = 1; side >= 0; --side) {
+    const cudaStream_t sst = (two_streams && side == 1) ? side_stream : st;      // this side's stream
     EmbBwdArgs A;
     A.w[0] = T->w[side];
     A.w[1] = T->w[2 + side];
@@ -946,7 +961,7 @@ int emb_bwd_both(const ncf_adam_cfg* adam, const ncf_tables* T, const float* den
     A.d_x = side ? dxp : dxu;
     A.dense = dense;
     A.dense_grad = dense_grad;
-    A.acc_buf = w.acc_buf;
+    A.acc_buf = (two_streams && side == 1) ? w.acc_buf2 : w.acc_buf;
     A.N = N;
     A.id_off = side ? (uint32_t)T->rows_user : 0u;
     A.mode = adam->emb_mode;
@@ -954,14 +969,18 @@ int emb_bwd_both(const ncf_adam_cfg* adam, const ncf_tables* T, const float* den
     A.adam = adam_scalars(*adam);
     A.chunk_counter = w.counters + side;
     if (A.other_y && (!A.accumulate_wmf || A.own_y)) {      // the usual case: K1 saved both LayerNorm-ed MF rows
-      if (A.accumulate_wmf) emb_bwd_phase1_lean_kernel<true><<<grid, EB_THREADS, 0, st>>>(A);
-      else emb_bwd_phase1_lean_kernel<false><<<grid, EB_THREADS, 0, st>>>(A);
+      if (A.accumulate_wmf) emb_bwd_phase1_lean_kernel<true><<<grid, EB_THREADS, 0, sst>>>(A);
+      else emb_bwd_phase1_lean_kernel<false><<<grid, EB_THREADS, 0, sst>>>(A);
     } else {
-      emb_bwd_phase1_kernel<<<grid, EB_THREADS, 0, st>>>(A);
+      emb_bwd_phase1_kernel<<<grid, EB_THREADS, 0, sst>>>(A);
     }
     NCF_LAUNCH_CHECK();
-    emb_bwd_phase2_kernel<<<std::min(grid, num_sms() * 3), EB_THREADS, 0, st>>>(A);     // resident blocks pull chunks
+    emb_bwd_phase2_kernel<<<std::min(grid, num_sms() * 3), EB_THREADS, 0, sst>>>(A);     // resident blocks pull chunks
     NCF_LAUNCH_CHECK();
+  }
+  if (two_streams) {
+    NCF_CUDA(cudaEventRecord(ev_join, side_stream));
+    NCF_CUDA(cudaStreamWaitEvent(st, ev_join, 0));
   }
   return NCF_OK;
 }
@@ -974,7 +993,7 @@ extern "C" int ncf_emb_bwd_adam_both(const ncf_adam_cfg* adam, const ncf_tables*
   NCF_REQUIRE(adam && T && dense && user_ids && item_ids && d_mf_pred && d_xu && d_xp && y_item_mf && workspace,
               "emb_bwd_adam_both: null argument");
   return emb_bwd_both(adam, T, dense, dense_grad, user_ids, item_ids, N, d_mf_pred, d_xu, d_xp, y_item_mf, y_user_mf,
-                      workspace, workspace_bytes, (cudaStream_t)stream, false, false);
+                      workspace, workspace_bytes, (cudaStream_t)stream, false, false, nullptr);
 }
 
 extern "C" int ncf_emb_bwd_adam(const ncf_adam_cfg* adam, const ncf_tables* T, const float* dense, float* dense_grad,
