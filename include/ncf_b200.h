@@ -118,7 +118,10 @@ NCF_API int64_t ncf_launch_count(void);   /* kernels this library has launched s
  * auxiliary stream set here, ncf_train_step forks the id sort of the embedding backward and, in
  * NCF_EMB_ADAM_DENSE_EQUIV mode, the sweep of the rows the batch does not name (both depend on the ids alone and
  * touch nothing the rest of the step reads or writes) onto it, ordered with events against the stream argument;
- * the fork is joined again before ncf_train_step's embedding backward.  NULL (default) switches that off. */
+ * the fork is joined again before ncf_train_step's embedding backward, which then runs its item side on the
+ * auxiliary stream next to the user side (so does a direct ncf_emb_bwd_adam_both call); everything is joined
+ * back into the stream argument before the call's last kernel.  The caller keeps the stream alive while it is
+ * set.  NULL (default) switches all of that off. */
 NCF_API int ncf_set_aux_stream(void* stream);
 NCF_API int64_t ncf_dense_numel(void);
 NCF_API int64_t ncf_dense_offset(int32_t dense_id);

@@ -28,7 +28,9 @@ extern "C" int64_t ncf_launch_count(void) { return (int64_t)g_launches; }
 
 // optional auxiliary stream for work that is independent of the main stream's kernels (ncf_train_step forks the
 // id sort of the embedding backward onto it); NULL = everything on the stream argument (default)
-static cudaStream_t g_aux_stream = nullptr;
+namespace ncf {
+cudaStream_t g_aux_stream = nullptr;
+}
 static cudaEvent_t g_ev_fork = nullptr, g_ev_sorted = nullptr;
 extern "C" int ncf_set_aux_stream(void* stream) {
   g_aux_stream = (cudaStream_t)stream;
@@ -104,10 +106,9 @@ static int backward_impl(const ncf_run_cfg* cfg, const ncf_adam_cfg* adam, const
   cudaStream_t st = (cudaStream_t)stream;
   NCF_TRY(tower_f32_backward(*cfg, dense, dense_grad, N, grad_out, w, st));
   if (adam->emb_mode != NCF_EMB_NONE) {
-    static const bool two_sides = !(getenv("NCF_K6_TWO_STREAMS") && getenv("NCF_K6_TWO_STREAMS")[0] == '0');   // A/B switch
     if (sorted) NCF_CUDA(cudaStreamWaitEvent(st, sorted, 0));
     NCF_TRY(emb_bwd_both(adam, T, dense, dense_grad, user_ids, item_ids, N, w.d_mf, w.dxu, w.dxp, w.y_pmf, w.y_umf, w.emb, w.emb_bytes, st,
-                         sorted != nullptr, preswept, sorted && two_sides ? g_aux_stream : nullptr));
+                         sorted != nullptr, preswept, sorted ? g_aux_stream : nullptr));
     if (adam->emb_mode == NCF_EMB_ADAM_DENSE_EQUIV && !preswept) NCF_TRY(ncf_emb_adam_sweep(adam, T, stream));
   }
   return NCF_OK;

@@ -6,9 +6,12 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
+#include <stdlib.h>
+
 #include "ncf_common.cuh"
 
 namespace ncf {
+extern cudaStream_t g_aux_stream;      // ncf_set_aux_stream (ncf_abi.cu); null = none
 
 // ---- mbarrier / bulk-copy PTX ---------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -293,9 +296,9 @@ __device__ __forceinline__ void block_flush(float* s_red, float4 val, float* dst
   }
 }
 
-// Phase 1, lean variant for the single-GPU step (both LayerNorm-ed MF rows were saved by K1, d_mf was gathered
-// into sorted order): every per-sample input is a [N,64] row indexed by the sample row, so a position costs three
-// shuffles (row, d_mf, id), one 128-bit load per half (two for the side that also forms d mf_output.weight) and
+// Phase 1, lean variant for the single-GPU step (both LayerNorm-ed MF rows were saved by K1): every per-sample input
+// is a [N,64] row (or the scalar d_mf) indexed by the sample row, so a position costs three shuffles (row, d_mf, id),
+// one 128-bit load per half (two for the side that also forms d mf_output.weight) and
 // the multiply-adds - none of the source-selection logic of the general kernel below.
 template <bool WMF>
 __global__ void __launch_bounds__(EB_THREADS, 3) emb_bwd_phase1_lean_kernel(EmbBwdArgs A) {
@@ -314,7 +317,7 @@ __global__ void __launch_bounds__(EB_THREADS, 3) emb_bwd_phase1_lean_kernel(EmbB
     const int cnt = (int)min((int64_t)EB_CHUNK, A.N - p0);
     const uint32_t my_id = lane < cnt ? A.sorted_ids[p0 + lane] : 0xffffffffu;
     const int32_t my_row = lane < cnt ? A.perm[p0 + lane] : 0;
-    const float my_dmf = lane < cnt ? A.dmf_sorted[p0 + lane] : 0.f;
+    const float my_dmf = lane < cnt ? __ldg(A.d_mf_pred + my_row) : 0.f;      // 1.3 MB array, L2-resident
     float4 acc = make_float4(0, 0, 0, 0);
     int piece_first = 0;
     uint32_t id_prev = __shfl_sync(0xffffffffu, my_id, 0);
@@ -911,9 +914,12 @@ int emb_bwd_both(const ncf_adam_cfg* adam, const ncf_tables* T, const float* den
   }
   if (adam->emb_mode == NCF_EMB_ADAM_DENSE_EQUIV) NCF_REQUIRE(T->touched[0] && T->touched[1], "dense-equivalent mode needs tables->touched");
   if (!presorted) NCF_TRY(emb_sort_both(T, user_ids, item_ids, N, workspace, workspace_bytes, st));
-  gather_sorted_kernel<<<(unsigned)((2 * N + 255) / 256), 256, 0, st>>>(w.vals_out, user_ids, item_ids, d_mf_pred, N,
-                                                                        w.other_sorted, w.dmf_sorted);
-  NCF_LAUNCH_CHECK();
+  const bool lean = y_item_mf && y_user_mf;      // K1 saved both LayerNorm-ed MF rows: phase 1 reads everything by sample row
+  if (!lean) {
+    gather_sorted_kernel<<<(unsigned)((2 * N + 255) / 256), 256, 0, st>>>(w.vals_out, user_ids, item_ids, d_mf_pred, N,
+                                                                          w.other_sorted, w.dmf_sorted);
+    NCF_LAUNCH_CHECK();
+  }
   const int64_t nchunks = (N + EB_CHUNK - 1) / EB_CHUNK;
   const int wpb = EB_THREADS / 32;
   const int grid = (int)std::min<int64_t>((nchunks + wpb - 1) / wpb, (int64_t)num_sms() * 8);
@@ -922,7 +928,8 @@ int emb_bwd_both(const ncf_adam_cfg* adam, const ncf_tables* T, const float* den
   // atomically flushed dense gradients: given a side stream, the item side runs there next to the user side, each
   // with its own segment-sum buffer.  Phase 2 is latency-bound (long runs of popular ids), so the overlap pays.
   static cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  const bool two_streams = side_stream && side_stream != st && y_item_mf && y_user_mf;
+  static const bool two_ok = !(getenv("NCF_K6_TWO_STREAMS") && getenv("NCF_K6_TWO_STREAMS")[0] == '0');   // A/B switch
+  const bool two_streams = two_ok && side_stream && side_stream != st && lean;
   if (two_streams) {
     if (!ev_fork) {
       NCF_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
@@ -968,7 +975,7 @@ int emb_bwd_both(const ncf_adam_cfg* adam, const ncf_tables* T, const float* den
     A.accumulate_wmf = side == 0 ? 1 : 0;
     A.adam = adam_scalars(*adam);
     A.chunk_counter = w.counters + side;
-    if (A.other_y && (!A.accumulate_wmf || A.own_y)) {      // the usual case: K1 saved both LayerNorm-ed MF rows
+    if (lean) {      // the usual case
       if (A.accumulate_wmf) emb_bwd_phase1_lean_kernel<true><<<grid, EB_THREADS, 0, sst>>>(A);
       else emb_bwd_phase1_lean_kernel<false><<<grid, EB_THREADS, 0, sst>>>(A);
     } else {
@@ -993,7 +1000,7 @@ extern "C" int ncf_emb_bwd_adam_both(const ncf_adam_cfg* adam, const ncf_tables*
   NCF_REQUIRE(adam && T && dense && user_ids && item_ids && d_mf_pred && d_xu && d_xp && y_item_mf && workspace,
               "emb_bwd_adam_both: null argument");
   return emb_bwd_both(adam, T, dense, dense_grad, user_ids, item_ids, N, d_mf_pred, d_xu, d_xp, y_item_mf, y_user_mf,
-                      workspace, workspace_bytes, (cudaStream_t)stream, false, false, nullptr);
+                      workspace, workspace_bytes, (cudaStream_t)stream, false, false, ncf::g_aux_stream);
 }
 
 extern "C" int ncf_emb_bwd_adam(const ncf_adam_cfg* adam, const ncf_tables* T, const float* dense, float* dense_grad,

@@ -69,6 +69,7 @@ int emb_bwd_both(const ncf_adam_cfg* adam, const ncf_tables* T, const float* den
                  const int64_t* user_ids, const int64_t* item_ids, int64_t N, const float* d_mf_pred, const float* dxu,
                  const float* dxp, const float* y_item_mf, const float* y_user_mf, void* workspace, int64_t workspace_bytes,
                  cudaStream_t st, bool presorted = false, bool preswept = false, cudaStream_t side_stream = nullptr);
+extern cudaStream_t g_aux_stream;      // ncf_set_aux_stream (ncf_abi.cu); null = none
 int emb_sweep_early(const ncf_adam_cfg* adam, const ncf_tables* T, const int64_t* user_ids, const int64_t* item_ids, int64_t N,
                     cudaStream_t st);
 int emb_sort_both(const ncf_tables* T, const int64_t* user_ids, const int64_t* item_ids, int64_t N, void* workspace,
