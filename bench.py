@@ -43,8 +43,8 @@ FLOP_MLP_FWD = 131.1e3 + 0.5e3                 # MLP + heads/LN per row; backwar
 # bytes per sample row a fused implementation has to move: fp32 row vectors in and out,
 # bf16 saved activations between forward and backward
 BYTES_ATTN_FWD = 2 * 128 + 128                 # xu, xp (bf16 rows) in; a (bf16) out
-BYTES_MLP_FWD = 128 + 2 * (512 + 256) + 128 + 24 + 256 + 16        # a in; r1,y1,r2,y2,r3 (bf16), LN stats, y3, scalars out
-BYTES_MLP_BWD = (256 + 20) + (896 + 24 + 896 + 128) + (128 + 768 + 896)   # head (y3 + scalars); chain (r, stats, dz, da); wgrad
+BYTES_MLP_FWD = 128 + 2 * (512 + 256) + 128 + 24 + 16              # a in; r1,y1,r2,y2,r3 (bf16), LN stats, scalars out
+BYTES_MLP_BWD = 28 + (896 + 24 + 896 + 128) + (128 + 768 + 896)   # head (scalars); chain (r, stats, dz, da); wgrad
 BYTES_ATTN_BWD = 3 * 128 + 2 * 256             # xu, xp, da (bf16 rows) in; dxu, dxp (fp32) out
 
 

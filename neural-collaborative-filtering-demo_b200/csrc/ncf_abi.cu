@@ -177,14 +177,23 @@ extern "C" int ncf_train_step(const ncf_run_cfg* cfg, const ncf_adam_cfg* adam, 
   // is forked off here and runs next to the gather / attention kernels, which leave SM resources free.  So does the
   // dense-equivalent sweep: it updates exactly the rows this batch does NOT name, which nothing else in the step reads
   // or writes, and the tower kernels it overlaps are not HBM-bound.
+  // K1 is launched first so that a caller who has just synchronised (a training loop reading its loss every step)
+  // gets the main stream going before the dozen launches of the auxiliary stream are issued.
+  NCF_REQUIRE(T && user_ids && item_ids && workspace, "train_step: null argument");
   cudaEvent_t sorted = nullptr;
   bool preswept = false;
-  if (g_aux_stream && adam->emb_mode != NCF_EMB_NONE && adam->emb_mode != NCF_EMB_MATERIALIZE) {
+  const bool fork = g_aux_stream && adam->emb_mode != NCF_EMB_NONE && adam->emb_mode != NCF_EMB_MATERIALIZE;
+  if (fork) {
     if (!g_ev_fork) {
       NCF_CUDA(cudaEventCreateWithFlags(&g_ev_fork, cudaEventDisableTiming));
       NCF_CUDA(cudaEventCreateWithFlags(&g_ev_sorted, cudaEventDisableTiming));
     }
     NCF_CUDA(cudaEventRecord(g_ev_fork, st));                  // the previous step's K6 has released the sort buffers
+  }
+  NCF_CUDA(cudaMemsetAsync(dense_grad, 0, sizeof(float) * kLayout.total, st));                       // optimizer.zero_grad()
+  NCF_TRY(gather_ln_gmf_fwd_rows(tower_bf16_rows(*cfg), T, dense, user_ids, item_ids, N, nullptr, nullptr, w.mf_pred, w.xu, w.xp,
+                                 w.y_pmf, w.y_umf, stream));
+  if (fork) {
     NCF_CUDA(cudaStreamWaitEvent(g_aux_stream, g_ev_fork, 0));
     NCF_TRY(emb_sort_both(T, user_ids, item_ids, N, w.emb, w.emb_bytes, g_aux_stream));
     static const bool early_sweep = !(getenv("NCF_EARLY_SWEEP") && getenv("NCF_EARLY_SWEEP")[0] == '0');   // A/B switch
@@ -195,8 +204,7 @@ extern "C" int ncf_train_step(const ncf_run_cfg* cfg, const ncf_adam_cfg* adam, 
     NCF_CUDA(cudaEventRecord(g_ev_sorted, g_aux_stream));
     sorted = g_ev_sorted;
   }
-  NCF_CUDA(cudaMemsetAsync(dense_grad, 0, sizeof(float) * kLayout.total, st));                       // optimizer.zero_grad()
-  NCF_TRY(ncf_forward(cfg, T, dense, user_ids, item_ids, N, nullptr, nullptr, nullptr, out, workspace, workspace_bytes, stream));
+  NCF_TRY(tower_f32_forward(*cfg, dense, N, nullptr, nullptr, out, w, st));
   // BCELoss gradient goes into the (not yet used) backward scratch g128b
   NCF_TRY(launch_bce(out, targets, N, loss_out, w.g128b, st));
   NCF_TRY(backward_impl(cfg, adam, T, dense, dense_grad, user_ids, item_ids, N, w.g128b, workspace, workspace_bytes, stream, sorted,

@@ -654,6 +654,46 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
   }
 }
 
+// The tcgen05 MLP backward forms dh3 and d mlp_output.weight itself (from its LayerNorm column sums), so its head
+// backward is per-row scalar work only: d_mf_pred, d_mlp_pred and the gradients of final.0 and the two output biases.
+__global__ void __launch_bounds__(256) head_bwd_scalar_kernel(const float* __restrict__ grad_out, const float* __restrict__ p_saved,
+                                                              const float* __restrict__ mf_pred, const float* __restrict__ mlp_pred,
+                                                              const float* __restrict__ dense, float* __restrict__ d_mf_pred,
+                                                              float* __restrict__ d_mlp_pred, float* __restrict__ dense_grad,
+                                                              int64_t N) {
+  __shared__ float s_sc[8][5];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float a = __ldg(dense + NCF_OFF(NCF_P_FINAL_W)), c = __ldg(dense + NCF_OFF(NCF_P_FINAL_W) + 1);
+  float s[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (int64_t)gridDim.x * blockDim.x) {
+    const float p = p_saved[n];
+    const float dz = grad_out[n] * p * (1.0f - p);
+    const float dmf = dz * a, dml = dz * c;
+    d_mf_pred[n] = dmf;
+    d_mlp_pred[n] = dml;
+    s[0] = fmaf(dz, mf_pred[n], s[0]);
+    s[1] = fmaf(dz, mlp_pred[n], s[1]);
+    s[2] += dz;
+    s[3] += dmf;
+    s[4] += dml;
+  }
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) s[k] += __shfl_xor_sync(0xffffffffu, s[k], off);
+    if (lane == 0) s_sc[warp][k] = s[k];
+  }
+  __syncthreads();
+  if (threadIdx.x < 5) {
+    const int k = threadIdx.x;
+    float t = 0.f;
+    for (int wv = 0; wv < 8; ++wv) t += s_sc[wv][k];
+    const int64_t off = k == 0 ? NCF_OFF(NCF_P_FINAL_W) : k == 1 ? NCF_OFF(NCF_P_FINAL_W) + 1
+                        : k == 2 ? NCF_OFF(NCF_P_FINAL_B) : k == 3 ? NCF_OFF(NCF_P_MF_OUT_B) : NCF_OFF(NCF_P_MLP_OUT_B);
+    atomicAdd(dense_grad + off, t);
+  }
+}
+
 // nn.BCELoss (mean) + gradient (ATen binary_cross_entropy: log clamped at -100, backward
 // (p - y) / max(p (1 - p), 1e-12) / N)
 __global__ void __launch_bounds__(256) bce_kernel(const float* __restrict__ out, const float* __restrict__ tgt, int64_t N,
@@ -828,8 +868,12 @@ int tower_mlp_backward(const ncf_run_cfg& cfg, const float* dense, float* dg, in
   const int hgrid = (int)std::min<int64_t>((N * 16 + 255) / 256, (int64_t)num_sms() * 8);
   // head: d_mf, dh3 (-> g64a)
   const bool tcm = cfg.precision == NCF_BF16_TC;
-  head_bwd_kernel<<<hgrid, 256, 0, st>>>(grad_out, w.p_saved, w.mf_pred, w.mlp_pred, w.y3, P, w.d_mf, tcm ? nullptr : w.g64a,
-                                         tcm ? w.d_mlp : nullptr, dg, N);
+  if (tcm) {
+    const int sgrid = (int)std::min<int64_t>((N + 255) / 256, (int64_t)num_sms() * 4);
+    head_bwd_scalar_kernel<<<sgrid, 256, 0, st>>>(grad_out, w.p_saved, w.mf_pred, w.mlp_pred, P, w.d_mf, w.d_mlp, dg, N);
+  } else {
+    head_bwd_kernel<<<hgrid, 256, 0, st>>>(grad_out, w.p_saved, w.mf_pred, w.mlp_pred, w.y3, P, w.d_mf, w.g64a, nullptr, dg, N);
+  }
   NCF_LAUNCH_CHECK();
   if (cfg.precision == NCF_BF16_TC) {
     NCF_TRY(mlp_tc_backward(cfg, dense, dg, N, w, st));   // dy3 (g64a) -> da (g64a), all MLP parameter gradients

@@ -1060,7 +1060,7 @@ int mlp_tc_forward(const ncf_run_cfg& cfg, const float* dense, int64_t N, const 
   A.out = out;
   A.out2 = w.p_saved;
   A.mlp_pred = w.mlp_pred;
-  A.y3 = w.y3;
+  A.y3 = nullptr;      // the head runs inside the kernel and the backward rebuilds y3's column sums from r3 (mlp_bwd_layer)
   A.r1 = train ? (__nv_bfloat16*)w.r1b : nullptr;
   A.y1 = train ? (__nv_bfloat16*)w.y1b : nullptr;
   A.r2 = train ? (__nv_bfloat16*)w.r2b : nullptr;
@@ -1170,11 +1170,12 @@ __device__ __forceinline__ void mlp_bwd_layer(uint32_t tmem_dy, float dml, const
     if (FROM_TMEM) {
       tmem_ldw<CW>(taddr + ch * CW, dy);
     } else {
-      // layer 3: dL/dy3 = dL/d mlp_pred * mlp_output.weight (backward of the output head, architecture.py:345);
-      // dml is 0 for rows beyond N
-      const int c0 = h * PART + ch * CW;
+      // layer 3: dL/dy3 = dL/d mlp_pred * mlp_output.weight (backward of the output head, architecture.py:345).
+      // The weight factor lives in `gam` (gamma * dropout scale * w_out), so the upstream value of every column of
+      // the row is dL/d mlp_pred itself and the column sums of pass B are those of keep * dml * xhat and keep * dml:
+      // d gamma, d beta AND d mlp_output.weight all follow from them at the flush.  dml is 0 for rows beyond N
 #pragma unroll
-      for (int i = 0; i < CW; ++i) dy[i] = dml * wout[c0 + i];
+      for (int i = 0; i < CW; ++i) dy[i] = dml;
     }
   };
 
@@ -1289,8 +1290,8 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_tc_bwd_kernel(MlpBwdArgs A
     par[PAR_G0 + i] = P[NCF_OFF(NCF_P_LN0_W) + i] * sc0;
     if (i < 128) par[PAR_G1 + i] = P[NCF_OFF(NCF_P_LN1_W) + i] * sc1;
     if (i < 64) {
-      par[PAR_G2 + i] = P[NCF_OFF(NCF_P_LN2_W) + i] * sc2;
       par[PAR_WOUT + i] = P[NCF_OFF(NCF_P_MLP_OUT_W) + i];
+      par[PAR_G2 + i] = P[NCF_OFF(NCF_P_LN2_W) + i] * sc2 * P[NCF_OFF(NCF_P_MLP_OUT_W) + i];     // see mlp_bwd_layer<64, false>
     }
   }
   for (int i = tid; i < ACC_COUNT; i += MLP_THREADS) s_acc[i] = 0.f;
@@ -1402,7 +1403,12 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_tc_bwd_kernel(MlpBwdArgs A
     } else {
       k -= ACC_L2;
       off = k < 64 ? NCF_OFF(NCF_P_LN2_W) + k : k < 128 ? NCF_OFF(NCF_P_LN2_B) + (k - 64) : NCF_OFF(NCF_P_MLP2_B) + (k - 128);
-      sc = k < 128 ? sc2 : 1.f;
+      // layer 3 summed keep * dml * xhat and keep * dml (no w_out): d gamma / d beta get the column's w_out here and
+      // d mlp_output.weight[c] = sum_r dml * y3[r,c] = scale * (gamma_c * sum keep dml xhat + beta_c * sum keep dml)
+      sc = k < 128 ? sc2 * par[PAR_WOUT + (k & 63)] : 1.f;
+      if (k < 64)
+        atomicAdd(dg + NCF_OFF(NCF_P_MLP_OUT_W) + k,
+                  sc2 * fmaf(P[NCF_OFF(NCF_P_LN2_W) + k], s_acc[i], P[NCF_OFF(NCF_P_LN2_B) + k] * s_acc[i + 64]));
     }
     atomicAdd(dg + off, s_acc[i] * sc);
   }
