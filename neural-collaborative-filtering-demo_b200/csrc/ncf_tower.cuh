@@ -48,10 +48,10 @@ int tower_mlp_forward(const ncf_run_cfg& cfg, const float* dense, int64_t N, con
 int tower_mlp_backward(const ncf_run_cfg& cfg, const float* dense, float* dense_grad, int64_t N, const float* grad_out,
                        TowerWs& w, cudaStream_t st);
 int tower_attn_backward(const ncf_run_cfg& cfg, const float* dense, float* dense_grad, int64_t N, TowerWs& w, cudaStream_t st);
-// tcgen05 MLP tower (ncf_tower_tc.cu): forward from w.a (fills w.y3, w.mlp_pred, w.p_saved, out)
+// tcgen05 MLP tower (ncf_tower_tc.cu): forward from w.a (fills w.mlp_pred, w.p_saved, out; w.y3 stays unused)
 int mlp_tc_forward(const ncf_run_cfg& cfg, const float* dense, int64_t N, const int64_t* hour, const float* tail1,
                    float* out, TowerWs& w, cudaStream_t st);
-// backward from dy3 = w.g64a (fp32 [N,64]) to da = w.g64a; accumulates the MLP parameter gradients
+// backward from w.d_mlp (dL/d mlp_pred per row) to da = w.g64a; accumulates the MLP parameter gradients incl. mlp_output.weight
 int mlp_tc_backward(const ncf_run_cfg& cfg, const float* dense, float* dense_grad, int64_t N, TowerWs& w, cudaStream_t st);
 // tcgen05 projections of the attention block (fp32 tensors, bf16 operands)
 int tc_proj_forward(int which, const float* X, const float* W, const float* bias, float* Y, int64_t N, cudaStream_t st);
