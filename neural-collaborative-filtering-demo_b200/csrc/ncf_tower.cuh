@@ -7,6 +7,7 @@
 namespace ncf {
 
 // activations kept between forward and backward, carved out of the caller's workspace
+constexpr int MLP_WG_PART_COLS = 448 + 3;    // weight-gradient TMEM columns + three bias-gradient columns
 struct TowerWs {
   float *mf_pred, *mlp_pred, *p_saved;     // [N]
   float *xu, *xp;                          // [N,64]  mlp_norm(user row), mlp_norm(item row)
@@ -19,7 +20,7 @@ struct TowerWs {
   float *dxu, *dxp;                        // aliases set by the backward
   // bf16 tensors of the tcgen05 path (NCF_BF16_TC): saved activations and pre-activation gradients
   void *r1b, *y1b, *r2b, *y2b, *r3b, *dz1b, *dz2b, *dz3b;
-  float* wg_partial;                       // per-CTA weight-gradient accumulators of the tcgen05 MLP wgrad kernel
+  float* wg_partial;                       // per-CTA accumulators of the tcgen05 MLP wgrad kernel: [SMs][MLP_WG_PART_COLS][128]
   float* at_partial;                       // same for the fused attention backward
   void* a_img;                             // attention output as bf16 tile image [ceil(N/128)][128 x 64]
   float *st1, *st2, *st3;                  // LayerNorm (mean, rstd) per row of the three MLP layers

@@ -779,7 +779,7 @@ TowerWs carve_tower_ws(void* ws, int64_t N, const ncf_run_cfg& cfg) {
       w.dz1b = c.take<uint16_t>(Np * H1);
       w.dz2b = c.take<uint16_t>(Np * H2);
       w.dz3b = c.take<uint16_t>(Np * H3);
-      w.wg_partial = c.take<float>((int64_t)num_sms() * 448 * 128);
+      w.wg_partial = c.take<float>((int64_t)num_sms() * MLP_WG_PART_COLS * 128);
       w.at_partial = c.take<float>(attn_tc_partial_floats());
     }
     w.emb_bytes = ncf_emb_bwd_workspace_bytes(N);

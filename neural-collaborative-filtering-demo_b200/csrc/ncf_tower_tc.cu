@@ -1263,8 +1263,10 @@ __device__ __forceinline__ void mlp_bwd_layer(uint32_t tmem_dy, float dml, const
       *reinterpret_cast<uint4*>(dztile + off) = pk;
       *reinterpret_cast<uint4*>(dz_img + off) = pk;
     }
-    const float cz = warp_transpose_sum<CW>(dy, lane);
-    if (acc_lane) atomicAdd(s_acc + 2 * C + c0 + lane, cz);
+    if constexpr (C == 64) {      // the 256- and 128-wide layers get their bias gradient from the wgrad kernel's ones-GEMM
+      const float cz = warp_transpose_sum<CW>(dy, lane);
+      if (acc_lane) atomicAdd(s_acc + 2 * C + c0 + lane, cz);
+    }
   }
 }
 
@@ -1428,7 +1430,8 @@ constexpr uint32_t SMW_Z2 = SMW_Z3 + 128 * 64 * 2;     // [128][128]      32 KB
 constexpr uint32_t SMW_Y1 = SMW_Z2 + 128 * 128 * 2;    // [128][256]      64 KB
 constexpr uint32_t SMW_Z1 = SMW_Y1 + 128 * 256 * 2;    // [128][256]      64 KB
 constexpr uint32_t SMW_A = SMW_Z1 + 128 * 256 * 2;     // [128][64]       16 KB
-constexpr uint32_t SMW_TOTAL = SMW_A + 128 * 64 * 2;   // 224 KB
+constexpr uint32_t SMW_ONES = SMW_A + 128 * 64 * 2;    // [16][16] bf16 ones, 512 B: every K step of the bias GEMMs reads it
+constexpr uint32_t SMW_TOTAL = SMW_ONES + 512;         // 224.5 KB
 
 __device__ __forceinline__ void copy_tile_image(uint8_t* dst, const __nv_bfloat16* __restrict__ img, int64_t tile, int bytes,
                                                 int tid, int nthreads) {
@@ -1436,7 +1439,9 @@ __device__ __forceinline__ void copy_tile_image(uint8_t* dst, const __nv_bfloat1
   for (int i = tid; i < bytes / 16; i += nthreads) reinterpret_cast<uint4*>(dst)[i] = __ldg(src + i);
 }
 
-constexpr int WG_PART = 448 * 128;     // accumulator words per CTA (TMEM columns x lanes)
+// accumulator words per CTA: 448 TMEM columns x 128 lanes of weight gradients + column 0 of the three 16-column bias
+// accumulators (NCF_P_MLP0_B rows 0-127, rows 128-255, NCF_P_MLP1_B)
+constexpr int WG_PART = MLP_WG_PART_COLS * 128;
 
 struct MlpWgradArgs {
   const __nv_bfloat16* a_img;                            // MLP input, bf16 tile image
@@ -1463,6 +1468,11 @@ __global__ void __launch_bounds__(TCM_THREADS, 1) mlp_tc_wgrad_kernel(MlpWgradAr
     mbar_fence_init();
   }
   if (warp == 0) tmem_alloc(&tmem_slot, 512);
+  // Bias gradients = column sums of the dz tiles = dz^T . ones: one more N = 16 GEMM per dz operand that is in shared
+  // memory anyway (B = a 16 x 16 block of ones, the same block for every K step), instead of shuffle-transposing
+  // every tile in the backward kernel's epilogue.
+  if (tid < 128) reinterpret_cast<uint32_t*>(smem + SMW_ONES)[tid] = 0x3F803F80u;
+  fence_async_smem();
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
@@ -1492,6 +1502,8 @@ __global__ void __launch_bounds__(TCM_THREADS, 1) mlp_tc_wgrad_kernel(MlpWgradAr
     // ---- MMA issuer ---------------------------------------------------------------------------
     const uint32_t sY2 = smem_addr(smem + SMW_Y2), sZ3 = smem_addr(smem + SMW_Z3), sZ2 = smem_addr(smem + SMW_Z2);
     const uint32_t sY1 = smem_addr(smem + SMW_Y1), sZ1 = smem_addr(smem + SMW_Z1), sA = smem_addr(smem + SMW_A);
+    const uint32_t sOnes = smem_addr(smem + SMW_ONES);
+    constexpr uint32_t idesc_b = make_idesc(128, 16, true, true);
     for (int64_t k = 0; k < my_tiles; ++k) {
       const bool acc = k > 0;
       mbar_wait(&fullA, k & 1);
@@ -1500,12 +1512,17 @@ __global__ void __launch_bounds__(TCM_THREADS, 1) mlp_tc_wgrad_kernel(MlpWgradAr
       issue_gemm(tmem + 0, sY2, 128 * 16, 128, 2 * 128 * 16, sZ3, 64 * 16, 128, 2 * 64 * 16, make_idesc(128, 64, true, true), 8, acc);
       // dW1[n_out 128][k_in 256] += dz2^T . y1
       issue_gemm(tmem + 64, sZ2, 128 * 16, 128, 2 * 128 * 16, sY1, 256 * 16, 128, 2 * 256 * 16, make_idesc(128, 256, true, true), 8, acc);
+      // bias gradient of the 256 -> 128 Linear (NCF_P_MLP1_B)[n_out 128] += dz2^T . 1
+      issue_gemm(tmem + 480, sZ2, 128 * 16, 128, 2 * 128 * 16, sOnes, 16 * 16, 128, 0, idesc_b, 8, acc);
       mma_commit(&emptyA);
       mbar_wait(&fullB, k & 1);
       fence_after_sync();
       // dW0[n_out 256][k_in 64] += dz1^T . a   (two M = 128 halves: +16 MN groups = 2048 B)
       issue_gemm(tmem + 320, sZ1, 256 * 16, 128, 2 * 256 * 16, sA, 64 * 16, 128, 2 * 64 * 16, make_idesc(128, 64, true, true), 8, acc);
       issue_gemm(tmem + 384, sZ1 + 2048, 256 * 16, 128, 2 * 256 * 16, sA, 64 * 16, 128, 2 * 64 * 16, make_idesc(128, 64, true, true), 8, acc);
+      // bias gradient of the 96 -> 256 Linear (NCF_P_MLP0_B)[n_out 256] += dz1^T . 1   (two halves)
+      issue_gemm(tmem + 448, sZ1, 256 * 16, 128, 2 * 256 * 16, sOnes, 16 * 16, 128, 0, idesc_b, 8, acc);
+      issue_gemm(tmem + 464, sZ1 + 2048, 256 * 16, 128, 2 * 256 * 16, sOnes, 16 * 16, 128, 0, idesc_b, 8, acc);
       mma_commit(&emptyB);
     }
     if (my_tiles > 0) {          // all accumulation done before the flush below
@@ -1528,6 +1545,13 @@ __global__ void __launch_bounds__(TCM_THREADS, 1) mlp_tc_wgrad_kernel(MlpWgradAr
 #pragma unroll
       for (int i = 0; i < 32; ++i) part[(int64_t)(c0 + i) * 128 + lane_row] = my_tiles > 0 ? v[i] : 0.f;
     }
+    if (h == 0) {                             // bias accumulators: all 16 columns hold the same sum
+      for (int j = 0; j < 3; ++j) {
+        float v[16];
+        tmem_ld16(tmem + lane_addr + 448 + 16 * j, v);
+        part[(int64_t)(448 + j) * 128 + lane_row] = my_tiles > 0 ? v[0] : 0.f;
+      }
+    }
   }
   fence_before_sync();
   __syncthreads();
@@ -1543,7 +1567,8 @@ __global__ void __launch_bounds__(256) mlp_wgrad_reduce_kernel(const float* __re
   for (int p = 0; p < nparts; ++p) s += partial[(int64_t)p * WG_PART + e];
   const int col = e >> 7, lane = e & 127;
   int64_t off;
-  if (col < 64) off = NCF_OFF(NCF_P_MLP2_W) + (int64_t)col * H2 + lane;                       // dW2^T: lane = k_in
+  if (col >= 448) off = col == 450 ? NCF_OFF(NCF_P_MLP1_B) + lane : NCF_OFF(NCF_P_MLP0_B) + (col - 448) * 128 + lane;
+  else if (col < 64) off = NCF_OFF(NCF_P_MLP2_W) + (int64_t)col * H2 + lane;                  // dW2^T: lane = k_in
   else if (col < 320) off = NCF_OFF(NCF_P_MLP1_W) + (int64_t)lane * H1 + (col - 64);           // dW1: lane = n_out
   else off = NCF_OFF(NCF_P_MLP0_W) + (int64_t)(((col - 320) >> 6) * 128 + lane) * K0 + ((col - 320) & 63);
   dg[off] += s;
