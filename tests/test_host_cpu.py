@@ -90,3 +90,25 @@ def test_metrics_match_reference_fixture():
             assert abs(v - exp[name][k]) < 1e-6, (name, k, v, exp[name][k])
     with pytest.raises(ValueError):
         ncf_b200.calculate_metrics(torch.rand(10), torch.rand(10), [1], 3, 4)
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` runs on the host cores only (the oracle port of the reference step) and prints ONE
+    JSON line with the keys the driver reads; nothing of it may touch CUDA."""
+    import json
+    import subprocess
+    import sys
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(repo, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--ref-batch", "64"], capture_output=True, text=True, timeout=300,
+                         env={**os.environ, "CUDA_VISIBLE_DEVICES": ""})
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "train_samples_per_s" and d["unit"] == "samples/s"
+    assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 1 and d["warmup"] == 0
+    assert d["value"] > 0 and d["ms_per_step"] > 0 and d["vs_baseline"] is None
+    assert d["config"]["workload"].startswith("c2") and "model" not in d["config"]
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
