@@ -610,7 +610,10 @@ def main():
     sweep_bytes = 2 * (users + items) * 1536
     tcp = precision == "bf16"
     kernels = {
-        "K1 gather_ln_gmf_fwd": hbm_piece(k1_ms, k1_bytes),
+        # SURVEY 8d "gather GB/s": every lookup counted (4 rows of 256 B per sample, no de-duplication), next to the
+        # algorithmic figure (the S rows of an interaction share their user rows)
+        "K1 gather_ln_gmf_fwd": hbm_piece(k1_ms, k1_bytes, gather_effective_gbs=4 * N * 256 / k1_ms / 1e6,
+                                          gather_lookups=4 * N),
         "attention forward" + (" (attn_tc_fwd_kernel)" if tcp else " (fp32 kernels)"): tensor_piece(afwd_ms, FLOP_ATTN_FWD, BYTES_ATTN_FWD),
         "MLP forward" + (" (mlp_tc_fwd_kernel)" if tcp else " (fp32 kernels)"): tensor_piece(mfwd_ms, FLOP_MLP_FWD, BYTES_MLP_FWD),
         "MLP backward" + (" (head_bwd + mlp_tc_bwd + mlp_tc_wgrad kernels)" if tcp else " (fp32 kernels)"):
