@@ -5,6 +5,10 @@ tracked summaries under profiles/:
   <tag>_ncu_full.json        per-kernel digest: time, DRAM bytes, pipes, occupancy, top stall reasons
   traffic.json               DRAM bytes per step of the stage bench.py reports as `roofline.kernel`
 usage: python tools/make_profiles.py <tag> <workload> gpurun_out/launches.csv gpurun_out/step.ncu-rep "<command>"
+
+The .ncu-rep may also come from a capture with an explicit --metrics list (the METRICS below; ~1 minute of GPU time
+instead of ~3.5 for --set full): the digest then has no stall reasons - say so in the note of the written JSON
+(profiles/r01_final_ncu_metrics.json was made that way).
 """
 import collections
 import csv
