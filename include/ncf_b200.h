@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define NCF_ABI_VERSION 1
+#define NCF_ABI_VERSION 2
 #if defined(__GNUC__)
 #define NCF_API __attribute__((visibility("default")))
 #else
@@ -63,7 +63,17 @@ typedef struct ncf_tables {
   uint8_t* touched[2];    /* [rows_user], [rows_item] scratch flags, zero between steps */
   int64_t rows_user;
   int64_t rows_item;
+  int32_t* status;        /* optional [NCF_STATUS_WORDS] sticky error words (see ncf_check_ids); device memory or pinned
+                             host memory mapped into the device address space (then the host reads them without a copy) */
 } ncf_tables;
+
+/* Id validation.  nn.EmbeddingBag raises on an id outside [0, rows) (reference architecture.py:286-287 through torchrec);
+ * a kernel cannot raise, so every kernel of this library that indexes a table with a caller-supplied id CLAMPS it into
+ * range (no out-of-bounds access, no cross-table corruption of the sorted-id backward) and the kernels that see the ids
+ * first (K1, ncf_gather_ln, the scoring kernels, ncf_check_ids) store 1 into the status word of the offending kind.  The
+ * words are never cleared by the library: the host side clears them and raises (IndexError in the Python module) at its
+ * next synchronisation point. */
+enum { NCF_STATUS_BAD_USER_ID = 0, NCF_STATUS_BAD_ITEM_ID = 1, NCF_STATUS_BAD_HOUR = 2, NCF_STATUS_WORDS = 4 };
 
 /* Offsets (in floats) of the 30 dense tensors `forward` uses inside ONE flat fp32 buffer
  * (83,909 values padded to 16-byte boundaries).  Names are the reference state_dict keys
@@ -126,6 +136,12 @@ NCF_API int ncf_set_aux_stream(void* stream);
 NCF_API int64_t ncf_dense_numel(void);
 NCF_API int64_t ncf_dense_offset(int32_t dense_id);
 NCF_API int64_t ncf_dense_size(int32_t dense_id);
+
+/* Stand-alone validator (callers that hand ids to entry points without an ncf_tables argument, e.g. the sharded
+ * requester): status[NCF_STATUS_BAD_USER_ID] = 1 if any user id is outside [0, rows_user), likewise item ids / rows_item
+ * and hour (optional) outside [0, 24).  item_ids may be NULL. */
+NCF_API int ncf_check_ids(const int64_t* user_ids, const int64_t* item_ids, int64_t N, int64_t rows_user, int64_t rows_item,
+                  const int64_t* hour, int32_t* status, void* stream);
 
 /* ---- forward ---------------------------------------------------------------------------
  * AdvancedNCF.forward (architecture.py:258-381) and forward_simple (:409-485).

@@ -38,7 +38,32 @@ class NcfError(RuntimeError):
 
 class Tables(C.Structure):
     _fields_ = [("w", C.c_void_p * 4), ("m", C.c_void_p * 4), ("v", C.c_void_p * 4), ("g", C.c_void_p * 4),
-                ("touched", C.c_void_p * 2), ("rows_user", C.c_int64), ("rows_item", C.c_int64)]
+                ("touched", C.c_void_p * 2), ("rows_user", C.c_int64), ("rows_item", C.c_int64), ("status", C.c_void_p)]
+
+
+STATUS_WORDS = 4
+STATUS_NAMES = ("user id outside [0, num_users)", "product id outside [0, num_products)", "hour outside [0, 24)")
+
+
+class StatusWord:
+    """The sticky error words of include/ncf_b200.h ("Id validation") in PINNED HOST memory: under unified addressing the
+    kernels store into them through the same pointer, so the host reads them without a copy.  `raise_if_set()` is called
+    where the host has synchronised anyway (after reading a loss / a result) and at the start of the next call."""
+
+    def __init__(self):
+        import torch
+        self.t = torch.zeros(STATUS_WORDS, dtype=torch.int32).pin_memory()
+        self.np = self.t.numpy()
+
+    def ptr(self):
+        return self.t.data_ptr()
+
+    def raise_if_set(self, what=""):
+        if self.np.any():
+            bad = [STATUS_NAMES[k] for k in range(len(STATUS_NAMES)) if self.np[k]]
+            self.np[:] = 0
+            raise IndexError(f"{what or 'libncf_b200'}: " + "; ".join(bad) +
+                             " (nn.EmbeddingBag / nn.Embedding raise on such an index; the kernels clamped it)")
 
 
 class RunCfg(C.Structure):
@@ -64,6 +89,7 @@ _SIGS = {
     "ncf_workspace_bytes": (_I64, [_I64, C.POINTER(RunCfg)]),
     "ncf_forward": (C.c_int, [C.POINTER(RunCfg), C.POINTER(Tables), _P, _P, _P, _I64, _P, _P, _P, _P, _P, _I64, _P]),
     "ncf_set_aux_stream": (C.c_int, [_P]),
+    "ncf_check_ids": (C.c_int, [_P, _P, _I64, _I64, _I64, _P, _P, _P]),
     "ncf_attn_fwd": (C.c_int, [C.POINTER(RunCfg), _P, _I64, _P, _I64, _P]),
     "ncf_mlp_fwd": (C.c_int, [C.POINTER(RunCfg), _P, _I64, _P, _P, _I64, _P]),
     "ncf_mlp_bwd": (C.c_int, [C.POINTER(RunCfg), _P, _P, _I64, _P, _P, _I64, _P]),
@@ -128,7 +154,7 @@ def load():
                 fn = getattr(lib, name)      # AttributeError here = header/library mismatch
                 fn.restype = res
                 fn.argtypes = args
-            if lib.ncf_version() != 1:
+            if lib.ncf_version() != 2:
                 raise NcfError("libncf_b200.so ABI version mismatch")
             _lib = lib
     return _lib

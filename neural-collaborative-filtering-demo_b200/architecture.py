@@ -82,6 +82,9 @@ class TemporalEncoding(nn.Module):
         lib = _lib.load()
         shape = hour.shape
         ids = [t.reshape(-1).to(device=w.device, dtype=torch.long).contiguous() for t in (hour, day, month, days_since)]
+        for t, hi, name in zip(ids[:3], (24, 7, 12), ("hour", "day", "month")):     # nn.Embedding raises (architecture.py:88-90)
+            if t.numel() and (int(t.min()) < 0 or int(t.max()) >= hi):
+                raise IndexError(f"TemporalEncoding: {name} index out of range [0, {hi})")
         n = ids[0].numel()
         out = torch.empty(n, self.embed_dim, device=w.device, dtype=torch.float32)
         _lib.check(lib.ncf_temporal_fwd(_lib.ptr(w), _lib.ptr(self.day_embed.weight), _lib.ptr(self.month_embed.weight),
@@ -247,6 +250,7 @@ class AdvancedNCF(nn.Module):
         self._table_hparams = None
         self._table_state = None
         self._table_step = 0
+        self._status: Optional[_lib.StatusWord] = None    # id-validation words the kernels set (pinned host memory)
 
     # ------------------------------------------------------------------------------------------
     # plumbing
@@ -295,6 +299,15 @@ class AdvancedNCF(nn.Module):
         for t in self._table_params():
             if t.device != dev or not t.is_contiguous() or t.dtype != torch.float32:
                 raise _lib.NcfError("embedding tables must be contiguous fp32 on the model's device")
+        if self._status is None:
+            self._status = _lib.StatusWord()
+
+    def check_status(self, what: str = "AdvancedNCF"):
+        """Raise IndexError if a kernel saw an id (or hour) outside its table since the last check - what
+        nn.EmbeddingBag does synchronously on the CPU (reference architecture.py:286-287).  Reads pinned host memory:
+        no device synchronisation; everything launched before the caller's last synchronisation is covered."""
+        if self._status is not None:
+            self._status.raise_if_set(what)
 
     def _scratch(self, nbytes, dev):
         if self._scratch_buf is None or self._scratch_buf.numel() < nbytes or self._scratch_buf.device != dev:
@@ -327,6 +340,7 @@ class AdvancedNCF(nn.Module):
             t.touched[1] = self._table_state["touched"][1].data_ptr()
         t.rows_user = self.num_users
         t.rows_item = self.num_products
+        t.status = self._status.ptr() if self._status is not None else None
         return t
 
     def _backward_cfg(self):
@@ -423,6 +437,7 @@ class AdvancedNCF(nn.Module):
         if not user_ids.is_cuda:
             raise _lib.NcfError("AdvancedNCF.forward needs CUDA tensors (no CPU fallback); call features.to('cuda')")
         self._ensure_flat()
+        self.check_status("AdvancedNCF.forward (an earlier call)")
         params = self._dense_params() + self._table_params()
         out = _NCFFunction.apply(self, user_ids, item_ids, S, self.training, *params)
         outputs = out.view(total, 1)
@@ -438,6 +453,7 @@ class AdvancedNCF(nn.Module):
         if not user_ids.is_cuda:
             raise _lib.NcfError("AdvancedNCF.forward_simple needs CUDA tensors (no CPU fallback)")
         self._ensure_flat()
+        self.check_status("AdvancedNCF.forward_simple (an earlier call)")
         lib = _lib.load()
         dev = user_ids.device
         u = user_ids.reshape(-1).long().contiguous()

@@ -28,12 +28,23 @@ extern "C" int64_t ncf_launch_count(void) { return (int64_t)g_launches; }
 
 // optional auxiliary stream for work that is independent of the main stream's kernels (ncf_train_step forks the
 // id sort of the embedding backward onto it); NULL = everything on the stream argument (default)
+// The stream and the events that order it against the caller's stream are kept PER DEVICE (the current device of the calling
+// thread), created lazily on that device: engines on different GPUs of one process do not share them.
 namespace ncf {
-cudaStream_t g_aux_stream = nullptr;
+static AuxCtx g_aux[NCF_MAX_DEVICES];
+AuxCtx* aux_ctx() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= NCF_MAX_DEVICES) dev = 0;
+  return &g_aux[dev];
 }
-static cudaEvent_t g_ev_fork = nullptr, g_ev_sorted = nullptr;
+int aux_events(AuxCtx* a) {
+  for (int i = 0; i < 4; ++i)
+    if (!a->ev[i]) NCF_CUDA(cudaEventCreateWithFlags(&a->ev[i], cudaEventDisableTiming));
+  return NCF_OK;
+}
+}
 extern "C" int ncf_set_aux_stream(void* stream) {
-  g_aux_stream = (cudaStream_t)stream;
+  aux_ctx()->stream = (cudaStream_t)stream;
   return NCF_OK;
 }
 extern "C" int64_t ncf_dense_numel(void) { return kLayout.total; }
@@ -108,7 +119,7 @@ static int backward_impl(const ncf_run_cfg* cfg, const ncf_adam_cfg* adam, const
   if (adam->emb_mode != NCF_EMB_NONE) {
     if (sorted) NCF_CUDA(cudaStreamWaitEvent(st, sorted, 0));
     NCF_TRY(emb_bwd_both(adam, T, dense, dense_grad, user_ids, item_ids, N, w.d_mf, w.dxu, w.dxp, w.y_pmf, w.y_umf, w.emb, w.emb_bytes, st,
-                         sorted != nullptr, preswept, sorted ? g_aux_stream : nullptr));
+                         sorted != nullptr, preswept, sorted ? aux_ctx()->stream : nullptr));
     if (adam->emb_mode == NCF_EMB_ADAM_DENSE_EQUIV && !preswept) NCF_TRY(ncf_emb_adam_sweep(adam, T, stream));
   }
   return NCF_OK;
@@ -182,12 +193,14 @@ extern "C" int ncf_train_step(const ncf_run_cfg* cfg, const ncf_adam_cfg* adam, 
   NCF_REQUIRE(T && user_ids && item_ids && workspace, "train_step: null argument");
   cudaEvent_t sorted = nullptr;
   bool preswept = false;
+  AuxCtx* aux = aux_ctx();
+  cudaStream_t g_aux_stream = aux->stream;
   const bool fork = g_aux_stream && adam->emb_mode != NCF_EMB_NONE && adam->emb_mode != NCF_EMB_MATERIALIZE;
+  cudaEvent_t g_ev_fork = nullptr, g_ev_sorted = nullptr;
   if (fork) {
-    if (!g_ev_fork) {
-      NCF_CUDA(cudaEventCreateWithFlags(&g_ev_fork, cudaEventDisableTiming));
-      NCF_CUDA(cudaEventCreateWithFlags(&g_ev_sorted, cudaEventDisableTiming));
-    }
+    NCF_TRY(aux_events(aux));
+    g_ev_fork = aux->ev[0];
+    g_ev_sorted = aux->ev[1];
     NCF_CUDA(cudaEventRecord(g_ev_fork, st));                  // the previous step's K6 has released the sort buffers
   }
   NCF_CUDA(cudaMemsetAsync(dense_grad, 0, sizeof(float) * kLayout.total, st));                       // optimizer.zero_grad()

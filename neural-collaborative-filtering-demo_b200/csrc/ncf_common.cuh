@@ -115,6 +115,12 @@ __device__ __forceinline__ float half_warp_sum(float v) {
   for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
+// caller-supplied table index -> always inside [0, rows): see "Id validation" in ncf_b200.h
+__device__ __forceinline__ int64_t clamp_id(int64_t id, int64_t rows) { return id < 0 ? 0 : (id >= rows ? rows - 1 : id); }
+__device__ __forceinline__ bool bad_id(int64_t id, int64_t rows) { return (unsigned long long)id >= (unsigned long long)rows; }
+__device__ __forceinline__ void flag_status(int32_t* status, int word) {
+  if (status) *reinterpret_cast<volatile int32_t*>(status + word) = 1;      // plain store: every writer stores 1
+}
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }

@@ -8,10 +8,9 @@
 
 #include <stdlib.h>
 
-#include "ncf_common.cuh"
+#include "ncf_tower.cuh"
 
 namespace ncf {
-extern cudaStream_t g_aux_stream;      // ncf_set_aux_stream (ncf_abi.cu); null = none
 
 // ---- mbarrier / bulk-copy PTX ---------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -65,7 +64,8 @@ __global__ void __launch_bounds__(K1_THREADS) gather_ln_gmf_fwd_kernel(
     const float* __restrict__ t_pmlp, const float* __restrict__ dense, const int64_t* __restrict__ user_ids,
     const int64_t* __restrict__ item_ids, int64_t N, const int64_t* __restrict__ hour,
     const float* __restrict__ tmod, float* __restrict__ mf_pred, float* __restrict__ xu, float* __restrict__ xp,
-    float* __restrict__ y_item_mf, float* __restrict__ y_user_mf, bool bf16_rows) {
+    float* __restrict__ y_item_mf, float* __restrict__ y_user_mf, bool bf16_rows, int64_t rows_user, int64_t rows_item,
+    int32_t* __restrict__ status) {
   __shared__ __align__(16) int64_t s_ids[2][2][K1_TILE];
   __shared__ __align__(8) uint64_t s_bar[2];
 
@@ -84,6 +84,8 @@ __global__ void __launch_bounds__(K1_THREADS) gather_ln_gmf_fwd_kernel(
   // per-lane constants: this half's tables and LayerNorm affine slices
   const float* tab_mf = half ? t_pmf : t_umf;
   const float* tab_mlp = half ? t_pmlp : t_umlp;
+  const int64_t tab_rows = half ? rows_item : rows_user;
+  bool bad = false, bad_hour = false;      // ids outside the tables are clamped and reported (ncf_b200.h "Id validation")
   const float4 g_mf = ldg4(dense + NCF_OFF(NCF_P_MF_NORM_W) + 4 * l16);
   const float4 b_mf = ldg4(dense + NCF_OFF(NCF_P_MF_NORM_B) + 4 * l16);
   const float4 g_ml = ldg4(dense + NCF_OFF(NCF_P_MLP_NORM_W) + 4 * l16);
@@ -130,7 +132,9 @@ __global__ void __launch_bounds__(K1_THREADS) gather_ln_gmf_fwd_kernel(
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int r = min(r0 + j, rows - 1);
-        id[j] = s_ids[buf][half][r];
+        const int64_t raw = s_ids[buf][half][r];
+        bad |= bad_id(raw, tab_rows);
+        id[j] = clamp_id(raw, tab_rows);
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -144,7 +148,9 @@ __global__ void __launch_bounds__(K1_THREADS) gather_ln_gmf_fwd_kernel(
         float4 y_mf = affine(ln_normalise(a[j], rs), g_mf, b_mf);
         float4 y_ml = affine(ln_normalise(b[j], rs), g_ml, b_ml);
         if (HOUR) {  // forward_simple hour path: item rows scaled by 1 + 0.3 * proj(hour_embed[h])
-          const int64_t h = hour[n0 + min(r, rows - 1)];
+          const int64_t hraw = hour[n0 + min(r, rows - 1)];
+          bad_hour |= bad_id(hraw, 24);
+          const int64_t h = clamp_id(hraw, 24);
           const float4 t = ldg4(tmod + h * D + 4 * l16);
           if (half) {
             y_mf = f4_mul(y_mf, t);
@@ -165,13 +171,16 @@ __global__ void __launch_bounds__(K1_THREADS) gather_ln_gmf_fwd_kernel(
     }
     __syncthreads();  // everyone is done with s_ids[buf] before it is refilled two tiles later
   }
+  if (bad) flag_status(status, half ? NCF_STATUS_BAD_ITEM_ID : NCF_STATUS_BAD_USER_ID);
+  if (HOUR && bad_hour) flag_status(status, NCF_STATUS_BAD_HOUR);
 }
 
 // LN'd rows of one side (get_user_embeddings / get_product_embeddings, architecture.py:383-407)
 __global__ void __launch_bounds__(256) gather_ln_kernel(const float* __restrict__ t_mf, const float* __restrict__ t_mlp,
                                                          const float* __restrict__ dense,
                                                          const int64_t* __restrict__ ids, int64_t n,
-                                                         float* __restrict__ mf_out, float* __restrict__ mlp_out) {
+                                                         float* __restrict__ mf_out, float* __restrict__ mlp_out,
+                                                         int64_t rows, int32_t* __restrict__ status, int status_word) {
   const int lane = threadIdx.x & 31, half = lane >> 4, l16 = lane & 15;
   const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
@@ -180,7 +189,9 @@ __global__ void __launch_bounds__(256) gather_ln_kernel(const float* __restrict_
   const float4 g = ldg4(dense + (half ? NCF_OFF(NCF_P_MLP_NORM_W) : NCF_OFF(NCF_P_MF_NORM_W)) + 4 * l16);
   const float4 b = ldg4(dense + (half ? NCF_OFF(NCF_P_MLP_NORM_B) : NCF_OFF(NCF_P_MF_NORM_B)) + 4 * l16);
   for (int64_t r = warp; r < n; r += nwarps) {
-    const int64_t id = ids[r];
+    const int64_t raw = ids[r];
+    if (bad_id(raw, rows)) flag_status(status, status_word);
+    const int64_t id = clamp_id(raw, rows);
     float rs;
     const float4 y = affine(ln_normalise(ldg4(tab + id * D + 4 * l16), rs), g, b);
     if (out) st4(out + r * D + 4 * l16, y);
@@ -257,6 +268,7 @@ struct EmbBwdArgs {
   float* out_rows;                // phase 2 output mode: [n_unique,128] summed upstream row per unique id, no update
   const int32_t* out_slot;        // [N] unique-id index of every sorted position
   const int64_t* other_ids;       // other side's ids, original sample order
+  int64_t other_nrows;            // rows of the other side's table (ids are clamped into it)
   const uint32_t* sorted_ids;     // this side's ids, sorted
   const int32_t* perm;            // sample row of each sorted position
   const float* d_mf_pred;         // [N]
@@ -393,7 +405,7 @@ __global__ void __launch_bounds__(EB_THREADS, 3) emb_bwd_phase1_kernel(EmbBwdArg
         my_other = A.other_sorted[p0 + lane];
         my_dmf = A.dmf_sorted[p0 + lane];
       } else {
-        if (!A.other_y) my_other = A.other_ids[my_row];
+        if (!A.other_y) my_other = clamp_id(A.other_ids[my_row], A.other_nrows);
         my_dmf = A.d_mf_pred[my_row];
       }
     }
@@ -578,11 +590,11 @@ __global__ void __launch_bounds__(EB_THREADS, 3) emb_bwd_phase2_kernel(EmbBwdArg
   block_flush(s_red, dbeta, dg ? dg + NCF_OFF(NCF_P_MLP_NORM_B) : nullptr, lane, warp, nwarps, half == 1, l16);
 }
 
-__global__ void ids_to_keys_kernel(const int64_t* __restrict__ ids, int64_t n, uint32_t* __restrict__ keys,
+__global__ void ids_to_keys_kernel(const int64_t* __restrict__ ids, int64_t n, int64_t rows, uint32_t* __restrict__ keys,
                                    int32_t* __restrict__ vals) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
-    keys[i] = (uint32_t)ids[i];
+    keys[i] = (uint32_t)clamp_id(ids[i], rows);
     vals[i] = (int32_t)i;
   }
 }
@@ -617,11 +629,24 @@ __global__ void __launch_bounds__(256) emb_adam_sweep_kernel(float* __restrict__
 
 // flags of the rows a batch will update, straight from its ids (benign write races: every writer stores 1)
 __global__ void mark_touched_kernel(const int64_t* __restrict__ user_ids, const int64_t* __restrict__ item_ids, int64_t n,
-                                    uint8_t* __restrict__ touched_user, uint8_t* __restrict__ touched_item) {
+                                    uint8_t* __restrict__ touched_user, uint8_t* __restrict__ touched_item, int64_t rows_user,
+                                    int64_t rows_item) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
-    touched_user[user_ids[i]] = 1;
-    touched_item[item_ids[i]] = 1;
+    touched_user[clamp_id(user_ids[i], rows_user)] = 1;
+    touched_item[clamp_id(item_ids[i], rows_item)] = 1;
+  }
+}
+
+// ncf_check_ids: sticky flags for ids / hours outside their range
+__global__ void check_ids_kernel(const int64_t* __restrict__ user_ids, const int64_t* __restrict__ item_ids, int64_t n,
+                                 int64_t rows_user, int64_t rows_item, const int64_t* __restrict__ hour,
+                                 int32_t* __restrict__ status) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    if (user_ids && bad_id(user_ids[i], rows_user)) flag_status(status, NCF_STATUS_BAD_USER_ID);
+    if (item_ids && bad_id(item_ids[i], rows_item)) flag_status(status, NCF_STATUS_BAD_ITEM_ID);
+    if (hour && bad_id(hour[i], 24)) flag_status(status, NCF_STATUS_BAD_HOUR);
   }
 }
 
@@ -649,9 +674,10 @@ __global__ void temporal_fwd_kernel(const float* __restrict__ he, const float* _
   if (r >= n) return;
   int64_t ds = days_since[r] % 365;
   if (ds < 0) ds += 365;  // python modulo
-  float4 a = ldg4(he + hour[r] * TDIM + c);
-  a = f4_add(a, ldg4(de + day[r] * TDIM + c));
-  a = f4_add(a, ldg4(me + month[r] * TDIM + c));
+  // nn.Embedding would raise on an index outside its table; here the index is clamped (the Python wrapper validates)
+  float4 a = ldg4(he + clamp_id(hour[r], 24) * TDIM + c);
+  a = f4_add(a, ldg4(de + clamp_id(day[r], 7) * TDIM + c));
+  a = f4_add(a, ldg4(me + clamp_id(month[r], 12) * TDIM + c));
   a = f4_add(a, ldg4(pe + ds * TDIM + c));
   st4(out + r * TDIM + c, a);
 }
@@ -701,10 +727,12 @@ int gather_ln_gmf_fwd_rows(bool bf16_rows, const ncf_tables* T, const float* den
   cudaStream_t st = (cudaStream_t)stream;
   if (hour)
     gather_ln_gmf_fwd_kernel<true><<<grid, K1_THREADS, 0, st>>>(T->w[0], T->w[1], T->w[2], T->w[3], dense, user_ids,
-                                                                item_ids, N, hour, tmod, mf_pred, xu, xp, y_item_mf, y_user_mf, bf16_rows);
+                                                                item_ids, N, hour, tmod, mf_pred, xu, xp, y_item_mf, y_user_mf, bf16_rows,
+                                                                T->rows_user, T->rows_item, T->status);
   else
     gather_ln_gmf_fwd_kernel<false><<<grid, K1_THREADS, 0, st>>>(T->w[0], T->w[1], T->w[2], T->w[3], dense, user_ids,
-                                                                 item_ids, N, nullptr, nullptr, mf_pred, xu, xp, y_item_mf, y_user_mf, bf16_rows);
+                                                                 item_ids, N, nullptr, nullptr, mf_pred, xu, xp, y_item_mf, y_user_mf, bf16_rows,
+                                                                 T->rows_user, T->rows_item, T->status);
   NCF_LAUNCH_CHECK();
   return NCF_OK;
 }
@@ -730,7 +758,9 @@ extern "C" int ncf_gather_ln(const ncf_tables* T, const float* dense, int32_t si
   NCF_REQUIRE(T && dense && ids && (side == 0 || side == 1), "gather_ln: bad argument");
   if (n == 0) return NCF_OK;
   const int grid = (int)std::min<int64_t>((n + 7) / 8, (int64_t)num_sms() * 8);
-  gather_ln_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(T->w[side], T->w[2 + side], dense, ids, n, mf_out, mlp_out);
+  gather_ln_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(T->w[side], T->w[2 + side], dense, ids, n, mf_out, mlp_out,
+                                                            side ? T->rows_item : T->rows_user, T->status,
+                                                            side ? NCF_STATUS_BAD_ITEM_ID : NCF_STATUS_BAD_USER_ID);
   NCF_LAUNCH_CHECK();
   return NCF_OK;
 }
@@ -796,7 +826,7 @@ static int run_emb_bwd(const ncf_adam_cfg* adam, const ncf_tables* T, const floa
   else
     NCF_REQUIRE(T->m[side] && T->v[side] && T->m[2 + side] && T->v[2 + side], "emb_bwd: Adam mode needs m and v");
   cudaStream_t st = (cudaStream_t)stream;
-  ids_to_keys_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(ids, N, w.keys_in, w.vals_in);
+  ids_to_keys_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(ids, N, rows, w.keys_in, w.vals_in);
   NCF_LAUNCH_CHECK();
   size_t tmp = w.cub_bytes;
   NCF_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tmp, w.keys_in, w.keys_out, w.vals_in, w.vals_out, (int)N, 0,
@@ -821,6 +851,7 @@ static int run_emb_bwd(const ncf_adam_cfg* adam, const ncf_tables* T, const floa
   A.out_slot = nullptr;
   A.upstream = upstream;
   A.other_ids = other_ids;
+  A.other_nrows = side ? T->rows_user : T->rows_item;
   A.sorted_ids = w.keys_out;
   A.perm = w.vals_out;
   A.d_mf_pred = d_mf_pred;
@@ -849,11 +880,13 @@ static int run_emb_bwd(const ncf_adam_cfg* adam, const ncf_tables* T, const floa
 }
 
 __global__ void ids_to_keys2_kernel(const int64_t* __restrict__ user_ids, const int64_t* __restrict__ item_ids, int64_t n,
-                                    uint32_t item_off, uint32_t* __restrict__ keys, int32_t* __restrict__ vals) {
+                                    uint32_t item_off, int64_t rows_item, uint32_t* __restrict__ keys,
+                                    int32_t* __restrict__ vals) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
-    keys[i] = (uint32_t)user_ids[i];
-    keys[n + i] = (uint32_t)item_ids[i] + item_off;
+    // clamped: a bad user id must not land in the item region of the combined key space (and vice versa)
+    keys[i] = (uint32_t)clamp_id(user_ids[i], (int64_t)item_off);
+    keys[n + i] = (uint32_t)clamp_id(item_ids[i], rows_item) + item_off;
     vals[i] = (int32_t)i;
     vals[n + i] = (int32_t)i;
   }
@@ -887,7 +920,7 @@ int emb_sort_both(const ncf_tables* T, const int64_t* user_ids, const int64_t* i
     set_error("emb_bwd: workspace %lld < %lld", (long long)workspace_bytes, (long long)w.total);
     return NCF_ERR_WORKSPACE;
   }
-  ids_to_keys2_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(user_ids, item_ids, N, (uint32_t)T->rows_user, w.keys_in, w.vals_in);
+  ids_to_keys2_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(user_ids, item_ids, N, (uint32_t)T->rows_user, T->rows_item, w.keys_in, w.vals_in);
   NCF_LAUNCH_CHECK();
   size_t tmp = w.cub_bytes;
   NCF_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tmp, w.keys_in, w.keys_out, w.vals_in, w.vals_out, (int)(2 * N), 0,
@@ -927,14 +960,14 @@ int emb_bwd_both(const ncf_adam_cfg* adam, const ncf_tables* T, const float* den
   // With the forward's saved rows (the lean phase 1) the two sides share nothing but the read-only inputs and the
   // atomically flushed dense gradients: given a side stream, the item side runs there next to the user side, each
   // with its own segment-sum buffer.  Phase 2 is latency-bound (long runs of popular ids), so the overlap pays.
-  static cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   static const bool two_ok = !(getenv("NCF_K6_TWO_STREAMS") && getenv("NCF_K6_TWO_STREAMS")[0] == '0');   // A/B switch
   const bool two_streams = two_ok && side_stream && side_stream != st && lean;
   if (two_streams) {
-    if (!ev_fork) {
-      NCF_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
-      NCF_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
-    }
+    AuxCtx* aux = aux_ctx();
+    NCF_TRY(aux_events(aux));
+    ev_fork = aux->ev[2];
+    ev_join = aux->ev[3];
     NCF_CUDA(cudaEventRecord(ev_fork, st));
     NCF_CUDA(cudaStreamWaitEvent(side_stream, ev_fork, 0));
   }
@@ -960,6 +993,7 @@ int emb_bwd_both(const ncf_adam_cfg* adam, const ncf_tables* T, const float* den
     A.out_slot = nullptr;
     A.upstream = nullptr;
     A.other_ids = side ? user_ids : item_ids;
+    A.other_nrows = side ? T->rows_user : T->rows_item;
     A.sorted_ids = w.keys_out + (side ? N : 0);
     A.perm = w.vals_out + (side ? N : 0);
     A.d_mf_pred = d_mf_pred;
@@ -1000,7 +1034,7 @@ extern "C" int ncf_emb_bwd_adam_both(const ncf_adam_cfg* adam, const ncf_tables*
   NCF_REQUIRE(adam && T && dense && user_ids && item_ids && d_mf_pred && d_xu && d_xp && y_item_mf && workspace,
               "emb_bwd_adam_both: null argument");
   return emb_bwd_both(adam, T, dense, dense_grad, user_ids, item_ids, N, d_mf_pred, d_xu, d_xp, y_item_mf, y_user_mf,
-                      workspace, workspace_bytes, (cudaStream_t)stream, false, false, ncf::g_aux_stream);
+                      workspace, workspace_bytes, (cudaStream_t)stream, false, false, ncf::aux_ctx()->stream);
 }
 
 extern "C" int ncf_emb_bwd_adam(const ncf_adam_cfg* adam, const ncf_tables* T, const float* dense, float* dense_grad,
@@ -1085,7 +1119,7 @@ int shard_route(const int64_t* user_ids, const int64_t* item_ids, int64_t N, int
     set_error("shard_route: workspace %lld < %lld", (long long)route_ws_bytes, (long long)w.total);
     return NCF_ERR_WORKSPACE;
   }
-  ids_to_keys2_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(user_ids, item_ids, N, (uint32_t)rows_user, w.keys_in, w.vals_in);
+  ids_to_keys2_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(user_ids, item_ids, N, (uint32_t)rows_user, rows_item, w.keys_in, w.vals_in);
   NCF_LAUNCH_CHECK();
   size_t tmp = w.cub_bytes;
   NCF_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tmp, w.keys_in, w.keys_out, w.vals_in, w.vals_out, (int)(2 * N), 0,
@@ -1187,7 +1221,8 @@ int emb_sweep_early(const ncf_adam_cfg* adam, const ncf_tables* T, const int64_t
                     cudaStream_t st) {
   NCF_REQUIRE(T->touched[0] && T->touched[1], "dense-equivalent mode needs tables->touched");
   if (N > 0) {
-    mark_touched_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(user_ids, item_ids, N, T->touched[0], T->touched[1]);
+    mark_touched_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(user_ids, item_ids, N, T->touched[0], T->touched[1], T->rows_user,
+                                                                     T->rows_item);
     NCF_LAUNCH_CHECK();
   }
   return launch_sweep(adam, T, true, st);
@@ -1204,6 +1239,16 @@ extern "C" int ncf_dense_adam(float* w, const float* g, float* m, float* v, int6
   NCF_REQUIRE(w && g && m && v && adam && n >= 0, "dense_adam: bad argument");
   if (n == 0) return NCF_OK;
   dense_adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(w, g, m, v, n, adam_scalars(*adam));
+  NCF_LAUNCH_CHECK();
+  return NCF_OK;
+}
+
+extern "C" int ncf_check_ids(const int64_t* user_ids, const int64_t* item_ids, int64_t N, int64_t rows_user, int64_t rows_item,
+                             const int64_t* hour, int32_t* status, void* stream) {
+  NCF_REQUIRE(status && N >= 0 && (user_ids || item_ids || hour), "check_ids: bad argument");
+  if (N == 0) return NCF_OK;
+  check_ids_kernel<<<(unsigned)((N + 255) / 256), 256, 0, (cudaStream_t)stream>>>(user_ids, item_ids, N, rows_user, rows_item,
+                                                                                  hour, status);
   NCF_LAUNCH_CHECK();
   return NCF_OK;
 }

@@ -97,7 +97,8 @@ __global__ void __launch_bounds__(TK_THREADS, 1) score_topk_kernel(const float* 
                                                                    const float* __restrict__ p_hat, const float* __restrict__ g,
                                                                    const int64_t* __restrict__ user_ids, int64_t n_users,
                                                                    int64_t I, int nsplit,
-                                                                   unsigned long long* __restrict__ part /*[n_users][nsplit][KMAX]*/) {
+                                                                   unsigned long long* __restrict__ part /*[n_users][nsplit][KMAX]*/,
+                                                                   int64_t rows_user, int32_t* __restrict__ status) {
   extern __shared__ __align__(16) uint8_t smem[];
   float* s_u = reinterpret_cast<float*>(smem + TKS_U);
   float* s_p = reinterpret_cast<float*>(smem + TKS_P);
@@ -115,7 +116,9 @@ __global__ void __launch_bounds__(TK_THREADS, 1) score_topk_kernel(const float* 
   for (int uu = warp; uu < TK_UT; uu += TK_THREADS / 32) {
     float x0 = 0.f, x1 = 0.f;
     if (uu < nu) {
-      const float* row = t_umf + user_ids[u0 + uu] * D;
+      const int64_t uid = user_ids[u0 + uu];
+      if (bad_id(uid, rows_user)) flag_status(status, NCF_STATUS_BAD_USER_ID);
+      const float* row = t_umf + clamp_id(uid, rows_user) * D;
       x0 = row[lane];
       x1 = row[lane + 32];
     }
@@ -254,7 +257,8 @@ __global__ void __launch_bounds__(TK_THREADS) score_topk_small_kernel(const floa
                                                                 const float* __restrict__ p_hat, const float* __restrict__ g,
                                                                 const int64_t* __restrict__ user_ids, int64_t n_users,
                                                                 int64_t I, int nsplit,
-                                                                unsigned long long* __restrict__ part /*[n_users][nsplit][KMAX]*/) {
+                                                                unsigned long long* __restrict__ part /*[n_users][nsplit][KMAX]*/,
+                                                                int64_t rows_user, int32_t* __restrict__ status) {
   __shared__ __align__(16) float s_u[TKS_UT][D];
   __shared__ unsigned long long s_buf[TKS_UT][TK_BUF];
   __shared__ int s_cnt[TKS_UT];
@@ -268,7 +272,11 @@ __global__ void __launch_bounds__(TK_THREADS) score_topk_small_kernel(const floa
     const int uu = threadIdx.x >> 6, c = threadIdx.x & 63;
     __shared__ float s_tmp[TKS_UT][D];
     float x = 0.f;
-    if (uu < nu) x = t_umf[user_ids[u0 + uu] * D + c];
+    if (uu < nu) {
+      const int64_t uid = user_ids[u0 + uu];
+      if (bad_id(uid, rows_user)) flag_status(status, NCF_STATUS_BAD_USER_ID);
+      x = t_umf[clamp_id(uid, rows_user) * D + c];
+    }
     s_tmp[uu][c] = x;
     __syncthreads();
     float mean = 0.f;
@@ -537,7 +545,7 @@ extern "C" int ncf_score_topk(const ncf_tables* T, const float* dense, const flo
     const int64_t tiles_s = (n_users + TKS_UT - 1) / TKS_UT;
     NCF_REQUIRE(tiles_s < ((int64_t)1 << 31), "score_topk: too many users in one call");
     dim3 grid_s((unsigned)tiles_s, nsplit);
-    score_topk_small_kernel<<<grid_s, TK_THREADS, 0, st>>>(T->w[0], dense, p_hat, g, user_ids, n_users, I, nsplit, part);
+    score_topk_small_kernel<<<grid_s, TK_THREADS, 0, st>>>(T->w[0], dense, p_hat, g, user_ids, n_users, I, nsplit, part, T->rows_user, T->status);
     NCF_LAUNCH_CHECK();
     topk_merge_kernel<<<(unsigned)n_users, 256, 0, st>>>(part, nsplit, k, topk_idx, topk_score);
     NCF_LAUNCH_CHECK();
@@ -551,7 +559,7 @@ extern "C" int ncf_score_topk(const ncf_tables* T, const float* dense, const flo
     NCF_CUDA(cudaFuncSetAttribute(score_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TKS_TOTAL));
     configured = true;
   }
-  score_topk_kernel<<<grid, TK_THREADS, TKS_TOTAL, st>>>(T->w[0], dense, p_hat, g, user_ids, n_users, I, nsplit, part);
+  score_topk_kernel<<<grid, TK_THREADS, TKS_TOTAL, st>>>(T->w[0], dense, p_hat, g, user_ids, n_users, I, nsplit, part, T->rows_user, T->status);
   NCF_LAUNCH_CHECK();
   topk_merge_kernel<<<(unsigned)n_users, 256, 0, st>>>(part, nsplit, k, topk_idx, topk_score);
   NCF_LAUNCH_CHECK();

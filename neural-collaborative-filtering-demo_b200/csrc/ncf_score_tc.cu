@@ -103,6 +103,8 @@ struct ScoreTcArgs {
   const uint8_t* img;      // item tile images
   const int64_t* user_ids;
   int64_t n_users, I;
+  int64_t rows_user;
+  int32_t* status;
   int nsplit;
   unsigned long long* cand;   // [gridDim.x * gridDim.y][128][512]
   unsigned long long* part;   // [n_users][nsplit][128]
@@ -143,7 +145,9 @@ __global__ void __launch_bounds__(SC_THREADS, 1) score_tc_kernel(ScoreTcArgs A) 
   for (int uu = warp; uu < SC_UT; uu += SC_THREADS / 32) {
     float x0 = 0.f, x1 = 0.f;
     if (uu < nu) {
-      const float* r = A.t_umf + A.user_ids[u0 + uu] * D;
+      const int64_t uid = A.user_ids[u0 + uu];
+      if (bad_id(uid, A.rows_user)) flag_status(A.status, NCF_STATUS_BAD_USER_ID);
+      const float* r = A.t_umf + clamp_id(uid, A.rows_user) * D;
       x0 = r[lane];
       x1 = r[lane + 32];
     }
@@ -443,6 +447,8 @@ extern "C" int ncf_score_topk_tc(const ncf_tables* T, const float* dense, const 
   A.user_ids = user_ids;
   A.n_users = n_users;
   A.I = I;
+  A.rows_user = T->rows_user;
+  A.status = T->status;
   A.nsplit = ns;
   A.part = static_cast<unsigned long long*>(workspace);
   A.cand = reinterpret_cast<unsigned long long*>(static_cast<char*>(workspace) + align_up(n_users * ns * SC_KMAX * 8, 256));

@@ -70,7 +70,14 @@ int emb_bwd_both(const ncf_adam_cfg* adam, const ncf_tables* T, const float* den
                  const int64_t* user_ids, const int64_t* item_ids, int64_t N, const float* d_mf_pred, const float* dxu,
                  const float* dxp, const float* y_item_mf, const float* y_user_mf, void* workspace, int64_t workspace_bytes,
                  cudaStream_t st, bool presorted = false, bool preswept = false, cudaStream_t side_stream = nullptr);
-extern cudaStream_t g_aux_stream;      // ncf_set_aux_stream (ncf_abi.cu); null = none
+// ncf_set_aux_stream (ncf_abi.cu): per-device auxiliary stream (null = none) + the events that order it
+constexpr int NCF_MAX_DEVICES = 64;
+struct AuxCtx {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};     // 0 fork, 1 sorted (ncf_train_step); 2 fork, 3 join (emb_bwd_both)
+};
+AuxCtx* aux_ctx();
+int aux_events(AuxCtx* a);
 int emb_sweep_early(const ncf_adam_cfg* adam, const ncf_tables* T, const int64_t* user_ids, const int64_t* item_ids, int64_t N,
                     cudaStream_t st);
 int emb_sort_both(const ncf_tables* T, const int64_t* user_ids, const int64_t* item_ids, int64_t N, void* workspace,

@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(LG_THREADS) linear_kernel(LinearArgs A) {
     for (int c = 0; c < CM::CN; ++c) y[c] = acc[r][c] + bias[c];
     if (EPI == EPI_RELU_LN_DROP) {
       if (A.hour && live) {
-        const float* t = A.tail1 + A.hour[row] * J;
+        const float* t = A.tail1 + clamp_id(A.hour[row], 24) * J;
 #pragma unroll
         for (int g = 0; g < CM::NG; ++g)
 #pragma unroll

@@ -349,7 +349,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_tc_fwd_kernel(MlpFwdArgs A
     float* st2 = A.st2 ? A.st2 + tile * 256 : nullptr;
     float* st3 = A.st3 ? A.st3 + tile * 256 : nullptr;
     if (A.hour) {
-      const float* tail_row = live ? A.tail1 + A.hour[grow] * H1 : nullptr;
+      const float* tail_row = live ? A.tail1 + clamp_id(A.hour[grow], 24) * H1 : nullptr;
       mlp_epilogue<256, false, true>(tmem + 0, q, h, lane, grow, live, par + PAR_B0, par + PAR_G0, par + PAR_E0, tail_row,
                                      A.rng[0], s_stat, smem + SM_Y, r1i, y1i, nullptr, nullptr, hp, st1);
     } else {
@@ -528,7 +528,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_tc_fwd2_kernel(MlpFwdArgs 
     float hp;
     const uint32_t slot = tmem + 256 * s;
     if (A.hour) {
-      const float* tail_row = live ? A.tail1 + A.hour[grow] * H1 : nullptr;
+      const float* tail_row = live ? A.tail1 + clamp_id(A.hour[grow], 24) * H1 : nullptr;
       mlp_epilogue<256, false, true, true>(slot, q, h, lane, grow, live, par + PAR_B0, par + PAR_G0, par + PAR_E0, tail_row,
                                            A.rng[0], s_stat, nullptr, r1i, y1i, nullptr, nullptr, hp, st1, slot);
     } else {

@@ -12,7 +12,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
-from typing import Tuple
+from typing import Optional, Tuple
 
 import torch
 
@@ -21,13 +21,17 @@ from .architecture import AdvancedNCF, _stream
 
 
 class CatalogueScorer:
-    def __init__(self, model: AdvancedNCF):
+    def __init__(self, model: AdvancedNCF, tc_min_items: Optional[int] = None, tc_min_users: Optional[int] = None):
         self.model = model
         self.lib = _lib.load()
         self.p_hat = None
         self.g = None
         self.img = None            # item tile images of the tensor-core pre-filter (large catalogues)
         self.use_tc = os.environ.get("NCF_SCORE_TC", "1") != "0"
+        if tc_min_items is not None:
+            self.TC_MIN_ITEMS = tc_min_items
+        if tc_min_users is not None:
+            self.TC_MIN_USERS = tc_min_users
         self.refresh()
 
     @torch.no_grad()

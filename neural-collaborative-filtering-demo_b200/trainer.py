@@ -34,6 +34,8 @@ class NCFTrainEngine:
         model._ensure_flat()
         model.configure_table_optimizer(table_mode, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
         dev = model._flat.device
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
         self.device = dev
         n = model._flat.numel()
         self.dense_grad = torch.zeros(n, device=dev)
@@ -54,6 +56,20 @@ class NCFTrainEngine:
         self._aux_stream = torch.cuda.Stream(device=dev) if os.environ.get("NCF_AUX_STREAM", "1") != "0" else None
         if max_rows:
             self._reserve(max_rows)
+
+    def close(self):
+        """Detach the auxiliary stream from the library (it must outlive every call that may use it)."""
+        if getattr(self, "_aux_stream", None) is not None:
+            torch.cuda.synchronize(self.device)
+            with torch.cuda.device(self.device):
+                self.lib.ncf_set_aux_stream(None)
+            self._aux_stream = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001 - interpreter shutdown
+            pass
 
     def _reserve(self, N):
         cfg = self._cfg()
@@ -100,6 +116,7 @@ class NCFTrainEngine:
         if N % self.S:
             raise ValueError(f"{N} rows are not groups of {self.S}")
         self._validate_model()
+        self.model.check_status("NCFTrainEngine.train_step (an earlier step)")
         self.step += 1
         self._reserve(N)
         cfg = self._cfg()
@@ -108,12 +125,20 @@ class NCFTrainEngine:
         adam.eps, adam.weight_decay, adam.step = self.hp["eps"], self.hp["weight_decay"], self.step
         adam.emb_mode = _lib.EMB_ADAM_DENSE_EQUIV if self.table_mode == "fused_dense_equiv" else _lib.EMB_ADAM_SPARSE
         tables = self._tables
-        self.lib.ncf_set_aux_stream(C.c_void_p(self._aux_stream.cuda_stream) if self._aux_stream is not None else None)
-        _lib.check(self.lib.ncf_train_step(C.byref(cfg), C.byref(adam), C.byref(tables), _lib.ptr(self.model._flat),
-                                           _lib.ptr(self.dense_grad), _lib.ptr(self.dense_m), _lib.ptr(self.dense_v),
-                                           _lib.ptr(user_ids), _lib.ptr(item_ids), _lib.ptr(targets), N,
-                                           _lib.ptr(self._out), _lib.ptr(self.loss), _lib.ptr(self._ws),
-                                           self._ws.numel(), _stream(self.device)), "ncf_train_step")
+        # the library keeps the auxiliary stream and its events per CURRENT device (ncf_set_aux_stream): make sure that is ours
+        prev = torch.cuda.current_device()
+        if prev != self.device.index:
+            torch.cuda.set_device(self.device)
+        try:
+            self.lib.ncf_set_aux_stream(C.c_void_p(self._aux_stream.cuda_stream) if self._aux_stream is not None else None)
+            _lib.check(self.lib.ncf_train_step(C.byref(cfg), C.byref(adam), C.byref(tables), _lib.ptr(self.model._flat),
+                                               _lib.ptr(self.dense_grad), _lib.ptr(self.dense_m), _lib.ptr(self.dense_v),
+                                               _lib.ptr(user_ids), _lib.ptr(item_ids), _lib.ptr(targets), N,
+                                               _lib.ptr(self._out), _lib.ptr(self.loss), _lib.ptr(self._ws),
+                                               self._ws.numel(), _stream(self.device)), "ncf_train_step")
+        finally:
+            if prev != self.device.index:
+                torch.cuda.set_device(prev)
         self.model._table_step = self.step
         self.outputs = self._out[:N]
         return self.loss
@@ -155,7 +180,9 @@ class NCFTrainEngine:
                     self._staged_event = self._copy_stream.record_event()
                 self._staged_key = (nu.data_ptr(), ni.data_ptr(), nt.data_ptr(), M)
         self._stage_slot = cur ^ 1
-        return float(loss.item())
+        value = float(loss.item())
+        self.model.check_status("NCFTrainEngine.train_step_host")      # the loss read above synchronised this step
+        return value
 
     def state_dict(self):
         return {"step": self.step, "dense_m": self.dense_m.clone(), "dense_v": self.dense_v.clone(),
@@ -246,7 +273,7 @@ class ModelTrainer:
             os.makedirs(checkpoint_dir, exist_ok=True)
             latest = self._find_latest_checkpoint(checkpoint_dir)
             if latest:
-                start = self._load_checkpoint(latest) + 1
+                start = self._load_checkpoint(latest)
         for epoch in range(start, num_epochs):
             tl = self.train_epoch(train_loader)
             vm = self.validate(val_loader)
@@ -266,21 +293,43 @@ class ModelTrainer:
                 break
         return history
 
-    # checkpoint format of trainer.py:548-609 plus the fused table-optimizer state
-    def _save_checkpoint(self, checkpoint_dir, epoch, metrics, is_best=False):
+    # ---- checkpoints: the reference's format (trainer.py:548-609) ------------------------------------------------
+    def _table_param_indices(self):
+        """positions of the four table parameters in `model.parameters()` order = their keys in optimizer.state_dict()"""
+        if not isinstance(self.model, AdvancedNCF):
+            return []
+        ids = [id(t) for t in self.model._table_params()]
+        pos = {id(p): k for k, p in enumerate(self.model.parameters())}
+        return [pos[i] for i in ids]
+
+    def _optimizer_state_with_tables(self):
+        """optimizer.state_dict() as the REFERENCE would have written it: in the fused table modes the tables' Adam moments
+        live in the module (their .grad stays None, so torch's Adam holds no state for them); mirror them into the
+        entries torch.optim.Adam uses (step / exp_avg / exp_avg_sq), so a reference-side resume finds them."""
+        sd = self.optimizer.state_dict()
         m = self.model
-        ck = {"epoch": epoch, "model_state_dict": m.state_dict(), "optimizer_state_dict": self.optimizer.state_dict(),
+        if isinstance(m, AdvancedNCF) and m._table_state is not None:
+            sd = {"state": dict(sd["state"]), "param_groups": sd["param_groups"]}
+            for k, idx in enumerate(self._table_param_indices()):
+                sd["state"][idx] = {"step": torch.tensor(float(m._table_step)), "exp_avg": m._table_state["m"][k].clone(),
+                                    "exp_avg_sq": m._table_state["v"][k].clone()}
+        return sd
+
+    def _save_checkpoint(self, checkpoint_dir, epoch, metrics, is_best=False, filename=None):
+        m = self.model
+        if filename is None:
+            filename = f"checkpoint_epoch_{epoch + 1}.pt"                                   # trainer.py:558
+        ck = {"epoch": epoch, "model_state_dict": m.state_dict(), "optimizer_state_dict": self._optimizer_state_with_tables(),
               "metrics": metrics, "config": self.config,
-              "model_config": {k: getattr(m, k) for k in ("num_users", "num_products", "num_departments", "num_categories",
-                                                          "mf_embedding_dim", "temporal_dim", "num_heads") if hasattr(m, k)},
-              "table_optimizer_state": m.table_optimizer_state_dict() if hasattr(m, "table_optimizer_state_dict") else {}}
-        path = os.path.join(checkpoint_dir, f"checkpoint_epoch_{epoch}.pt")
+              "model_config": {"num_users": m.num_users, "num_products": m.num_products,
+                               "embedding_dim": m.mf_embedding_dim}}                       # trainer.py:566-570
+        path = os.path.join(checkpoint_dir, filename)
         torch.save(ck, path)
         if is_best:
             best = os.path.join(checkpoint_dir, "best_model.pt")
             if os.path.lexists(best):
                 os.remove(best)
-            os.symlink(os.path.basename(path), best)
+            os.symlink(filename, best)
         return path
 
     @staticmethod
@@ -298,9 +347,22 @@ class ModelTrainer:
         return best
 
     def _load_checkpoint(self, path) -> int:
+        """trainer.py:588-609: returns the epoch to resume FROM (saved epoch + 1).  A checkpoint written by the reference
+        (or by the "autograd" table mode) keeps the tables' moments inside optimizer_state_dict: in the fused modes they
+        are moved into the module's table state, so the resumed run continues the same Adam trajectory."""
         ck = torch.load(path, map_location=self.device, weights_only=False)
         self.model.load_state_dict(ck["model_state_dict"])
-        self.optimizer.load_state_dict(ck["optimizer_state_dict"])
-        if hasattr(self.model, "load_table_optimizer_state_dict"):
-            self.model.load_table_optimizer_state_dict(ck.get("table_optimizer_state", {}))
-        return int(ck["epoch"])
+        osd = ck["optimizer_state_dict"]
+        m = self.model
+        fused = isinstance(m, AdvancedNCF) and m._table_mode != "autograd"
+        if fused:
+            osd = {"state": dict(osd["state"]), "param_groups": osd["param_groups"]}
+            idxs = self._table_param_indices()
+            if all(i in osd["state"] for i in idxs):
+                st = [osd["state"].pop(i) for i in idxs]
+                m.load_table_optimizer_state_dict({"step": int(float(st[0]["step"])), "m": [x["exp_avg"] for x in st],
+                                                   "v": [x["exp_avg_sq"] for x in st]})
+            elif ck.get("table_optimizer_state"):                                          # round-1 format of this repo
+                m.load_table_optimizer_state_dict(ck["table_optimizer_state"])
+        self.optimizer.load_state_dict(osd)
+        return int(ck["epoch"]) + 1

@@ -442,6 +442,49 @@ def test_errors_are_loud():
         m.eval()(ncf_b200.make_kjt(torch.arange(4), torch.arange(4)))   # no CPU fallback
 
 
+def test_out_of_range_ids_raise_and_never_corrupt_the_tables():
+    """nn.EmbeddingBag raises on an id outside its table (reference architecture.py:286-287).  A kernel cannot raise: it
+    clamps the id (no out-of-bounds access, no spill of a bad user id into the item region of the combined sort keys) and
+    sets a sticky status word; the host raises IndexError at its next synchronisation point."""
+    import ncf_b200
+    p, _ = golden_params()
+    m = _model(p, 8031, 366).eval()
+    good_u, good_i = torch.tensor([1, 2, 3, 4]), torch.tensor([5, 6, 7, 8])
+    for bad_u, bad_i, frag in ((torch.tensor([1, 8031, 3, 4]), good_i, "user id"), (good_u, torch.tensor([5, -1, 7, 366]), "product id")):
+        with torch.no_grad():
+            m(_kjt(bad_u, bad_i))
+        torch.cuda.synchronize()
+        with pytest.raises(IndexError, match=frag):
+            m.check_status()
+        with torch.no_grad():
+            out = m(_kjt(good_u, good_i))            # the flag was consumed: good ids work again
+        torch.cuda.synchronize()
+        m.check_status()
+        assert bool(torch.isfinite(out).all())
+    with torch.no_grad():
+        m.forward_simple(good_u.cuda(), good_i.cuda(), hour=torch.tensor([0, 23, 24, 5]).cuda())
+    torch.cuda.synchronize()
+    with pytest.raises(IndexError, match="hour"):
+        m.check_status()
+    with pytest.raises(IndexError):
+        ncf_b200.CatalogueScorer(m).topk(torch.tensor([0, 9000]).cuda(), 5)
+        torch.cuda.synchronize()
+        m.check_status()
+    # training engine: a bad id in a step is reported when the loss is read, and the tables stay finite everywhere
+    m = _model(p, 8031, 366).train()
+    eng = ncf_b200.NCFTrainEngine(m, lr=1e-3)
+    u = torch.tensor([10, 10, 10, 10, 10, 9000, 9000, 9000, 9000, 9000]).pin_memory()
+    i = torch.tensor([1, 2, 3, 4, 5, 6, 7, 400, 9, 10]).pin_memory()
+    t = torch.tensor([1.0, 0, 0, 0, 0, 1, 0, 0, 0, 0]).pin_memory()
+    before = [w.detach().clone() for w in m._table_params()]
+    with pytest.raises(IndexError):
+        eng.train_step_host(u, i, t)
+    for w, w0 in zip(m._table_params(), before):
+        assert bool(torch.isfinite(w).all()) and w.shape == w0.shape
+    with pytest.raises(IndexError):
+        m.temporal_encoding(torch.tensor([24]).cuda(), torch.tensor([0]).cuda(), torch.tensor([0]).cuda(), torch.tensor([0]).cuda())
+
+
 def test_topk_large_catalogue_tiled_kernel():
     """> 1M items selects the register-tiled cp.async scoring kernel: indices equal the oracle's stable
     order up to fp32 near-ties, scores within 1e-5, order property exact."""
@@ -534,3 +577,41 @@ def test_embedding_export_and_exact_cosine_index(tmp_path):
     want = torch.argsort(full, dim=1, descending=True, stable=True)[:, :10]
     assert torch.equal(pos.cpu(), want) or float((torch.gather(full, 1, pos.cpu()) - torch.gather(full, 1, want)).abs().max()) < 1e-6
     assert float((sim.cpu() - torch.gather(full, 1, pos.cpu())).abs().max()) < 1e-5
+
+
+def test_model_trainer_checkpoint_keeps_the_reference_format_and_resumes_table_moments(tmp_path):
+    """trainer.py:548-609: file name checkpoint_epoch_{epoch+1}.pt, model_config keys, and the four tables' Adam moments
+    inside optimizer_state_dict under torch.optim.Adam's own keys (so a reference-side resume finds them); loading moves
+    them back into the fused table state and the next step continues the same trajectory."""
+    import ncf_b200
+    z = load_npz("train_step.npz")
+    p = small_params(z)
+    cfg = {"num_users": 97, "num_products": 53, "batch_size": 6, "learning_rate": 1e-3}
+    u, i, t = (torch.from_numpy(z[f"s1/{k}"]) for k in ("users", "items", "targets"))
+    batch = [(_kjt(u, i), t.cuda())]
+
+    def trainer():
+        m = _model(p, 97, 53).train()
+        return ncf_b200.ModelTrainer(m, cfg)
+    a = trainer()
+    a.train_epoch(batch)
+    a.train_epoch(batch)
+    path = a._save_checkpoint(str(tmp_path), 1, {"loss": 0.5}, is_best=True)
+    assert path.endswith("checkpoint_epoch_2.pt") and (tmp_path / "best_model.pt").is_symlink()
+    ck = torch.load(path, map_location="cpu", weights_only=False)
+    assert set(ck["model_config"]) == {"num_users", "num_products", "embedding_dim"}
+    idxs = a._table_param_indices()
+    for k, idx in enumerate(idxs):
+        st = ck["optimizer_state_dict"]["state"][idx]
+        assert float(st["step"]) == 2.0 and st["exp_avg"].shape == a.model._table_params()[k].shape
+        assert float(st["exp_avg_sq"].abs().max()) > 0
+    b = trainer()
+    assert b._load_checkpoint(ncf_b200.ModelTrainer._find_latest_checkpoint(str(tmp_path))) == 2
+    assert b.model._table_step == 2
+    for k in range(4):
+        assert torch.equal(b.model._table_state["m"][k], a.model._table_state["m"][k])
+        assert torch.equal(b.model._table_state["v"][k], a.model._table_state["v"][k])
+    a.train_epoch(batch)
+    b.train_epoch(batch)
+    for wa, wb in zip(a.model._table_params(), b.model._table_params()):
+        assert float((wa - wb).abs().max()) < 1e-7

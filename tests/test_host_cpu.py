@@ -21,7 +21,8 @@ def test_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(_lib.LIB_PATH)
     for name in declared:
         assert hasattr(lib, name), name
-    assert _lib.load().ncf_version() == 1
+    version = int(re.search(r"#define NCF_ABI_VERSION (\d+)", hdr).group(1))
+    assert _lib.load().ncf_version() == version
 
 
 def test_dense_layout_matches_module_parameters():
