@@ -208,31 +208,78 @@ def time_kernel(fn, iters, stream_sync):
     return e0.elapsed_time(e1) / iters
 
 
+def timed_blocks(step_fn, K, barrier, world, dev, min_seconds=1.0, max_blocks=200):
+    """Times blocks of EXACTLY K steps (CUDA events on the launch stream, barrier + synchronize on both sides, max over
+    ranks per block) until at least `min_seconds` of timed work have run, so that clocks are sampled under load; the
+    reported number is the MEDIAN block.  Returns the list of block times in ms."""
+    import torch
+    import torch.distributed as dist
+    blocks, total = [], 0.0
+    while True:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for s in range(K):
+            step_fn(s)
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+        blocks.append(ms)
+        total += ms
+        if total >= min_seconds * 1e3 or len(blocks) >= max_blocks:
+            return blocks
+
+
+def wall_blocks(step_fn, K, barrier, world, dev, min_seconds=0.5, max_blocks=100):
+    """Same for the end-to-end leg: wall clock around K steps that each end with a device->host read."""
+    import torch
+    import torch.distributed as dist
+    blocks, total = [], 0.0
+    while True:
+        barrier()
+        t0 = time.perf_counter()
+        for s in range(K):
+            step_fn(s)
+        torch.cuda.synchronize()
+        t = torch.tensor([(time.perf_counter() - t0) * 1e3], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+        blocks.append(ms)
+        total += ms
+        if total >= min_seconds * 1e3 or len(blocks) >= max_blocks:
+            return blocks
+
+
+def build_model_on_device(users, items, device, precision):
+    """Like build_model but the (large) tables are drawn on the device: no multi-GB host init + copy."""
+    import torch
+    import ncf_b200
+    torch.manual_seed(1234)
+    with torch.device(device):
+        m = ncf_b200.AdvancedNCF(users, items, 5, 24, 64, 64, 32, [256, 128, 64], 4, 0.2, 4)
+    m.compute_precision = precision
+    return m.train()
+
+
 SCORE_SHAPES = {"score": (1000000, 10000000, "config[4] full-catalogue scoring + top-100: 1M users x 10M items"),
                 "score_small": (138493, 26744, "full-catalogue scoring + top-100 at the config[2] shape")}
 
 
-def run_score(args):
-    """Full-catalogue scoring + top-100 (app.py:43-77 at scale).  A step scores `--batch` users (default 2048
-    per GPU) against ALL items; metric = (user,item) pairs scored per second.  Users are sharded over the
-    ranks, the folded item side is replicated."""
+def score_measure(users, items, n, k, steps, warmup, world, rank, dev, min_seconds=0.5, verify_users=0, verify_where="cuda"):
+    """Full-catalogue scoring + top-k (app.py:43-77 at scale) on this rank: a step scores `n` users against ALL `items`.
+    Users are sharded over the ranks, the folded item side is replicated.  Returns per-rank timing dict
+    (block times already max-reduced over ranks)."""
     import torch
     import torch.distributed as dist
     import ncf_b200
     from ncf_b200 import _lib
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
-    users, items, desc = SCORE_SHAPES[args.workload]
-    n = args.batch or 2048          # users per GPU per step: 16 tiles of 128 users for the tensor-core pre-filter
-    k = 100
     users_local = (users + world - 1) // world
-    model = build_model(users_local, items, dev, "fp32").eval()      # same seed on every rank: replicated item side
+    model = build_model_on_device(users_local, items, dev, "fp32").eval()      # same seed on every rank: replicated item side
     scorer = ncf_b200.CatalogueScorer(model)
     g = torch.Generator().manual_seed(77 + rank)
     dev_b = [torch.randint(0, users_local, (n,), generator=g).to(dev) for _ in range(4)]
@@ -242,57 +289,122 @@ def run_score(args):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-    for s in range(args.warmup):
+    for s in range(warmup):
         scorer.topk(dev_b[s % 4], k)
     barrier()
+    l0 = int(lib.ncf_launch_count())
+    blocks = timed_blocks(lambda s: scorer.topk(dev_b[s % 4], k), steps, barrier, world, dev, min_seconds)
+    launches = (int(lib.ncf_launch_count()) - l0) // len(blocks)
+
+    def e2e_step(s):
+        idx, sc = scorer.topk(host_b[s % 4].to(dev, non_blocking=True), k)
+        idx.cpu(), sc.cpu()
+    e2e = wall_blocks(e2e_step, steps, barrier, world, dev, min_seconds)
+    out = {"ms_block": statistics.median(blocks), "blocks": len(blocks), "e2e_ms_block": statistics.median(e2e),
+           "launches": launches, "tc": scorer.img is not None and n >= scorer.TC_MIN_USERS}
+    if verify_users:
+        out["verify"] = score_verify(model, scorer, verify_users, k, rank, verify_where)
+    del scorer, model
+    torch.cuda.empty_cache()
+    return out
+
+
+def score_verify(model, scorer, n_users, k, rank, where="cuda"):
+    """seeded users scored by the oracle's forward_simple (oracle/ncf_oracle.py, the reference's per-pair
+    arithmetic: full attention + MLP tower for every (user, item)) over ALL items in 1M-item chunks + stable top-k (score
+    desc, index asc), compared position by position with the product's result; a differing position must be an fp32
+    near-tie (reference gap below 2 ulp of the score).  where = "cpu": the oracle on the host cores (about 15 s per user
+    at 10M items); "cuda": the same torch code executed on the device (256 users in seconds)."""
+    import torch
+    from oracle import ncf_oracle as O
+    g = torch.Generator().manual_seed(4242 + rank)
+    users = torch.randint(0, model.num_users, (n_users,), generator=g)
+    dev = next(model.parameters()).device
+    idx, sc = scorer.topk(users.to(dev), k)
+    odev = dev if where == "cuda" else torch.device("cpu")
+    idx = idx.to(odev)
+    sd = {kk: v.detach().to(odev) for kk, v in model.state_dict().items()}
+    I = model.num_products
+    exact = near = bad = 0
+    t0 = time.perf_counter()
+    for j, u in enumerate(users.tolist()):
+        parts = []
+        for s0 in range(0, I, 1 << 20):
+            it = torch.arange(s0, min(I, s0 + (1 << 20)), device=odev)
+            parts.append(O.forward_simple(sd, torch.full((it.numel(),), u, dtype=torch.long, device=odev), it))
+        ref = torch.cat(parts)
+        want = O.topk_stable(ref, k)
+        d = idx[j] != want
+        exact += int((~d).sum())
+        if bool(d.any()):
+            gap = (ref[idx[j]] - ref[want]).abs()[d]
+            ulp2 = 2.4e-7 * ref[want][d].abs().clamp_min(1e-3)
+            near += int((gap <= ulp2).sum())
+            bad += int((gap > ulp2).sum())
+    return {"users": n_users, "items": I, "k": k, "positions": n_users * k, "index_equal": exact, "near_tie_swaps": near,
+            "mismatches": bad, "reference_seconds": time.perf_counter() - t0,
+            "reference": f"oracle forward_simple in 1M-item chunks + stable top-k (app.py:48-75), torch fp32 on {where}"}
+
+
+def score_line(args, world, rank, local):
+    import torch
+    import torch.distributed as dist
+    dev = torch.device("cuda", local)
+    users, items, desc = SCORE_SHAPES[args.workload]
+    n = args.batch or 2048          # users per GPU per step: 16 tiles of 128 users for the tensor-core pre-filter
+    k = 100
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    l0 = int(lib.ncf_launch_count())
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for s in range(args.steps):
-        scorer.topk(dev_b[s % 4], k)
-    e1.record()
-    barrier()
-    ms_total = e0.elapsed_time(e1)
-    launches = int(lib.ncf_launch_count()) - l0
-    t0 = time.perf_counter()
-    for s in range(args.steps):
-        idx, sc = scorer.topk(host_b[s % 4].to(dev, non_blocking=True), k)
-        idx_h, sc_h = idx.cpu(), sc.cpu()
-    torch.cuda.synchronize()
-    e2e_ms = (time.perf_counter() - t0) * 1e3
+    r = score_measure(users, items, n, k, args.steps, args.warmup, world, rank, dev, 1.0,
+                      verify_users=args.verify_users if args.verify else 0, verify_where=args.verify_where)
     clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([ms_total, e2e_ms], device=dev, dtype=torch.float64)
+    ver = r.get("verify")
+    if world > 1 and ver is not None:
+        t = torch.tensor([ver["index_equal"], ver["near_tie_swaps"], ver["mismatches"], ver["positions"]], device=dev)
+        dist.all_reduce(t)
+        ver.update(index_equal=int(t[0]), near_tie_swaps=int(t[1]), mismatches=int(t[2]), positions=int(t[3]),
+                   users=ver["users"] * world)
+    if rank != 0:
+        return
+    pk = peaks()
+    pairs = world * n * items * args.steps
+    value = pairs / (r["ms_block"] / 1e3)
+    tflops = value * 128 / 1e12
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_score_rate(items, os.cpu_count() or 1)
+    line = {"metric": "scoring_samples_per_s", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": r["ms_block"] / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "fp32", "data": "synthetic", "timed_blocks": r["blocks"],
+            "config": {"workload": f"{args.workload}: {desc}", "users_per_step_per_gpu": n, "items": items, "top_k": k,
+                       "l2": f"folded item table {items * 260 / 1e6:.0f} MB streamed per user tile"},
+            "users_per_s": world * n * args.steps / (r["ms_block"] / 1e3),
+            "e2e": {"value": pairs / (r["e2e_ms_block"] / 1e3), "unit": "pairs/s", "h2d_bytes_per_step": n * 8,
+                    "d2h_bytes_per_step": n * k * 12, "ms_per_step": r["e2e_ms_block"] / args.steps},
+            "gpu_launches": r["launches"], "clocks": clocks,
+            "roofline": {"kernel": "score_tc_kernel (tcgen05 bf16 upper-bound GEMM + exact fp32 re-scoring of survivors)"
+                                   if r["tc"] else "score_topk_kernel (exact fp32)",
+                         "bound": "tensor", "achieved": tflops, "peak": world * pk["bf16_tflops"],
+                         "unit": "TFLOP/s", "frac": tflops / (world * pk["bf16_tflops"]), "traffic": None,
+                         "peak_source": pk["source"] + " (bf16 burst) x n_gpus; 128 flop per (user, item) pair; the kernel is "
+                                        "bound by its per-tile epilogue (threshold scan of the TMEM accumulators), not by the tensor pipe"},
+            "cpu_baseline": cpu}
+    if ver is not None:
+        line["topk_verify"] = ver
+    print(json.dumps(line))
+
+
+def run_score(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms = float(t[0]), float(t[1])
-    if rank == 0:
-        pairs = world * n * items * args.steps
-        pk = peaks()
-        value = pairs / (ms_total / 1e3)
-        tflops = value * 128 / 1e12
-        cpu = None
-        if world == 1 and not args.no_cpu_baseline:
-            cpu = cpu_score_rate(items, os.cpu_count() or 1)
-        line = {"metric": "scoring_samples_per_s", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-                "config": {"workload": f"{args.workload}: {desc}", "users_per_step_per_gpu": n, "items": items, "top_k": k,
-                           "l2": f"folded item table {items * 260 / 1e6:.0f} MB streamed per user tile"},
-                "users_per_s": world * n * args.steps / (ms_total / 1e3),
-                "e2e": {"value": pairs / (e2e_ms / 1e3), "unit": "pairs/s", "h2d_bytes_per_step": n * 8,
-                        "d2h_bytes_per_step": n * k * 12, "ms_per_step": e2e_ms / args.steps},
-                "gpu_launches": launches, "clocks": clocks,
-                "roofline": {"kernel": "score_tc_kernel (tcgen05 bf16 upper-bound GEMM + exact fp32 re-scoring of survivors)"
-                                       if scorer.img is not None and n >= scorer.TC_MIN_USERS else "score_topk_kernel (exact fp32)",
-                             "bound": "tensor", "achieved": tflops, "peak": pk["bf16_tflops"],
-                             "unit": "TFLOP/s", "frac": tflops / pk["bf16_tflops"], "traffic": None,
-                             "peak_source": pk["source"] + " (bf16 burst); 128 flop per (user, item) pair; the kernel is bound by its "
-                                            "per-tile epilogue (threshold scan of the TMEM accumulators), not by the tensor pipe"},
-                "cpu_baseline": cpu}
-        print(json.dumps(line))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    score_line(args, world, rank, local)
     if world > 1:
         dist.destroy_process_group()
 
@@ -348,6 +460,15 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=4096, help="interactions per CPU-reference step (bounded sample)")
     ap.add_argument("--cpu-baseline-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--verify", action="store_true",
+                    help="score workloads: check the top-k of seeded users against the CPU oracle (SURVEY 8d C4); "
+                         "train workloads at N > 1: always on (3 sharded steps vs the single-GPU engine)")
+    ap.add_argument("--verify-users", type=int, default=32, help="users per rank checked by --verify (score workloads)")
+    ap.add_argument("--verify-where", default="cuda", choices=["cuda", "cpu"],
+                    help="run the oracle of --verify on the device (fast) or on the host cores (about 15 s per user at 10M items)")
+    ap.add_argument("--min-seconds", type=float, default=1.0, help="timed blocks of --steps steps are repeated until this much "
+                                                                    "timed work has run; the median block is reported")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary blocks (scoring, c3shard / c3)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -393,132 +514,122 @@ def main():
     if table_mode == "auto":
         table_mode = "fused_sparse" if args.workload in ("c3shard", "c3") else "fused_dense_equiv"
 
-    if world > 1:
-        # row-sharded tables: the model object only carries the replicated dense parameters
-        from ncf_b200.sharding import ShardedNCFEngine
-        model = build_model(1, 1, dev, precision)
-        eng = ShardedNCFEngine(model, users, items, lr=1e-3, weight_decay=1e-5, table_mode=table_mode)
-        # two sets of device staging buffers: while step s runs, the ids of step s+1 are already on the device, so
-        # the engine can route them ahead (ShardedNCFEngine.train_step next_ids)
-        dev_in = [[torch.empty(N, dtype=torch.long, device=dev), torch.empty(N, dtype=torch.long, device=dev),
-                   torch.empty(N, dtype=torch.float32, device=dev)] for _ in range(2)]
-        staged = {"slot": 0, "have": False}
-
-        def stage(slot, batch):
-            for d, h in zip(dev_in[slot], batch):
-                d.copy_(h, non_blocking=True)
-
-        def step_host(u, i, t, nxt=None):
-            cur = staged["slot"]
-            if not staged["have"]:
-                stage(cur, (u, i, t))
-            nids = None
-            if nxt is not None:
-                stage(cur ^ 1, nxt)
-                nids = tuple(dev_in[cur ^ 1][:2])
-            staged["slot"], staged["have"] = cur ^ 1, nxt is not None
-            return float(eng.train_step(*dev_in[cur], next_ids=nids).item())
-        eng.train_step_host = step_host
-    else:
-        if args.workload == "c3":
-            raise SystemExit("workload c3 (169 GB of tables + Adam state) needs --gpus >= 2")
-        model = build_model(users, items, dev, precision)
-        eng = ncf_b200.NCFTrainEngine(model, lr=1e-3, weight_decay=1e-5, table_mode=table_mode, max_rows=N)
-    nb = 4
-    dev_batches = make_batches(users, items, B, nb, 1234 + rank, device=dev)
-    host_batches = make_batches(users, items, B, nb, 4321 + rank, pin=True)
-
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident throughput ("value") ----
-    for s in range(args.warmup):
-        eng.train_step(*dev_batches[s % nb])
-    barrier()
-    if getattr(eng, "phase_ms", None):
-        eng.phase_ms.clear()                 # NCF_SHARD_PROFILE: steady state only
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    launches0 = int(lib.ncf_launch_count())
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for s in range(args.steps):
-        if world > 1:      # sharded engine: the next batch's ids are known (input-pipeline look-ahead)
-            eng.train_step(*dev_batches[s % nb], next_ids=dev_batches[(s + 1) % nb][:2] if s + 1 < args.steps else None)
-        else:
-            eng.train_step(*dev_batches[s % nb])
-    e1.record()
-    barrier()
-    ms_total = e0.elapsed_time(e1)
-    launches = int(lib.ncf_launch_count()) - launches0
-    last_loss = float(eng.loss.item())
-
-    # ---- end to end from pinned host buffers ("e2e") ----
-    for s in range(3):
-        eng.train_step_host(*host_batches[s % nb])
-    barrier()
-    t0 = time.perf_counter()
-    for s in range(args.steps):
-        if world > 1:
-            eng.train_step_host(*host_batches[s % nb], nxt=host_batches[(s + 1) % nb] if s + 1 < args.steps else None)
-        else:
-            eng.train_step_host(*host_batches[s % nb], next_batch=host_batches[(s + 1) % nb] if s + 1 < args.steps else None)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    clocks = sampler.stop() if rank == 0 else None
-
-    t = torch.tensor([ms_total, e2e_s * 1e3], device=dev, dtype=torch.float64)
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms_total = float(t[0]), float(t[1])
-    ms_step = ms_total / args.steps
-    value = world * N * args.steps / (ms_total / 1e3)
-    e2e_value = world * N * args.steps / (e2e_ms_total / 1e3)
+        r = sharded_measure(args, users, items, B, precision, table_mode, world, rank, dev, barrier)
+    else:
+        if args.workload == "c3":
+            raise SystemExit("workload c3 (169 GB of tables + Adam state) needs --gpus >= 2")
+        r = single_measure(args, users, items, B, precision, table_mode, dev, barrier)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_step = r["ms_block"] / args.steps
+    value = world * N * args.steps / (r["ms_block"] / 1e3)
+    e2e_value = world * N * args.steps / (r["e2e_ms_block"] / 1e3)
+    pk = peaks()
+    hbm = pk["hbm_gbs"]
+    sus = pk["bf16_tflops_sustained"]
+    # SURVEY 8d basis for the WHOLE step: 4,316.8 algorithmic bytes and 495 kFLOP per sample row
+    survey = {"bytes_per_sample": 4316.8, "flop_per_sample": FLOP_TRAIN_PER_ROW,
+              "hbm": {"achieved": N * 4316.8 / ms_step / 1e6, "unit": "GB/s per GPU", "peak": hbm,
+                      "frac": N * 4316.8 / ms_step / 1e6 / hbm},
+              "tensor": {"achieved": N * FLOP_TRAIN_PER_ROW / ms_step / 1e9, "unit": "TFLOP/s per GPU", "peak": sus,
+                         "frac": N * FLOP_TRAIN_PER_ROW / ms_step / 1e9 / sus}}
 
-    if getattr(eng, "phase_ms", None):
-        n = eng.phase_ms.pop("steps")
-        sys.stderr.write(f"sharded phases, ms per step (rank {rank}): " + ", ".join(f"{k} {v / n:.3f}" for k, v in eng.phase_ms.items()) + "\n")
+    extras = {}
+    if not args.no_extras and args.workload == "c2":
+        extras = extra_blocks(args, world, rank, dev, precision, barrier)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
+    line = {
+        "metric": "train_samples_per_s", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16" if precision == "bf16" else "fp32", "data": "synthetic", "timed_blocks": r["blocks"],
+        "config": {"workload": f"{args.workload}: {desc}", "interactions_per_step_per_gpu": B, "rows_per_interaction": S,
+                   "table_update": table_mode, "towers": precision,
+                   "timing": f"median of {r['blocks']} blocks of {args.steps} steps (>= 1 s of timed work), CUDA events, max over ranks",
+                   "l2": f"inputs larger than L2: activations+ids of one step {N * 4316.8 / 1e6:.0f} MB algorithmic, 4 rotating batches"},
+        "interactions_per_s": value / S,
+        "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": N * (8 + 8 + 4), "d2h_bytes_per_step": 4,
+                "ms_per_step": r["e2e_ms_block"] / args.steps},
+        "gpu_launches": r["launches"], "clocks": clocks, "roofline": r.get("roofline"), "survey_basis_whole_step": survey,
+        "cpu_baseline": r.get("cpu_baseline"), "last_loss": r["last_loss"],
+    }
     if world > 1:
-        line = {
-            "metric": "train_samples_per_s", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "bf16" if precision == "bf16" else "fp32", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {desc}", "interactions_per_step_per_gpu": B,
-                       "rows_per_interaction": S, "table_update": table_mode, "towers": precision,
-                       "parallelism": f"tables row-sharded over {world} GPUs (all-to-all ids/rows/grads), towers "
-                                      f"data-parallel (dense all-reduce)",
-                       "l2": "per-step working set exceeds L2"},
-            "interactions_per_s": value / S,
-            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": N * (8 + 8 + 4),
-                    "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms_total / args.steps},
-            "gpu_launches": launches, "clocks": clocks, "roofline": None, "cpu_baseline": None, "last_loss": last_loss}
-        # whole-step HBM view over all ranks (per-kernel pieces are measured by the N=1 run): algorithmic bytes
-        # of the towers + embedding path per sample row, sparse table update
-        pk = peaks()
-        row_bytes = (BYTES_ATTN_FWD + BYTES_MLP_FWD + BYTES_MLP_BWD + BYTES_ATTN_BWD
-                     + (BYTES_FWD_PER_INTERACTION + BYTES_BWD_PER_INTERACTION) / S)
-        gbs = world * N * row_bytes / ms_step / 1e6
-        line["roofline"] = {"kernel": "whole step, all ranks (NVLink exchange not counted)", "bound": "hbm", "achieved": gbs,
-                            "peak": world * pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / (world * pk["hbm_gbs"]),
-                            "traffic": None, "peak_source": pk["source"] + " (copy) x n_gpus",
-                            "algorithmic_bytes_per_row": row_bytes}
-        print(json.dumps(line))
+        line["config"]["parallelism"] = (f"tables row-sharded over {world} GPUs (all-to-all ids/rows/grads), towers "
+                                         f"data-parallel (dense all-reduce)")
+        line["parity_vs_single_gpu"] = r.get("parity_vs_single_gpu")
+        line["parity_detail"] = r.get("parity_detail")
+        if r.get("phases"):
+            line["sharded_phases_ms"] = r["phases"]
+    line.update(extras)
+    print(json.dumps(line))
+    if world > 1:
         dist.destroy_process_group()
-        return
 
-    # ---- per-kernel roofline (rank 0, same inputs, CUDA events on the launch stream) ----
-    # The step is timed piecewise through the C ABI: K1 (ncf_gather_ln_gmf_fwd), the whole forward
-    # (ncf_forward), the tower backward alone (ncf_backward with emb_mode NONE), K6 (ncf_emb_bwd_adam_both)
-    # and the dense-equivalent sweep; towers forward = forward - K1.
+
+def single_measure(args, users, items, B, precision, table_mode, dev, barrier):
+    """N = 1: NCFTrainEngine on the device-resident batches (value), from pinned host buffers (e2e), and every stage of
+    the step on its own through the C ABI (roofline)."""
+    import torch
+    import ncf_b200
+    from ncf_b200 import _lib
+    lib = _lib.load()
+    N = B * S
+    big = users * 64 * 4 * 6 > (8 << 30)
+    model = build_model_on_device(users, items, dev, precision) if big else build_model(users, items, dev, precision)
+    eng = ncf_b200.NCFTrainEngine(model, lr=1e-3, weight_decay=1e-5, table_mode=table_mode, max_rows=N)
+    nb = 4
+    dev_batches = make_batches(users, items, B, nb, 1234, device=dev)
+    host_batches = make_batches(users, items, B, nb, 4321, pin=True)
+    for s in range(args.warmup):
+        eng.train_step(*dev_batches[s % nb])
+    barrier()
+    l0 = int(lib.ncf_launch_count())
+    blocks = timed_blocks(lambda s: eng.train_step(*dev_batches[s % nb]), args.steps, barrier, 1, dev, args.min_seconds)
+    launches = (int(lib.ncf_launch_count()) - l0) // len(blocks)
+    last_loss = float(eng.loss.item())
+    for s in range(3):
+        eng.train_step_host(*host_batches[s % nb])
+
+    def e2e_step(s):
+        eng.train_step_host(*host_batches[s % nb], next_batch=host_batches[(s + 1) % nb] if s + 1 < args.steps else None)
+    e2e = wall_blocks(e2e_step, args.steps, barrier, 1, dev, args.min_seconds / 2)
+    ms_step = statistics.median(blocks) / args.steps
+    roofline = stage_roofline(args, model, dev_batches[0], users, items, B, precision, table_mode, dev, ms_step)
+    cpu_baseline = None
+    if not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        Bs = min(B, args.ref_batch)
+        rate, ms = cpu_reference_rate(users, items, Bs, args.cpu_baseline_steps, 1, threads)
+        cpu_baseline = {"value": rate, "unit": "samples/s", "cores": threads, "kind": "port", "ms_per_step": ms,
+                        "sample": f"{Bs} of the {B} interactions of a step, {args.cpu_baseline_steps} steps"}
+    eng.close()
+    del eng, model
+    torch.cuda.empty_cache()
+    return {"ms_block": statistics.median(blocks), "blocks": len(blocks), "e2e_ms_block": statistics.median(e2e),
+            "launches": launches, "last_loss": last_loss, "roofline": roofline, "cpu_baseline": cpu_baseline}
+
+
+def stage_roofline(args, model, batch, users, items, B, precision, table_mode, dev, ms_step, brief=False):
+    """Per-kernel roofline (same inputs, CUDA events on the launch stream): the step is timed piecewise through the C ABI:
+    K1 (ncf_gather_ln_gmf_fwd), the tower stages in place on the workspace of a full forward, K6 (ncf_emb_bwd_adam_both)
+    and the dense-equivalent sweep.  brief: K1 / K6 / sweep only (the embedding path of another table size)."""
+    import torch
+    from ncf_b200 import _lib
+    lib = _lib.load()
+    N = B * S
     pk = peaks()
-    u, it, tg = dev_batches[0]
+    u, it, tg = batch
     tabs = model._tables_struct()
     st = torch.cuda.current_stream(dev)
     sync = torch.cuda.synchronize
@@ -576,24 +687,33 @@ def main():
         adam.emb_mode = _lib.EMB_ADAM_DENSE_EQUIV
         _lib.check(lib.ncf_emb_adam_sweep(C.byref(adam), C.byref(tabs), sptr))
 
-    # Stage calls run in place on the workspace a full forward left behind (include/ncf_b200.h); every stage moves
-    # more bytes per call than the 126 MB L2 holds except K1/K6/sweep at this table size (noted below).
-    fwd()
-    k1_ms = time_kernel(k1, 20, sync)
-    afwd_ms = time_kernel(attn_fwd, 10, sync)
-    mfwd_ms = time_kernel(mlp_fwd, 10, sync)
-    mbwd_ms = time_kernel(mlp_bwd, 10, sync)
-    abwd_ms = time_kernel(attn_bwd, 10, sync)
-    k6_ms = time_kernel(k6, 10, sync)
-    sweep_ms = time_kernel(sweep, 10, sync) if table_mode == "fused_dense_equiv" else 0.0
-    sus = pk["bf16_tflops_sustained"]
     hbm = pk["hbm_gbs"]
+    sus = pk["bf16_tflops_sustained"]
+    table_mb = 2 * (users + items) * 256 / 1e6
+    resident = "L2-resident" if table_mb < 120 else "HBM-resident"
+    residency = (f"{resident}: the four tables are {table_mb:.0f} MB against the 126 MB L2"
+                 + (" - the fraction below is an L2-assisted figure, NOT an HBM measurement (see c3shard_embedding_path for "
+                    "the HBM-resident one)" if resident == "L2-resident" else ""))
 
     def hbm_piece(ms, nbytes, **extra):
         d = {"ms": ms, "bound": "hbm", "achieved": nbytes / ms / 1e6, "unit": "GB/s", "peak": hbm,
              "frac": nbytes / ms / 1e6 / hbm, "algorithmic_bytes": nbytes}
         d.update(extra)
         return d
+
+    k1_bytes = B * BYTES_FWD_PER_INTERACTION
+    k6_bytes = B * BYTES_BWD_PER_INTERACTION
+    k1()
+    k1_ms = time_kernel(k1, 20, sync)
+    k6_ms = time_kernel(k6, 10, sync)
+    emb_ms, emb_bytes = k1_ms + k6_ms, k1_bytes + k6_bytes
+    emb = {"ms": emb_ms, "achieved": emb_bytes / emb_ms / 1e6, "unit": "GB/s", "peak": hbm, "frac": emb_bytes / emb_ms / 1e6 / hbm,
+           "tables": residency,
+           "K1": hbm_piece(k1_ms, k1_bytes, gather_effective_gbs=4 * N * 256 / k1_ms / 1e6, gather_lookups=4 * N,
+                           gather_note="SURVEY 8d gather GB/s: every lookup counted (4 rows x 256 B per sample, no de-duplication); " + resident),
+           "K6": hbm_piece(k6_ms, k6_bytes)}
+    if brief:
+        return emb
 
     def tensor_piece(ms, flop_per_row, bytes_per_row):
         # SURVEY 8d counts the towers against the tensor pipe; their arithmetic intensity (flop / byte of
@@ -605,25 +725,27 @@ def main():
                                                                    "unit": "GB/s", "peak": hbm, "frac": gb / hbm,
                                                                    "flop_per_byte": flop_per_row / bytes_per_row}}
 
-    k1_bytes = B * BYTES_FWD_PER_INTERACTION
-    k6_bytes = B * BYTES_BWD_PER_INTERACTION
+    # Stage calls run in place on the workspace a full forward left behind (include/ncf_b200.h); every tower stage moves
+    # more bytes per call than the 126 MB L2 holds.
+    fwd()
+    afwd_ms = time_kernel(attn_fwd, 10, sync)
+    mfwd_ms = time_kernel(mlp_fwd, 10, sync)
+    mbwd_ms = time_kernel(mlp_bwd, 10, sync)
+    abwd_ms = time_kernel(attn_bwd, 10, sync)
+    sweep_ms = time_kernel(sweep, 10, sync) if table_mode == "fused_dense_equiv" else 0.0
     sweep_bytes = 2 * (users + items) * 1536
     tcp = precision == "bf16"
     kernels = {
-        # SURVEY 8d "gather GB/s": every lookup counted (4 rows of 256 B per sample, no de-duplication), next to the
-        # algorithmic figure (the S rows of an interaction share their user rows)
-        "K1 gather_ln_gmf_fwd": hbm_piece(k1_ms, k1_bytes, gather_effective_gbs=4 * N * 256 / k1_ms / 1e6,
-                                          gather_lookups=4 * N),
+        "K1 gather_ln_gmf_fwd": emb["K1"],
         "attention forward" + (" (attn_tc_fwd_kernel)" if tcp else " (fp32 kernels)"): tensor_piece(afwd_ms, FLOP_ATTN_FWD, BYTES_ATTN_FWD),
         "MLP forward" + (" (mlp_tc_fwd_kernel)" if tcp else " (fp32 kernels)"): tensor_piece(mfwd_ms, FLOP_MLP_FWD, BYTES_MLP_FWD),
         "MLP backward" + (" (head_bwd + mlp_tc_bwd + mlp_tc_wgrad kernels)" if tcp else " (fp32 kernels)"):
             tensor_piece(mbwd_ms, 2 * FLOP_MLP_FWD, BYTES_MLP_BWD),
         "attention backward" + (" (attn_tc_bwd_kernel)" if tcp else " (fp32 kernels)"): tensor_piece(abwd_ms, 3 * FLOP_ATTN_FWD, BYTES_ATTN_BWD),
-        "K6 emb_bwd_adam_both (1 sort + segment-sum + apply, both sides)": hbm_piece(k6_ms, k6_bytes),
+        "K6 emb_bwd_adam_both (1 sort + segment-sum + apply, both sides)": emb["K6"],
     }
     if sweep_ms:
-        kernels["dense-equivalent Adam sweep"] = hbm_piece(sweep_ms, sweep_bytes,
-                                                           note="tables that fit the 126 MB L2 read above the HBM copy peak")
+        kernels["dense-equivalent Adam sweep"] = hbm_piece(sweep_ms, sweep_bytes, note=residency)
     top = max(kernels, key=lambda k: kernels[k]["ms"])
     kt = kernels[top]
     traffic = None
@@ -631,45 +753,237 @@ def main():
     if os.path.exists(tpath):
         with open(tpath) as f:
             traffic = json.load(f).get(args.workload, {}).get(top)
-    emb_ms, emb_bytes = k1_ms + k6_ms, k1_bytes + k6_bytes
     pieces_ms = k1_ms + afwd_ms + mfwd_ms + mbwd_ms + abwd_ms + k6_ms + sweep_ms
     step_bytes = N * (BYTES_ATTN_FWD + BYTES_MLP_FWD + BYTES_MLP_BWD + BYTES_ATTN_BWD) + emb_bytes + (sweep_bytes if sweep_ms else 0)
     roofline = {"kernel": top, "bound": kt["bound"], "achieved": kt["achieved"], "peak": kt["peak"], "unit": kt["unit"],
                 "frac": kt["frac"], "traffic": traffic,
                 "peak_source": pk["source"] + (" (sustained bf16)" if kt["bound"] == "tensor" else " (copy)"),
-                "embedding_path": {"ms": emb_ms, "achieved": emb_bytes / emb_ms / 1e6, "unit": "GB/s",
-                                   "frac": emb_bytes / emb_ms / 1e6 / hbm},
+                "embedding_path": {k: v for k, v in emb.items() if k not in ("K1", "K6")},
                 "whole_step_hbm_view": {"algorithmic_bytes": step_bytes, "ms": ms_step, "achieved": step_bytes / ms_step / 1e6,
-                                        "unit": "GB/s", "frac": step_bytes / ms_step / 1e6 / hbm},
+                                        "unit": "GB/s", "frac": step_bytes / ms_step / 1e6 / hbm,
+                                        "note": "implementation view: counts the activation bytes this implementation moves "
+                                                "between its kernels; the SURVEY-basis fractions are in survey_basis_whole_step"},
                 "pieces_sum_ms": pieces_ms, "kernels": kernels}
     if "hbm_view" in kt:          # tower stages: SURVEY 8d counts them against the tensor pipe; their intensity says HBM
         roofline["hbm_view"] = kt["hbm_view"]
+    return roofline
 
-    cpu_baseline = None
-    if not args.no_cpu_baseline and world == 1:
-        threads = os.cpu_count() or 1
-        Bs = min(B, args.ref_batch)
-        rate, ms = cpu_reference_rate(users, items, Bs, args.cpu_baseline_steps, 1, threads)
-        cpu_baseline = {"value": rate, "unit": "samples/s", "cores": threads, "kind": "port", "ms_per_step": ms,
-                        "sample": f"{Bs} of the {B} interactions of a step, {args.cpu_baseline_steps} steps"}
 
-    line = {
-        "metric": "train_samples_per_s", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16" if precision == "bf16" else "fp32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {desc}", "interactions_per_step_per_gpu": B, "rows_per_interaction": S,
-                   "table_update": table_mode, "towers": precision,
-                   "l2": f"inputs larger than L2: activations+ids of one step {N * 4316.8 / 1e6:.0f} MB algorithmic, "
-                         f"{nb} rotating batches"},
-        "interactions_per_s": value / S,
-        "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": N * (8 + 8 + 4), "d2h_bytes_per_step": 4,
-                "ms_per_step": e2e_ms_total / args.steps},
-        "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
-        "last_loss": last_loss,
-    }
-    print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+def sharded_measure(args, users, items, B, precision, table_mode, world, rank, dev, barrier):
+    """N > 1: ShardedNCFEngine (tables row-sharded) on this rank's batches; also verifies the NCCL path against
+    the single-GPU engine on the gathered batch (parity_vs_single_gpu)."""
+    import torch
+    import torch.distributed as dist
+    from ncf_b200 import _lib
+    from ncf_b200.sharding import ShardedNCFEngine
+    lib = _lib.load()
+    N = B * S
+    parity, detail = verify_sharded(world, rank, dev)
+    model = build_model(1, 1, dev, precision)
+    eng = ShardedNCFEngine(model, users, items, lr=1e-3, weight_decay=1e-5, table_mode=table_mode)
+    nb = 4
+    dev_batches = make_batches(users, items, B, nb, 1234 + rank, device=dev)
+    host_batches = make_batches(users, items, B, nb, 4321 + rank, pin=True)
+    # two sets of device staging buffers: while step s runs, the ids of step s+1 are already on the device, so
+    # the engine can route them ahead (ShardedNCFEngine.train_step next_ids)
+    dev_in = [[torch.empty(N, dtype=torch.long, device=dev), torch.empty(N, dtype=torch.long, device=dev),
+               torch.empty(N, dtype=torch.float32, device=dev)] for _ in range(2)]
+    staged = {"slot": 0, "have": False}
+
+    def stage(slot, batch):
+        for d, h in zip(dev_in[slot], batch):
+            d.copy_(h, non_blocking=True)
+
+    def step_host(u, i, t, nxt=None):
+        cur = staged["slot"]
+        if not staged["have"]:
+            stage(cur, (u, i, t))
+        nids = None
+        if nxt is not None:
+            stage(cur ^ 1, nxt)
+            nids = tuple(dev_in[cur ^ 1][:2])
+        staged["slot"], staged["have"] = cur ^ 1, nxt is not None
+        return float(eng.train_step(*dev_in[cur], next_ids=nids).item())
+
+    def dev_step(s):
+        eng.train_step(*dev_batches[s % nb], next_ids=dev_batches[(s + 1) % nb][:2] if s + 1 < args.steps else None)
+    for s in range(args.warmup):
+        eng.train_step(*dev_batches[s % nb])
+    barrier()
+    l0 = int(lib.ncf_launch_count())
+    blocks = timed_blocks(dev_step, args.steps, barrier, world, dev, args.min_seconds)
+    launches = (int(lib.ncf_launch_count()) - l0) // len(blocks)
+    last_loss = float(eng.loss.item())
+    for s in range(3):
+        step_host(*host_batches[s % nb])
+
+    def e2e_step(s):
+        step_host(*host_batches[s % nb], nxt=host_batches[(s + 1) % nb] if s + 1 < args.steps else None)
+    e2e = wall_blocks(e2e_step, args.steps, barrier, world, dev, args.min_seconds / 2)
+    phases = profile_phases(eng, dev_batches, nb, 6)
+    ms_step = statistics.median(blocks) / args.steps
+    pk = peaks()
+    gbs = N * 4316.8 / ms_step / 1e6
+    roofline = {"kernel": "whole step per GPU on the SURVEY 8d basis (4,316.8 algorithmic B per sample; NVLink exchange not counted; "
+                          "the per-kernel pieces are measured by the N = 1 run)", "bound": "hbm", "achieved": gbs,
+                "peak": pk["hbm_gbs"], "unit": "GB/s per GPU", "frac": gbs / pk["hbm_gbs"], "traffic": None,
+                "peak_source": pk["source"] + " (copy)"}
+    del eng
+    torch.cuda.empty_cache()
+    return {"ms_block": statistics.median(blocks), "blocks": len(blocks), "e2e_ms_block": statistics.median(e2e),
+            "launches": launches, "last_loss": last_loss, "roofline": roofline, "parity_vs_single_gpu": parity,
+            "parity_detail": detail, "phases": phases}
+
+
+def profile_phases(eng, dev_batches, nb, steps):
+    """CUDA-event time of every phase of the sharded step (NCF_SHARD_PROFILE), a few extra steps after the timed region;
+    the per-phase synchronisation removes overlap, so the phases sum to more than a timed step."""
+    os.environ["NCF_SHARD_PROFILE"] = "1"
+    try:
+        if getattr(eng, "phase_ms", None):
+            eng.phase_ms.clear()
+        for s in range(steps):
+            eng.train_step(*dev_batches[s % nb])
+        prof = dict(getattr(eng, "phase_ms", {}) or {})
+    finally:
+        os.environ.pop("NCF_SHARD_PROFILE", None)
+    n = prof.pop("steps", 0)
+    return {k: v / n for k, v in prof.items()} if n else None
+
+
+def verify_sharded(world, rank, dev, steps=3):
+    """The REAL NCCL path against the single-GPU engine: 3 steps of ShardedNCFEngine over all_to_all_single / all_reduce,
+    fp32, dropout on; rank 0 runs NCFTrainEngine on the all-gathered batch with the SAME tables.  Loss within 2e-6, tables
+    within the bound the emulated-cluster test uses (tests/test_sharding.py)."""
+    import torch
+    import torch.distributed as dist
+    import ncf_b200
+    from ncf_b200.sharding import ShardedNCFEngine
+    U, I, Bv = 20011, 5003, 2048
+    torch.manual_seed(99)
+    tables = [(torch.rand(r, 64) * 2 - 1) * (1.0 / r) ** 0.5 for r in (U, I, U, I)]
+    model = build_model(1, 1, dev, "fp32")
+    model.dropout = 0.0            # per-rank Philox streams differ from one global stream: parity is checked without dropout
+    eng = ShardedNCFEngine(model, U, I, lr=1e-3, weight_decay=1e-5, table_mode="fused_dense_equiv", init_tables=tables)
+    batches = make_batches(U, I, Bv, steps, 555 + rank, device=dev)
+    single = None
+    if rank == 0:
+        ref_model = ncf_b200.AdvancedNCF(U, I, 5, 24, dropout=0.0)
+        sd = ref_model.state_dict()
+        for k, v in model.state_dict().items():
+            if "embedding_collection" not in k:
+                sd[k] = v.detach().cpu().clone()
+        for k, t in zip(("mf_embedding_collection.embedding_bags.user_id.weight", "mf_embedding_collection.embedding_bags.product_id.weight",
+                         "mlp_embedding_collection.embedding_bags.user_id.weight", "mlp_embedding_collection.embedding_bags.product_id.weight"), tables):
+            sd[k] = t.clone()
+        ref_model.load_state_dict(sd)
+        ref_model = ref_model.to(dev).train()
+        single = ncf_b200.NCFTrainEngine(ref_model, lr=1e-3, weight_decay=1e-5, table_mode="fused_dense_equiv")
+    worst_loss = 0.0
+    for s in range(steps):
+        u, i, t = batches[s]
+        loss = float(eng.train_step(u, i, t).item())
+        parts = [[torch.empty_like(x) for _ in range(world)] for x in (u, i, t)]
+        for p, x in zip(parts, (u, i, t)):
+            dist.all_gather(p, x)
+        if rank == 0:
+            ref = float(single.train_step(torch.cat(parts[0]), torch.cat(parts[1]), torch.cat(parts[2])).item())
+            worst_loss = max(worst_loss, abs(loss - ref))
+    got = eng.gather_tables()
+    ok, detail = True, None
+    if rank == 0:
+        worst_w, frac = 0.0, 0.0
+        for g, w in zip(got, single.model._table_params()):
+            d = (g - w.detach()).abs()
+            worst_w = max(worst_w, float(d.max()))
+            frac = max(frac, float((d > 8e-6).float().mean()))
+        ok = worst_loss <= 2e-6 and worst_w < 1.5e-3 and frac < 3e-3
+        detail = {"steps": steps, "world": world, "max_abs_loss_diff": worst_loss, "max_abs_table_diff": worst_w,
+                  "frac_table_elements_off_by_more_than_8e-6": frac, "shape": f"{U} x {I}, {Bv} interactions per rank, fp32, dropout 0"}
+        single.close()
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.broadcast(flag, 0)
+    del eng
+    torch.cuda.empty_cache()
+    return bool(flag.item()), detail
+
+
+def extra_blocks(args, world, rank, dev, precision, barrier):
+    """Secondary measurements the BASELINE metric names next to the c2 headline:
+      N = 1 : "scoring"  config[4] shape, 2,048 users x 10M items, top-100 (pairs/s, tensor fraction, e2e, top-k check)
+              "c3shard_embedding_path"  K1 / K6 on one GPU's 1/8 share of config[3] (tables HBM-resident)
+      N > 1 : "c3"  config[3] 100M x 10M row-sharded over the N GPUs: ms/step, samples/s, embedding-path fraction per GPU"""
+    import torch
+    import torch.distributed as dist
+    out = {}
+    pk = peaks()
+    if world == 1:
+        users, items, desc = SCORE_SHAPES["score"]
+        n, k, steps = 2048, 100, 5
+        r = score_measure(users, items, n, k, steps, 3, 1, 0, dev, 0.3, verify_users=16)
+        pairs_s = n * items * steps / (r["ms_block"] / 1e3)
+        tf = pairs_s * 128 / 1e12
+        out["scoring"] = {"metric": "scoring_samples_per_s", "value": pairs_s, "unit": "pairs/s", "users_per_s": pairs_s / items,
+                          "config": {"workload": "score: " + desc, "users_per_step": n, "items": items, "top_k": k},
+                          "ms_per_step": r["ms_block"] / steps,
+                          "e2e": {"value": n * items * steps / (r["e2e_ms_block"] / 1e3), "unit": "pairs/s",
+                                  "h2d_bytes_per_step": n * 8, "d2h_bytes_per_step": n * k * 12},
+                          "roofline": {"kernel": "score_tc_kernel", "bound": "tensor", "achieved": tf, "peak": pk["bf16_tflops"],
+                                       "unit": "TFLOP/s", "frac": tf / pk["bf16_tflops"], "traffic": None,
+                                       "peak_source": pk["source"] + " (bf16 burst); 128 flop per (user, item) pair"},
+                          "topk_verify": r.get("verify"), "gpu_launches": r["launches"],
+                          "cpu_baseline": None if args.no_cpu_baseline else cpu_score_rate(items, os.cpu_count() or 1)}
+        users3, items3, B3, desc3 = WORKLOADS["c3shard"]
+        m3 = build_model_on_device(users3, items3, dev, precision)
+        m3.configure_table_optimizer("fused_sparse")
+        m3._ensure_flat()
+        b3 = make_batches(users3, items3, B3, 1, 1234, device=dev)[0]
+        out["c3shard_embedding_path"] = stage_roofline(args, m3, b3, users3, items3, B3, precision, "fused_sparse", dev, 1.0, brief=True)
+        out["c3shard_embedding_path"]["workload"] = "c3shard: " + desc3
+        del m3
+        torch.cuda.empty_cache()
+    else:
+        from ncf_b200.sharding import ShardedNCFEngine
+        users3, items3, B3, desc3 = WORKLOADS["c3"]
+        N3 = B3 * S
+        per_gpu_gb = 2 * ((users3 + items3) // world) * 256 * 3 / 1e9
+        free = torch.cuda.mem_get_info(dev)[0] / 1e9
+        if per_gpu_gb + 12 > free:
+            if rank == 0:
+                out["c3"] = {"unavailable": f"needs {per_gpu_gb:.0f} GB per GPU for tables + Adam state, {free:.0f} GB free"}
+            return out
+        model = build_model(1, 1, dev, precision)
+        eng = ShardedNCFEngine(model, users3, items3, lr=1e-3, weight_decay=1e-5, table_mode="fused_sparse")
+        nb = 4
+        batches = make_batches(users3, items3, B3, nb, 777 + rank, device=dev)
+        for s in range(3):
+            eng.train_step(*batches[s % nb])
+        barrier()
+        steps = max(5, args.steps // 2)
+        blocks = timed_blocks(lambda s: eng.train_step(*batches[s % nb], next_ids=batches[(s + 1) % nb][:2] if s + 1 < steps else None),
+                              steps, barrier, world, dev, 0.5)
+        phases = profile_phases(eng, batches, nb, 6)
+        ms = statistics.median(blocks) / steps
+        t = torch.tensor([phases.get("owner rows", 0.0) + phases.get("owner update", 0.0)] if phases else [0.0], device=dev,
+                         dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        emb_ms = float(t[0])
+        emb_bytes = B3 * (BYTES_FWD_PER_INTERACTION + BYTES_BWD_PER_INTERACTION)      # per GPU: it owns 1/world of every batch's rows
+        if rank == 0:
+            out["c3"] = {"workload": "c3: " + desc3, "n_gpus": world, "ms_per_step": ms, "samples_per_s": world * N3 / (ms / 1e3),
+                         "interactions_per_step_per_gpu": B3, "table_update": "fused_sparse", "tables_gb_per_gpu": per_gpu_gb,
+                         "embedding_path": {"what": "owner-side gather + LayerNorm (ncf_shard_owner_rows) and segment-sum + LayerNorm "
+                                                    "backward + Adam (ncf_shard_owner_update), max over ranks, timed phase by phase",
+                                            "ms": emb_ms, "algorithmic_bytes_per_gpu": emb_bytes,
+                                            "achieved": emb_bytes / emb_ms / 1e6 if emb_ms else None, "unit": "GB/s per GPU",
+                                            "peak": pk["hbm_gbs"], "frac": emb_bytes / emb_ms / 1e6 / pk["hbm_gbs"] if emb_ms else None,
+                                            "tables": "HBM-resident"},
+                         "whole_step_survey_basis": {"achieved": N3 * 4316.8 / ms / 1e6, "unit": "GB/s per GPU", "peak": pk["hbm_gbs"],
+                                                     "frac": N3 * 4316.8 / ms / 1e6 / pk["hbm_gbs"]},
+                         "sharded_phases_ms": phases}
+        del eng
+        torch.cuda.empty_cache()
+    return out
 
 
 if __name__ == "__main__":

@@ -39,7 +39,7 @@ def _close(got, ref, rtol=RTOL, what=""):
 def test_library_loaded_and_native():
     import ncf_b200
     lib = ncf_b200.load_library()
-    assert lib.ncf_version() == 1
+    assert lib.ncf_version() == 2
 
 
 def test_golden_predictions_csv_on_gpu():
