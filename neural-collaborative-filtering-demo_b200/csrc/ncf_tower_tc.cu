@@ -1420,6 +1420,346 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_tc_bwd_kernel(MlpBwdArgs A
 }
 
 // =============================================================================================
+// MLP tower backward, part 1, second version (default; NCF_MLP_BWD=1 selects the kernel above).  Same GEMM chain,
+// leaner CUDA-core epilogue - the first version spends 38 instructions per element, almost half of them moving bits:
+//   * pass B leaves dg = keep * dy * gamma (in place, over dy) and xhat in TENSOR MEMORY, so pass C is two FMAs, a
+//     compare-select and the bf16 pack per element: the saved r tile is read once, not twice, and neither unpacked nor
+//     sign-tested again.  (relu' is taken from xhat > -mean * rstd, which is r > 0 up to fp32 rounding of r * rstd.)
+//   * the column sums for d gamma / d beta (and the 64-wide layer's bias) go through a per-warp 2 KB shared-memory
+//     transposition scratch instead of a 5-stage shuffle butterfly (2 FSEL + SHFL + FADD per element and stage): the
+//     lane = row values are stored with 128-bit stores (XOR-swizzled 16-byte chunks, conflict-free), lane = (column,
+//     row half) reads 16 rows back, and the partial sums stay in REGISTERS across all tiles of the CTA - no shuffles,
+//     no shared-memory atomics in the loop.
+// Tensor-memory map (512 columns): dy2 -> dg2 [0,128) | xhat2 [128,256) | dy1 -> dg1 [256,512) | xhat1 [0,256) |
+// layer 3: dg3 [0,64), xhat3 [64,128) | da [0,64).  Every region is dead before its next writer is issued (one tile in flight).
+// =============================================================================================
+constexpr uint32_t SM2B_Z = SM_W2 + 64 * 128 * 2;                       // dz tile (next GEMM's A operand)   64 KB
+constexpr uint32_t SM2B_SCR = SM2B_Z + 128 * 256 * 2;                   // 16 warps x 2 KB transposition scratch
+constexpr uint32_t SM2B_PAR = SM2B_SCR + 16 * 2048;
+constexpr uint32_t SM2B_STAT = SM2B_PAR + PAR_COUNT * 4;                // [128][4][2] floats
+constexpr uint32_t SM2B_ACC = SM2B_STAT + 128 * MLP_NH * 2 * 4;
+constexpr uint32_t SM2B_TOTAL = SM2B_ACC + ACC_COUNT * 4;
+static_assert(SM2B_TOTAL <= 232448, "mlp_tc_bwd2: shared memory");
+
+// per-warp scratch [32 rows][16 cols] fp32; the 16-byte chunk j of row r sits at position j ^ ((r >> 1) & 3)
+struct ColScratch {
+  float* base;          // the CTA's dynamic shared memory as floats (the compiler keeps shared-window addressing)
+  uint32_t st[4];       // word index of this lane's (= row's) four chunks
+  uint32_t ld[2][4];    // read bases (word index): [parity of the step][(step >> 1) & 3]
+  __device__ __forceinline__ void init(float* smem_f, uint32_t word0, int lane) {
+    base = smem_f;
+    const int sw = (lane >> 1) & 3;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) st[j] = word0 + lane * 16 + ((j ^ sw) << 2);
+    const int c = lane & 15, hf = lane >> 4;
+    // step i: the lower half warp reads row i, the upper one row 16 + (i ^ 1) (opposite bank half: no conflicts)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t off = (((c >> 2) ^ k) << 2) + (c & 3);
+      ld[0][k] = word0 + (hf ? 17 * 16 : 0) + off;      // even steps
+      ld[1][k] = word0 + (hf ? 15 * 16 : 0) + off;      // odd steps
+    }
+  }
+  __device__ __forceinline__ void put(const float (&v)[16]) const {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      *reinterpret_cast<float4*>(base + st[j]) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  }
+  // sum over this lane's 16 rows of column (lane & 15)
+  __device__ __forceinline__ float get() const {
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float x = *reinterpret_cast<volatile const float*>(base + ld[i & 1][(i >> 1) & 3] + i * 16);
+      if (i & 1) s1 += x;
+      else s0 += x;
+    }
+    return s0 + s1;
+  }
+};
+
+// one layer of the chain for this thread's row and column part, 16 columns at a time
+template <int C, bool FROM_TMEM>
+__device__ __forceinline__ void mlp_bwd2_layer(uint32_t tmem_dg, uint32_t tmem_xh, float dml, int q, int h, int lane, int rt,
+                                               const uint8_t* __restrict__ r_img, uint4 (&rw)[2], const float* __restrict__ gam,
+                                               float* s_stat, const ColScratch& cs, float* accd, float* acct, float* accz,
+                                               uint8_t* dztile, uint8_t* __restrict__ dz_img, const float* __restrict__ st_tile) {
+  constexpr int PART = C / MLP_NH, NSUB = PART / 16;
+  const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+  const uint32_t a_dg = tmem_dg + lane_addr + h * PART, a_xh = tmem_xh + lane_addr + h * PART;
+  const float2 ms = *reinterpret_cast<const float2*>(st_tile + rt * 2);
+  const float rstd = ms.y, nmr = -ms.x * ms.y;
+  float s1p[2] = {0.f, 0.f}, s2p[2] = {0.f, 0.f};
+  // ---- pass B: dg, xhat -> tensor memory; row sums; column sums of d and d * xhat ----
+#pragma unroll
+  for (int sub = 0; sub < NSUB; ++sub) {
+    const int c0 = h * PART + sub * 16;
+    uint4 rn[2];
+    if (sub + 1 < NSUB) {      // next 16 saved values of the row: two 16-byte pieces, 128 bytes apart in the tile image
+      const uint8_t* p = r_img + tile_off(rt, c0 + 16, C);
+      rn[0] = __ldg(reinterpret_cast<const uint4*>(p));
+      rn[1] = __ldg(reinterpret_cast<const uint4*>(p + 128));
+    }
+    float d[16], xh[16], t[16];
+    if (FROM_TMEM) {
+      tmem_ld16(a_dg + sub * 16, d);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) d[i] = dml;      // layer 3: see mlp_bwd_layer
+    }
+    const uint32_t w8[8] = {rw[0].x, rw[0].y, rw[0].z, rw[0].w, rw[1].x, rw[1].y, rw[1].z, rw[1].w};
+#pragma unroll
+    for (int i2 = 0; i2 < 8; ++i2) {
+      const uint32_t w = w8[i2], lo = w << 16;
+      xh[2 * i2] = fmaf(fabsf(__uint_as_float(lo)), rstd, nmr);
+      xh[2 * i2 + 1] = fmaf(fabsf(__uint_as_float(w & 0xffff0000u)), rstd, nmr);
+      d[2 * i2] = (int32_t)lo < 0 ? 0.f : d[2 * i2];
+      d[2 * i2 + 1] = (int32_t)w < 0 ? 0.f : d[2 * i2 + 1];
+    }
+#pragma unroll
+    for (int i4 = 0; i4 < 4; ++i4) {
+      const float4 g4 = *reinterpret_cast<const float4*>(gam + c0 + 4 * i4);
+      const float gg[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int i = 4 * i4 + k;
+        const float dg = d[i] * gg[k];
+        s1p[k & 1] += dg;
+        s2p[k & 1] = fmaf(dg, xh[i], s2p[k & 1]);
+        t[i] = dg;
+      }
+    }
+    tmem_st16(a_dg + sub * 16, t);
+    tmem_st16(a_xh + sub * 16, xh);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) t[i] = d[i] * xh[i];
+    cs.put(d);
+    __syncwarp();
+    accd[sub] += cs.get();
+    __syncwarp();
+    cs.put(t);
+    __syncwarp();
+    acct[sub] += cs.get();
+    __syncwarp();
+    if (sub + 1 < NSUB) {
+      rw[0] = rn[0];
+      rw[1] = rn[1];
+    }
+  }
+  tmem_st_wait();
+  s_stat[(rt * MLP_NH + h) * 2 + 0] = s1p[0] + s1p[1];
+  s_stat[(rt * MLP_NH + h) * 2 + 1] = s2p[0] + s2p[1];
+  quarter_sync(q);          // only the four warps that share these 32 rows exchange their sums
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int k = 0; k < MLP_NH; ++k) {
+    s1 += s_stat[(rt * MLP_NH + k) * 2 + 0];
+    s2 += s_stat[(rt * MLP_NH + k) * 2 + 1];
+  }
+  const float nm2 = -s2 * (1.0f / C), nm1r = -s1 * (1.0f / C) * rstd;
+  // ---- pass C: dz = relu' * rstd * (dg - mean(dg) - xhat * mean(dg * xhat)) ----
+#pragma unroll
+  for (int sub = 0; sub < NSUB; ++sub) {
+    const int c0 = h * PART + sub * 16;
+    float dg[16], xh[16];
+    tmem_ld16(a_dg + sub * 16, dg);
+    tmem_ld16(a_xh + sub * 16, xh);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float dr = fmaf(fmaf(xh[i], nm2, dg[i]), rstd, nm1r);
+      dg[i] = xh[i] > nmr ? dr : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const uint4 pk = make_uint4(pack_bf16(dg[8 * j], dg[8 * j + 1]), pack_bf16(dg[8 * j + 2], dg[8 * j + 3]),
+                                  pack_bf16(dg[8 * j + 4], dg[8 * j + 5]), pack_bf16(dg[8 * j + 6], dg[8 * j + 7]));
+      const uint32_t off = tile_off(rt, c0 + 8 * j, C);
+      *reinterpret_cast<uint4*>(dztile + off) = pk;
+      *reinterpret_cast<uint4*>(dz_img + off) = pk;
+    }
+    if constexpr (C == 64) {      // the 256- and 128-wide layers get their bias gradient from the wgrad kernel's ones-GEMM
+      cs.put(dg);
+      __syncwarp();
+      accz[sub] += cs.get();
+      __syncwarp();
+    }
+  }
+}
+
+__global__ void __launch_bounds__(MLP_THREADS, 1) mlp_tc_bwd2_kernel(MlpBwdArgs A) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q = warp & 3, h = warp >> 2;
+  float* par = reinterpret_cast<float*>(smem + SM2B_PAR);
+  float* s_stat = reinterpret_cast<float*>(smem + SM2B_STAT);
+  float* s_acc = reinterpret_cast<float*>(smem + SM2B_ACC);
+  const float* P = A.dense;
+
+  load_weight_image<256, 64>(smem + SM_W0, P + NCF_OFF(NCF_P_MLP0_W), K0, tid, MLP_THREADS);
+  load_weight_image<128, 256>(smem + SM_W1, P + NCF_OFF(NCF_P_MLP1_W), H1, tid, MLP_THREADS);
+  load_weight_image<64, 128>(smem + SM_W2, P + NCF_OFF(NCF_P_MLP2_W), H2, tid, MLP_THREADS);
+  const float sc0 = A.rng[0].thresh ? A.rng[0].scale : 1.f, sc1 = A.rng[1].thresh ? A.rng[1].scale : 1.f,
+              sc2 = A.rng[2].thresh ? A.rng[2].scale : 1.f;
+  for (int i = tid; i < 256; i += MLP_THREADS) {
+    par[PAR_G0 + i] = P[NCF_OFF(NCF_P_LN0_W) + i] * sc0;
+    if (i < 128) par[PAR_G1 + i] = P[NCF_OFF(NCF_P_LN1_W) + i] * sc1;
+    if (i < 64) {
+      par[PAR_WOUT + i] = P[NCF_OFF(NCF_P_MLP_OUT_W) + i];
+      par[PAR_G2 + i] = P[NCF_OFF(NCF_P_LN2_W) + i] * sc2 * P[NCF_OFF(NCF_P_MLP_OUT_W) + i];     // see mlp_bwd_layer<64, false>
+    }
+  }
+  for (int i = tid; i < ACC_COUNT; i += MLP_THREADS) s_acc[i] = 0.f;
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_slot, 512);
+  fence_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t sW0 = smem_addr(smem + SM_W0), sW1 = smem_addr(smem + SM_W1), sW2 = smem_addr(smem + SM_W2);
+  const uint32_t sZ = smem_addr(smem + SM2B_Z);
+  uint8_t* ztile = smem + SM2B_Z;
+  ColScratch cs;
+  cs.init(reinterpret_cast<float*>(smem), (SM2B_SCR + warp * 2048) / 4, lane);
+  // column-sum partials of this lane = (column lane & 15 of each 16-column group, row half lane >> 4), all tiles
+  float ad1[4] = {0.f, 0.f, 0.f, 0.f}, at1[4] = {0.f, 0.f, 0.f, 0.f}, ad2[2] = {0.f, 0.f}, at2[2] = {0.f, 0.f}, ad3[1] = {0.f},
+        at3[1] = {0.f}, az3[1] = {0.f};
+  uint32_t phase = 0;
+  const int rt = q * 32 + lane;
+
+  const int64_t ntiles = (A.N + TCM_ROWS - 1) / TCM_ROWS;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t row0 = tile * TCM_ROWS;
+    const int64_t avail = min((int64_t)TCM_ROWS, A.N - row0);
+    const int64_t grow = row0 + rt;
+    const bool live = rt < avail;
+    const uint8_t* r1i = reinterpret_cast<const uint8_t*>(A.r1) + tile * (128 * 256 * 2);
+    const uint8_t* r2i = reinterpret_cast<const uint8_t*>(A.r2) + tile * (128 * 128 * 2);
+    const uint8_t* r3i = reinterpret_cast<const uint8_t*>(A.r3) + tile * (128 * 64 * 2);
+    uint8_t* z1i = reinterpret_cast<uint8_t*>(A.dz1) + tile * (128 * 256 * 2);
+    uint8_t* z2i = reinterpret_cast<uint8_t*>(A.dz2) + tile * (128 * 128 * 2);
+    uint8_t* z3i = reinterpret_cast<uint8_t*>(A.dz3) + tile * (128 * 64 * 2);
+    if (tid == 0) {       // pull the NEXT tile's saved tensors into L2 while this one is processed
+      const int64_t nt = tile + gridDim.x;
+      if (nt < ntiles) {
+        bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(A.r1) + nt * (128 * 256 * 2), 128 * 256 * 2);
+        bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(A.r2) + nt * (128 * 128 * 2), 128 * 128 * 2);
+        bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(A.r3) + nt * (128 * 64 * 2), 128 * 64 * 2);
+      }
+    }
+    uint4 rw3[2], rw2[2], rw1[2];
+    auto load16 = [&](const uint8_t* img, int C, int c0, uint4 (&w)[2]) {
+      const uint8_t* p = img + tile_off(rt, c0, C);
+      w[0] = __ldg(reinterpret_cast<const uint4*>(p));
+      w[1] = __ldg(reinterpret_cast<const uint4*>(p + 128));
+    };
+    load16(r3i, 64, h * 16, rw3);
+    load16(r2i, 128, h * 32, rw2);      // consumed after the first MMA: its latency hides behind layer 3
+    mlp_bwd2_layer<64, false>(tmem + 0, tmem + 64, live ? A.d_mlp_pred[grow] : 0.f, q, h, lane, rt, r3i, rw3, par + PAR_G2, s_stat, cs,
+                              ad3, at3, az3, ztile, z3i, A.st3 + tile * 256);
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+      fence_after_sync();   // dy2[128x128] = dz3[128x64] . W2[64x128]
+      issue_gemm(tmem + 0, sZ, 128, 64 * 16, 256, sW2, 128 * 16, 128, 2 * 128 * 16, make_idesc(128, 128, false, true), 4, false);
+      mma_commit(&bar);
+    }
+    load16(r1i, 256, h * 64, rw1);      // consumed after the second MMA
+    mbar_wait(&bar, phase);             // every warp polls for itself
+    phase ^= 1;
+    fence_after_sync();
+    mlp_bwd2_layer<128, true>(tmem + 0, tmem + 128, 0.f, q, h, lane, rt, r2i, rw2, par + PAR_G1, s_stat, cs, ad2, at2, nullptr, ztile,
+                              z2i, A.st2 + tile * 256);
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+      fence_after_sync();   // dy1[128x256] = dz2[128x128] . W1[128x256]
+      issue_gemm(tmem + 256, sZ, 128, 128 * 16, 256, sW1, 256 * 16, 128, 2 * 256 * 16, make_idesc(128, 256, false, true), 8, false);
+      mma_commit(&bar);
+    }
+    mbar_wait(&bar, phase);
+    phase ^= 1;
+    fence_after_sync();
+    mlp_bwd2_layer<256, true>(tmem + 256, tmem + 0, 0.f, q, h, lane, rt, r1i, rw1, par + PAR_G0, s_stat, cs, ad1, at1, nullptr, ztile,
+                              z1i, A.st1 + tile * 256);
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+      fence_after_sync();   // da[128x64] = dz1[128x256] . W0[256x64]
+      issue_gemm(tmem + 0, sZ, 128, 256 * 16, 256, sW0, 64 * 16, 128, 2 * 64 * 16, make_idesc(128, 64, false, true), 16, false);
+      mma_commit(&bar);
+    }
+    mbar_wait(&bar, phase);
+    phase ^= 1;
+    fence_after_sync();
+    {
+      float v[16];
+      tmem_ld16(tmem + 0 + ((uint32_t)(q * 32) << 16) + h * 16, v);
+      if (live) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          st_row4(A.da, grow, h * 16 + 4 * j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]), A.da_bf16);
+      }
+    }
+    fence_before_sync();
+    __syncthreads();
+  }
+  // the register partials of all warps -> s_acc ([dgamma | dbeta | dbias] per layer, as the first version keeps them)
+  {
+    const int c = lane & 15;
+#pragma unroll
+    for (int sub = 0; sub < 4; ++sub) {
+      atomicAdd(s_acc + ACC_L0 + h * 64 + sub * 16 + c, at1[sub]);
+      atomicAdd(s_acc + ACC_L0 + 256 + h * 64 + sub * 16 + c, ad1[sub]);
+    }
+#pragma unroll
+    for (int sub = 0; sub < 2; ++sub) {
+      atomicAdd(s_acc + ACC_L1 + h * 32 + sub * 16 + c, at2[sub]);
+      atomicAdd(s_acc + ACC_L1 + 128 + h * 32 + sub * 16 + c, ad2[sub]);
+    }
+    atomicAdd(s_acc + ACC_L2 + h * 16 + c, at3[0]);
+    atomicAdd(s_acc + ACC_L2 + 64 + h * 16 + c, ad3[0]);
+    atomicAdd(s_acc + ACC_L2 + 128 + h * 16 + c, az3[0]);
+  }
+  __syncthreads();
+  float* dg = A.dense_grad;
+  for (int i = tid; i < ACC_COUNT; i += MLP_THREADS) {
+    int64_t off;
+    int k = i;
+    float sc;          // d gamma / d beta sums were taken without the dropout scale; the bias sums carry it already
+    if (k < ACC_L1) {
+      if (k >= 512) continue;        // bias of the 256-wide layer: wgrad kernel
+      off = k < 256 ? NCF_OFF(NCF_P_LN0_W) + k : NCF_OFF(NCF_P_LN0_B) + (k - 256);
+      sc = sc0;
+    } else if (k < ACC_L2) {
+      k -= ACC_L1;
+      if (k >= 256) continue;        // bias of the 128-wide layer: wgrad kernel
+      off = k < 128 ? NCF_OFF(NCF_P_LN1_W) + k : NCF_OFF(NCF_P_LN1_B) + (k - 128);
+      sc = sc1;
+    } else {
+      k -= ACC_L2;
+      off = k < 64 ? NCF_OFF(NCF_P_LN2_W) + k : k < 128 ? NCF_OFF(NCF_P_LN2_B) + (k - 64) : NCF_OFF(NCF_P_MLP2_B) + (k - 128);
+      sc = k < 128 ? sc2 * par[PAR_WOUT + (k & 63)] : 1.f;
+      if (k < 64)
+        atomicAdd(dg + NCF_OFF(NCF_P_MLP_OUT_W) + k,
+                  sc2 * fmaf(P[NCF_OFF(NCF_P_LN2_W) + k], s_acc[i], P[NCF_OFF(NCF_P_LN2_B) + k] * s_acc[i + 64]));
+    }
+    atomicAdd(dg + off, s_acc[i] * sc);
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+// =============================================================================================
 // MLP tower backward, part 2: weight gradients.  Per 128-row tile the saved tiles are read as MN-major
 // operands (K = the 128 rows) and accumulated over ALL tiles of the CTA in TMEM:
 //   dW2^T [128 x 64] += y2^T . dz3      dW1 [128 x 256] += dz2^T . y1      dW0 [256 x 64] += dz1^T . a
@@ -1579,6 +1919,7 @@ int mlp_tc_backward(const ncf_run_cfg& cfg, const float* dense, float* dense_gra
   static bool configured = false;
   if (!configured) {
     NCF_CUDA(cudaFuncSetAttribute(mlp_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMB_TOTAL));
+    NCF_CUDA(cudaFuncSetAttribute(mlp_tc_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM2B_TOTAL));
     NCF_CUDA(cudaFuncSetAttribute(mlp_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMW_TOTAL));
     configured = true;
   }
@@ -1601,7 +1942,9 @@ int mlp_tc_backward(const ncf_run_cfg& cfg, const float* dense, float* dense_gra
   B.dz3 = (__nv_bfloat16*)w.dz3b;
   B.N = N;
   for (int l = 0; l < 3; ++l) B.rng[l] = make_rng(cfg, 1 + l);
-  mlp_tc_bwd_kernel<<<grid, MLP_THREADS, SMB_TOTAL, st>>>(B);
+  static const int bwd_variant = getenv("NCF_MLP_BWD") ? atoi(getenv("NCF_MLP_BWD")) : 2;     // A/B switch
+  if (bwd_variant == 1) mlp_tc_bwd_kernel<<<grid, MLP_THREADS, SMB_TOTAL, st>>>(B);
+  else mlp_tc_bwd2_kernel<<<grid, MLP_THREADS, SM2B_TOTAL, st>>>(B);
   NCF_LAUNCH_CHECK();
   MlpWgradArgs W{};
   W.a_img = (const __nv_bfloat16*)w.a_img;
