@@ -336,6 +336,47 @@ NCF_API int ncf_shard_owner_update(const ncf_adam_cfg* adam, const ncf_tables* l
                            float* dense_grad, int32_t side, const int64_t* local_ids, int64_t n,
                            const float* grad_rows, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* ---- row-sharded step over PEER MEMORY (NVLink / NVSwitch, one-sided) ------------------------------------------
+ * SURVEY section 5 "stretch design": every rank maps its peers' table shards and gradient receive buffers into its own
+ * address space (CUDA IPC: ncf_ipc_open), so the two bulk exchanges of a step need no collective and no owner-side
+ * kernel in the forward direction:
+ *   forward   the requester's gather kernel PULLS the raw rows of its distinct ids straight from the owners' HBM with
+ *             128-bit loads and applies the (row-local) LayerNorm itself                       ncf_shard_pull_rows
+ *   backward  the requester's sorted segment-sum kernel PUSHES every summed gradient row (and its local id) into the
+ *             owner's receive buffer with 128-bit stores, fused into the kernel that forms it    ncf_shard_backward(plan)
+ *   owner     after a cross-rank barrier (the step's next collective) the owner runs ncf_shard_owner_update on its
+ *             receive buffer.
+ * The per-step plan lives in DEVICE memory (the host fills a pinned copy and uploads it on the stream): */
+#define NCF_MAX_WORLD 16
+typedef struct ncf_shard_plan {
+  int32_t world, rank;
+  int64_t begin[2][NCF_MAX_WORLD + 1];     /* [side][o]: first of MY distinct ids (owner-major order) that owner o holds */
+  const float* tab[NCF_MAX_WORLD][4];      /* peers' table shards (NCF_T_* order), pointers valid on THIS device */
+  float* push_rows[2][NCF_MAX_WORLD];      /* [side][o]: owner o's receive buffer where my segment starts ([n,128] fp32) */
+  int64_t* push_ids[2][NCF_MAX_WORLD];     /* likewise for the local ids of those rows */
+} ncf_shard_plan;
+
+/* CUDA IPC plumbing for the plan's peer pointers: the exporter passes (handle of the allocation that contains ptr, offset
+ * of ptr inside it) to its peers by any host-side channel; ncf_ipc_open maps it (peer access enabled) and returns
+ * base + offset; ncf_ipc_close takes what ncf_ipc_open returned.  handle: 64 bytes (cudaIpcMemHandle_t). */
+NCF_API int ncf_ipc_export(const void* ptr, void* handle_out, int64_t* offset_out);
+NCF_API int ncf_ipc_open(const void* handle, int64_t offset, void** ptr_out);
+NCF_API int ncf_ipc_close(void* ptr);
+
+/* requester: rows [n,128] = [mf_norm(T_mf[id]) | mlp_norm(T_mlp[id])] for its n = plan->begin[side][world] distinct
+ * ids of one side, each row read from its owner's shard through plan->tab (local_ids: ncf_shard_route's output for the
+ * side, owner-major).  plan: device pointer. */
+NCF_API int ncf_shard_pull_rows(const ncf_shard_plan* plan, const float* dense, int32_t side, const int64_t* local_ids,
+                        int64_t n, float* rows, void* stream);
+
+/* ncf_shard_backward with the gradient exchange fused in: instead of grad_rows_u / grad_rows_i the summed row of every
+ * distinct id is stored at plan->push_rows[side][owner] + (slot - plan->begin[side][owner]) * 128 and its local id at
+ * plan->push_ids (route_ws is required: the routing of ncf_shard_route for this batch; local_ids = its output). */
+NCF_API int ncf_shard_backward_push(const ncf_run_cfg* cfg, const float* dense, float* dense_grad,
+                            const float* rows_u, const float* rows_i, const int64_t* pos_u, const int64_t* pos_i,
+                            int64_t N, const float* grad_out, const ncf_shard_plan* plan, const int64_t* local_ids,
+                            const void* route_ws, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---- input pipeline on the device --------------------------------------------
  * SheetzDataset.__getitem__ + _sample_negative (data_prep.py:134-161, 181-212) + collate_recommender_batch
  * (:230-320) for B positive interactions: writes the key-major id columns user_ids / item_ids [B*S] (row

@@ -41,6 +41,16 @@ class Tables(C.Structure):
                 ("touched", C.c_void_p * 2), ("rows_user", C.c_int64), ("rows_item", C.c_int64), ("status", C.c_void_p)]
 
 
+MAX_WORLD = 16
+
+
+class ShardPlan(C.Structure):
+    """ncf_shard_plan of include/ncf_b200.h (the per-step plan of the one-sided sharded step; lives in device memory)."""
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("begin", (C.c_int64 * (MAX_WORLD + 1)) * 2),
+                ("tab", (C.c_void_p * 4) * MAX_WORLD), ("push_rows", (C.c_void_p * MAX_WORLD) * 2),
+                ("push_ids", (C.c_void_p * MAX_WORLD) * 2)]
+
+
 STATUS_WORDS = 4
 STATUS_NAMES = ("user id outside [0, num_users)", "product id outside [0, num_products)", "hour outside [0, 24)")
 
@@ -127,6 +137,11 @@ _SIGS = {
     "ncf_shard_owner_rows": (C.c_int, [C.POINTER(Tables), _P, _I32, _P, _I64, _P, _P]),
     "ncf_shard_forward": (C.c_int, [C.POINTER(RunCfg), _P, _P, _P, _P, _P, _I64, _P, _P, _I64, _P]),
     "ncf_shard_backward": (C.c_int, [C.POINTER(RunCfg), _P, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _I64, _P]),
+    "ncf_ipc_export": (C.c_int, [_P, _P, C.POINTER(C.c_int64)]),
+    "ncf_ipc_open": (C.c_int, [_P, _I64, C.POINTER(C.c_void_p)]),
+    "ncf_ipc_close": (C.c_int, [_P]),
+    "ncf_shard_pull_rows": (C.c_int, [_P, _P, _I32, _P, _I64, _P, _P]),
+    "ncf_shard_backward_push": (C.c_int, [C.POINTER(RunCfg), _P, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _I64, _P]),
     "ncf_shard_route_workspace_bytes": (_I64, [_I64]),
     "ncf_shard_route": (C.c_int, [_P, _P, _I64, _I64, _I64, _I32, _P, _P, _P, _P, _I64, _P]),
     "ncf_sample_batch": (C.c_int, [_P, _P, _I64, _I32, _P, _I64, _P, _P, C.c_uint64, C.c_uint64, _P, _P, _P, _P]),

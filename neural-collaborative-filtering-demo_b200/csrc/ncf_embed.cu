@@ -267,6 +267,9 @@ struct EmbBwdArgs {
   const int64_t* own_pos;
   float* out_rows;                // phase 2 output mode: [n_unique,128] summed upstream row per unique id, no update
   const int32_t* out_slot;        // [N] unique-id index of every sorted position
+  const ncf_shard_plan* push;     // output mode over peer memory: rows (and ids) go to the owners' receive buffers
+  const int64_t* push_local;      // [n_unique] local id of every distinct id of this side (ncf_shard_route)
+  int32_t push_side;
   const int64_t* other_ids;       // other side's ids, original sample order
   int64_t other_nrows;            // rows of the other side's table (ids are clamped into it)
   const uint32_t* sorted_ids;     // this side's ids, sorted
@@ -500,8 +503,9 @@ __global__ void __launch_bounds__(EB_THREADS, 3) emb_bwd_phase2_kernel(EmbBwdArg
       L.m = make_float4(0, 0, 0, 0);
       L.v = L.m;
       L.w = L.m;
-      if (!A.out_rows) L.w = ld4(A.w[half] + o);
-      if (adam && !A.out_rows) {
+      const bool output_mode = A.out_rows || A.push;
+      if (!output_mode) L.w = ld4(A.w[half] + o);
+      if (adam && !output_mode) {
         L.m = ld4(A.m[half] + o);
         L.v = ld4(A.v[half] + o);
       }
@@ -557,6 +561,17 @@ __global__ void __launch_bounds__(EB_THREADS, 3) emb_bwd_phase2_kernel(EmbBwdArg
           }
           cs += 4 * EB_CHUNK;
         }
+      }
+      if (A.push) {            // sharded requester, one-sided: the summed upstream row goes straight into its OWNER's
+        // receive buffer over NVLink (128-bit stores to the peer-mapped pointer), at this rank's segment of that buffer
+        const int64_t slot = A.out_slot[p0 + i];
+        const int world = A.push->world;
+        int o = 0;
+        while (o + 1 < world && slot >= __ldg(&A.push->begin[A.push_side][o + 1])) ++o;
+        const int64_t r = slot - __ldg(&A.push->begin[A.push_side][o]);
+        st4(A.push->push_rows[A.push_side][o] + r * 2 * D + half * D + 4 * l16, acc);
+        if (lane == 0) A.push->push_ids[A.push_side][o][r] = A.push_local[slot];
+        continue;
       }
       if (A.out_rows) {        // sharded requester: the summed upstream row of this unique id goes to the exchange buffer
         st4(A.out_rows + (int64_t)A.out_slot[p0 + i] * 2 * D + half * D + 4 * l16, acc);
@@ -848,6 +863,9 @@ static int run_emb_bwd(const ncf_adam_cfg* adam, const ncf_tables* T, const floa
   A.other_rows = A.own_rows = nullptr;
   A.other_pos = A.own_pos = nullptr;
   A.out_rows = nullptr;
+  A.push = nullptr;
+  A.push_local = nullptr;
+  A.push_side = 0;
   A.out_slot = nullptr;
   A.upstream = upstream;
   A.other_ids = other_ids;
@@ -990,6 +1008,12 @@ int emb_bwd_both(const ncf_adam_cfg* adam, const ncf_tables* T, const float* den
     A.other_rows = A.own_rows = nullptr;
     A.other_pos = A.own_pos = nullptr;
     A.out_rows = nullptr;
+    A.push = nullptr;
+    A.push_local = nullptr;
+    A.push_side = 0;
+  A.push = nullptr;
+  A.push_local = nullptr;
+  A.push_side = 0;
     A.out_slot = nullptr;
     A.upstream = nullptr;
     A.other_ids = side ? user_ids : item_ids;
@@ -1140,7 +1164,8 @@ int shard_route(const int64_t* user_ids, const int64_t* item_ids, int64_t N, int
 // d mf_output.weight.  route_ws = the buffer shard_route filled for the same batch.
 int shard_requester_grads(const float* dense, float* dense_grad, const float* rows_u, const float* rows_i, const int64_t* pos_u,
                           const int64_t* pos_i, int64_t N, const float* d_mf, const float* dxu, const float* dxp,
-                          const void* route_ws, float* gu, float* gi, void* emb_ws, int64_t emb_ws_bytes, cudaStream_t st) {
+                          const void* route_ws, float* gu, float* gi, void* emb_ws, int64_t emb_ws_bytes, cudaStream_t st,
+                          const ncf_shard_plan* plan, const int64_t* local_ids) {
   if (N == 0) return NCF_OK;
   RouteWs r = carve_route_ws(const_cast<void*>(route_ws), N);
   EmbWs w = carve_emb_ws(emb_ws, N);
@@ -1164,6 +1189,9 @@ int shard_requester_grads(const float* dense, float* dense_grad, const float* ro
     A.own_pos = side ? pos_i : pos_u;
     A.out_rows = side ? gi : gu;
     A.out_slot = r.slot + (side ? N : 0);
+    A.push = plan;
+    A.push_local = local_ids ? local_ids + (side ? N : 0) : nullptr;
+    A.push_side = side;
     A.dense = dense;
     A.dense_grad = dense_grad;
     A.acc_buf = w.acc_buf;

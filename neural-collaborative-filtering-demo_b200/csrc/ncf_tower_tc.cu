@@ -1483,12 +1483,11 @@ template <int C, bool FROM_TMEM>
 __device__ __forceinline__ void mlp_bwd2_layer(uint32_t tmem_dg, uint32_t tmem_xh, float dml, int q, int h, int lane, int rt,
                                                const uint8_t* __restrict__ r_img, uint4 (&rw)[2], const float* __restrict__ gam,
                                                float* s_stat, const ColScratch& cs, float* accd, float* acct, float* accz,
-                                               uint8_t* dztile, uint8_t* __restrict__ dz_img, const float* __restrict__ st_tile) {
+                                               uint8_t* dztile, uint8_t* __restrict__ dz_img, float2 ms) {
   constexpr int PART = C / MLP_NH, NSUB = PART / 16;
   const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
   const uint32_t a_dg = tmem_dg + lane_addr + h * PART, a_xh = tmem_xh + lane_addr + h * PART;
-  const float2 ms = *reinterpret_cast<const float2*>(st_tile + rt * 2);
-  const float rstd = ms.y, nmr = -ms.x * ms.y;
+  const float rstd = ms.y, nmr = -ms.x * ms.y;      // LayerNorm (mean, rstd) of the row, saved by the forward
   float s1p[2] = {0.f, 0.f}, s2p[2] = {0.f, 0.f};
   // ---- pass B: dg, xhat -> tensor memory; row sums; column sums of d and d * xhat ----
 #pragma unroll
@@ -1633,6 +1632,23 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_tc_bwd2_kernel(MlpBwdArgs 
   const int rt = q * 32 + lane;
 
   const int64_t ntiles = (A.N + TCM_ROWS - 1) / TCM_ROWS;
+  auto load16 = [&](const uint8_t* img, int C, int c0, uint4 (&w)[2]) {
+    const uint8_t* p = img + tile_off(rt, c0, C);
+    w[0] = __ldg(reinterpret_cast<const uint4*>(p));
+    w[1] = __ldg(reinterpret_cast<const uint4*>(p + 128));
+  };
+  // everything layer 3 needs from global memory is requested ONE TILE AHEAD (while the previous tile waits for its last
+  // GEMM), and the LayerNorm statistics of layers 2 / 1 at the top of the tile: no phase starts with a cold load
+  uint4 rw3[2];
+  float2 ms3 = make_float2(0.f, 1.f);
+  float dml = 0.f;
+  auto prefetch_l3 = [&](int64_t t) {
+    load16(reinterpret_cast<const uint8_t*>(A.r3) + t * (128 * 64 * 2), 64, h * 16, rw3);
+    ms3 = __ldg(reinterpret_cast<const float2*>(A.st3 + t * 256 + rt * 2));
+    const int64_t g = t * TCM_ROWS + rt;
+    dml = g < A.N ? __ldg(A.d_mlp_pred + g) : 0.f;
+  };
+  if ((int64_t)blockIdx.x < ntiles) prefetch_l3(blockIdx.x);
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int64_t row0 = tile * TCM_ROWS;
     const int64_t avail = min((int64_t)TCM_ROWS, A.N - row0);
@@ -1644,24 +1660,17 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_tc_bwd2_kernel(MlpBwdArgs 
     uint8_t* z1i = reinterpret_cast<uint8_t*>(A.dz1) + tile * (128 * 256 * 2);
     uint8_t* z2i = reinterpret_cast<uint8_t*>(A.dz2) + tile * (128 * 128 * 2);
     uint8_t* z3i = reinterpret_cast<uint8_t*>(A.dz3) + tile * (128 * 64 * 2);
-    if (tid == 0) {       // pull the NEXT tile's saved tensors into L2 while this one is processed
-      const int64_t nt = tile + gridDim.x;
-      if (nt < ntiles) {
-        bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(A.r1) + nt * (128 * 256 * 2), 128 * 256 * 2);
-        bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(A.r2) + nt * (128 * 128 * 2), 128 * 128 * 2);
-        bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(A.r3) + nt * (128 * 64 * 2), 128 * 64 * 2);
-      }
+    const int64_t nt = tile + gridDim.x;
+    if (tid == 0 && nt < ntiles) {       // pull the NEXT tile's saved tensors into L2 while this one is processed
+      bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(A.r1) + nt * (128 * 256 * 2), 128 * 256 * 2);
+      bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(A.r2) + nt * (128 * 128 * 2), 128 * 128 * 2);
+      bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(A.r3) + nt * (128 * 64 * 2), 128 * 64 * 2);
     }
-    uint4 rw3[2], rw2[2], rw1[2];
-    auto load16 = [&](const uint8_t* img, int C, int c0, uint4 (&w)[2]) {
-      const uint8_t* p = img + tile_off(rt, c0, C);
-      w[0] = __ldg(reinterpret_cast<const uint4*>(p));
-      w[1] = __ldg(reinterpret_cast<const uint4*>(p + 128));
-    };
-    load16(r3i, 64, h * 16, rw3);
+    uint4 rw2[2], rw1[2];
     load16(r2i, 128, h * 32, rw2);      // consumed after the first MMA: its latency hides behind layer 3
-    mlp_bwd2_layer<64, false>(tmem + 0, tmem + 64, live ? A.d_mlp_pred[grow] : 0.f, q, h, lane, rt, r3i, rw3, par + PAR_G2, s_stat, cs,
-                              ad3, at3, az3, ztile, z3i, A.st3 + tile * 256);
+    const float2 ms2 = __ldg(reinterpret_cast<const float2*>(A.st2 + tile * 256 + rt * 2));
+    mlp_bwd2_layer<64, false>(tmem + 0, tmem + 64, dml, q, h, lane, rt, r3i, rw3, par + PAR_G2, s_stat, cs, ad3, at3, az3, ztile, z3i,
+                              ms3);
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
@@ -1671,11 +1680,12 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_tc_bwd2_kernel(MlpBwdArgs 
       mma_commit(&bar);
     }
     load16(r1i, 256, h * 64, rw1);      // consumed after the second MMA
+    const float2 ms1 = __ldg(reinterpret_cast<const float2*>(A.st1 + tile * 256 + rt * 2));
     mbar_wait(&bar, phase);             // every warp polls for itself
     phase ^= 1;
     fence_after_sync();
     mlp_bwd2_layer<128, true>(tmem + 0, tmem + 128, 0.f, q, h, lane, rt, r2i, rw2, par + PAR_G1, s_stat, cs, ad2, at2, nullptr, ztile,
-                              z2i, A.st2 + tile * 256);
+                              z2i, ms2);
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
@@ -1688,7 +1698,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_tc_bwd2_kernel(MlpBwdArgs 
     phase ^= 1;
     fence_after_sync();
     mlp_bwd2_layer<256, true>(tmem + 256, tmem + 0, 0.f, q, h, lane, rt, r1i, rw1, par + PAR_G0, s_stat, cs, ad1, at1, nullptr, ztile,
-                              z1i, A.st1 + tile * 256);
+                              z1i, ms1);
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
@@ -1697,6 +1707,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_tc_bwd2_kernel(MlpBwdArgs 
       issue_gemm(tmem + 0, sZ, 128, 256 * 16, 256, sW0, 64 * 16, 128, 2 * 64 * 16, make_idesc(128, 64, false, true), 16, false);
       mma_commit(&bar);
     }
+    if (nt < ntiles) prefetch_l3(nt);   // in flight while the last GEMM of this tile runs
     mbar_wait(&bar, phase);
     phase ^= 1;
     fence_after_sync();
@@ -1709,9 +1720,12 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_tc_bwd2_kernel(MlpBwdArgs 
           st_row4(A.da, grow, h * 16 + 4 * j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]), A.da_bf16);
       }
     }
+    // No CTA barrier here: the next tile's layer 3 touches, before its own barrier, only this thread's tensor-memory lanes
+    // and columns (the da read above is the same thread's), this warp's scratch, and s_stat / the dz tile, whose last
+    // readers passed the barrier in front of the da GEMM (and its completion wait) above.
     fence_before_sync();
-    __syncthreads();
   }
+  __syncthreads();
   // the register partials of all warps -> s_acc ([dgamma | dbeta | dbias] per layer, as the first version keeps them)
   {
     const int c = lane & 15;

@@ -156,17 +156,25 @@ class ShardRouter:
 
 class ShardedNCFEngine:
     """One process per GPU.  `model` holds the replicated dense parameters (its own tables are not
-    used); this engine owns the local shard of the four tables and their Adam state."""
+    used); this engine owns the local shard of the four tables and their Adam state.
+
+    exchange = "p2p" (default on a multi-GPU NCCL group): the ONE-SIDED step of include/ncf_b200.h - every rank maps its
+    peers' table shards and gradient receive buffers (CUDA IPC over NVLink / NVSwitch); the forward gather pulls remote
+    rows itself, the backward segment-sum pushes gradient rows into the owners' buffers, and the only collectives left
+    are three small ones that double as the step's barriers (count all-gather, dense all-reduce).
+    exchange = "nccl": the all-to-all(v) version (ids -> owner gather -> rows back -> gradient rows)."""
 
     def __init__(self, model: AdvancedNCF, num_users: int, num_products: int, lr: float = 1e-3, betas=(0.9, 0.999),
                  eps: float = 1e-8, weight_decay: float = 1e-5, table_mode: str = "fused_dense_equiv", group=None,
                  seed: int = 1234, init_tables: Optional[List[torch.Tensor]] = None, rank: Optional[int] = None,
-                 world: Optional[int] = None):
+                 world: Optional[int] = None, exchange: Optional[str] = None):
         self.lib = _lib.load()
         self.model = model
         self.group = group
         self.world = world if world is not None else (dist.get_world_size(group) if dist.is_initialized() else 1)
         self.rank = rank if rank is not None else (dist.get_rank(group) if dist.is_initialized() else 0)
+        if self.world > _lib.MAX_WORLD:
+            raise ValueError(f"world size {self.world} exceeds NCF_MAX_WORLD = {_lib.MAX_WORLD}")
         self.U, self.I = num_users, num_products
         model._ensure_flat()
         self.device = model._flat.device
@@ -177,21 +185,26 @@ class ShardedNCFEngine:
         bu, bi = shard_block(num_users, self.world), shard_block(num_products, self.world)
         self.rows_u, self.rows_i = shard_rows(num_users, self.world, self.rank), shard_rows(num_products, self.world, self.rank)
         dev = self.device
+        # a rank whose block is empty (rows = 9, world = 4) keeps one dummy row per table: nothing ever addresses it
+        alloc_u, alloc_i = max(self.rows_u, 1), max(self.rows_i, 1)
         if init_tables is not None:        # global tables given (tests / small models): keep this rank's slice
             sl = [slice(self.rank * bu, self.rank * bu + self.rows_u), slice(self.rank * bi, self.rank * bi + self.rows_i)]
-            self.w = [init_tables[k][sl[k & 1]].to(dev).contiguous().clone() for k in range(4)]
+            self.w = []
+            for k in range(4):
+                t = torch.zeros(alloc_u if k % 2 == 0 else alloc_i, 64, device=dev)
+                t[:(self.rows_u if k % 2 == 0 else self.rows_i)] = init_tables[k][sl[k & 1]].to(dev)
+                self.w.append(t)
         else:                              # torchrec init U(+-sqrt(1/rows)) with the GLOBAL row count, on device
             g = torch.Generator(device=dev).manual_seed(seed + 7919 * self.rank)
             self.w = []
             for k in range(4):
-                rows, glob = (self.rows_u, num_users) if k % 2 == 0 else (self.rows_i, num_products)
-                t = torch.empty(max(rows, 1), 64, device=dev)
+                rows, glob = (alloc_u, num_users) if k % 2 == 0 else (alloc_i, num_products)
+                t = torch.empty(rows, 64, device=dev)
                 t.uniform_(-(1.0 / glob) ** 0.5, (1.0 / glob) ** 0.5, generator=g)
-                self.w.append(t[:rows] if rows else t[:0])
+                self.w.append(t)
         self.m = [torch.zeros_like(t) for t in self.w]
         self.v = [torch.zeros_like(t) for t in self.w]
-        self.touched = [torch.zeros(max(self.rows_u, 1), dtype=torch.uint8, device=dev),
-                        torch.zeros(max(self.rows_i, 1), dtype=torch.uint8, device=dev)]
+        self.touched = [torch.zeros(alloc_u, dtype=torch.uint8, device=dev), torch.zeros(alloc_i, dtype=torch.uint8, device=dev)]
         n = model._flat.numel()
         self._dense_and_loss = torch.zeros(n + 1, device=dev)             # [dense gradients | loss]: one all-reduce
         self.dense_grad = self._dense_and_loss[:n]
@@ -200,9 +213,26 @@ class ShardedNCFEngine:
         self.loss = torch.zeros(1, device=dev)
         self.routers = [ShardRouter(group), ShardRouter(group)]
         self._prefetched = None
+        self._status = _lib.StatusWord()
         if self.world == 1 or not dist.is_initialized():
             for r in self.routers:
                 r.world = 1
+        if exchange is None:
+            exchange = os.environ.get("NCF_SHARD_EXCHANGE") or ("p2p" if (self.world > 1 and dist.is_initialized()) else "nccl")
+        if exchange not in ("p2p", "nccl"):
+            raise ValueError(f"unknown exchange {exchange!r}")
+        self.exchange = exchange
+        # ---- one-sided state (set up lazily: needs the batch size) ----
+        self._cap = 0                      # rows per side the buffers are sized for
+        self._peers = None                 # peers' pointers: {"w": [world][4], "rows": [world][2], "ids": [world][2]}
+        self._bufs = None
+        self._plans = None
+        self._plan_slot = 0
+        self._barrier_word = torch.zeros(1, device=dev)
+
+    def table(self, k: int) -> torch.Tensor:
+        """this rank's REAL rows of table k (without the dummy row of an empty shard)"""
+        return self.w[k][:(self.rows_u if k % 2 == 0 else self.rows_i)]
 
     # ---- small helpers ----------------------------------------------------------------------
     def _tables(self):
@@ -211,6 +241,7 @@ class ShardedNCFEngine:
             t.w[k], t.m[k], t.v[k] = self.w[k].data_ptr(), self.m[k].data_ptr(), self.v[k].data_ptr()
         t.touched[0], t.touched[1] = self.touched[0].data_ptr(), self.touched[1].data_ptr()
         t.rows_user, t.rows_item = max(self.rows_u, 1), max(self.rows_i, 1)
+        t.status = self._status.ptr()
         return t
 
     def _cfg(self):
@@ -233,22 +264,74 @@ class ShardedNCFEngine:
     def _s(self):
         return _stream(self.device)
 
-    # ---- phases (the emulated-cluster test drives these one by one) -----------------------------
-    def phase_bucketize(self, user_ids, item_ids):
-        """requester: every DISTINCT id of the batch is exchanged once (one radix sort of both sides): owner-major
-        local ids + per-owner counts + the exchanged-row position of every sample."""
-        self.step += 1
-        self.N = n = user_ids.numel()
+    def check_status(self):
+        """IndexError if a step saw an id outside [0, num_users) / [0, num_products) (ncf_check_ids)."""
+        self._status.raise_if_set("ShardedNCFEngine")
+
+    def _buffers(self, n: int):
+        """Per-step device buffers, allocated once for the largest batch seen (no torch.empty inside the step)."""
+        if self._bufs is not None and self._bufs["n"] >= n:
+            return self._bufs
         dev = self.device
-        counts = torch.empty(2, self.world, dtype=torch.long, device=dev)
-        local = torch.empty(2, max(n, 1), dtype=torch.long, device=dev)
-        pos = torch.empty(2, max(n, 1), dtype=torch.long, device=dev)
-        nbytes = int(self.lib.ncf_shard_route_workspace_bytes(n))
-        self._route_ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        cfg = self._cfg()
+        b = {"n": n,
+             "counts": [torch.zeros(2 * self.world + 1, dtype=torch.long, device=dev) for _ in range(2)],
+             "local": [torch.empty(2, max(n, 1), dtype=torch.long, device=dev) for _ in range(2)],
+             "pos": [torch.empty(2, max(n, 1), dtype=torch.long, device=dev) for _ in range(2)],
+             "route_ws": [torch.empty(int(self.lib.ncf_shard_route_workspace_bytes(n)), dtype=torch.uint8, device=dev)
+                          for _ in range(2)],
+             "ws": torch.empty(int(self.lib.ncf_workspace_bytes(n, C.byref(cfg))), dtype=torch.uint8, device=dev),
+             "out": torch.empty(max(n, 1), device=dev), "grad_out": torch.empty(max(n, 1), device=dev),
+             "rows": [torch.empty(max(n, 1), 128, device=dev) for _ in range(2)],
+             "grads": [torch.empty(max(n, 1), 128, device=dev) for _ in range(2)],
+             "counts_all": [torch.zeros(self.world, 2 * self.world + 1, dtype=torch.long, device=dev) for _ in range(2)],
+             "counts_host": [torch.zeros(self.world, 2 * self.world + 1, dtype=torch.long).pin_memory() for _ in range(2)],
+             "slot": 0}
+        self._bufs = b
+        return b
+
+    # ---- routing (both exchange modes) --------------------------------------------------------------------------
+    def _route(self, user_ids, item_ids, slot: int):
+        """requester: every DISTINCT id of the batch is exchanged once (one radix sort of both sides): owner-major local
+        ids + per-owner counts + the exchanged-row position of every sample.  counts tensor = [user counts | item counts |
+        N] (the row count travels with them: the global mean needs every rank's N)."""
+        n = user_ids.numel()
+        b = self._buffers(n)
+        counts, local, pos, rws = b["counts"][slot], b["local"][slot], b["pos"][slot], b["route_ws"][slot]
+        _lib.check(self.lib.ncf_check_ids(_lib.ptr(user_ids), _lib.ptr(item_ids), n, self.U, self.I, None,
+                                          C.c_void_p(self._status.ptr()), self._s()), "ncf_check_ids")
         _lib.check(self.lib.ncf_shard_route(_lib.ptr(user_ids), _lib.ptr(item_ids), n, self.U, self.I, self.world,
-                                            _lib.ptr(counts), _lib.ptr(local), _lib.ptr(pos), _lib.ptr(self._route_ws), nbytes,
+                                            _lib.ptr(counts), _lib.ptr(local), _lib.ptr(pos), _lib.ptr(rws), rws.numel(),
                                             self._s()), "ncf_shard_route")
-        self._plan = [(counts[0], local[0], pos[0]), (counts[1], local[1], pos[1])]
+        counts[2 * self.world:].fill_(n)
+        return dict(N=n, slot=slot, counts=counts, local=local, pos=pos, route_ws=rws,
+                    key=(user_ids.data_ptr(), item_ids.data_ptr(), n))
+
+    def _begin_count_gather(self, routed):
+        """all-gather of every rank's [2 * world + 1] counts (a collective every rank reaches: it also serves as a barrier
+        of the one-sided step) + the device -> pinned host copy; nothing waits yet."""
+        b = self._bufs
+        slot = routed["slot"]
+        all_dev, host = b["counts_all"][slot], b["counts_host"][slot]
+        if self.world > 1 and dist.is_initialized():
+            dist.all_gather_into_tensor(all_dev.view(-1), routed["counts"], group=self.group)
+        else:
+            all_dev[self.rank].copy_(routed["counts"])
+        host.copy_(all_dev, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        routed["counts_all"], routed["counts_host"], routed["event"] = all_dev, host, ev
+        return routed
+
+    # ---- phases of the all-to-all version (the emulated-cluster test drives these one by one) -------------------
+    def phase_bucketize(self, user_ids, item_ids):
+        self.step += 1
+        r = self._route(user_ids, item_ids, 0)
+        self.N = r["N"]
+        self._routed = r
+        self._plan = [(r["counts"][:self.world], r["local"][0], r["pos"][0]),
+                      (r["counts"][self.world:2 * self.world], r["local"][1], r["pos"][1])]
+        self._route_ws = r["route_ws"]
         return [(p[1], p[0]) for p in self._plan]        # [(local ids owner-major, counts)] per side
 
     def phase_owner_rows(self, served_ids: List[torch.Tensor]):
@@ -263,27 +346,34 @@ class ShardedNCFEngine:
             out.append(rows)
         return out
 
-    def phase_forward_backward(self, rows: List[torch.Tensor], targets: torch.Tensor, global_rows: int):
-        """requester: forward, BCELoss (mean over the GLOBAL batch), backward; returns the gradient rows."""
+    def phase_forward_backward(self, rows: List[torch.Tensor], targets: torch.Tensor, global_rows: int, push_plan=None):
+        """requester: forward, BCELoss (mean over the GLOBAL batch), backward.  Returns the gradient rows (all-to-all
+        version), or pushes them into the owners' receive buffers when push_plan (device plan pointer) is given."""
         N = self.N
         cfg = self._cfg()
-        nbytes = int(self.lib.ncf_workspace_bytes(N, C.byref(cfg)))
-        ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
-        self.outputs = torch.empty(N, device=self.device)
+        b = self._buffers(N)
+        ws, nbytes = b["ws"], b["ws"].numel()
+        self.outputs = b["out"][:N]
         pos_u, pos_i = self._plan[0][2], self._plan[1][2]
         flat = self.model._flat
         _lib.check(self.lib.ncf_shard_forward(C.byref(cfg), _lib.ptr(flat), _lib.ptr(rows[0]), _lib.ptr(rows[1]),
                                               _lib.ptr(pos_u), _lib.ptr(pos_i), N, _lib.ptr(self.outputs), _lib.ptr(ws),
                                               nbytes, self._s()), "ncf_shard_forward")
-        grad_out = torch.empty(N, device=self.device)
+        grad_out = b["grad_out"][:N]
         _lib.check(self.lib.ncf_bce_loss(_lib.ptr(self.outputs), _lib.ptr(targets), N, _lib.ptr(self.loss),
                                          _lib.ptr(grad_out), self._s()), "ncf_bce_loss")
         scale = float(N) / float(global_rows)            # local mean -> share of the global mean
         grad_out.mul_(scale)
         self.loss.mul_(scale)
         self.dense_grad.zero_()
-        gu = torch.empty(rows[0].shape[0], 128, device=self.device)     # one gradient row per exchanged row
-        gi = torch.empty(rows[1].shape[0], 128, device=self.device)
+        if push_plan is not None:
+            _lib.check(self.lib.ncf_shard_backward_push(C.byref(cfg), _lib.ptr(flat), _lib.ptr(self.dense_grad), _lib.ptr(rows[0]),
+                                                        _lib.ptr(rows[1]), _lib.ptr(pos_u), _lib.ptr(pos_i), N, _lib.ptr(grad_out),
+                                                        push_plan, _lib.ptr(self._routed["local"]), _lib.ptr(self._route_ws),
+                                                        _lib.ptr(ws), nbytes, self._s()), "ncf_shard_backward_push")
+            return None
+        gu = b["grads"][0][:rows[0].shape[0]]            # one gradient row per exchanged row
+        gi = b["grads"][1][:rows[1].shape[0]]
         _lib.check(self.lib.ncf_shard_backward(C.byref(cfg), _lib.ptr(flat), _lib.ptr(self.dense_grad), _lib.ptr(rows[0]),
                                                _lib.ptr(rows[1]), _lib.ptr(pos_u), _lib.ptr(pos_i), N, _lib.ptr(grad_out),
                                                _lib.ptr(gu), _lib.ptr(gi), _lib.ptr(self._route_ws), _lib.ptr(ws), nbytes,
@@ -291,16 +381,19 @@ class ShardedNCFEngine:
                    "ncf_shard_backward")
         return [gu, gi]
 
-    def phase_owner_update(self, grad_rows: List[torch.Tensor]):
+    def phase_owner_update(self, grad_rows: List[torch.Tensor], served: Optional[List[torch.Tensor]] = None):
         """owner: segment-sum the received gradient rows per local id, LN backward, Adam."""
         adam = self._adam()
         tabs = self._tables()
+        served = served if served is not None else self._served
         for side in (1, 0):
-            ids, g = self._served[side], grad_rows[side]
+            ids, g = served[side], grad_rows[side]
             n = ids.numel()
             if n:
                 nbytes = int(self.lib.ncf_emb_bwd_workspace_bytes(n))
-                ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+                if getattr(self, "_own_ws", None) is None or self._own_ws.numel() < nbytes:
+                    self._own_ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+                ws = self._own_ws
                 _lib.check(self.lib.ncf_shard_owner_update(C.byref(adam), C.byref(tabs), _lib.ptr(self.model._flat),
                                                            _lib.ptr(self.dense_grad), side, _lib.ptr(ids), n, _lib.ptr(g),
                                                            _lib.ptr(ws), nbytes, self._s()), "ncf_shard_owner_update")
@@ -313,45 +406,217 @@ class ShardedNCFEngine:
         _lib.check(self.lib.ncf_dense_adam(_lib.ptr(flat), _lib.ptr(self.dense_grad), _lib.ptr(self.dense_m),
                                            _lib.ptr(self.dense_v), flat.numel(), C.byref(adam), self._s()), "ncf_dense_adam")
 
+    # ---- the one-sided step over peer memory ----------------------------------------------------------------------
+    def _own_pointers(self):
+        return {"w": [t.data_ptr() for t in self.w], "rows": [t.data_ptr() for t in self._recv_rows],
+                "ids": [t.data_ptr() for t in self._recv_ids]}
+
+    def _setup_p2p(self, n: int, peers: Optional[List["ShardedNCFEngine"]] = None):
+        """Receive buffers for the gradient rows of every requester (+ their local ids) and the peers' pointers.
+        peers = the other in-process engines (emulated cluster, one GPU): plain device pointers; otherwise the pointers
+        travel as CUDA IPC handles through all_gather_object and are mapped with ncf_ipc_open."""
+        if self._peers is not None and self._cap >= n:
+            return
+        dev = self.device
+        cap = [self.world * min(n, max(self.rows_u, 1)), self.world * min(n, max(self.rows_i, 1))]
+        self._recv_rows = [torch.empty(c, 128, device=dev) for c in cap]
+        self._recv_ids = [torch.empty(c, dtype=torch.long, device=dev) for c in cap]
+        self._cap = n
+        if peers is None and (self.world == 1 or not dist.is_initialized()):
+            peers = [self]
+        if peers is not None:
+            self._peer_engines = peers
+            return                                   # pointers are read from the peer engines when the plan is filled
+        mine = self._own_pointers()
+        exported = {}
+        for kind, ptrs in mine.items():
+            exported[kind] = []
+            for p in ptrs:
+                h = (C.c_char * 64)()
+                off = C.c_int64(0)
+                _lib.check(self.lib.ncf_ipc_export(C.c_void_p(p), h, C.byref(off)), "ncf_ipc_export")
+                exported[kind].append((bytes(h), int(off.value)))
+        gathered = [None] * self.world
+        dist.all_gather_object(gathered, exported, group=self.group)
+        if self._peers is not None:                   # re-sized buffers: drop the old mappings
+            self._close_peers()
+        self._peers = {"w": [], "rows": [], "ids": []}
+        for r in range(self.world):
+            for kind in ("w", "rows", "ids"):
+                if r == self.rank:
+                    self._peers[kind].append(list(mine[kind]))
+                    continue
+                ptrs = []
+                for hbytes, off in gathered[r][kind]:
+                    out = C.c_void_p()
+                    _lib.check(self.lib.ncf_ipc_open(hbytes, off, C.byref(out)), "ncf_ipc_open")
+                    ptrs.append(int(out.value))
+                self._peers[kind].append(ptrs)
+        self._mapped = [p for kind in ("w", "rows", "ids") for r in range(self.world) if r != self.rank for p in self._peers[kind][r]]
+
+    def _close_peers(self):
+        for p in getattr(self, "_mapped", []):
+            self.lib.ncf_ipc_close(C.c_void_p(p))
+        self._mapped = []
+
+    def _peer_ptrs(self, r: int):
+        if getattr(self, "_peer_engines", None) is not None:
+            e = self._peer_engines[r]
+            return e._own_pointers()
+        return {k: self._peers[k][r] for k in ("w", "rows", "ids")}
+
+    def _fill_plan(self, counts_host: torch.Tensor):
+        """counts_host [world(requester), 2 * world + 1]: builds this step's ncf_shard_plan in pinned memory, uploads it on
+        the stream, and returns (device plan pointer, (n distinct users, items), (rows received users, items), global N)."""
+        W, me = self.world, self.rank
+        c = counts_host[:, :2 * W].reshape(W, 2, W)                   # [requester, side, owner]
+        if self._plans is None:
+            self._plans = [(torch.zeros(C.sizeof(_lib.ShardPlan), dtype=torch.uint8).pin_memory(),
+                            torch.zeros(C.sizeof(_lib.ShardPlan), dtype=torch.uint8, device=self.device)) for _ in range(4)]
+        host, dev = self._plans[self._plan_slot]
+        self._plan_slot = (self._plan_slot + 1) % len(self._plans)
+        plan = _lib.ShardPlan.from_buffer(host.numpy())
+        plan.world, plan.rank = W, me
+        n_dist, n_recv = [], []
+        for side in (0, 1):
+            acc = 0
+            for o in range(W):
+                plan.begin[side][o] = acc
+                acc += int(c[me, side, o])
+            plan.begin[side][W] = acc
+            n_dist.append(acc)
+            n_recv.append(int(c[:, side, me].sum()))
+        for o in range(W):
+            ptrs = self._peer_ptrs(o)
+            for k in range(4):
+                plan.tab[o][k] = ptrs["w"][k]
+            for side in (0, 1):
+                off = int(c[:me, side, o].sum())                      # rows of the requesters before me in o's buffer
+                plan.push_rows[side][o] = ptrs["rows"][side] + off * 512
+                plan.push_ids[side][o] = ptrs["ids"][side] + off * 8
+        dev.copy_(host, non_blocking=True)
+        return C.c_void_p(dev.data_ptr()), n_dist, n_recv, int(counts_host[:, 2 * W].sum())
+
+    def phase_pull(self, plan_ptr, n_dist):
+        """requester: LN'd [n,128] rows of its distinct ids, read from the owners' shards (one kernel per side)."""
+        r = self._routed
+        rows = []
+        for side in (0, 1):
+            out = self._bufs["rows"][side][:max(n_dist[side], 1)]
+            _lib.check(self.lib.ncf_shard_pull_rows(plan_ptr, _lib.ptr(self.model._flat), side, _lib.ptr(r["local"][side]),
+                                                    n_dist[side], _lib.ptr(out), self._s()), "ncf_shard_pull_rows")
+            rows.append(out[:n_dist[side]])
+        return rows
+
+    def _barrier(self):
+        """a collective every rank reaches in stream order (used where the step has no other one at that point)"""
+        if self.world > 1 and dist.is_initialized():
+            dist.all_reduce(self._barrier_word, group=self.group)
+
+    def _adopt(self, routed):
+        self._routed = routed
+        self.N = routed["N"]
+        self._plan = [(routed["counts"][:self.world], routed["local"][0], routed["pos"][0]),
+                      (routed["counts"][self.world:2 * self.world], routed["local"][1], routed["pos"][1])]
+        self._route_ws = routed["route_ws"]
+
+    def _train_step_p2p(self, user_ids, item_ids, targets, next_ids):
+        mark = self._mark
+        mark(None)
+        self._buffers(user_ids.numel())
+        self._setup_p2p(self._bufs["n"])
+        pre, self._prefetched = self._prefetched, None
+        key = (user_ids.data_ptr(), item_ids.data_ptr(), user_ids.numel())
+        if pre is None or pre["key"] != key:
+            pre = self._begin_count_gather(self._route(user_ids, item_ids, self._bufs["slot"]))
+            self._bufs["slot"] ^= 1
+        self.step += 1
+        self._adopt(pre)
+        pre["event"].synchronize()                   # the split sizes: already there when the batch was routed a step ahead
+        plan_ptr, n_dist, n_recv, global_rows = self._fill_plan(pre["counts_host"])
+        mark("route + plan")
+        rows = self.phase_pull(plan_ptr, n_dist)
+        mark("pull rows (P2P)")
+        self.phase_forward_backward(rows, targets, global_rows, push_plan=plan_ptr)
+        mark("forward+backward+push (P2P)")
+        # barrier A: every requester's pushed rows have landed before an owner reads its buffer.  With look-ahead the
+        # count all-gather of the NEXT batch is that collective; without, a one-word all-reduce.
+        if next_ids is not None:
+            nxt = self._begin_count_gather(self._route(next_ids[0], next_ids[1], self._bufs["slot"]))
+            self._bufs["slot"] ^= 1
+            self._prefetched = nxt
+        else:
+            self._barrier()
+        mark("route next (barrier)")
+        self.phase_owner_update([self._recv_rows[0][:n_recv[0]], self._recv_rows[1][:n_recv[1]]],
+                                served=[self._recv_ids[0][:n_recv[0]], self._recv_ids[1][:n_recv[1]]])
+        mark("owner update")
+        # barrier B: the dense all-reduce - after it every owner has updated its shard (the next pull may read it) and has
+        # consumed its receive buffer (the next push may overwrite it)
+        if self.world > 1 and dist.is_initialized():
+            self._dense_and_loss[-1:].copy_(self.loss)
+            dist.all_reduce(self._dense_and_loss, group=self.group)
+            self.loss.copy_(self._dense_and_loss[-1:])
+        self.phase_dense_adam()
+        mark("dense allreduce+adam")
+        return self.loss
+
     # ---- the real step ----------------------------------------------------------------------------
     def train_step(self, user_ids: torch.Tensor, item_ids: torch.Tensor, targets: torch.Tensor,
                    next_ids: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> torch.Tensor:
-        """Global ids int64 [N] and targets fp32 [N] of THIS rank's batch (device tensors).  Returns the
-        global mean loss (device scalar, identical on all ranks).
+        """Global ids int64 [N] and targets fp32 [N] of THIS rank's batch (device tensors; N may differ between ranks).
+        Returns the global mean loss (device scalar, identical on all ranks).
 
         next_ids = (user_ids, item_ids) the NEXT call will be given (input-pipeline look-ahead; all ranks must pass it
-        or none): that batch is routed (sort, de-duplication, count exchange) right after this step's gradient exchange
-        is queued, so the one host synchronisation of a step - reading the split sizes - waits while the GPU still has
-        the owner update of this step to do, instead of draining the queue."""
+        or none): that batch is routed (sort, de-duplication, count exchange) inside this step, so the one host
+        synchronisation of a step - reading the counts - finds them already there instead of draining the queue."""
+        self.check_status()
+        if self.exchange == "p2p":
+            return self._train_step_p2p(user_ids, item_ids, targets, next_ids)
         mark = self._mark
         mark(None)
         pre, self._prefetched = self._prefetched, None
         key = (user_ids.data_ptr(), item_ids.data_ptr(), user_ids.numel())
         if pre is not None and pre["key"] == key:
             self.step += 1
-            self._plan, self.N, self._route_ws = pre["plan"], pre["N"], pre["route_ws"]
+            self._adopt(pre)
             mark("bucketize")
-            served = ShardRouter.finish_id_exchange(pre["handle"])
         else:
-            plan = self.phase_bucketize(user_ids, item_ids)
+            self.phase_bucketize(user_ids, item_ids)
+            pre = self._begin_count_gather(self._routed)
             mark("bucketize")
-            served = ShardRouter.exchange_ids_multi(self.routers, plan)
+        pre["event"].synchronize()
+        ch = pre["counts_host"]
+        W = self.world
+        global_rows = int(ch[:, 2 * W].sum())
+        for side, r in enumerate(self.routers):
+            r.send_counts = ch[self.rank, side * W:(side + 1) * W].tolist()
+            r.recv_counts = ch[:, side * W + self.rank].tolist()
+        ids_items, served = [], []
+        for side, r in enumerate(self.routers):
+            ids = self._plan[side][1]
+            if r.world == 1:
+                served.append(ids[:r.send_counts[0]])
+                continue
+            out = ids.new_empty(sum(r.recv_counts))
+            ids_items.append((out, ids[:sum(r.send_counts)], r.recv_counts, r.send_counts))
+            served.append(out)
+        if ids_items:
+            _alltoallv_many(ids_items, self.group)
         mark("a2a ids")
         rows_out = self.phase_owner_rows(served)
         mark("owner rows")
         rows = ShardRouter.exchange_rows_multi(self.routers, rows_out, to_owner=False)
         mark("a2a rows")
-        grads = self.phase_forward_backward(rows, targets, self.N * self.world)
+        grads = self.phase_forward_backward(rows, targets, global_rows)
         mark("forward+backward")
         recv = ShardRouter.exchange_rows_multi(self.routers, grads, to_owner=True)
         mark("a2a grads")
         if next_ids is not None:
-            keep = (self.step, self._plan, self.N, self._route_ws, self._served)
-            plan = self.phase_bucketize(*next_ids)
-            handle = ShardRouter.begin_id_exchange(self.routers, plan)
-            self._prefetched = dict(key=(next_ids[0].data_ptr(), next_ids[1].data_ptr(), next_ids[0].numel()), plan=self._plan,
-                                    N=self.N, route_ws=self._route_ws, handle=handle)
-            self.step, self._plan, self.N, self._route_ws, self._served = keep
+            keep = (self._routed, self._served)
+            nxt = self._begin_count_gather(self._route(next_ids[0], next_ids[1], pre["slot"] ^ 1))
+            self._prefetched = nxt
+            self._routed, self._served = keep
             mark("route next")
         self.phase_owner_update(recv)
         mark("owner update")
@@ -386,7 +651,8 @@ class ShardedNCFEngine:
         writes `dense.pt` (the reference state_dict keys of the replicated parameters, their Adam state, step)."""
         os.makedirs(directory, exist_ok=True)
         torch.save({"rank": self.rank, "world": self.world, "num_users": self.U, "num_products": self.I,
-                    "w": [t.cpu() for t in self.w], "m": [t.cpu() for t in self.m], "v": [t.cpu() for t in self.v]},
+                    "w": [self.table(k).cpu() for k in range(4)], "m": [self.m[k][:self.table(k).shape[0]].cpu() for k in range(4)],
+                    "v": [self.v[k][:self.table(k).shape[0]].cpu() for k in range(4)]},
                    os.path.join(directory, f"shard_{self.rank}_of_{self.world}.pt"))
         if self.rank == 0:
             dense = {k: v.detach().cpu() for k, v in self.model.state_dict().items() if "embedding_collection" not in k}
@@ -416,7 +682,7 @@ class ShardedNCFEngine:
                 src0 = sh["rank"] * src_block
                 src1 = src0 + sh["w"][k].shape[0]
                 dst0 = self.rank * dst_block
-                dst1 = dst0 + self.w[k].shape[0]
+                dst1 = dst0 + self.table(k).shape[0]
                 lo, hi = max(src0, dst0), min(src1, dst1)
                 if lo >= hi:
                     continue
@@ -426,12 +692,12 @@ class ShardedNCFEngine:
     def gather_tables(self) -> List[torch.Tensor]:
         """Reassemble the global tables on every rank (tests / checkpointing of small models)."""
         if self.world == 1:
-            return [t.clone() for t in self.w]
+            return [self.table(k).clone() for k in range(4)]
         out = []
         for k in range(4):
             block = shard_block(self.U if k % 2 == 0 else self.I, self.world)
             pad = torch.zeros(block, 64, device=self.device)
-            pad[:self.w[k].shape[0]] = self.w[k]
+            pad[:self.table(k).shape[0]] = self.table(k)
             parts = [torch.empty_like(pad) for _ in range(self.world)]
             dist.all_gather(parts, pad, group=self.group)
             out.append(torch.cat(parts)[:self.U if k % 2 == 0 else self.I])

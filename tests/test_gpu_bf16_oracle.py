@@ -84,6 +84,7 @@ def _batch(U, I, B, g):
 Q_PATH = ("mlp_embedding_collection.embedding_bags.user_id.weight", "user_product_attention.q_proj.weight",
           "user_product_attention.q_proj.bias", "user_product_attention.k_proj.weight")
 Q_PATH_RTOL, Q_PATH_COS = 0.2, 0.99
+FRESH_COS = 0.995        # every other tensor of the freshly initialised model (its gradients are smaller and noisier)
 
 
 def _check_grads(named, leaves, what, fresh_init=False):
@@ -94,7 +95,7 @@ def _check_grads(named, leaves, what, fresh_init=False):
         a, b = leaf.grad.detach().double().reshape(-1), named[k].grad.detach().double().reshape(-1)
         rel = float((a - b).abs().max() / a.abs().max().clamp_min(1e-30))
         cos = float((a @ b) / (a.norm() * b.norm()).clamp_min(1e-30))
-        rtol, cmin = (Q_PATH_RTOL, Q_PATH_COS) if (fresh_init and k in Q_PATH) else (GRAD_RTOL, GRAD_COS)
+        rtol, cmin = (Q_PATH_RTOL, Q_PATH_COS) if (fresh_init and k in Q_PATH) else (GRAD_RTOL, FRESH_COS if fresh_init else GRAD_COS)
         rows.append((rel, cos, k))
         if not (rel <= rtol and cos >= cmin):
             bad.append((k, rel, cos))

@@ -81,14 +81,42 @@ def _emulated_exchange(per_rank_bufs, per_rank_counts, world):
     return out
 
 
+def _p2p_emulated_step(engines, batches):
+    """One step of the ONE-SIDED exchange with `world` in-process ranks on one GPU: the peers' pointers are plain device
+    pointers, the count all-gather is a torch.stack, and the stream order of the phases stands in for the barriers."""
+    world = len(engines)
+    n = max(b[0].numel() for b in batches)
+    for e in engines:
+        e._buffers(n)
+        e._setup_p2p(n, peers=engines)
+    for e, b in zip(engines, batches):
+        e.step += 1
+        e._adopt(e._route(b[0], b[1], 0))
+    counts = torch.stack([e._routed["counts"] for e in engines]).cpu()
+    plans = [e._fill_plan(counts) for e in engines]
+    rows = [e.phase_pull(pl[0], pl[1]) for e, pl in zip(engines, plans)]
+    for e, b, pl, r in zip(engines, batches, plans, rows):
+        assert e.phase_forward_backward(r, b[2], pl[3], push_plan=pl[0]) is None
+    for e, pl in zip(engines, plans):
+        n_recv = pl[2]
+        e.phase_owner_update([e._recv_rows[0][:n_recv[0]], e._recv_rows[1][:n_recv[1]]],
+                             served=[e._recv_ids[0][:n_recv[0]], e._recv_ids[1][:n_recv[1]]])
+    assert plans[0][3] == sum(b[0].numel() for b in batches)
+
+
 @pytest.mark.gpu
-@pytest.mark.parametrize("world,precision", [(1, "fp32"), (2, "fp32"), (3, "fp32"), (2, "bf16")])
-def test_emulated_cluster_matches_single_gpu_engine(world, precision):
-    """`world` ShardedNCFEngine ranks driven phase by phase in one process (the exchanges emulated by
-    copies) must reproduce NCFTrainEngine on the concatenated batch: same loss, same weights."""
+@pytest.mark.parametrize("world,precision,exchange", [(1, "fp32", "nccl"), (2, "fp32", "nccl"), (3, "fp32", "nccl"), (2, "bf16", "nccl"),
+                                                      (1, "fp32", "p2p"), (2, "fp32", "p2p"), (3, "fp32", "p2p"), (4, "fp32", "p2p"), (5, "fp32", "p2p"),
+                                                      (2, "bf16", "p2p")])
+def test_emulated_cluster_matches_single_gpu_engine(world, precision, exchange):
+    """`world` ShardedNCFEngine ranks driven phase by phase in one process must reproduce NCFTrainEngine on the
+    concatenated batch: same loss, same weights.  exchange = "nccl": the all-to-alls emulated by copies; "p2p": the
+    one-sided pull / push kernels on the other ranks' buffers (plain pointers on one GPU), with ragged batches (the ranks
+    hold different numbers of rows) and, at world = 4, a 9-row item table whose last block is EMPTY (torchrec ROW_WISE
+    handles empty shards)."""
     import ncf_b200
     from ncf_b200.sharding import ShardedNCFEngine
-    U, I, B = 211, 97, 40
+    U, I, B = 211, (9 if world == 4 else 97), 40
     pg, _ = golden_params()
     g = torch.Generator().manual_seed(world)
     p = {k: v.clone() for k, v in pg.items()}
@@ -105,18 +133,28 @@ def test_emulated_cluster_matches_single_gpu_engine(world, precision):
     ref = ncf_b200.NCFTrainEngine(ref_model, table_mode="fused_dense_equiv")
     models = [fresh() for _ in range(world)]
     tabs = [p[k] for k in O.TABLE_KEYS]
-    engines = [ShardedNCFEngine(models[r], U, I, table_mode="fused_dense_equiv", init_tables=tabs, rank=r, world=world)
-               for r in range(world)]
+    engines = [ShardedNCFEngine(models[r], U, I, table_mode="fused_dense_equiv", init_tables=tabs, rank=r, world=world,
+                                exchange=exchange) for r in range(world)]
     for step in range(3):
         batches = []
         for r in range(world):
-            u = torch.randint(0, U, (B,), generator=g).repeat_interleave(5)
-            i = torch.randint(0, I, (B * 5,), generator=g)
-            t = torch.zeros(B, 5)
+            Br = B + (3 * r if exchange == "p2p" else 0)            # ragged: the global mean needs every rank's row count
+            u = torch.randint(0, U, (Br,), generator=g).repeat_interleave(5)
+            i = torch.randint(0, I, (Br * 5,), generator=g)
+            t = torch.zeros(Br, 5)
             t[:, 0] = 1
             batches.append((u.cuda(), i.cuda(), t.reshape(-1).cuda()))
         ref_loss = ref.train_step(torch.cat([b[0] for b in batches]), torch.cat([b[1] for b in batches]),
                                   torch.cat([b[2] for b in batches])).clone()
+        if exchange == "p2p":
+            _p2p_emulated_step(engines, batches)
+            dsum = sum(e.dense_grad for e in engines)
+            lsum = sum(e.loss for e in engines)
+            for e in engines:
+                e.dense_grad.copy_(dsum)
+                e.phase_dense_adam()
+            assert abs(float(lsum) - float(ref_loss)) < (2e-6 if precision == "fp32" else 2e-3)
+            continue
         plans = [engines[r].phase_bucketize(batches[r][0], batches[r][1]) for r in range(world)]
         served = [[None, None] for _ in range(world)]
         counts = [[plans[r][s][1].tolist() for r in range(world)] for s in (0, 1)]
@@ -149,7 +187,7 @@ def test_emulated_cluster_matches_single_gpu_engine(world, precision):
     block_u, block_i = (U + world - 1) // world, (I + world - 1) // world
     ref_tabs = ref_model._table_params()
     for k in range(4):
-        full = torch.cat([e.w[k] for e in engines])
+        full = torch.cat([e.table(k) for e in engines])
         d = (full - ref_tabs[k].detach()).abs()
         assert full.shape == ref_tabs[k].shape
         if precision == "fp32":
@@ -249,16 +287,18 @@ def test_lookahead_routing_does_not_change_results():
         t[:, 0] = 1
         batches.append((u.cuda(), i.cuda(), t.reshape(-1).cuda()))
     out = []
-    for look in (False, True):
+    for look, exchange in ((False, "nccl"), (True, "nccl"), (False, "p2p"), (True, "p2p")):
         m = ncf_b200.AdvancedNCF(U, I, 5, 24, dropout=0.0)
         m.load_state_dict(p)
         m = m.cuda().train()
-        eng = ShardedNCFEngine(m, U, I, table_mode="fused_sparse", init_tables=[p[k] for k in O.TABLE_KEYS], rank=0, world=1)
+        eng = ShardedNCFEngine(m, U, I, table_mode="fused_sparse", init_tables=[p[k] for k in O.TABLE_KEYS], rank=0, world=1,
+                               exchange=exchange)
         losses = []
         for s, b in enumerate(batches):
             nxt = batches[s + 1][:2] if (look and s + 1 < len(batches)) else None
             losses.append(float(eng.train_step(*b, next_ids=nxt)))
         out.append((losses, [t.clone() for t in eng.w]))
-    assert max(abs(a - b) for a, b in zip(out[0][0], out[1][0])) < 1e-5
-    for a, b in zip(out[0][1], out[1][1]):
-        assert float((a - b).abs().mean()) < 1e-6
+    for other in out[1:]:
+        assert max(abs(a - b) for a, b in zip(out[0][0], other[0])) < 1e-5
+        for a, b in zip(out[0][1], other[1]):
+            assert float((a - b).abs().mean()) < 1e-6
