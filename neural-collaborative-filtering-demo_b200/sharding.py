@@ -297,7 +297,10 @@ class ShardedNCFEngine:
         N] (the row count travels with them: the global mean needs every rank's N)."""
         n = user_ids.numel()
         b = self._buffers(n)
-        counts, local, pos, rws = b["counts"][slot], b["local"][slot], b["pos"][slot], b["route_ws"][slot]
+        counts, rws = b["counts"][slot], b["route_ws"][slot]
+        # ncf_shard_route lays local ids / positions out as [2][N] for THIS batch's N (the buffers may be larger)
+        local = b["local"][slot].view(-1)[:2 * max(n, 1)].view(2, max(n, 1))
+        pos = b["pos"][slot].view(-1)[:2 * max(n, 1)].view(2, max(n, 1))
         _lib.check(self.lib.ncf_check_ids(_lib.ptr(user_ids), _lib.ptr(item_ids), n, self.U, self.I, None,
                                           C.c_void_p(self._status.ptr()), self._s()), "ncf_check_ids")
         _lib.check(self.lib.ncf_shard_route(_lib.ptr(user_ids), _lib.ptr(item_ids), n, self.U, self.I, self.world,
@@ -415,7 +418,7 @@ class ShardedNCFEngine:
         """Receive buffers for the gradient rows of every requester (+ their local ids) and the peers' pointers.
         peers = the other in-process engines (emulated cluster, one GPU): plain device pointers; otherwise the pointers
         travel as CUDA IPC handles through all_gather_object and are mapped with ncf_ipc_open."""
-        if self._peers is not None and self._cap >= n:
+        if (self._peers is not None or getattr(self, "_peer_engines", None) is not None) and self._cap >= n:
             return
         dev = self.device
         cap = [self.world * min(n, max(self.rows_u, 1)), self.world * min(n, max(self.rows_i, 1))]
