@@ -1177,7 +1177,17 @@ int shard_requester_grads(const float* dense, float* dense_grad, const float* ro
   const int64_t nchunks = (N + EB_CHUNK - 1) / EB_CHUNK;
   const int wpb = EB_THREADS / 32;
   const int grid = (int)std::min<int64_t>((nchunks + wpb - 1) / wpb, (int64_t)num_sms() * 8);
+  // the two sides share read-only inputs only (own segment-sum buffer each): with an auxiliary stream (ncf_set_aux_stream)
+  // the item side runs next to the user side, like the single-GPU embedding backward
+  AuxCtx* aux = aux_ctx();
+  const bool two_streams = aux->stream && aux->stream != st;
+  if (two_streams) {
+    NCF_TRY(aux_events(aux));
+    NCF_CUDA(cudaEventRecord(aux->ev[2], st));
+    NCF_CUDA(cudaStreamWaitEvent(aux->stream, aux->ev[2], 0));
+  }
   for (int side = 0; side < 2; ++side) {
+    const cudaStream_t sst = (two_streams && side == 1) ? aux->stream : st;
     EmbBwdArgs A{};
     A.sorted_ids = r.keys_out + (side ? N : 0);
     A.perm = r.vals_out + (side ? N : 0);
@@ -1194,16 +1204,20 @@ int shard_requester_grads(const float* dense, float* dense_grad, const float* ro
     A.push_side = side;
     A.dense = dense;
     A.dense_grad = dense_grad;
-    A.acc_buf = w.acc_buf;
+    A.acc_buf = (two_streams && side == 1) ? w.acc_buf2 : w.acc_buf;
     A.chunk_counter = w.counters + side;
     A.N = N;
     A.mode = NCF_EMB_ADAM_SPARSE;
     A.accumulate_wmf = side == 0 ? 1 : 0;
-    emb_bwd_phase1_kernel<<<grid, EB_THREADS, 0, st>>>(A);
+    emb_bwd_phase1_kernel<<<grid, EB_THREADS, 0, sst>>>(A);
     NCF_LAUNCH_CHECK();
     A.dense_grad = nullptr;                  // output mode: no LayerNorm-affine gradients here (the owners add them)
-    emb_bwd_phase2_kernel<<<std::min(grid, num_sms() * 3), EB_THREADS, 0, st>>>(A);
+    emb_bwd_phase2_kernel<<<std::min(grid, num_sms() * 3), EB_THREADS, 0, sst>>>(A);
     NCF_LAUNCH_CHECK();
+  }
+  if (two_streams) {
+    NCF_CUDA(cudaEventRecord(aux->ev[3], aux->stream));
+    NCF_CUDA(cudaStreamWaitEvent(st, aux->ev[3], 0));
   }
   return NCF_OK;
 }

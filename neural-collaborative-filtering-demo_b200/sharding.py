@@ -229,6 +229,9 @@ class ShardedNCFEngine:
         self._plans = None
         self._plan_slot = 0
         self._barrier_word = torch.zeros(1, device=dev)
+        # auxiliary stream: the item side of the segment sums / owner update next to the user side, and the routing of the
+        # next batch next to whatever leaves SMs free (NCF_SHARD_AUX=0 switches it off)
+        self._aux = torch.cuda.Stream(device=dev) if os.environ.get("NCF_SHARD_AUX", "1") != "0" else None
 
     def table(self, k: int) -> torch.Tensor:
         """this rank's REAL rows of table k (without the dummy row of an empty shard)"""
@@ -357,6 +360,7 @@ class ShardedNCFEngine:
         b = self._buffers(N)
         ws, nbytes = b["ws"], b["ws"].numel()
         self.outputs = b["out"][:N]
+        self.lib.ncf_set_aux_stream(C.c_void_p(self._aux.cuda_stream) if self._aux is not None else None)
         pos_u, pos_i = self._plan[0][2], self._plan[1][2]
         flat = self.model._flat
         _lib.check(self.lib.ncf_shard_forward(C.byref(cfg), _lib.ptr(flat), _lib.ptr(rows[0]), _lib.ptr(rows[1]),
@@ -385,21 +389,31 @@ class ShardedNCFEngine:
         return [gu, gi]
 
     def phase_owner_update(self, grad_rows: List[torch.Tensor], served: Optional[List[torch.Tensor]] = None):
-        """owner: segment-sum the received gradient rows per local id, LN backward, Adam."""
+        """owner: segment-sum the received gradient rows per local id, LN backward, Adam.  The two sides touch different
+        tables (their LayerNorm-affine gradients are added atomically), so the item side runs on the auxiliary stream."""
         adam = self._adam()
         tabs = self._tables()
         served = served if served is not None else self._served
+        main = torch.cuda.current_stream(self.device)
+        ws_list = self.__dict__.setdefault("_own_ws", [None, None])
         for side in (1, 0):
             ids, g = served[side], grad_rows[side]
             n = ids.numel()
-            if n:
-                nbytes = int(self.lib.ncf_emb_bwd_workspace_bytes(n))
-                if getattr(self, "_own_ws", None) is None or self._own_ws.numel() < nbytes:
-                    self._own_ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
-                ws = self._own_ws
+            if not n:
+                continue
+            nbytes = int(self.lib.ncf_emb_bwd_workspace_bytes(n))
+            if ws_list[side] is None or ws_list[side].numel() < nbytes:
+                ws_list[side] = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            ws = ws_list[side]
+            stream = self._aux if (side == 1 and self._aux is not None) else main
+            if stream is not main:
+                stream.wait_stream(main)
+            with torch.cuda.stream(stream):
                 _lib.check(self.lib.ncf_shard_owner_update(C.byref(adam), C.byref(tabs), _lib.ptr(self.model._flat),
                                                            _lib.ptr(self.dense_grad), side, _lib.ptr(ids), n, _lib.ptr(g),
                                                            _lib.ptr(ws), nbytes, self._s()), "ncf_shard_owner_update")
+        if self._aux is not None:
+            main.wait_stream(self._aux)
         if self.table_mode == "fused_dense_equiv":
             _lib.check(self.lib.ncf_emb_adam_sweep(C.byref(adam), C.byref(tabs), self._s()), "ncf_emb_adam_sweep")
 
@@ -535,6 +549,17 @@ class ShardedNCFEngine:
             self._bufs["slot"] ^= 1
         self.step += 1
         self._adopt(pre)
+        main = torch.cuda.current_stream(self.device)
+        nxt = None
+        if next_ids is not None:
+            # the next batch's routing (sort, de-duplication) depends on its ids only: on the auxiliary stream it fills the
+            # SMs this step's kernels leave idle (kernel boundaries, tails of the persistent tower kernels)
+            rs = self._aux if self._aux is not None else main
+            if rs is not main:
+                rs.wait_stream(main)
+            with torch.cuda.stream(rs):
+                nxt = self._route(next_ids[0], next_ids[1], self._bufs["slot"])
+            self._bufs["slot"] ^= 1
         pre["event"].synchronize()                   # the split sizes: already there when the batch was routed a step ahead
         plan_ptr, n_dist, n_recv, global_rows = self._fill_plan(pre["counts_host"])
         mark("route + plan")
@@ -544,10 +569,14 @@ class ShardedNCFEngine:
         mark("forward+backward+push (P2P)")
         # barrier A: every requester's pushed rows have landed before an owner reads its buffer.  With look-ahead the
         # count all-gather of the NEXT batch is that collective; without, a one-word all-reduce.
-        if next_ids is not None:
-            nxt = self._begin_count_gather(self._route(next_ids[0], next_ids[1], self._bufs["slot"]))
-            self._bufs["slot"] ^= 1
-            self._prefetched = nxt
+        if nxt is not None:
+            rs = self._aux if self._aux is not None else main
+            if rs is not main:
+                rs.wait_stream(main)                 # the collective comes after this rank's push
+            with torch.cuda.stream(rs):
+                self._prefetched = self._begin_count_gather(nxt)
+            if rs is not main:
+                main.wait_stream(rs)
         else:
             self._barrier()
         mark("route next (barrier)")
