@@ -964,16 +964,18 @@ def extra_blocks(args, world, rank, dev, precision, barrier):
                               steps, barrier, world, dev, 0.5)
         phases = profile_phases(eng, batches, nb, 6)
         ms = statistics.median(blocks) / steps
-        t = torch.tensor([phases.get("owner rows", 0.0) + phases.get("owner update", 0.0)] if phases else [0.0], device=dev,
-                         dtype=torch.float64)
+        emb_keys = ("owner rows", "pull rows (P2P)", "requester segment sum + push (inside backward)", "owner update")
+        t = torch.tensor([sum(phases.get(k, 0.0) for k in emb_keys)] if phases else [0.0], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         emb_ms = float(t[0])
         emb_bytes = B3 * (BYTES_FWD_PER_INTERACTION + BYTES_BWD_PER_INTERACTION)      # per GPU: it owns 1/world of every batch's rows
         if rank == 0:
             out["c3"] = {"workload": "c3: " + desc3, "n_gpus": world, "ms_per_step": ms, "samples_per_s": world * N3 / (ms / 1e3),
                          "interactions_per_step_per_gpu": B3, "table_update": "fused_sparse", "tables_gb_per_gpu": per_gpu_gb,
-                         "embedding_path": {"what": "owner-side gather + LayerNorm (ncf_shard_owner_rows) and segment-sum + LayerNorm "
-                                                    "backward + Adam (ncf_shard_owner_update), max over ranks, timed phase by phase",
+                         "embedding_path": {"what": "requester pull gather + LayerNorm over peer memory (ncf_shard_pull_rows), requester "
+                                                    "segment sum + push of the gradient rows (inside ncf_shard_backward_push: that call "
+                                                    "minus the towers' stage calls) and owner segment-sum + LayerNorm backward + Adam "
+                                                    "(ncf_shard_owner_update); max over ranks, timed phase by phase (no overlap)",
                                             "ms": emb_ms, "algorithmic_bytes_per_gpu": emb_bytes,
                                             "achieved": emb_bytes / emb_ms / 1e6 if emb_ms else None, "unit": "GB/s per GPU",
                                             "peak": pk["hbm_gbs"], "frac": emb_bytes / emb_ms / 1e6 / pk["hbm_gbs"] if emb_ms else None,

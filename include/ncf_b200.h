@@ -388,6 +388,19 @@ NCF_API int ncf_sample_batch(const int64_t* pos_user, const int64_t* pos_item, i
                      uint64_t seed, uint64_t step, int64_t* user_ids, int64_t* item_ids, float* targets,
                      void* stream);
 
+/* ---- ranking metrics on the device (reference src/utils/metrics.py) ---------------------------------
+ * scores / targets [groups, M] row-major (targets 1.0 = relevant).  out [n_k][4] = SUMS over the groups of hit@K, ndcg@K,
+ * mrr@K, map@K (calculate_hit_rate :110-134, calculate_ndcg :136-177, calculate_mrr :179-205, calculate_map :207-242);
+ * the caller divides by `groups`.  Order inside a group: score descending, equal scores by index (stable). */
+NCF_API int ncf_rank_metrics(const float* scores, const float* targets, int64_t groups, int32_t M, const int32_t* host_k_values,
+                     int32_t n_k, double* out, void* stream);
+/* out[0] = ROC AUC exactly as sklearn.roc_auc_score (metrics.py:244-252: Mann-Whitney U, ties 1/2; NaN for a single class;
+ * -1 when the smaller class exceeds small_class_cap: call again with 0), out[1] = accuracy at `threshold` (:267-275),
+ * out[2], out[3] = number of positives / negatives.  small_class_cap: upper bound of min(#pos, #neg) if known, else 0. */
+NCF_API int64_t ncf_auc_workspace_bytes(int64_t n, int64_t small_class_cap);
+NCF_API int ncf_auc(const float* scores, const float* targets, int64_t n, int64_t small_class_cap, float threshold, double* out,
+            void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---- tensor-core self test: one 128-row tcgen05 GEMM tile in the three operand arrangements the
  * towers use (0 forward A.B^T, 1 input-gradient A.B, 2 weight-gradient A^T.B); fp32 in/out. */
 NCF_API int ncf_tc_selftest(int32_t mode, int32_t K, int32_t N, const float* A, const float* B, float* D, void* stream);

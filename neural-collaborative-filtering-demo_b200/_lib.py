@@ -145,6 +145,9 @@ _SIGS = {
     "ncf_shard_route_workspace_bytes": (_I64, [_I64]),
     "ncf_shard_route": (C.c_int, [_P, _P, _I64, _I64, _I64, _I32, _P, _P, _P, _P, _I64, _P]),
     "ncf_sample_batch": (C.c_int, [_P, _P, _I64, _I32, _P, _I64, _P, _P, C.c_uint64, C.c_uint64, _P, _P, _P, _P]),
+    "ncf_rank_metrics": (C.c_int, [_P, _P, _I64, _I32, C.POINTER(C.c_int32), _I32, _P, _P]),
+    "ncf_auc_workspace_bytes": (_I64, [_I64, _I64]),
+    "ncf_auc": (C.c_int, [_P, _P, _I64, _I64, C.c_float, _P, _P, _I64, _P]),
     "ncf_tc_selftest": (C.c_int, [_I32, _I32, _I32, _P, _P, _P, _P]),
     "ncf_shard_owner_update": (C.c_int, [C.POINTER(AdamCfg), C.POINTER(Tables), _P, _P, _I32, _P, _I64, _P, _P, _I64, _P]),
 }

@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REPO = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libncf_b200.so")
-SOURCES = ["ncf_abi.cu", "ncf_embed.cu", "ncf_tower_f32.cu", "ncf_score.cu", "ncf_shard.cu", "ncf_tower_tc.cu", "ncf_attn_tc.cu", "ncf_score_tc.cu", "ncf_sampler.cu"]
+SOURCES = ["ncf_abi.cu", "ncf_embed.cu", "ncf_tower_f32.cu", "ncf_score.cu", "ncf_shard.cu", "ncf_tower_tc.cu", "ncf_attn_tc.cu", "ncf_score_tc.cu", "ncf_sampler.cu", "ncf_metrics.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
               "-I" + os.path.join(REPO, "include"), "-I" + CSRC]

@@ -1,15 +1,64 @@
-"""Ranking metrics of the reference (`src/utils/metrics.py`), vectorised so they run on the device
-that holds the scores: HR@K, NDCG@K, MRR@K, MAP@K over [batch, 1+neg] groups
-(:110-242), AUC (:244-265, rank-sum form of sklearn.roc_auc_score) and accuracy (:267-275).
-Same keys and argument meaning as `calculate_metrics` (:9-108)."""
+"""Ranking metrics of the reference (`src/utils/metrics.py`) on the device that holds the scores:
+HR@K, NDCG@K, MRR@K, MAP@K over [batch, 1+neg] groups (:110-242), AUC (:244-265, sklearn.roc_auc_score) and accuracy
+(:267-275).  Same keys and argument meaning as `calculate_metrics` (:9-108).
+
+CUDA tensors go through two kernels of libncf_b200 (`ncf_rank_metrics`: the rank of every positive inside its group, one
+pass, nothing sorted; `ncf_auc`: exact Mann-Whitney count in 64-bit integers).  Host tensors (the reference's own
+`validate` gathers everything to the CPU, trainer.py:387-400) use the vectorised torch code below - this is the
+reference's host function, not part of the GPU hot path."""
 from __future__ import annotations
 
+import ctypes as C
 from typing import Dict, List, Optional
 
 import torch
 
+from . import _lib
+
+
+def _run_auc(P: torch.Tensor, T: torch.Tensor, out4: torch.Tensor, cap: int) -> None:
+    lib = _lib.load()
+    n = P.numel()
+    nbytes = int(lib.ncf_auc_workspace_bytes(n, cap))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=P.device)
+    _lib.check(lib.ncf_auc(_lib.ptr(P), _lib.ptr(T), n, cap, 0.5, _lib.ptr(out4), _lib.ptr(ws), nbytes,
+                           C.c_void_p(torch.cuda.current_stream(P.device).cuda_stream)), "ncf_auc")
+
+
+def _device_metrics(P: torch.Tensor, T: torch.Tensor, k_values: List[int], small_class_cap: int = 0) -> Dict[str, float]:
+    """all metrics for CUDA score / target matrices [groups, M] with one D2H read of 4 * n_k + 4 doubles"""
+    lib = _lib.load()
+    dev = P.device
+    stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    P = P.contiguous().float()
+    T = T.contiguous().float()
+    groups, M = P.shape
+    out: Dict[str, float] = {}
+    res = torch.zeros(4 * len(k_values) + 4, dtype=torch.float64, device=dev)
+    for s in range(0, len(k_values), 8):
+        ks = k_values[s:s + 8]
+        kv = (C.c_int32 * len(ks))(*ks)
+        _lib.check(lib.ncf_rank_metrics(_lib.ptr(P), _lib.ptr(T), groups, M, kv, len(ks),
+                                        C.c_void_p(res.data_ptr() + 32 * s), stream), "ncf_rank_metrics")
+    auc_out = res[4 * len(k_values):]
+    _run_auc(P, T, auc_out, small_class_cap)
+    host = res.cpu()
+    if small_class_cap and float(host[4 * len(k_values)]) == -1.0:      # the capacity hint was too small: full-size network
+        _run_auc(P, T, auc_out, 0)
+        host = res.cpu()
+    for q, k in enumerate(k_values):
+        h = host[4 * q:4 * q + 4] / max(groups, 1)
+        out[f"hit_rate@{k}"], out[f"ndcg@{k}"], out[f"mrr@{k}"], out[f"map@{k}"] = (float(x) for x in h)
+    out["auc"] = float(host[4 * len(k_values)])
+    out["accuracy"] = float(host[4 * len(k_values) + 1])
+    return out
+
 
 def calculate_auc(preds: torch.Tensor, targets: torch.Tensor) -> float:
+    if preds.is_cuda:
+        out4 = torch.zeros(4, dtype=torch.float64, device=preds.device)
+        _run_auc(preds.reshape(-1).contiguous().float(), targets.reshape(-1).to(preds.device).contiguous().float(), out4, 0)
+        return float(out4[0])
     preds = preds.reshape(-1).double()
     pos = targets.reshape(-1) > 0.5
     n_pos = int(pos.sum())
@@ -48,6 +97,15 @@ def calculate_metrics(predictions: torch.Tensor, targets: torch.Tensor, k_values
     P = predictions.reshape(batch_size, M).float()
     T = targets.reshape(batch_size, M).float()
     dev = P.device
+    if P.is_cuda:
+        out = _device_metrics(P, T.to(dev), list(k_values), small_class_cap=2 * batch_size)
+        flat_p, flat_t = P.reshape(-1), T.reshape(-1).to(dev)
+        pm, nm = flat_t == 1, flat_t == 0
+        if bool(pm.any()):
+            out["pos_accuracy"] = calculate_accuracy(flat_p[pm], flat_t[pm])
+        if bool(nm.any()):
+            out["neg_accuracy"] = calculate_accuracy(flat_p[nm], flat_t[nm])
+        return out
     out: Dict[str, float] = {}
     order = torch.sort(P, dim=1, descending=True).indices
     rel_sorted = torch.gather(T, 1, order)

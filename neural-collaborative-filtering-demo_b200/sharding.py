@@ -374,10 +374,28 @@ class ShardedNCFEngine:
         self.loss.mul_(scale)
         self.dense_grad.zero_()
         if push_plan is not None:
+            prof = bool(os.environ.get("NCF_SHARD_PROFILE"))
+            if prof:
+                e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+                e0.record()
             _lib.check(self.lib.ncf_shard_backward_push(C.byref(cfg), _lib.ptr(flat), _lib.ptr(self.dense_grad), _lib.ptr(rows[0]),
                                                         _lib.ptr(rows[1]), _lib.ptr(pos_u), _lib.ptr(pos_i), N, _lib.ptr(grad_out),
                                                         push_plan, _lib.ptr(self._routed["local"]), _lib.ptr(self._route_ws),
                                                         _lib.ptr(ws), nbytes, self._s()), "ncf_shard_backward_push")
+            if prof:
+                # the towers' share of that call, re-run in place through the stage exports (gradients into a scratch buffer):
+                # the rest is the requester's segment sum + push, i.e. embedding-path work
+                e1.record()
+                scratch = self.__dict__.setdefault("_prof_grad", torch.zeros_like(self.dense_grad))
+                _lib.check(self.lib.ncf_mlp_bwd(C.byref(cfg), _lib.ptr(flat), _lib.ptr(scratch), N, _lib.ptr(grad_out), _lib.ptr(ws),
+                                                nbytes, self._s()), "ncf_mlp_bwd")
+                _lib.check(self.lib.ncf_attn_bwd(C.byref(cfg), _lib.ptr(flat), _lib.ptr(scratch), N, _lib.ptr(ws), nbytes, self._s()),
+                           "ncf_attn_bwd")
+                e2.record()
+                torch.cuda.synchronize()
+                p = self.__dict__.setdefault("phase_ms", {})
+                p["requester segment sum + push (inside backward)"] = (p.get("requester segment sum + push (inside backward)", 0.0)
+                                                                       + max(e0.elapsed_time(e1) - e1.elapsed_time(e2), 0.0))
             return None
         gu = b["grads"][0][:rows[0].shape[0]]            # one gradient row per exchanged row
         gi = b["grads"][1][:rows[1].shape[0]]

@@ -615,3 +615,40 @@ def test_model_trainer_checkpoint_keeps_the_reference_format_and_resumes_table_m
     b.train_epoch(batch)
     for wa, wb in zip(a.model._table_params(), b.model._table_params()):
         assert float((wa - wb).abs().max()) < 1e-7
+
+
+def test_device_metric_kernels_match_reference_fixture_and_host_code():
+    """N2: `ncf_rank_metrics` + `ncf_auc` on device tensors vs (a) the values the UNMODIFIED reference `calculate_metrics`
+    produced (tests/golden/metrics.npz) and (b) this repo's host implementation on random groups with ties, several
+    positives per group, a group without positives, and negative scores."""
+    import ncf_b200
+    from ncf_b200 import metrics as M
+    z = load_npz("metrics.npz")
+    from tests.helpers import expected_metrics
+    exp = expected_metrics(z)
+    for name in ("a", "b", "c"):
+        P = torch.from_numpy(z[f"{name}/pred"]).cuda()
+        T = torch.from_numpy(z[f"{name}/target"]).cuda()
+        neg = int(z[f"{name}/neg"])
+        got = ncf_b200.calculate_metrics(P.reshape(-1, 1), T.reshape(-1, 1), [1, 5, 10], P.shape[0], neg)
+        assert set(got) == set(exp[name])
+        for k, v in got.items():
+            if name == "c" and not k.startswith(("auc", "acc", "pos_", "neg_")):
+                continue      # tie order of torch.sort is unspecified in the reference itself
+            assert abs(v - exp[name][k]) < 1e-6, (name, k, v, exp[name][k])
+    g = torch.Generator().manual_seed(0)
+    G, Mm = 333, 100
+    P = (torch.randn(G, Mm, generator=g) * 0.5).round(decimals=1)            # many exact ties, negative values
+    T = (torch.rand(G, Mm, generator=g) < 0.03).float()
+    T[:, 0] = 1.0
+    T[7] = 0.0                                                                # a group without any positive
+    host = M.calculate_metrics(P, T, [1, 5, 10, 200], batch_size=G, negative_samples=Mm - 1)
+    dev = M.calculate_metrics(P.cuda(), T.cuda(), [1, 5, 10, 200], batch_size=G, negative_samples=Mm - 1)
+    for k, v in host.items():
+        assert abs(dev[k] - v) < 2e-6, (k, dev[k], v)
+    # AUC alone, both class balances (the kernel sorts the smaller class), and the single-class case
+    s = torch.rand(5000, generator=g)
+    for frac in (0.02, 0.5, 0.97):
+        t = (torch.rand(5000, generator=g) < frac).float()
+        assert abs(M.calculate_auc(s.cuda(), t.cuda()) - M.calculate_auc(s, t)) < 1e-12
+    assert M.calculate_auc(s.cuda(), torch.ones(5000).cuda()) != M.calculate_auc(s.cuda(), torch.ones(5000).cuda())   # NaN
