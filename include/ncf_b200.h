@@ -284,6 +284,15 @@ NCF_API int ncf_score_topk_tc(const ncf_tables* tables, const float* dense, cons
                       int64_t* topk_idx, float* topk_score,
                       void* workspace, int64_t workspace_bytes, void* stream);
 
+/* Exact top-k of sigmoid(q . v_i + bias_i) for n raw 64-d query rows against I vectors, same kernels and the same order
+ * (score descending, ties -> lowest index) as ncf_score_topk: the nearest-neighbour step behind the embedding export
+ * (src/inference/generate_embeddings.py:184-236 feeds a cosine Tree-AH index, setup_tree_ah_endpoint.py:25-32; with
+ * L2-normalised rows the dot product IS the cosine, and the monotone sigmoid keeps the sort keys positive).
+ * image: ncf_item_image(vectors, bias) for the tensor-core pre-filter, or NULL. */
+NCF_API int64_t ncf_dot_topk_workspace_bytes(int64_t n, int64_t I, int32_t k, int32_t with_image);
+NCF_API int ncf_dot_topk(const float* queries, int64_t n, const float* vectors, const float* bias, const void* image, int64_t I,
+                 int32_t k, int64_t* topk_idx, float* topk_score, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---- row-wise sharding (torchrec ROW_WISE convention) ------------------------- */
 /* block = ceil(rows/world); owner = id / block; local = id % block.  Buckets ids by owner:
  * counts[world], perm[n] (stable: position of each id in owner-major order), local_ids[n]

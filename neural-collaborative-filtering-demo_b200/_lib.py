@@ -130,6 +130,8 @@ _SIGS = {
     "ncf_item_image": (C.c_int, [_P, _P, _I64, _P, _P]),
     "ncf_score_topk_tc_workspace_bytes": (_I64, [_I64, _I64, _I32]),
     "ncf_score_topk_tc": (C.c_int, [C.POINTER(Tables), _P, _P, _P, _P, _P, _I64, _I64, _I32, _P, _P, _P, _I64, _P]),
+    "ncf_dot_topk_workspace_bytes": (_I64, [_I64, _I64, _I32, _I32]),
+    "ncf_dot_topk": (C.c_int, [_P, _I64, _P, _P, _P, _I64, _I32, _P, _P, _P, _I64, _P]),
     "ncf_shard_bucketize_workspace_bytes": (_I64, [_I64, _I32]),
     "ncf_shard_bucketize": (C.c_int, [_P, _I64, _I64, _I32, _P, _P, _P, _P, _I64, _P]),
     "ncf_shard_bucketize_runs_workspace_bytes": (_I64, [_I64, _I32]),

@@ -116,11 +116,16 @@ __global__ void __launch_bounds__(TK_THREADS, 1) score_topk_kernel(const float* 
   for (int uu = warp; uu < TK_UT; uu += TK_THREADS / 32) {
     float x0 = 0.f, x1 = 0.f;
     if (uu < nu) {
-      const int64_t uid = user_ids[u0 + uu];
+      const int64_t uid = user_ids ? user_ids[u0 + uu] : u0 + uu;
       if (bad_id(uid, rows_user)) flag_status(status, NCF_STATUS_BAD_USER_ID);
       const float* row = t_umf + clamp_id(uid, rows_user) * D;
       x0 = row[lane];
       x1 = row[lane + 32];
+    }
+    if (!dense) {      // raw query rows (ncf_dot_topk): no LayerNorm
+      s_u[uu * TK_LD + lane] = x0;
+      s_u[uu * TK_LD + lane + 32] = x1;
+      continue;
     }
     const float mean = warp_sum(x0 + x1) * (1.0f / D);
     const float d0 = x0 - mean, d1 = x1 - mean;
@@ -273,19 +278,23 @@ __global__ void __launch_bounds__(TK_THREADS) score_topk_small_kernel(const floa
     __shared__ float s_tmp[TKS_UT][D];
     float x = 0.f;
     if (uu < nu) {
-      const int64_t uid = user_ids[u0 + uu];
+      const int64_t uid = user_ids ? user_ids[u0 + uu] : u0 + uu;
       if (bad_id(uid, rows_user)) flag_status(status, NCF_STATUS_BAD_USER_ID);
       x = t_umf[clamp_id(uid, rows_user) * D + c];
     }
     s_tmp[uu][c] = x;
     __syncthreads();
-    float mean = 0.f;
-    for (int k = 0; k < D; ++k) mean += s_tmp[uu][k];
-    mean *= (1.0f / D);
-    float var = 0.f;
-    for (int k = 0; k < D; ++k) var = fmaf(s_tmp[uu][k] - mean, s_tmp[uu][k] - mean, var);
-    const float rstd = rsqrtf(var * (1.0f / D) + LN_EPS);
-    s_u[uu][c] = fmaf((x - mean) * rstd, __ldg(dense + NCF_OFF(NCF_P_MF_NORM_W) + c), __ldg(dense + NCF_OFF(NCF_P_MF_NORM_B) + c));
+    if (!dense) {      // raw query rows (ncf_dot_topk): no LayerNorm
+      s_u[uu][c] = x;
+    } else {
+      float mean = 0.f;
+      for (int k = 0; k < D; ++k) mean += s_tmp[uu][k];
+      mean *= (1.0f / D);
+      float var = 0.f;
+      for (int k = 0; k < D; ++k) var = fmaf(s_tmp[uu][k] - mean, s_tmp[uu][k] - mean, var);
+      const float rstd = rsqrtf(var * (1.0f / D) + LN_EPS);
+      s_u[uu][c] = fmaf((x - mean) * rstd, __ldg(dense + NCF_OFF(NCF_P_MF_NORM_W) + c), __ldg(dense + NCF_OFF(NCF_P_MF_NORM_B) + c));
+    }
   }
   for (int i = threadIdx.x; i < TKS_UT * TK_BUF; i += TK_THREADS) (&s_buf[0][0])[i] = 0ull;
   if (threadIdx.x < TKS_UT) {
@@ -526,10 +535,22 @@ extern "C" int64_t ncf_score_topk_workspace_bytes(int64_t n_users, int64_t I, in
   return align_up(std::max<int64_t>(n_users, 1) * topk_splits(n_users, I) * TK_KMAX * 8, 256);
 }
 
+namespace ncf {
+int score_topk_impl(const ncf_tables* T, const float* dense, const float* p_hat, const float* g, const int64_t* user_ids,
+                    int64_t n_users, int64_t I, int32_t k, int64_t* topk_idx, float* topk_score, void* workspace,
+                    int64_t workspace_bytes, void* stream);
+}
 extern "C" int ncf_score_topk(const ncf_tables* T, const float* dense, const float* p_hat, const float* g,
                               const int64_t* user_ids, int64_t n_users, int64_t I, int32_t k, int64_t* topk_idx,
                               float* topk_score, void* workspace, int64_t workspace_bytes, void* stream) {
-  NCF_REQUIRE(T && dense && p_hat && g && user_ids && topk_idx && topk_score && workspace, "score_topk: null argument");
+  NCF_REQUIRE(dense && user_ids, "score_topk: null argument");
+  return score_topk_impl(T, dense, p_hat, g, user_ids, n_users, I, k, topk_idx, topk_score, workspace, workspace_bytes, stream);
+}
+// dense == NULL: the "user" rows are raw query vectors (no LayerNorm); user_ids == NULL: rows 0 .. n_users-1
+int ncf::score_topk_impl(const ncf_tables* T, const float* dense, const float* p_hat, const float* g, const int64_t* user_ids,
+                         int64_t n_users, int64_t I, int32_t k, int64_t* topk_idx, float* topk_score, void* workspace,
+                         int64_t workspace_bytes, void* stream) {
+  NCF_REQUIRE(T && p_hat && g && topk_idx && topk_score && workspace, "score_topk: null argument");
   NCF_REQUIRE(k >= 1 && k <= TK_KMAX, "score_topk: k=%d outside [1,%d]", k, TK_KMAX);
   NCF_REQUIRE(I >= 1 && I < ((int64_t)1 << 32) - 1, "score_topk: bad catalogue size");
   if (n_users == 0) return NCF_OK;

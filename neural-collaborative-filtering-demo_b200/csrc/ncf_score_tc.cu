@@ -145,18 +145,20 @@ __global__ void __launch_bounds__(SC_THREADS, 1) score_tc_kernel(ScoreTcArgs A) 
   for (int uu = warp; uu < SC_UT; uu += SC_THREADS / 32) {
     float x0 = 0.f, x1 = 0.f;
     if (uu < nu) {
-      const int64_t uid = A.user_ids[u0 + uu];
+      const int64_t uid = A.user_ids ? A.user_ids[u0 + uu] : u0 + uu;
       if (bad_id(uid, A.rows_user)) flag_status(A.status, NCF_STATUS_BAD_USER_ID);
       const float* r = A.t_umf + clamp_id(uid, A.rows_user) * D;
       x0 = r[lane];
       x1 = r[lane + 32];
     }
-    const float mean = warp_sum(x0 + x1) * (1.0f / D);
-    const float d0 = x0 - mean, d1 = x1 - mean;
-    const float rstd = rsqrtf(warp_sum(d0 * d0 + d1 * d1) * (1.0f / D) + LN_EPS);
-    float y0 = fmaf(d0 * rstd, __ldg(A.dense + NCF_OFF(NCF_P_MF_NORM_W) + lane), __ldg(A.dense + NCF_OFF(NCF_P_MF_NORM_B) + lane));
-    float y1 = fmaf(d1 * rstd, __ldg(A.dense + NCF_OFF(NCF_P_MF_NORM_W) + lane + 32),
-                    __ldg(A.dense + NCF_OFF(NCF_P_MF_NORM_B) + lane + 32));
+    float y0 = x0, y1 = x1;                  // A.dense == NULL: raw query rows (ncf_dot_topk), no LayerNorm
+    if (A.dense) {
+      const float mean = warp_sum(x0 + x1) * (1.0f / D);
+      const float d0 = x0 - mean, d1 = x1 - mean;
+      const float rstd = rsqrtf(warp_sum(d0 * d0 + d1 * d1) * (1.0f / D) + LN_EPS);
+      y0 = fmaf(d0 * rstd, __ldg(A.dense + NCF_OFF(NCF_P_MF_NORM_W) + lane), __ldg(A.dense + NCF_OFF(NCF_P_MF_NORM_B) + lane));
+      y1 = fmaf(d1 * rstd, __ldg(A.dense + NCF_OFF(NCF_P_MF_NORM_W) + lane + 32), __ldg(A.dense + NCF_OFF(NCF_P_MF_NORM_B) + lane + 32));
+    }
     if (uu >= nu) {
       y0 = 0.f;
       y1 = 0.f;
@@ -417,10 +419,41 @@ extern "C" int64_t ncf_score_topk_tc_workspace_bytes(int64_t n_users, int64_t I,
   return align_up(n * ns * SC_KMAX * 8, 256) + align_up(tiles * ns * SC_CTA_WS, 256);
 }
 
+namespace ncf {
+int score_topk_impl(const ncf_tables* T, const float* dense, const float* p_hat, const float* g, const int64_t* user_ids,
+                    int64_t n_users, int64_t I, int32_t k, int64_t* topk_idx, float* topk_score, void* workspace,
+                    int64_t workspace_bytes, void* stream);
+static int score_topk_tc_impl(const ncf_tables* T, const float* dense, const float* p_hat, const float* g, const void* img,
+                              const int64_t* user_ids, int64_t n_users, int64_t I, int32_t k, int64_t* topk_idx,
+                              float* topk_score, void* workspace, int64_t workspace_bytes, void* stream);
+}
 extern "C" int ncf_score_topk_tc(const ncf_tables* T, const float* dense, const float* p_hat, const float* g, const void* img,
                                  const int64_t* user_ids, int64_t n_users, int64_t I, int32_t k, int64_t* topk_idx,
                                  float* topk_score, void* workspace, int64_t workspace_bytes, void* stream) {
-  NCF_REQUIRE(T && dense && p_hat && g && img && user_ids && topk_idx && topk_score && workspace, "score_topk_tc: null argument");
+  NCF_REQUIRE(dense && user_ids, "score_topk_tc: null argument");
+  return score_topk_tc_impl(T, dense, p_hat, g, img, user_ids, n_users, I, k, topk_idx, topk_score, workspace, workspace_bytes, stream);
+}
+
+// Exact top-k of sigmoid(q . v_i + bias_i) for raw 64-d query rows against I vectors (order: score descending, ties -> lowest
+// index): the retrieval step of the serving design (cosine similarity when both sides are L2-normalised; the sigmoid is
+// monotone and keeps the keys positive).  image: ncf_item_image(vectors, bias) or NULL (exact fp32 kernel only).
+extern "C" int64_t ncf_dot_topk_workspace_bytes(int64_t n, int64_t I, int32_t k, int32_t with_image) {
+  return with_image ? ncf_score_topk_tc_workspace_bytes(n, I, k) : ncf_score_topk_workspace_bytes(n, I, k);
+}
+extern "C" int ncf_dot_topk(const float* queries, int64_t n, const float* vectors, const float* bias, const void* image, int64_t I,
+                            int32_t k, int64_t* topk_idx, float* topk_score, void* workspace, int64_t workspace_bytes, void* stream) {
+  NCF_REQUIRE(queries && vectors && bias && n >= 0, "dot_topk: null argument");
+  ncf_tables T{};
+  T.w[0] = const_cast<float*>(queries);
+  T.rows_user = std::max<int64_t>(n, 1);
+  if (image) return score_topk_tc_impl(&T, nullptr, vectors, bias, image, nullptr, n, I, k, topk_idx, topk_score, workspace, workspace_bytes, stream);
+  return score_topk_impl(&T, nullptr, vectors, bias, nullptr, n, I, k, topk_idx, topk_score, workspace, workspace_bytes, stream);
+}
+
+static int ncf::score_topk_tc_impl(const ncf_tables* T, const float* dense, const float* p_hat, const float* g, const void* img,
+                                   const int64_t* user_ids, int64_t n_users, int64_t I, int32_t k, int64_t* topk_idx,
+                                   float* topk_score, void* workspace, int64_t workspace_bytes, void* stream) {
+  NCF_REQUIRE(T && p_hat && g && img && topk_idx && topk_score && workspace, "score_topk_tc: null argument");
   NCF_REQUIRE(k >= 1 && k <= SC_KMAX, "score_topk_tc: k=%d outside [1,%d]", k, SC_KMAX);
   NCF_REQUIRE(I >= 1 && I < ((int64_t)1 << 32) - 1, "score_topk_tc: bad catalogue size");
   if (n_users == 0) return NCF_OK;

@@ -107,7 +107,7 @@ def calculate_metrics(predictions: torch.Tensor, targets: torch.Tensor, k_values
             out["neg_accuracy"] = calculate_accuracy(flat_p[nm], flat_t[nm])
         return out
     out: Dict[str, float] = {}
-    order = torch.sort(P, dim=1, descending=True).indices
+    order = torch.sort(P, dim=1, descending=True, stable=True).indices      # ties: lower index first, as the kernel
     rel_sorted = torch.gather(T, 1, order)
     ideal = torch.sort(T, dim=1, descending=True).values
     for k in k_values:
