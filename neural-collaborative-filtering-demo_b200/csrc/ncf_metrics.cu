@@ -105,7 +105,8 @@ __global__ void __launch_bounds__(256) rank_metrics_kernel(RankArgs A) {
 // ---- AUC ---------------------------------------------------------------------------------------------------------
 // order-preserving key of a float (handles negative scores too): larger float <=> larger key
 __device__ __forceinline__ uint32_t float_key(float x) {
-  const uint32_t b = __float_as_uint(x);
+  uint32_t b = __float_as_uint(x);
+  if (b == 0x80000000u) b = 0u;        // -0.0 == +0.0
   return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
 }
 // counts[0] = positives, counts[1] = negatives, counts[2] = accuracy hits at the threshold

@@ -789,6 +789,15 @@ class ShardedCatalogueScorer:
             self.g = torch.cat(gs)[:e.I].contiguous()
         else:
             self.p_hat, self.g = p_local[:e.I].contiguous(), g_local[:e.I].contiguous()
+        # large catalogues: operand images of the tensor-core pre-filter, as CatalogueScorer builds them
+        self.img = None
+        if e.I >= self.TC_MIN_ITEMS and os.environ.get("NCF_SCORE_TC", "1") != "0":
+            self.img = torch.empty(int(self.lib.ncf_item_image_bytes(e.I)), dtype=torch.uint8, device=dev)
+            _lib.check(self.lib.ncf_item_image(_lib.ptr(self.p_hat), _lib.ptr(self.g), e.I, _lib.ptr(self.img), e._s()),
+                       "ncf_item_image")
+
+    TC_MIN_ITEMS = 1 << 16
+    TC_MIN_USERS = 64
 
     @torch.no_grad()
     def topk_local_users(self, local_user_ids: torch.Tensor, k: int):
@@ -801,9 +810,16 @@ class ShardedCatalogueScorer:
         sc = torch.empty(n, k_eff, dtype=torch.float32, device=e.device)
         if n == 0:
             return idx, sc
+        tabs = e._tables()
+        if self.img is not None and n >= self.TC_MIN_USERS:      # same bits as the exact kernel (tests/test_gpu_parity.py)
+            nbytes = int(self.lib.ncf_score_topk_tc_workspace_bytes(n, e.I, k_eff))
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=e.device)
+            _lib.check(self.lib.ncf_score_topk_tc(C.byref(tabs), _lib.ptr(e.model._flat), _lib.ptr(self.p_hat), _lib.ptr(self.g),
+                                                  _lib.ptr(self.img), _lib.ptr(u), n, e.I, k_eff, _lib.ptr(idx), _lib.ptr(sc),
+                                                  _lib.ptr(ws), nbytes, e._s()), "ncf_score_topk_tc")
+            return idx, sc
         nbytes = int(self.lib.ncf_score_topk_workspace_bytes(n, e.I, k_eff))
         ws = torch.empty(nbytes, dtype=torch.uint8, device=e.device)
-        tabs = e._tables()
         _lib.check(self.lib.ncf_score_topk(C.byref(tabs), _lib.ptr(e.model._flat), _lib.ptr(self.p_hat), _lib.ptr(self.g),
                                            _lib.ptr(u), n, e.I, k_eff, _lib.ptr(idx), _lib.ptr(sc), _lib.ptr(ws), nbytes,
                                            e._s()), "ncf_score_topk")
