@@ -947,10 +947,13 @@ def extra_blocks(args, world, rank, dev, precision, barrier):
         users3, items3, B3, desc3 = WORKLOADS["c3"]
         N3 = B3 * S
         per_gpu_gb = 2 * ((users3 + items3) // world) * 256 * 3 / 1e9
-        free = torch.cuda.mem_get_info(dev)[0] / 1e9
+        ft = torch.tensor([torch.cuda.mem_get_info(dev)[0] / 1e9], device=dev)
+        dist.all_reduce(ft, op=dist.ReduceOp.MIN)               # the same decision on every rank
+        free = float(ft[0])
         if per_gpu_gb + 12 > free:
             if rank == 0:
                 out["c3"] = {"unavailable": f"needs {per_gpu_gb:.0f} GB per GPU for tables + Adam state, {free:.0f} GB free"}
+            out.update(sharded_score_block(args, world, rank, dev, barrier))
             return out
         model = build_model(1, 1, dev, precision)
         eng = ShardedNCFEngine(model, users3, items3, lr=1e-3, weight_decay=1e-5, table_mode="fused_sparse")
