@@ -22,12 +22,13 @@ constexpr int SC_UT = 128;                 // users per CTA (M)
 constexpr int SC_IT = 256;                 // items per tile (N)
 constexpr int SC_KMAX = 128;               // running list length (k <= 128), same as the exact kernel
 constexpr int SC_CAP = 512;                // list + candidates per user
-constexpr uint32_t SC_IMG = SC_IT * 64 * 2;                 // bf16 operand image of one item tile
-constexpr uint32_t SC_TILE_BYTES = SC_IMG + 2 * SC_IT * 4;  // + g[256] + margin[256]
+constexpr int SC_K = 80;                   // GEMM depth: 64 embedding columns + [g_hi, g_lo, margin, slack] + 12 zero columns
+constexpr uint32_t SC_IMG = SC_IT * SC_K * 2;               // bf16 operand image of one item tile
+constexpr uint32_t SC_TILE_BYTES = SC_IMG;
 constexpr float SC_EPS = 0.0078125f * 1.01f;   // 1.01 * 2^-7, see the bound above
 
-constexpr uint32_t SCS_A = 0;                               // [128][64] bf16 image            16 KB
-constexpr uint32_t SCS_U = SCS_A + SC_UT * 64 * 2;          // [128][64] fp32 LN'd user rows   32 KB
+constexpr uint32_t SCS_A = 0;                               // [128][80] bf16 image            20 KB
+constexpr uint32_t SCS_U = SCS_A + SC_UT * SC_K * 2;        // [128][64] fp32 LN'd user rows   32 KB
 constexpr int SC_NB = 3;                                    // item tile buffers: a load has a whole iteration to land
 constexpr uint32_t SCS_B = SCS_U + SC_UT * 64 * 4;          // 3 x item tile                   102 KB
 constexpr uint32_t SCS_SORT = SCS_B + SC_NB * SC_TILE_BYTES;    // 512 keys being merged         4 KB
@@ -47,6 +48,22 @@ __device__ __forceinline__ unsigned long long sc_key(float score, uint32_t idx) 
 }
 
 // ---- item tile images ----------------------------------------------------------------------------------
+// The per-item terms of the bound ride in the GEMM itself (columns 64..67 of the operand images):
+//     bound(u, i) = sum_k bf16(u_k) bf16(p_ik)  +  1 * g_hi  +  1 * g_lo  +  up(||u||) * up(margin_i)  +  1 * up(slack_i)
+// g = g_hi + g_lo up to 2^-18 |g| (two bf16 pieces); margin_i = 1.01 * 2^-7 ||p_i|| as before; slack_i = 2^-15 |g_i| + the
+// split's remainder covers the fp32 accumulation of the extra terms; up() rounds to the next bf16 ABOVE, so every
+// replacement errs upwards and the accumulator is an upper bound of the exact logit by construction.  The scan of a pair
+// is then one subtraction (bound - threshold) and one funnel shift: no per-item loads in the epilogue at all.
+__device__ __forceinline__ uint16_t bf16_bits_up(float x) {          // x >= 0: smallest bf16 >= x
+  __nv_bfloat16 b = __float2bfloat16_rn(x);
+  uint16_t bits = *reinterpret_cast<uint16_t*>(&b);
+  if (__bfloat162float(b) < x) ++bits;
+  return bits;
+}
+__device__ __forceinline__ uint16_t bf16_bits_rn(float x) {
+  __nv_bfloat16 b = __float2bfloat16_rn(x);
+  return *reinterpret_cast<uint16_t*>(&b);
+}
 // thread = (item, 8-column chunk); the 8 chunk threads of an item are adjacent lanes
 __global__ void __launch_bounds__(256) item_image_kernel(const float* __restrict__ p_hat, const float* __restrict__ g, int64_t I,
                                                          uint8_t* __restrict__ img) {
@@ -66,12 +83,26 @@ __global__ void __launch_bounds__(256) item_image_kernel(const float* __restrict
   ss += __shfl_xor_sync(0xffffffffu, ss, 4);
   uint8_t* tile = img + (i / SC_IT) * SC_TILE_BYTES;
   const uint32_t r = (uint32_t)(i % SC_IT);
-  *reinterpret_cast<uint4*>(tile + tile_off(r, 8 * j, 64)) =
+  *reinterpret_cast<uint4*>(tile + tile_off(r, 8 * j, SC_K)) =
       make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(b.x, b.y), pack_bf16(b.z, b.w));
   if (j == 0) {
-    float* tail = reinterpret_cast<float*>(tile + SC_IMG);
-    tail[r] = i < I ? __ldg(g + i) : -INFINITY;          // padding items can never pass the filter
-    tail[SC_IT + r] = SC_EPS * sqrtf(ss) * 1.0001f;      // rounded up a little: the bound must stay a bound
+    uint32_t w0, w1;
+    if (i < I) {
+      const float gi = __ldg(g + i);
+      const uint16_t hi = bf16_bits_rn(gi);
+      const float rem = gi - __uint_as_float((uint32_t)hi << 16);                 // exact in fp32
+      const uint16_t lo = bf16_bits_rn(rem);
+      const float rem2 = fabsf(rem - __uint_as_float((uint32_t)lo << 16));
+      const uint16_t mg = bf16_bits_up(SC_EPS * sqrtf(ss) * 1.0001f);
+      const uint16_t sl = bf16_bits_up(fabsf(gi) * 3.0517578125e-5f + rem2 + 1e-30f);
+      w0 = (uint32_t)hi | ((uint32_t)lo << 16);
+      w1 = (uint32_t)mg | ((uint32_t)sl << 16);
+    } else {            // padding items can never pass the filter: a huge negative bias, no NaN
+      w0 = 0xff00u;     // bf16(-1.7e38)
+      w1 = 0u;
+    }
+    *reinterpret_cast<uint4*>(tile + tile_off(r, 64, SC_K)) = make_uint4(w0, w1, 0u, 0u);
+    *reinterpret_cast<uint4*>(tile + tile_off(r, 72, SC_K)) = make_uint4(0u, 0u, 0u, 0u);
   }
 }
 
@@ -165,9 +196,14 @@ __global__ void __launch_bounds__(SC_THREADS, 1) score_tc_kernel(ScoreTcArgs A) 
     }
     s_u[uu * 64 + lane] = y0;
     s_u[uu * 64 + lane + 32] = y1;
-    reinterpret_cast<__nv_bfloat16*>(smem + SCS_A + tile_off(uu, lane, 64))[0] = __float2bfloat16_rn(y0);
-    reinterpret_cast<__nv_bfloat16*>(smem + SCS_A + tile_off(uu, lane + 32, 64))[0] = __float2bfloat16_rn(y1);
+    reinterpret_cast<__nv_bfloat16*>(smem + SCS_A + tile_off(uu, lane, SC_K))[0] = __float2bfloat16_rn(y0);
+    reinterpret_cast<__nv_bfloat16*>(smem + SCS_A + tile_off(uu, lane + 32, SC_K))[0] = __float2bfloat16_rn(y1);
     const float nn = sqrtf(warp_sum(y0 * y0 + y1 * y1)) * 1.0001f;
+    if (lane < 16) {      // columns 64..79: [1, 1, up(||u||), 1, 0 ...] = the coefficients of g_hi, g_lo, margin, slack
+      uint16_t c = 0;
+      if (uu < nu) c = (lane == 0 || lane == 1 || lane == 3) ? (uint16_t)0x3f80 : (lane == 2 ? bf16_bits_up(nn) : (uint16_t)0);
+      reinterpret_cast<uint16_t*>(smem + SCS_A + tile_off(uu, 64 + lane, SC_K))[0] = c;
+    }
     if (lane == 0) {
       s_nu[uu] = nn;
       s_lthr[uu] = uu < nu ? -INFINITY : INFINITY;      // rows without a user never pass
@@ -208,8 +244,8 @@ __global__ void __launch_bounds__(SC_THREADS, 1) score_tc_kernel(ScoreTcArgs A) 
     const int nb = (int)(t % SC_NB), b = (int)(t & 1);
     mbar_wait(&full[nb], (uint32_t)((t / SC_NB) & 1));
     fence_after_sync();
-    issue_gemm(tmem + 256 * b, sA, 128, 64 * 16, 256, smem_addr(smem + SCS_B + nb * SC_TILE_BYTES), 128, 64 * 16, 256,
-               make_idesc(128, SC_IT, false, false), 4, false);
+    issue_gemm(tmem + 256 * b, sA, 128, SC_K * 16, 256, smem_addr(smem + SCS_B + nb * SC_TILE_BYTES), 128, SC_K * 16, 256,
+               make_idesc(128, SC_IT, false, false), SC_K / 16, false);
     mma_commit(&accb[b]);
   };
   // merge the candidate buffer of one user into its running list (whole CTA): sort, keep the best KMAX, refresh the
@@ -334,26 +370,19 @@ __global__ void __launch_bounds__(SC_THREADS, 1) score_tc_kernel(ScoreTcArgs A) 
     }
     mbar_wait(&accb[b], (uint32_t)((t >> 1) & 1));       // every warp polls for itself: one CTA barrier per tile, below
     fence_after_sync();
-    const float* tail = reinterpret_cast<const float*>(smem + SCS_B + (int)(t % SC_NB) * SC_TILE_BYTES + SC_IMG);
-    const float lthr = s_lthr[row], nrm = s_nu[row];
+    const float lthr = s_lthr[row];
     const int64_t base = (t_begin + t) * SC_IT;
 #pragma unroll 1
     for (int ch = 0; ch < 2; ++ch) {
       float z[32];
       tmem_ld32(tmem + 256 * b + lane_addr + cq * 64 + ch * 32, z);
       const int j0 = cq * 64 + ch * 32;
-      // three instructions per pair: d = (g - lthr) + z, diff = nrm * margin + d = bound - lthr, and a funnel shift
-      // that appends diff's sign bit to the mask (element j ends up at bit 31 - j; set = below the threshold)
+      // two instructions per pair: the accumulator IS the upper bound of the logit (bias, margin and slack ride in the
+      // GEMM), so diff = bound - lthr and a funnel shift that appends diff's sign bit to the mask (element j ends up at
+      // bit 31 - j; set = below the threshold)
       uint32_t miss = 0;
 #pragma unroll
-      for (int j4 = 0; j4 < 8; ++j4) {
-        const float4 g4 = *reinterpret_cast<const float4*>(tail + j0 + 4 * j4);
-        const float4 m4 = *reinterpret_cast<const float4*>(tail + SC_IT + j0 + 4 * j4);
-        miss = __funnelshift_l(__float_as_uint(fmaf(nrm, m4.x, (g4.x - lthr) + z[4 * j4 + 0])), miss, 1);
-        miss = __funnelshift_l(__float_as_uint(fmaf(nrm, m4.y, (g4.y - lthr) + z[4 * j4 + 1])), miss, 1);
-        miss = __funnelshift_l(__float_as_uint(fmaf(nrm, m4.z, (g4.z - lthr) + z[4 * j4 + 2])), miss, 1);
-        miss = __funnelshift_l(__float_as_uint(fmaf(nrm, m4.w, (g4.w - lthr) + z[4 * j4 + 3])), miss, 1);
-      }
+      for (int j = 0; j < 32; ++j) miss = __funnelshift_l(__float_as_uint(z[j] - lthr), miss, 1);
       uint32_t hit = ~miss;
       while (hit) {                                      // rare after the first tiles
         const int j = __clz(hit);                        // element j sits at bit 31 - j
