@@ -126,6 +126,46 @@ __device__ __forceinline__ void cta_sort_desc(unsigned long long* a, int tid) {
   __syncthreads();
 }
 
+// ---- warp-level descending sort of 512 keys (16 per lane; element e = lane * 16 + r) ---------------------------------
+// A candidate-list merge used to be one 512-key bitonic network run by the WHOLE CTA (45 stages, a CTA barrier each, one
+// user at a time: a quarter of the kernel's time).  Here a warp sorts a user's list on its own - register-local stages for
+// partner distances below 16, shuffles above - so the 16 warps merge 16 users at once and no barrier is involved.
+template <int J>
+__device__ __forceinline__ void sort_local_stage(unsigned long long (&v)[16], int lane, int k) {
+#pragma unroll
+  for (int r = 0; r < 16; ++r) {
+    if ((r & J) == 0) {
+      const bool desc = (((lane << 4) | r) & k) == 0;
+      const unsigned long long a = v[r], b = v[r | J];
+      const unsigned long long hi = a > b ? a : b, lo = a > b ? b : a;
+      v[r] = desc ? hi : lo;
+      v[r | J] = desc ? lo : hi;
+    }
+  }
+}
+__device__ __forceinline__ void warp_sort512_desc(unsigned long long (&v)[16], int lane) {
+#pragma unroll 1
+  for (int k = 2; k <= 512; k <<= 1) {
+#pragma unroll 1
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      if (j >= 16) {
+        const int lj = j >> 4;                                   // partner lane distance
+        const bool lower = (lane & lj) == 0;                     // this lane holds the lower index of every pair
+        const bool desc = ((lane << 4) & k) == 0;                // k >= 32 here: the block direction depends on the lane only
+        const bool keep_max = lower == desc;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+          const unsigned long long o = __shfl_xor_sync(0xffffffffu, v[r], lj);
+          v[r] = keep_max ? (v[r] > o ? v[r] : o) : (v[r] > o ? o : v[r]);
+        }
+      } else if (j == 8) sort_local_stage<8>(v, lane, k);
+      else if (j == 4) sort_local_stage<4>(v, lane, k);
+      else if (j == 2) sort_local_stage<2>(v, lane, k);
+      else sort_local_stage<1>(v, lane, k);
+    }
+  }
+}
+
 struct ScoreTcArgs {
   const float* t_umf;
   const float* dense;
@@ -248,19 +288,28 @@ __global__ void __launch_bounds__(SC_THREADS, 1) score_tc_kernel(ScoreTcArgs A) 
                make_idesc(128, SC_IT, false, false), SC_K / 16, false);
     mma_commit(&accb[b]);
   };
-  // merge the candidate buffer of one user into its running list (whole CTA): sort, keep the best KMAX, refresh the
-  // thresholds.  Called by all threads with the same uu.
-  unsigned long long* s_sort = reinterpret_cast<unsigned long long*>(smem + SCS_SORT);
-  auto merge_user = [&](int uu) {
+  // merge the candidate buffer of one user into its running list: ONE WARP sorts the (at most 512) keys in registers,
+  // keeps the best KMAX and refreshes the thresholds (dst != null: also emits the list - the final pass).
+  auto warp_merge = [&](int uu, unsigned long long* dst) {
     const int cnt = min(s_cnt[uu], SC_CAP);
     unsigned long long* c = cand + (int64_t)uu * SC_CAP;
-    __syncthreads();
-    for (int i = tid; i < SC_CAP; i += SC_THREADS) s_sort[i] = i < cnt ? c[i] : 0ull;
-    cta_sort_desc(s_sort, tid);
-    for (int i = tid; i < SC_KMAX; i += SC_THREADS) c[i] = s_sort[i];
-    if (tid == 0) {
+    unsigned long long v[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      const int e = lane * 16 + r;
+      v[r] = e < cnt ? __ldcg(c + e) : 0ull;
+    }
+    warp_sort512_desc(v, lane);
+    if (lane < SC_KMAX / 16) {
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        c[lane * 16 + r] = v[r];
+        if (dst) dst[lane * 16 + r] = v[r];
+      }
+    }
+    const unsigned long long kth = __shfl_sync(0xffffffffu, v[15], SC_KMAX / 16 - 1);
+    if (lane == 0) {
       s_cnt[uu] = SC_KMAX;
-      const unsigned long long kth = s_sort[SC_KMAX - 1];
       s_kthr[uu] = kth;
       const float sk = __uint_as_float((uint32_t)(kth >> 32));
       float lt = -INFINITY;
@@ -270,19 +319,23 @@ __global__ void __launch_bounds__(SC_THREADS, 1) score_tc_kernel(ScoreTcArgs A) 
       }
       s_lthr[uu] = lt;
     }
-    __syncthreads();
   };
   auto mark_merge = [&](int r) { atomicOr(&s_mmask[r >> 5], 1u << (r & 31)); };
-  auto run_merges = [&]() {            // all threads; merges every marked user
+  auto run_merges = [&]() {            // all threads; the marked users are dealt round-robin to the 16 warps
     __syncthreads();
+    uint32_t m[SC_UT / 32];
+#pragma unroll
+    for (int wd = 0; wd < SC_UT / 32; ++wd) m[wd] = s_mmask[wd];
+    __syncthreads();
+    if (tid < SC_UT / 32) s_mmask[tid] = 0u;
+    int nth = 0;
+#pragma unroll
     for (int wd = 0; wd < SC_UT / 32; ++wd) {
-      uint32_t m = s_mmask[wd];
-      __syncthreads();
-      if (tid == 0) s_mmask[wd] = 0u;
-      while (m) {
-        const int uu = wd * 32 + __ffs(m) - 1;
-        m &= m - 1;
-        merge_user(uu);
+      uint32_t mm = m[wd];
+      while (mm) {
+        const int uu = wd * 32 + __ffs(mm) - 1;
+        mm &= mm - 1;
+        if ((nth++ & (SC_THREADS / 32 - 1)) == warp) warp_merge(uu, nullptr);
       }
     }
     __syncthreads();
@@ -403,12 +456,9 @@ __global__ void __launch_bounds__(SC_THREADS, 1) score_tc_kernel(ScoreTcArgs A) 
     want_flush = false;
     if (do_flush) flush();
   }
-  // final lists: merge every user once more and emit the best KMAX keys
-  for (int uu = 0; uu < nu; ++uu) {
-    merge_user(uu);
-    unsigned long long* dst = A.part + ((u0 + uu) * A.nsplit + split) * SC_KMAX;
-    for (int k = tid; k < SC_KMAX; k += SC_THREADS) dst[k] = s_sort[k];
-  }
+  // final lists: merge every user once more and emit the best KMAX keys (one warp per user)
+  __syncthreads();
+  for (int uu = warp; uu < nu; uu += SC_THREADS / 32) warp_merge(uu, A.part + ((u0 + uu) * A.nsplit + split) * SC_KMAX);
   fence_before_sync();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, 512);
