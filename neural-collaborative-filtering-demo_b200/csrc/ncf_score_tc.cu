@@ -38,9 +38,7 @@ constexpr uint32_t SCS_KTHR = SCS_LTHR + SC_UT * 4;         // key of the runnin
 constexpr uint32_t SCS_CNT = SCS_KTHR + SC_UT * 8;
 constexpr int SC_QCAP = 4096;                               // survivors queued for exact re-scoring (flushed when half full)
 constexpr int SC_HIGH = SC_CAP - 64;                        // merge a list when it holds more than this
-constexpr int SC_FLUSH_EVERY = 4;                           // tiles between two CTA-wide flush decisions
-constexpr int SC_RCAP = SC_FLUSH_EVERY * SC_UT * SC_IT + SC_QCAP;   // keys whose candidate buffer was full: every pair of
-                                                            // the tiles between two flushes + the queue
+constexpr int SC_RCAP = SC_UT * SC_IT + SC_QCAP;            // keys whose candidate buffer was full: one tile + the queue
 constexpr uint32_t SCS_QUEUE = SCS_CNT + SC_UT * 4;         // (row << 8 | column) per survivor
 constexpr uint32_t SCS_TOTAL = SCS_QUEUE + SC_QCAP * 8;     // (row, item index) per survivor
 constexpr int64_t SC_CTA_WS = (int64_t)SC_UT * SC_CAP * 8 + 2 * ((int64_t)SC_RCAP * 8 + SC_RCAP);   // candidates + 2 retry lists
@@ -185,7 +183,7 @@ struct ScoreTcArgs {
 
 __global__ void __launch_bounds__(SC_THREADS, 1) score_tc_kernel(ScoreTcArgs A) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ __align__(8) uint64_t full[SC_NB], accb[2], done[2];
+  __shared__ __align__(8) uint64_t full[SC_NB], accb[2];
   __shared__ uint32_t tmem_slot;
   __shared__ int s_qn, s_rn;
   __shared__ uint32_t s_mmask[SC_UT / 32];               // users whose list has to be merged
@@ -261,8 +259,6 @@ __global__ void __launch_bounds__(SC_THREADS, 1) score_tc_kernel(ScoreTcArgs A) 
     for (int i = 0; i < SC_NB; ++i) mbar_init(&full[i], 1);
     mbar_init(&accb[0], 1);
     mbar_init(&accb[1], 1);
-    mbar_init(&done[0], SC_THREADS / 32);      // one arrival per warp: "this warp has read accumulator b"
-    mbar_init(&done[1], SC_THREADS / 32);
     mbar_fence_init();
   }
   if (warp == 0) tmem_alloc(&tmem_slot, 512);
@@ -421,19 +417,13 @@ __global__ void __launch_bounds__(SC_THREADS, 1) score_tc_kernel(ScoreTcArgs A) 
   }
   for (int64_t t = 0; t < ntile; ++t) {
     const int b = (int)(t & 1);
-    const float lthr = s_lthr[row];                     // refreshed by flushes only (a CTA barrier precedes every change)
     if (tid == 0) {
-      if (t + 2 < ntile) load_tile(t + 2);              // its buffer held tile t - 1, whose GEMM this thread saw complete
-      if (t + 1 < ntile) {
-        if (t >= 1) {                                   // accumulator b ^ 1 held tile t - 1: every warp has read it
-          mbar_wait(&done[b ^ 1], (uint32_t)(((t - 1) >> 1) & 1));
-          fence_after_sync();
-        }
-        issue_mma(t + 1);
-      }
+      if (t + 2 < ntile) load_tile(t + 2);              // its buffer held tile t - 1: GEMM and epilogue are done
+      if (t + 1 < ntile) issue_mma(t + 1);              // the other accumulator was drained by the previous epilogue
     }
-    mbar_wait(&accb[b], (uint32_t)((t >> 1) & 1));       // every warp polls for itself; no CTA barrier per tile
+    mbar_wait(&accb[b], (uint32_t)((t >> 1) & 1));       // every warp polls for itself: one CTA barrier per tile, below
     fence_after_sync();
+    const float lthr = s_lthr[row];
     const int64_t base = (t_begin + t) * SC_IT;
 #pragma unroll 1
     for (int ch = 0; ch < 2; ++ch) {
@@ -459,17 +449,12 @@ __global__ void __launch_bounds__(SC_THREADS, 1) score_tc_kernel(ScoreTcArgs A) 
       }
     }
     fence_before_sync();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&done[b]);                // accumulator b is free once all 16 warps have arrived
-    // The flush decision needs the whole CTA (a thread that pushed past the queue's half mark, or parked a key, votes
-    // yes): taken every SC_FLUSH_EVERY tiles only, so the warps drift apart in between instead of meeting at a barrier
-    // per tile.  Survivors wait in the queue (re-scored in place when it is full); the retry lists hold every pair of
-    // the tiles in between, so nothing overflows however loose the thresholds still are.
-    if ((t & (SC_FLUSH_EVERY - 1)) == SC_FLUSH_EVERY - 1 || t + 1 == ntile) {
-      const int do_flush = __syncthreads_or((want_flush || t + 1 == ntile) ? 1 : 0);
-      want_flush = false;
-      if (do_flush) flush();
-    }
+    // The one CTA barrier of a tile: accumulator b and the tile's g / margin are free after it, and it carries the
+    // flush decision (a thread that pushed past the queue's half mark, or parked a key, votes yes).  Survivors wait
+    // in the queue until then, so late in the run a flush - and the barriers it costs - happens once in many tiles.
+    const int do_flush = __syncthreads_or((want_flush || t + 1 == ntile) ? 1 : 0);
+    want_flush = false;
+    if (do_flush) flush();
   }
   // final lists: merge every user once more and emit the best KMAX keys (one warp per user)
   __syncthreads();
