@@ -421,27 +421,34 @@ __global__ void __launch_bounds__(SC_THREADS, 1) score_tc_kernel(ScoreTcArgs A) 
       if (t + 2 < ntile) load_tile(t + 2);              // its buffer held tile t - 1: GEMM and epilogue are done
       if (t + 1 < ntile) issue_mma(t + 1);              // the other accumulator was drained by the previous epilogue
     }
+    const float lthr = s_lthr[row];                      // changed by flushes only (CTA barriers on both sides)
     mbar_wait(&accb[b], (uint32_t)((t >> 1) & 1));       // every warp polls for itself: one CTA barrier per tile, below
     fence_after_sync();
-    const float lthr = s_lthr[row];
     const int64_t base = (t_begin + t) * SC_IT;
-#pragma unroll 1
+    // both halves of this thread's 64 accumulator columns are requested before either is used
+    float z[2][32];
+    tmem_ld32_nowait(tmem + 256 * b + lane_addr + cq * 64, z[0]);
+    tmem_ld32_nowait(tmem + 256 * b + lane_addr + cq * 64 + 32, z[1]);
+    tmem_ld_wait();
+#pragma unroll
     for (int ch = 0; ch < 2; ++ch) {
-      float z[32];
-      tmem_ld32(tmem + 256 * b + lane_addr + cq * 64 + ch * 32, z);
       const int j0 = cq * 64 + ch * 32;
       // two instructions per pair: the accumulator IS the upper bound of the logit (bias, margin and slack ride in the
-      // GEMM), so diff = bound - lthr and a funnel shift that appends diff's sign bit to the mask (element j ends up at
-      // bit 31 - j; set = below the threshold)
-      uint32_t miss = 0;
+      // GEMM), so diff = bound - lthr and a funnel shift that appends diff's sign bit to a mask; four independent chains
+      // of eight (a single 32-long chain is pure latency), joined so that element j ends up at bit 31 - j (set = miss)
+      uint32_t m4[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
-      for (int j = 0; j < 32; ++j) miss = __funnelshift_l(__float_as_uint(z[j] - lthr), miss, 1);
+      for (int j = 0; j < 8; ++j) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) m4[c] = __funnelshift_l(__float_as_uint(z[ch][8 * c + j] - lthr), m4[c], 1);
+      }
+      const uint32_t miss = (m4[0] << 24) | (m4[1] << 16) | (m4[2] << 8) | m4[3];
       uint32_t hit = ~miss;
       while (hit) {                                      // rare after the first tiles
         const int j = __clz(hit);                        // element j sits at bit 31 - j
         hit &= ~(0x80000000u >> j);
         const int64_t i = base + j0 + j;
-        if (i >= A.I) continue;                          // padding of the last tile (its -inf bias can turn into NaN above)
+        if (i >= A.I) continue;                          // padding of the last tile
         const int qp = atomicAdd(&s_qn, 1);
         if (qp >= SC_QCAP / 2) want_flush = true;
         if (qp < SC_QCAP) s_queue[qp] = ((unsigned long long)row << 32) | (unsigned long long)i;   // re-scored at the flush
