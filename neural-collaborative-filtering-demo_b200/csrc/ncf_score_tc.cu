@@ -451,8 +451,13 @@ __global__ void __launch_bounds__(SC_THREADS, 1) score_tc_kernel(ScoreTcArgs A) 
         if (i >= A.I) continue;                          // padding of the last tile
         const int qp = atomicAdd(&s_qn, 1);
         if (qp >= SC_QCAP / 2) want_flush = true;
-        if (qp < SC_QCAP) s_queue[qp] = ((unsigned long long)row << 32) | (unsigned long long)i;   // re-scored at the flush
-        else rescore(row, i);                                                                      // queue full: in place
+        if (qp < SC_QCAP) {      // re-scored at the flush: ask for its fp32 row now, so the flush finds it in L2
+          s_queue[qp] = ((unsigned long long)row << 32) | (unsigned long long)i;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(A.p_hat + i * 64));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(A.p_hat + i * 64 + 32));
+        } else {
+          rescore(row, i);       // queue full: in place
+        }
       }
     }
     fence_before_sync();
