@@ -204,6 +204,7 @@ extern "C" int ncf_train_step(const ncf_run_cfg* cfg, const ncf_adam_cfg* adam, 
     NCF_CUDA(cudaEventRecord(g_ev_fork, st));                  // the previous step's K6 has released the sort buffers
   }
   NCF_CUDA(cudaMemsetAsync(dense_grad, 0, sizeof(float) * kLayout.total, st));                       // optimizer.zero_grad()
+  NCF_CUDA(cudaMemsetAsync(loss_out, 0, sizeof(float), st));      // here, not in front of the loss kernel: see launch_bce
   NCF_TRY(gather_ln_gmf_fwd_rows(tower_bf16_rows(*cfg), T, dense, user_ids, item_ids, N, nullptr, nullptr, w.mf_pred, w.xu, w.xp,
                                  w.y_pmf, w.y_umf, stream));
   if (fork) {
@@ -219,7 +220,7 @@ extern "C" int ncf_train_step(const ncf_run_cfg* cfg, const ncf_adam_cfg* adam, 
   }
   NCF_TRY(tower_f32_forward(*cfg, dense, N, nullptr, nullptr, out, w, st));
   // BCELoss gradient goes into the (not yet used) backward scratch g128b
-  NCF_TRY(launch_bce(out, targets, N, loss_out, w.g128b, st));
+  NCF_TRY(launch_bce(out, targets, N, loss_out, w.g128b, st, true));
   NCF_TRY(backward_impl(cfg, adam, T, dense, dense_grad, user_ids, item_ids, N, w.g128b, workspace, workspace_bytes, stream, sorted,
                         preswept));
   return ncf_dense_adam(dense, dense_grad, dense_m, dense_v, kLayout.total, adam, stream);

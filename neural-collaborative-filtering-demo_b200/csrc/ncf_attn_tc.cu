@@ -129,6 +129,7 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_fwd_kernel(AttnFwdArgs 
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t tmem_slot;
+  pdl_launch_dependents();
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q = warp & 3, h = warp >> 2;
   const int row = q * 32 + lane;
@@ -143,6 +144,7 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_tc_fwd_kernel(AttnFwdArgs 
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
+  pdl_wait();      // prologue done: from here on the kernel reads what the previous kernels of the step wrote
   const uint32_t tmem = tmem_slot;
   const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
   const uint32_t sWQ = smem_addr(smem + AF_WQ), sWKV = smem_addr(smem + AF_WKV), sWO = smem_addr(smem + AF_WO);
@@ -339,6 +341,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_bwd_kernel(AttnBwdArgs 
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t tmem_slot;
+  pdl_launch_dependents();
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q = warp & 3, h = warp >> 2;
   const int row = q * 32 + lane;
@@ -357,6 +360,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_bwd_kernel(AttnBwdArgs 
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
+  pdl_wait();      // prologue done: from here on the kernel reads what the previous kernels of the step wrote
   const uint32_t tmem = tmem_slot;
   const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
   const uint32_t sWQ = smem_addr(smem + AB_WQ), sWKV = smem_addr(smem + AB_WKV), sWO = smem_addr(smem + AB_WO);
@@ -592,6 +596,8 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_bwd_kernel(AttnBwdArgs 
 // dense_grad += sum over CTAs of the partial accumulators.  Columns [0,80) = dWq (lane = out feature, 64 =
 // bias), [80,160) = d[Wk;Wv], [160,240) = dWo.
 __global__ void __launch_bounds__(256) attn_wgrad_reduce_kernel(const float* __restrict__ partial, int nparts, float* __restrict__ dg) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= AB_ACC) return;
   const int col = e >> 7, lane = e & 127;
@@ -622,7 +628,7 @@ int attn_tc_forward(const ncf_run_cfg& cfg, const float* dense, int64_t N, Tower
   A.N = N;
   A.rng = make_rng(cfg, 0);
   const int grid = (int)std::min<int64_t>(attn_tc_tiles(N), (int64_t)num_sms() * 2);
-  attn_tc_fwd_kernel<<<grid, AT_THREADS, AF_TOTAL, st>>>(A);
+  NCF_CUDA(launch_pdl(attn_tc_fwd_kernel, dim3(grid), dim3(AT_THREADS), AF_TOTAL, st, A));
   NCF_LAUNCH_CHECK();
   return NCF_OK;
 }
@@ -646,9 +652,9 @@ int attn_tc_backward(const ncf_run_cfg& cfg, const float* dense, float* dense_gr
   A.N = N;
   A.rng = make_rng(cfg, 0);
   const int grid = (int)std::min<int64_t>((N + AT_RT - 1) / AT_RT, (int64_t)num_sms());
-  attn_tc_bwd_kernel<<<grid, AT_THREADS, AB_TOTAL, st>>>(A);
+  NCF_CUDA(launch_pdl(attn_tc_bwd_kernel, dim3(grid), dim3(AT_THREADS), AB_TOTAL, st, A));
   NCF_LAUNCH_CHECK();
-  attn_wgrad_reduce_kernel<<<(AB_ACC + 255) / 256, 256, 0, st>>>(w.at_partial, grid, dense_grad);
+  NCF_CUDA(launch_pdl(attn_wgrad_reduce_kernel, dim3((AB_ACC + 255) / 256), dim3(256), 0, st, (const float*)w.at_partial, grid, dense_grad));
   NCF_LAUNCH_CHECK();
   return NCF_OK;
 }

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "ncf_b200.h"
 
@@ -43,6 +44,40 @@ extern unsigned long long g_launches;   // kernels launched by this library (ben
     int rc__ = (expr);           \
     if (rc__ != NCF_OK) return rc__; \
   } while (0)
+
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------------------------
+// The tower kernels of one step form a chain of persistent grids, each with a prologue (weight images, parameters, tensor
+// memory) that depends on nothing the chain computes.  Launched with cudaLaunchAttributeProgrammaticStreamSerialization,
+// a kernel's CTAs take over an SM as soon as the previous kernel's CTA on it exits, run the prologue, and only then wait
+// (griddepcontrol.wait) for the previous grid to have completed: the tail of one kernel overlaps the prologue of the
+// next.  Rules kept by every kernel that uses this: nothing written, and nothing another kernel of the step produces
+// read, before pdl_wait().  NCF_PDL=0 launches everything the ordinary way (the instructions are no-ops then).
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
+inline bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("NCF_PDL");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on != 0;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 // ---- dense flat layout --------------------------------------------------------------------
 struct DenseLayout {

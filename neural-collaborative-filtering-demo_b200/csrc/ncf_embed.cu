@@ -68,6 +68,7 @@ __global__ void __launch_bounds__(K1_THREADS) gather_ln_gmf_fwd_kernel(
     int32_t* __restrict__ status) {
   __shared__ __align__(16) int64_t s_ids[2][2][K1_TILE];
   __shared__ __align__(8) uint64_t s_bar[2];
+  pdl_launch_dependents();      // the attention forward that follows may start its prologue (ncf_common.cuh, PDL)
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int half = lane >> 4, l16 = lane & 15;

@@ -90,6 +90,7 @@ int shard_requester_grads(const float* dense, float* dense_grad, const float* ro
 // fused backward of one projection: dX = dY.W and dW += dY^T.X, db += colsum(dY) (which: 0 = 64 cols, 1 = 128)
 int tc_proj_backward(int which, const float* dY, const float* X, const float* W, float* dX, float* dW, float* db, int64_t N,
                      cudaStream_t st);
-int launch_bce(const float* out, const float* targets, int64_t N, float* loss_out, float* grad_out, cudaStream_t st);
+int launch_bce(const float* out, const float* targets, int64_t N, float* loss_out, float* grad_out, cudaStream_t st,
+               bool loss_zeroed = false);
 
 }  // namespace ncf

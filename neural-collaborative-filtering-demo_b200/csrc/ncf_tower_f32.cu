@@ -662,6 +662,8 @@ __global__ void __launch_bounds__(256) head_bwd_scalar_kernel(const float* __res
                                                               float* __restrict__ d_mlp_pred, float* __restrict__ dense_grad,
                                                               int64_t N) {
   __shared__ float s_sc[8][5];
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float a = __ldg(dense + NCF_OFF(NCF_P_FINAL_W)), c = __ldg(dense + NCF_OFF(NCF_P_FINAL_W) + 1);
   float s[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
@@ -699,6 +701,8 @@ __global__ void __launch_bounds__(256) head_bwd_scalar_kernel(const float* __res
 __global__ void __launch_bounds__(256) bce_kernel(const float* __restrict__ out, const float* __restrict__ tgt, int64_t N,
                                                   float* __restrict__ loss, float* __restrict__ grad) {
   __shared__ float s_part[8];
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float acc = 0.f;
   const float invN = 1.0f / (float)N;
@@ -870,7 +874,8 @@ int tower_mlp_backward(const ncf_run_cfg& cfg, const float* dense, float* dg, in
   const bool tcm = cfg.precision == NCF_BF16_TC;
   if (tcm) {
     const int sgrid = (int)std::min<int64_t>((N + 255) / 256, (int64_t)num_sms() * 4);
-    head_bwd_scalar_kernel<<<sgrid, 256, 0, st>>>(grad_out, w.p_saved, w.mf_pred, w.mlp_pred, P, w.d_mf, w.d_mlp, dg, N);
+    NCF_CUDA(launch_pdl(head_bwd_scalar_kernel, dim3(sgrid), dim3(256), 0, st, grad_out, (const float*)w.p_saved, (const float*)w.mf_pred,
+                        (const float*)w.mlp_pred, P, w.d_mf, w.d_mlp, dg, N));
   } else {
     head_bwd_kernel<<<hgrid, 256, 0, st>>>(grad_out, w.p_saved, w.mf_pred, w.mlp_pred, w.y3, P, w.d_mf, w.g64a, nullptr, dg, N);
   }
@@ -933,11 +938,13 @@ int tower_attn_backward(const ncf_run_cfg& cfg, const float* dense, float* dg, i
   return NCF_OK;
 }
 
-int launch_bce(const float* out, const float* targets, int64_t N, float* loss_out, float* grad_out, cudaStream_t st) {
-  NCF_CUDA(cudaMemsetAsync(loss_out, 0, sizeof(float), st));
+// loss_zeroed: the caller has already zeroed *loss_out on the stream (ncf_train_step does it before its first kernel, so
+// that no memset node interrupts the chain of programmatically dependent tower kernels)
+int launch_bce(const float* out, const float* targets, int64_t N, float* loss_out, float* grad_out, cudaStream_t st, bool loss_zeroed) {
+  if (!loss_zeroed) NCF_CUDA(cudaMemsetAsync(loss_out, 0, sizeof(float), st));
   if (N == 0) return NCF_OK;
   const int grid = (int)std::min<int64_t>((N + 255) / 256, (int64_t)num_sms() * 4);
-  bce_kernel<<<grid, 256, 0, st>>>(out, targets, N, loss_out, grad_out);
+  NCF_CUDA(launch_pdl(bce_kernel, dim3(grid), dim3(256), 0, st, out, targets, N, loss_out, grad_out));
   NCF_LAUNCH_CHECK();
   return NCF_OK;
 }

@@ -433,6 +433,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_tc_fwd2_kernel(MlpFwdArgs 
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t full[2], bl1[2], bl2[2], bl3[2];
   __shared__ uint32_t tmem_slot;
+  pdl_launch_dependents();
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q = warp & 3, h = warp >> 2;
   float* par = reinterpret_cast<float*>(smem + SM2_PAR);
@@ -480,6 +481,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_tc_fwd2_kernel(MlpFwdArgs 
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
+  pdl_wait();      // prologue done: from here on the kernel reads what the previous kernels of the step wrote
   const uint32_t tmem = tmem_slot;
   const uint32_t sW0 = smem_addr(smem + SM_W0), sW1 = smem_addr(smem + SM_W1), sW2 = smem_addr(smem + SM_W2);
   const int64_t ntiles = (A.N + TCM_ROWS - 1) / TCM_ROWS;
@@ -623,7 +625,7 @@ int launch_mlp_tc_fwd(const MlpFwdArgs& A, cudaStream_t st) {
   const int64_t ntiles = (A.N + TCM_ROWS - 1) / TCM_ROWS;
   const int grid = (int)std::min<int64_t>(ntiles, num_sms());
   if (variant == 1) mlp_tc_fwd_kernel<<<grid, MLP_THREADS, SM_MLP_TOTAL, st>>>(A);
-  else mlp_tc_fwd2_kernel<<<grid, MLP_THREADS, SM2_TOTAL, st>>>(A);
+  else NCF_CUDA(launch_pdl(mlp_tc_fwd2_kernel, dim3(grid), dim3(MLP_THREADS), SM2_TOTAL, st, A));
   NCF_LAUNCH_CHECK();
   return NCF_OK;
 }
@@ -1589,6 +1591,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_tc_bwd2_kernel(MlpBwdArgs 
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t tmem_slot;
+  pdl_launch_dependents();
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q = warp & 3, h = warp >> 2;
   float* par = reinterpret_cast<float*>(smem + SM2B_PAR);
@@ -1619,6 +1622,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) mlp_tc_bwd2_kernel(MlpBwdArgs 
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
+  pdl_wait();      // prologue done: from here on the kernel reads what the previous kernels of the step wrote
   const uint32_t tmem = tmem_slot;
   const uint32_t sW0 = smem_addr(smem + SM_W0), sW1 = smem_addr(smem + SM_W1), sW2 = smem_addr(smem + SM_W2);
   const uint32_t sZ = smem_addr(smem + SM2B_Z);
@@ -1812,6 +1816,7 @@ __global__ void __launch_bounds__(TCM_THREADS, 1) mlp_tc_wgrad_kernel(MlpWgradAr
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t fullA, fullB, emptyA, emptyB;
   __shared__ uint32_t tmem_slot;
+  pdl_launch_dependents();
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q = warp & 3, h = warp >> 2;
   if (tid == 0) {
@@ -1830,6 +1835,7 @@ __global__ void __launch_bounds__(TCM_THREADS, 1) mlp_tc_wgrad_kernel(MlpWgradAr
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
+  pdl_wait();
   const uint32_t tmem = tmem_slot;
   const int64_t ntiles = (A.N + TCM_ROWS - 1) / TCM_ROWS;
   const int64_t my_tiles = (int64_t)blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
@@ -1915,6 +1921,8 @@ __global__ void __launch_bounds__(TCM_THREADS, 1) mlp_tc_wgrad_kernel(MlpWgradAr
 // dense_grad += sum over CTAs of the partial accumulators; e = column * 128 + lane
 __global__ void __launch_bounds__(256) mlp_wgrad_reduce_kernel(const float* __restrict__ partial, int nparts,
                                                                float* __restrict__ dg) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= WG_PART) return;
   float s = 0.f;
@@ -1958,7 +1966,7 @@ int mlp_tc_backward(const ncf_run_cfg& cfg, const float* dense, float* dense_gra
   for (int l = 0; l < 3; ++l) B.rng[l] = make_rng(cfg, 1 + l);
   static const int bwd_variant = getenv("NCF_MLP_BWD") ? atoi(getenv("NCF_MLP_BWD")) : 2;     // A/B switch
   if (bwd_variant == 1) mlp_tc_bwd_kernel<<<grid, MLP_THREADS, SMB_TOTAL, st>>>(B);
-  else mlp_tc_bwd2_kernel<<<grid, MLP_THREADS, SM2B_TOTAL, st>>>(B);
+  else NCF_CUDA(launch_pdl(mlp_tc_bwd2_kernel, dim3(grid), dim3(MLP_THREADS), SM2B_TOTAL, st, B));
   NCF_LAUNCH_CHECK();
   MlpWgradArgs W{};
   W.a_img = (const __nv_bfloat16*)w.a_img;
@@ -1970,9 +1978,9 @@ int mlp_tc_backward(const ncf_run_cfg& cfg, const float* dense, float* dense_gra
   W.dense_grad = dense_grad;
   W.partial = w.wg_partial;
   W.N = N;
-  mlp_tc_wgrad_kernel<<<grid, TCM_THREADS, SMW_TOTAL, st>>>(W);
+  NCF_CUDA(launch_pdl(mlp_tc_wgrad_kernel, dim3(grid), dim3(TCM_THREADS), SMW_TOTAL, st, W));
   NCF_LAUNCH_CHECK();
-  mlp_wgrad_reduce_kernel<<<(WG_PART + 255) / 256, 256, 0, st>>>(w.wg_partial, grid, dense_grad);
+  NCF_CUDA(launch_pdl(mlp_wgrad_reduce_kernel, dim3((WG_PART + 255) / 256), dim3(256), 0, st, (const float*)w.wg_partial, grid, dense_grad));
   NCF_LAUNCH_CHECK();
   return NCF_OK;
 }
