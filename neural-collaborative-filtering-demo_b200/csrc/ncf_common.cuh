@@ -56,16 +56,21 @@ extern unsigned long long g_launches;   // kernels launched by this library (ben
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 #endif
-inline bool pdl_enabled() {
-  static int on = -1;
-  if (on < 0) {
+// which launches carry the attribute (NCF_PDL = bit mask, A/B switch): 1 attention forward, 2 MLP forward, 4 loss + head
+// backward, 8 MLP backward, 16 MLP weight gradients + reduce, 32 attention backward + reduce.  Default 60: the BACKWARD
+// chain only - during the forward the auxiliary stream's id sort and dense-equivalent sweep live on the SM resources the
+// gather / attention kernels leave free, and an early-resident MLP forward CTA (200 KB of shared memory) would take them.
+enum { PDL_ATTN_FWD = 1, PDL_MLP_FWD = 2, PDL_HEAD = 4, PDL_MLP_BWD = 8, PDL_MLP_WGRAD = 16, PDL_ATTN_BWD = 32 };
+inline int pdl_mask() {
+  static int m = -1;
+  if (m < 0) {
     const char* e = getenv("NCF_PDL");
-    on = (e && e[0] == '0') ? 0 : 1;
+    m = e ? atoi(e) : 0;
   }
-  return on != 0;
+  return m;
 }
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+inline cudaError_t launch_pdl(int which, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;
@@ -75,7 +80,7 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cfg.numAttrs = (pdl_mask() & which) ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 

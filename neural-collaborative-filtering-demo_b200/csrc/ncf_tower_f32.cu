@@ -874,7 +874,7 @@ int tower_mlp_backward(const ncf_run_cfg& cfg, const float* dense, float* dg, in
   const bool tcm = cfg.precision == NCF_BF16_TC;
   if (tcm) {
     const int sgrid = (int)std::min<int64_t>((N + 255) / 256, (int64_t)num_sms() * 4);
-    NCF_CUDA(launch_pdl(head_bwd_scalar_kernel, dim3(sgrid), dim3(256), 0, st, grad_out, (const float*)w.p_saved, (const float*)w.mf_pred,
+    NCF_CUDA(launch_pdl(PDL_HEAD, head_bwd_scalar_kernel, dim3(sgrid), dim3(256), 0, st, grad_out, (const float*)w.p_saved, (const float*)w.mf_pred,
                         (const float*)w.mlp_pred, P, w.d_mf, w.d_mlp, dg, N));
   } else {
     head_bwd_kernel<<<hgrid, 256, 0, st>>>(grad_out, w.p_saved, w.mf_pred, w.mlp_pred, w.y3, P, w.d_mf, w.g64a, nullptr, dg, N);
@@ -944,7 +944,7 @@ int launch_bce(const float* out, const float* targets, int64_t N, float* loss_ou
   if (!loss_zeroed) NCF_CUDA(cudaMemsetAsync(loss_out, 0, sizeof(float), st));
   if (N == 0) return NCF_OK;
   const int grid = (int)std::min<int64_t>((N + 255) / 256, (int64_t)num_sms() * 4);
-  NCF_CUDA(launch_pdl(bce_kernel, dim3(grid), dim3(256), 0, st, out, targets, N, loss_out, grad_out));
+  NCF_CUDA(launch_pdl(PDL_HEAD, bce_kernel, dim3(grid), dim3(256), 0, st, out, targets, N, loss_out, grad_out));
   NCF_LAUNCH_CHECK();
   return NCF_OK;
 }

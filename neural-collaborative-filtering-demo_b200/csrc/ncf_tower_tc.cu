@@ -625,7 +625,7 @@ int launch_mlp_tc_fwd(const MlpFwdArgs& A, cudaStream_t st) {
   const int64_t ntiles = (A.N + TCM_ROWS - 1) / TCM_ROWS;
   const int grid = (int)std::min<int64_t>(ntiles, num_sms());
   if (variant == 1) mlp_tc_fwd_kernel<<<grid, MLP_THREADS, SM_MLP_TOTAL, st>>>(A);
-  else NCF_CUDA(launch_pdl(mlp_tc_fwd2_kernel, dim3(grid), dim3(MLP_THREADS), SM2_TOTAL, st, A));
+  else NCF_CUDA(launch_pdl(PDL_MLP_FWD, mlp_tc_fwd2_kernel, dim3(grid), dim3(MLP_THREADS), SM2_TOTAL, st, A));
   NCF_LAUNCH_CHECK();
   return NCF_OK;
 }
@@ -1966,7 +1966,7 @@ int mlp_tc_backward(const ncf_run_cfg& cfg, const float* dense, float* dense_gra
   for (int l = 0; l < 3; ++l) B.rng[l] = make_rng(cfg, 1 + l);
   static const int bwd_variant = getenv("NCF_MLP_BWD") ? atoi(getenv("NCF_MLP_BWD")) : 2;     // A/B switch
   if (bwd_variant == 1) mlp_tc_bwd_kernel<<<grid, MLP_THREADS, SMB_TOTAL, st>>>(B);
-  else NCF_CUDA(launch_pdl(mlp_tc_bwd2_kernel, dim3(grid), dim3(MLP_THREADS), SM2B_TOTAL, st, B));
+  else NCF_CUDA(launch_pdl(PDL_MLP_BWD, mlp_tc_bwd2_kernel, dim3(grid), dim3(MLP_THREADS), SM2B_TOTAL, st, B));
   NCF_LAUNCH_CHECK();
   MlpWgradArgs W{};
   W.a_img = (const __nv_bfloat16*)w.a_img;
@@ -1978,9 +1978,9 @@ int mlp_tc_backward(const ncf_run_cfg& cfg, const float* dense, float* dense_gra
   W.dense_grad = dense_grad;
   W.partial = w.wg_partial;
   W.N = N;
-  NCF_CUDA(launch_pdl(mlp_tc_wgrad_kernel, dim3(grid), dim3(TCM_THREADS), SMW_TOTAL, st, W));
+  NCF_CUDA(launch_pdl(PDL_MLP_WGRAD, mlp_tc_wgrad_kernel, dim3(grid), dim3(TCM_THREADS), SMW_TOTAL, st, W));
   NCF_LAUNCH_CHECK();
-  NCF_CUDA(launch_pdl(mlp_wgrad_reduce_kernel, dim3((WG_PART + 255) / 256), dim3(256), 0, st, (const float*)w.wg_partial, grid, dense_grad));
+  NCF_CUDA(launch_pdl(PDL_MLP_WGRAD, mlp_wgrad_reduce_kernel, dim3((WG_PART + 255) / 256), dim3(256), 0, st, (const float*)w.wg_partial, grid, dense_grad));
   NCF_LAUNCH_CHECK();
   return NCF_OK;
 }
