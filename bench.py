@@ -142,14 +142,22 @@ def build_model(users, items, device, precision):
 
 
 def cpu_reference_rate(users, items, B_sample, steps, warmup, threads):
-    """The CPU oracle port of the reference step (oracle/ncf_oracle.py: forward, BCELoss, dense table
-    gradients, torch-Adam update of every row) on the host cores.  Returns (rows/s, ms/step)."""
+    """The reference training step on the host cores: (rows/s, ms/step, kind).
+    kind "reference": the UNMODIFIED reference `ModelTrainer.train_epoch` imported through oracle/shims (only where the
+    reference tree is mounted, i.e. the build container); kind "port": the oracle port of the same step
+    (oracle/ncf_oracle.py: forward, BCELoss, dense table gradients, torch-Adam update of every row)."""
     import torch
     from oracle import ncf_oracle as O
+    from oracle import reference_runner as R
+    if R.available() and not os.environ.get("NCF_CPU_PORT"):
+        batches = make_batches(users, items, B_sample, 2, 99)
+        rate, ms = R.train_rate(users, items, batches, steps, max(warmup, 1), threads)
+        return rate, ms, "reference"
     torch.set_num_threads(threads)
     g = torch.Generator().manual_seed(1234)
     p = cpu_params(users, items, g)
-    return _cpu_train_rate(p, users, items, B_sample, steps, warmup, g)
+    rate, ms = _cpu_train_rate(p, users, items, B_sample, steps, warmup, g)
+    return rate, ms, "port"
 
 
 def cpu_params(users, items, g):
@@ -434,15 +442,17 @@ def run_reference(args):
     B = args.batch or B
     threads = os.cpu_count() or 1
     B_sample = min(B, args.ref_batch)
-    rate, ms = cpu_reference_rate(users, items, B_sample, args.steps, args.warmup, threads)
+    rate, ms, kind = cpu_reference_rate(users, items, B_sample, args.steps, args.warmup, threads)
     line = {"impl": "reference", "metric": "train_samples_per_s", "value": rate, "unit": "samples/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {desc}", "interactions_per_step_per_gpu": B, "rows_per_interaction": S,
                        "table_update": "dense torch.optim.Adam on every row (the reference's own semantics)", "towers": "fp32",
                        "l2": "host DRAM; bounded sample of the step"},
-            "cpu_baseline": {"value": rate, "unit": "samples/s", "cores": threads, "kind": "port",
-                             "sample": f"{B_sample} of the {B} interactions of a step, {args.steps} steps"},
+            "cpu_baseline": {"value": rate, "unit": "samples/s", "cores": threads, "kind": kind,
+                             "sample": f"{B_sample} of the {B} interactions of a step, {args.steps} steps; "
+                                       + ("the unmodified reference ModelTrainer.train_epoch through oracle/shims" if kind == "reference"
+                                          else "oracle port of the reference step (the reference tree is not on this box)")},
             "e2e": {"value": rate, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -610,8 +620,8 @@ def single_measure(args, users, items, B, precision, table_mode, dev, barrier):
     if not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         Bs = min(B, args.ref_batch)
-        rate, ms = cpu_reference_rate(users, items, Bs, args.cpu_baseline_steps, 1, threads)
-        cpu_baseline = {"value": rate, "unit": "samples/s", "cores": threads, "kind": "port", "ms_per_step": ms,
+        rate, ms, kind = cpu_reference_rate(users, items, Bs, args.cpu_baseline_steps, 1, threads)
+        cpu_baseline = {"value": rate, "unit": "samples/s", "cores": threads, "kind": kind, "ms_per_step": ms,
                         "sample": f"{Bs} of the {B} interactions of a step, {args.cpu_baseline_steps} steps"}
     eng.close()
     del eng, model
