@@ -184,10 +184,11 @@ __device__ __forceinline__ float f4_hsum(float4 a) { return (a.x + a.y) + (a.z +
 
 // Philox4x32-10 (Salmon et al. 2011): counter-based, so every dropout element is a pure function
 // of (seed, step, site, element index) - the backward and the test-side mask dump regenerate it.
-__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+template <int ROUNDS>
+__device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
   constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
 #pragma unroll
-  for (int r = 0; r < 10; ++r) {
+  for (int r = 0; r < ROUNDS; ++r) {
     const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
     const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
     ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
@@ -196,6 +197,7 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
   }
   return ctr;
 }
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) { return philox4x32<10>(ctr, key); }
 // Dropout stream: one Philox call yields 8 x 16-bit lanes = the keep decisions of 8 consecutive
 // elements (element idx uses call idx >> 3, lane idx & 7).  The low 15 bits of a lane are the uniform
 // draw: keep iff (lane & 0x7fff) >= thresh (p quantised to 1/32768; kept values are scaled by 1/(1-p)
@@ -208,7 +210,9 @@ struct DropoutRng {
   uint32_t thresh;  // 15-bit threshold; 0 = dropout off
   float scale;      // 1/(1-p)
   __device__ __forceinline__ uint4 draw8(uint64_t group) const {
-    return philox4x32_10(make_uint4((uint32_t)group, (uint32_t)(group >> 32), step_lo, step_hi_site), key);
+    // Philox4x32-7: the smallest round count that passes BigCrush (Salmon et al. 2011, table 2); the dropout draw is
+    // ~30 % of the MLP forward epilogue's instructions, and three rounds less is a tenth of that kernel
+    return philox4x32<7>(make_uint4((uint32_t)group, (uint32_t)(group >> 32), step_lo, step_hi_site), key);
   }
   __device__ __forceinline__ bool keep16(uint32_t lane16) const { return (lane16 & 0x7fffu) >= thresh; }
   __device__ __forceinline__ float mask(float x, uint32_t lane16) const { return keep16(lane16) ? x * scale : 0.f; }

@@ -1846,7 +1846,8 @@ __global__ void __launch_bounds__(TCM_THREADS, 1) mlp_tc_wgrad_kernel(MlpWgradAr
     const uint8_t *y2 = (const uint8_t*)A.y2, *z3 = (const uint8_t*)A.dz3, *z2 = (const uint8_t*)A.dz2,
                   *y1 = (const uint8_t*)A.y1, *z1 = (const uint8_t*)A.dz1, *ai = (const uint8_t*)A.a_img;
     for (int64_t k = 0; k < my_tiles; ++k) {
-      const int64_t tile = blockIdx.x + k * gridDim.x;
+      // LAST tiles first: the dz tiles the input-gradient kernel wrote last are the ones still in the 126 MB L2
+      const int64_t tile = ntiles - 1 - (blockIdx.x + k * gridDim.x);
       if (k > 0) mbar_wait(&emptyA, (k - 1) & 1);
       mbar_arrive_expect_tx(&fullA, B_Y2 + B_Z3 + B_Z2 + B_Y1);
       bulk_g2s(smem + SMW_Y2, y2 + tile * B_Y2, B_Y2, &fullA);

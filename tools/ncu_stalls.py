@@ -1,14 +1,15 @@
 #!/usr/bin/env python3
 """Digest of one kernel of an .ncu-rep (needs --set full --import-source on): headline counters, stall-reason totals and
-the instructions with the most stall samples.  usage: python tools/ncu_stalls.py <report.ncu-rep> [top]"""
+the instructions with the most stall samples.  usage: python tools/ncu_stalls.py <report.ncu-rep> [top] [kernel-name regex]"""
 import csv
 import io
 import subprocess
 import sys
 
 
-def main(rep, top=30):
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+def main(rep, top=30, kernel=None):
+    sel = ["--kernel-name", "regex:" + kernel] if kernel else []
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"] + sel, capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, r = rows[0], rows[2]
     for w in ("Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "smsp__inst_executed.sum",
@@ -19,7 +20,7 @@ def main(rep, top=30):
               "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"):
         if w in hdr:
             print(f"{w:70s} {r[hdr.index(w)]}")
-    src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + sel, capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(src)))
     hdr = rows[1]
     ix = {h: i for i, h in enumerate(hdr)}
@@ -28,7 +29,11 @@ def main(rep, top=30):
     data = []
     for r in rows[2:]:
         if len(r) < len(hdr):
+            if data:
+                break              # next kernel's section
             continue
+        if r[ix["# Samples"]] == "# Samples":
+            break
         d = {s: int(r[ix[s]] or 0) for s in stalls}
         for s in stalls:
             tot[s] += d[s]
@@ -44,4 +49,4 @@ def main(rep, top=30):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 30)
+    main(sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 30, sys.argv[3] if len(sys.argv) > 3 else None)
