@@ -406,10 +406,14 @@ class ShardedNCFEngine:
                    "ncf_shard_backward")
         return [gu, gi]
 
-    def phase_owner_update(self, grad_rows: List[torch.Tensor], served: Optional[List[torch.Tensor]] = None):
+    def phase_owner_update(self, grad_rows: List[torch.Tensor], served: Optional[List[torch.Tensor]] = None,
+                           ln_grad: Optional[torch.Tensor] = None):
         """owner: segment-sum the received gradient rows per local id, LN backward, Adam.  The two sides touch different
-        tables (their LayerNorm-affine gradients are added atomically), so the item side runs on the auxiliary stream."""
+        tables (their LayerNorm-affine gradients are added atomically), so the item side runs on the auxiliary stream.
+        ln_grad: where the gradients of mf_norm / mlp_norm (the first 256 floats of the flat layout - the only dense
+        gradients an owner produces) are accumulated; default: the engine's dense gradient buffer."""
         adam = self._adam()
+        dense_grad = ln_grad if ln_grad is not None else self.dense_grad
         tabs = self._tables()
         served = served if served is not None else self._served
         main = torch.cuda.current_stream(self.device)
@@ -428,7 +432,7 @@ class ShardedNCFEngine:
                 stream.wait_stream(main)
             with torch.cuda.stream(stream):
                 _lib.check(self.lib.ncf_shard_owner_update(C.byref(adam), C.byref(tabs), _lib.ptr(self.model._flat),
-                                                           _lib.ptr(self.dense_grad), side, _lib.ptr(ids), n, _lib.ptr(g),
+                                                           _lib.ptr(dense_grad), side, _lib.ptr(ids), n, _lib.ptr(g),
                                                            _lib.ptr(ws), nbytes, self._s()), "ncf_shard_owner_update")
         if self._aux is not None:
             main.wait_stream(self._aux)
@@ -585,27 +589,43 @@ class ShardedNCFEngine:
         mark("pull rows (P2P)")
         self.phase_forward_backward(rows, targets, global_rows, push_plan=plan_ptr)
         mark("forward+backward+push (P2P)")
-        # barrier A: every requester's pushed rows have landed before an owner reads its buffer.  With look-ahead the
-        # count all-gather of the NEXT batch is that collective; without, a one-word all-reduce.
-        if nxt is not None:
-            rs = self._aux if self._aux is not None else main
-            if rs is not main:
-                rs.wait_stream(main)                 # the collective comes after this rank's push
-            with torch.cuda.stream(rs):
+        # Collectives of the step, all issued on their own stream in the same order on every rank:
+        #   A  count all-gather of the NEXT batch (look-ahead; else a one-word all-reduce): a barrier - every requester's
+        #      pushed rows have landed before an owner reads its receive buffer;
+        #   D  all-reduce of the tower gradients + the loss (336 KB): needs nothing from the owners, so it runs NEXT TO the
+        #      owner update instead of after it;
+        #   B  all-reduce of the 256 LayerNorm-affine gradients the owners produce: the barrier after which every shard is
+        #      updated (the next pull may read it) and every receive buffer consumed (the next push may overwrite it).
+        multi = self.world > 1 and dist.is_initialized()
+        if self._aux is not None and getattr(self, "_coll", None) is None:
+            self._coll = torch.cuda.Stream(device=self.device)
+        coll = self._coll if self._aux is not None else main
+        if coll is not main:
+            coll.wait_stream(main)                   # after this rank's push and its tower gradients
+            coll.wait_stream(self._aux)              # ... and after the routing kernels of the next batch
+        with torch.cuda.stream(coll):
+            if nxt is not None:
                 self._prefetched = self._begin_count_gather(nxt)
-            if rs is not main:
-                main.wait_stream(rs)
-        else:
-            self._barrier()
+            else:
+                self._barrier()
+            ev_a = coll.record_event() if coll is not main else None
+            if multi:
+                self._dense_and_loss[-1:].copy_(self.loss)
+                dist.all_reduce(self._dense_and_loss, group=self.group)
+        if ev_a is not None:
+            main.wait_event(ev_a)
         mark("route next (barrier)")
+        ln = self.__dict__.setdefault("_ln_grad", torch.zeros(256, device=self.device))
+        ln.zero_()
         self.phase_owner_update([self._recv_rows[0][:n_recv[0]], self._recv_rows[1][:n_recv[1]]],
-                                served=[self._recv_ids[0][:n_recv[0]], self._recv_ids[1][:n_recv[1]]])
+                                served=[self._recv_ids[0][:n_recv[0]], self._recv_ids[1][:n_recv[1]]], ln_grad=ln)
         mark("owner update")
-        # barrier B: the dense all-reduce - after it every owner has updated its shard (the next pull may read it) and has
-        # consumed its receive buffer (the next push may overwrite it)
-        if self.world > 1 and dist.is_initialized():
-            self._dense_and_loss[-1:].copy_(self.loss)
-            dist.all_reduce(self._dense_and_loss, group=self.group)
+        if multi:
+            dist.all_reduce(ln, group=self.group)
+        if coll is not main:
+            main.wait_stream(coll)
+        self.dense_grad[:256].add_(ln)
+        if multi:
             self.loss.copy_(self._dense_and_loss[-1:])
         self.phase_dense_adam()
         mark("dense allreduce+adam")
