@@ -50,6 +50,31 @@ def shard_rows(rows: int, world: int, rank: int) -> int:
     return max(0, min(rows, (rank + 1) * block) - rank * block)
 
 
+def plan_offsets(counts, rank: int):
+    """Host arithmetic of the one-sided step, from the all-gathered counts [world(requester), 2 * world + 1]
+    (= [user counts per owner | item counts per owner | rows of the batch] of every rank):
+      begin[side][o]     first of THIS rank's distinct ids (ascending = owner-major order) that owner o holds
+      push_off[side][o]  row of owner o's receive buffer where this rank's segment starts (requesters in rank order)
+      n_dist[side]       distinct ids this rank pulls / pushes;  n_recv[side]  rows this rank receives as an owner
+      global_rows        sample rows of the whole step (the loss is the mean over them)
+    Pure integer code (bit-exact on any host; tests/test_sharding.py checks it against a brute-force layout)."""
+    W = len(counts)
+    c = [[[int(counts[r][side * W + o]) for o in range(W)] for side in (0, 1)] for r in range(W)]
+    begin = [[0] * (W + 1) for _ in (0, 1)]
+    push_off = [[0] * W for _ in (0, 1)]
+    n_dist, n_recv = [0, 0], [0, 0]
+    for side in (0, 1):
+        acc = 0
+        for o in range(W):
+            begin[side][o] = acc
+            acc += c[rank][side][o]
+            push_off[side][o] = sum(c[r][side][o] for r in range(rank))
+        begin[side][W] = acc
+        n_dist[side] = acc
+        n_recv[side] = sum(c[r][side][rank] for r in range(W))
+    return begin, push_off, n_dist, n_recv, sum(int(counts[r][2 * W]) for r in range(W))
+
+
 def _alltoallv_many(items, group) -> None:
     """Several all-to-all(v) exchanges launched back to back (async) and awaited together.
     items = [(out, inp, recv_counts, send_counts)].  (A single batched point-to-point group was tried instead of one
@@ -508,7 +533,7 @@ class ShardedNCFEngine:
         """counts_host [world(requester), 2 * world + 1]: builds this step's ncf_shard_plan in pinned memory, uploads it on
         the stream, and returns (device plan pointer, (n distinct users, items), (rows received users, items), global N)."""
         W, me = self.world, self.rank
-        c = counts_host[:, :2 * W].reshape(W, 2, W)                   # [requester, side, owner]
+        begin, push_off, n_dist, n_recv, global_rows = plan_offsets(counts_host.tolist(), me)
         if self._plans is None:
             self._plans = [(torch.zeros(C.sizeof(_lib.ShardPlan), dtype=torch.uint8).pin_memory(),
                             torch.zeros(C.sizeof(_lib.ShardPlan), dtype=torch.uint8, device=self.device)) for _ in range(4)]
@@ -516,25 +541,18 @@ class ShardedNCFEngine:
         self._plan_slot = (self._plan_slot + 1) % len(self._plans)
         plan = _lib.ShardPlan.from_buffer(host.numpy())
         plan.world, plan.rank = W, me
-        n_dist, n_recv = [], []
         for side in (0, 1):
-            acc = 0
-            for o in range(W):
-                plan.begin[side][o] = acc
-                acc += int(c[me, side, o])
-            plan.begin[side][W] = acc
-            n_dist.append(acc)
-            n_recv.append(int(c[:, side, me].sum()))
+            for o in range(W + 1):
+                plan.begin[side][o] = begin[side][o]
         for o in range(W):
             ptrs = self._peer_ptrs(o)
             for k in range(4):
                 plan.tab[o][k] = ptrs["w"][k]
             for side in (0, 1):
-                off = int(c[:me, side, o].sum())                      # rows of the requesters before me in o's buffer
-                plan.push_rows[side][o] = ptrs["rows"][side] + off * 512
-                plan.push_ids[side][o] = ptrs["ids"][side] + off * 8
+                plan.push_rows[side][o] = ptrs["rows"][side] + push_off[side][o] * 512
+                plan.push_ids[side][o] = ptrs["ids"][side] + push_off[side][o] * 8
         dev.copy_(host, non_blocking=True)
-        return C.c_void_p(dev.data_ptr()), n_dist, n_recv, int(counts_host[:, 2 * W].sum())
+        return C.c_void_p(dev.data_ptr()), n_dist, n_recv, global_rows
 
     def phase_pull(self, plan_ptr, n_dist):
         """requester: LN'd [n,128] rows of its distinct ids, read from the owners' shards (one kernel per side)."""

@@ -25,6 +25,29 @@ def test_shard_arithmetic_bit_exact():
         assert int(owner.max()) < world
 
 
+def test_plan_offsets_of_the_one_sided_step_match_a_brute_force_layout():
+    """The host arithmetic behind the pull / push kernels: every requester's segment lands exactly once, in requester order,
+    inside every owner's receive buffer, and the row counts add up (also with ragged batches and empty segments)."""
+    from ncf_b200.sharding import plan_offsets
+    g = torch.Generator().manual_seed(0)
+    for W in (1, 2, 3, 8):
+        counts = torch.randint(0, 50, (W, 2 * W + 1), generator=g)
+        counts[torch.rand(W, 2 * W + 1, generator=g) < 0.2] = 0
+        counts = counts.tolist()
+        for side in (0, 1):
+            for o in range(W):                      # owner o's receive buffer: rank 0's rows, then rank 1's, ...
+                layout, at = [], 0
+                for r in range(W):
+                    begin, push_off, n_dist, n_recv, total = plan_offsets(counts, r)
+                    n = counts[r][side * W + o]
+                    assert push_off[side][o] == at and begin[side][o + 1] - begin[side][o] == n
+                    assert begin[side][0] == 0 and begin[side][W] == n_dist[side] == sum(counts[r][side * W:(side + 1) * W])
+                    layout += [r] * n
+                    at += n
+                    assert total == sum(c[2 * W] for c in counts)
+                assert plan_offsets(counts, o)[3][side] == len(layout)
+
+
 def _router_worker(rank, world, init_file, rows, ret):
     from ncf_b200.sharding import ShardRouter, shard_block, shard_owner_local
     dist.init_process_group("gloo", init_method=f"file://{init_file}", rank=rank, world_size=world)
