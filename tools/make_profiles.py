@@ -33,8 +33,8 @@ STAGES = {
     "K1 gather_ln_gmf_fwd": ["gather_ln_gmf_fwd_kernel"],
     "attention forward (attn_tc_fwd_kernel)": ["attn_tc_fwd_kernel"],
     "MLP forward (mlp_tc_fwd_kernel)": ["mlp_tc_fwd_kernel", "mlp_tc_fwd2_kernel"],
-    "MLP backward (head_bwd + mlp_tc_bwd + mlp_tc_wgrad kernels)": ["head_bwd", "mlp_tc_bwd_kernel", "mlp_tc_wgrad_kernel",
-                                                                    "mlp_wgrad_reduce_kernel"],
+    "MLP backward (head_bwd + mlp_tc_bwd + mlp_tc_wgrad kernels)": ["head_bwd", "mlp_tc_bwd_kernel", "mlp_tc_bwd2_kernel",
+                                                                    "mlp_tc_wgrad_kernel", "mlp_wgrad_reduce_kernel"],
     "attention backward (attn_tc_bwd_kernel)": ["attn_tc_bwd_kernel", "attn_wgrad_reduce_kernel"],
     "K6 emb_bwd_adam_both (1 sort + segment-sum + apply, both sides)": ["emb_bwd_phase1", "emb_bwd_phase2_kernel", "DeviceRadixSort",
                                                                         "gather_sorted_kernel", "ids_to_keys2_kernel"],
