@@ -133,6 +133,12 @@ NCF_API int64_t ncf_launch_count(void);   /* kernels this library has launched s
  * back into the stream argument before the call's last kernel.  The caller keeps the stream alive while it is
  * set.  NULL (default) switches all of that off. */
 NCF_API int ncf_set_aux_stream(void* stream);
+/* Early loss read-back for ncf_train_step (opt-in, per device like the auxiliary stream): the loss of a step is final after
+ * the forward, a third of the way into the step.  With a pinned host float and an event set here, ncf_train_step copies
+ * the loss to the host right after the loss kernel and records the event behind the copy, so a training loop that reads
+ * its loss every step (trainer.py:289 `loss.item()`) waits for THAT event instead of draining the whole step, and
+ * enqueues the next step while the backward still runs.  NULL, NULL switches it off. */
+NCF_API int ncf_set_loss_readback(float* host_loss_pinned, void* cuda_event);
 NCF_API int64_t ncf_dense_numel(void);
 NCF_API int64_t ncf_dense_offset(int32_t dense_id);
 NCF_API int64_t ncf_dense_size(int32_t dense_id);

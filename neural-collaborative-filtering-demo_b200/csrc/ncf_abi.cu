@@ -47,6 +47,12 @@ extern "C" int ncf_set_aux_stream(void* stream) {
   aux_ctx()->stream = (cudaStream_t)stream;
   return NCF_OK;
 }
+extern "C" int ncf_set_loss_readback(float* host_loss_pinned, void* cuda_event) {
+  AuxCtx* a = aux_ctx();
+  a->loss_host = host_loss_pinned;
+  a->loss_event = (cudaEvent_t)cuda_event;
+  return NCF_OK;
+}
 extern "C" int64_t ncf_dense_numel(void) { return kLayout.total; }
 extern "C" int64_t ncf_dense_offset(int32_t id) { return id >= 0 && id < NCF_P_COUNT ? kLayout.off[id] : -1; }
 extern "C" int64_t ncf_dense_size(int32_t id) { return id >= 0 && id < NCF_P_COUNT ? kLayout.size[id] : -1; }
@@ -221,6 +227,10 @@ extern "C" int ncf_train_step(const ncf_run_cfg* cfg, const ncf_adam_cfg* adam, 
   NCF_TRY(tower_f32_forward(*cfg, dense, N, nullptr, nullptr, out, w, st));
   // BCELoss gradient goes into the (not yet used) backward scratch g128b
   NCF_TRY(launch_bce(out, targets, N, loss_out, w.g128b, st, true));
+  if (aux->loss_host && aux->loss_event) {        // ncf_set_loss_readback: the loss is final here
+    NCF_CUDA(cudaMemcpyAsync(aux->loss_host, loss_out, sizeof(float), cudaMemcpyDeviceToHost, st));
+    NCF_CUDA(cudaEventRecord(aux->loss_event, st));
+  }
   NCF_TRY(backward_impl(cfg, adam, T, dense, dense_grad, user_ids, item_ids, N, w.g128b, workspace, workspace_bytes, stream, sorted,
                         preswept));
   return ncf_dense_adam(dense, dense_grad, dense_m, dense_v, kLayout.total, adam, stream);

@@ -74,6 +74,8 @@ int emb_bwd_both(const ncf_adam_cfg* adam, const ncf_tables* T, const float* den
 constexpr int NCF_MAX_DEVICES = 64;
 struct AuxCtx {
   cudaStream_t stream = nullptr;
+  float* loss_host = nullptr;          // ncf_set_loss_readback
+  cudaEvent_t loss_event = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};     // 0 fork, 1 sorted (ncf_train_step); 2 fork, 3 join (emb_bwd_both)
 };
 AuxCtx* aux_ctx();

@@ -54,6 +54,10 @@ class NCFTrainEngine:
         self.S = 1 + model.negative_samples
         # the id sort of the embedding backward runs on this stream, next to the forward (ncf_set_aux_stream)
         self._aux_stream = torch.cuda.Stream(device=dev) if os.environ.get("NCF_AUX_STREAM", "1") != "0" else None
+        # early loss read-back (ncf_set_loss_readback): train_step_host waits for the loss only, not for the whole step
+        self._loss_host = torch.zeros(1).pin_memory() if os.environ.get("NCF_EARLY_LOSS", "1") != "0" else None
+        self._loss_event = torch.cuda.Event() if self._loss_host is not None else None
+        self._early_loss = False
         if max_rows:
             self._reserve(max_rows)
 
@@ -131,6 +135,11 @@ class NCFTrainEngine:
             torch.cuda.set_device(self.device)
         try:
             self.lib.ncf_set_aux_stream(C.c_void_p(self._aux_stream.cuda_stream) if self._aux_stream is not None else None)
+            if self._early_loss:
+                self._loss_event.record(torch.cuda.current_stream(self.device))      # creates the event handle on this device
+                self.lib.ncf_set_loss_readback(C.c_void_p(self._loss_host.data_ptr()), C.c_void_p(self._loss_event.cuda_event))
+            else:
+                self.lib.ncf_set_loss_readback(None, None)
             _lib.check(self.lib.ncf_train_step(C.byref(cfg), C.byref(adam), C.byref(tables), _lib.ptr(self.model._flat),
                                                _lib.ptr(self.dense_grad), _lib.ptr(self.dense_m), _lib.ptr(self.dense_v),
                                                _lib.ptr(user_ids), _lib.ptr(item_ids), _lib.ptr(targets), N,
@@ -158,6 +167,7 @@ class NCFTrainEngine:
                              torch.empty(N, dtype=torch.float32, device=self.device)) for _ in range(2)]
             self._stage_slot, self._staged_key, self._staged_event = 0, None, None
             self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._slot_free = [None, None]          # event behind the last step that read each staging set
         cur = self._stage_slot
         du, di, dt = (b[:N] for b in self._dev_in[cur])
         key = (user_ids.data_ptr(), item_ids.data_ptr(), targets.data_ptr(), N)
@@ -167,21 +177,35 @@ class NCFTrainEngine:
             du.copy_(user_ids.reshape(-1), non_blocking=True)
             di.copy_(item_ids.reshape(-1), non_blocking=True)
             dt.copy_(targets.reshape(-1), non_blocking=True)
-        loss = self.train_step(du, di, dt)
+        self._early_loss = self._loss_host is not None
+        try:
+            loss = self.train_step(du, di, dt)
+        finally:
+            self._early_loss = False
         self._staged_key = None
+        self._slot_free[cur] = torch.cuda.current_stream(self.device).record_event()
         if next_batch is not None:
-            # the other staging set was last read by the previous step, whose loss has been read back: it is free
+            # the other staging set was last read by the PREVIOUS step, which may still be in its backward (the host runs
+            # ahead since it waits for the loss only): the copies wait for the event behind that step
             nu, ni, nt = next_batch
             M = nu.numel()
             if M <= self._dev_in[cur ^ 1][0].numel():
+                if self._slot_free[cur ^ 1] is not None:
+                    self._copy_stream.wait_event(self._slot_free[cur ^ 1])
                 with torch.cuda.stream(self._copy_stream):
                     for d, h in zip(self._dev_in[cur ^ 1], (nu, ni, nt)):
                         d[:M].copy_(h.reshape(-1), non_blocking=True)
                     self._staged_event = self._copy_stream.record_event()
                 self._staged_key = (nu.data_ptr(), ni.data_ptr(), nt.data_ptr(), M)
         self._stage_slot = cur ^ 1
-        value = float(loss.item())
-        self.model.check_status("NCFTrainEngine.train_step_host")      # the loss read above synchronised this step
+        if self._loss_host is not None:
+            # the loss is final after the forward: wait for its copy only, the backward keeps running while the caller
+            # prepares (and this engine enqueues) the next step
+            self._loss_event.synchronize()
+            value = float(self._loss_host[0])
+        else:
+            value = float(loss.item())
+        self.model.check_status("NCFTrainEngine.train_step_host")      # K1 (which validates the ids) ran before the loss
         return value
 
     def state_dict(self):
