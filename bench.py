@@ -794,26 +794,8 @@ def sharded_measure(args, users, items, B, precision, table_mode, world, rank, d
     nb = 4
     dev_batches = make_batches(users, items, B, nb, 1234 + rank, device=dev)
     host_batches = make_batches(users, items, B, nb, 4321 + rank, pin=True)
-    # two sets of device staging buffers: while step s runs, the ids of step s+1 are already on the device, so
-    # the engine can route them ahead (ShardedNCFEngine.train_step next_ids)
-    dev_in = [[torch.empty(N, dtype=torch.long, device=dev), torch.empty(N, dtype=torch.long, device=dev),
-               torch.empty(N, dtype=torch.float32, device=dev)] for _ in range(2)]
-    staged = {"slot": 0, "have": False}
-
-    def stage(slot, batch):
-        for d, h in zip(dev_in[slot], batch):
-            d.copy_(h, non_blocking=True)
-
     def step_host(u, i, t, nxt=None):
-        cur = staged["slot"]
-        if not staged["have"]:
-            stage(cur, (u, i, t))
-        nids = None
-        if nxt is not None:
-            stage(cur ^ 1, nxt)
-            nids = tuple(dev_in[cur ^ 1][:2])
-        staged["slot"], staged["have"] = cur ^ 1, nxt is not None
-        return float(eng.train_step(*dev_in[cur], next_ids=nids).item())
+        return eng.train_step_host(u, i, t, next_batch=nxt)
 
     def dev_step(s):
         eng.train_step(*dev_batches[s % nb], next_ids=dev_batches[(s + 1) % nb][:2] if s + 1 < args.steps else None)

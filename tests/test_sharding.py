@@ -310,7 +310,8 @@ def test_lookahead_routing_does_not_change_results():
         t[:, 0] = 1
         batches.append((u.cuda(), i.cuda(), t.reshape(-1).cuda()))
     out = []
-    for look, exchange in ((False, "nccl"), (True, "nccl"), (False, "p2p"), (True, "p2p")):
+    host = [tuple(x.cpu().pin_memory() for x in b) for b in batches]
+    for look, exchange in ((False, "nccl"), (True, "nccl"), (False, "p2p"), (True, "p2p"), ("host", "p2p"), ("host", "nccl")):
         m = ncf_b200.AdvancedNCF(U, I, 5, 24, dropout=0.0)
         m.load_state_dict(p)
         m = m.cuda().train()
@@ -318,8 +319,13 @@ def test_lookahead_routing_does_not_change_results():
                                exchange=exchange)
         losses = []
         for s, b in enumerate(batches):
+            if look == "host":        # host buffers in, loss out; the next batch staged on the copy stream (every other step)
+                nb = host[s + 1] if (s + 1 < len(host) and s != 1) else None
+                losses.append(eng.train_step_host(*host[s], next_batch=nb))
+                continue
             nxt = batches[s + 1][:2] if (look and s + 1 < len(batches)) else None
             losses.append(float(eng.train_step(*b, next_ids=nxt)))
+        torch.cuda.synchronize()
         out.append((losses, [t.clone() for t in eng.w]))
     for other in out[1:]:
         assert max(abs(a - b) for a, b in zip(out[0][0], other[0])) < 1e-5
