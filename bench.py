@@ -812,6 +812,11 @@ def sharded_measure(args, users, items, B, precision, table_mode, world, rank, d
     def e2e_step(s):
         step_host(*host_batches[s % nb], nxt=host_batches[(s + 1) % nb] if s + 1 < args.steps else None)
     e2e = wall_blocks(e2e_step, args.steps, barrier, world, dev, args.min_seconds / 2)
+    # the loss train_step_host hands back early (its own all-reduce behind the forward) is the step's global loss
+    early = step_host(*host_batches[0])
+    final = float(eng.loss.item())
+    if abs(early - final) > 1e-6 * max(1.0, abs(final)):
+        raise RuntimeError(f"train_step_host returned {early}, the step's loss is {final}")
     phases = profile_phases(eng, dev_batches, nb, 6)
     ms_step = statistics.median(blocks) / args.steps
     pk = peaks()

@@ -133,6 +133,12 @@ NCF_API int64_t ncf_launch_count(void);   /* kernels this library has launched s
  * back into the stream argument before the call's last kernel.  The caller keeps the stream alive while it is
  * set.  NULL (default) switches all of that off. */
 NCF_API int ncf_set_aux_stream(void* stream);
+/* SMs the persistent tower kernels (attention / MLP forward and backward: CTAs that own an SM's registers and shared
+ * memory) leave free, process-wide, 0 by default.  The sharded step sets 1: its small collectives (a communication
+ * kernel on another stream) then start at once instead of waiting for the running tower kernel to end - nothing can
+ * co-reside with those CTAs.  At 65,536 interactions per step the tile counts per CTA do not change (2,560 MLP tiles
+ * over 147 CTAs = 18 rounds, as over 148), so the towers lose nothing. */
+NCF_API int ncf_set_sm_reserve(int32_t sms);
 /* Early loss read-back for ncf_train_step (opt-in, per device like the auxiliary stream): the loss of a step is final after
  * the forward, a third of the way into the step.  With a pinned host float and an event set here, ncf_train_step copies
  * the loss to the host right after the loss kernel and records the event behind the copy, so a training loop that reads

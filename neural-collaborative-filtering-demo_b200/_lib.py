@@ -99,6 +99,7 @@ _SIGS = {
     "ncf_workspace_bytes": (_I64, [_I64, C.POINTER(RunCfg)]),
     "ncf_forward": (C.c_int, [C.POINTER(RunCfg), C.POINTER(Tables), _P, _P, _P, _I64, _P, _P, _P, _P, _P, _I64, _P]),
     "ncf_set_aux_stream": (C.c_int, [_P]),
+    "ncf_set_sm_reserve": (C.c_int, [C.c_int32]),
     "ncf_set_loss_readback": (C.c_int, [_P, _P]),
     "ncf_check_ids": (C.c_int, [_P, _P, _I64, _I64, _I64, _P, _P, _P]),
     "ncf_attn_fwd": (C.c_int, [C.POINTER(RunCfg), _P, _I64, _P, _I64, _P]),

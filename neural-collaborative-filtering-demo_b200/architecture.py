@@ -145,7 +145,12 @@ class EmbeddingTables(nn.Module):
 
 
 def _stream(device):
-    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+    """torch's current stream of `device` as the C ABI's stream argument.  The raw accessor is one C call (~0.3 us);
+    torch.cuda.current_stream builds a Stream object (~4 us), and a step passes the stream to two dozen calls."""
+    index = device.index if isinstance(device, torch.device) else device
+    if index is None:
+        index = torch.cuda.current_device()
+    return C.c_void_p(torch._C._cuda_getCurrentRawStream(index))
 
 
 class _NCFFunction(torch.autograd.Function):

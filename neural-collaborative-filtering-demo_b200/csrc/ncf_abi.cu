@@ -47,6 +47,11 @@ extern "C" int ncf_set_aux_stream(void* stream) {
   aux_ctx()->stream = (cudaStream_t)stream;
   return NCF_OK;
 }
+extern "C" int ncf_set_sm_reserve(int32_t sms) {
+  NCF_REQUIRE(sms >= 0 && sms < num_sms(), "set_sm_reserve: %d outside [0, %d)", sms, num_sms());
+  sm_reserve() = sms;
+  return NCF_OK;
+}
 extern "C" int ncf_set_loss_readback(float* host_loss_pinned, void* cuda_event) {
   AuxCtx* a = aux_ctx();
   a->loss_host = host_loss_pinned;

@@ -6,6 +6,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "ncf_b200.h"
 
 namespace ncf {
@@ -125,6 +127,15 @@ inline int num_sms() {
   }
   return n;
 }
+
+// ncf_set_sm_reserve: SMs the persistent tower kernels (one or two CTAs per SM that own its registers / shared memory)
+// leave free, so that a communication kernel queued on another stream (NCCL) starts at once instead of at the end of
+// the tower kernel that happens to be running.  Process-wide; 0 by default.
+inline int& sm_reserve() {
+  static int r = getenv("NCF_SM_RESERVE") ? atoi(getenv("NCF_SM_RESERVE")) : 0;
+  return r;
+}
+inline int tower_sms() { return std::max(1, num_sms() - sm_reserve()); }
 
 inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 

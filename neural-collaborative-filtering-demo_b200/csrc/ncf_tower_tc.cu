@@ -623,7 +623,7 @@ int launch_mlp_tc_fwd(const MlpFwdArgs& A, cudaStream_t st) {
     NCF_CUDA(cudaFuncSetAttribute(mlp_tc_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM2_TOTAL));
   }
   const int64_t ntiles = (A.N + TCM_ROWS - 1) / TCM_ROWS;
-  const int grid = (int)std::min<int64_t>(ntiles, num_sms());
+  const int grid = (int)std::min<int64_t>(ntiles, tower_sms());
   if (variant == 1) mlp_tc_fwd_kernel<<<grid, MLP_THREADS, SM_MLP_TOTAL, st>>>(A);
   else NCF_CUDA(launch_pdl(PDL_MLP_FWD, mlp_tc_fwd2_kernel, dim3(grid), dim3(MLP_THREADS), SM2_TOTAL, st, A));
   NCF_LAUNCH_CHECK();
@@ -1947,7 +1947,7 @@ int mlp_tc_backward(const ncf_run_cfg& cfg, const float* dense, float* dense_gra
     configured = true;
   }
   const int64_t ntiles = (N + TCM_ROWS - 1) / TCM_ROWS;
-  const int grid = (int)std::min<int64_t>(ntiles, num_sms());
+  const int grid = (int)std::min<int64_t>(ntiles, tower_sms());
   MlpBwdArgs B{};
   B.dense = dense;
   B.dense_grad = dense_grad;

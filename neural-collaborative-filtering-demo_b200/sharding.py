@@ -28,6 +28,7 @@ import glob
 import os
 from typing import List, Optional, Tuple
 
+import numpy as np
 import torch
 import torch.distributed as dist
 
@@ -73,6 +74,18 @@ def plan_offsets(counts, rank: int):
         n_dist[side] = acc
         n_recv[side] = sum(c[r][side][rank] for r in range(W))
     return begin, push_off, n_dist, n_recv, sum(int(counts[r][2 * W]) for r in range(W))
+
+
+def plan_offsets_np(counts, rank: int):
+    """plan_offsets as array arithmetic (what the step runs; counts = int64 ndarray): begin int64 [2, world + 1], push_off
+    int64 [2, world], n_dist / n_recv lists of two ints, global_rows int."""
+    W = counts.shape[0]
+    c = counts[:, :2 * W].reshape(W, 2, W)                     # [requester, side, owner]
+    begin = np.zeros((2, W + 1), dtype=np.int64)
+    np.cumsum(c[rank], axis=1, out=begin[:, 1:])
+    push_off = c[:rank].sum(axis=0, dtype=np.int64)
+    n_recv = c[:, :, rank].sum(axis=0)
+    return begin, push_off, [int(begin[0, W]), int(begin[1, W])], [int(n_recv[0]), int(n_recv[1])], int(counts[:, 2 * W].sum())
 
 
 def _alltoallv_many(items, group) -> None:
@@ -253,6 +266,11 @@ class ShardedNCFEngine:
         self._bufs = None
         self._plans = None
         self._plan_slot = 0
+        if self.world > 1:
+            # the step's small collectives must not queue behind a whole tower kernel (include/ncf_b200.h ncf_set_sm_reserve)
+            _lib.check(self.lib.ncf_set_sm_reserve(int(os.environ.get("NCF_SM_RESERVE", "1"))), "ncf_set_sm_reserve")
+        self.profile = bool(os.environ.get("NCF_SHARD_PROFILE"))     # CUDA-event time of every phase (bench.py sets it)
+        self._plan_static = None       # peer pointers of the plan (change only when _setup_p2p remaps)
         self._barrier_word = torch.zeros(1, device=dev)
         # auxiliary stream: the item side of the segment sums / owner update next to the user side, and the routing of the
         # next batch next to whatever leaves SMs free (NCF_SHARD_AUX=0 switches it off)
@@ -303,7 +321,7 @@ class ShardedNCFEngine:
         dev = self.device
         cfg = self._cfg()
         b = {"n": n,
-             "counts": [torch.zeros(2 * self.world + 1, dtype=torch.long, device=dev) for _ in range(2)],
+             "counts": [torch.zeros(2 * self.world + 2, dtype=torch.long, device=dev) for _ in range(2)],      # [users per owner | items per owner | N | loss bits]
              "local": [torch.empty(2, max(n, 1), dtype=torch.long, device=dev) for _ in range(2)],
              "pos": [torch.empty(2, max(n, 1), dtype=torch.long, device=dev) for _ in range(2)],
              "route_ws": [torch.empty(int(self.lib.ncf_shard_route_workspace_bytes(n)), dtype=torch.uint8, device=dev)
@@ -312,8 +330,8 @@ class ShardedNCFEngine:
              "out": torch.empty(max(n, 1), device=dev), "grad_out": torch.empty(max(n, 1), device=dev),
              "rows": [torch.empty(max(n, 1), 128, device=dev) for _ in range(2)],
              "grads": [torch.empty(max(n, 1), 128, device=dev) for _ in range(2)],
-             "counts_all": [torch.zeros(self.world, 2 * self.world + 1, dtype=torch.long, device=dev) for _ in range(2)],
-             "counts_host": [torch.zeros(self.world, 2 * self.world + 1, dtype=torch.long).pin_memory() for _ in range(2)],
+             "counts_all": [torch.zeros(self.world, 2 * self.world + 2, dtype=torch.long, device=dev) for _ in range(2)],
+             "counts_host": [torch.zeros(self.world, 2 * self.world + 2, dtype=torch.long).pin_memory() for _ in range(2)],
              "slot": 0}
         self._bufs = b
         return b
@@ -334,15 +352,18 @@ class ShardedNCFEngine:
         _lib.check(self.lib.ncf_shard_route(_lib.ptr(user_ids), _lib.ptr(item_ids), n, self.U, self.I, self.world,
                                             _lib.ptr(counts), _lib.ptr(local), _lib.ptr(pos), _lib.ptr(rws), rws.numel(),
                                             self._s()), "ncf_shard_route")
-        counts[2 * self.world:].fill_(n)
+        counts[2 * self.world:2 * self.world + 1].fill_(n)
         return dict(N=n, slot=slot, counts=counts, local=local, pos=pos, route_ws=rws,
                     key=(user_ids.data_ptr(), item_ids.data_ptr(), n))
 
-    def _begin_count_gather(self, routed):
-        """all-gather of every rank's [2 * world + 1] counts (a collective every rank reaches: it also serves as a barrier
-        of the one-sided step) + the device -> pinned host copy; nothing waits yet."""
+    def _begin_count_gather(self, routed, loss=None):
+        """all-gather of every rank's [2 * world + 2] counts (a collective every rank reaches: it also serves as a barrier
+        of the one-sided step) + the device -> pinned host copy; nothing waits yet.  loss = this rank's share of the
+        CURRENT step's global loss: rides in the last word (fp32 bits), see _early_loss."""
         b = self._bufs
         slot = routed["slot"]
+        if loss is not None:
+            routed["counts"][2 * self.world + 1:].view(torch.float32)[:1].copy_(loss)
         all_dev, host = b["counts_all"][slot], b["counts_host"][slot]
         if self.world > 1 and dist.is_initialized():
             dist.all_gather_into_tensor(all_dev.view(-1), routed["counts"], group=self.group)
@@ -397,9 +418,11 @@ class ShardedNCFEngine:
         scale = float(N) / float(global_rows)            # local mean -> share of the global mean
         grad_out.mul_(scale)
         self.loss.mul_(scale)
+        if getattr(self, "_want_loss_event", False):
+            self._early_loss()
         self.dense_grad.zero_()
         if push_plan is not None:
-            prof = bool(os.environ.get("NCF_SHARD_PROFILE"))
+            prof = self.profile
             if prof:
                 e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
                 e0.record()
@@ -505,6 +528,7 @@ class ShardedNCFEngine:
         if self._peers is not None:                   # re-sized buffers: drop the old mappings
             self._close_peers()
         self._peers = {"w": [], "rows": [], "ids": []}
+        self._plan_static = None
         for r in range(self.world):
             for kind in ("w", "rows", "ids"):
                 if r == self.rank:
@@ -533,24 +557,31 @@ class ShardedNCFEngine:
         """counts_host [world(requester), 2 * world + 1]: builds this step's ncf_shard_plan in pinned memory, uploads it on
         the stream, and returns (device plan pointer, (n distinct users, items), (rows received users, items), global N)."""
         W, me = self.world, self.rank
-        begin, push_off, n_dist, n_recv, global_rows = plan_offsets(counts_host.tolist(), me)
+        begin, push_off, n_dist, n_recv, global_rows = plan_offsets_np(counts_host.numpy(), me)
         if self._plans is None:
             self._plans = [(torch.zeros(C.sizeof(_lib.ShardPlan), dtype=torch.uint8).pin_memory(),
                             torch.zeros(C.sizeof(_lib.ShardPlan), dtype=torch.uint8, device=self.device)) for _ in range(4)]
         host, dev = self._plans[self._plan_slot]
         self._plan_slot = (self._plan_slot + 1) % len(self._plans)
-        plan = _lib.ShardPlan.from_buffer(host.numpy())
-        plan.world, plan.rank = W, me
-        for side in (0, 1):
-            for o in range(W + 1):
-                plan.begin[side][o] = begin[side][o]
-        for o in range(W):
-            ptrs = self._peer_ptrs(o)
-            for k in range(4):
-                plan.tab[o][k] = ptrs["w"][k]
-            for side in (0, 1):
-                plan.push_rows[side][o] = ptrs["rows"][side] + push_off[side][o] * 512
-                plan.push_ids[side][o] = ptrs["ids"][side] + push_off[side][o] * 8
+        # the struct as 163 int64 words (include/ncf_b200.h ncf_shard_plan): [world | rank] begin[2][17] tab[16][4]
+        # push_rows[2][16] push_ids[2][16]; only begin and the two push pointer tables change from step to step
+        MW = _lib.MAX_WORLD
+        words = host.numpy().view(np.int64)
+        static = self._plan_static if getattr(self, "_peer_engines", None) is None else None
+        if static is None:
+            ptrs = [self._peer_ptrs(o) for o in range(W)]
+            static = {"tab": np.array([[p["w"][k] for k in range(4)] for p in ptrs], dtype=np.int64),
+                      "rows": np.array([[p["rows"][side] for p in ptrs] for side in (0, 1)], dtype=np.int64),
+                      "ids": np.array([[p["ids"][side] for p in ptrs] for side in (0, 1)], dtype=np.int64)}
+            self._plan_static = static
+        host.numpy().view(np.int32)[:2] = (W, me)
+        words[1:1 + 2 * (MW + 1)].reshape(2, MW + 1)[:, :W + 1] = begin
+        o_tab = 1 + 2 * (MW + 1)
+        words[o_tab:o_tab + 4 * MW].reshape(MW, 4)[:W] = static["tab"]
+        o_rows = o_tab + 4 * MW
+        words[o_rows:o_rows + 2 * MW].reshape(2, MW)[:, :W] = static["rows"] + push_off * 512
+        o_ids = o_rows + 2 * MW
+        words[o_ids:o_ids + 2 * MW].reshape(2, MW)[:, :W] = static["ids"] + push_off * 8
         dev.copy_(host, non_blocking=True)
         return C.c_void_p(dev.data_ptr()), n_dist, n_recv, global_rows
 
@@ -564,6 +595,36 @@ class ShardedNCFEngine:
                                                     n_dist[side], _lib.ptr(out), self._s()), "ncf_shard_pull_rows")
             rows.append(out[:n_dist[side]])
         return rows
+
+    def _early_loss(self):
+        """train_step_host: the global loss needs the forward only.  Right behind the loss kernel (on the collectives'
+        stream, at the same point of the step on every rank) this rank's share is exchanged and copied to pinned memory: the
+        host has the step's result while the backward is still running, so preparing the next step (staging, routing,
+        ~0.9 ms of host work per step) is off the critical path - read behind the tower-gradient all-reduce instead, every
+        step started one host latency late (N = 2: 1.63 vs 1.49 ms per step end to end).  With look-ahead the share rides
+        in the count all-gather of the NEXT batch (one collective, one event for the host: this step's loss and the next
+        step's split sizes); the barrier that collective used to be becomes a one-word all-reduce (_train_step_p2p)."""
+        main = torch.cuda.current_stream(self.device)
+        multi = self.world > 1 and dist.is_initialized()
+        nxt = self.__dict__.pop("_pending_next", None)
+        if multi and self._aux is not None:
+            if getattr(self, "_coll", None) is None:
+                self._coll = torch.cuda.Stream(device=self.device)
+            self._coll.wait_event(main.record_event())
+            with torch.cuda.stream(self._coll):
+                if nxt is not None:
+                    self._coll.wait_stream(self._aux)            # the routing kernels of the next batch
+                    self._prefetched = self._begin_count_gather(nxt, loss=self.loss)
+                    self._loss_event, self._loss_from_counts = nxt["event"], nxt["counts_host"]
+                else:
+                    word = self.__dict__.setdefault("_loss_word", torch.zeros(1, device=self.device))
+                    word.copy_(self.loss)
+                    dist.all_reduce(word, group=self.group)
+                    self._loss_host.copy_(word, non_blocking=True)
+                    self._loss_event = self._coll.record_event()
+        elif not multi:
+            self._loss_host.copy_(self.loss, non_blocking=True)
+            self._loss_event = main.record_event()
 
     def _barrier(self):
         """a collective every rank reaches in stream order (used where the step has no other one at that point)"""
@@ -580,20 +641,25 @@ class ShardedNCFEngine:
     def train_step_host(self, user_ids: torch.Tensor, item_ids: torch.Tensor, targets: torch.Tensor, next_batch=None) -> float:
         """End-to-end step from HOST (ideally pinned) buffers (what trainer.py:253-254, 289 do per batch): H2D copies of
         this rank's ids and targets, the step, and the D2H read of the global loss.  next_batch = the host tensors of the
-        NEXT call: copied on a copy stream into the other staging set while this step computes, and routed a step ahead
-        (train_step next_ids).  The host waits for the loss only - it is final after the tower-gradient all-reduce - so the
-        owner update and the dense Adam of this step overlap the host's work on the next one."""
+        NEXT call: copied on a copy stream into another staging set while this step computes, and routed a step ahead
+        (train_step next_ids).  THREE staging sets: the set the next batch goes into was last read two steps ago, so its
+        copy never waits for the step the device is still running - with two sets the copy, and with it the routing of
+        the next batch, started 0.2 ms into the step, behind the towers (1.61 vs 1.49 ms per step at N = 2).  The host waits for the loss only, which is
+        exchanged right behind the forward (_early_loss): the backward, the owner update and the dense Adam of this step
+        overlap the host's work on the next one.  Every rank must drive the same sequence of calls (the exchanges are
+        collectives)."""
         N = user_ids.numel()
         dev = self.device
         main = torch.cuda.current_stream(dev)
         if getattr(self, "_dev_in", None) is None or self._dev_in[0][0].numel() < N:
             self._dev_in = [(torch.empty(N, dtype=torch.long, device=dev), torch.empty(N, dtype=torch.long, device=dev),
-                             torch.empty(N, dtype=torch.float32, device=dev)) for _ in range(2)]
+                             torch.empty(N, dtype=torch.float32, device=dev)) for _ in range(3)]
             self._stage_slot, self._staged_key, self._staged_event = 0, None, None
             self._copy_stream = torch.cuda.Stream(device=dev)
-            self._slot_free = [None, None]
+            self._slot_free = [None, None, None]
             self._loss_host = torch.zeros(1).pin_memory()
         cur = self._stage_slot
+        nxt_slot = (cur + 1) % 3
         du, di, dt = (b[:N] for b in self._dev_in[cur])
         key = (user_ids.data_ptr(), item_ids.data_ptr(), targets.data_ptr(), N)
         if self._staged_key == key:
@@ -603,32 +669,41 @@ class ShardedNCFEngine:
             di.copy_(item_ids.reshape(-1), non_blocking=True)
             dt.copy_(targets.reshape(-1), non_blocking=True)
         self._staged_key = None
-        nids = None
-        if next_batch is not None:
+        self._next_ids_event = None
+
+        def stage_next():
+            """copies the next batch into the other staging set on the copy stream; returns its device ids (or None).
+            Called by the step once its own first kernels are enqueued (train_step next_ids as a callable)."""
             nu, ni, nt = next_batch
             M = nu.numel()
-            if M <= self._dev_in[cur ^ 1][0].numel():
-                if self._slot_free[cur ^ 1] is not None:      # the step that last read that staging set may still be running
-                    self._copy_stream.wait_event(self._slot_free[cur ^ 1])
-                with torch.cuda.stream(self._copy_stream):
-                    for d, h in zip(self._dev_in[cur ^ 1], (nu, ni, nt)):
-                        d[:M].copy_(h.reshape(-1), non_blocking=True)
-                    self._staged_event = self._copy_stream.record_event()
-                self._staged_key = (nu.data_ptr(), ni.data_ptr(), nt.data_ptr(), M)
-                nids = (self._dev_in[cur ^ 1][0][:M], self._dev_in[cur ^ 1][1][:M])
+            if self._slot_free[nxt_slot] is not None:      # the step that last read that staging set may still be running
+                self._copy_stream.wait_event(self._slot_free[nxt_slot])
+            with torch.cuda.stream(self._copy_stream):
+                for d, h in zip(self._dev_in[nxt_slot], (nu, ni, nt)):
+                    d[:M].copy_(h.reshape(-1), non_blocking=True)
+                self._staged_event = self._copy_stream.record_event()
+            self._staged_key = (nu.data_ptr(), ni.data_ptr(), nt.data_ptr(), M)
+            self._next_ids_event = self._staged_event
+            return self._dev_in[nxt_slot][0][:M], self._dev_in[nxt_slot][1][:M]
+        look = next_batch is not None and next_batch[0].numel() <= self._dev_in[nxt_slot][0].numel()
         self._want_loss_event = True
-        self._next_ids_event = self._staged_event if nids is not None else None
         try:
-            loss = self.train_step(du, di, dt, next_ids=nids)
+            loss = self.train_step(du, di, dt, next_ids=stage_next if look else None)
         finally:
             self._want_loss_event = False
             self._next_ids_event = None
         self._slot_free[cur] = main.record_event()
-        self._stage_slot = cur ^ 1
+        self._stage_slot = nxt_slot
         ev = self.__dict__.pop("_loss_event", None)
+        shares = self.__dict__.pop("_loss_from_counts", None)
         if ev is not None:
+            if getattr(self, "_debug_no_loss_wait", False):      # tools/host_profile_sharded.py: is the wait the bottleneck?
+                return float("nan")
             ev.synchronize()
-            value = float(self._loss_host[0])
+            if shares is not None:      # every rank's share, summed in rank order (fp32, the same bits on every rank)
+                value = float(shares[:, 2 * self.world + 1:].contiguous().view(torch.float32)[:, 0].sum(dtype=torch.float32))
+            else:
+                value = float(self._loss_host[0])
         else:
             value = float(loss.item())
         self.check_status()
@@ -647,26 +722,32 @@ class ShardedNCFEngine:
         self.step += 1
         self._adopt(pre)
         main = torch.cuda.current_stream(self.device)
-        nxt = None
-        if next_ids is not None:
-            # the next batch's routing (sort, de-duplication) depends on its ids only: on the auxiliary stream it fills the
-            # SMs this step's kernels leave idle (kernel boundaries, tails of the persistent tower kernels).  It is enqueued
-            # FIRST: enqueued after this step's own kernels it starts later on the device and the step is 6 % slower
-            # (measured at N = 2: 1.576 vs 1.484 ms), more than the host gains by reaching the first kernel sooner.
-            rs = self._aux if self._aux is not None else main
-            if rs is not main:
-                rs.wait_stream(main)
-            if getattr(self, "_next_ids_event", None) is not None:
-                rs.wait_event(self._next_ids_event)          # the next ids arrive on a copy stream (train_step_host)
-            with torch.cuda.stream(rs):
-                nxt = self._route(next_ids[0], next_ids[1], self._bufs["slot"])
-            self._bufs["slot"] ^= 1
+        step_start = main.record_event() if next_ids is not None else None      # the previous step is complete here
         pre["event"].synchronize()                   # the split sizes: already there when the batch was routed a step ahead
         plan_ptr, n_dist, n_recv, global_rows = self._fill_plan(pre["counts_host"])
         mark("route + plan")
         rows = self.phase_pull(plan_ptr, n_dist)
         mark("pull rows (P2P)")
+        nxt = None
+        if next_ids is not None:
+            # the next batch's routing (sort, de-duplication) depends on its ids only: on the auxiliary stream it fills the
+            # SMs this step's kernels leave idle (kernel boundaries, tails of the persistent tower kernels).  It is enqueued
+            # BEFORE the towers: behind them it starts late on the device - they own every SM's shared memory - and the step
+            # is 6 % slower (N = 2: 1.576 vs 1.484 ms); but AFTER the pull, so that a host that comes straight from waiting
+            # for the previous loss (train_step_host) reaches this step's first kernel 0.2 ms sooner.
+            if callable(next_ids):
+                next_ids = next_ids()                # train_step_host: stages the next batch on its copy stream here
+            rs = self._aux if self._aux is not None else main
+            if rs is not main:
+                rs.wait_event(step_start)
+            if getattr(self, "_next_ids_event", None) is not None:
+                rs.wait_event(self._next_ids_event)          # the next ids arrive on a copy stream (train_step_host)
+            with torch.cuda.stream(rs):
+                nxt = self._route(next_ids[0], next_ids[1], self._bufs["slot"])
+            self._bufs["slot"] ^= 1
+        self._pending_next = nxt if getattr(self, "_want_loss_event", False) else None
         self.phase_forward_backward(rows, targets, global_rows, push_plan=plan_ptr)
+        self._pending_next = None
         mark("forward+backward+push (P2P)")
         # Collectives of the step, all issued on their own stream in the same order on every rank:
         #   A  count all-gather of the NEXT batch (look-ahead; else a one-word all-reduce): a barrier - every requester's
@@ -683,15 +764,16 @@ class ShardedNCFEngine:
             coll.wait_stream(main)                   # after this rank's push and its tower gradients
             coll.wait_stream(self._aux)              # ... and after the routing kernels of the next batch
         with torch.cuda.stream(coll):
-            if nxt is not None:
+            if nxt is not None and self._prefetched is not nxt:
                 self._prefetched = self._begin_count_gather(nxt)
             else:
-                self._barrier()
+                self._barrier()                      # (the counts travelled with the loss already: _early_loss)
             ev_a = coll.record_event() if coll is not main else None
             if multi:
                 self._dense_and_loss[-1:].copy_(self.loss)
                 dist.all_reduce(self._dense_and_loss, group=self.group)
-            if getattr(self, "_want_loss_event", False):     # train_step_host: the global loss is final here
+            if getattr(self, "_want_loss_event", False) and getattr(self, "_loss_event", None) is None:
+                # train_step_host without the early read (_early_loss): the global loss is final here
                 self._loss_host.copy_(self._dense_and_loss[-1:] if multi else self.loss, non_blocking=True)
                 self._loss_event = coll.record_event() if coll is not main else main.record_event()
         if ev_a is not None:
@@ -721,7 +803,9 @@ class ShardedNCFEngine:
 
         next_ids = (user_ids, item_ids) the NEXT call will be given (input-pipeline look-ahead; all ranks must pass it
         or none): that batch is routed (sort, de-duplication, count exchange) inside this step, so the one host
-        synchronisation of a step - reading the counts - finds them already there instead of draining the queue."""
+        synchronisation of a step - reading the counts - finds them already there instead of draining the queue.  It may
+        be a callable returning that pair: the step calls it once its own first kernels are enqueued (train_step_host
+        stages the next batch there)."""
         self.check_status()
         if self.exchange == "p2p":
             return self._train_step_p2p(user_ids, item_ids, targets, next_ids)
@@ -765,6 +849,8 @@ class ShardedNCFEngine:
         recv = ShardRouter.exchange_rows_multi(self.routers, grads, to_owner=True)
         mark("a2a grads")
         if next_ids is not None:
+            if callable(next_ids):
+                next_ids = next_ids()
             keep = (self._routed, self._served)
             if getattr(self, "_next_ids_event", None) is not None:
                 torch.cuda.current_stream(self.device).wait_event(self._next_ids_event)
@@ -784,7 +870,7 @@ class ShardedNCFEngine:
 
     # NCF_SHARD_PROFILE=1: CUDA-event time of every phase, summed over the steps (bench.py prints it to stderr)
     def _mark(self, name):
-        if not os.environ.get("NCF_SHARD_PROFILE"):
+        if not self.profile:
             return
         ev = torch.cuda.Event(enable_timing=True)
         ev.record()

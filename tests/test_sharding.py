@@ -28,7 +28,8 @@ def test_shard_arithmetic_bit_exact():
 def test_plan_offsets_of_the_one_sided_step_match_a_brute_force_layout():
     """The host arithmetic behind the pull / push kernels: every requester's segment lands exactly once, in requester order,
     inside every owner's receive buffer, and the row counts add up (also with ragged batches and empty segments)."""
-    from ncf_b200.sharding import plan_offsets
+    import numpy as np
+    from ncf_b200.sharding import plan_offsets, plan_offsets_np
     g = torch.Generator().manual_seed(0)
     for W in (1, 2, 3, 8):
         counts = torch.randint(0, 50, (W, 2 * W + 1), generator=g)
@@ -46,6 +47,9 @@ def test_plan_offsets_of_the_one_sided_step_match_a_brute_force_layout():
                     at += n
                     assert total == sum(c[2 * W] for c in counts)
                 assert plan_offsets(counts, o)[3][side] == len(layout)
+        for r in range(W):                          # the array form the step runs is the same arithmetic
+            a, b = plan_offsets(counts, r), plan_offsets_np(np.asarray(counts, dtype=np.int64), r)
+            assert [row[:W + 1] for row in a[0]] == b[0].tolist() and a[1] == b[1].tolist() and a[2:] == b[2:]
 
 
 def _router_worker(rank, world, init_file, rows, ret):

@@ -4,7 +4,7 @@ tracked summaries under profiles/:
   <tag>_launches.csv / .md   per-kernel launch list (copy + table)
   <tag>_ncu_full.json        per-kernel digest: time, DRAM bytes, pipes, occupancy, top stall reasons
   traffic.json               DRAM bytes per step of the stage bench.py reports as `roofline.kernel`
-usage: python tools/make_profiles.py <tag> <workload> gpurun_out/launches.csv gpurun_out/step.ncu-rep "<command>"
+usage: python tools/make_profiles.py <tag> <workload> gpurun_out/launches.csv gpurun_out/step.ncu-rep "<command>" [full|metrics]
 
 The .ncu-rep may also come from a capture with an explicit --metrics list (the METRICS below; ~1 minute of GPU time
 instead of ~3.5 for --set full): the digest then has no stall reasons - say so in the note of the written JSON
@@ -49,7 +49,8 @@ def num(x):
         return None
 
 
-def main(tag, workload, launches, rep, command):
+def main(tag, workload, launches, rep, command, kind="full"):
+    how = "ncu --set full" if kind == "full" else "ncu with an explicit metric list (time, DRAM bytes, pipes, occupancy; no stall reasons)"
     prof = os.path.join(REPO, "profiles")
     os.makedirs(prof, exist_ok=True)
     shutil.copy(launches, os.path.join(prof, f"{tag}_launches.csv"))
@@ -82,7 +83,7 @@ def main(tag, workload, launches, rep, command):
         a[2] += d.get("dram__bytes_read.sum") or 0
         a[3] += d.get("dram__bytes_write.sum") or 0
     with open(os.path.join(prof, f"{tag}_ncu_full.json"), "w") as f:
-        json.dump({"command": command, "note": "one training step captured with ncu --set full --clock-control none; "
+        json.dump({"command": command, "note": f"one training step captured with {how} --clock-control none; "
                    "cold-cache, serialised kernels: compare shares and bytes, not absolute times", "kernels": digest}, f, indent=1)
     stages = {}
     for label, pats in STAGES.items():
@@ -102,7 +103,7 @@ def main(tag, workload, launches, rep, command):
         f.write(f"# {tag}: launch list, workload {workload}\n\nCommand: `{command}`\n\n"
                 "Cold-cache, serialised per-launch times (`--clock-control none`): read the shares, not the absolute times.\n\n")
         f.write(table)
-        f.write("\n## DRAM traffic per step by stage (ncu --set full, same command)\n\n| stage | kernels | time us | DRAM read MB | DRAM write MB |\n|---|---|---:|---:|---:|\n")
+        f.write(f"\n## DRAM traffic per step by stage ({how}, same command)\n\n| stage | kernels | time us | DRAM read MB | DRAM write MB |\n|---|---|---:|---:|---:|\n")
         for label, pats in STAGES.items():
             ks = {k: v for k, v in per_kernel.items() if any(p in k for p in pats)}
             if ks:
@@ -112,4 +113,4 @@ def main(tag, workload, launches, rep, command):
 
 
 if __name__ == "__main__":
-    main(*sys.argv[1:6])
+    main(*sys.argv[1:7])
