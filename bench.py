@@ -833,9 +833,9 @@ def sharded_measure(args, users, items, B, precision, table_mode, world, rank, d
 
 
 def profile_phases(eng, dev_batches, nb, steps):
-    """CUDA-event time of every phase of the sharded step (NCF_SHARD_PROFILE), a few extra steps after the timed region;
+    """CUDA-event time of every phase of the sharded step (ShardedNCFEngine.profile), a few extra steps after the timed region;
     the per-phase synchronisation removes overlap, so the phases sum to more than a timed step."""
-    os.environ["NCF_SHARD_PROFILE"] = "1"
+    eng.profile = True
     try:
         if getattr(eng, "phase_ms", None):
             eng.phase_ms.clear()
@@ -843,7 +843,7 @@ def profile_phases(eng, dev_batches, nb, steps):
             eng.train_step(*dev_batches[s % nb])
         prof = dict(getattr(eng, "phase_ms", {}) or {})
     finally:
-        os.environ.pop("NCF_SHARD_PROFILE", None)
+        eng.profile = False
     n = prof.pop("steps", 0)
     return {k: v / n for k, v in prof.items()} if n else None
 
