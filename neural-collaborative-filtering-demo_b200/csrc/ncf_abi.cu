@@ -38,9 +38,14 @@ AuxCtx* aux_ctx() {
   return &g_aux[dev];
 }
 int aux_events(AuxCtx* a) {
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 6; ++i)
     if (!a->ev[i]) NCF_CUDA(cudaEventCreateWithFlags(&a->ev[i], cudaEventDisableTiming));
+  if (!a->side) NCF_CUDA(cudaStreamCreateWithFlags(&a->side, cudaStreamNonBlocking));
   return NCF_OK;
+}
+int& wgrad_side_sms() {
+  static int r = getenv("NCF_WGRAD_SMS") ? atoi(getenv("NCF_WGRAD_SMS")) : 28;     // measured: tools/ab_env.sh NCF_WGRAD_SMS
+  return r;
 }
 }
 extern "C" int ncf_set_aux_stream(void* stream) {

@@ -627,14 +627,15 @@ int attn_tc_forward(const ncf_run_cfg& cfg, const float* dense, int64_t N, Tower
   A.a_img = w.a_img;
   A.N = N;
   A.rng = make_rng(cfg, 0);
-  const int grid = (int)std::min<int64_t>(attn_tc_tiles(N), (int64_t)tower_sms() * 2);
+  const int grid = even_grid(attn_tc_tiles(N), (int64_t)tower_sms() * 2);
   NCF_CUDA(launch_pdl(PDL_ATTN_FWD, attn_tc_fwd_kernel, dim3(grid), dim3(AT_THREADS), AF_TOTAL, st, A));
   NCF_LAUNCH_CHECK();
   return NCF_OK;
 }
 
 // da = w.g64a -> dxu = w.g64b, dxp = w.g256 ([N,64]); accumulates the six attention parameter gradients
-int attn_tc_backward(const ncf_run_cfg& cfg, const float* dense, float* dense_grad, int64_t N, TowerWs& w, cudaStream_t st) {
+int attn_tc_backward(const ncf_run_cfg& cfg, const float* dense, float* dense_grad, int64_t N, TowerWs& w, cudaStream_t st,
+                     int leave_sms) {
   if (N == 0) return NCF_OK;
   static bool configured = false;
   if (!configured) {
@@ -651,7 +652,7 @@ int attn_tc_backward(const ncf_run_cfg& cfg, const float* dense, float* dense_gr
   A.partial = w.at_partial;
   A.N = N;
   A.rng = make_rng(cfg, 0);
-  const int grid = (int)std::min<int64_t>((N + AT_RT - 1) / AT_RT, (int64_t)tower_sms());
+  const int grid = even_grid((N + AT_RT - 1) / AT_RT, std::max(1, tower_sms() - leave_sms));
   NCF_CUDA(launch_pdl(PDL_ATTN_BWD, attn_tc_bwd_kernel, dim3(grid), dim3(AT_THREADS), AB_TOTAL, st, A));
   NCF_LAUNCH_CHECK();
   NCF_CUDA(launch_pdl(PDL_ATTN_BWD, attn_wgrad_reduce_kernel, dim3((AB_ACC + 255) / 256), dim3(256), 0, st, (const float*)w.at_partial, grid, dense_grad));

@@ -136,6 +136,16 @@ inline int& sm_reserve() {
   return r;
 }
 inline int tower_sms() { return std::max(1, num_sms() - sm_reserve()); }
+// Persistent kernels walk their tiles round-robin: `ctas` CTAs need ceil(ntiles / ctas) rounds, and the smallest grid with
+// that round count finishes at the same time while leaving the other SMs to whatever waits on another stream (the id sort
+// and the dense-equivalent sweep of the auxiliary stream).  2,560 tiles: 143 CTAs instead of 148, 18 rounds either way.
+inline int even_grid(int64_t ntiles, int64_t ctas) {
+  static const bool on = !(getenv("NCF_EVEN_GRID") && getenv("NCF_EVEN_GRID")[0] == '0');     // A/B switch
+  ctas = std::max<int64_t>(1, std::min(ntiles, ctas));
+  if (!on || ntiles <= 0) return (int)ctas;
+  const int64_t rounds = (ntiles + ctas - 1) / ctas;
+  return (int)((ntiles + rounds - 1) / rounds);
+}
 
 inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 

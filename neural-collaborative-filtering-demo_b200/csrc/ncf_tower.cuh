@@ -47,13 +47,17 @@ int tower_attn_forward(const ncf_run_cfg& cfg, const float* dense, int64_t N, To
 int tower_mlp_forward(const ncf_run_cfg& cfg, const float* dense, int64_t N, const int64_t* hour, const float* tail1,
                       float* out, TowerWs& w, cudaStream_t st);
 int tower_mlp_backward(const ncf_run_cfg& cfg, const float* dense, float* dense_grad, int64_t N, const float* grad_out,
-                       TowerWs& w, cudaStream_t st);
+                       TowerWs& w, cudaStream_t st, cudaStream_t side = nullptr, int side_sms = 0, cudaEvent_t fork = nullptr,
+                       cudaEvent_t join = nullptr);
 int tower_attn_backward(const ncf_run_cfg& cfg, const float* dense, float* dense_grad, int64_t N, TowerWs& w, cudaStream_t st);
 // tcgen05 MLP tower (ncf_tower_tc.cu): forward from w.a (fills w.mlp_pred, w.p_saved, out; w.y3 stays unused)
 int mlp_tc_forward(const ncf_run_cfg& cfg, const float* dense, int64_t N, const int64_t* hour, const float* tail1,
                    float* out, TowerWs& w, cudaStream_t st);
 // backward from w.d_mlp (dL/d mlp_pred per row) to da = w.g64a; accumulates the MLP parameter gradients incl. mlp_output.weight
-int mlp_tc_backward(const ncf_run_cfg& cfg, const float* dense, float* dense_grad, int64_t N, TowerWs& w, cudaStream_t st);
+// side != null: the weight-gradient kernel (HBM-bound, independent of everything up to the dense Adam) is launched on that
+// stream with side_sms CTAs behind the event `fork` and signals `join`; the caller's next tower kernel leaves those SMs free
+int mlp_tc_backward(const ncf_run_cfg& cfg, const float* dense, float* dense_grad, int64_t N, TowerWs& w, cudaStream_t st,
+                    cudaStream_t side = nullptr, int side_sms = 0, cudaEvent_t fork = nullptr, cudaEvent_t join = nullptr);
 // tcgen05 projections of the attention block (fp32 tensors, bf16 operands)
 int tc_proj_forward(int which, const float* X, const float* W, const float* bias, float* Y, int64_t N, cudaStream_t st);
 // 64 -> 64 projection whose output is written as a bf16 tile image (the MLP kernels' A operand)
@@ -63,7 +67,8 @@ int tc_proj_wgrad(int which, const float* Z, const float* X, float* dW, float* d
 // fused attention block on tcgen05 for S = 5 (ncf_attn_tc.cu): forward xu, xp -> a_img; backward da (w.g64a) ->
 // dxu (w.g64b), dxp (w.g256) + the attention parameter gradients, recomputing q, k, v and the probabilities
 int attn_tc_forward(const ncf_run_cfg& cfg, const float* dense, int64_t N, TowerWs& w, cudaStream_t st);
-int attn_tc_backward(const ncf_run_cfg& cfg, const float* dense, float* dense_grad, int64_t N, TowerWs& w, cudaStream_t st);
+int attn_tc_backward(const ncf_run_cfg& cfg, const float* dense, float* dense_grad, int64_t N, TowerWs& w, cudaStream_t st,
+                     int leave_sms = 0);
 int64_t attn_tc_partial_floats();
 // fused embedding backward of both sides with a single radix sort (ncf_embed.cu)
 int emb_bwd_both(const ncf_adam_cfg* adam, const ncf_tables* T, const float* dense, float* dense_grad,
@@ -76,10 +81,14 @@ struct AuxCtx {
   cudaStream_t stream = nullptr;
   float* loss_host = nullptr;          // ncf_set_loss_readback
   cudaEvent_t loss_event = nullptr;
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};     // 0 fork, 1 sorted (ncf_train_step); 2 fork, 3 join (emb_bwd_both)
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};     // 0 fork, 1 sorted (ncf_train_step); 2 fork, 3 join (emb_bwd_both); 4 fork, 5 join (side stream)
+  cudaStream_t side = nullptr;         // library-owned second stream (created with the first use): MLP weight gradients next to the attention backward
 };
 AuxCtx* aux_ctx();
 int aux_events(AuxCtx* a);
+// SMs given to the MLP weight-gradient kernel while the attention backward runs on the others (0 = one after the other);
+// only with an auxiliary stream set (the opt-in for concurrency inside a step)
+int& wgrad_side_sms();
 int emb_sweep_early(const ncf_adam_cfg* adam, const ncf_tables* T, const int64_t* user_ids, const int64_t* item_ids, int64_t N,
                     cudaStream_t st);
 int emb_sort_both(const ncf_tables* T, const int64_t* user_ids, const int64_t* item_ids, int64_t N, void* workspace,

@@ -860,13 +860,26 @@ int tower_mlp_forward(const ncf_run_cfg& cfg, const float* dense, int64_t N, con
 // produces w.d_mf [N], dxu = w.g64b, dxp = w.g256 and accumulates every dense gradient
 int tower_f32_backward(const ncf_run_cfg& cfg, const float* dense, float* dg, int64_t N, const float* grad_out,
                        TowerWs& w, cudaStream_t st) {
+  // bf16 towers with an auxiliary stream set: the MLP weight-gradient kernel (HBM-bound) runs on a few SMs NEXT TO the
+  // attention backward (issue-bound, 1.3 TB/s of DRAM traffic), which leaves them those SMs
+  AuxCtx* aux = aux_ctx();
+  const int side_sms = wgrad_side_sms();
+  if (side_sms > 0 && side_sms < tower_sms() && aux->stream && tower_bf16_rows(cfg) && N >= (int64_t)128 * num_sms()) {
+    NCF_TRY(aux_events(aux));
+    NCF_TRY(tower_mlp_backward(cfg, dense, dg, N, grad_out, w, st, aux->side, side_sms, aux->ev[4], aux->ev[5]));
+    NCF_TRY(attn_tc_backward(cfg, dense, dg, N, w, st, side_sms));
+    w.dxu = w.g64b;
+    w.dxp = w.g256;
+    NCF_CUDA(cudaStreamWaitEvent(st, aux->ev[5], 0));
+    return NCF_OK;
+  }
   NCF_TRY(tower_mlp_backward(cfg, dense, dg, N, grad_out, w, st));
   return tower_attn_backward(cfg, dense, dg, N, w, st);
 }
 
 // head + MLP tower: grad_out -> w.d_mf, da (w.g64a) + their parameter gradients
 int tower_mlp_backward(const ncf_run_cfg& cfg, const float* dense, float* dg, int64_t N, const float* grad_out,
-                       TowerWs& w, cudaStream_t st) {
+                       TowerWs& w, cudaStream_t st, cudaStream_t side, int side_sms, cudaEvent_t fork, cudaEvent_t join) {
   const float* P = dense;
   if (!cfg.training) { set_error("backward needs a training-mode forward"); return NCF_ERR_ARG; }
   const int hgrid = (int)std::min<int64_t>((N * 16 + 255) / 256, (int64_t)num_sms() * 8);
@@ -881,7 +894,7 @@ int tower_mlp_backward(const ncf_run_cfg& cfg, const float* dense, float* dg, in
   }
   NCF_LAUNCH_CHECK();
   if (cfg.precision == NCF_BF16_TC) {
-    NCF_TRY(mlp_tc_backward(cfg, dense, dg, N, w, st));   // dy3 (g64a) -> da (g64a), all MLP parameter gradients
+    NCF_TRY(mlp_tc_backward(cfg, dense, dg, N, w, st, side, side_sms, fork, join));   // dy3 (g64a) -> da (g64a), all MLP parameter gradients
   } else {
   // layer 3: dz3 (g64b); dW8 += dz3^T y2 ; dy2 (g128) = dz3 . W8
   NCF_TRY(launch_relu_ln_drop_bwd<64>(w.g64a, w.r3, P + NCF_OFF(NCF_P_LN2_W), w.g64b, N, make_rng(cfg, 3),

@@ -623,7 +623,7 @@ int launch_mlp_tc_fwd(const MlpFwdArgs& A, cudaStream_t st) {
     NCF_CUDA(cudaFuncSetAttribute(mlp_tc_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM2_TOTAL));
   }
   const int64_t ntiles = (A.N + TCM_ROWS - 1) / TCM_ROWS;
-  const int grid = (int)std::min<int64_t>(ntiles, tower_sms());
+  const int grid = even_grid(ntiles, tower_sms());
   if (variant == 1) mlp_tc_fwd_kernel<<<grid, MLP_THREADS, SM_MLP_TOTAL, st>>>(A);
   else NCF_CUDA(launch_pdl(PDL_MLP_FWD, mlp_tc_fwd2_kernel, dim3(grid), dim3(MLP_THREADS), SM2_TOTAL, st, A));
   NCF_LAUNCH_CHECK();
@@ -1937,7 +1937,8 @@ __global__ void __launch_bounds__(256) mlp_wgrad_reduce_kernel(const float* __re
   dg[off] += s;
 }
 
-int mlp_tc_backward(const ncf_run_cfg& cfg, const float* dense, float* dense_grad, int64_t N, TowerWs& w, cudaStream_t st) {
+int mlp_tc_backward(const ncf_run_cfg& cfg, const float* dense, float* dense_grad, int64_t N, TowerWs& w, cudaStream_t st,
+                    cudaStream_t side, int side_sms, cudaEvent_t fork, cudaEvent_t join) {
   if (N == 0) return NCF_OK;
   static bool configured = false;
   if (!configured) {
@@ -1947,7 +1948,7 @@ int mlp_tc_backward(const ncf_run_cfg& cfg, const float* dense, float* dense_gra
     configured = true;
   }
   const int64_t ntiles = (N + TCM_ROWS - 1) / TCM_ROWS;
-  const int grid = (int)std::min<int64_t>(ntiles, tower_sms());
+  const int grid = even_grid(ntiles, tower_sms());
   MlpBwdArgs B{};
   B.dense = dense;
   B.dense_grad = dense_grad;
@@ -1979,10 +1980,19 @@ int mlp_tc_backward(const ncf_run_cfg& cfg, const float* dense, float* dense_gra
   W.dense_grad = dense_grad;
   W.partial = w.wg_partial;
   W.N = N;
-  NCF_CUDA(launch_pdl(PDL_MLP_WGRAD, mlp_tc_wgrad_kernel, dim3(grid), dim3(TCM_THREADS), SMW_TOTAL, st, W));
+  cudaStream_t wst = st;
+  int wgrid = grid;
+  if (side && side_sms > 0 && fork && join) {
+    NCF_CUDA(cudaEventRecord(fork, st));
+    NCF_CUDA(cudaStreamWaitEvent(side, fork, 0));
+    wst = side;
+    wgrid = (int)std::min<int64_t>(ntiles, side_sms);
+  }
+  NCF_CUDA(launch_pdl(PDL_MLP_WGRAD, mlp_tc_wgrad_kernel, dim3(wgrid), dim3(TCM_THREADS), SMW_TOTAL, wst, W));
   NCF_LAUNCH_CHECK();
-  NCF_CUDA(launch_pdl(PDL_MLP_WGRAD, mlp_wgrad_reduce_kernel, dim3((WG_PART + 255) / 256), dim3(256), 0, st, (const float*)w.wg_partial, grid, dense_grad));
+  NCF_CUDA(launch_pdl(PDL_MLP_WGRAD, mlp_wgrad_reduce_kernel, dim3((WG_PART + 255) / 256), dim3(256), 0, wst, (const float*)w.wg_partial, wgrid, dense_grad));
   NCF_LAUNCH_CHECK();
+  if (wst != st) NCF_CUDA(cudaEventRecord(join, wst));
   return NCF_OK;
 }
 
