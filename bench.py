@@ -45,7 +45,7 @@ FLOP_MLP_FWD = 131.1e3 + 0.5e3                 # MLP + heads/LN per row; backwar
 BYTES_ATTN_FWD = 2 * 128 + 128                 # xu, xp (bf16 rows) in; a (bf16) out
 BYTES_MLP_FWD = 128 + 2 * (512 + 256) + 128 + 24 + 16              # a in; r1,y1,r2,y2,r3 (bf16), LN stats, scalars out
 BYTES_MLP_BWD = 28 + (896 + 24 + 896 + 128) + (128 + 768 + 896)   # head (scalars); chain (r, stats, dz, da); wgrad
-BYTES_ATTN_BWD = 3 * 128 + 2 * 256             # xu, xp, da (bf16 rows) in; dxu, dxp (fp32) out
+BYTES_ATTN_BWD = 3 * 128 + 2 * 128             # xu, xp, da (bf16 rows) in; dxu, dxp (bf16 rows) out
 
 
 def peaks():
@@ -656,16 +656,18 @@ def stage_roofline(args, model, batch, users, items, B, precision, table_mode, d
     mf = torch.empty(N, device=dev)
     xu = torch.empty(N, 64, device=dev)
     xp = torch.empty(N, 64, device=dev)
-    ypm = torch.empty(N, 64, device=dev)
-    yum = torch.empty(N, 64, device=dev)
+    row_dt = torch.bfloat16 if precision == "bf16" else torch.float32     # per-sample row arrays: the format the step uses
+    ypm = torch.empty(N, 64, device=dev, dtype=row_dt)
+    yum = torch.empty(N, 64, device=dev, dtype=row_dt)
     adam = _lib.AdamCfg()
     adam.lr, adam.beta1, adam.beta2, adam.eps, adam.weight_decay, adam.step = 1e-3, 0.9, 0.999, 1e-8, 1e-5, 7
     ews_bytes = int(lib.ncf_emb_bwd_workspace_bytes(N))
     ews = torch.empty(ews_bytes, dtype=torch.uint8, device=dev)
     dmf = torch.randn(N, device=dev) * 1e-6
-    dx = torch.randn(N, 64, device=dev) * 1e-6
+    dx = (torch.randn(N, 64, device=dev) * 1e-6).to(row_dt)
 
     k1_fn = lib.ncf_gather_ln_gmf_fwd_bf16 if precision == "bf16" else lib.ncf_gather_ln_gmf_fwd    # the variant the step runs
+    k6_fn = lib.ncf_emb_bwd_adam_both_bf16 if precision == "bf16" else lib.ncf_emb_bwd_adam_both   # (bf16 row arrays: the fp32-sized buffers are large enough)
 
     def k1():
         _lib.check(k1_fn(C.byref(tabs), _lib.ptr(flat), _lib.ptr(u), _lib.ptr(it), N, None, None,
@@ -689,7 +691,7 @@ def stage_roofline(args, model, batch, users, items, B, precision, table_mode, d
 
     def k6():
         adam.emb_mode = _lib.EMB_ADAM_SPARSE
-        _lib.check(lib.ncf_emb_bwd_adam_both(C.byref(adam), C.byref(tabs), _lib.ptr(flat), _lib.ptr(dgrad), _lib.ptr(u),
+        _lib.check(k6_fn(C.byref(adam), C.byref(tabs), _lib.ptr(flat), _lib.ptr(dgrad), _lib.ptr(u),
                                              _lib.ptr(it), N, _lib.ptr(dmf), _lib.ptr(dx), _lib.ptr(dx), _lib.ptr(ypm),
                                              _lib.ptr(yum), _lib.ptr(ews), ews_bytes, sptr))
 

@@ -220,11 +220,13 @@ NCF_API int ncf_gather_ln_gmf_fwd(const ncf_tables* tables, const float* dense,
                           void* stream);
 
 /* The same kernel writing xu / xp as bf16 rows [N,64] (128 B per row): the form ncf_forward hands to the fused
- * tcgen05 attention block (precision NCF_BF16_TC, S = 5), which would round them to bf16 anyway. */
+ * tcgen05 attention block (precision NCF_BF16_TC, S = 5), which would round them to bf16 anyway.  The saved
+ * mf_norm rows (y_item_mf / y_user_mf, optional) are bf16 rows too in this variant: only
+ * ncf_emb_bwd_adam_both_bf16 reads them, and it sums per id in fp32. */
 NCF_API int ncf_gather_ln_gmf_fwd_bf16(const ncf_tables* tables, const float* dense,
                                const int64_t* user_ids, const int64_t* item_ids, int64_t N,
                                const int64_t* hour, const float* tmod,
-                               float* mf_pred, void* xu_bf16, void* xp_bf16, float* y_item_mf, float* y_user_mf,
+                               float* mf_pred, void* xu_bf16, void* xp_bf16, void* y_item_mf_bf16, void* y_user_mf_bf16,
                                void* stream);
 
 /* get_user_embeddings / get_product_embeddings rows (architecture.py:383-407): LN'd rows of one
@@ -252,6 +254,15 @@ NCF_API int ncf_emb_bwd_adam_both(const ncf_adam_cfg* adam, const ncf_tables* ta
                           float* dense_grad, const int64_t* user_ids, const int64_t* item_ids, int64_t N,
                           const float* d_mf_pred, const float* d_xu, const float* d_xp, const float* y_item_mf,
                           const float* y_user_mf, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* The same with the four per-sample row arrays as bf16 rows [N,64] (what ncf_backward runs with precision
+ * NCF_BF16_TC and S = 5: rows written by ncf_gather_ln_gmf_fwd_bf16 and by the fused attention backward); the
+ * per-id sums, the LayerNorm backward and Adam stay fp32.  trainer.py:284-285 (loss.backward + optimizer.step). */
+NCF_API int ncf_emb_bwd_adam_both_bf16(const ncf_adam_cfg* adam, const ncf_tables* tables, const float* dense,
+                          float* dense_grad, const int64_t* user_ids, const int64_t* item_ids, int64_t N,
+                          const float* d_mf_pred, const void* d_xu_bf16, const void* d_xp_bf16,
+                          const void* y_item_mf_bf16, const void* y_user_mf_bf16, void* workspace,
+                          int64_t workspace_bytes, void* stream);
 
 /* the "every untouched row" half of NCF_EMB_ADAM_DENSE_EQUIV; clears tables->touched. */
 NCF_API int ncf_emb_adam_sweep(const ncf_adam_cfg* adam, const ncf_tables* tables, void* stream);

@@ -120,6 +120,8 @@ _SIGS = {
                                    _I64, _P]),
     "ncf_emb_bwd_adam_both": (C.c_int, [C.POINTER(AdamCfg), C.POINTER(Tables), _P, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _P,
                                         _I64, _P]),
+    "ncf_emb_bwd_adam_both_bf16": (C.c_int, [C.POINTER(AdamCfg), C.POINTER(Tables), _P, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _P,
+                                        _I64, _P]),
     "ncf_emb_adam_sweep": (C.c_int, [C.POINTER(AdamCfg), C.POINTER(Tables), _P]),
     "ncf_temporal_fwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _P, _P]),
     "ncf_temporal_tables": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),

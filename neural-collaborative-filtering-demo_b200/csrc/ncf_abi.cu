@@ -135,7 +135,7 @@ static int backward_impl(const ncf_run_cfg* cfg, const ncf_adam_cfg* adam, const
   if (adam->emb_mode != NCF_EMB_NONE) {
     if (sorted) NCF_CUDA(cudaStreamWaitEvent(st, sorted, 0));
     NCF_TRY(emb_bwd_both(adam, T, dense, dense_grad, user_ids, item_ids, N, w.d_mf, w.dxu, w.dxp, w.y_pmf, w.y_umf, w.emb, w.emb_bytes, st,
-                         sorted != nullptr, preswept, sorted ? aux_ctx()->stream : nullptr));
+                         sorted != nullptr, preswept, sorted ? aux_ctx()->stream : nullptr, tower_bf16_rows(*cfg)));
     if (adam->emb_mode == NCF_EMB_ADAM_DENSE_EQUIV && !preswept) NCF_TRY(ncf_emb_adam_sweep(adam, T, stream));
   }
   return NCF_OK;

@@ -564,12 +564,18 @@ __global__ void __launch_bounds__(AT_THREADS, 1) attn_tc_bwd_kernel(AttnBwdArgs 
       tmem_ld16(tmem + lane_addr + T_DXU + h * 16, t);
       if (live) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) st4(A.dxu + n * 64 + h * 16 + 4 * j, make_float4(t[4 * j], t[4 * j + 1], t[4 * j + 2], t[4 * j + 3]));
+        for (int j = 0; j < 2; ++j)      // bf16 rows: K6 sums them per id in fp32
+          *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(A.dxu) + n * 64 + h * 16 + 8 * j) =
+              make_uint4(pack_bf16(t[8 * j], t[8 * j + 1]), pack_bf16(t[8 * j + 2], t[8 * j + 3]), pack_bf16(t[8 * j + 4], t[8 * j + 5]),
+                         pack_bf16(t[8 * j + 6], t[8 * j + 7]));
       }
       tmem_ld16(tmem + lane_addr + T_DXP + h * 16, t);
       if (live) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) st4(A.dxp + n * 64 + h * 16 + 4 * j, make_float4(t[4 * j], t[4 * j + 1], t[4 * j + 2], t[4 * j + 3]));
+        for (int j = 0; j < 2; ++j)      // bf16 rows: K6 sums them per id in fp32
+          *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(A.dxp) + n * 64 + h * 16 + 8 * j) =
+              make_uint4(pack_bf16(t[8 * j], t[8 * j + 1]), pack_bf16(t[8 * j + 2], t[8 * j + 3]), pack_bf16(t[8 * j + 4], t[8 * j + 5]),
+                         pack_bf16(t[8 * j + 6], t[8 * j + 7]));
       }
     }
     fence_before_sync();

@@ -195,6 +195,15 @@ __device__ __forceinline__ void st_row4(float* base, int64_t n, int c, float4 v,
     *reinterpret_cast<float4*>(base + n * 64 + c) = v;
   }
 }
+// four columns c..c+3 of row n of a [*,64] row array held as fp32 or (bf16_rows) as bf16 (see st_row4)
+__device__ __forceinline__ float4 ld_row4(const float* base, int64_t n, int c, bool bf16_rows) {
+  if (bf16_rows) {
+    const uint2 q = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(base) + n * 64 + c));
+    return make_float4(__uint_as_float(q.x << 16), __uint_as_float(q.x & 0xffff0000u), __uint_as_float(q.y << 16),
+                       __uint_as_float(q.y & 0xffff0000u));
+  }
+  return __ldg(reinterpret_cast<const float4*>(base + n * 64 + c));
+}
 __device__ __forceinline__ float4 f4_fma(float a, float4 x, float4 y) {
   return make_float4(fmaf(a, x.x, y.x), fmaf(a, x.y, y.y), fmaf(a, x.z, y.z), fmaf(a, x.w, y.w));
 }

@@ -8,6 +8,8 @@
 
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "ncf_tower.cuh"
 
 namespace ncf {
@@ -166,7 +168,7 @@ __global__ void __launch_bounds__(K1_THREADS) gather_ln_gmf_fwd_kernel(
           if (lane == 0) mf_pred[n] = dot + b_out;
           st_row4(half ? xp : xu, n, 4 * l16, y_ml, bf16_rows);
           float* ykeep = half ? y_item_mf : y_user_mf;                      // mf_norm rows kept for the backward
-          if (ykeep) st4(ykeep + n * D + 4 * l16, y_mf);
+          if (ykeep) st_row4(ykeep, n, 4 * l16, y_mf, bf16_rows);
         }
       }
     }
@@ -279,6 +281,7 @@ struct EmbBwdArgs {
   const uint32_t* other_sorted;   // optional: other side's id per SORTED position (pre-gathered, coalesced)
   const float* dmf_sorted;        // optional: d_mf_pred per sorted position
   const float* d_x;               // [N,64] gradient wrt this side's LN'd MLP row
+  int32_t rows_bf16;              // the per-sample [N,64] row arrays (d_x, other_y, own_y) hold bf16 rows (bf16 towers, S = 5)
   const float* dense;
   float* dense_grad;
   float* acc_buf;                 // [N][2][64] upstream sum of the run piece that starts at each sorted position
@@ -316,7 +319,7 @@ __device__ __forceinline__ void block_flush(float* s_red, float4 val, float* dst
 // is a [N,64] row (or the scalar d_mf) indexed by the sample row, so a position costs three shuffles (row, d_mf, id),
 // one 128-bit load per half (two for the side that also forms d mf_output.weight) and
 // the multiply-adds - none of the source-selection logic of the general kernel below.
-template <bool WMF>
+template <bool WMF, bool BF>
 __global__ void __launch_bounds__(EB_THREADS, 3) emb_bwd_phase1_lean_kernel(EmbBwdArgs A) {
   __shared__ float s_red[(EB_THREADS / 32) * 32 * 4];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = EB_THREADS / 32;
@@ -324,9 +327,21 @@ __global__ void __launch_bounds__(EB_THREADS, 3) emb_bwd_phase1_lean_kernel(EmbB
   const int64_t nchunks = (A.N + EB_CHUNK - 1) / EB_CHUNK;
   const int64_t gw = (int64_t)blockIdx.x * nwarps + warp, gstride = (int64_t)gridDim.x * nwarps;
   const float4 w_out = ldg4(A.dense + NCF_OFF(NCF_P_MF_OUT_W) + 4 * l16);
-  const float* src = (half ? A.d_x : A.other_y) + 4 * l16;
-  const float* own = A.own_y + 4 * l16;
+  const float* src = half ? A.d_x : A.other_y;
+  const float* own = A.own_y;
   float4 dwout = make_float4(0, 0, 0, 0);
+  // positions in flight per lane: bf16 rows are 8 B per lane, so twice as many keep the same bytes in flight
+  constexpr int U = BF ? 8 : 4;
+  using Raw = typename std::conditional<BF, uint2, float4>::type;
+  auto load = [&](const float* base, int64_t row) -> Raw {
+    if constexpr (BF) return __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(base) + row * 64 + 4 * l16));
+    else return __ldg(reinterpret_cast<const float4*>(base + row * 64 + 4 * l16));
+  };
+  auto widen = [](Raw q) -> float4 {
+    if constexpr (BF) return make_float4(__uint_as_float(q.x << 16), __uint_as_float(q.x & 0xffff0000u), __uint_as_float(q.y << 16),
+                                         __uint_as_float(q.y & 0xffff0000u));
+    else return q;
+  };
 
   for (int64_t c = gw; c < nchunks; c += gstride) {
     const int64_t p0 = c * EB_CHUNK;
@@ -337,21 +352,21 @@ __global__ void __launch_bounds__(EB_THREADS, 3) emb_bwd_phase1_lean_kernel(EmbB
     float4 acc = make_float4(0, 0, 0, 0);
     int piece_first = 0;
     uint32_t id_prev = __shfl_sync(0xffffffffu, my_id, 0);
-    for (int k0 = 0; k0 < cnt; k0 += 4) {
-      float4 x[4], sf[4];
-      float dmf[4];
-      uint32_t idk[4];
+    for (int k0 = 0; k0 < cnt; k0 += U) {
+      Raw x[U], sf[U];
+      float dmf[U];
+      uint32_t idk[U];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < U; ++u) {
         const int kk = min(k0 + u, cnt - 1);
-        const int64_t off = (int64_t)__shfl_sync(0xffffffffu, my_row, kk) * D;
+        const int64_t srow = __shfl_sync(0xffffffffu, my_row, kk);
         dmf[u] = __shfl_sync(0xffffffffu, my_dmf, kk);
         idk[u] = __shfl_sync(0xffffffffu, my_id, kk);
-        x[u] = ldg4(src + off);
-        if (WMF) sf[u] = half ? make_float4(0, 0, 0, 0) : ldg4(own + off);
+        x[u] = load(src, srow);
+        if (WMF) sf[u] = half ? Raw{} : load(own, srow);
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < U; ++u) {
         if (k0 + u < cnt) {                                   // warp-uniform
           if (idk[u] != id_prev) {                            // a new run starts: flush the piece
             st4(A.acc_buf + ((p0 + piece_first) * 2 + half) * D + 4 * l16, acc);
@@ -359,12 +374,13 @@ __global__ void __launch_bounds__(EB_THREADS, 3) emb_bwd_phase1_lean_kernel(EmbB
             piece_first = k0 + u;
             id_prev = idk[u];
           }
+          const float4 xv = widen(x[u]);
           if (half) {
-            acc = f4_add(acc, x[u]);
+            acc = f4_add(acc, xv);
           } else {
-            const float4 t = make_float4(dmf[u] * x[u].x, dmf[u] * x[u].y, dmf[u] * x[u].z, dmf[u] * x[u].w);
+            const float4 t = make_float4(dmf[u] * xv.x, dmf[u] * xv.y, dmf[u] * xv.z, dmf[u] * xv.w);
             acc = f4_add(acc, f4_mul(t, w_out));
-            if (WMF) dwout = f4_add(dwout, f4_mul(t, sf[u]));
+            if (WMF) dwout = f4_add(dwout, f4_mul(t, widen(sf[u])));
           }
         }
       }
@@ -428,14 +444,15 @@ __global__ void __launch_bounds__(EB_THREADS, 3) emb_bwd_phase1_kernel(EmbBwdArg
         const int64_t oid = __shfl_sync(0xffffffffu, my_other, kk);
         dmf[u] = __shfl_sync(0xffffffffu, my_dmf, kk);
         idk[u] = __shfl_sync(0xffffffffu, my_id, kk);
-        const float* src = A.upstream ? A.upstream + (int64_t)row * 2 * D + half * D
-                           : half ? A.d_x + (int64_t)row * D
-                           : A.other_rows ? A.other_rows + oid * 2 * D
-                                  : (A.other_y ? A.other_y + (int64_t)row * D : A.other_mf + oid * D);
-        x[u] = ldg4(src + 4 * l16);
+        const bool bf = A.rows_bf16 != 0;
+        if (A.upstream) x[u] = ldg4(A.upstream + (int64_t)row * 2 * D + half * D + 4 * l16);
+        else if (half) x[u] = ld_row4(A.d_x, row, 4 * l16, bf);
+        else if (A.other_rows) x[u] = ldg4(A.other_rows + oid * 2 * D + 4 * l16);
+        else if (A.other_y) x[u] = ld_row4(A.other_y, row, 4 * l16, bf);
+        else x[u] = ldg4(A.other_mf + oid * D + 4 * l16);
         sf[u] = !wmf ? make_float4(0, 0, 0, 0)                    // own MF row (d mf_output.weight): saved LN'd row or table row
                 : A.own_rows ? ldg4(A.own_rows + __shfl_sync(0xffffffffu, my_own, kk) * 2 * D + 4 * l16)
-                : A.own_y ? ldg4(A.own_y + (int64_t)row * D + 4 * l16)
+                : A.own_y ? ld_row4(A.own_y, row, 4 * l16, bf)
                           : ld4(A.w[0] + (int64_t)(idk[u] - A.id_off) * D + 4 * l16);
       }
 #pragma unroll
@@ -763,10 +780,11 @@ extern "C" int ncf_gather_ln_gmf_fwd(const ncf_tables* T, const float* dense, co
 
 extern "C" int ncf_gather_ln_gmf_fwd_bf16(const ncf_tables* T, const float* dense, const int64_t* user_ids,
                                           const int64_t* item_ids, int64_t N, const int64_t* hour, const float* tmod,
-                                          float* mf_pred, void* xu_bf16, void* xp_bf16, float* y_item_mf, float* y_user_mf,
-                                          void* stream) {
+                                          float* mf_pred, void* xu_bf16, void* xp_bf16, void* y_item_mf_bf16,
+                                          void* y_user_mf_bf16, void* stream) {
   return gather_ln_gmf_fwd_rows(true, T, dense, user_ids, item_ids, N, hour, tmod, mf_pred, static_cast<float*>(xu_bf16),
-                                static_cast<float*>(xp_bf16), y_item_mf, y_user_mf, stream);
+                                static_cast<float*>(xp_bf16), static_cast<float*>(y_item_mf_bf16),
+                                static_cast<float*>(y_user_mf_bf16), stream);
 }
 
 extern "C" int ncf_gather_ln(const ncf_tables* T, const float* dense, int32_t side, const int64_t* ids, int64_t n,
@@ -875,6 +893,7 @@ static int run_emb_bwd(const ncf_adam_cfg* adam, const ncf_tables* T, const floa
   A.perm = w.vals_out;
   A.d_mf_pred = d_mf_pred;
   A.d_x = d_x;
+  A.rows_bf16 = 0;
   A.dense = dense;
   A.dense_grad = dense_grad;
   A.acc_buf = w.acc_buf;
@@ -950,7 +969,7 @@ int emb_sort_both(const ncf_tables* T, const int64_t* user_ids, const int64_t* i
 int emb_bwd_both(const ncf_adam_cfg* adam, const ncf_tables* T, const float* dense, float* dense_grad,
                  const int64_t* user_ids, const int64_t* item_ids, int64_t N, const float* d_mf_pred, const float* dxu,
                  const float* dxp, const float* y_item_mf, const float* y_user_mf, void* workspace, int64_t workspace_bytes,
-                 cudaStream_t st, bool presorted, bool preswept, cudaStream_t side_stream) {
+                 cudaStream_t st, bool presorted, bool preswept, cudaStream_t side_stream, bool rows_bf16) {
   if (N == 0 || adam->emb_mode == NCF_EMB_NONE) return NCF_OK;
   NCF_REQUIRE(2 * N < ((int64_t)1 << 31), "emb_bwd: N too large");
   NCF_REQUIRE(T->rows_user + T->rows_item < ((int64_t)1 << 32), "emb_bwd: too many table rows for 32-bit keys");
@@ -1025,6 +1044,7 @@ int emb_bwd_both(const ncf_adam_cfg* adam, const ncf_tables* T, const float* den
     A.other_sorted = w.other_sorted + (side ? N : 0);
     A.dmf_sorted = w.dmf_sorted + (side ? N : 0);
     A.d_x = side ? dxp : dxu;
+    A.rows_bf16 = rows_bf16 ? 1 : 0;
     A.dense = dense;
     A.dense_grad = dense_grad;
     A.acc_buf = (two_streams && side == 1) ? w.acc_buf2 : w.acc_buf;
@@ -1035,8 +1055,13 @@ int emb_bwd_both(const ncf_adam_cfg* adam, const ncf_tables* T, const float* den
     A.adam = adam_scalars(*adam);
     A.chunk_counter = w.counters + side;
     if (lean) {      // the usual case
-      if (A.accumulate_wmf) emb_bwd_phase1_lean_kernel<true><<<grid, EB_THREADS, 0, sst>>>(A);
-      else emb_bwd_phase1_lean_kernel<false><<<grid, EB_THREADS, 0, sst>>>(A);
+      if (A.accumulate_wmf) {
+        if (rows_bf16) emb_bwd_phase1_lean_kernel<true, true><<<grid, EB_THREADS, 0, sst>>>(A);
+        else emb_bwd_phase1_lean_kernel<true, false><<<grid, EB_THREADS, 0, sst>>>(A);
+      } else {
+        if (rows_bf16) emb_bwd_phase1_lean_kernel<false, true><<<grid, EB_THREADS, 0, sst>>>(A);
+        else emb_bwd_phase1_lean_kernel<false, false><<<grid, EB_THREADS, 0, sst>>>(A);
+      }
     } else {
       emb_bwd_phase1_kernel<<<grid, EB_THREADS, 0, sst>>>(A);
     }
@@ -1059,7 +1084,19 @@ extern "C" int ncf_emb_bwd_adam_both(const ncf_adam_cfg* adam, const ncf_tables*
   NCF_REQUIRE(adam && T && dense && user_ids && item_ids && d_mf_pred && d_xu && d_xp && y_item_mf && workspace,
               "emb_bwd_adam_both: null argument");
   return emb_bwd_both(adam, T, dense, dense_grad, user_ids, item_ids, N, d_mf_pred, d_xu, d_xp, y_item_mf, y_user_mf,
-                      workspace, workspace_bytes, (cudaStream_t)stream, false, false, ncf::aux_ctx()->stream);
+                      workspace, workspace_bytes, (cudaStream_t)stream, false, false, ncf::aux_ctx()->stream, false);
+}
+
+extern "C" int ncf_emb_bwd_adam_both_bf16(const ncf_adam_cfg* adam, const ncf_tables* T, const float* dense, float* dense_grad,
+                                          const int64_t* user_ids, const int64_t* item_ids, int64_t N, const float* d_mf_pred,
+                                          const void* d_xu_bf16, const void* d_xp_bf16, const void* y_item_mf_bf16,
+                                          const void* y_user_mf_bf16, void* workspace, int64_t workspace_bytes, void* stream) {
+  NCF_REQUIRE(adam && T && dense && user_ids && item_ids && d_mf_pred && d_xu_bf16 && d_xp_bf16 && y_item_mf_bf16 &&
+                  y_user_mf_bf16 && workspace, "emb_bwd_adam_both_bf16: null argument");
+  return emb_bwd_both(adam, T, dense, dense_grad, user_ids, item_ids, N, d_mf_pred, static_cast<const float*>(d_xu_bf16),
+                      static_cast<const float*>(d_xp_bf16), static_cast<const float*>(y_item_mf_bf16),
+                      static_cast<const float*>(y_user_mf_bf16), workspace, workspace_bytes, (cudaStream_t)stream, false, false,
+                      ncf::aux_ctx()->stream, true);
 }
 
 extern "C" int ncf_emb_bwd_adam(const ncf_adam_cfg* adam, const ncf_tables* T, const float* dense, float* dense_grad,
@@ -1166,7 +1203,7 @@ int shard_route(const int64_t* user_ids, const int64_t* item_ids, int64_t N, int
 int shard_requester_grads(const float* dense, float* dense_grad, const float* rows_u, const float* rows_i, const int64_t* pos_u,
                           const int64_t* pos_i, int64_t N, const float* d_mf, const float* dxu, const float* dxp,
                           const void* route_ws, float* gu, float* gi, void* emb_ws, int64_t emb_ws_bytes, cudaStream_t st,
-                          const ncf_shard_plan* plan, const int64_t* local_ids) {
+                          const ncf_shard_plan* plan, const int64_t* local_ids, bool rows_bf16) {
   if (N == 0) return NCF_OK;
   RouteWs r = carve_route_ws(const_cast<void*>(route_ws), N);
   EmbWs w = carve_emb_ws(emb_ws, N);
@@ -1194,6 +1231,7 @@ int shard_requester_grads(const float* dense, float* dense_grad, const float* ro
     A.perm = r.vals_out + (side ? N : 0);
     A.d_mf_pred = d_mf;
     A.d_x = side ? dxp : dxu;
+    A.rows_bf16 = rows_bf16 ? 1 : 0;
     A.other_rows = side ? rows_u : rows_i;
     A.other_pos = side ? pos_u : pos_i;
     A.own_rows = side ? rows_i : rows_u;

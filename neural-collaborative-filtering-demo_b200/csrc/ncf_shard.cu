@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(256) pack_grads_kernel(const float* __restrict
                                                          const float* __restrict__ dense, const float* __restrict__ d_mf,
                                                          const float* __restrict__ dxu, const float* __restrict__ dxp,
                                                          int64_t N, float* __restrict__ gu, float* __restrict__ gi,
-                                                         float* __restrict__ dense_grad) {
+                                                         float* __restrict__ dense_grad, bool rows_bf16) {
   __shared__ float s_red[8][D];
   const int lane = threadIdx.x & 31, warpi = threadIdx.x >> 5, half = lane >> 4, l16 = lane & 15;
   const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + warpi;
@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(256) pack_grads_kernel(const float* __restrict
       const float g = d_mf[j];
       const float4 t = make_float4(g * y_other.x, g * y_other.y, g * y_other.z, g * y_other.w);
       a_mf = f4_add(a_mf, f4_mul(t, w_out));
-      a_ml = f4_add(a_ml, ldg4(dx + j * D + 4 * l16));
+      a_ml = f4_add(a_ml, ld_row4(dx, j, 4 * l16, rows_bf16));
       if (half == 0) dw = f4_add(dw, f4_mul(t, y_mine));
     }
     st4(dst + p * 2 * D + 4 * l16, a_mf);
@@ -312,10 +312,10 @@ static int shard_backward_impl(const ncf_run_cfg* cfg, const float* dense, float
   NCF_TRY(tower_f32_backward(*cfg, dense, dense_grad, N, grad_out, w, st));
   if (route_ws)     // ids routed by ncf_shard_route: samples that share a row are scattered -> sorted segment sum
     return shard_requester_grads(dense, dense_grad, rows_u, rows_i, pos_u, pos_i, N, w.d_mf, w.dxu, w.dxp, route_ws, grad_rows_u,
-                                 grad_rows_i, w.emb, w.emb_bytes, st, plan, local_ids);
+                                 grad_rows_i, w.emb, w.emb_bytes, st, plan, local_ids, tower_bf16_rows(*cfg));
   const int grid = (int)std::min<int64_t>((N + 7) / 8, (int64_t)num_sms() * 8);
   pack_grads_kernel<<<grid, 256, 0, st>>>(rows_u, rows_i, pos_u, pos_i, dense, w.d_mf, w.dxu, w.dxp, N, grad_rows_u,
-                                          grad_rows_i, dense_grad);
+                                          grad_rows_i, dense_grad, tower_bf16_rows(*cfg));
   NCF_LAUNCH_CHECK();
   return NCF_OK;
 }

@@ -37,6 +37,8 @@ int tower_f32_backward(const ncf_run_cfg& cfg, const float* dense, float* dense_
 // True when the attention block runs as the fused tcgen05 kernels (bf16 towers, S = 5): then its row-vector
 // interfaces w.xu, w.xp (from K1 / the sharded requester) and da = w.g64a (from the MLP backward) hold bf16
 // [N,64] rows instead of fp32 - the same values the operand tiles would be rounded to anyway, half the traffic.
+// So do the rows that only the embedding backward reads: the LayerNorm-ed MF rows K1 saves (w.y_pmf, w.y_umf) and the
+// attention backward's dxu / dxp (summed per id in fp32 by K6).
 bool tower_bf16_rows(const ncf_run_cfg& cfg);
 // K1 with selectable row format (ncf_embed.cu); the C-ABI export ncf_gather_ln_gmf_fwd is the fp32 case
 int gather_ln_gmf_fwd_rows(bool bf16_rows, const ncf_tables* T, const float* dense, const int64_t* user_ids,
@@ -74,7 +76,8 @@ int64_t attn_tc_partial_floats();
 int emb_bwd_both(const ncf_adam_cfg* adam, const ncf_tables* T, const float* dense, float* dense_grad,
                  const int64_t* user_ids, const int64_t* item_ids, int64_t N, const float* d_mf_pred, const float* dxu,
                  const float* dxp, const float* y_item_mf, const float* y_user_mf, void* workspace, int64_t workspace_bytes,
-                 cudaStream_t st, bool presorted = false, bool preswept = false, cudaStream_t side_stream = nullptr);
+                 cudaStream_t st, bool presorted = false, bool preswept = false, cudaStream_t side_stream = nullptr,
+                 bool rows_bf16 = false);
 // ncf_set_aux_stream (ncf_abi.cu): per-device auxiliary stream (null = none) + the events that order it
 constexpr int NCF_MAX_DEVICES = 64;
 struct AuxCtx {
@@ -97,7 +100,7 @@ int emb_sort_both(const ncf_tables* T, const int64_t* user_ids, const int64_t* i
 int shard_requester_grads(const float* dense, float* dense_grad, const float* rows_u, const float* rows_i, const int64_t* pos_u,
                           const int64_t* pos_i, int64_t N, const float* d_mf, const float* dxu, const float* dxp,
                           const void* route_ws, float* gu, float* gi, void* emb_ws, int64_t emb_ws_bytes, cudaStream_t st,
-                          const ncf_shard_plan* plan = nullptr, const int64_t* local_ids = nullptr);
+                          const ncf_shard_plan* plan = nullptr, const int64_t* local_ids = nullptr, bool rows_bf16 = false);
 // fused backward of one projection: dX = dY.W and dW += dY^T.X, db += colsum(dY) (which: 0 = 64 cols, 1 = 128)
 int tc_proj_backward(int which, const float* dY, const float* X, const float* W, float* dX, float* dW, float* db, int64_t N,
                      cudaStream_t st);
