@@ -851,59 +851,90 @@ def profile_phases(eng, dev_batches, nb, steps):
 
 
 def verify_sharded(world, rank, dev, steps=3):
-    """The REAL NCCL path against the single-GPU engine: 3 steps of ShardedNCFEngine over all_to_all_single / all_reduce,
-    fp32, dropout on; rank 0 runs NCFTrainEngine on the all-gathered batch with the SAME tables.  Loss within 2e-6, tables
-    within the bound the emulated-cluster test uses (tests/test_sharding.py)."""
+    """The REAL NCCL / peer-memory path against the single-GPU engine: `steps` steps of ShardedNCFEngine, fp32, no dropout
+    (per-rank Philox streams differ from one global stream); rank 0 runs NCFTrainEngine on the all-gathered batch with the
+    SAME tables.  Two passes:
+      sharp   Adam eps = 1e-4, far above every gradient of this problem (1e-7 .. 1e-5): the update is lr * m / (sqrt(v) + eps)
+              ~ linear in the gradient, so rounding noise is NOT amplified and a lost, doubled or stale row (any logic error of
+              the exchange: the MF and MLP halves of a row travel together) is off by >= 1e-5.  Asserted: loss 2e-6 every step;
+              the two MF tables equal to 1e-6 EVERYWHERE; the two MLP tables to 5e-4 (the share of their rows that is off by more
+              than 1e-7 is reported).  The MLP tables get the loose bound because their gradient passes three ReLUs: about once per
+              step some pre-activation of the 9 M in a batch lies within rounding noise of 0 (fp32 atomics order the dense-gradient
+              sums differently from run to run, in BOTH engines), its relu' flips, and that ONE interaction's user row and five
+              item rows move by a fraction of an update - then whatever those rows touch in the next steps (5,003 items, every one
+              in ~4 interactions of a step: after 6 steps half of the rows have moved).  Measured with
+              tools/stress_pair.py: two single-GPU engines on one GPU differ the same way on the same interactions, and a 1e-7
+              relative perturbation of the dense weights reproduces it; the forward value (ReLU is continuous) and with it the
+              loss and the MF-side gradients do not move;
+      stock   Adam eps = 1e-8 (the reference's): loss within 2e-6 every step.  Its tables are reported, not asserted: Adam turns
+              such a flip into whole +-lr steps."""
     import torch
     import torch.distributed as dist
     import ncf_b200
     from ncf_b200.sharding import ShardedNCFEngine
     U, I, Bv = 20011, 5003, 2048
-    torch.manual_seed(99)
-    tables = [(torch.rand(r, 64) * 2 - 1) * (1.0 / r) ** 0.5 for r in (U, I, U, I)]
-    model = build_model(1, 1, dev, "fp32")
-    model.dropout = 0.0            # per-rank Philox streams differ from one global stream: parity is checked without dropout
-    eng = ShardedNCFEngine(model, U, I, lr=1e-3, weight_decay=1e-5, table_mode="fused_dense_equiv", init_tables=tables)
-    batches = make_batches(U, I, Bv, steps, 555 + rank, device=dev)
-    single = None
-    if rank == 0:
-        ref_model = ncf_b200.AdvancedNCF(U, I, 5, 24, dropout=0.0)
-        sd = ref_model.state_dict()
-        for k, v in model.state_dict().items():
-            if "embedding_collection" not in k:
-                sd[k] = v.detach().cpu().clone()
-        for k, t in zip(("mf_embedding_collection.embedding_bags.user_id.weight", "mf_embedding_collection.embedding_bags.product_id.weight",
-                         "mlp_embedding_collection.embedding_bags.user_id.weight", "mlp_embedding_collection.embedding_bags.product_id.weight"), tables):
-            sd[k] = t.clone()
-        ref_model.load_state_dict(sd)
-        ref_model = ref_model.to(dev).train()
-        single = ncf_b200.NCFTrainEngine(ref_model, lr=1e-3, weight_decay=1e-5, table_mode="fused_dense_equiv")
-    worst_loss = 0.0
-    for s in range(steps):
-        u, i, t = batches[s]
-        loss = float(eng.train_step(u, i, t).item())
-        parts = [[torch.empty_like(x) for _ in range(world)] for x in (u, i, t)]
-        for p, x in zip(parts, (u, i, t)):
-            dist.all_gather(p, x)
+    KEYS = ("mf_embedding_collection.embedding_bags.user_id.weight", "mf_embedding_collection.embedding_bags.product_id.weight",
+            "mlp_embedding_collection.embedding_bags.user_id.weight", "mlp_embedding_collection.embedding_bags.product_id.weight")
+
+    def one_pass(eps):
+        torch.manual_seed(99)
+        tables = [(torch.rand(r, 64) * 2 - 1) * (1.0 / r) ** 0.5 for r in (U, I, U, I)]
+        model = build_model(1, 1, dev, "fp32")
+        model.dropout = 0.0
+        eng = ShardedNCFEngine(model, U, I, lr=1e-3, eps=eps, weight_decay=1e-5, table_mode="fused_dense_equiv", init_tables=tables)
+        batches = make_batches(U, I, Bv, steps, 555 + rank, device=dev)
+        single = None
         if rank == 0:
-            ref = float(single.train_step(torch.cat(parts[0]), torch.cat(parts[1]), torch.cat(parts[2])).item())
-            worst_loss = max(worst_loss, abs(loss - ref))
-    got = eng.gather_tables()
+            ref_model = ncf_b200.AdvancedNCF(U, I, 5, 24, dropout=0.0)
+            sd = ref_model.state_dict()
+            for k, v in model.state_dict().items():
+                if "embedding_collection" not in k:
+                    sd[k] = v.detach().cpu().clone()
+            for k, t in zip(KEYS, tables):
+                sd[k] = t.clone()
+            ref_model.load_state_dict(sd)
+            ref_model = ref_model.to(dev).train()
+            single = ncf_b200.NCFTrainEngine(ref_model, lr=1e-3, eps=eps, weight_decay=1e-5, table_mode="fused_dense_equiv")
+        worst_loss = 0.0
+        for s in range(steps):
+            u, i, t = batches[s]
+            loss = float(eng.train_step(u, i, t).item())
+            parts = [[torch.empty_like(x) for _ in range(world)] for x in (u, i, t)]
+            for p, x in zip(parts, (u, i, t)):
+                dist.all_gather(p, x)
+            if rank == 0:
+                ref = float(single.train_step(torch.cat(parts[0]), torch.cat(parts[1]), torch.cat(parts[2])).item())
+                worst_loss = max(worst_loss, abs(loss - ref))
+        got = eng.gather_tables()
+        r = {"loss": worst_loss, "mf": 0.0, "mlp": 0.0, "mlp_rows_off": 0.0, "frac6": 0.0}
+        if rank == 0:
+            for k, (g, w) in enumerate(zip(got, single.model._table_params())):
+                d = (g - w.detach()).abs()
+                fam = "mf" if k < 2 else "mlp"
+                r[fam] = max(r[fam], float(d.max()))
+                r["frac6"] = max(r["frac6"], float((d > 8e-6).float().mean()))
+                if k >= 2:
+                    r["mlp_rows_off"] = max(r["mlp_rows_off"], float((d.max(dim=1).values > 1e-7).float().mean()))
+            single.close()
+        eng.close()
+        del eng
+        torch.cuda.empty_cache()
+        return r
+
+    sharp = one_pass(1e-4)
+    stock = one_pass(1e-8)
     ok, detail = True, None
     if rank == 0:
-        worst_w, frac = 0.0, 0.0
-        for g, w in zip(got, single.model._table_params()):
-            d = (g - w.detach()).abs()
-            worst_w = max(worst_w, float(d.max()))
-            frac = max(frac, float((d > 8e-6).float().mean()))
-        ok = worst_loss <= 2e-6 and worst_w < 1.5e-3 and frac < 3e-3
-        detail = {"steps": steps, "world": world, "max_abs_loss_diff": worst_loss, "max_abs_table_diff": worst_w,
-                  "frac_table_elements_off_by_more_than_8e-6": frac, "shape": f"{U} x {I}, {Bv} interactions per rank, fp32, dropout 0"}
-        single.close()
+        ok = sharp["loss"] <= 2e-6 and sharp["mf"] <= 1e-6 and sharp["mlp"] <= 5e-4 and stock["loss"] <= 2e-6
+        detail = {"steps": steps, "world": world, "shape": f"{U} x {I}, {Bv} interactions per rank, fp32, dropout 0",
+                  "adam_eps_1e-4": {"max_abs_loss_diff": sharp["loss"], "max_abs_diff_mf_tables": sharp["mf"],
+                                    "max_abs_diff_mlp_tables": sharp["mlp"], "frac_mlp_rows_off_by_more_than_1e-7": sharp["mlp_rows_off"],
+                                    "asserted": "loss 2e-6; MF tables 1e-6 everywhere; MLP tables 5e-4 (relu' flips of single "
+                                                "interactions under rounding noise, see bench.verify_sharded)"},
+                  "adam_eps_1e-8": {"max_abs_loss_diff": stock["loss"], "max_abs_table_diff": max(stock["mf"], stock["mlp"]),
+                                    "frac_table_elements_off_by_more_than_8e-6": stock["frac6"], "asserted": "loss 2e-6"}}
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.broadcast(flag, 0)
-    del eng
-    torch.cuda.empty_cache()
     return bool(flag.item()), detail
 
 

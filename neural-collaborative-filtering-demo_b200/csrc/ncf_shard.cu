@@ -221,12 +221,15 @@ extern "C" int ncf_ipc_open(const void* handle, int64_t offset, void** ptr_out) 
       *ptr_out = static_cast<char*>(g_ipc[i].base) + offset;
       return NCF_OK;
     }
-  NCF_REQUIRE(g_ipc_n < 256, "ipc_open: too many mappings");
+  int slot = -1;                              // a closed mapping's entry is reused
+  for (int i = 0; i < g_ipc_n && slot < 0; ++i)
+    if (g_ipc[i].refs == 0) slot = i;
+  NCF_REQUIRE(slot >= 0 || g_ipc_n < 256, "ipc_open: too many mappings");
   cudaIpcMemHandle_t h;
   memcpy(&h, handle, sizeof(h));
   void* base = nullptr;
   NCF_CUDA(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
-  IpcMapping& m = g_ipc[g_ipc_n++];
+  IpcMapping& m = g_ipc[slot >= 0 ? slot : g_ipc_n++];
   m.base = base;
   m.refs = 1;
   memcpy(m.handle, handle, sizeof(h));

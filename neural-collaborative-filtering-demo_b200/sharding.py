@@ -547,6 +547,20 @@ class ShardedNCFEngine:
             self.lib.ncf_ipc_close(C.c_void_p(p))
         self._mapped = []
 
+    def close(self):
+        """Unmap the peers' buffers (CUDA IPC).  Every rank closes its engine at the same point of the program: a peer
+        must not be inside a step that still reads this rank's tables."""
+        if getattr(self, "_mapped", None):
+            torch.cuda.synchronize(self.device)
+            self._close_peers()
+            self._peers = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001 - interpreter shutdown
+            pass
+
     def _peer_ptrs(self, r: int):
         if getattr(self, "_peer_engines", None) is not None:
             e = self._peer_engines[r]
