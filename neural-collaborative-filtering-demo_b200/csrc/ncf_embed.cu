@@ -1203,8 +1203,12 @@ int shard_route(const int64_t* user_ids, const int64_t* item_ids, int64_t N, int
 int shard_requester_grads(const float* dense, float* dense_grad, const float* rows_u, const float* rows_i, const int64_t* pos_u,
                           const int64_t* pos_i, int64_t N, const float* d_mf, const float* dxu, const float* dxp,
                           const void* route_ws, float* gu, float* gi, void* emb_ws, int64_t emb_ws_bytes, cudaStream_t st,
-                          const ncf_shard_plan* plan, const int64_t* local_ids, bool rows_bf16) {
+                          const ncf_shard_plan* plan, const int64_t* local_ids, bool rows_bf16, const float* y_item_mf,
+                          const float* y_user_mf) {
   if (N == 0) return NCF_OK;
+  // the forward kept both LayerNorm-ed MF rows per sample (ncf_shard_forward): phase 1 reads everything by sample row
+  static const bool lean_ok = !(getenv("NCF_SHARD_LEAN") && getenv("NCF_SHARD_LEAN")[0] == '0');     // A/B switch
+  const bool lean = lean_ok && y_item_mf && y_user_mf;
   RouteWs r = carve_route_ws(const_cast<void*>(route_ws), N);
   EmbWs w = carve_emb_ws(emb_ws, N);
   if (emb_ws_bytes < w.total) {
@@ -1248,7 +1252,19 @@ int shard_requester_grads(const float* dense, float* dense_grad, const float* ro
     A.N = N;
     A.mode = NCF_EMB_ADAM_SPARSE;
     A.accumulate_wmf = side == 0 ? 1 : 0;
-    emb_bwd_phase1_kernel<<<grid, EB_THREADS, 0, sst>>>(A);
+    if (lean) {
+      A.other_y = side ? y_user_mf : y_item_mf;
+      A.own_y = side ? nullptr : y_user_mf;
+      if (A.accumulate_wmf) {
+        if (rows_bf16) emb_bwd_phase1_lean_kernel<true, true><<<grid, EB_THREADS, 0, sst>>>(A);
+        else emb_bwd_phase1_lean_kernel<true, false><<<grid, EB_THREADS, 0, sst>>>(A);
+      } else {
+        if (rows_bf16) emb_bwd_phase1_lean_kernel<false, true><<<grid, EB_THREADS, 0, sst>>>(A);
+        else emb_bwd_phase1_lean_kernel<false, false><<<grid, EB_THREADS, 0, sst>>>(A);
+      }
+    } else {
+      emb_bwd_phase1_kernel<<<grid, EB_THREADS, 0, sst>>>(A);
+    }
     NCF_LAUNCH_CHECK();
     A.dense_grad = nullptr;                  // output mode: no LayerNorm-affine gradients here (the owners add them)
     emb_bwd_phase2_kernel<<<std::min(grid, num_sms() * 3), EB_THREADS, 0, sst>>>(A);

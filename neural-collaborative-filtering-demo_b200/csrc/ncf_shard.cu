@@ -84,25 +84,44 @@ __global__ void __launch_bounds__(256) pull_rows_kernel(const ncf_shard_plan* __
   }
 }
 
-// requester: sample n reads its user rows at rows_u[pos_u[n]] and its item rows at rows_i[pos_i[n]]
+// requester: sample n reads its user rows at rows_u[pos_u[n]] and its item rows at rows_i[pos_i[n]].  Training: the two
+// LayerNorm-ed MF rows of every sample are kept per SAMPLE (y_item_mf, y_user_mf, like K1 does), so that the requester's
+// segment sum of the backward reads everything by sample row (the lean phase-1 kernel) instead of chasing pos -> row twice.
 __global__ void __launch_bounds__(256) gmf_from_rows_kernel(const float* __restrict__ rows_u, const float* __restrict__ rows_i,
                                                             const int64_t* __restrict__ pos_u, const int64_t* __restrict__ pos_i,
                                                             const float* __restrict__ dense, int64_t N,
                                                             float* __restrict__ mf_pred, float* __restrict__ xu,
-                                                            float* __restrict__ xp, bool bf16_rows) {
+                                                            float* __restrict__ xp, float* __restrict__ y_item_mf,
+                                                            float* __restrict__ y_user_mf, bool bf16_rows) {
   const int lane = threadIdx.x & 31, half = lane >> 4, l16 = lane & 15;
   const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
   const float4 w_out = ldg4(dense + NCF_OFF(NCF_P_MF_OUT_W) + 4 * l16);
   const float b_out = __ldg(dense + NCF_OFF(NCF_P_MF_OUT_B));
-  for (int64_t n = warp; n < N; n += nwarps) {
-    const float* src = half ? rows_i + pos_i[n] * 2 * D : rows_u + pos_u[n] * 2 * D;
-    const float4 y_mf = ldg4(src + 4 * l16), y_ml = ldg4(src + D + 4 * l16);
-    const float4 other = make_float4(__shfl_xor_sync(0xffffffffu, y_mf.x, 16), __shfl_xor_sync(0xffffffffu, y_mf.y, 16),
-                                     __shfl_xor_sync(0xffffffffu, y_mf.z, 16), __shfl_xor_sync(0xffffffffu, y_mf.w, 16));
-    const float dot = half_warp_sum(f4_dot(f4_mul(y_mf, other), w_out));
-    if (lane == 0) mf_pred[n] = dot + b_out;
-    st_row4(half ? xp : xu, n, 4 * l16, y_ml, bf16_rows);
+  const float* rows = half ? rows_i : rows_u;
+  const int64_t* pos = half ? pos_i : pos_u;
+  float* ykeep = half ? y_item_mf : y_user_mf;
+  // four samples per trip: eight independent 128-bit loads per lane in flight
+  for (int64_t n0 = warp * 4; n0 < N; n0 += nwarps * 4) {
+    float4 y_mf[4], y_ml[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float* src = rows + pos[min(n0 + j, N - 1)] * 2 * D;
+      y_mf[j] = ldg4(src + 4 * l16);
+      y_ml[j] = ldg4(src + D + 4 * l16);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t n = n0 + j;
+      const float4 other = make_float4(__shfl_xor_sync(0xffffffffu, y_mf[j].x, 16), __shfl_xor_sync(0xffffffffu, y_mf[j].y, 16),
+                                       __shfl_xor_sync(0xffffffffu, y_mf[j].z, 16), __shfl_xor_sync(0xffffffffu, y_mf[j].w, 16));
+      const float dot = half_warp_sum(f4_dot(f4_mul(y_mf[j], other), w_out));
+      if (n < N) {
+        if (lane == 0) mf_pred[n] = dot + b_out;
+        st_row4(half ? xp : xu, n, 4 * l16, y_ml[j], bf16_rows);
+        if (ykeep) st_row4(ykeep, n, 4 * l16, y_mf[j], bf16_rows);
+      }
+    }
   }
 }
 
@@ -266,8 +285,9 @@ extern "C" int ncf_shard_forward(const ncf_run_cfg* cfg, const float* dense, con
     return NCF_ERR_WORKSPACE;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  const int grid = (int)std::min<int64_t>((N + 7) / 8, (int64_t)num_sms() * 8);
-  gmf_from_rows_kernel<<<grid, 256, 0, st>>>(rows_u, rows_i, pos_u, pos_i, dense, N, w.mf_pred, w.xu, w.xp, tower_bf16_rows(*cfg));
+  const int grid = (int)std::min<int64_t>((N + 31) / 32, (int64_t)num_sms() * 8);
+  gmf_from_rows_kernel<<<grid, 256, 0, st>>>(rows_u, rows_i, pos_u, pos_i, dense, N, w.mf_pred, w.xu, w.xp,
+                                             cfg->training ? w.y_pmf : nullptr, cfg->training ? w.y_umf : nullptr, tower_bf16_rows(*cfg));
   NCF_LAUNCH_CHECK();
   return tower_f32_forward(*cfg, dense, N, nullptr, nullptr, out, w, st);
 }
@@ -315,7 +335,7 @@ static int shard_backward_impl(const ncf_run_cfg* cfg, const float* dense, float
   NCF_TRY(tower_f32_backward(*cfg, dense, dense_grad, N, grad_out, w, st));
   if (route_ws)     // ids routed by ncf_shard_route: samples that share a row are scattered -> sorted segment sum
     return shard_requester_grads(dense, dense_grad, rows_u, rows_i, pos_u, pos_i, N, w.d_mf, w.dxu, w.dxp, route_ws, grad_rows_u,
-                                 grad_rows_i, w.emb, w.emb_bytes, st, plan, local_ids, tower_bf16_rows(*cfg));
+                                 grad_rows_i, w.emb, w.emb_bytes, st, plan, local_ids, tower_bf16_rows(*cfg), w.y_pmf, w.y_umf);
   const int grid = (int)std::min<int64_t>((N + 7) / 8, (int64_t)num_sms() * 8);
   pack_grads_kernel<<<grid, 256, 0, st>>>(rows_u, rows_i, pos_u, pos_i, dense, w.d_mf, w.dxu, w.dxp, N, grad_rows_u,
                                           grad_rows_i, dense_grad, tower_bf16_rows(*cfg));

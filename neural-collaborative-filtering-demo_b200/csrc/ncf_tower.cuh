@@ -100,7 +100,8 @@ int emb_sort_both(const ncf_tables* T, const int64_t* user_ids, const int64_t* i
 int shard_requester_grads(const float* dense, float* dense_grad, const float* rows_u, const float* rows_i, const int64_t* pos_u,
                           const int64_t* pos_i, int64_t N, const float* d_mf, const float* dxu, const float* dxp,
                           const void* route_ws, float* gu, float* gi, void* emb_ws, int64_t emb_ws_bytes, cudaStream_t st,
-                          const ncf_shard_plan* plan = nullptr, const int64_t* local_ids = nullptr, bool rows_bf16 = false);
+                          const ncf_shard_plan* plan = nullptr, const int64_t* local_ids = nullptr, bool rows_bf16 = false,
+                          const float* y_item_mf = nullptr, const float* y_user_mf = nullptr);
 // fused backward of one projection: dX = dY.W and dW += dY^T.X, db += colsum(dY) (which: 0 = 64 cols, 1 = 128)
 int tc_proj_backward(int which, const float* dY, const float* X, const float* W, float* dX, float* dW, float* db, int64_t N,
                      cudaStream_t st);
