@@ -281,6 +281,7 @@ struct EmbBwdArgs {
   const uint32_t* other_sorted;   // optional: other side's id per SORTED position (pre-gathered, coalesced)
   const float* dmf_sorted;        // optional: d_mf_pred per sorted position
   const float* d_x;               // [N,64] gradient wrt this side's LN'd MLP row
+  int32_t boundary_only;          // phase 2 behind the fused kernel: only the runs that leave their chunk are still to be applied
   int32_t rows_bf16;              // the per-sample [N,64] row arrays (d_x, other_y, own_y) hold bf16 rows (bf16 towers, S = 5)
   const float* dense;
   float* dense_grad;
@@ -389,6 +390,138 @@ __global__ void __launch_bounds__(EB_THREADS, 3) emb_bwd_phase1_lean_kernel(EmbB
   }
   if (WMF) block_flush(s_red, dwout, A.dense_grad ? A.dense_grad + NCF_OFF(NCF_P_MF_OUT_W) : nullptr, lane, warp, nwarps,
                        half == 0, l16);
+}
+
+// Single-pass variant of the lean phase 1 (Adam modes, single-GPU step): a run of equal ids that lies inside the warp's
+// chunk of 32 sorted positions is applied RIGHT HERE (LayerNorm backward + Adam, the arithmetic of phase 2), so its 512-byte
+// sum never travels through acc_buf and its ids are not read a second time; only the pieces of runs that cross a chunk border
+// (the chunk's first piece if the run came in from the previous chunk, its last piece if the run goes on) are left in acc_buf
+// for phase 2, which then runs with boundary_only.  Same order of additions as the two-phase path: bit-identical tables.
+// The state rows (w, m, v of both towers) of every run start are prefetched into L2 when the chunk is picked up.
+template <bool WMF, bool BF>
+__global__ void __launch_bounds__(EB_THREADS, 2) emb_bwd_fused_kernel(EmbBwdArgs A) {
+  __shared__ float s_red[(EB_THREADS / 32) * 32 * 4];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = EB_THREADS / 32;
+  const int half = lane >> 4, l16 = lane & 15;
+  const int64_t nchunks = (A.N + EB_CHUNK - 1) / EB_CHUNK;
+  const int64_t gw = (int64_t)blockIdx.x * nwarps + warp, gstride = (int64_t)gridDim.x * nwarps;
+  const float4 w_out = ldg4(A.dense + NCF_OFF(NCF_P_MF_OUT_W) + 4 * l16);
+  const float4 gamma = ldg4(A.dense + (half ? NCF_OFF(NCF_P_MLP_NORM_W) : NCF_OFF(NCF_P_MF_NORM_W)) + 4 * l16);
+  const float* src = half ? A.d_x : A.other_y;
+  const float* own = A.own_y;
+  float* tw = A.w[half];
+  float* tm = A.m[half];
+  float* tv = A.v[half];
+  float4 dwout = make_float4(0, 0, 0, 0), dgamma = dwout, dbeta = dwout;
+  constexpr int U = BF ? 8 : 4;
+  using Raw = typename std::conditional<BF, uint2, float4>::type;
+  auto load = [&](const float* base, int64_t row) -> Raw {
+    if constexpr (BF) return __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(base) + row * 64 + 4 * l16));
+    else return __ldg(reinterpret_cast<const float4*>(base + row * 64 + 4 * l16));
+  };
+  auto widen = [](Raw q) -> float4 {
+    if constexpr (BF) return make_float4(__uint_as_float(q.x << 16), __uint_as_float(q.x & 0xffff0000u), __uint_as_float(q.y << 16),
+                                         __uint_as_float(q.y & 0xffff0000u));
+    else return q;
+  };
+
+  for (int64_t c = gw; c < nchunks; c += gstride) {
+    const int64_t p0 = c * EB_CHUNK;
+    const int cnt = (int)min((int64_t)EB_CHUNK, A.N - p0);
+    const uint32_t my_id = lane < cnt ? A.sorted_ids[p0 + lane] : 0xffffffffu;
+    const int32_t my_row = lane < cnt ? A.perm[p0 + lane] : 0;
+    const float my_dmf = lane < cnt ? __ldg(A.d_mf_pred + my_row) : 0.f;
+    // neighbours across the chunk borders: lane 0 looks back, lane 1 looks ahead
+    uint32_t nb = 0xfffffffeu;
+    if (lane == 0 && p0 > 0) nb = A.sorted_ids[p0 - 1];
+    if (lane == 1 && p0 + cnt < A.N) nb = A.sorted_ids[p0 + cnt];
+    const uint32_t id_first = __shfl_sync(0xffffffffu, my_id, 0), id_last = __shfl_sync(0xffffffffu, my_id, cnt - 1);
+    const bool cont_in = __shfl_sync(0xffffffffu, nb, 0) == id_first;
+    const bool cont_out = __shfl_sync(0xffffffffu, nb, 1) == id_last;
+    {   // L2 prefetch of the state rows of every run that starts here (each row = two 128-byte lines per tower and array)
+      const uint32_t prev = __shfl_up_sync(0xffffffffu, my_id, 1);
+      if (lane < cnt && (lane == 0 ? !cont_in : prev != my_id)) {
+        const int64_t o = (int64_t)(my_id - A.id_off) * D;
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(A.w[t] + o + 32 * q));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(A.m[t] + o + 32 * q));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(A.v[t] + o + 32 * q));
+          }
+        }
+      }
+    }
+    float4 acc = make_float4(0, 0, 0, 0);
+    int piece_first = 0;
+    uint32_t id_prev = id_first;
+    // a piece [piece_first, end) of id `id` is complete: apply it (complete = the whole run lies in this chunk)
+    auto finish = [&](uint32_t id, bool complete) {
+      if (!complete) {
+        st4(A.acc_buf + ((p0 + piece_first) * 2 + half) * D + 4 * l16, acc);
+        return;
+      }
+      const int64_t o = (int64_t)(id - A.id_off) * D + 4 * l16;
+      const float4 wrow = ld4(tw + o);
+      float4 mm = ld4(tm + o), vv = ld4(tv + o);
+      float rstd;
+      const float4 xhat = ln_normalise(wrow, rstd);
+      dgamma = f4_add(dgamma, f4_mul(acc, xhat));
+      dbeta = f4_add(dbeta, acc);
+      const float4 dyg = f4_mul(acc, gamma);
+      const float m1 = half_warp_sum(f4_hsum(dyg)) * (1.0f / 64.0f);
+      const float m2 = half_warp_sum(f4_dot(dyg, xhat)) * (1.0f / 64.0f);
+      const float4 graw = make_float4(rstd * (dyg.x - m1 - xhat.x * m2), rstd * (dyg.y - m1 - xhat.y * m2),
+                                      rstd * (dyg.z - m1 - xhat.z * m2), rstd * (dyg.w - m1 - xhat.w * m2));
+      float4 wn = wrow;
+      adam_update4(wn, mm, vv, graw, A.adam);
+      st4(tw + o, wn);
+      st4(tm + o, mm);
+      st4(tv + o, vv);
+      if (A.touched && lane == 0) A.touched[id - A.id_off] = A.touched_val;
+    };
+    for (int k0 = 0; k0 < cnt; k0 += U) {
+      Raw x[U], sf[U];
+      float dmf[U];
+      uint32_t idk[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int kk = min(k0 + u, cnt - 1);
+        const int64_t srow = __shfl_sync(0xffffffffu, my_row, kk);
+        dmf[u] = __shfl_sync(0xffffffffu, my_dmf, kk);
+        idk[u] = __shfl_sync(0xffffffffu, my_id, kk);
+        x[u] = load(src, srow);
+        if (WMF) sf[u] = half ? Raw{} : load(own, srow);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (k0 + u < cnt) {                                   // warp-uniform
+          if (idk[u] != id_prev) {                            // a new run starts: the piece before it ends inside the chunk
+            finish(id_prev, !(piece_first == 0 && cont_in));
+            acc = make_float4(0, 0, 0, 0);
+            piece_first = k0 + u;
+            id_prev = idk[u];
+          }
+          const float4 xv = widen(x[u]);
+          if (half) {
+            acc = f4_add(acc, xv);
+          } else {
+            const float4 t = make_float4(dmf[u] * xv.x, dmf[u] * xv.y, dmf[u] * xv.z, dmf[u] * xv.w);
+            acc = f4_add(acc, f4_mul(t, w_out));
+            if (WMF) dwout = f4_add(dwout, f4_mul(t, widen(sf[u])));
+          }
+        }
+      }
+    }
+    finish(id_prev, !(piece_first == 0 && cont_in) && !cont_out);
+  }
+  float* dg = A.dense_grad;
+  if (WMF) block_flush(s_red, dwout, dg ? dg + NCF_OFF(NCF_P_MF_OUT_W) : nullptr, lane, warp, nwarps, half == 0, l16);
+  block_flush(s_red, dgamma, dg ? dg + NCF_OFF(NCF_P_MF_NORM_W) : nullptr, lane, warp, nwarps, half == 0, l16);
+  block_flush(s_red, dgamma, dg ? dg + NCF_OFF(NCF_P_MLP_NORM_W) : nullptr, lane, warp, nwarps, half == 1, l16);
+  block_flush(s_red, dbeta, dg ? dg + NCF_OFF(NCF_P_MF_NORM_B) : nullptr, lane, warp, nwarps, half == 0, l16);
+  block_flush(s_red, dbeta, dg ? dg + NCF_OFF(NCF_P_MLP_NORM_B) : nullptr, lane, warp, nwarps, half == 1, l16);
 }
 
 // Phase 1 - streaming segment sum.  A warp owns a chunk of 32 sorted positions and adds up the
@@ -513,6 +646,13 @@ __global__ void __launch_bounds__(EB_THREADS, 3) emb_bwd_phase2_kernel(EmbBwdArg
     const uint32_t my_id = lane < cnt ? A.sorted_ids[p0 + lane] : 0xffffffffu;
     const uint32_t before = (p0 + lane > 0 && lane < cnt) ? A.sorted_ids[p0 + lane - 1] : 0xfffffffeu;
     uint32_t starts = __ballot_sync(0xffffffffu, lane < cnt && (p0 + lane == 0 || before != my_id));
+    if (A.boundary_only) {      // behind emb_bwd_fused_kernel: only the chunk's last run is left, and only if it goes on
+      uint32_t ahead = 0xfffffffeu;
+      if (lane == 0 && p0 + cnt < A.N) ahead = A.sorted_ids[p0 + cnt];
+      ahead = __shfl_sync(0xffffffffu, ahead, 0);
+      if (!starts || ahead != __shfl_sync(0xffffffffu, my_id, cnt - 1)) continue;
+      starts = 1u << (31 - __clz(starts));
+    }
     // software pipeline over the run starts: the loads of the NEXT run are in flight while this one is applied
     struct Loads { float4 w, m, v, a; };
     auto issue = [&](int i, uint32_t id) {
@@ -894,6 +1034,7 @@ static int run_emb_bwd(const ncf_adam_cfg* adam, const ncf_tables* T, const floa
   A.d_mf_pred = d_mf_pred;
   A.d_x = d_x;
   A.rows_bf16 = 0;
+  A.boundary_only = 0;
   A.dense = dense;
   A.dense_grad = dense_grad;
   A.acc_buf = w.acc_buf;
@@ -1045,6 +1186,7 @@ int emb_bwd_both(const ncf_adam_cfg* adam, const ncf_tables* T, const float* den
     A.dmf_sorted = w.dmf_sorted + (side ? N : 0);
     A.d_x = side ? dxp : dxu;
     A.rows_bf16 = rows_bf16 ? 1 : 0;
+    A.boundary_only = 0;
     A.dense = dense;
     A.dense_grad = dense_grad;
     A.acc_buf = (two_streams && side == 1) ? w.acc_buf2 : w.acc_buf;
@@ -1054,7 +1196,20 @@ int emb_bwd_both(const ncf_adam_cfg* adam, const ncf_tables* T, const float* den
     A.accumulate_wmf = side == 0 ? 1 : 0;
     A.adam = adam_scalars(*adam);
     A.chunk_counter = w.counters + side;
-    if (lean) {      // the usual case
+    // measured SLOWER than the two phases (c2 step 1.101 -> 1.169 ms, c3shard 1.213 -> 1.346 ms): every run's w / m / v loads sit
+    // in series with its LayerNorm backward + Adam inside one warp, at 16 warps per SM (128 registers); opt-in A/B switch
+    static const bool fused_ok = getenv("NCF_K6_FUSED") && getenv("NCF_K6_FUSED")[0] == '1';
+    if (lean && fused_ok && adam->emb_mode != NCF_EMB_MATERIALIZE) {      // single pass + phase 2 for the runs that cross chunk borders
+      const int fgrid = (int)std::min<int64_t>((nchunks + wpb - 1) / wpb, (int64_t)num_sms() * 2);
+      if (A.accumulate_wmf) {
+        if (rows_bf16) emb_bwd_fused_kernel<true, true><<<fgrid, EB_THREADS, 0, sst>>>(A);
+        else emb_bwd_fused_kernel<true, false><<<fgrid, EB_THREADS, 0, sst>>>(A);
+      } else {
+        if (rows_bf16) emb_bwd_fused_kernel<false, true><<<fgrid, EB_THREADS, 0, sst>>>(A);
+        else emb_bwd_fused_kernel<false, false><<<fgrid, EB_THREADS, 0, sst>>>(A);
+      }
+      A.boundary_only = 1;
+    } else if (lean) {      // two phases
       if (A.accumulate_wmf) {
         if (rows_bf16) emb_bwd_phase1_lean_kernel<true, true><<<grid, EB_THREADS, 0, sst>>>(A);
         else emb_bwd_phase1_lean_kernel<true, false><<<grid, EB_THREADS, 0, sst>>>(A);

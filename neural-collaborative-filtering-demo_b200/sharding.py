@@ -418,6 +418,9 @@ class ShardedNCFEngine:
         scale = float(N) / float(global_rows)            # local mean -> share of the global mean
         grad_out.mul_(scale)
         self.loss.mul_(scale)
+        hook = self.__dict__.pop("_mid_hook", None)
+        if hook is not None:
+            hook()
         if getattr(self, "_want_loss_event", False):
             self._early_loss()
         self.dense_grad.zero_()
@@ -742,26 +745,36 @@ class ShardedNCFEngine:
         mark("route + plan")
         rows = self.phase_pull(plan_ptr, n_dist)
         mark("pull rows (P2P)")
-        nxt = None
-        if next_ids is not None:
+        nxt_box = [None]
+
+        def route_next():
             # the next batch's routing (sort, de-duplication) depends on its ids only: on the auxiliary stream it fills the
             # SMs this step's kernels leave idle (kernel boundaries, tails of the persistent tower kernels).  It is enqueued
             # BEFORE the towers: behind them it starts late on the device - they own every SM's shared memory - and the step
             # is 6 % slower (N = 2: 1.576 vs 1.484 ms); but AFTER the pull, so that a host that comes straight from waiting
             # for the previous loss (train_step_host) reaches this step's first kernel 0.2 ms sooner.
-            if callable(next_ids):
-                next_ids = next_ids()                # train_step_host: stages the next batch on its copy stream here
+            ids = next_ids() if callable(next_ids) else next_ids      # train_step_host: stages the next batch on its copy stream here
             rs = self._aux if self._aux is not None else main
             if rs is not main:
                 rs.wait_event(step_start)
             if getattr(self, "_next_ids_event", None) is not None:
                 rs.wait_event(self._next_ids_event)          # the next ids arrive on a copy stream (train_step_host)
             with torch.cuda.stream(rs):
-                nxt = self._route(next_ids[0], next_ids[1], self._bufs["slot"])
+                nxt_box[0] = self._route(ids[0], ids[1], self._bufs["slot"])
             self._bufs["slot"] ^= 1
-        self._pending_next = nxt if getattr(self, "_want_loss_event", False) else None
+            self._pending_next = nxt_box[0] if getattr(self, "_want_loss_event", False) else None
+        self._pending_next = None
+        if next_ids is not None:
+            # enqueued between the forward and the backward (NCF_SHARD_ROUTE_AT=pre: in front of the forward): the same device time
+            # (1.366 vs 1.365 ms at N = 2), but a host that comes from waiting for the previous loss reaches this step's forward
+            # sooner (end to end 1.375 vs 1.40 ms)
+            if os.environ.get("NCF_SHARD_ROUTE_AT", "mid") == "mid":
+                self._mid_hook = route_next
+            else:
+                route_next()
         self.phase_forward_backward(rows, targets, global_rows, push_plan=plan_ptr)
         self._pending_next = None
+        nxt = nxt_box[0]
         mark("forward+backward+push (P2P)")
         # Collectives of the step, all issued on their own stream in the same order on every rank:
         #   A  count all-gather of the NEXT batch (look-ahead; else a one-word all-reduce): a barrier - every requester's
