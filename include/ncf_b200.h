@@ -368,6 +368,15 @@ NCF_API int ncf_shard_owner_update(const ncf_adam_cfg* adam, const ncf_tables* l
                            float* dense_grad, int32_t side, const int64_t* local_ids, int64_t n,
                            const float* grad_rows, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* The same in two halves, for the one-sided step below: ncf_shard_pull_rows has already written the ids a requester will
+ * push rows for, so the owner sorts them early (on another stream, next to the towers) and only the segment sum + update
+ * wait for the rows.  Same workspace in both calls; local_ids / n as in ncf_shard_owner_update.  (trainer.py:84-88, 284-285) */
+NCF_API int ncf_shard_owner_sort(const ncf_tables* local_tables, int32_t side, const int64_t* local_ids, int64_t n,
+                         void* workspace, int64_t workspace_bytes, void* stream);
+NCF_API int ncf_shard_owner_update_sorted(const ncf_adam_cfg* adam, const ncf_tables* local_tables, const float* dense,
+                                  float* dense_grad, int32_t side, const int64_t* local_ids, int64_t n,
+                                  const float* grad_rows, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---- row-sharded step over PEER MEMORY (NVLink / NVSwitch, one-sided) ------------------------------------------
  * SURVEY section 5 "stretch design": every rank maps its peers' table shards and gradient receive buffers into its own
  * address space (CUDA IPC: ncf_ipc_open), so the two bulk exchanges of a step need no collective and no owner-side

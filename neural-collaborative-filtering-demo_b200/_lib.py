@@ -156,6 +156,8 @@ _SIGS = {
     "ncf_auc": (C.c_int, [_P, _P, _I64, _I64, C.c_float, _P, _P, _I64, _P]),
     "ncf_tc_selftest": (C.c_int, [_I32, _I32, _I32, _P, _P, _P, _P]),
     "ncf_shard_owner_update": (C.c_int, [C.POINTER(AdamCfg), C.POINTER(Tables), _P, _P, _I32, _P, _I64, _P, _P, _I64, _P]),
+    "ncf_shard_owner_update_sorted": (C.c_int, [C.POINTER(AdamCfg), C.POINTER(Tables), _P, _P, _I32, _P, _I64, _P, _P, _I64, _P]),
+    "ncf_shard_owner_sort": (C.c_int, [C.POINTER(Tables), _I32, _P, _I64, _P, _I64, _P]),
 }
 EXPORTS = tuple(_SIGS)
 

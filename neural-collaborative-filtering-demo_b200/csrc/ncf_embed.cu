@@ -981,10 +981,32 @@ extern "C" int64_t ncf_emb_bwd_workspace_bytes(int64_t N) { return carve_emb_ws(
 
 // shared by the single-GPU backward (ids = this side's global ids, per-sample inputs) and the sharded
 // owner update (ids = local row ids, `upstream` = received gradient rows)
+// keys = clamped ids, one radix sort (key, position): the id-only half of run_emb_bwd.  The sharded owner runs it ahead of
+// time (ncf_shard_owner_sort) on the ids the requesters write next to their pull
+static int emb_sort_one(const ncf_tables* T, int32_t side, const int64_t* ids, int64_t N, void* workspace,
+                        int64_t workspace_bytes, cudaStream_t st) {
+  NCF_REQUIRE(side == 0 || side == 1, "emb_bwd: side must be 0 or 1");
+  NCF_REQUIRE(N < ((int64_t)1 << 31), "emb_bwd: N too large");
+  if (N == 0) return NCF_OK;
+  EmbWs w = carve_emb_ws(workspace, N);
+  if (workspace_bytes < w.total) {
+    set_error("emb_bwd: workspace %lld < %lld", (long long)workspace_bytes, (long long)w.total);
+    return NCF_ERR_WORKSPACE;
+  }
+  const int64_t rows = side ? T->rows_item : T->rows_user;
+  NCF_REQUIRE(rows > 0 && rows < ((int64_t)1 << 32), "emb_bwd: table rows out of range");
+  ids_to_keys_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(ids, N, rows, w.keys_in, w.vals_in);
+  NCF_LAUNCH_CHECK();
+  size_t tmp = w.cub_bytes;
+  NCF_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tmp, w.keys_in, w.keys_out, w.vals_in, w.vals_out, (int)N, 0,
+                                           bits_for(rows), st));
+  return NCF_OK;
+}
+
 static int run_emb_bwd(const ncf_adam_cfg* adam, const ncf_tables* T, const float* dense, float* dense_grad,
                        int32_t side, const int64_t* ids, const int64_t* other_ids, int64_t N, const float* d_mf_pred,
                        const float* d_x, const float* other_y_mf, const float* upstream, void* workspace,
-                       int64_t workspace_bytes, void* stream) {
+                       int64_t workspace_bytes, void* stream, bool presorted = false) {
   NCF_REQUIRE(side == 0 || side == 1, "emb_bwd: side must be 0 or 1");
   NCF_REQUIRE(N < ((int64_t)1 << 31), "emb_bwd: N too large");
   if (N == 0 || adam->emb_mode == NCF_EMB_NONE) return NCF_OK;
@@ -1000,11 +1022,7 @@ static int run_emb_bwd(const ncf_adam_cfg* adam, const ncf_tables* T, const floa
   else
     NCF_REQUIRE(T->m[side] && T->v[side] && T->m[2 + side] && T->v[2 + side], "emb_bwd: Adam mode needs m and v");
   cudaStream_t st = (cudaStream_t)stream;
-  ids_to_keys_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(ids, N, rows, w.keys_in, w.vals_in);
-  NCF_LAUNCH_CHECK();
-  size_t tmp = w.cub_bytes;
-  NCF_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, tmp, w.keys_in, w.keys_out, w.vals_in, w.vals_out, (int)N, 0,
-                                           bits_for(rows), st));
+  if (!presorted) NCF_TRY(emb_sort_one(T, side, ids, N, workspace, workspace_bytes, st));
   EmbBwdArgs A;
   A.w[0] = T->w[side];
   A.w[1] = T->w[2 + side];
@@ -1439,6 +1457,24 @@ extern "C" int ncf_shard_route(const int64_t* user_ids, const int64_t* item_ids,
                                int64_t route_ws_bytes, void* stream) {
   return ncf::shard_route(user_ids, item_ids, N, rows_user, rows_item, world, counts, local_ids, pos, route_ws, route_ws_bytes,
                           (cudaStream_t)stream);
+}
+
+extern "C" int ncf_shard_owner_sort(const ncf_tables* T, int32_t side, const int64_t* local_ids, int64_t n, void* workspace,
+                                    int64_t workspace_bytes, void* stream) {
+  NCF_REQUIRE(T && n >= 0, "shard_owner_sort: bad argument");
+  if (n == 0) return NCF_OK;
+  NCF_REQUIRE(local_ids && workspace, "shard_owner_sort: null buffer");
+  return emb_sort_one(T, side, local_ids, n, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int ncf_shard_owner_update_sorted(const ncf_adam_cfg* adam, const ncf_tables* T, const float* dense,
+                                             float* dense_grad, int32_t side, const int64_t* local_ids, int64_t n,
+                                             const float* grad_rows, void* workspace, int64_t workspace_bytes, void* stream) {
+  NCF_REQUIRE(adam && T && dense && n >= 0, "shard_owner_update_sorted: bad argument");
+  if (n == 0) return NCF_OK;
+  NCF_REQUIRE(local_ids && grad_rows && workspace, "shard_owner_update_sorted: null buffer");
+  return run_emb_bwd(adam, T, dense, dense_grad, side, local_ids, nullptr, n, nullptr, nullptr, nullptr, grad_rows,
+                     workspace, workspace_bytes, stream, true);
 }
 
 extern "C" int ncf_shard_owner_update(const ncf_adam_cfg* adam, const ncf_tables* T, const float* dense,

@@ -81,6 +81,15 @@ __global__ void __launch_bounds__(256) pull_rows_kernel(const ncf_shard_plan* __
             make_float4(fmaf(d.x * rstd, g.x, b.x), fmaf(d.y * rstd, g.y, b.y), fmaf(d.z * rstd, g.z, b.z),
                         fmaf(d.w * rstd, g.w, b.w)));
     }
+    // The ids this rank will send gradient rows for go into the owners' receive buffers NOW (the backward's push stores the
+    // same words again next to the rows): behind a barrier the owner sorts them next to the towers (ncf_shard_owner_sort)
+    // instead of between the push and its update.
+    if (lane < 4 && r0 + lane < n) {
+      const int64_t r = r0 + lane;
+      int o = 0;
+      while (o + 1 < world && r >= s_begin[o + 1]) ++o;
+      plan->push_ids[side][o][r - s_begin[o]] = local_ids[r];
+    }
   }
 }
 

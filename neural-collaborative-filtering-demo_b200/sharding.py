@@ -457,8 +457,25 @@ class ShardedNCFEngine:
                    "ncf_shard_backward")
         return [gu, gi]
 
+    def phase_owner_sort(self, served: List[torch.Tensor]):
+        """owner, one-sided step: radix sort of the local ids the requesters wrote next to their pull (the id-only half of
+        the update), enqueued on the current stream; phase_owner_update(presorted=True) then starts at the segment sum."""
+        tabs = self._tables()
+        ws_list = self.__dict__.setdefault("_own_ws", [None, None])
+        for side in (1, 0):
+            ids = served[side]
+            n = ids.numel()
+            if not n:
+                continue
+            nbytes = int(self.lib.ncf_emb_bwd_workspace_bytes(n))
+            if ws_list[side] is None or ws_list[side].numel() < nbytes:
+                ws_list[side] = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            ws = ws_list[side]
+            _lib.check(self.lib.ncf_shard_owner_sort(C.byref(tabs), side, _lib.ptr(ids), n, _lib.ptr(ws), nbytes, self._s()),
+                       "ncf_shard_owner_sort")
+
     def phase_owner_update(self, grad_rows: List[torch.Tensor], served: Optional[List[torch.Tensor]] = None,
-                           ln_grad: Optional[torch.Tensor] = None):
+                           ln_grad: Optional[torch.Tensor] = None, presorted: bool = False):
         """owner: segment-sum the received gradient rows per local id, LN backward, Adam.  The two sides touch different
         tables (their LayerNorm-affine gradients are added atomically), so the item side runs on the auxiliary stream.
         ln_grad: where the gradients of mf_norm / mlp_norm (the first 256 floats of the flat layout - the only dense
@@ -481,10 +498,10 @@ class ShardedNCFEngine:
             stream = self._aux if (side == 1 and self._aux is not None) else main
             if stream is not main:
                 stream.wait_stream(main)
+            fn = self.lib.ncf_shard_owner_update_sorted if presorted else self.lib.ncf_shard_owner_update
             with torch.cuda.stream(stream):
-                _lib.check(self.lib.ncf_shard_owner_update(C.byref(adam), C.byref(tabs), _lib.ptr(self.model._flat),
-                                                           _lib.ptr(dense_grad), side, _lib.ptr(ids), n, _lib.ptr(g),
-                                                           _lib.ptr(ws), nbytes, self._s()), "ncf_shard_owner_update")
+                _lib.check(fn(C.byref(adam), C.byref(tabs), _lib.ptr(self.model._flat), _lib.ptr(dense_grad), side, _lib.ptr(ids),
+                              n, _lib.ptr(g), _lib.ptr(ws), nbytes, self._s()), "ncf_shard_owner_update")
         if self._aux is not None:
             main.wait_stream(self._aux)
         if self.table_mode == "fused_dense_equiv":
@@ -745,6 +762,25 @@ class ShardedNCFEngine:
         mark("route + plan")
         rows = self.phase_pull(plan_ptr, n_dist)
         mark("pull rows (P2P)")
+        # The pull kernels have written the ids this rank will push rows for into the owners' receive buffers.  Behind a
+        # one-word all-reduce (every rank's ids have landed) each owner sorts what it received on the auxiliary stream, next
+        # to the towers: the update behind the push starts at the segment sum (6 small kernels per side off the critical path).
+        served = [self._recv_ids[0][:n_recv[0]], self._recv_ids[1][:n_recv[1]]]
+        # Opt-in (NCF_SHARD_EARLY_SORT=1): measured at N = 2 it does not pay - 1.364 / 1.417 ms against 1.370 / 1.372 ms per step;
+        # the extra collective and the sort's kernels compete with the routing of the next batch for the few free SMs.
+        early_sort = self._aux is not None and os.environ.get("NCF_SHARD_EARLY_SORT", "0") == "1"
+        ev_sorted = None
+        if early_sort:
+            if getattr(self, "_coll", None) is None:
+                self._coll = torch.cuda.Stream(device=self.device)
+            self._coll.wait_event(main.record_event())
+            with torch.cuda.stream(self._coll):
+                self._barrier()
+                ev_ids = self._coll.record_event()
+            self._aux.wait_event(ev_ids)
+            with torch.cuda.stream(self._aux):
+                self.phase_owner_sort(served)
+                ev_sorted = self._aux.record_event()
         nxt_box = [None]
 
         def route_next():
@@ -808,8 +844,10 @@ class ShardedNCFEngine:
         mark("route next (barrier)")
         ln = self.__dict__.setdefault("_ln_grad", torch.zeros(256, device=self.device))
         ln.zero_()
-        self.phase_owner_update([self._recv_rows[0][:n_recv[0]], self._recv_rows[1][:n_recv[1]]],
-                                served=[self._recv_ids[0][:n_recv[0]], self._recv_ids[1][:n_recv[1]]], ln_grad=ln)
+        if ev_sorted is not None:
+            main.wait_event(ev_sorted)
+        self.phase_owner_update([self._recv_rows[0][:n_recv[0]], self._recv_rows[1][:n_recv[1]]], served=served, ln_grad=ln,
+                                presorted=ev_sorted is not None)
         mark("owner update")
         if multi:
             dist.all_reduce(ln, group=self.group)

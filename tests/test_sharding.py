@@ -315,7 +315,10 @@ def test_lookahead_routing_does_not_change_results():
         batches.append((u.cuda(), i.cuda(), t.reshape(-1).cuda()))
     out = []
     host = [tuple(x.cpu().pin_memory() for x in b) for b in batches]
-    for look, exchange in ((False, "nccl"), (True, "nccl"), (False, "p2p"), (True, "p2p"), ("host", "p2p"), ("host", "nccl")):
+    for look, exchange in ((False, "nccl"), (True, "nccl"), (False, "p2p"), (True, "p2p"), ("host", "p2p"), ("host", "nccl"),
+                           ("early_sort", "p2p")):
+        # "early_sort": the owner's id sort ahead of the push (ncf_shard_owner_sort + ncf_shard_owner_update_sorted)
+        os.environ["NCF_SHARD_EARLY_SORT"] = "1" if look == "early_sort" else "0"
         m = ncf_b200.AdvancedNCF(U, I, 5, 24, dropout=0.0)
         m.load_state_dict(p)
         m = m.cuda().train()
@@ -330,6 +333,7 @@ def test_lookahead_routing_does_not_change_results():
             nxt = batches[s + 1][:2] if (look and s + 1 < len(batches)) else None
             losses.append(float(eng.train_step(*b, next_ids=nxt)))
         torch.cuda.synchronize()
+        os.environ.pop("NCF_SHARD_EARLY_SORT", None)
         out.append((losses, [t.clone() for t in eng.w]))
     for other in out[1:]:
         assert max(abs(a - b) for a, b in zip(out[0][0], other[0])) < 1e-5
