@@ -683,3 +683,47 @@ def test_device_metric_kernels_match_reference_fixture_and_host_code():
         t = (torch.rand(5000, generator=g) < frac).float()
         assert abs(M.calculate_auc(s.cuda(), t.cuda()) - M.calculate_auc(s, t)) < 1e-12
     assert M.calculate_auc(s.cuda(), torch.ones(5000).cuda()) != M.calculate_auc(s.cuda(), torch.ones(5000).cuda())   # NaN
+
+
+@pytest.mark.gpu
+def test_k1_grouping_does_not_depend_on_the_user_layout():
+    """K1 takes five consecutive rows at a time and gathers / normalises the user's rows once when they carry the same user
+    (the reference's collate layout, data_prep.py:286-303); rows with mixed users and the tail of the batch go through the
+    per-sample mapping.  Both give the values of ncf_gather_ln (one row at a time) and the oracle's GMF head, for a batch
+    that mixes uniform groups, mixed groups and a tail that is not a multiple of five."""
+    import ctypes as C
+    import ncf_b200
+    from ncf_b200 import _lib
+    from tests.helpers import golden_params
+    lib = _lib.load()
+    p, _ = golden_params()
+    m = ncf_b200.AdvancedNCF(8031, 366, 5, 24, dropout=0.0)
+    m.load_state_dict({k: v.clone() for k, v in p.items()}, strict=True)
+    m = m.cuda().eval()
+    m._ensure_flat()
+    g = torch.Generator().manual_seed(77)
+    n_groups = 301
+    u = torch.randint(0, 8031, (n_groups,), generator=g).repeat_interleave(5)
+    mixed = torch.rand(n_groups, generator=g) < 0.3
+    rnd = torch.randint(0, 8031, (n_groups * 5,), generator=g)
+    u = torch.where(mixed.repeat_interleave(5), rnd, u)
+    u = torch.cat([u, torch.randint(0, 8031, (3,), generator=g)])          # tail: N = 1508 = 301 * 5 + 3
+    N = u.numel()
+    i = torch.randint(0, 366, (N,), generator=g)
+    u, i = u.cuda(), i.cuda()
+    tabs, flat = m._tables_struct(), m._flat
+    mf = torch.empty(N, device="cuda")
+    xu, xp, yp, yu = (torch.empty(N, 64, device="cuda") for _ in range(4))
+    _lib.check(lib.ncf_gather_ln_gmf_fwd(C.byref(tabs), _lib.ptr(flat), _lib.ptr(u), _lib.ptr(i), N, None, None, _lib.ptr(mf),
+                                         _lib.ptr(xu), _lib.ptr(xp), _lib.ptr(yp), _lib.ptr(yu), None))
+    ref = {}
+    for side, ids, names in ((0, u, ("yu", "xu")), (1, i, ("yp", "xp"))):
+        a, b = torch.empty(N, 64, device="cuda"), torch.empty(N, 64, device="cuda")
+        _lib.check(lib.ncf_gather_ln(C.byref(tabs), _lib.ptr(flat), side, _lib.ptr(ids), N, _lib.ptr(a), _lib.ptr(b), None))
+        ref[names[0]], ref[names[1]] = a, b
+    torch.cuda.synchronize()
+    for name, got in (("yu", yu), ("xu", xu), ("yp", yp), ("xp", xp)):
+        assert torch.equal(got, ref[name]), name
+    w = p["mf_output.weight"].cuda().reshape(-1)
+    expect = (ref["yu"] * ref["yp"] * w).sum(1) + p["mf_output.bias"].cuda()
+    assert float((mf - expect).abs().max()) <= 2e-6

@@ -239,3 +239,59 @@ def test_aux_stream_and_host_prefetch_do_not_change_results():
         assert max(abs(a - b) for a, b in zip(l, base_l)) < 2e-4, (aux, pf, l, base_l)
         assert float((w - base_w).abs().mean()) < 1e-5
         assert torch.equal(w[300:], base_w[300:]) and not torch.equal(w[300:], _initial_user_mf()[300:])
+
+
+@pytest.mark.gpu
+def test_side_stream_weight_gradients_match_the_serial_backward():
+    """ncf_backward at a batch large enough for the concurrent schedule (>= 128 rows per SM): with an auxiliary stream set
+    the MLP weight-gradient kernel runs on a library-owned side stream over a few SMs next to the attention backward,
+    which leaves them free (tower_f32_backward).  Same kernels, same tiles - only the grouping of the per-CTA partial sums
+    differs - so every dense gradient agrees with the serial schedule to fp32 rounding, and the row gradients (bf16 dxu /
+    dxp, summed per id by K6 into the materialised table gradients) are bit-identical."""
+    import ctypes as C
+    from ncf_b200 import _lib
+    from tests.helpers import golden_params
+    lib = _lib.load()
+    p, _ = golden_params()
+    m = _model(p, 8031, 366, dropout=0.2).train()
+    g = torch.Generator().manual_seed(23)
+    B, S = 20480, 5
+    N = B * S
+    u = torch.randint(0, 8031, (B,), generator=g).repeat_interleave(S).cuda()
+    i = torch.randint(0, 366, (N,), generator=g).cuda()
+    gout = (torch.randn(N, generator=g) * 1e-5).cuda()
+    cfg = _lib.RunCfg()
+    cfg.S, cfg.training, cfg.dropout_p, cfg.seed, cfg.step, cfg.precision = S, 1, 0.2, 11, 2, _lib.NCF_BF16_TC
+    wsb = int(lib.ncf_workspace_bytes(N, C.byref(cfg)))
+    ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
+    m._ensure_flat()
+    flat = m._flat
+    out = torch.empty(N, device="cuda")
+    adam = _lib.AdamCfg()
+    adam.lr, adam.beta1, adam.beta2, adam.eps, adam.weight_decay, adam.step = 1e-3, 0.9, 0.999, 1e-8, 0.0, 1
+    adam.emb_mode = _lib.EMB_MATERIALIZE
+    aux = torch.cuda.Stream()
+    results = []
+    try:
+        for use_aux in (False, True):
+            tabs = m._tables_struct()
+            tg = [torch.zeros(r, 64, device="cuda") for r in (8031, 366, 8031, 366)]
+            for k in range(4):
+                tabs.g[k] = tg[k].data_ptr()
+            dg = torch.zeros_like(flat)
+            lib.ncf_set_aux_stream(C.c_void_p(aux.cuda_stream) if use_aux else None)
+            _lib.check(lib.ncf_forward(C.byref(cfg), C.byref(tabs), _lib.ptr(flat), _lib.ptr(u), _lib.ptr(i), N, None, None, None,
+                                       _lib.ptr(out), _lib.ptr(ws), wsb, None))
+            _lib.check(lib.ncf_backward(C.byref(cfg), C.byref(adam), C.byref(tabs), _lib.ptr(flat), _lib.ptr(dg), _lib.ptr(u),
+                                        _lib.ptr(i), N, _lib.ptr(gout), _lib.ptr(ws), wsb, None))
+            torch.cuda.synchronize()
+            results.append((dg.clone(), [t.clone() for t in tg]))
+    finally:
+        lib.ncf_set_aux_stream(None)
+    (dg0, tg0), (dg1, tg1) = results
+    assert float(dg0.abs().max()) > 0
+    scale = float(dg0.abs().max())
+    assert float((dg0 - dg1).abs().max()) <= 2e-5 * scale, float((dg0 - dg1).abs().max()) / scale
+    for a, b in zip(tg0, tg1):
+        assert float(a.abs().max()) > 0
+        assert torch.equal(a, b)
