@@ -746,6 +746,26 @@ def stage_roofline(args, model, batch, users, items, B, precision, table_mode, d
     abwd_ms = time_kernel(attn_bwd, 10, sync)
     sweep_ms = time_kernel(sweep, 10, sync) if table_mode == "fused_dense_equiv" else 0.0
     sweep_bytes = 2 * (users + items) * 1536
+    # Both backward towers the way the step schedules them (ncf_backward without the embedding half, auxiliary stream set):
+    # the MLP weight-gradient kernel runs on a side stream over 28 SMs NEXT TO the attention backward, so the two stages
+    # above, timed one after the other, sum to more than the step spends on them.
+    sched = None
+    if tcp_sched := (precision == "bf16"):
+        aux_s = torch.cuda.Stream(device=dev)
+
+        def bwd_towers():
+            adam.emb_mode = _lib.EMB_NONE
+            _lib.check(lib.ncf_backward(C.byref(cfg), C.byref(adam), C.byref(tabs), _lib.ptr(flat), _lib.ptr(dgrad), _lib.ptr(u),
+                                        _lib.ptr(it), N, _lib.ptr(gout), _lib.ptr(ws), wsb, sptr))
+        lib.ncf_set_aux_stream(C.c_void_p(aux_s.cuda_stream))
+        try:
+            both_ms = time_kernel(bwd_towers, 10, sync)
+        finally:
+            lib.ncf_set_aux_stream(None)
+        tf = N * (2 * FLOP_MLP_FWD + 3 * FLOP_ATTN_FWD) / both_ms / 1e9
+        sched = {"ms": both_ms, "one_after_the_other_ms": mbwd_ms + abwd_ms, "achieved": tf, "unit": "TFLOP/s", "peak": sus,
+                 "frac": tf / sus, "what": "head_bwd + mlp_tc_bwd2, then attn_tc_bwd on 120 SMs next to mlp_tc_wgrad on 28 SMs "
+                                           "(side stream), as ncf_train_step runs them"}
     tcp = precision == "bf16"
     kernels = {
         "K1 gather_ln_gmf_fwd": emb["K1"],
@@ -776,6 +796,8 @@ def stage_roofline(args, model, batch, users, items, B, precision, table_mode, d
                                         "note": "implementation view: counts the activation bytes this implementation moves "
                                                 "between its kernels; the SURVEY-basis fractions are in survey_basis_whole_step"},
                 "pieces_sum_ms": pieces_ms, "kernels": kernels}
+    if sched:
+        roofline["backward_towers_as_scheduled"] = sched
     if "hbm_view" in kt:          # tower stages: SURVEY 8d counts them against the tensor pipe; their intensity says HBM
         roofline["hbm_view"] = kt["hbm_view"]
     return roofline

@@ -30,7 +30,7 @@ METRICS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.
            "launch__registers_per_thread", "launch__grid_size", "launch__block_size"]
 # which kernels make up the stages bench.py times through the C ABI
 STAGES = {
-    "K1 gather_ln_gmf_fwd": ["gather_ln_gmf_fwd_kernel"],
+    "K1 gather_ln_gmf_fwd": ["gather_ln_gmf_fwd_kernel", "gather_ln_gmf_fwd_grouped_kernel"],
     "attention forward (attn_tc_fwd_kernel)": ["attn_tc_fwd_kernel"],
     "MLP forward (mlp_tc_fwd_kernel)": ["mlp_tc_fwd_kernel", "mlp_tc_fwd2_kernel"],
     "MLP backward (head_bwd + mlp_tc_bwd + mlp_tc_wgrad kernels)": ["head_bwd", "mlp_tc_bwd_kernel", "mlp_tc_bwd2_kernel",
