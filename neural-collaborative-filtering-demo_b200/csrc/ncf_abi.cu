@@ -131,7 +131,12 @@ static int backward_impl(const ncf_run_cfg* cfg, const ncf_adam_cfg* adam, const
     return NCF_ERR_WORKSPACE;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  NCF_TRY(tower_f32_backward(*cfg, dense, dense_grad, N, grad_out, w, st));
+  static const bool defer = !(getenv("NCF_WGRAD_JOIN_LATE") && getenv("NCF_WGRAD_JOIN_LATE")[0] == '0');     // A/B switch
+  NCF_TRY(tower_f32_backward(*cfg, dense, dense_grad, N, grad_out, w, st, defer));
+  struct Join {        // the embedding backward does not read the MLP weight gradients: the side stream is joined behind it
+    cudaStream_t st;
+    ~Join() { tower_side_join(st); }
+  } join{st};
   if (adam->emb_mode != NCF_EMB_NONE) {
     if (sorted) NCF_CUDA(cudaStreamWaitEvent(st, sorted, 0));
     NCF_TRY(emb_bwd_both(adam, T, dense, dense_grad, user_ids, item_ids, N, w.d_mf, w.dxu, w.dxp, w.y_pmf, w.y_umf, w.emb, w.emb_bytes, st,

@@ -341,7 +341,11 @@ static int shard_backward_impl(const ncf_run_cfg* cfg, const float* dense, float
     return NCF_ERR_WORKSPACE;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  NCF_TRY(tower_f32_backward(*cfg, dense, dense_grad, N, grad_out, w, st));
+  NCF_TRY(tower_f32_backward(*cfg, dense, dense_grad, N, grad_out, w, st, true));
+  struct Join {        // the requester's segment sum + push do not read the MLP weight gradients: joined behind them
+    cudaStream_t st;
+    ~Join() { tower_side_join(st); }
+  } join{st};
   if (route_ws)     // ids routed by ncf_shard_route: samples that share a row are scattered -> sorted segment sum
     return shard_requester_grads(dense, dense_grad, rows_u, rows_i, pos_u, pos_i, N, w.d_mf, w.dxu, w.dxp, route_ws, grad_rows_u,
                                  grad_rows_i, w.emb, w.emb_bytes, st, plan, local_ids, tower_bf16_rows(*cfg), w.y_pmf, w.y_umf);

@@ -32,8 +32,10 @@ struct TowerWs {
 TowerWs carve_tower_ws(void* ws, int64_t N, const ncf_run_cfg& cfg);
 int tower_f32_forward(const ncf_run_cfg& cfg, const float* dense, int64_t N, const int64_t* hour, const float* tail1,
                       float* out, TowerWs& w, cudaStream_t st);
+// defer_join: the caller calls tower_side_join(st) once it has enqueued the work that does not need the MLP weight gradients
 int tower_f32_backward(const ncf_run_cfg& cfg, const float* dense, float* dense_grad, int64_t N, const float* grad_out,
-                       TowerWs& w, cudaStream_t st);
+                       TowerWs& w, cudaStream_t st, bool defer_join = false);
+int tower_side_join(cudaStream_t st);
 // True when the attention block runs as the fused tcgen05 kernels (bf16 towers, S = 5): then its row-vector
 // interfaces w.xu, w.xp (from K1 / the sharded requester) and da = w.g64a (from the MLP backward) hold bf16
 // [N,64] rows instead of fp32 - the same values the operand tiles would be rounded to anyway, half the traffic.
@@ -85,6 +87,7 @@ struct AuxCtx {
   float* loss_host = nullptr;          // ncf_set_loss_readback
   cudaEvent_t loss_event = nullptr;
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};     // 0 fork, 1 sorted (ncf_train_step); 2 fork, 3 join (emb_bwd_both); 4 fork, 5 join (side stream)
+  bool side_pending = false;           // the side stream's weight-gradient kernels have not been joined into the caller's stream yet
   cudaStream_t side = nullptr;         // library-owned second stream (created with the first use): MLP weight gradients next to the attention backward
 };
 AuxCtx* aux_ctx();

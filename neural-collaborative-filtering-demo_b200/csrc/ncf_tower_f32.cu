@@ -858,8 +858,17 @@ int tower_mlp_forward(const ncf_run_cfg& cfg, const float* dense, int64_t N, con
 }
 
 // produces w.d_mf [N], dxu = w.g64b, dxp = w.g256 and accumulates every dense gradient
+int tower_side_join(cudaStream_t st) {
+  AuxCtx* aux = aux_ctx();
+  if (aux->side_pending) {
+    aux->side_pending = false;
+    NCF_CUDA(cudaStreamWaitEvent(st, aux->ev[5], 0));
+  }
+  return NCF_OK;
+}
+
 int tower_f32_backward(const ncf_run_cfg& cfg, const float* dense, float* dg, int64_t N, const float* grad_out,
-                       TowerWs& w, cudaStream_t st) {
+                       TowerWs& w, cudaStream_t st, bool defer_join) {
   // bf16 towers with an auxiliary stream set: the MLP weight-gradient kernel (HBM-bound) runs on a few SMs NEXT TO the
   // attention backward (issue-bound, 1.3 TB/s of DRAM traffic), which leaves them those SMs
   AuxCtx* aux = aux_ctx();
@@ -870,7 +879,10 @@ int tower_f32_backward(const ncf_run_cfg& cfg, const float* dense, float* dg, in
     NCF_TRY(attn_tc_backward(cfg, dense, dg, N, w, st, side_sms));
     w.dxu = w.g64b;
     w.dxp = w.g256;
-    NCF_CUDA(cudaStreamWaitEvent(st, aux->ev[5], 0));
+    // nothing up to the dense Adam reads the MLP weight gradients: a caller that has more work for `st` (the embedding
+    // backward) joins the side stream behind it (tower_side_join), everyone else here
+    if (defer_join) aux->side_pending = true;
+    else NCF_CUDA(cudaStreamWaitEvent(st, aux->ev[5], 0));
     return NCF_OK;
   }
   NCF_TRY(tower_mlp_backward(cfg, dense, dg, N, grad_out, w, st));
