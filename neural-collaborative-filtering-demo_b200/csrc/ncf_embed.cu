@@ -1503,18 +1503,25 @@ __global__ void route_finish_kernel(const uint32_t* __restrict__ skeys, const in
                                     unsigned long long* __restrict__ counts, int64_t* __restrict__ local_ids,
                                     int64_t* __restrict__ pos) {
   const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= 2 * N) return;
-  const int side = p >= N;
-  const int32_t s = incl[p] - 1 - (side ? __ldg(incl + N - 1) : 0);
-  slot[p] = s;
-  pos[(int64_t)side * N + perm[p]] = s;
-  const bool head = p == 0 || p == N || skeys[p] != skeys[p - 1];
-  if (head) {
-    const int64_t id = (int64_t)skeys[p] - (side ? item_off : 0u);
-    const int64_t block = side ? block_i : block_u;
-    local_ids[(int64_t)side * N + s] = id % block;
-    atomicAdd(counts + side * world + (int)(id / block), 1ull);
+  const bool valid = p < 2 * N;
+  int owner = -1;                   // counter index of a run head (side * world + owner rank), -1 for everyone else
+  if (valid) {
+    const int side = p >= N;
+    const int32_t s = incl[p] - 1 - (side ? __ldg(incl + N - 1) : 0);
+    slot[p] = s;
+    pos[(int64_t)side * N + perm[p]] = s;
+    const bool head = p == 0 || p == N || skeys[p] != skeys[p - 1];
+    if (head) {
+      const int64_t id = (int64_t)skeys[p] - (side ? item_off : 0u);
+      const int64_t block = side ? block_i : block_u;
+      local_ids[(int64_t)side * N + s] = id % block;
+      owner = side * world + (int)(id / block);
+    }
   }
+  // Sorted keys are owner-major: the heads of a warp name one or two owners.  One atomic per owner and warp instead of one
+  // per distinct id - 100M x 10M ids are almost all distinct, and 655k atomics on 2 * world words took 236 us (12 us now).
+  const unsigned peers = __match_any_sync(0xffffffffu, owner);
+  if (owner >= 0 && (int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(counts + owner, (unsigned long long)__popc(peers));
 }
 
 int64_t shard_route_ws_bytes(int64_t N) { return carve_route_ws(nullptr, std::max<int64_t>(N, 1)).total; }
