@@ -130,8 +130,11 @@ NCF_API int64_t ncf_launch_count(void);   /* kernels this library has launched s
  * touch nothing the rest of the step reads or writes) onto it, ordered with events against the stream argument;
  * the fork is joined again before ncf_train_step's embedding backward, which then runs its item side on the
  * auxiliary stream next to the user side (so does a direct ncf_emb_bwd_adam_both call); everything is joined
- * back into the stream argument before the call's last kernel.  The caller keeps the stream alive while it is
- * set.  NULL (default) switches all of that off. */
+ * back into the stream argument before the call's last kernel.  With the auxiliary stream set, ncf_backward /
+ * ncf_train_step / ncf_shard_backward* (NCF_BF16_TC, S = 5, >= 128 rows per SM) also run the MLP weight-gradient
+ * kernel on a second, library-owned stream (created with the first use, per device) over 28 SMs next to the
+ * attention backward, which leaves those SMs free; joined like the rest (NCF_WGRAD_SMS=0 in the environment: off).
+ * The caller keeps the stream alive while it is set.  NULL (default) switches all of that off. */
 NCF_API int ncf_set_aux_stream(void* stream);
 /* SMs the persistent tower kernels (attention / MLP forward and backward: CTAs that own an SM's registers and shared
  * memory) leave free, process-wide, 0 by default.  The sharded step sets 1: its small collectives (a communication
