@@ -106,7 +106,7 @@ extern "C" int ncf_forward(const ncf_run_cfg* cfg, const ncf_tables* T, const fl
 static int backward_impl(const ncf_run_cfg* cfg, const ncf_adam_cfg* adam, const ncf_tables* T, const float* dense,
                          float* dense_grad, const int64_t* user_ids, const int64_t* item_ids, int64_t N,
                          const float* grad_out, void* workspace, int64_t workspace_bytes, void* stream, cudaEvent_t sorted,
-                         bool preswept);
+                         bool preswept, bool head_done = false);
 
 extern "C" int ncf_backward(const ncf_run_cfg* cfg, const ncf_adam_cfg* adam, const ncf_tables* T, const float* dense,
                             float* dense_grad, const int64_t* user_ids, const int64_t* item_ids, int64_t N,
@@ -120,7 +120,7 @@ extern "C" int ncf_backward(const ncf_run_cfg* cfg, const ncf_adam_cfg* adam, co
 static int backward_impl(const ncf_run_cfg* cfg, const ncf_adam_cfg* adam, const ncf_tables* T, const float* dense,
                          float* dense_grad, const int64_t* user_ids, const int64_t* item_ids, int64_t N,
                          const float* grad_out, void* workspace, int64_t workspace_bytes, void* stream, cudaEvent_t sorted,
-                         bool preswept) {
+                         bool preswept, bool head_done) {
   NCF_TRY(check_cfg(cfg, N));
   NCF_REQUIRE(adam && T && dense && dense_grad && user_ids && item_ids && grad_out && workspace, "backward: null argument");
   NCF_REQUIRE(cfg->training, "backward: needs the workspace of a training-mode forward");
@@ -132,7 +132,7 @@ static int backward_impl(const ncf_run_cfg* cfg, const ncf_adam_cfg* adam, const
   }
   cudaStream_t st = (cudaStream_t)stream;
   static const bool defer = !(getenv("NCF_WGRAD_JOIN_LATE") && getenv("NCF_WGRAD_JOIN_LATE")[0] == '0');     // A/B switch
-  NCF_TRY(tower_f32_backward(*cfg, dense, dense_grad, N, grad_out, w, st, defer));
+  NCF_TRY(tower_f32_backward(*cfg, dense, dense_grad, N, grad_out, w, st, defer, head_done));
   struct Join {        // the embedding backward does not read the MLP weight gradients: the side stream is joined behind it
     cudaStream_t st;
     ~Join() { tower_side_join(st); }
@@ -240,13 +240,17 @@ extern "C" int ncf_train_step(const ncf_run_cfg* cfg, const ncf_adam_cfg* adam, 
     sorted = g_ev_sorted;
   }
   NCF_TRY(tower_f32_forward(*cfg, dense, N, nullptr, nullptr, out, w, st));
-  // BCELoss gradient goes into the (not yet used) backward scratch g128b
-  NCF_TRY(launch_bce(out, targets, N, loss_out, w.g128b, st, true));
+  // bf16 towers: loss, its gradient and the scalar half of the head's backward in ONE kernel (bce_head_bwd_kernel); otherwise
+  // the BCELoss gradient goes into the (not yet used) backward scratch g128b
+  static const bool fuse_head = !(getenv("NCF_FUSE_HEAD") && getenv("NCF_FUSE_HEAD")[0] == '0');     // A/B switch
+  const bool head_done = fuse_head && cfg->precision == NCF_BF16_TC;
+  if (head_done) NCF_TRY(launch_bce_head_bwd(out, targets, N, loss_out, dense, dense_grad, w, st));
+  else NCF_TRY(launch_bce(out, targets, N, loss_out, w.g128b, st, true));
   if (aux->loss_host && aux->loss_event) {        // ncf_set_loss_readback: the loss is final here
     NCF_CUDA(cudaMemcpyAsync(aux->loss_host, loss_out, sizeof(float), cudaMemcpyDeviceToHost, st));
     NCF_CUDA(cudaEventRecord(aux->loss_event, st));
   }
   NCF_TRY(backward_impl(cfg, adam, T, dense, dense_grad, user_ids, item_ids, N, w.g128b, workspace, workspace_bytes, stream, sorted,
-                        preswept));
+                        preswept, head_done));
   return ncf_dense_adam(dense, dense_grad, dense_m, dense_v, kLayout.total, adam, stream);
 }

@@ -34,7 +34,7 @@ int tower_f32_forward(const ncf_run_cfg& cfg, const float* dense, int64_t N, con
                       float* out, TowerWs& w, cudaStream_t st);
 // defer_join: the caller calls tower_side_join(st) once it has enqueued the work that does not need the MLP weight gradients
 int tower_f32_backward(const ncf_run_cfg& cfg, const float* dense, float* dense_grad, int64_t N, const float* grad_out,
-                       TowerWs& w, cudaStream_t st, bool defer_join = false);
+                       TowerWs& w, cudaStream_t st, bool defer_join = false, bool head_done = false);
 int tower_side_join(cudaStream_t st);
 // True when the attention block runs as the fused tcgen05 kernels (bf16 towers, S = 5): then its row-vector
 // interfaces w.xu, w.xp (from K1 / the sharded requester) and da = w.g64a (from the MLP backward) hold bf16
@@ -52,7 +52,7 @@ int tower_mlp_forward(const ncf_run_cfg& cfg, const float* dense, int64_t N, con
                       float* out, TowerWs& w, cudaStream_t st);
 int tower_mlp_backward(const ncf_run_cfg& cfg, const float* dense, float* dense_grad, int64_t N, const float* grad_out,
                        TowerWs& w, cudaStream_t st, cudaStream_t side = nullptr, int side_sms = 0, cudaEvent_t fork = nullptr,
-                       cudaEvent_t join = nullptr);
+                       cudaEvent_t join = nullptr, bool head_done = false);
 int tower_attn_backward(const ncf_run_cfg& cfg, const float* dense, float* dense_grad, int64_t N, TowerWs& w, cudaStream_t st);
 // tcgen05 MLP tower (ncf_tower_tc.cu): forward from w.a (fills w.mlp_pred, w.p_saved, out; w.y3 stays unused)
 int mlp_tc_forward(const ncf_run_cfg& cfg, const float* dense, int64_t N, const int64_t* hour, const float* tail1,
@@ -110,5 +110,7 @@ int tc_proj_backward(int which, const float* dY, const float* X, const float* W,
                      cudaStream_t st);
 int launch_bce(const float* out, const float* targets, int64_t N, float* loss_out, float* grad_out, cudaStream_t st,
                bool loss_zeroed = false);
+int launch_bce_head_bwd(const float* out, const float* targets, int64_t N, float* loss_out, const float* dense, float* dense_grad,
+                        TowerWs& w, cudaStream_t st);
 
 }  // namespace ncf

@@ -722,6 +722,57 @@ __global__ void __launch_bounds__(256) bce_kernel(const float* __restrict__ out,
   }
 }
 
+// bce_kernel + head_bwd_scalar_kernel in one pass (ncf_train_step, bf16 towers): the loss gradient of a row is consumed where
+// it is formed instead of travelling through memory to a second small kernel between the forward and the backward towers.
+// Same expressions in the same order as the two kernels, so d_mf / d_mlp come out bit-identical.
+__global__ void __launch_bounds__(256) bce_head_bwd_kernel(const float* __restrict__ out, const float* __restrict__ tgt, int64_t N,
+                                                           float* __restrict__ loss, const float* __restrict__ mf_pred,
+                                                           const float* __restrict__ mlp_pred, const float* __restrict__ dense,
+                                                           float* __restrict__ d_mf_pred, float* __restrict__ d_mlp_pred,
+                                                           float* __restrict__ dense_grad) {
+  __shared__ float s_sc[8][6];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float a = __ldg(dense + NCF_OFF(NCF_P_FINAL_W)), c = __ldg(dense + NCF_OFF(NCF_P_FINAL_W) + 1);
+  const float invN = 1.0f / (float)N;
+  float s[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (int64_t)gridDim.x * blockDim.x) {
+    const float p = out[n], y = tgt[n];
+    const float lp = fmaxf(logf(p), -100.f), l1p = fmaxf(logf(1.0f - p), -100.f);
+    s[5] -= y * lp + (1.0f - y) * l1p;
+    const float g = (p - y) / fmaxf(p * (1.0f - p), 1e-12f) * invN;
+    const float dz = g * p * (1.0f - p);
+    const float dmf = dz * a, dml = dz * c;
+    d_mf_pred[n] = dmf;
+    d_mlp_pred[n] = dml;
+    s[0] = fmaf(dz, mf_pred[n], s[0]);
+    s[1] = fmaf(dz, mlp_pred[n], s[1]);
+    s[2] += dz;
+    s[3] += dmf;
+    s[4] += dml;
+  }
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) s[k] += __shfl_xor_sync(0xffffffffu, s[k], off);
+    if (lane == 0) s_sc[warp][k] = s[k];
+  }
+  __syncthreads();
+  if (threadIdx.x < 6) {
+    const int k = threadIdx.x;
+    float t = 0.f;
+    for (int wv = 0; wv < 8; ++wv) t += s_sc[wv][k];
+    if (k == 5) {
+      atomicAdd(loss, t * invN);
+    } else {
+      const int64_t off = k == 0 ? NCF_OFF(NCF_P_FINAL_W) : k == 1 ? NCF_OFF(NCF_P_FINAL_W) + 1
+                          : k == 2 ? NCF_OFF(NCF_P_FINAL_B) : k == 3 ? NCF_OFF(NCF_P_MF_OUT_B) : NCF_OFF(NCF_P_MLP_OUT_B);
+      atomicAdd(dense_grad + off, t);
+    }
+  }
+}
+
 // =============================================================================================
 // orchestration
 // =============================================================================================
@@ -868,14 +919,14 @@ int tower_side_join(cudaStream_t st) {
 }
 
 int tower_f32_backward(const ncf_run_cfg& cfg, const float* dense, float* dg, int64_t N, const float* grad_out,
-                       TowerWs& w, cudaStream_t st, bool defer_join) {
+                       TowerWs& w, cudaStream_t st, bool defer_join, bool head_done) {
   // bf16 towers with an auxiliary stream set: the MLP weight-gradient kernel (HBM-bound) runs on a few SMs NEXT TO the
   // attention backward (issue-bound, 1.3 TB/s of DRAM traffic), which leaves them those SMs
   AuxCtx* aux = aux_ctx();
   const int side_sms = wgrad_side_sms();
   if (side_sms > 0 && side_sms < tower_sms() && aux->stream && tower_bf16_rows(cfg) && N >= (int64_t)128 * num_sms()) {
     NCF_TRY(aux_events(aux));
-    NCF_TRY(tower_mlp_backward(cfg, dense, dg, N, grad_out, w, st, aux->side, side_sms, aux->ev[4], aux->ev[5]));
+    NCF_TRY(tower_mlp_backward(cfg, dense, dg, N, grad_out, w, st, aux->side, side_sms, aux->ev[4], aux->ev[5], head_done));
     NCF_TRY(attn_tc_backward(cfg, dense, dg, N, w, st, side_sms));
     w.dxu = w.g64b;
     w.dxp = w.g256;
@@ -885,19 +936,22 @@ int tower_f32_backward(const ncf_run_cfg& cfg, const float* dense, float* dg, in
     else NCF_CUDA(cudaStreamWaitEvent(st, aux->ev[5], 0));
     return NCF_OK;
   }
-  NCF_TRY(tower_mlp_backward(cfg, dense, dg, N, grad_out, w, st));
+  NCF_TRY(tower_mlp_backward(cfg, dense, dg, N, grad_out, w, st, nullptr, 0, nullptr, nullptr, head_done));
   return tower_attn_backward(cfg, dense, dg, N, w, st);
 }
 
 // head + MLP tower: grad_out -> w.d_mf, da (w.g64a) + their parameter gradients
 int tower_mlp_backward(const ncf_run_cfg& cfg, const float* dense, float* dg, int64_t N, const float* grad_out,
-                       TowerWs& w, cudaStream_t st, cudaStream_t side, int side_sms, cudaEvent_t fork, cudaEvent_t join) {
+                       TowerWs& w, cudaStream_t st, cudaStream_t side, int side_sms, cudaEvent_t fork, cudaEvent_t join,
+                       bool head_done) {
   const float* P = dense;
   if (!cfg.training) { set_error("backward needs a training-mode forward"); return NCF_ERR_ARG; }
   const int hgrid = (int)std::min<int64_t>((N * 16 + 255) / 256, (int64_t)num_sms() * 8);
   // head: d_mf, dh3 (-> g64a)
   const bool tcm = cfg.precision == NCF_BF16_TC;
-  if (tcm) {
+  if (tcm && head_done) {
+    // launch_bce_head_bwd has produced w.d_mf, w.d_mlp and the head's parameter gradients already
+  } else if (tcm) {
     const int sgrid = (int)std::min<int64_t>((N + 255) / 256, (int64_t)num_sms() * 4);
     NCF_CUDA(launch_pdl(PDL_HEAD, head_bwd_scalar_kernel, dim3(sgrid), dim3(256), 0, st, grad_out, (const float*)w.p_saved, (const float*)w.mf_pred,
                         (const float*)w.mlp_pred, P, w.d_mf, w.d_mlp, dg, N));
@@ -970,6 +1024,19 @@ int launch_bce(const float* out, const float* targets, int64_t N, float* loss_ou
   if (N == 0) return NCF_OK;
   const int grid = (int)std::min<int64_t>((N + 255) / 256, (int64_t)num_sms() * 4);
   NCF_CUDA(launch_pdl(PDL_HEAD, bce_kernel, dim3(grid), dim3(256), 0, st, out, targets, N, loss_out, grad_out));
+  NCF_LAUNCH_CHECK();
+  return NCF_OK;
+}
+
+
+// BCELoss + its gradient + the scalar half of the head's backward in one kernel (see bce_head_bwd_kernel); *loss_out is zeroed
+// by the caller on the stream
+int launch_bce_head_bwd(const float* out, const float* targets, int64_t N, float* loss_out, const float* dense, float* dense_grad,
+                        TowerWs& w, cudaStream_t st) {
+  if (N == 0) return NCF_OK;
+  const int grid = (int)std::min<int64_t>((N + 255) / 256, (int64_t)num_sms() * 4);
+  NCF_CUDA(launch_pdl(PDL_HEAD, bce_head_bwd_kernel, dim3(grid), dim3(256), 0, st, out, targets, N, loss_out, (const float*)w.mf_pred,
+                      (const float*)w.mlp_pred, dense, w.d_mf, w.d_mlp, dense_grad));
   NCF_LAUNCH_CHECK();
   return NCF_OK;
 }
