@@ -38,7 +38,7 @@ AuxCtx* aux_ctx() {
   return &g_aux[dev];
 }
 int aux_events(AuxCtx* a) {
-  for (int i = 0; i < 6; ++i)
+  for (int i = 0; i < 8; ++i)
     if (!a->ev[i]) NCF_CUDA(cudaEventCreateWithFlags(&a->ev[i], cudaEventDisableTiming));
   if (!a->side) NCF_CUDA(cudaStreamCreateWithFlags(&a->side, cudaStreamNonBlocking));
   return NCF_OK;

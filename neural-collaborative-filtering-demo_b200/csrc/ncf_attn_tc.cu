@@ -641,7 +641,7 @@ int attn_tc_forward(const ncf_run_cfg& cfg, const float* dense, int64_t N, Tower
 
 // da = w.g64a -> dxu = w.g64b, dxp = w.g256 ([N,64]); accumulates the six attention parameter gradients
 int attn_tc_backward(const ncf_run_cfg& cfg, const float* dense, float* dense_grad, int64_t N, TowerWs& w, cudaStream_t st,
-                     int leave_sms) {
+                     int leave_sms, cudaStream_t reduce_st, cudaEvent_t done) {
   if (N == 0) return NCF_OK;
   static bool configured = false;
   if (!configured) {
@@ -661,7 +661,13 @@ int attn_tc_backward(const ncf_run_cfg& cfg, const float* dense, float* dense_gr
   const int grid = even_grid((N + AT_RT - 1) / AT_RT, std::max(1, tower_sms() - leave_sms));
   NCF_CUDA(launch_pdl(PDL_ATTN_BWD, attn_tc_bwd_kernel, dim3(grid), dim3(AT_THREADS), AB_TOTAL, st, A));
   NCF_LAUNCH_CHECK();
-  NCF_CUDA(launch_pdl(PDL_ATTN_BWD, attn_wgrad_reduce_kernel, dim3((AB_ACC + 255) / 256), dim3(256), 0, st, (const float*)w.at_partial, grid, dense_grad));
+  cudaStream_t rst = st;
+  if (reduce_st && done) {      // nothing before the dense Adam reads these gradients: off the stream the embedding backward waits on
+    NCF_CUDA(cudaEventRecord(done, st));
+    NCF_CUDA(cudaStreamWaitEvent(reduce_st, done, 0));
+    rst = reduce_st;
+  }
+  NCF_CUDA(launch_pdl(PDL_ATTN_BWD, attn_wgrad_reduce_kernel, dim3((AB_ACC + 255) / 256), dim3(256), 0, rst, (const float*)w.at_partial, grid, dense_grad));
   NCF_LAUNCH_CHECK();
   return NCF_OK;
 }

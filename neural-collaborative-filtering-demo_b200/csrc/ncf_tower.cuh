@@ -71,8 +71,9 @@ int tc_proj_wgrad(int which, const float* Z, const float* X, float* dW, float* d
 // fused attention block on tcgen05 for S = 5 (ncf_attn_tc.cu): forward xu, xp -> a_img; backward da (w.g64a) ->
 // dxu (w.g64b), dxp (w.g256) + the attention parameter gradients, recomputing q, k, v and the probabilities
 int attn_tc_forward(const ncf_run_cfg& cfg, const float* dense, int64_t N, TowerWs& w, cudaStream_t st);
+// reduce_st != null: the reduction of the per-CTA weight-gradient partials runs there, behind `done` recorded on st
 int attn_tc_backward(const ncf_run_cfg& cfg, const float* dense, float* dense_grad, int64_t N, TowerWs& w, cudaStream_t st,
-                     int leave_sms = 0);
+                     int leave_sms = 0, cudaStream_t reduce_st = nullptr, cudaEvent_t done = nullptr);
 int64_t attn_tc_partial_floats();
 // fused embedding backward of both sides with a single radix sort (ncf_embed.cu)
 int emb_bwd_both(const ncf_adam_cfg* adam, const ncf_tables* T, const float* dense, float* dense_grad,
@@ -86,7 +87,7 @@ struct AuxCtx {
   cudaStream_t stream = nullptr;
   float* loss_host = nullptr;          // ncf_set_loss_readback
   cudaEvent_t loss_event = nullptr;
-  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};     // 0 fork, 1 sorted (ncf_train_step); 2 fork, 3 join (emb_bwd_both); 4 fork, 5 join (side stream)
+  cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};     // 0 fork, 1 sorted (ncf_train_step); 2 fork, 3 join (emb_bwd_both); 4 fork, 5 join, 6 attention backward done (side stream)
   bool side_pending = false;           // the side stream's weight-gradient kernels have not been joined into the caller's stream yet
   cudaStream_t side = nullptr;         // library-owned second stream (created with the first use): MLP weight gradients next to the attention backward
 };

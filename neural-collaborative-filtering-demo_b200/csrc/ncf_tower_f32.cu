@@ -926,8 +926,9 @@ int tower_f32_backward(const ncf_run_cfg& cfg, const float* dense, float* dg, in
   const int side_sms = wgrad_side_sms();
   if (side_sms > 0 && side_sms < tower_sms() && aux->stream && tower_bf16_rows(cfg) && N >= (int64_t)128 * num_sms()) {
     NCF_TRY(aux_events(aux));
-    NCF_TRY(tower_mlp_backward(cfg, dense, dg, N, grad_out, w, st, aux->side, side_sms, aux->ev[4], aux->ev[5], head_done));
-    NCF_TRY(attn_tc_backward(cfg, dense, dg, N, w, st, side_sms));
+    NCF_TRY(tower_mlp_backward(cfg, dense, dg, N, grad_out, w, st, aux->side, side_sms, aux->ev[4], nullptr, head_done));
+    NCF_TRY(attn_tc_backward(cfg, dense, dg, N, w, st, side_sms, aux->side, aux->ev[6]));     // its partial-sum reduction: side stream too
+    NCF_CUDA(cudaEventRecord(aux->ev[5], aux->side));
     w.dxu = w.g64b;
     w.dxp = w.g256;
     // nothing up to the dense Adam reads the MLP weight gradients: a caller that has more work for `st` (the embedding

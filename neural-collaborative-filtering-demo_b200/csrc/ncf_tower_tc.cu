@@ -1982,7 +1982,7 @@ int mlp_tc_backward(const ncf_run_cfg& cfg, const float* dense, float* dense_gra
   W.N = N;
   cudaStream_t wst = st;
   int wgrid = grid;
-  if (side && side_sms > 0 && fork && join) {
+  if (side && side_sms > 0 && fork) {
     NCF_CUDA(cudaEventRecord(fork, st));
     NCF_CUDA(cudaStreamWaitEvent(side, fork, 0));
     wst = side;
@@ -1992,7 +1992,7 @@ int mlp_tc_backward(const ncf_run_cfg& cfg, const float* dense, float* dense_gra
   NCF_LAUNCH_CHECK();
   NCF_CUDA(launch_pdl(PDL_MLP_WGRAD, mlp_wgrad_reduce_kernel, dim3((WG_PART + 255) / 256), dim3(256), 0, wst, (const float*)w.wg_partial, wgrid, dense_grad));
   NCF_LAUNCH_CHECK();
-  if (wst != st) NCF_CUDA(cudaEventRecord(join, wst));
+  if (wst != st && join) NCF_CUDA(cudaEventRecord(join, wst));
   return NCF_OK;
 }
 
